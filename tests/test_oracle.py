@@ -113,6 +113,8 @@ def test_live_fuzz_against_compiled_reference(ednafull):
         read = "".join(c if rng.random() > 0.08 else rng.choice("ACGTN") for c in ref)
         cut = rng.randrange(I)
         read = read[:cut] + read[cut + rng.randrange(0, 6):] if rng.random() < 0.5 else read[:cut] + "ACG" + read[cut:]
+        if len(read) < 3:
+            continue
         gi = Z(I + 1)
         gi[rng.randrange(I + 1)] = 1
         go, ge = rng.choice([(-20, -2), (-1, -1), (-7, -3)])
