@@ -1,0 +1,253 @@
+"""Host-side mirror of the reference's per-read driver for the GPU path.
+
+Same call signatures as the reference functions they stand in for:
+  process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory)
+      -> (aln_stats, not_aligned_variants)                        CRISPRessoCORE.py:1735-2000
+  get_new_variant_object(args, fastq_seq, refs, ref_names, aln_matrix, pe_scaffold_dna_info)
+      -> variant dict                                             CRISPRessoCORE.py:627-798
+and, for the count arrays the quantification loop builds from variantCache (CRISPRessoCORE.py:3964-4115),
+  quantify(variantCache) -> CountBlock        (the device block accumulated by the process_fastq call)
+
+Everything decided per read (strand, alignment, best reference, classification, counts) is decided by the CUDA
+kernel; this module parses the FASTQ, de-duplicates reads exactly like the reference (:1825-1849), derives the
+reverse-complement merge weights of :3971-3975, launches one batch and re-labels the outputs as the reference's
+dict / ResultsSlotsDict shapes.  process_fastq bypasses CRISPRessoMultiProcessing (n_processes is ignored) and
+follows the SERIAL branch's statistics (:1956-1981).
+"""
+import gzip
+import os
+
+import numpy as np
+
+from . import _lib
+from .align import read_matrix
+from .engine import Engine, EngineError
+from .resources import payload_from_device
+
+_COMP = str.maketrans("ACGTN_-", "TGCAN_-")
+_engines = {}
+_blocks = {}
+
+
+def reverse_complement(seq):
+    """CRISPRessoShared.py:399-403 (KeyError on symbols outside ACGTN_- like the reference)."""
+    up = seq.upper()
+    bad = set(up) - set("ACGTN_-")
+    if bad:
+        raise KeyError(sorted(bad)[0])
+    return up.translate(_COMP)[::-1]
+
+
+def _flags(args):
+    f = 0
+    if getattr(args, "ignore_substitutions", False):
+        f |= _lib.F_IGNORE_SUBSTITUTIONS
+    if getattr(args, "ignore_insertions", False):
+        f |= _lib.F_IGNORE_INSERTIONS
+    if getattr(args, "ignore_deletions", False):
+        f |= _lib.F_IGNORE_DELETIONS
+    if getattr(args, "expand_ambiguous_alignments", False):
+        f |= _lib.F_EXPAND_AMBIGUOUS
+    if getattr(args, "assign_ambiguous_alignments_to_first_reference", False):
+        f |= _lib.F_ASSIGN_FIRST
+    if getattr(args, "discard_indel_reads", False):
+        f |= _lib.F_DISCARD_INDEL_READS
+    return f
+
+
+def _unsupported(args):
+    if getattr(args, "use_legacy_insertion_quantification", False):
+        raise NotImplementedError("use_legacy_insertion_quantification is not built on the GPU path")
+    if getattr(args, "prime_editing_pegRNA_scaffold_seq", ""):
+        raise NotImplementedError("prime-editing scaffold search (CRISPRessoCORE.py:789-796) is not built on the GPU path")
+
+
+def get_engine(device=0, lib_path=None):
+    key = (device, lib_path)
+    if key not in _engines:
+        _engines[key] = Engine(device, lib_path)
+    return _engines[key]
+
+
+def configure_engine(engine, args, refs, ref_names, aln_matrix, edit_cap=24):
+    engine.configure(refs, ref_names, aln_matrix, args.needleman_wunsch_gap_open, args.needleman_wunsch_gap_extend,
+                     args.aln_seed_count, args.aln_seed_min, _flags(args), "ACGTN", edit_cap)
+    return engine
+
+
+def merge_weights(uniques, counts):
+    """Weights the quantification loop ends up using after its reverse-complement merge (CRISPRessoCORE.py:3971-3975):
+    walking the cache in first-seen order, a read absorbs the count of its reverse complement (which drops to 0);
+    a palindromic read absorbs itself.  Valid because a read and its reverse complement always share their aligned
+    status (same score set), so both are in the cache or neither is."""
+    pos = {s: k for k, s in enumerate(uniques)}
+    w = list(counts)
+    for k, s in enumerate(uniques):
+        if w[k] == 0:
+            continue
+        try:
+            rc = reverse_complement(s)
+        except KeyError:
+            continue
+        j = pos.get(rc)
+        if j is not None and w[j] > 0:
+            tot = w[k] + w[j]
+            w[j] = 0
+            w[k] = tot
+    return w
+
+
+def _variant_from(res, i, seq, ref_names, refs):
+    """dict of get_new_variant_object (CRISPRessoCORE.py:709-798) for read i of a batch result."""
+    rec = res.recs[i]
+    nref = len(ref_names)
+    scores = [res.score(i, r) for r in range(nref)]
+    details = []
+    for r in range(nref):
+        s1, s2 = res.pair(i, r)
+        details.append((ref_names[r], s1, s2, scores[r]))
+    v = {"count": 1, "aln_scores": scores, "ref_aln_details": details}
+    if rec["best_score_milli"] <= 0:
+        v["best_match_score"] = -1
+        return v
+    winners = [r for r in range(nref) if (int(rec["winner_mask"]) >> r) & 1]
+    v["aln_ref_names"] = [ref_names[r] for r in winners]
+    v["best_match_score"] = int(rec["best_score_milli"]) / 1000.0
+    labels = []
+    for r in winners:
+        a = res.alns[i, r]
+        name = ref_names[r]
+        s1, s2 = details[r][1], details[r][2]
+        p = payload_from_device(a, res.edits[i, r], s1, s2)
+        p["ref_name"] = name
+        p["aln_scores"] = scores
+        p["irregular_ends"] = bool(a["irregular_ends"])
+        n_ins_all, n_ins_win = int(a["n_ins_all"]), int(a["n_ins_win"])
+        p["insertions_outside_window"] = n_ins_all - n_ins_win
+        p["deletions_outside_window"] = int(a["n_del_all"]) - int(a["n_del_win"])
+        p["substitutions_outside_window"] = int(a["n_sub_all"]) - int(a["substitution_n"])
+        p["total_mods"] = n_ins_all + int(a["n_del_pos_all"]) + int(a["n_sub_all"])
+        p["mods_in_window"] = int(a["substitution_n"]) + int(a["deletion_n"]) + int(a["insertion_n"])
+        p["mods_outside_window"] = p["total_mods"] - p["mods_in_window"]
+        p["classification"] = "MODIFIED" if a["modified"] else "UNMODIFIED"
+        labels.append(name + "_" + p["classification"])
+        p["aln_seq"], p["aln_ref"] = s1, s2
+        p["aln_strand"] = "-" if a["strand"] else "+"
+        v["variant_" + name] = p
+        v["best_match_name"] = name
+    v["class_name"] = "&".join(labels)
+    if len(winners) > 1:
+        if rec["ambiguous"]:
+            v["class_name"] = "AMBIGUOUS"
+        elif len(labels) > 1 and not (res_flags(res) & _lib.F_EXPAND_AMBIGUOUS):
+            v["class_name"] = labels[0]
+            v["aln_ref_names"] = [ref_names[winners[0]]]
+    return v
+
+
+def res_flags(res):
+    return getattr(res, "flags", 0)
+
+
+def align_uniques(engine, uniques, counts, ref_names, refs, flags, weights=None):
+    """One GPU batch over unique reads -> (variants list, BatchResult).  Reads whose edit list overflowed the
+    per-read cap are re-run with a cap that cannot overflow (their counts are only added in the re-run)."""
+    weights = merge_weights(uniques, counts) if weights is None else weights
+    res = engine.align(uniques, count=np.asarray(counts, dtype=np.int32), qweight=np.asarray(weights, dtype=np.int32))
+    res.flags = flags
+    st = res.recs["status"]
+    hard = st & ~np.uint32(_lib.ST_EDIT_OVERFLOW)
+    if hard.any():
+        k = int(np.nonzero(hard)[0][0])
+        raise EngineError("read %d (%r...) outside the engine's contract: status %d" % (k, uniques[k][:30], int(st[k])))
+    return res, weights
+
+
+def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory,
+                  engine=None, aln_matrix=None):
+    _unsupported(args)
+    if aln_matrix is None:
+        loc = args.needleman_wunsch_aln_matrix_loc
+        if not os.path.isabs(loc) and not os.path.exists(loc):
+            raise FileNotFoundError("needleman_wunsch_aln_matrix_loc %r not found (pass an absolute path)" % loc)
+        aln_matrix = read_matrix(loc)
+    opener = (lambda p: gzip.open(p, "rt")) if fastq_filename.endswith(".gz") else open
+    with opener(fastq_filename) as fh:                      # CRISPRessoCORE.py:1820-1849
+        while True:
+            head = fh.readline()
+            if not head:
+                break
+            seq = fh.readline().strip()
+            fh.readline()
+            fh.readline()
+            variantCache[seq] = variantCache.get(seq, 0) + 1
+    engine = engine or get_engine()
+    configure_engine(engine, args, refs, ref_names, aln_matrix)
+    engine.counts_reset()
+    uniques = list(variantCache.keys())
+    counts = [variantCache[s] for s in uniques]
+    flags = _flags(args)
+    res, weights = align_uniques(engine, uniques, counts, ref_names, refs, flags)
+    over = np.nonzero(res.recs["status"] & _lib.ST_EDIT_OVERFLOW)[0]
+    fix = {}
+    if len(over):
+        # the kernel leaves overflowed reads out of the count block; re-run them with a cap that cannot overflow
+        cap0 = engine.edit_cap
+        engine.set_edit_cap(max(engine.ref_lens) + _lib.MAX_READ_LEN)
+        sub = [uniques[k] for k in over]
+        r2 = engine.align(sub, count=np.asarray([counts[k] for k in over], dtype=np.int32),
+                          qweight=np.asarray([weights[k] for k in over], dtype=np.int32))
+        r2.flags = flags
+        engine.set_edit_cap(cap0)
+        fix = {int(k): (r2, j) for j, k in enumerate(over)}
+
+    st = dict.fromkeys(["N_TOT_READS", "N_CACHED_ALN", "N_CACHED_NOTALN", "N_COMPUTED_ALN", "N_COMPUTED_NOTALN",
+                        "N_GLOBAL_SUBS", "N_SUBS_OUTSIDE_WINDOW", "N_MODS_IN_WINDOW", "N_MODS_OUTSIDE_WINDOW",
+                        "N_READS_IRREGULAR_ENDS", "READ_LENGTH"], 0)
+    not_aligned = {}
+    for k, seq in enumerate(uniques):                       # CRISPRessoCORE.py:1956-1981
+        c = counts[k]
+        st["N_TOT_READS"] += c
+        rr, kk = fix.get(k, (res, k))
+        v = _variant_from(rr, kk, seq, ref_names, refs)
+        v["count"] = c
+        if v["best_match_score"] <= 0:
+            st["N_COMPUTED_NOTALN"] += 1
+            st["N_CACHED_NOTALN"] += c - 1
+            not_aligned[seq] = v
+            continue
+        variantCache[seq] = v
+        st["N_COMPUTED_ALN"] += 1
+        st["N_CACHED_ALN"] += c - 1
+        p = v["variant_" + v["best_match_name"]]
+        if st["READ_LENGTH"] == 0:
+            st["READ_LENGTH"] = len(p["aln_seq"])
+        st["N_GLOBAL_SUBS"] += (p["substitution_n"] + p["substitutions_outside_window"]) * c
+        st["N_SUBS_OUTSIDE_WINDOW"] += p["substitutions_outside_window"] * c
+        st["N_MODS_IN_WINDOW"] += p["mods_in_window"] * c
+        st["N_MODS_OUTSIDE_WINDOW"] += p["mods_outside_window"] * c
+        if p["irregular_ends"]:
+            st["N_READS_IRREGULAR_ENDS"] += c
+    for seq in not_aligned:
+        del variantCache[seq]
+    block = engine.counts()
+    dev = block.aln_stats_partial()                         # the kernel's own sums must agree with the records
+    for key, val in dev.items():
+        if val != st[key]:
+            raise EngineError("device aln_stats disagree with per-read records for %s: %d != %d" % (key, val, st[key]))
+    _blocks[id(variantCache)] = block
+    return st, not_aligned
+
+
+def quantify(variantCache):
+    """Count block accumulated on the device by the process_fastq call that filled this variantCache."""
+    return _blocks[id(variantCache)]
+
+
+def get_new_variant_object(args, fastq_seq, refs, ref_names, aln_matrix, pe_scaffold_dna_info=None, engine=None):
+    _unsupported(args)
+    engine = engine or get_engine()
+    configure_engine(engine, args, refs, ref_names, aln_matrix, edit_cap=max(len(refs[r]["sequence"]) for r in ref_names)
+                     + len(fastq_seq) + 1)
+    res, _ = align_uniques(engine, [fastq_seq], [1], ref_names, refs, _flags(args), weights=[0])
+    return _variant_from(res, 0, fastq_seq, ref_names, refs)

@@ -1,0 +1,58 @@
+"""View of the engine's int64 count block as the named per-position vectors / counters that the reference's
+quantification loop builds (CRISPRessoCORE.py:3841-3907, :3964-4115).  Pure re-labelling plus the one
+closed-form step the device leaves to the host: all_base_count = deviation + (ref base ? counts_total : 0).
+"""
+import numpy as np
+
+from . import _lib
+
+
+class CountBlock:
+    def __init__(self, raw, ref_names, ref_seqs, alphabet, n_vec, stride, n_scal):
+        self.raw = raw
+        self.ref_names, self.ref_seqs, self.alphabet = list(ref_names), list(ref_seqs), alphabet
+        self.n_vec, self.stride, self.n_scal = n_vec, stride, n_scal
+        per = n_vec * stride + n_scal
+        self._vec, self._scal = {}, {}
+        for k, name in enumerate(ref_names):
+            blk = raw[k * per:(k + 1) * per]
+            self._vec[name] = blk[:n_vec * stride].reshape(n_vec, stride)
+            self._scal[name] = blk[n_vec * stride:]
+
+    def scalar(self, ref, name):
+        return int(self._scal[ref][_lib.S[name]])
+
+    def scalars(self, ref):
+        """counters of CRISPRessoCORE.py:3844-3863 under the reference's names"""
+        g = lambda n: self.scalar(ref, n)
+        return {"counts_total": g("TOTAL"), "counts_modified": g("MODIFIED"), "counts_unmodified": g("UNMODIFIED"),
+                "counts_discarded": g("DISCARDED"), "counts_insertion": g("INS"), "counts_deletion": g("DEL"),
+                "counts_substitution": g("SUB"), "counts_only_insertion": g("ONLY_INS"),
+                "counts_only_deletion": g("ONLY_DEL"), "counts_only_substitution": g("ONLY_SUB"),
+                "counts_insertion_and_deletion": g("INS_DEL"), "counts_insertion_and_substitution": g("INS_SUB"),
+                "counts_deletion_and_substitution": g("DEL_SUB"),
+                "counts_insertion_and_deletion_and_substitution": g("INS_DEL_SUB")}
+
+    def vectors(self, ref):
+        """float64 vectors under the names of oracle.VECTOR_NAMES (the reference keeps float64 too, :3865)"""
+        k = self.ref_names.index(ref)
+        L = len(self.ref_seqs[k])
+        V = self._vec[ref]
+        f = lambda row: V[row, :L].astype(np.float64)
+        out = {"all_insertion_count": f(_lib.V_ALL_INS), "all_insertion_left_count": f(_lib.V_ALL_INS_LEFT),
+               "all_deletion_count": f(_lib.V_ALL_DEL), "all_substitution_count": f(_lib.V_ALL_SUB),
+               "insertion_count": f(_lib.V_INS), "deletion_count": f(_lib.V_DEL), "substitution_count": f(_lib.V_SUB),
+               "insertion_length": f(_lib.V_INS_LEN), "deletion_length": f(_lib.V_DEL_LEN)}
+        total = self.scalar(ref, "TOTAL")
+        seq = np.frombuffer(self.ref_seqs[k].encode(), dtype=np.uint8)
+        for q, ch in enumerate(self.alphabet):
+            out["all_substitution_base_" + ch] = f(_lib.V_SUBBASE0 + q)
+            out["all_base_count_" + ch] = f(_lib.V_BASEDEV0 + q) + np.where(seq == ord(ch), float(total), 0.0)
+        out["all_base_count_-"] = f(_lib.V_BASEDEV0 + len(self.alphabet))
+        return out
+
+    def aln_stats_partial(self):
+        """The aln_stats sums the device accumulates (CRISPRessoCORE.py:1974-1979), summed over references."""
+        keys = ["N_GLOBAL_SUBS", "N_SUBS_OUTSIDE_WINDOW", "N_MODS_IN_WINDOW", "N_MODS_OUTSIDE_WINDOW",
+                "N_READS_IRREGULAR_ENDS"]
+        return {k: sum(self.scalar(r, k) for r in self.ref_names) for k in keys}

@@ -1,0 +1,641 @@
+// c2b_core.cuh -- warp-level align + traceback + classification for CRISPResso2's per-read hot path.
+//
+// One warp owns one read.  For every (read, reference, strand) it runs
+//   1. dp_block<KSTAR>  : the three-state affine Needleman-Wunsch of CRISPResso2Align.global_align
+//                         (reference: CRISPResso2/CRISPResso2Align.pyx:142-317) as an anti-diagonal
+//                         wavefront -- lane l owns reference rows 8l+1..8l+8 and steps over read columns,
+//                         lane edges travel by warp shuffle, 4 traceback bits per cell go to an
+//                         L2-resident scratch slab (one coalesced 128-byte row per step);
+//   2. walk             : the traceback of Align.pyx:338-421, warp-uniform, reading the slab through a
+//                         32-column shuffle window, producing a 2-bit op stream held in registers;
+//   3. columns          : lane-parallel emission of the aligned strings (right-aligned, 16-byte vector
+//                         stores), match count, and a per-reference-position scatter into shared memory;
+//   4. rows             : find_indels_substitutions (CRISPRessoCOREResources.pyx:68-187) + the per-read
+//                         part of the quantification loop (CRISPRessoCORE.py:3964-4115) evaluated in
+//                         reference-position space with ballots, emitting scalars, the edit list and the
+//                         per-position count vectors (integer atomics).
+//
+// Exactness device: every DP value is stored as 4*score + tag with tag(M)=0 < tag(J)=1 < tag(I)=2, so that a
+// plain integer max reproduces the reference's strict-'>' cascades (ties: I beats J beats M,
+// Align.pyx:195-229) and the winner's identity is the low two bits of the max.
+//
+// The same header is compiled by nvcc for sm_100a (c2b_engine.cu) and by g++ against a fiber-based warp
+// emulator (tests/emu/) -- the emulator exists only so the kernel logic can be checked on a CPU-only box.
+#pragma once
+#include <stdint.h>
+#include "c2b200.h"
+
+#ifndef C2B_EMU
+#include <cuda_runtime.h>
+#define C2B_DEV __device__ __forceinline__
+#define C2B_DEVNOINL __device__ __noinline__
+namespace wp {
+C2B_DEV int lane() { return threadIdx.x & 31; }
+C2B_DEV int shfl_up(int v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+C2B_DEV int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+C2B_DEV uint32_t shflu(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+C2B_DEV int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+C2B_DEV uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+C2B_DEV void sync() { __syncwarp(); }
+C2B_DEV int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
+C2B_DEV int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }   // max(a+b, c)
+C2B_DEV int popc(uint32_t x) { return __popc(x); }
+C2B_DEV int popcll(uint64_t x) { return __popcll(x); }
+C2B_DEV int clz(uint32_t x) { return __clz(x); }
+C2B_DEV int ffs(uint32_t x) { return __ffs(x); }
+C2B_DEV uint32_t ldcg(const uint32_t *p) { return __ldcg(p); }
+C2B_DEV int ldcgi(const int *p) { return __ldcg(p); }
+C2B_DEV uint64_t ldcg64(const uint64_t *p) { return __ldcg((const unsigned long long *)p); }
+C2B_DEV int4 ldg4(const int4 *p) { return __ldg(p); }
+C2B_DEV void addg(unsigned long long *p, long long v) { atomicAdd(p, (unsigned long long)v); }
+C2B_DEV uint32_t adds(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+C2B_DEV unsigned long long fetch_work(unsigned long long *p) { return atomicAdd(p, 1ull); }
+}  // namespace wp
+#else
+#include "warp_emu.h"   // provides C2B_DEV, C2B_DEVNOINL, int4/uint4 and namespace wp
+#endif
+
+namespace c2b {
+
+constexpr int MAXJ = C2B_MAX_READ_LEN;
+constexpr int MAXI = C2B_MAX_REF_LEN;
+constexpr int OP_M = 0, OP_J = 1, OP_I = 2, OP_NONE = 3;   // = DP tags; J: gap in read (deletion), I: gap in ref
+
+// Per-reference device tables (built on the host by c2b_configure; "Ipad" = rows padded to 256).
+struct RefDev {
+    int32_t I, nrb, kstar, lstar, Ipad;
+    int32_t gi0_4;                 // 4*gap_incentive[0]
+    int32_t nseeds, seed_len;
+    double min_aln;
+    const int32_t *prof;           // [nq][Ipad]  4*matrix[ref[row]][alphabet[q]]
+    const int32_t *cIe;            // [Ipad]      4*(gap_extend + gi[row+1])
+    const int32_t *g4;             // [Ipad]      4*gi[row]                 (incentive of the row above, "i-1")
+    const uint8_t *asc;            // [Ipad]      reference ASCII
+    const uint8_t *rcode;          // [Ipad]      reference base as alphabet code, 255 if not in alphabet
+    const uint8_t *incl;           // [Ipad+1]    1 inside the quantification window
+    const uint16_t *cum;           // [Ipad+2]    cum[p] = #window positions < p
+    uint64_t fw_seed[C2B_MAX_SEEDS], rc_seed[C2B_MAX_SEEDS];   // 3 bits per base, first base lowest
+    unsigned long long *vec;       // [C2B_NVEC][vstride]
+    unsigned long long *scal;      // [C2B_NSCAL]
+};
+
+struct KParams {
+    const uint8_t *reads; const int64_t *offsets; int64_t n_reads;
+    const int32_t *count, *qweight, *ref_id;
+    c2b_read_rec *recs; c2b_aln_rec *alns; uint8_t *strings; c2b_edit *edits;
+    int32_t W, edit_cap;
+    const RefDev *refs; int32_t n_refs;
+    int32_t go, ge, seed_count, seed_min; uint32_t flags; int32_t nq;
+    uint8_t alpha[C2B_MAX_Q]; uint8_t comp[C2B_MAX_Q];
+    uint32_t *tb; int64_t tb_words_per_warp; int32_t TS;      // TS = steps stride per row block (maxJ + 32)
+    int32_t *bnd; int64_t bnd_words_per_warp;                 // 2 x 3 x (maxJ+1): row-block boundary rows
+    uint64_t *opsbuf;                                         // [warp][n_refs][32] op streams (multi-reference)
+    unsigned long long *work_counter;
+    int32_t vstride;
+    const uint64_t *forced_ops;       // c2b_classify_aligned: op streams supplied by the caller, [read][32]
+    const int32_t *forced_n;
+};
+
+struct WarpSmem {
+    uint8_t fw[MAXJ];          // read as alphabet codes
+    uint8_t rc[MAXJ];          // reverse complement
+    uint8_t rowinfo[MAXI];     // per reference position: read code of its column, or 8 = deleted
+    uint32_t rowins[MAXI + 4]; // rowins[r]: bases inserted between reference positions r-1 and r
+};
+
+struct Walked { uint64_t ops; int n; int err; };
+
+// ------------------------------------------------------------------------------------------------ DP
+template <int KSTAR>
+C2B_DEV void dp_block(const KParams &P, const RefDev &R, const uint8_t *codes, int J, int rb, int NEG4,
+                      uint32_t *tb, const int32_t *bnd_in, int32_t *bnd_out, int &cM, int &cX, int &cY)
+{
+    const int lane = wp::lane();
+    const bool lastblk = (rb == R.nrb - 1);
+    const int nl = lastblk ? R.lstar + 1 : 32;
+    const int rowbase = rb * 256;
+    const int r0 = rowbase + 8 * lane;
+    const bool islast = lastblk && lane == R.lstar;
+    const int ge4 = 4 * P.ge, d4 = 4 * (P.go - P.ge);
+
+    int M[8], X[8], Y[8], cIe[8], g4[8];
+    {
+        const int4 *pc = reinterpret_cast<const int4 *>(R.cIe + r0);
+        const int4 *pg = reinterpret_cast<const int4 *>(R.g4 + r0);
+        int4 a = wp::ldg4(pc), b = wp::ldg4(pc + 1), c = wp::ldg4(pg), d = wp::ldg4(pg + 1);
+        cIe[0] = a.x; cIe[1] = a.y; cIe[2] = a.z; cIe[3] = a.w; cIe[4] = b.x; cIe[5] = b.y; cIe[6] = b.z; cIe[7] = b.w;
+        g4[0] = c.x; g4[1] = c.y; g4[2] = c.z; g4[3] = c.w; g4[4] = d.x; g4[5] = d.y; g4[6] = d.z; g4[7] = d.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {          // column 0 (Align.pyx:153-176)
+        M[k] = NEG4; X[k] = NEG4 | 2; Y[k] = (ge4 * (r0 + k + 1) + R.gi0_4) | 1;
+    }
+    int pM, pX, pY;                         // row above my first row, previous column (the diagonal of k=0)
+    if (rb == 0) { pM = 0; pX = NEG4 | 2; pY = NEG4 | 1; }
+    else { pM = NEG4; pX = NEG4 | 2; pY = (ge4 * rowbase + R.gi0_4) | 1; }
+
+    const int nsteps = J + nl - 1;
+    const int32_t *prof0 = R.prof + r0;
+    uint32_t *tbw = tb + ((int64_t)rb * P.TS) * 32 + lane;
+
+    for (int t = 1; t <= nsteps; t++) {
+        int uM = wp::shfl_up(M[7], 1), uX = wp::shfl_up(X[7], 1), uY = wp::shfl_up(Y[7], 1);
+        const int j = t - lane;
+        if (lane == 0) {
+            if (rb == 0) { uM = NEG4; uX = (ge4 * j + R.gi0_4) | 2; uY = NEG4 | 1; }     // row 0
+            else if (j <= J) { uM = bnd_in[3 * j]; uX = bnd_in[3 * j + 1]; uY = bnd_in[3 * j + 2]; }
+        }
+        if (j >= 1 && j <= J && lane < nl) {
+            const int q = codes[j - 1];
+            const int4 *pp = reinterpret_cast<const int4 *>(prof0 + q * R.Ipad);
+            const int4 sa = wp::ldg4(pp), sb = wp::ldg4(pp + 1);
+            const int s[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+            const int dcol = (j == J) ? 0 : d4;             // free opening in the last column (Align.pyx:234-273)
+            const int dsp = islast ? 0 : dcol;              // ... and in the last row (:277-317)
+            int dM = pM, dX = pX, dY = pY;
+            int upM = uM, upY = uY;
+            uint32_t word = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int dik = (k == KSTAR) ? dsp : dcol;
+                const int z = wp::max3(dM, dY, dX);                  // diagonal, tie order I > J > M
+                const int tag = z & 3;
+                const int nm = (z - tag) + s[k];
+                const int x = wp::addmax(M[k], dik, X[k]) + cIe[k];  // gap in reference ("I"), incentive of row i
+                const int y = wp::addmax(upM, dik + g4[k], upY) + ge4;   // gap in read ("J"), incentive of row i-1 on open
+                const uint32_t nib = (uint32_t)tag | ((uint32_t)((x & 2) | (y & 1)) << 2);
+                word |= nib << (4 * k);
+                dM = M[k]; dX = X[k]; dY = Y[k];
+                M[k] = nm; X[k] = x | 2; Y[k] = y | 1;
+                upM = nm; upY = Y[k];
+            }
+            tbw[(int64_t)t * 32] = word;
+            if (!lastblk && lane == 31) { bnd_out[3 * j] = M[7]; bnd_out[3 * j + 1] = X[7]; bnd_out[3 * j + 2] = Y[7]; }
+        }
+        pM = uM; pX = uX; pY = uY;
+    }
+    if (lastblk) {
+        const int k = (KSTAR < 8) ? KSTAR : 0;
+        cM = wp::shfl(M[k], R.lstar); cX = wp::shfl(X[k], R.lstar); cY = wp::shfl(Y[k], R.lstar);
+    }
+}
+
+C2B_DEVNOINL void dp_dispatch(const KParams &P, const RefDev &R, const uint8_t *codes, int J, int rb, int NEG4,
+                              uint32_t *tb, const int32_t *bi, int32_t *bo, int &cM, int &cX, int &cY)
+{
+    const int ks = (rb == R.nrb - 1) ? R.kstar : 8;
+    switch (ks) {
+    case 0: dp_block<0>(P, R, codes, J, rb, NEG4, tb, bi, bo, cM, cX, cY); break;
+    case 1: dp_block<1>(P, R, codes, J, rb, NEG4, tb, bi, bo, cM, cX, cY); break;
+    case 2: dp_block<2>(P, R, codes, J, rb, NEG4, tb, bi, bo, cM, cX, cY); break;
+    case 3: dp_block<3>(P, R, codes, J, rb, NEG4, tb, bi, bo, cM, cX, cY); break;
+    case 4: dp_block<4>(P, R, codes, J, rb, NEG4, tb, bi, bo, cM, cX, cY); break;
+    case 5: dp_block<5>(P, R, codes, J, rb, NEG4, tb, bi, bo, cM, cX, cY); break;
+    case 6: dp_block<6>(P, R, codes, J, rb, NEG4, tb, bi, bo, cM, cX, cY); break;
+    case 7: dp_block<7>(P, R, codes, J, rb, NEG4, tb, bi, bo, cM, cX, cY); break;
+    default: dp_block<8>(P, R, codes, J, rb, NEG4, tb, bi, bo, cM, cX, cY); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- traceback
+// Warp-uniform walk from (I,J) to (0,0) (Align.pyx:338-421).  Lane L ends up holding ops 32L..32L+31
+// (2 bits each, op n = n-th column from the RIGHT end of the alignment).
+C2B_DEVNOINL Walked walk(const KParams &P, const RefDev &R, int J, const uint32_t *tb, int s)
+{
+    const int lane = wp::lane();
+    Walked out; out.ops = ~0ull; out.err = 0;
+    int i = R.I, j = J, n = 0;
+    uint64_t acc = 0;
+    int wrb = -1, wl = -1, wj = 0; uint32_t wreg = 0;
+    while (i > 0 || j > 0) {
+        int op;
+        if (i == 0) { op = OP_I; if (s != OP_I) out.err = 1; j--; }
+        else if (j == 0) { op = OP_J; if (s != OP_J) out.err = 1; i--; }
+        else {
+            const int r = i - 1, rb = r >> 8, l = (r >> 3) & 31, k = r & 7;
+            if (rb != wrb || l != wl || wj - j >= 32) {         // refill the 32-column window of lane-row (rb,l)
+                wrb = rb; wl = l; wj = j;
+                const int cj = j - lane;
+                wreg = (cj >= 1) ? wp::ldcg(tb + ((int64_t)rb * P.TS + cj + l) * 32 + l) : 0u;
+            }
+            const uint32_t w = wp::shflu(wreg, wj - j);
+            const uint32_t nib = (w >> (4 * k)) & 15u;
+            op = s;
+            if (s == OP_M) { s = nib & 3; if (s == 3) { out.err = 1; s = OP_M; } }
+            else if (s == OP_J) s = (nib >> 2) & 1 ? OP_J : OP_M;
+            else s = (nib >> 3) & 1 ? OP_I : OP_M;
+            i -= (op != OP_I); j -= (op != OP_J);
+        }
+        acc |= (uint64_t)op << (2 * (n & 31));
+        if ((n & 31) == 31) { if (lane == (n >> 5)) out.ops = acc; acc = 0; }
+        n++;
+        if (n >= C2B_MAX_ALN_LEN) { out.err = 1; break; }
+    }
+    if (n & 31) { acc |= ~0ull << (2 * (n & 31)); if (lane == (n >> 5)) out.ops = acc; }
+    out.n = n;
+    return out;
+}
+
+// Full alignment of one strand against one reference: DP over row blocks, then the walk.
+C2B_DEVNOINL Walked align_strand(const KParams &P, const RefDev &R, const uint8_t *codes, int J,
+                                 uint32_t *tb, int32_t *bnd)
+{
+    const int NEG4 = 4 * (int)((int64_t)P.go * J * R.I);        // sentinel of Align.pyx:150, scaled
+    int cM = 0, cX = 0, cY = 0;
+    const int bstride = 3 * (P.TS);
+    for (int rb = 0; rb < R.nrb; rb++) {
+        dp_dispatch(P, R, codes, J, rb, NEG4, tb, bnd + ((rb + 1) & 1) * bstride, bnd + (rb & 1) * bstride, cM, cX, cY);
+        wp::sync();
+    }
+    const int s = wp::max3(cM, cY, cX) & 3;                     // start state, Align.pyx:349-358
+    return walk(P, R, J, tb, s);
+}
+
+// --------------------------------------------------------------------------------------------- columns
+// mode bits: 1 = write strings, 2 = scatter per-reference-position info into shared memory.
+struct ColOut { int n_match; int irregular; };
+
+C2B_DEVNOINL ColOut columns(const KParams &P, const RefDev &R, WarpSmem &S, const uint8_t *codes, int J,
+                            uint64_t ops, int n, int mode, uint8_t *out_read, uint8_t *out_ref)
+{
+    const int lane = wp::lane();
+    const uint64_t lo = 0x5555555555555555ull;
+    const int ci = 32 - wp::popcll((ops >> 1) & lo);     // ops consuming a reference base (M, J)
+    const int cj = 32 - wp::popcll(ops & lo);            // ops consuming a read base (M, I)
+    int pk = (ci << 16) | cj;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int v = wp::shfl_up(pk, d); if (lane >= d) pk += v; }
+    pk -= (ci << 16) | cj;                               // exclusive
+    int i = R.I - (pk >> 16), j = J - (pk & 0xffff);
+    uint32_t wr[8], wf[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) { wr[q] = 0; wf[q] = 0; }
+    int match = 0, irr = 0;
+    const int n0 = 32 * lane;
+    if (n0 < n) {
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+            const int op = (int)(ops >> (2 * e)) & 3;
+            if (op != OP_NONE) {
+                const int code = (op != OP_J) ? codes[j - 1] : 0;
+                const uint32_t rd = (op == OP_J) ? (uint32_t)'-' : (uint32_t)P.alpha[code];
+                const uint32_t rf = (op == OP_I) ? (uint32_t)'-' : (uint32_t)R.asc[i - 1];
+                if (op == OP_M && rd == rf) match++;
+                if ((n0 + e == 0 || n0 + e == n - 1) && (op != OP_M || rd != rf)) irr = 1;   // CRISPRessoCORE.py:729-733
+                const int byte = 15 - (e & 15), wi = (e >> 4) * 4 + (byte >> 2), sh = 8 * (byte & 3);
+                wr[wi] |= rd << sh; wf[wi] |= rf << sh;
+                if (mode & 2) {
+                    if (op == OP_M) S.rowinfo[i - 1] = (uint8_t)code;
+                    else if (op == OP_J) S.rowinfo[i - 1] = 8;
+                    else if (i > 0 && i < R.I) wp::adds(&S.rowins[i], 1u);
+                }
+                i -= (op != OP_I); j -= (op != OP_J);
+            }
+        }
+        if (mode & 1) {
+            // right-aligned slots: column n (from the right) lives at byte W-1-n
+            uint4 *pr = reinterpret_cast<uint4 *>(out_read + P.W - 32 * lane - 16);
+            uint4 *pf = reinterpret_cast<uint4 *>(out_ref + P.W - 32 * lane - 16);
+            pr[0] = make_uint4(wr[0], wr[1], wr[2], wr[3]); pf[0] = make_uint4(wf[0], wf[1], wf[2], wf[3]);
+            if (n0 + 16 < n) { pr[-1] = make_uint4(wr[4], wr[5], wr[6], wr[7]); pf[-1] = make_uint4(wf[4], wf[5], wf[6], wf[7]); }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { match += wp::shfl_xor(match, d); irr |= wp::shfl_xor(irr, d); }
+    ColOut o; o.n_match = match; o.irregular = irr;
+    return o;
+}
+
+// exact round(100*m/n, 3)*1000 with Python's round-half-even (ties are exactly representable)
+C2B_DEV int score_milli(int m, int n)
+{
+    const long long num = 100000ll * m;
+    long long q = num / n; const long long r = num - q * n;
+    if (2 * r > n || (2 * r == n && (q & 1))) q++;
+    return (int)q;
+}
+
+// ------------------------------------------------------------------------------------------------ rows
+struct RowOut {
+    int ins_n, del_n, sub_n, n_ins_all, n_ins_win, n_del_all, n_del_win, n_del_pos, n_sub_all, nent;
+};
+
+// PASS 0: scalars + edit list.  PASS 1: per-position count vectors (weight w).
+template <int PASS>
+C2B_DEV void rows_pass(const KParams &P, const RefDev &R, WarpSmem &S, RowOut &o, c2b_edit *ed, long long w,
+                       bool len_vectors)
+{
+    const int lane = wp::lane();
+    const uint32_t lt = (1u << lane) - 1u;
+    const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
+               ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
+    unsigned long long *V = R.vec;
+    const int vs = P.vstride;
+    int open_a = -1; uint32_t prevD = 0;
+    const int I = R.I;
+    const int nchunks = (I + 32) >> 5;                    // covers position I itself (end of a trailing deletion)
+
+    auto run = [&](int a, int b) {                         // one deletion run [a,b)  (COREResources.pyx:143-160)
+        const int size = b - a;
+        const bool hit = (int)R.cum[b] - (int)R.cum[a] > 0;
+        if (PASS == 0) {
+            o.n_del_all++; o.n_del_pos += size;
+            if (hit) { o.n_del_win++; o.del_n += size; }
+            if (lane == 0 && o.nent < P.edit_cap && ed) {
+                c2b_edit e; e.a = (uint16_t)a; e.b = (uint16_t)b; e.type = 3; e.in_window = hit; e.base = 0; e.pad = 0;
+                ed[o.nent] = e;
+            }
+            o.nent++;
+        } else if (hit) {
+            for (int p = a + lane; p < b; p += 32) {
+                if (!ign_d) wp::addg(V + (int64_t)C2B_V_DEL * vs + p, w);
+                if (len_vectors) wp::addg(V + (int64_t)C2B_V_DEL_LEN * vs + p, w * size);
+            }
+        }
+    };
+
+    for (int c = 0; c < nchunks; c++) {
+        const int p = 32 * c + lane;
+        const bool valid = p < I;
+        const int info = valid ? S.rowinfo[p] : 0;
+        const bool isdel = valid && info == 8;
+        const int rcode = info & 7;
+        const uint32_t refc = valid ? R.asc[p] : 0u, readc = P.alpha[rcode];
+        const bool differs = valid && !isdel && readc != refc;
+        const bool issub = differs && readc != 'N';                         // COREResources.pyx:111
+        const bool inc_p = valid && R.incl[p];
+        const uint32_t insr = (valid && p + 1 <= I - 1) ? S.rowins[p + 1] : 0u;   // insertion right of p
+        const uint32_t insl = (valid && p >= 1 && p <= I - 1) ? S.rowins[p] : 0u; // insertion left of p
+        const bool win_r = insr > 0 && inc_p && R.incl[p + 1];                    // both flanks in window (:120)
+        const bool win_l = insl > 0 && inc_p && R.incl[p - 1];
+        const uint32_t D = wp::ballot(isdel);
+        if (PASS == 0) {
+            const uint32_t Bs = wp::ballot(issub), Bsw = wp::ballot(issub && inc_p);
+            const uint32_t Bi = wp::ballot(insr > 0), Biw = wp::ballot(win_r);
+            o.n_sub_all += wp::popc(Bs); o.sub_n += wp::popc(Bsw);
+            o.n_ins_all += wp::popc(Bi); o.n_ins_win += wp::popc(Biw);
+            if (Biw) {
+                int v = win_r ? (int)insr : 0;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) v += wp::shfl_xor(v, d);
+                o.ins_n += v;
+            }
+            if (Bs) {
+                const int idx = o.nent + wp::popc(Bs & lt);
+                if (issub && idx < P.edit_cap && ed) {
+                    c2b_edit e; e.a = (uint16_t)p; e.b = 0; e.type = 1; e.in_window = inc_p; e.base = (uint8_t)readc; e.pad = 0;
+                    ed[idx] = e;
+                }
+                o.nent += wp::popc(Bs);
+            }
+            if (Bi) {
+                const int idx = o.nent + wp::popc(Bi & lt);
+                if (insr > 0 && idx < P.edit_cap && ed) {
+                    c2b_edit e; e.a = (uint16_t)p; e.b = (uint16_t)insr; e.type = 2; e.in_window = win_r; e.base = 0; e.pad = 0;
+                    ed[idx] = e;
+                }
+                o.nent += wp::popc(Bi);
+            }
+        } else {
+            if (insr > 0) wp::addg(V + (int64_t)C2B_V_ALL_INS_LEFT * vs + p, w);
+            if (insr > 0 || insl > 0) wp::addg(V + (int64_t)C2B_V_ALL_INS * vs + p, w);   // a shared flank counts once
+            if (!ign_i && (win_r || win_l)) wp::addg(V + (int64_t)C2B_V_INS * vs + p, w);
+            if (len_vectors && (win_r || win_l))
+                wp::addg(V + (int64_t)C2B_V_INS_LEN * vs + p, w * (long long)((win_r ? insr : 0u) + (win_l ? insl : 0u)));
+            if (isdel) wp::addg(V + (int64_t)C2B_V_ALL_DEL * vs + p, w);
+            if (issub) {
+                wp::addg(V + (int64_t)C2B_V_ALL_SUB * vs + p, w);
+                if (!ign_s) {
+                    wp::addg(V + (int64_t)(C2B_V_SUBBASE0 + rcode) * vs + p, w);
+                    if (inc_p) wp::addg(V + (int64_t)C2B_V_SUB * vs + p, w);
+                }
+            }
+            if (isdel || differs) {                       // all_base_count_vectors as deviation from "read == ref"
+                const int rc = R.rcode[p];
+                wp::addg(V + (int64_t)(C2B_V_BASEDEV0 + (isdel ? P.nq : rcode)) * vs + p, w);
+                if (rc != 255) wp::addg(V + (int64_t)(C2B_V_BASEDEV0 + rc) * vs + p, -w);
+            }
+        }
+        // deletion runs: ends inside this chunk
+        const uint32_t Dsh = (D << 1) | prevD;
+        const uint32_t Sm = D & ~Dsh;
+        uint32_t E = ~D & Dsh;
+        uint32_t Erem = E;
+        while (Erem) {
+            const int eb = wp::ffs(Erem) - 1;
+            Erem &= Erem - 1;
+            const uint32_t below = Sm & ((1u << eb) - 1u);
+            const int a = below ? 32 * c + (31 - wp::clz(below)) : open_a;
+            run(a, 32 * c + eb);
+        }
+        if (D >> 31) {
+            const int hs = Sm ? 31 - wp::clz(Sm) : -1, he = E ? 31 - wp::clz(E) : -1;
+            if (hs > he) open_a = 32 * c + hs;
+        }
+        prevD = D >> 31;
+    }
+    if (prevD) run(open_a, I);
+}
+
+// ------------------------------------------------------------------------------------------ per read
+C2B_DEV int strand_mode(const KParams &P, const RefDev &R, const WarpSmem &S, int J)
+{
+    // seed test of CRISPRessoCORE.py:656-687: 0 forward only, 1 reverse-complement only, 2 both
+    if (P.flags & C2B_F_NO_STRAND_SEARCH) return 0;
+    const int lane = wp::lane();
+    const int L = R.seed_len, ns = R.nseeds;
+    uint32_t hit = 0;                                        // bit s: fw seed s seen ; bit 8+s: rc seed s seen
+    if (ns > 0 && L > 0) {
+        for (int p = lane; p + L <= J; p += 32) {
+            uint64_t km = 0;
+            for (int c = 0; c < L; c++) km |= (uint64_t)S.fw[p + c] << (3 * c);
+            for (int s = 0; s < ns; s++) {
+                if (km == R.fw_seed[s]) hit |= 1u << s;
+                if (km == R.rc_seed[s]) hit |= 1u << (8 + s);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) hit |= (uint32_t)wp::shfl_xor((int)hit, d);
+    const int nf = wp::popc(hit & 0xffu), nr = wp::popc(hit >> 8);
+    if (nf > P.seed_min && nr == 0) return 0;
+    if (nf == 0 && nr > P.seed_min) return 1;
+    return 2;
+}
+
+C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_slot)
+{
+    const int lane = wp::lane();
+    const int64_t off = P.offsets[rd];
+    const int J = (int)(P.offsets[rd + 1] - off);
+    uint32_t *tb = P.tb + (int64_t)warp_slot * P.tb_words_per_warp;
+    int32_t *bnd = P.bnd + (int64_t)warp_slot * P.bnd_words_per_warp;
+    uint64_t *opsbuf = P.opsbuf + (int64_t)warp_slot * P.n_refs * 32;
+
+    c2b_read_rec rec; rec.winner_mask = 0; rec.best_score_milli = -1000; rec.best_ref = -1; rec.n_winners = 0;
+    rec.ambiguous = 0; rec.status = 0;
+
+    uint32_t st = 0;
+    if (J < 1 || J > MAXJ || J + 32 > P.TS) st |= C2B_ST_TOO_LONG;
+    else {
+        bool bad = false;
+        for (int p = lane; p < J; p += 32) {
+            const uint8_t ch = P.reads[off + p];
+            int code = 255;
+#pragma unroll
+            for (int q = 0; q < C2B_MAX_Q; q++) if (q < P.nq && ch == P.alpha[q]) code = q;
+            if (code == 255) { bad = true; code = 0; }
+            S.fw[p] = (uint8_t)code;
+            S.rc[J - 1 - p] = P.comp[code];
+        }
+        if (wp::ballot(bad)) st |= C2B_ST_BAD_CHAR;
+    }
+    wp::sync();
+
+    const int r_begin = P.ref_id ? P.ref_id[rd] : 0;
+    const int r_end = P.ref_id ? r_begin + 1 : P.n_refs;
+    const bool multi = (r_end - r_begin) > 1;
+    uint64_t keep_ops = ~0ull; int keep_n = 0, keep_strand = 0, keep_irr = 0;
+
+    for (int r = r_begin; r < r_end; r++) {
+        const RefDev &R = P.refs[r];
+        c2b_aln_rec a;
+        a.n_match = 0; a.aln_len = 0; a.score_milli = -1000; a.strand = 0; a.status = (uint8_t)st; a.n_edits = 0;
+        a.insertion_n = a.deletion_n = a.substitution_n = 0; a.n_ins_all = a.n_ins_win = 0; a.n_del_all = a.n_del_win = 0;
+        a.n_del_pos_all = 0; a.n_sub_all = 0; a.irregular_ends = 0; a.modified = 0;
+        if (!st && (R.I + J > C2B_MAX_ALN_LEN)) a.status |= C2B_ST_TOO_LONG;
+        if (!a.status) {
+            const int mode = P.forced_ops ? 0 : strand_mode(P, R, S, J);
+            Walked wf; wf.ops = ~0ull; wf.n = 0; wf.err = 0;
+            Walked wr = wf;
+            int mf = 0, mr = 0, sf = -1000000, sr = -1000000;
+            if (mode != 1) {
+                if (P.forced_ops) { wf.ops = P.forced_ops[rd * 32 + lane]; wf.n = P.forced_n[rd]; wf.err = 0; }
+                else wf = align_strand(P, R, S.fw, J, tb, bnd);
+                if (wf.err) a.status |= C2B_ST_UNDEFINED;
+                else if (mode == 2) { mf = columns(P, R, S, S.fw, J, wf.ops, wf.n, 0, nullptr, nullptr).n_match; sf = score_milli(mf, wf.n); }
+            }
+            if (mode != 0) {
+                wr = align_strand(P, R, S.rc, J, tb, bnd);
+                if (wr.err) a.status |= C2B_ST_UNDEFINED;
+                else if (mode == 2) { mr = columns(P, R, S, S.rc, J, wr.ops, wr.n, 0, nullptr, nullptr).n_match; sr = score_milli(mr, wr.n); }
+            }
+            if (!a.status) {
+                const bool use_rc = (mode == 1) || (mode == 2 && sr > sf);      // strict '>' of CRISPRessoCORE.py:682
+                const Walked &wk = use_rc ? wr : wf;
+                const uint8_t *codes = use_rc ? S.rc : S.fw;
+                uint8_t *o_read = P.strings ? P.strings + ((rd * P.n_refs + r) * 2) * (int64_t)P.W : nullptr;
+                uint8_t *o_ref = o_read ? o_read + P.W : nullptr;
+                int cmode = (o_read ? 1 : 0);
+                if (!multi) {                                   // single reference: scatter now, classify below
+                    for (int p = lane; p <= R.I; p += 32) S.rowins[p] = 0;
+                    wp::sync();
+                    cmode |= 2;
+                }
+                const ColOut co = columns(P, R, S, codes, J, wk.ops, wk.n, cmode, o_read, o_ref);
+                a.n_match = (uint16_t)co.n_match; a.aln_len = (uint16_t)wk.n; a.strand = use_rc;
+                a.score_milli = score_milli(co.n_match, wk.n);
+                a.irregular_ends = (uint8_t)co.irregular;
+                if (multi) opsbuf[r * 32 + lane] = wk.ops;
+                keep_ops = wk.ops; keep_n = wk.n; keep_strand = use_rc; keep_irr = co.irregular;
+                // best-reference bookkeeping (CRISPRessoCORE.py:697-707)
+                const int sc = a.score_milli;
+                if (sc > rec.best_score_milli && (double)sc / 1000.0 > R.min_aln) {
+                    rec.best_score_milli = sc; rec.winner_mask = 1u << (r & 31); rec.n_winners = 1;
+                } else if (sc == rec.best_score_milli) {
+                    rec.winner_mask |= 1u << (r & 31); rec.n_winners++;
+                }
+            }
+        }
+        rec.status |= a.status;
+        if (lane == 0) P.alns[rd * P.n_refs + r] = a;
+    }
+    wp::sync();
+
+    if (rec.best_score_milli <= 0) { rec.winner_mask = 0; rec.n_winners = 0; }
+    else {
+        const bool expand = P.flags & C2B_F_EXPAND_AMBIGUOUS, first = P.flags & C2B_F_ASSIGN_FIRST;
+        const bool ambiguous = rec.n_winners > 1 && !first && !expand;     // CRISPRessoCORE.py:780-785
+        rec.ambiguous = ambiguous;
+        const long long cnt = P.count ? P.count[rd] : 1;
+        const long long w = P.qweight ? P.qweight[rd] : cnt;
+        int nth = 0;
+        for (int r = r_begin; r < r_end; r++) {
+            if (!((rec.winner_mask >> (r & 31)) & 1u)) continue;
+            const RefDev &R = P.refs[r];
+            rec.best_ref = (int16_t)r;                          // best_match_name = last winner (:768)
+            uint64_t ops = keep_ops; int n = keep_n, strand = keep_strand, irr = keep_irr;
+            if (multi) {
+                wp::sync();
+                ops = wp::ldcg64(opsbuf + r * 32 + lane);
+                const c2b_aln_rec prev = P.alns[rd * P.n_refs + r];      // written by lane 0 above
+                n = wp::shfl((int)prev.aln_len, 0); strand = wp::shfl((int)prev.strand, 0); irr = wp::shfl((int)prev.irregular_ends, 0);
+                for (int p = lane; p <= R.I; p += 32) S.rowins[p] = 0;
+                wp::sync();
+                columns(P, R, S, strand ? S.rc : S.fw, J, ops, n, 2, nullptr, nullptr);
+            }
+            wp::sync();
+            RowOut o; o.ins_n = o.del_n = o.sub_n = 0; o.n_ins_all = o.n_ins_win = o.n_del_all = o.n_del_win = 0;
+            o.n_del_pos = o.n_sub_all = 0; o.nent = 0;
+            c2b_edit *ed = P.edits ? P.edits + (rd * P.n_refs + r) * (int64_t)P.edit_cap : nullptr;
+            rows_pass<0>(P, R, S, o, ed, 0, false);
+            const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
+                       ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
+            const bool has_d = !ign_d && o.del_n > 0, has_i = !ign_i && o.ins_n > 0, has_s = !ign_s && o.sub_n > 0;
+            const bool modified = has_d || has_i || has_s;     // CRISPRessoCORE.py:746-753 (same truth table)
+            uint32_t astatus = 0;
+            if (P.edits && o.nent > P.edit_cap) astatus |= C2B_ST_EDIT_OVERFLOW;
+            // contribution to the count block (CRISPRessoCORE.py:3989-4072)
+            const bool overflow = astatus & C2B_ST_EDIT_OVERFLOW;          // caller re-runs these with a larger cap
+            const bool counted = !ambiguous && (!first || nth == 0) && !overflow;
+            unsigned long long *SC = R.scal;
+            if (counted && w > 0) {
+                const bool discard = (P.flags & C2B_F_DISCARD_INDEL_READS) && (o.del_n > 0 || o.ins_n > 0);
+                if (discard) { if (lane == 0) wp::addg(SC + C2B_S_DISCARDED, w); }
+                else {
+                    rows_pass<1>(P, R, S, o, nullptr, w, has_d || has_i || has_s);
+                    if (lane == 0) {
+                        wp::addg(SC + C2B_S_TOTAL, w);
+                        wp::addg(SC + (modified ? C2B_S_MODIFIED : C2B_S_UNMODIFIED), w);
+                        if (has_i) wp::addg(SC + C2B_S_INS, w);
+                        if (has_d) wp::addg(SC + C2B_S_DEL, w);
+                        if (has_s) wp::addg(SC + C2B_S_SUB, w);
+                        const int combo = (has_i ? 4 : 0) | (has_d ? 2 : 0) | (has_s ? 1 : 0);
+                        const int slot[8] = {-1, C2B_S_ONLY_SUB, C2B_S_ONLY_DEL, C2B_S_DEL_SUB, C2B_S_ONLY_INS, C2B_S_INS_SUB,
+                                             C2B_S_INS_DEL, C2B_S_INS_DEL_SUB};
+                        if (slot[combo] >= 0) wp::addg(SC + slot[combo], w);
+                    }
+                }
+            } else if (ambiguous && nth == 0 && w > 0 && lane == 0 && !overflow) wp::addg(SC + C2B_S_AMBIGUOUS_W, w);
+            if (lane == 0) {
+                c2b_aln_rec a = P.alns[rd * P.n_refs + r];
+                a.insertion_n = (uint16_t)o.ins_n; a.deletion_n = (uint16_t)o.del_n; a.substitution_n = (uint16_t)o.sub_n;
+                a.n_ins_all = (uint16_t)o.n_ins_all; a.n_ins_win = (uint16_t)o.n_ins_win;
+                a.n_del_all = (uint16_t)o.n_del_all; a.n_del_win = (uint16_t)o.n_del_win;
+                a.n_del_pos_all = (uint16_t)o.n_del_pos; a.n_sub_all = (uint16_t)o.n_sub_all;
+                a.n_edits = (uint16_t)o.nent; a.modified = modified; a.status |= (uint8_t)astatus;
+                a.irregular_ends = (uint8_t)irr;
+                P.alns[rd * P.n_refs + r] = a;
+            }
+            rec.status |= astatus;
+            nth++;
+            // aln_stats of the serial process_fastq branch use best_match_name only (:1971-1979): the LAST winner
+            const bool is_last = (rec.winner_mask >> (r & 31)) >> 1 == 0;
+            if (is_last && lane == 0 && !overflow) {
+                const long long total_mods = o.n_ins_all + o.n_del_pos + o.n_sub_all;
+                const long long in_win = o.sub_n + o.del_n + o.ins_n;
+                wp::addg(SC + C2B_S_N_GLOBAL_SUBS, cnt * o.n_sub_all);
+                wp::addg(SC + C2B_S_N_SUBS_OUTSIDE_WINDOW, cnt * (o.n_sub_all - o.sub_n));
+                wp::addg(SC + C2B_S_N_MODS_IN_WINDOW, cnt * in_win);
+                wp::addg(SC + C2B_S_N_MODS_OUTSIDE_WINDOW, cnt * (total_mods - in_win));
+                if (irr) wp::addg(SC + C2B_S_N_READS_IRREGULAR_ENDS, cnt);
+                wp::addg(SC + C2B_S_N_ALIGNED_UNIQUE, 1);
+                wp::addg(SC + C2B_S_N_ALIGNED_COUNT, cnt);
+            }
+            wp::sync();
+        }
+    }
+    if (lane == 0) P.recs[rd] = rec;
+}
+
+}  // namespace c2b

@@ -1,0 +1,559 @@
+// c2b_engine.cu -- the sm_100a kernel entry + the C ABI declared in include/c2b200.h.
+//
+// Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC \
+//        -Iinclude -o crispresso2_b200/libc2b200.so crispresso2_b200/csrc/c2b_engine.cu
+// The same file compiles with g++ -DC2B_EMU against tests/emu/warp_emu.h (CPU-only logic tests).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "c2b_core.cuh"
+
+using namespace c2b;
+
+// ----------------------------------------------------------------------------------- runtime shim
+#ifndef C2B_EMU
+#define RT_OK cudaSuccess
+typedef cudaStream_t rt_stream;
+static const char *rt_errstr(cudaError_t e) { return cudaGetErrorString(e); }
+typedef cudaError_t rt_err;
+static rt_err rt_malloc(void **p, size_t n) { return cudaMalloc(p, n ? n : 16); }
+static rt_err rt_free(void *p) { return cudaFree(p); }
+static rt_err rt_h2d(void *d, const void *h, size_t n, rt_stream s) { return n ? cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s) : cudaSuccess; }
+static rt_err rt_d2h(void *h, const void *d, size_t n, rt_stream s) { return n ? cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) : cudaSuccess; }
+static rt_err rt_zero(void *d, size_t n, rt_stream s) { return cudaMemsetAsync(d, 0, n, s); }
+static rt_err rt_sync(rt_stream s) { return cudaStreamSynchronize(s); }
+#else
+typedef int rt_err;
+typedef int rt_stream;
+#define RT_OK 0
+thread_local emu::Warp *emu::g_warp = nullptr;
+static const char *rt_errstr(int) { return "emu"; }
+static rt_err rt_malloc(void **p, size_t n) { *p = calloc(1, n ? n : 16); return *p ? 0 : 1; }
+static rt_err rt_free(void *p) { free(p); return 0; }
+static rt_err rt_h2d(void *d, const void *h, size_t n, rt_stream) { if (n) memcpy(d, h, n); return 0; }
+static rt_err rt_d2h(void *h, const void *d, size_t n, rt_stream) { if (n) memcpy(h, d, n); return 0; }
+static rt_err rt_zero(void *d, size_t n, rt_stream) { memset(d, 0, n); return 0; }
+static rt_err rt_sync(rt_stream) { return 0; }
+#endif
+
+// ----------------------------------------------------------------------------------------- kernel
+#ifndef C2B_EMU
+constexpr int WARPS_PER_CTA = 8;
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) c2b_align_classify_kernel(const KParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSmem *S = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
+    const int warp_slot = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    for (;;) {
+        unsigned long long rd = 0;
+        if ((threadIdx.x & 31) == 0) rd = wp::fetch_work(P.work_counter);
+        rd = __shfl_sync(0xffffffffu, rd, 0);
+        if (rd >= (unsigned long long)P.n_reads) break;
+        process_read(P, *S, (int64_t)rd, warp_slot);
+        __syncwarp();
+    }
+}
+#endif
+
+// ----------------------------------------------------------------------------------------- engine
+struct RefHost {
+    std::string seq; std::vector<int64_t> gi, inc; double min_aln; std::vector<int64_t> rows;
+    std::vector<std::string> fw, rc;
+};
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+};
+
+struct c2b_engine {
+    int device = 0;
+    rt_stream stream = 0;
+    std::string err;
+    bool configured = false;
+    c2b_params prm;
+    int n_refs = 0, max_I = 0, max_nrb = 1, vstride = 0;
+    std::vector<RefHost> refs;
+    std::vector<RefDev> refdev;         // host mirror (device pointers inside)
+    void *d_tables = nullptr; RefDev *d_refs = nullptr;
+    unsigned long long *d_counts = nullptr; size_t counts_n = 0;
+    // scratch
+    DevBuf tb, bnd, ops, work;
+    int n_warps = 0, grid = 0;
+    int scratch_TS = 0;
+    // staging for the host-pointer API
+    DevBuf s_reads, s_off, s_cnt, s_qw, s_rid, s_recs, s_alns, s_str, s_ed;
+    double last_ms = 0; int64_t launches = 0;
+    const uint64_t *forced_ops = nullptr; const int32_t *forced_n = nullptr;
+#ifndef C2B_EMU
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+#endif
+};
+
+static std::string g_create_err;
+
+static int fail(c2b_engine *e, int code, const std::string &m) { if (e) e->err = m; else g_create_err = m; return code; }
+
+#define RTCHK(call) do { rt_err _r = (call); if (_r != RT_OK) return fail(e, C2B_E_CUDA, std::string(#call) + ": " + rt_errstr(_r)); } while (0)
+
+static int ensure(c2b_engine *e, DevBuf &b, size_t n)
+{
+    if (n <= b.cap) return C2B_OK;
+    if (b.p) rt_free(b.p);
+    b.p = nullptr; b.cap = 0;
+    size_t want = n + n / 8 + 256;
+    RTCHK(rt_malloc(&b.p, want));
+    b.cap = want;
+    return C2B_OK;
+}
+
+extern "C" {
+
+int c2b_create(int device, c2b_engine **out)
+{
+    if (!out) return C2B_E_ARG;
+    c2b_engine *e = new c2b_engine();
+    e->device = device;
+#ifndef C2B_EMU
+    cudaError_t r = cudaSetDevice(device);
+    if (r == cudaSuccess) r = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (r == cudaSuccess) r = cudaEventCreate(&e->ev0);
+    if (r == cudaSuccess) r = cudaEventCreate(&e->ev1);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(c2b_align_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(sizeof(WarpSmem) * WARPS_PER_CTA));
+    int nsm = 0, occ = 0;
+    if (r == cudaSuccess) r = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c2b_align_classify_kernel, WARPS_PER_CTA * 32,
+                                                                            sizeof(WarpSmem) * WARPS_PER_CTA);
+    if (r != cudaSuccess) { g_create_err = std::string("c2b_create: ") + cudaGetErrorString(r); delete e; return C2B_E_CUDA; }
+    if (occ < 1) occ = 1;
+    e->grid = nsm * occ;                 // persistent: one wave of CTAs, warps pull reads from a counter
+    e->n_warps = e->grid * WARPS_PER_CTA;
+#else
+    e->grid = 1; e->n_warps = 1;
+#endif
+    *out = e;
+    return C2B_OK;
+}
+
+void c2b_destroy(c2b_engine *e)
+{
+    if (!e) return;
+    DevBuf *bufs[] = {&e->tb, &e->bnd, &e->ops, &e->work, &e->s_reads, &e->s_off, &e->s_cnt, &e->s_qw, &e->s_rid,
+                      &e->s_recs, &e->s_alns, &e->s_str, &e->s_ed};
+    for (DevBuf *b : bufs) if (b->p) rt_free(b->p);
+    if (e->d_tables) rt_free(e->d_tables);
+    if (e->d_counts) rt_free(e->d_counts);
+#ifndef C2B_EMU
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+#endif
+    delete e;
+}
+
+const char *c2b_last_error(const c2b_engine *e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+static uint64_t pack_seed(const c2b_params &p, const std::string &s)
+{
+    uint64_t v = 0;
+    for (size_t c = 0; c < s.size(); c++) {
+        int code = -1;
+        for (int q = 0; q < p.nq; q++) if (s[c] == p.alphabet[q]) code = q;
+        if (code < 0) return ~0ull;                     // can never equal a read k-mer
+        v |= (uint64_t)code << (3 * c);
+    }
+    return v;
+}
+
+int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_ref *refs)
+{
+    if (!e || !p || !refs || n_refs < 1) return fail(e, C2B_E_ARG, "c2b_configure: bad argument");
+    if (n_refs > C2B_MAX_REFS) return fail(e, C2B_E_LIMIT, "c2b_configure: more than C2B_MAX_REFS references");
+    if (p->nq < 1 || p->nq > C2B_MAX_Q) return fail(e, C2B_E_ARG, "c2b_configure: alphabet size out of range");
+    if (p->seed_count < 0 || p->edit_cap < 0) return fail(e, C2B_E_ARG, "c2b_configure: negative seed_count/edit_cap");
+    e->configured = false;
+    e->prm = *p;
+    e->n_refs = n_refs;
+    e->refs.assign(n_refs, RefHost());
+    e->refdev.assign(n_refs, RefDev());
+    int maxI = 0, max_nrb = 1;
+    size_t bytes = 0;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    std::vector<size_t> base(n_refs);
+    for (int r = 0; r < n_refs; r++) {
+        const c2b_ref &rf = refs[r];
+        if (!rf.seq || rf.len < 1 || !rf.gap_incentive || !rf.score_rows) return fail(e, C2B_E_ARG, "c2b_configure: incomplete reference");
+        if (rf.len > C2B_MAX_REF_LEN) return fail(e, C2B_E_LIMIT, "c2b_configure: reference longer than C2B_MAX_REF_LEN");
+        if (rf.n_seeds > 0 && (!rf.fw_seeds || !rf.rc_seeds)) return fail(e, C2B_E_ARG, "c2b_configure: seeds missing");
+        maxI = std::max(maxI, rf.len);
+        const int nrb = (rf.len + 255) / 256, Ipad = nrb * 256;
+        max_nrb = std::max(max_nrb, nrb);
+        base[r] = bytes;
+        bytes += al((size_t)p->nq * Ipad * 4) + 2 * al((size_t)Ipad * 4) + 2 * al(Ipad) + al(Ipad + 1) + al((size_t)(Ipad + 2) * 2);
+    }
+    const size_t refs_off = bytes;
+    bytes += al(sizeof(RefDev) * n_refs);
+    std::vector<unsigned char> blob(bytes, 0);
+    if (e->d_tables) { rt_free(e->d_tables); e->d_tables = nullptr; }
+    RTCHK(rt_malloc(&e->d_tables, bytes));
+    e->vstride = (maxI + 31) & ~31;
+    e->counts_n = (size_t)n_refs * (C2B_NVEC * (size_t)e->vstride + C2B_NSCAL);
+    if (e->d_counts) { rt_free(e->d_counts); e->d_counts = nullptr; }
+    RTCHK(rt_malloc((void **)&e->d_counts, e->counts_n * 8));
+    RTCHK(rt_zero(e->d_counts, e->counts_n * 8, e->stream));
+
+    for (int r = 0; r < n_refs; r++) {
+        const c2b_ref &rf = refs[r];
+        const int I = rf.len, nrb = (I + 255) / 256, Ipad = nrb * 256;
+        RefDev &d = e->refdev[r];
+        d.I = I; d.nrb = nrb; d.Ipad = Ipad; d.kstar = (I - 1) & 7; d.lstar = ((I - 1) >> 3) & 31;
+        d.min_aln = rf.min_aln_score;
+        unsigned char *hb = blob.data() + base[r];
+        unsigned char *db = (unsigned char *)e->d_tables + base[r];
+        size_t o = 0;
+        int32_t *prof = (int32_t *)(hb + o); d.prof = (const int32_t *)(db + o); o += al((size_t)p->nq * Ipad * 4);
+        int32_t *cIe = (int32_t *)(hb + o); d.cIe = (const int32_t *)(db + o); o += al((size_t)Ipad * 4);
+        int32_t *g4 = (int32_t *)(hb + o); d.g4 = (const int32_t *)(db + o); o += al((size_t)Ipad * 4);
+        uint8_t *asc = hb + o; d.asc = db + o; o += al(Ipad);
+        uint8_t *rcode = hb + o; d.rcode = db + o; o += al(Ipad);
+        uint8_t *incl = hb + o; d.incl = db + o; o += al(Ipad + 1);
+        uint16_t *cum = (uint16_t *)(hb + o); d.cum = (const uint16_t *)(db + o); o += al((size_t)(Ipad + 2) * 2);
+        const int64_t lim = (1ll << 27);
+        for (int q = 0; q < p->nq; q++)
+            for (int i = 0; i < I; i++) {
+                const int64_t v = rf.score_rows[(size_t)q * I + i];
+                if (v > lim || v < -lim) return fail(e, C2B_E_LIMIT, "c2b_configure: substitution score out of range");
+                prof[(size_t)q * Ipad + i] = (int32_t)(4 * v);
+            }
+        for (int i = 0; i <= I; i++) if (rf.gap_incentive[i] > lim || rf.gap_incentive[i] < -lim) return fail(e, C2B_E_LIMIT, "c2b_configure: gap incentive out of range");
+        for (int row = 0; row < I; row++) {
+            cIe[row] = (int32_t)(4 * (p->gap_extend + rf.gap_incentive[row + 1]));
+            g4[row] = (int32_t)(4 * rf.gap_incentive[row]);
+            asc[row] = (uint8_t)rf.seq[row];
+            int code = 255;
+            for (int q = 0; q < p->nq; q++) if (rf.seq[row] == p->alphabet[q]) code = q;
+            rcode[row] = (uint8_t)code;
+        }
+        d.gi0_4 = (int32_t)(4 * rf.gap_incentive[0]);
+        for (int k = 0; k < rf.n_include; k++) {
+            const int64_t v = rf.include_idx[k];
+            if (v >= 0 && v < I) incl[v] = 1;
+        }
+        cum[0] = 0;
+        for (int q = 0; q <= Ipad; q++) cum[q + 1] = (uint16_t)(cum[q] + (q < I && incl[q] ? 1 : 0));
+        const int ns = std::min({(int)rf.n_seeds, (int)p->seed_count, (int)C2B_MAX_SEEDS});
+        if (rf.n_seeds > 0 && std::min((int)rf.n_seeds, (int)p->seed_count) > C2B_MAX_SEEDS)
+            return fail(e, C2B_E_LIMIT, "c2b_configure: more seeds than C2B_MAX_SEEDS");
+        d.nseeds = ns; d.seed_len = 0;
+        for (int s = 0; s < C2B_MAX_SEEDS; s++) { d.fw_seed[s] = ~0ull; d.rc_seed[s] = ~0ull; }
+        for (int s = 0; s < ns; s++) {
+            const std::string f = rf.fw_seeds[s], c = rf.rc_seeds[s];
+            if (f.size() != c.size() || f.empty() || f.size() > C2B_MAX_SEED_LEN) return fail(e, C2B_E_LIMIT, "c2b_configure: seed length unsupported");
+            if (s && (int)f.size() != d.seed_len) return fail(e, C2B_E_LIMIT, "c2b_configure: seeds of unequal length");
+            d.seed_len = (int)f.size();
+            d.fw_seed[s] = pack_seed(*p, f); d.rc_seed[s] = pack_seed(*p, c);
+        }
+        d.vec = e->d_counts + (size_t)r * (C2B_NVEC * (size_t)e->vstride + C2B_NSCAL);
+        d.scal = d.vec + C2B_NVEC * (size_t)e->vstride;
+    }
+    memcpy(blob.data() + refs_off, e->refdev.data(), sizeof(RefDev) * n_refs);
+    e->d_refs = (RefDev *)((unsigned char *)e->d_tables + refs_off);
+    RTCHK(rt_h2d(e->d_tables, blob.data(), bytes, e->stream));
+    RTCHK(rt_sync(e->stream));
+    e->max_I = maxI; e->max_nrb = max_nrb;
+    e->scratch_TS = 0;
+    e->configured = true;
+    return C2B_OK;
+}
+
+int c2b_set_edit_cap(c2b_engine *e, int32_t edit_cap)
+{
+    if (!e || !e->configured || edit_cap < 0) return fail(e, C2B_E_ARG, "c2b_set_edit_cap: bad argument");
+    e->prm.edit_cap = edit_cap;
+    return C2B_OK;
+}
+
+int c2b_string_width(const c2b_engine *e, int32_t max_read_len)
+{
+    if (!e || !e->configured) return C2B_E_STATE;
+    return (e->max_I + max_read_len + 31) & ~31;
+}
+
+static int ensure_scratch(c2b_engine *e, int maxJ)
+{
+    const int TS = ((maxJ + 32 + 31) & ~31);
+    if (TS <= e->scratch_TS) return C2B_OK;
+    int rc;
+    if ((rc = ensure(e, e->tb, (size_t)e->n_warps * e->max_nrb * TS * 32 * 4))) return rc;
+    if ((rc = ensure(e, e->bnd, (size_t)e->n_warps * 2 * 3 * TS * 4))) return rc;
+    if ((rc = ensure(e, e->ops, (size_t)e->n_warps * e->n_refs * 32 * 8))) return rc;
+    if ((rc = ensure(e, e->work, 64))) return rc;
+    e->scratch_TS = TS;
+    return C2B_OK;
+}
+
+int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t *d_offsets, int64_t n_reads,
+                           int32_t max_read_len, const int32_t *d_count, const int32_t *d_qweight,
+                           const int32_t *d_ref_id, c2b_read_rec *d_recs, c2b_aln_rec *d_alns,
+                           uint8_t *d_strings, c2b_edit *d_edits)
+{
+    if (!e || !e->configured) return fail(e, C2B_E_STATE, "c2b_align_batch: engine not configured");
+    if (n_reads < 0 || !d_recs || !d_alns || (n_reads && (!d_reads || !d_offsets))) return fail(e, C2B_E_ARG, "c2b_align_batch: bad argument");
+    if (max_read_len < 1) max_read_len = 1;
+    if (max_read_len > C2B_MAX_READ_LEN) return fail(e, C2B_E_LIMIT, "c2b_align_batch: read longer than C2B_MAX_READ_LEN");
+    if ((int64_t)std::abs((long long)e->prm.gap_open) * max_read_len * e->max_I >= (1ll << 28))
+        return fail(e, C2B_E_LIMIT, "c2b_align_batch: gap_open * lengths exceeds the int32 score range");
+    int rc = ensure_scratch(e, max_read_len);
+    if (rc) return rc;
+    if (n_reads == 0) return C2B_OK;
+    KParams P;
+    memset(&P, 0, sizeof P);
+    P.reads = d_reads; P.offsets = d_offsets; P.n_reads = n_reads; P.count = d_count; P.qweight = d_qweight; P.ref_id = d_ref_id;
+    P.recs = d_recs; P.alns = d_alns; P.strings = d_strings; P.edits = d_edits;
+    P.W = (e->max_I + max_read_len + 31) & ~31; P.edit_cap = d_edits ? e->prm.edit_cap : 0;
+    if (P.edit_cap == 0) P.edits = nullptr;
+    P.refs = e->d_refs; P.n_refs = e->n_refs;
+    P.go = e->prm.gap_open; P.ge = e->prm.gap_extend; P.seed_count = e->prm.seed_count; P.seed_min = e->prm.seed_min;
+    P.flags = e->prm.flags; P.nq = e->prm.nq;
+    memcpy(P.alpha, e->prm.alphabet, C2B_MAX_Q); memcpy(P.comp, e->prm.complement, C2B_MAX_Q);
+    P.TS = e->scratch_TS;
+    P.tb = (uint32_t *)e->tb.p; P.tb_words_per_warp = (int64_t)e->max_nrb * P.TS * 32;
+    P.bnd = (int32_t *)e->bnd.p; P.bnd_words_per_warp = 2 * 3 * (int64_t)P.TS;
+    P.opsbuf = (uint64_t *)e->ops.p;
+    P.work_counter = (unsigned long long *)e->work.p;
+    P.vstride = e->vstride;
+    P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
+    RTCHK(rt_zero(e->work.p, 8, e->stream));
+#ifndef C2B_EMU
+    cudaEventRecord(e->ev0, e->stream);
+    c2b_align_classify_kernel<<<e->grid, WARPS_PER_CTA * 32, sizeof(WarpSmem) * WARPS_PER_CTA, e->stream>>>(P);
+    cudaEventRecord(e->ev1, e->stream);
+    RTCHK(cudaGetLastError());
+#else
+    {
+        static WarpSmem S;
+        for (int64_t rd = 0; rd < n_reads; rd++) emu::run_warp([&]() { process_read(P, S, rd, 0); });
+    }
+#endif
+    e->launches++;
+    return C2B_OK;
+}
+
+int c2b_sync(c2b_engine *e)
+{
+    if (!e) return C2B_E_ARG;
+    RTCHK(rt_sync(e->stream));
+    return C2B_OK;
+}
+
+void *c2b_stream(c2b_engine *e) { return e ? (void *)(uintptr_t)e->stream : nullptr; }
+
+double c2b_last_kernel_ms(c2b_engine *e)
+{
+#ifndef C2B_EMU
+    if (!e || !e->launches) return 0.0;
+    float ms = 0.f;
+    if (cudaEventSynchronize(e->ev1) != cudaSuccess) return 0.0;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) return 0.0;
+    return (double)ms;
+#else
+    (void)e; return 0.0;
+#endif
+}
+
+int64_t c2b_launch_count(const c2b_engine *e) { return e ? e->launches : 0; }
+
+int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads,
+                    const int32_t *count, const int32_t *qweight, const int32_t *ref_id,
+                    c2b_read_rec *recs, c2b_aln_rec *alns, uint8_t *strings, c2b_edit *edits)
+{
+    if (!e || !e->configured) return fail(e, C2B_E_STATE, "c2b_align_batch: engine not configured");
+    if (n_reads < 0 || !recs || !alns || (n_reads && (!reads || !offsets))) return fail(e, C2B_E_ARG, "c2b_align_batch: bad argument");
+    if (n_reads == 0) return C2B_OK;
+    int64_t maxJ = 1;
+    for (int64_t r = 0; r < n_reads; r++) {
+        const int64_t L = offsets[r + 1] - offsets[r];
+        if (L < 0) return fail(e, C2B_E_ARG, "c2b_align_batch: offsets not monotone");
+        maxJ = std::max(maxJ, L);
+    }
+    if (maxJ > C2B_MAX_READ_LEN) return fail(e, C2B_E_LIMIT, "c2b_align_batch: read longer than C2B_MAX_READ_LEN");
+    const int W = (e->max_I + (int)maxJ + 31) & ~31;
+    const int cap = edits ? e->prm.edit_cap : 0;
+    // chunk so that device staging stays bounded (strings dominate: n * n_refs * 2 * W bytes)
+    const int64_t per_read = (int64_t)e->n_refs * (2 * (int64_t)W * (strings ? 1 : 0) + (int64_t)cap * 8 + 32) + 16 + maxJ + 24;
+    int64_t chunk = std::max<int64_t>(1024, (int64_t)(1ll << 31) / per_read);
+    for (int64_t c0 = 0; c0 < n_reads; c0 += chunk) {
+        const int64_t n = std::min(chunk, n_reads - c0);
+        const int64_t b0 = offsets[c0], b1 = offsets[c0 + n];
+        int rc;
+        if ((rc = ensure(e, e->s_reads, (size_t)(b1 - b0) + 16))) return rc;
+        if ((rc = ensure(e, e->s_off, (size_t)(n + 1) * 8))) return rc;
+        if ((rc = ensure(e, e->s_recs, (size_t)n * sizeof(c2b_read_rec)))) return rc;
+        if ((rc = ensure(e, e->s_alns, (size_t)n * e->n_refs * sizeof(c2b_aln_rec)))) return rc;
+        if (strings && (rc = ensure(e, e->s_str, (size_t)n * e->n_refs * 2 * W))) return rc;
+        if (cap && (rc = ensure(e, e->s_ed, (size_t)n * e->n_refs * cap * sizeof(c2b_edit)))) return rc;
+        if (count && (rc = ensure(e, e->s_cnt, (size_t)n * 4))) return rc;
+        if (qweight && (rc = ensure(e, e->s_qw, (size_t)n * 4))) return rc;
+        if (ref_id && (rc = ensure(e, e->s_rid, (size_t)n * 4))) return rc;
+        // offsets are rebased so that the chunk's reads start at 0
+        std::vector<int64_t> off(n + 1);
+        for (int64_t k = 0; k <= n; k++) off[k] = offsets[c0 + k] - b0;
+        RTCHK(rt_h2d(e->s_reads.p, reads + b0, (size_t)(b1 - b0), e->stream));
+        RTCHK(rt_h2d(e->s_off.p, off.data(), (size_t)(n + 1) * 8, e->stream));
+        if (count) RTCHK(rt_h2d(e->s_cnt.p, count + c0, (size_t)n * 4, e->stream));
+        if (qweight) RTCHK(rt_h2d(e->s_qw.p, qweight + c0, (size_t)n * 4, e->stream));
+        if (ref_id) RTCHK(rt_h2d(e->s_rid.p, ref_id + c0, (size_t)n * 4, e->stream));
+        RTCHK(rt_sync(e->stream));      // `off` is a stack-lifetime host buffer
+        rc = c2b_align_batch_device(e, (const uint8_t *)e->s_reads.p, (const int64_t *)e->s_off.p, n, (int32_t)maxJ,
+                                    count ? (const int32_t *)e->s_cnt.p : nullptr, qweight ? (const int32_t *)e->s_qw.p : nullptr,
+                                    ref_id ? (const int32_t *)e->s_rid.p : nullptr, (c2b_read_rec *)e->s_recs.p,
+                                    (c2b_aln_rec *)e->s_alns.p, strings ? (uint8_t *)e->s_str.p : nullptr,
+                                    cap ? (c2b_edit *)e->s_ed.p : nullptr);
+        if (rc) return rc;
+        RTCHK(rt_d2h(recs + c0, e->s_recs.p, (size_t)n * sizeof(c2b_read_rec), e->stream));
+        RTCHK(rt_d2h(alns + c0 * e->n_refs, e->s_alns.p, (size_t)n * e->n_refs * sizeof(c2b_aln_rec), e->stream));
+        if (strings) RTCHK(rt_d2h(strings + c0 * e->n_refs * 2 * W, e->s_str.p, (size_t)n * e->n_refs * 2 * W, e->stream));
+        if (cap) RTCHK(rt_d2h(edits + c0 * e->n_refs * cap, e->s_ed.p, (size_t)n * e->n_refs * cap * sizeof(c2b_edit), e->stream));
+        RTCHK(rt_sync(e->stream));
+    }
+    return C2B_OK;
+}
+
+int c2b_counts_layout(const c2b_engine *e, int32_t *n_refs, int32_t *n_vec, int32_t *stride, int32_t *n_scal)
+{
+    if (!e || !e->configured) return C2B_E_STATE;
+    if (n_refs) *n_refs = e->n_refs;
+    if (n_vec) *n_vec = C2B_NVEC;
+    if (stride) *stride = e->vstride;
+    if (n_scal) *n_scal = C2B_NSCAL;
+    return C2B_OK;
+}
+
+int c2b_counts_reset(c2b_engine *e)
+{
+    if (!e || !e->configured) return fail(e, C2B_E_STATE, "c2b_counts_reset: engine not configured");
+    RTCHK(rt_zero(e->d_counts, e->counts_n * 8, e->stream));
+    RTCHK(rt_sync(e->stream));
+    return C2B_OK;
+}
+
+int c2b_counts_read(c2b_engine *e, int64_t *out, size_t n_int64)
+{
+    if (!e || !e->configured || !out) return fail(e, C2B_E_STATE, "c2b_counts_read: engine not configured");
+    if (n_int64 < e->counts_n) return fail(e, C2B_E_ARG, "c2b_counts_read: buffer too small");
+    RTCHK(rt_d2h(out, e->d_counts, e->counts_n * 8, e->stream));
+    RTCHK(rt_sync(e->stream));
+    return C2B_OK;
+}
+
+int c2b_counts_device(c2b_engine *e, void **d_ptr, size_t *n_int64)
+{
+    if (!e || !e->configured) return C2B_E_STATE;
+    if (d_ptr) *d_ptr = e->d_counts;
+    if (n_int64) *n_int64 = e->counts_n;
+    return C2B_OK;
+}
+
+int c2b_global_align(c2b_engine *e, const char *read, int32_t read_len, const char *ref, int32_t ref_len,
+                     const char *alphabet, int32_t nq, const int64_t *score_rows, const int64_t *gap_incentive,
+                     int32_t gap_open, int32_t gap_extend,
+                     char *out_read, char *out_ref, int32_t *aln_len, int32_t *n_match)
+{
+    if (!e || !read || !ref || !alphabet || !score_rows || !gap_incentive || !out_read || !out_ref || !aln_len || !n_match)
+        return fail(e, C2B_E_ARG, "c2b_global_align: bad argument");
+    c2b_params p; memset(&p, 0, sizeof p);
+    p.gap_open = gap_open; p.gap_extend = gap_extend; p.flags = C2B_F_NO_STRAND_SEARCH; p.nq = nq;
+    if (nq < 1 || nq > C2B_MAX_Q) return fail(e, C2B_E_LIMIT, "c2b_global_align: alphabet larger than C2B_MAX_Q");
+    memcpy(p.alphabet, alphabet, nq);
+    for (int q = 0; q < nq; q++) p.complement[q] = (uint8_t)q;
+    c2b_ref r; memset(&r, 0, sizeof r);
+    r.seq = ref; r.len = ref_len; r.gap_incentive = gap_incentive; r.score_rows = score_rows; r.min_aln_score = -1.0;
+    int rc = c2b_configure(e, &p, 1, &r);
+    if (rc) return rc;
+    const int W = c2b_string_width(e, read_len);
+    std::vector<uint8_t> str((size_t)2 * W);
+    int64_t off[2] = {0, read_len};
+    c2b_read_rec rec; c2b_aln_rec a;
+    rc = c2b_align_batch(e, (const uint8_t *)read, off, 1, nullptr, nullptr, nullptr, &rec, &a, str.data(), nullptr);
+    if (rc) return rc;
+    if (a.status) { e->err = "c2b_global_align: alignment status " + std::to_string(a.status); return 100 + a.status; }
+    memcpy(out_read, str.data() + W - a.aln_len, a.aln_len);
+    memcpy(out_ref, str.data() + 2 * W - a.aln_len, a.aln_len);
+    *aln_len = a.aln_len; *n_match = a.n_match;
+    return C2B_OK;
+}
+
+int c2b_classify_aligned(c2b_engine *e, const char *read_al, const char *ref_al, int32_t n_cols,
+                         const char *alphabet, int32_t nq, const int64_t *include_idx, int32_t n_include,
+                         c2b_aln_rec *out, c2b_edit *edits)
+{
+    if (!e || !read_al || !ref_al || !alphabet || !out || !edits || n_cols < 1) return fail(e, C2B_E_ARG, "c2b_classify_aligned: bad argument");
+    if (n_cols > C2B_MAX_ALN_LEN) return fail(e, C2B_E_LIMIT, "c2b_classify_aligned: alignment longer than C2B_MAX_ALN_LEN");
+    if (nq < 1 || nq > C2B_MAX_Q) return fail(e, C2B_E_LIMIT, "c2b_classify_aligned: alphabet larger than C2B_MAX_Q");
+    std::string read, ref;
+    std::vector<uint64_t> ops(32, ~0ull);
+    int prev = -1;
+    for (int c = n_cols - 1, n = 0; c >= 0; c--, n++) {           // op n = n-th column from the right
+        const bool gq = read_al[c] == '-', gr = ref_al[c] == '-';
+        if (gq && gr) return fail(e, C2B_E_ARG, "c2b_classify_aligned: column with two gaps");
+        const int op = gq ? OP_J : gr ? OP_I : OP_M;
+        if ((op == OP_I && prev == OP_J) || (op == OP_J && prev == OP_I))
+            return fail(e, C2B_E_ARG, "c2b_classify_aligned: insertion column adjacent to a deletion column");
+        prev = op;
+        ops[n >> 5] &= ~(3ull << (2 * (n & 31)));
+        ops[n >> 5] |= (uint64_t)op << (2 * (n & 31));
+    }
+    for (int c = 0; c < n_cols; c++) { if (read_al[c] != '-') read.push_back(read_al[c]); if (ref_al[c] != '-') ref.push_back(ref_al[c]); }
+    if (read.empty() || ref.empty()) return fail(e, C2B_E_ARG, "c2b_classify_aligned: empty sequence");
+    if ((int)read.size() > C2B_MAX_READ_LEN || (int)ref.size() > C2B_MAX_REF_LEN) return fail(e, C2B_E_LIMIT, "c2b_classify_aligned: sequence too long");
+    c2b_params p; memset(&p, 0, sizeof p);
+    p.gap_open = -1; p.gap_extend = -1; p.flags = C2B_F_NO_STRAND_SEARCH; p.nq = nq; p.edit_cap = n_cols + 1;
+    memcpy(p.alphabet, alphabet, nq);
+    for (int q = 0; q < nq; q++) p.complement[q] = (uint8_t)q;
+    std::vector<int64_t> gi(ref.size() + 1, 0), rows((size_t)nq * ref.size(), 0);
+    c2b_ref r; memset(&r, 0, sizeof r);
+    r.seq = ref.c_str(); r.len = (int32_t)ref.size(); r.gap_incentive = gi.data(); r.score_rows = rows.data();
+    r.include_idx = include_idx; r.n_include = n_include; r.min_aln_score = -1.0;
+    int rc = c2b_configure(e, &p, 1, &r);
+    if (rc) return rc;
+    DevBuf d_ops, d_n;
+    if ((rc = ensure(e, d_ops, 32 * 8)) || (rc = ensure(e, d_n, 4))) return rc;
+    const int32_t n32 = n_cols;
+    RTCHK(rt_h2d(d_ops.p, ops.data(), 32 * 8, e->stream));
+    RTCHK(rt_h2d(d_n.p, &n32, 4, e->stream));
+    e->forced_ops = (const uint64_t *)d_ops.p; e->forced_n = (const int32_t *)d_n.p;
+    int64_t off[2] = {0, (int64_t)read.size()};
+    c2b_read_rec rec;
+    rc = c2b_align_batch(e, (const uint8_t *)read.data(), off, 1, nullptr, nullptr, nullptr, &rec, out, nullptr, edits);
+    e->forced_ops = nullptr; e->forced_n = nullptr;
+    rt_free(d_ops.p); rt_free(d_n.p);
+    return rc;
+}
+
+// pinned host memory for callers that want full-speed copies (bench.py, the Python wrapper)
+void *c2b_host_alloc(size_t n)
+{
+#ifndef C2B_EMU
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, n ? n : 16, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+#else
+    return malloc(n ? n : 16);
+#endif
+}
+void c2b_host_free(void *p)
+{
+#ifndef C2B_EMU
+    if (p) cudaFreeHost(p);
+#else
+    free(p);
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+/*
+ * c2b200.h -- C ABI of the B200 align-and-classify engine (libc2b200.so).
+ *
+ * This is the drop-in boundary for CRISPResso2's per-read hot path.  The reference has no FFI of its own
+ * (its two native modules are Cython, called from Python); each entry point below names the reference
+ * interface it replaces (paths relative to the reference repository root).  Plain pointers and sizes only;
+ * no torch / Python types.  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Threading: an engine is owned by one host thread at a time.  All calls are synchronous unless suffixed
+ * _async.  Never create an engine in a process that will later fork() CUDA work (reference workers are
+ * forked by CRISPRessoCORE.py:1878-1896; the GPU path bypasses them).
+ */
+#ifndef C2B200_H
+#define C2B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C2B_MAX_Q        8      /* read alphabet size (codes 0..nq-1); DNA uses "ACGTN" */
+#define C2B_MAX_SEEDS    8      /* seeds tested per strand (args.aln_seed_count, default 5) */
+#define C2B_MAX_SEED_LEN 20
+#define C2B_MAX_REF_LEN  1024   /* amplicon length limit of this build */
+#define C2B_MAX_READ_LEN 512
+#define C2B_MAX_ALN_LEN  1024   /* I + J */
+#define C2B_MAX_REFS     32
+
+/* status codes */
+#define C2B_OK            0
+#define C2B_E_CUDA       -1
+#define C2B_E_ARG        -2
+#define C2B_E_LIMIT      -3     /* a length / range limit of this build is exceeded */
+#define C2B_E_STATE      -4
+
+/* c2b_params.flags  (CRISPRessoCORE.py:746-760, 780-785, 3998-4002) */
+#define C2B_F_IGNORE_SUBSTITUTIONS  1u
+#define C2B_F_IGNORE_INSERTIONS     2u
+#define C2B_F_IGNORE_DELETIONS      4u
+#define C2B_F_EXPAND_AMBIGUOUS      8u
+#define C2B_F_ASSIGN_FIRST         16u
+#define C2B_F_DISCARD_INDEL_READS  32u
+#define C2B_F_NO_STRAND_SEARCH     64u   /* global_align-only mode: forward strand, no seed test */
+
+typedef struct {
+    int32_t  gap_open;        /* args.needleman_wunsch_gap_open   (Align.pyx:104) */
+    int32_t  gap_extend;      /* args.needleman_wunsch_gap_extend */
+    int32_t  seed_count;      /* args.aln_seed_count */
+    int32_t  seed_min;        /* args.aln_seed_min   */
+    uint32_t flags;
+    int32_t  nq;              /* alphabet size */
+    char     alphabet[C2B_MAX_Q];   /* code -> ASCII, e.g. "ACGTN" */
+    uint8_t  complement[C2B_MAX_Q]; /* code -> code of the complementary base (CRISPRessoShared.py:399-403) */
+    int32_t  edit_cap;        /* edit-list slots per (read, winning reference); see c2b_edit */
+} c2b_params;
+
+/* One amplicon: the refs[ref_name] keys the hot path reads. */
+typedef struct {
+    const char    *seq;            /* refs[name]['sequence'] */
+    int32_t        len;
+    const int64_t *gap_incentive;  /* refs[name]['gap_incentive'], len+1 entries (CRISPRessoCORE.py:3205-3207) */
+    const int64_t *include_idx;    /* refs[name]['include_idxs'] */
+    int32_t        n_include;
+    double         min_aln_score;  /* refs[name]['min_aln_score'] */
+    const int64_t *score_rows;     /* [nq][len]: matrix[ord(seq[i]), ord(alphabet[q])] -- the aln_matrix
+                                      lookups of Align.pyx:212, tabulated per reference position by the host */
+    const char *const *fw_seeds;   /* refs[name]['fw_seeds'][:seed_count] */
+    const char *const *rc_seeds;   /* refs[name]['rc_seeds'][:seed_count] */
+    int32_t        n_seeds;
+} c2b_ref;
+
+/* Per (read, reference) alignment result: what global_align returns (Align.pyx:422-434) plus, when the
+ * reference is a best match, the scalar fields of find_indels_substitutions / get_new_variant_object
+ * (COREResources.pyx:161-186, CRISPRessoCORE.py:726-760). 32 bytes. */
+typedef struct {
+    uint16_t n_match;          /* matchCount */
+    uint16_t aln_len;          /* alignment columns */
+    int32_t  score_milli;      /* round(100*n_match/aln_len, 3) * 1000, exact (half-even) */
+    uint8_t  strand;           /* 0 '+', 1 '-' */
+    uint8_t  status;           /* 0 ok; C2B_ST_* bits otherwise */
+    uint16_t n_edits;          /* edit-list entries produced (may exceed edit_cap: then C2B_ST_EDIT_OVERFLOW) */
+    uint16_t insertion_n, deletion_n, substitution_n;          /* inside the quantification window */
+    uint16_t n_ins_all, n_ins_win;        /* insertion runs: all / in window  */
+    uint16_t n_del_all, n_del_win;        /* deletion runs */
+    uint16_t n_del_pos_all;               /* len(all_deletion_positions) */
+    uint16_t n_sub_all;                   /* len(all_substitution_positions) */
+    uint8_t  irregular_ends;
+    uint8_t  modified;                    /* classification == 'MODIFIED' */
+} c2b_aln_rec;
+
+#define C2B_ST_BAD_CHAR       1u   /* read holds a symbol outside the alphabet */
+#define C2B_ST_UNDEFINED      2u   /* traceback left the zone where the reference is defined */
+#define C2B_ST_EDIT_OVERFLOW  4u   /* more edits than edit_cap: counts excluded, rerun with a larger cap */
+#define C2B_ST_TOO_LONG       8u
+
+/* Per read: best-reference selection of get_new_variant_object (CRISPRessoCORE.py:690-716, 780-785). 16 bytes */
+typedef struct {
+    uint32_t winner_mask;      /* bit r set: reference r is in best_match_names (before assign-first trimming) */
+    int32_t  best_score_milli; /* best_match_score*1000 ; <= 0: not aligned */
+    int16_t  best_ref;         /* index of new_variant['best_match_name'] (last winner), -1 if none */
+    uint8_t  n_winners;
+    uint8_t  ambiguous;        /* class_name == 'AMBIGUOUS' */
+    uint32_t status;           /* OR of the per-alignment status bits */
+} c2b_read_rec;
+
+/* Edit list entry (8 bytes); expands on the host into the list fields of ResultsSlotsDict
+ * (COREResources.pyx:18-65).  Entries of one type appear in increasing reference position. */
+typedef struct {
+    uint16_t a;        /* SUB: position           INS: left flank (start)        DEL: start            */
+    uint16_t b;        /* SUB: unused             INS: size of the insertion     DEL: end (exclusive)  */
+    uint8_t  type;     /* 1 SUB, 2 INS, 3 DEL */
+    uint8_t  in_window;
+    uint8_t  base;     /* SUB: read base (ASCII) */
+    uint8_t  pad;
+} c2b_edit;
+
+/* Count block: int64 [n_refs][C2B_NVEC][stride] followed by [n_refs][C2B_NSCAL] scalars.
+ * Vectors follow CRISPRessoCORE.py:3865-3896 / the table in SURVEY.md 3.4. */
+enum {
+    C2B_V_ALL_INS = 0, C2B_V_ALL_INS_LEFT, C2B_V_ALL_DEL, C2B_V_ALL_SUB,
+    C2B_V_INS, C2B_V_DEL, C2B_V_SUB,
+    C2B_V_SUBBASE0,                    /* + alphabet code : all_substitution_base_vectors */
+    C2B_V_BASEDEV0 = C2B_V_SUBBASE0 + C2B_MAX_Q,   /* + code (nq = '-') : all_base_count deviation from "read == ref" */
+    C2B_V_INS_LEN = C2B_V_BASEDEV0 + C2B_MAX_Q + 1,
+    C2B_V_DEL_LEN,
+    C2B_NVEC
+};
+enum {
+    C2B_S_TOTAL = 0, C2B_S_MODIFIED, C2B_S_UNMODIFIED, C2B_S_DISCARDED,
+    C2B_S_INS, C2B_S_DEL, C2B_S_SUB,
+    C2B_S_ONLY_INS, C2B_S_ONLY_DEL, C2B_S_ONLY_SUB, C2B_S_INS_DEL, C2B_S_INS_SUB, C2B_S_DEL_SUB, C2B_S_INS_DEL_SUB,
+    C2B_S_AMBIGUOUS_W,     /* weight of reads classed AMBIGUOUS with this reference as first winner */
+    /* aln_stats of process_fastq (CRISPRessoCORE.py:1988-1999), accumulated with the dedup count */
+    C2B_S_N_GLOBAL_SUBS, C2B_S_N_SUBS_OUTSIDE_WINDOW, C2B_S_N_MODS_IN_WINDOW, C2B_S_N_MODS_OUTSIDE_WINDOW,
+    C2B_S_N_READS_IRREGULAR_ENDS, C2B_S_N_ALIGNED_UNIQUE, C2B_S_N_ALIGNED_COUNT,
+    C2B_NSCAL
+};
+
+typedef struct c2b_engine c2b_engine;
+
+/* lifecycle -------------------------------------------------------------------------------------------- */
+int  c2b_create(int device, c2b_engine **out);
+void c2b_destroy(c2b_engine *e);
+const char *c2b_last_error(const c2b_engine *e);   /* e may be NULL: error of the last failed c2b_create */
+
+/* replaces: the args/refs plumbing of process_fastq (CRISPRessoCORE.py:1735, :1811-1813) */
+int  c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_ref *refs);
+
+/* Changes c2b_params.edit_cap for the following batches without touching tables or counts (used to re-run
+ * the few reads whose edit list overflowed with a cap that cannot overflow). */
+int  c2b_set_edit_cap(c2b_engine *e, int32_t edit_cap);
+
+/* Output geometry for a batch whose longest read is max_read_len:
+ *   string width W (multiple of 16): every aligned string is right-aligned in a W-byte slot;
+ *   alns    : n_reads * n_refs records, [read][ref]
+ *   strings : n_reads * n_refs * 2 * W bytes, [read][ref][0 = read, 1 = reference][W]
+ *   edits   : n_reads * n_refs * edit_cap entries                                                  */
+int  c2b_string_width(const c2b_engine *e, int32_t max_read_len);
+
+/* replaces: the serial loop of process_fastq over unique reads (CRISPRessoCORE.py:1956-1981), i.e. one
+ * get_new_variant_object (:627-798) per read = seed test, global_align per strand and reference,
+ * best-reference choice, find_indels_substitutions per winner, and the per-read part of the
+ * quantification loop (:3964-4115).  Host buffers in, host buffers out (copies inside).
+ *   reads/offsets : packed ASCII reads, offsets[n_reads+1]
+ *   count         : dedup multiplicity per read (variant_count of :1957)          (NULL = 1)
+ *   qweight       : count after the reverse-complement merge of :3971-3975        (NULL = count)
+ *   ref_id        : NULL = try every reference; else the single reference index of each read (Pooled)
+ *   strings/edits may be NULL (not produced).                                                         */
+int  c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads,
+                     const int32_t *count, const int32_t *qweight, const int32_t *ref_id,
+                     c2b_read_rec *recs, c2b_aln_rec *alns, uint8_t *strings, c2b_edit *edits);
+
+/* Same, with every pointer a DEVICE pointer on the engine's device and no copies; the launch is queued on
+ * the engine's stream.  max_read_len must bound the reads.  Use c2b_sync() before reading results.     */
+int  c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t *d_offsets, int64_t n_reads,
+                            int32_t max_read_len, const int32_t *d_count, const int32_t *d_qweight,
+                            const int32_t *d_ref_id, c2b_read_rec *d_recs, c2b_aln_rec *d_alns,
+                            uint8_t *d_strings, c2b_edit *d_edits);
+int  c2b_sync(c2b_engine *e);
+void *c2b_stream(c2b_engine *e);                    /* cudaStream_t of the engine */
+double c2b_last_kernel_ms(c2b_engine *e);           /* CUDA-event time of the last align kernel launch */
+int64_t c2b_launch_count(const c2b_engine *e);      /* kernels launched by this engine so far */
+
+/* replaces: the count vectors / counters built by the quantification loop (CRISPRessoCORE.py:3841-3907,
+ * :3964-4115).  Layout above.  c2b_counts_device exposes the block for an NCCL all-reduce.            */
+int  c2b_counts_layout(const c2b_engine *e, int32_t *n_refs, int32_t *n_vec, int32_t *stride, int32_t *n_scal);
+int  c2b_counts_reset(c2b_engine *e);
+int  c2b_counts_read(c2b_engine *e, int64_t *out, size_t n_int64);
+int  c2b_counts_device(c2b_engine *e, void **d_ptr, size_t *n_int64);
+
+/* replaces: CRISPResso2Align.global_align (Align.pyx:101-434), one pair, forward strand only.
+ * score_rows as in c2b_ref.  out_read/out_ref need read_len+ref_len bytes; returns C2B_OK or a status.  */
+int  c2b_global_align(c2b_engine *e, const char *read, int32_t read_len, const char *ref, int32_t ref_len,
+                      const char *alphabet, int32_t nq, const int64_t *score_rows, const int64_t *gap_incentive,
+                      int32_t gap_open, int32_t gap_extend,
+                      char *out_read, char *out_ref, int32_t *aln_len, int32_t *n_match);
+
+/* replaces: CRISPRessoCOREResources.find_indels_substitutions (COREResources.pyx:68-187) for ONE aligned
+ * pair that obeys the aligner's invariants (no column with two gaps, no insertion column adjacent to a
+ * deletion column).  Runs the same row-classification kernel as the batch path.  Reconfigures the engine.
+ * edits must hold n_cols+1 entries.  Returns C2B_E_ARG when the pair violates the invariants.        */
+int  c2b_classify_aligned(c2b_engine *e, const char *read_al, const char *ref_al, int32_t n_cols,
+                          const char *alphabet, int32_t nq, const int64_t *include_idx, int32_t n_include,
+                          c2b_aln_rec *out, c2b_edit *edits);
+
+/* pinned host memory (cudaHostAlloc) for callers that want full-speed host<->device copies */
+void *c2b_host_alloc(size_t n_bytes);
+void  c2b_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

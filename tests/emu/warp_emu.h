@@ -1,0 +1,93 @@
+// warp_emu.h -- TEST INFRASTRUCTURE: a 32-fiber lock-step emulator of one CUDA warp, so that
+// crispresso2_b200/csrc/c2b_core.cuh (the real kernel logic) can be compiled with g++ and checked against the
+// oracle on a box without a GPU.  Never shipped, never loaded by the product package.
+//
+// Each lane is a ucontext fiber; a warp collective writes the lane's value into a double-buffered slot array,
+// yields round-robin, and reads the peers' values when control returns.  A tag per collective asserts that all
+// lanes reached the same kind of collective (a divergence there would be undefined behaviour on the GPU).
+#pragma once
+#include <algorithm>
+#include <cassert>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <ucontext.h>
+
+#define C2B_DEV static inline
+#define C2B_DEVNOINL static
+struct int4 { int x, y, z, w; };
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { uint4 r = {a, b, c, d}; return r; }
+
+namespace emu {
+struct Warp {
+    ucontext_t main_ctx, ctx[32];
+    char *stacks[32];
+    bool done[32];
+    int cur = 0;
+    uint64_t slot[2][32]; int tag[2][32]; unsigned cnt[32];
+    std::function<void()> body;
+};
+extern thread_local Warp *g_warp;
+static void fiber_entry() { g_warp->body(); g_warp->done[g_warp->cur] = true; swapcontext(&g_warp->ctx[g_warp->cur], &g_warp->main_ctx); }
+inline void yield() { Warp *w = g_warp; swapcontext(&w->ctx[w->cur], &w->main_ctx); }
+inline void run_warp(const std::function<void()> &fn)
+{
+    static thread_local Warp *W = nullptr;
+    if (!W) { W = new Warp(); for (int l = 0; l < 32; l++) W->stacks[l] = (char *)malloc(1 << 19); }
+    g_warp = W; W->body = fn;
+    for (int l = 0; l < 32; l++) {
+        getcontext(&W->ctx[l]); W->ctx[l].uc_stack.ss_sp = W->stacks[l]; W->ctx[l].uc_stack.ss_size = 1 << 19;
+        W->ctx[l].uc_link = &W->main_ctx; makecontext(&W->ctx[l], fiber_entry, 0);
+        W->done[l] = false; W->cnt[l] = 0;
+    }
+    bool any = true;
+    while (any) {
+        any = false;
+        for (int l = 0; l < 32; l++) if (!W->done[l]) { W->cur = l; swapcontext(&W->main_ctx, &W->ctx[l]); any = true; }
+    }
+}
+inline uint64_t exchange(uint64_t v, int kind, int src_lane_fn(int, int), int arg)
+{
+    Warp *w = g_warp; const int l = w->cur; const int b = w->cnt[l] & 1;
+    w->slot[b][l] = v; w->tag[b][l] = kind; w->cnt[l]++;
+    yield();
+    for (int q = 0; q < 32; q++) {
+        if (w->cnt[q] < w->cnt[l]) { fprintf(stderr, "warp_emu: lane %d did not reach a collective (kind %d) that lane %d executes\n", q, kind, l); abort(); }
+        if (w->tag[b][q] != kind) { fprintf(stderr, "warp_emu: divergent collective (lane %d kind %d vs %d)\n", q, w->tag[b][q], kind); abort(); }
+    }
+    const int s = src_lane_fn(l, arg);
+    return w->slot[b][s];
+}
+}  // namespace emu
+
+namespace wp {
+C2B_DEV int lane() { return emu::g_warp->cur; }
+C2B_DEV int shfl_up(int v, int d) { return (int)(uint32_t)emu::exchange((uint32_t)v, 1, [](int l, int a) { return l >= a ? l - a : l; }, d); }
+C2B_DEV int shfl(int v, int src) { return (int)(uint32_t)emu::exchange((uint32_t)v, 2, [](int, int a) { return a & 31; }, src); }
+C2B_DEV uint32_t shflu(uint32_t v, int src) { return (uint32_t)emu::exchange(v, 2, [](int, int a) { return a & 31; }, src); }
+C2B_DEV int shfl_xor(int v, int m) { return (int)(uint32_t)emu::exchange((uint32_t)v, 3, [](int l, int a) { return (l ^ a) & 31; }, m); }
+C2B_DEV uint32_t ballot(bool p)
+{
+    emu::Warp *w = emu::g_warp; const int l = w->cur; const int b = w->cnt[l] & 1;
+    emu::exchange(p ? 1 : 0, 4, [](int l2, int) { return l2; }, 0);
+    uint32_t m = 0; for (int q = 0; q < 32; q++) if (w->slot[b][q]) m |= 1u << q;
+    return m;
+}
+C2B_DEV void sync() { emu::exchange(0, 5, [](int l, int) { return l; }, 0); }
+C2B_DEV int max3(int a, int b, int c) { return std::max(a, std::max(b, c)); }
+C2B_DEV int addmax(int a, int b, int c) { return std::max(a + b, c); }
+C2B_DEV int popc(uint32_t x) { return __builtin_popcount(x); }
+C2B_DEV int popcll(uint64_t x) { return __builtin_popcountll(x); }
+C2B_DEV int clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+C2B_DEV int ffs(uint32_t x) { return __builtin_ffs((int)x); }
+C2B_DEV uint32_t ldcg(const uint32_t *p) { return *p; }
+C2B_DEV int ldcgi(const int *p) { return *p; }
+C2B_DEV uint64_t ldcg64(const uint64_t *p) { return *p; }
+C2B_DEV int4 ldg4(const int4 *p) { return *p; }
+C2B_DEV void addg(unsigned long long *p, long long v) { *p += (unsigned long long)v; }
+C2B_DEV uint32_t adds(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
+C2B_DEV unsigned long long fetch_work(unsigned long long *p) { return (*p)++; }
+}  // namespace wp
