@@ -135,19 +135,20 @@ C2B_DEV void dp_block(const KParams &P, const RefDev &R, const uint8_t *codes, i
     else { pM = NEG4; pX = NEG4 | 2; pY = (ge4 * rowbase + R.gi0_4) | 1; }
 
     const int nsteps = J + nl - 1;
-    const int32_t *prof0 = R.prof + r0;
-    uint32_t *tbw = tb + ((int64_t)rb * P.TS) * 32 + lane;
+    const int32_t *__restrict__ prof0 = R.prof + r0;
+    uint32_t *__restrict__ tbw = tb + ((int64_t)rb * P.TS) * 32 + lane;
+    const int Ipad = R.Ipad, gi0_4 = R.gi0_4;          // hoisted: the loop stores through tb, keep these in registers
 
     for (int t = 1; t <= nsteps; t++) {
         int uM = wp::shfl_up(M[7], 1), uX = wp::shfl_up(X[7], 1), uY = wp::shfl_up(Y[7], 1);
         const int j = t - lane;
         if (lane == 0) {
-            if (rb == 0) { uM = NEG4; uX = (ge4 * j + R.gi0_4) | 2; uY = NEG4 | 1; }     // row 0
-            else if (j <= J) { uM = bnd_in[3 * j]; uX = bnd_in[3 * j + 1]; uY = bnd_in[3 * j + 2]; }
+            if (rb == 0) { uM = NEG4; uX = (ge4 * j + gi0_4) | 2; uY = NEG4 | 1; }       // row 0
+            else if (j <= J) { uM = wp::ldcgi(bnd_in + 3 * j); uX = wp::ldcgi(bnd_in + 3 * j + 1); uY = wp::ldcgi(bnd_in + 3 * j + 2); }
         }
         if (j >= 1 && j <= J && lane < nl) {
             const int q = codes[j - 1];
-            const int4 *pp = reinterpret_cast<const int4 *>(prof0 + q * R.Ipad);
+            const int4 *pp = reinterpret_cast<const int4 *>(prof0 + q * Ipad);
             const int4 sa = wp::ldg4(pp), sb = wp::ldg4(pp + 1);
             const int s[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
             const int dcol = (j == J) ? 0 : d4;             // free opening in the last column (Align.pyx:234-273)

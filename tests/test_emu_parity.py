@@ -42,3 +42,56 @@ def test_align_vectors(emu):
         a, ed = emu.classify_pair(c["s1"], c["s2"], c["inc"])
         p = resources.payload_from_device(a, ed, c["s1"], c["s2"])
         assert not G.payload_equal(c["payload"], p), (c, p.__dict__)
+
+
+@pytest.mark.parametrize("flags", [{}, {"ignore_substitutions": True}, {"discard_indel_reads": True},
+                                   {"ignore_deletions": True, "ignore_insertions": True}])
+def test_seeded_batch_against_oracle(emu, flags):
+    rng = np.random.default_rng(11)
+    amp = synth.random_amplicon(rng, 250)
+    ref = synth.amplicon_setup(amp)
+    reads = synth.synth_reads(rng, amp, 150, 250, sub_rate=0.01, rc_frac=0.08, n_rate=0.002, cut=ref["cut_point"])
+    reads = [r.tobytes().decode() for r in reads] + ["".join(rng.choice(list("ACGT"), 250)) for _ in range(3)]
+    PU.check_against_oracle(emu, {"Reference": ref}, ["Reference"], O.Params(**flags), reads, O.make_matrix())
+
+
+def test_ragged_and_long_inputs_against_oracle(emu):
+    """Read lengths 30..400, a 300-bp amplicon (two row blocks), a wide quantification window."""
+    rng = np.random.default_rng(5)
+    amp = synth.random_amplicon(rng, 300)
+    ref = synth.amplicon_setup(amp, guide_start=140, window_size=20)
+    reads = []
+    for _ in range(60):
+        L = int(rng.integers(30, 401))
+        s = synth.synth_reads(rng, amp, 1, 300, sub_rate=0.02, cut=ref["cut_point"])[0].tobytes().decode()
+        s = (s + "".join(rng.choice(list("ACGT"), 120)))[:L]
+        reads.append(s)
+    PU.check_against_oracle(emu, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
+
+
+def test_three_amplicons_and_ambiguity_flags(emu):
+    rng = np.random.default_rng(3)
+    amp = synth.random_amplicon(rng, 120)
+    hdr = amp[:60] + "TGA" + amp[63:68] + "ACGTAC" + amp[68:]
+    snp = list(amp)
+    for p in (20, 50, 70, 100):
+        snp[p] = "A" if snp[p] != "A" else "C"
+    snp = "".join(snp)
+    refs = {"WT": synth.amplicon_setup(amp, guide_start=45), "HDR": synth.amplicon_setup(hdr, guide_start=45),
+            "SNP": synth.amplicon_setup(snp, guide_start=45), "WT2": synth.amplicon_setup(amp, guide_start=45)}
+    names = ["WT", "HDR", "SNP", "WT2"]
+    reads = []
+    for a in (amp, hdr, snp):
+        reads += [r.tobytes().decode() for r in synth.synth_reads(rng, a, 40, 120, sub_rate=0.01, rc_frac=0.1, cut=62)]
+    for kw in ({}, {"expand_ambiguous_alignments": True}, {"assign_ambiguous_alignments_to_first_reference": True}):
+        PU.check_against_oracle(emu, refs, names, O.Params(**kw), reads, O.make_matrix())
+
+
+def test_bad_symbols_and_empty(emu):
+    rng = np.random.default_rng(1)
+    amp = synth.random_amplicon(rng, 120)
+    ref = synth.amplicon_setup(amp, guide_start=50)
+    emu.configure({"Reference": ref}, ["Reference"], O.make_matrix(), -20, -2)
+    assert len(emu.align([]).recs) == 0
+    res = emu.align([amp, amp[:50] + "x" + amp[51:]])
+    assert res.recs["status"][0] == 0 and res.recs["status"][1] == _lib.ST_BAD_CHAR

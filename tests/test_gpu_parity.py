@@ -1,0 +1,154 @@
+"""Parity tests proper: the sm_100a build of the engine, called through the C ABI, against the reference goldens,
+the oracle on seeded inputs, and size-independent properties at the benchmark's full size."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+import golden_util as G
+import parity_util as PU
+from crispresso2_b200 import _lib, align, resources, synth
+from crispresso2_b200.engine import Engine, pack_reads
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return Engine(0)
+
+
+@pytest.mark.parametrize("case", G.CASES)
+def test_golden_whole_path(eng, case, tmp_path):
+    PU.check_golden_case(eng, case, tmp_path)
+
+
+def test_align_vectors_and_classify_kats(eng):
+    with gzip.open(os.path.join(G.GOLD, "align_vectors.json.gz"), "rt") as fh:
+        cases = json.load(fh)
+    m = O.make_matrix()
+    for c in cases:
+        got = align.global_align(c["read"], c["ref"], m, np.array(c["gi"], dtype=np.int64), c["go"], c["ge"], engine=eng)
+        assert got == (c["s1"], c["s2"], c["score"]), c
+        a, ed = eng.classify_pair(c["s1"], c["s2"], c["inc"])
+        assert not G.payload_equal(c["payload"], resources.payload_from_device(a, ed, c["s1"], c["s2"]))
+
+
+def test_reference_kats_through_the_dropin_names(eng):
+    """The reference's own known-answer tests (tests/unit_tests/test_CRISPResso2Align.py) read the same here."""
+    m = O.make_matrix()
+    Z = lambda n: np.zeros(n, dtype=np.int64)
+    assert align.global_align("ATTA", "ATTA", matrix=m, gap_incentive=Z(5), engine=eng) == ("ATTA", "ATTA", 100.0)
+    assert align.global_align("ANNG", "ATCG", matrix=m, gap_incentive=Z(5), engine=eng) == ("A-NNG", "ATC-G", 40.0)
+    assert align.global_align("AAAA", "TTTT", matrix=m, gap_incentive=Z(5), engine=eng) == ("---AAAA", "TTTT---", 0.0)
+    assert align.global_align("A", "A", matrix=m, gap_incentive=Z(2), engine=eng) == ("A", "A", 100.0)
+    gi = Z(6); gi[2] = 1
+    assert align.global_align("ATTA", "ATTTA", matrix=m, gap_incentive=gi, engine=eng)[:2] == ("AT-TA", "ATTTA")
+    assert align.global_align("ATTA", "ATTTA", matrix=m, gap_incentive=Z(5), engine=eng) == 0      # length mismatch
+
+
+@pytest.mark.parametrize("flags", [{}, {"ignore_substitutions": True}, {"discard_indel_reads": True},
+                                   {"ignore_deletions": True, "ignore_insertions": True}])
+def test_seeded_batch_against_oracle(eng, flags):
+    rng = np.random.default_rng(11)
+    amp = synth.random_amplicon(rng, 250)
+    ref = synth.amplicon_setup(amp)
+    reads = synth.synth_reads(rng, amp, 1200, 250, sub_rate=0.01, rc_frac=0.08, n_rate=0.002, cut=ref["cut_point"])
+    reads = [r.tobytes().decode() for r in reads] + ["".join(rng.choice(list("ACGT"), 250)) for _ in range(10)]
+    PU.check_against_oracle(eng, {"Reference": ref}, ["Reference"], O.Params(**flags), reads, O.make_matrix())
+
+
+def test_ragged_and_long_inputs_against_oracle(eng):
+    """Read lengths 30..400, a 300-bp amplicon (two row blocks), a wide quantification window."""
+    rng = np.random.default_rng(5)
+    amp = synth.random_amplicon(rng, 300)
+    ref = synth.amplicon_setup(amp, guide_start=140, window_size=20)
+    reads = []
+    for _ in range(300):
+        L = int(rng.integers(30, 401))
+        s = synth.synth_reads(rng, amp, 1, 300, sub_rate=0.02, cut=ref["cut_point"])[0].tobytes().decode()
+        s = (s + "".join(rng.choice(list("ACGT"), 120)))[:L]
+        reads.append(s)
+    PU.check_against_oracle(eng, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
+
+
+def test_three_amplicons_and_ambiguity_flags(eng):
+    rng = np.random.default_rng(3)
+    amp = synth.random_amplicon(rng, 200)
+    hdr = amp[:100] + "TGA" + amp[103:108] + "ACGTAC" + amp[108:]
+    snp = list(amp)
+    for p in (20, 60, 110, 150, 180):
+        snp[p] = "A" if snp[p] != "A" else "C"
+    snp = "".join(snp)
+    refs = {"WT": synth.amplicon_setup(amp, guide_start=85), "HDR": synth.amplicon_setup(hdr, guide_start=85),
+            "SNP": synth.amplicon_setup(snp, guide_start=85), "WT2": synth.amplicon_setup(amp, guide_start=85)}
+    names = ["WT", "HDR", "SNP", "WT2"]       # WT2 == WT: every WT read is ambiguous
+    reads = []
+    for a in (amp, hdr, snp):
+        reads += [r.tobytes().decode() for r in synth.synth_reads(rng, a, 150, 200, sub_rate=0.01, rc_frac=0.1, cut=102)]
+    for kw in ({}, {"expand_ambiguous_alignments": True}, {"assign_ambiguous_alignments_to_first_reference": True}):
+        PU.check_against_oracle(eng, refs, names, O.Params(**kw), reads, O.make_matrix())
+
+
+def test_full_size_properties(eng):
+    """1M x 250 bp (the benchmark workload): properties that need no oracle run."""
+    rng = np.random.default_rng(42)
+    amp = synth.random_amplicon(rng, 250)
+    ref = synth.amplicon_setup(amp)
+    n = 1 << 20
+    reads = synth.synth_reads_fast(rng, amp, n, 250, cut=ref["cut_point"])
+    eng.configure({"Reference": ref}, ["Reference"], O.make_matrix(), -20, -2, 5, 2, 0, "ACGTN", 8)
+    eng.counts_reset()
+    off = np.arange(n + 1, dtype=np.int64) * 250
+    res = eng.align_packed(reads.reshape(-1), off)
+    a = res.alns[:, 0]
+    assert (res.recs["status"] & ~np.uint32(_lib.ST_EDIT_OVERFLOW)).max() == 0
+    # (1) stripping gaps from the aligned read gives back the read; from the aligned reference, the amplicon
+    S = res.strings[:, 0]
+    W = res.W
+    cols = np.arange(W)[None, :] >= (W - a["aln_len"].astype(np.int64))[:, None]
+    rd = S[:, 0, :]
+    rf = S[:, 1, :]
+    keep_r = cols & (rd != ord("-"))
+    assert (keep_r.sum(1) == 250).all()
+    assert (rd[keep_r].reshape(n, 250) == reads).all()
+    keep_f = cols & (rf != ord("-"))
+    assert (keep_f.sum(1) == 250).all()
+    assert (rf[keep_f].reshape(n, 250) == np.frombuffer(amp.encode(), dtype=np.uint8)[None, :]).all()
+    # (2) match count and score recomputed from the strings
+    m = (cols & (rd == rf)).sum(1)
+    assert (m == a["n_match"]).all()
+    # (3) no column holds two gaps; an insertion column never touches a deletion column
+    assert not (cols & (rd == ord("-")) & (rf == ord("-"))).any()
+    ins, dele = cols & (rf == ord("-")), cols & (rd == ord("-"))
+    assert not (ins[:, 1:] & dele[:, :-1]).any() and not (ins[:, :-1] & dele[:, 1:]).any()
+    # (4) count block: every position is covered exactly once per counted read
+    blk = eng.counts()
+    V = blk.vectors("Reference")
+    tot = blk.scalar("Reference", "TOTAL")
+    assert tot == int((res.recs["best_score_milli"] > 0).sum())
+    cover = sum(V["all_base_count_" + b] for b in "ACGTN-")
+    assert (cover == tot).all()
+    assert (V["all_deletion_count"] == V["all_base_count_-"]).all()
+    assert blk.scalar("Reference", "MODIFIED") + blk.scalar("Reference", "UNMODIFIED") == tot
+    assert blk.scalar("Reference", "MODIFIED") == int(a["modified"][res.recs["best_score_milli"] > 0].sum())
+    # (5) batch-composition independence: a shuffled sub-batch reproduces its records bit for bit
+    pick = rng.permutation(n)[:50000]
+    eng.counts_reset()
+    res2 = eng.align_packed(reads[pick].reshape(-1), np.arange(len(pick) + 1, dtype=np.int64) * 250)
+    assert (res2.alns[:, 0] == res.alns[pick, 0]).all()
+    assert (res2.strings == res.strings[pick]).all()
+
+
+def test_empty_batch_and_bad_symbols(eng):
+    rng = np.random.default_rng(1)
+    amp = synth.random_amplicon(rng, 120)
+    ref = synth.amplicon_setup(amp, guide_start=50)
+    eng.configure({"Reference": ref}, ["Reference"], O.make_matrix(), -20, -2)
+    res = eng.align([])
+    assert len(res.recs) == 0
+    res = eng.align([amp, amp[:50] + "x" + amp[51:], amp.lower()[:60]])
+    assert res.recs["status"][0] == 0 and res.recs["status"][1] == _lib.ST_BAD_CHAR and res.recs["status"][2] == _lib.ST_BAD_CHAR
