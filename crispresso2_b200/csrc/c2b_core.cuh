@@ -39,6 +39,7 @@ C2B_DEV uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 C2B_DEV void sync() { __syncwarp(); }
 C2B_DEV int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 C2B_DEV int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }   // max(a+b, c)
+C2B_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }   // (hi:lo) >> sh
 C2B_DEV int popc(uint32_t x) { return __popc(x); }
 C2B_DEV int popcll(uint64_t x) { return __popcll(x); }
 C2B_DEV int clz(uint32_t x) { return __clz(x); }
@@ -106,16 +107,19 @@ struct WarpSmem {
 struct Walked { uint64_t ops; int n; int err; };
 
 // ------------------------------------------------------------------------------------------------ DP
+// Traceback word of (lane l, column j): bits [16+2k, 17+2k] = origin of M[i][j] (0 M, 1 J, 2 I) and bits
+// [2k, 2k+1] = (bit 1: I[i][j] extends an I gap, bit 0: J[i][j] extends a J gap) for row i = 8l+k+1.
 template <int KSTAR>
-C2B_DEV void dp_block(const KParams &P, const RefDev &R, const uint8_t *codes, int J, int rb, int NEG4,
-                      uint32_t *tb, const int32_t *bnd_in, int32_t *bnd_out, int &cM, int &cX, int &cY)
+C2B_DEV void dp_block(const KParams &P, const RefDev &R, const uint8_t *codes, const int J, const int rb, const int NEG4,
+                      uint32_t *__restrict__ tb, const int32_t *bnd_in, int32_t *bnd_out, int &cM, int &cX, int &cY)
 {
     const int lane = wp::lane();
-    const bool lastblk = (rb == R.nrb - 1);
-    const int nl = lastblk ? R.lstar + 1 : 32;
+    const int nrb = R.nrb, lstar = R.lstar, Ipad = R.Ipad, gi0_4 = R.gi0_4;
+    const bool lastblk = (rb == nrb - 1);
+    const int nl = lastblk ? lstar + 1 : 32;
     const int rowbase = rb * 256;
     const int r0 = rowbase + 8 * lane;
-    const bool islast = lastblk && lane == R.lstar;
+    const bool islast = lastblk && lane == lstar;
     const int ge4 = 4 * P.ge, d4 = 4 * (P.go - P.ge);
 
     int M[8], X[8], Y[8], cIe[8], g4[8];
@@ -128,25 +132,26 @@ C2B_DEV void dp_block(const KParams &P, const RefDev &R, const uint8_t *codes, i
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) {          // column 0 (Align.pyx:153-176)
-        M[k] = NEG4; X[k] = NEG4 | 2; Y[k] = (ge4 * (r0 + k + 1) + R.gi0_4) | 1;
+        M[k] = NEG4; X[k] = NEG4 | 2; Y[k] = (ge4 * (r0 + k + 1) + gi0_4) | 1;
     }
     int pM, pX, pY;                         // row above my first row, previous column (the diagonal of k=0)
     if (rb == 0) { pM = 0; pX = NEG4 | 2; pY = NEG4 | 1; }
-    else { pM = NEG4; pX = NEG4 | 2; pY = (ge4 * rowbase + R.gi0_4) | 1; }
+    else { pM = NEG4; pX = NEG4 | 2; pY = (ge4 * rowbase + gi0_4) | 1; }
 
     const int nsteps = J + nl - 1;
     const int32_t *__restrict__ prof0 = R.prof + r0;
     uint32_t *__restrict__ tbw = tb + ((int64_t)rb * P.TS) * 32 + lane;
-    const int Ipad = R.Ipad, gi0_4 = R.gi0_4;          // hoisted: the loop stores through tb, keep these in registers
+    const bool lane_on = lane < nl;
+    int topX = gi0_4 | 2;                   // row 0: X[0][j] = 4*(ge*j + gi0) | 2, advanced by one column per step
 
     for (int t = 1; t <= nsteps; t++) {
         int uM = wp::shfl_up(M[7], 1), uX = wp::shfl_up(X[7], 1), uY = wp::shfl_up(Y[7], 1);
         const int j = t - lane;
         if (lane == 0) {
-            if (rb == 0) { uM = NEG4; uX = (ge4 * j + gi0_4) | 2; uY = NEG4 | 1; }       // row 0
+            if (rb == 0) { topX += ge4; uM = NEG4; uX = topX; uY = NEG4 | 1; }
             else if (j <= J) { uM = wp::ldcgi(bnd_in + 3 * j); uX = wp::ldcgi(bnd_in + 3 * j + 1); uY = wp::ldcgi(bnd_in + 3 * j + 2); }
         }
-        if (j >= 1 && j <= J && lane < nl) {
+        if (lane_on && j >= 1 && j <= J) {
             const int q = codes[j - 1];
             const int4 *pp = reinterpret_cast<const int4 *>(prof0 + q * Ipad);
             const int4 sa = wp::ldg4(pp), sb = wp::ldg4(pp + 1);
@@ -155,34 +160,34 @@ C2B_DEV void dp_block(const KParams &P, const RefDev &R, const uint8_t *codes, i
             const int dsp = islast ? 0 : dcol;              // ... and in the last row (:277-317)
             int dM = pM, dX = pX, dY = pY;
             int upM = uM, upY = uY;
-            uint32_t word = 0;
+            uint32_t wT = 0, wIJ = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int dik = (k == KSTAR) ? dsp : dcol;
-                const int z = wp::max3(dM, dY, dX);                  // diagonal, tie order I > J > M
+                const int z = wp::max3(dM, dY, dX);                      // diagonal, tie order I > J > M
                 const int tag = z & 3;
                 const int nm = (z - tag) + s[k];
-                const int x = wp::addmax(M[k], dik, X[k]) + cIe[k];  // gap in reference ("I"), incentive of row i
+                const int x = wp::addmax(M[k], dik, X[k]) + cIe[k];      // gap in reference ("I"), incentive of row i
                 const int y = wp::addmax(upM, dik + g4[k], upY) + ge4;   // gap in read ("J"), incentive of row i-1 on open
-                const uint32_t nib = (uint32_t)tag | ((uint32_t)((x & 2) | (y & 1)) << 2);
-                word |= nib << (4 * k);
+                wT = wp::funnel_r(wT, (uint32_t)z, 2);                   // low two bits of z = origin of M
+                wIJ = wp::funnel_r(wIJ, (uint32_t)((x & 2) | (y & ~2)), 2);   // bit1: I extends, bit0: J extends
                 dM = M[k]; dX = X[k]; dY = Y[k];
                 M[k] = nm; X[k] = x | 2; Y[k] = y | 1;
                 upM = nm; upY = Y[k];
             }
-            tbw[(int64_t)t * 32] = word;
+            tbw[(int64_t)t * 32] = (wT & 0xffff0000u) | (wIJ >> 16);
             if (!lastblk && lane == 31) { bnd_out[3 * j] = M[7]; bnd_out[3 * j + 1] = X[7]; bnd_out[3 * j + 2] = Y[7]; }
         }
         pM = uM; pX = uX; pY = uY;
     }
     if (lastblk) {
         const int k = (KSTAR < 8) ? KSTAR : 0;
-        cM = wp::shfl(M[k], R.lstar); cX = wp::shfl(X[k], R.lstar); cY = wp::shfl(Y[k], R.lstar);
+        cM = wp::shfl(M[k], lstar); cX = wp::shfl(X[k], lstar); cY = wp::shfl(Y[k], lstar);
     }
 }
 
-C2B_DEVNOINL void dp_dispatch(const KParams &P, const RefDev &R, const uint8_t *codes, int J, int rb, int NEG4,
-                              uint32_t *tb, const int32_t *bi, int32_t *bo, int &cM, int &cX, int &cY)
+C2B_DEV void dp_dispatch(const KParams &P, const RefDev &R, const uint8_t *codes, int J, int rb, int NEG4,
+                         uint32_t *tb, const int32_t *bi, int32_t *bo, int &cM, int &cX, int &cY)
 {
     const int ks = (rb == R.nrb - 1) ? R.kstar : 8;
     switch (ks) {
@@ -201,50 +206,55 @@ C2B_DEVNOINL void dp_dispatch(const KParams &P, const RefDev &R, const uint8_t *
 // ------------------------------------------------------------------------------------------- traceback
 // Warp-uniform walk from (I,J) to (0,0) (Align.pyx:338-421).  Lane L ends up holding ops 32L..32L+31
 // (2 bits each, op n = n-th column from the RIGHT end of the alignment).
-C2B_DEVNOINL Walked walk(const KParams &P, const RefDev &R, int J, const uint32_t *tb, int s)
+C2B_DEV Walked walk(const KParams &P, const RefDev &R, const int J, const uint32_t *__restrict__ tb, int s)
 {
     const int lane = wp::lane();
-    Walked out; out.ops = ~0ull; out.err = 0;
-    int i = R.I, j = J, n = 0;
-    uint64_t acc = 0;
-    int wrb = -1, wl = -1, wj = 0; uint32_t wreg = 0;
-    while (i > 0 || j > 0) {
-        int op;
-        if (i == 0) { op = OP_I; if (s != OP_I) out.err = 1; j--; }
-        else if (j == 0) { op = OP_J; if (s != OP_J) out.err = 1; i--; }
-        else {
-            const int r = i - 1, rb = r >> 8, l = (r >> 3) & 31, k = r & 7;
-            if (rb != wrb || l != wl || wj - j >= 32) {         // refill the 32-column window of lane-row (rb,l)
-                wrb = rb; wl = l; wj = j;
-                const int cj = j - lane;
-                wreg = (cj >= 1) ? wp::ldcg(tb + ((int64_t)rb * P.TS + cj + l) * 32 + l) : 0u;
-            }
-            const uint32_t w = wp::shflu(wreg, wj - j);
-            const uint32_t nib = (w >> (4 * k)) & 15u;
-            op = s;
-            if (s == OP_M) { s = nib & 3; if (s == 3) { out.err = 1; s = OP_M; } }
-            else if (s == OP_J) s = (nib >> 2) & 1 ? OP_J : OP_M;
-            else s = (nib >> 3) & 1 ? OP_I : OP_M;
-            i -= (op != OP_I); j -= (op != OP_J);
+    const int TS = P.TS;
+    int i = R.I, j = J, n = 0, err = 0;
+    uint32_t acc = 0, lo = ~0u, hi = ~0u;
+    int wkey = -1, wj = 0; uint32_t wreg = 0;
+#define C2B_PUSH(op_)                                                                         \
+    do {                                                                                      \
+        acc = wp::funnel_r(acc, (uint32_t)(op_), 2); n++;                                     \
+        if ((n & 15) == 0) { const int ix = (n >> 4) - 1; if (lane == (ix >> 1)) { if (ix & 1) hi = acc; else lo = acc; } } \
+    } while (0)
+    while (i > 0 && j > 0) {
+        const int r = i - 1, key = r >> 3;
+        if (key != wkey || wj - j >= 32) {                 // refill the 32-column window of lane-row `key`
+            wkey = key; wj = j;
+            const int cj = j - lane, rb = key >> 5, l = key & 31;
+            wreg = (cj >= 1) ? wp::ldcg(tb + ((int64_t)rb * TS + cj + l) * 32 + l) : 0u;
         }
-        acc |= (uint64_t)op << (2 * (n & 31));
-        if ((n & 31) == 31) { if (lane == (n >> 5)) out.ops = acc; acc = 0; }
-        n++;
-        if (n >= C2B_MAX_ALN_LEN) { out.err = 1; break; }
+        const uint32_t v = wp::shflu(wreg, wj - j) >> (2 * (r & 7));
+        const int op = s;
+        s = (s == OP_M) ? (int)((v >> 16) & 3u) : (int)(v & (uint32_t)s);   // J keeps bit0, I keeps bit1 (= its own code)
+        err |= (s == 3);
+        i -= (op != OP_I); j -= (op != OP_J);
+        C2B_PUSH(op);
     }
-    if (n & 31) { acc |= ~0ull << (2 * (n & 31)); if (lane == (n >> 5)) out.ops = acc; }
-    out.n = n;
+    if (j > 0 && s != OP_I) err = 1;                        // row 0 can only be left along the I border (Align.pyx:153-176)
+    if (i > 0 && s != OP_J) err = 1;
+    while (j > 0) { j--; C2B_PUSH(OP_I); }
+    while (i > 0) { i--; C2B_PUSH(OP_J); }
+#undef C2B_PUSH
+    if (n & 15) {
+        const int ix = n >> 4, used = 2 * (n & 15);
+        const uint32_t a = (acc >> (32 - used)) | (~0u << used);
+        if (lane == (ix >> 1)) { if (ix & 1) hi = a; else lo = a; }
+    }
+    Walked out; out.ops = (uint64_t)lo | ((uint64_t)hi << 32); out.n = n; out.err = err;
     return out;
 }
 
 // Full alignment of one strand against one reference: DP over row blocks, then the walk.
-C2B_DEVNOINL Walked align_strand(const KParams &P, const RefDev &R, const uint8_t *codes, int J,
-                                 uint32_t *tb, int32_t *bnd)
+C2B_DEV Walked align_strand(const KParams &P, const RefDev &R, const uint8_t *codes, int J,
+                            uint32_t *tb, int32_t *bnd)
 {
     const int NEG4 = 4 * (int)((int64_t)P.go * J * R.I);        // sentinel of Align.pyx:150, scaled
     int cM = 0, cX = 0, cY = 0;
     const int bstride = 3 * (P.TS);
-    for (int rb = 0; rb < R.nrb; rb++) {
+    const int nrb = R.nrb;
+    for (int rb = 0; rb < nrb; rb++) {
         dp_dispatch(P, R, codes, J, rb, NEG4, tb, bnd + ((rb + 1) & 1) * bstride, bnd + (rb & 1) * bstride, cM, cX, cY);
         wp::sync();
     }
@@ -509,17 +519,17 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
             const int mode = P.forced_ops ? 0 : strand_mode(P, R, S, J);
             Walked wf; wf.ops = ~0ull; wf.n = 0; wf.err = 0;
             Walked wr = wf;
-            int mf = 0, mr = 0, sf = -1000000, sr = -1000000;
-            if (mode != 1) {
-                if (P.forced_ops) { wf.ops = P.forced_ops[rd * 32 + lane]; wf.n = P.forced_n[rd]; wf.err = 0; }
-                else wf = align_strand(P, R, S.fw, J, tb, bnd);
-                if (wf.err) a.status |= C2B_ST_UNDEFINED;
-                else if (mode == 2) { mf = columns(P, R, S, S.fw, J, wf.ops, wf.n, 0, nullptr, nullptr).n_match; sf = score_milli(mf, wf.n); }
-            }
-            if (mode != 0) {
-                wr = align_strand(P, R, S.rc, J, tb, bnd);
-                if (wr.err) a.status |= C2B_ST_UNDEFINED;
-                else if (mode == 2) { mr = columns(P, R, S, S.rc, J, wr.ops, wr.n, 0, nullptr, nullptr).n_match; sr = score_milli(mr, wr.n); }
+            int sf = -1000000, sr = -1000000;
+            for (int pass = 0; pass < 2; pass++) {              // one call site: forward, then reverse complement
+                if (pass == (mode == 1 ? 0 : mode == 0 ? 1 : 2)) continue;
+                const uint8_t *codes = pass ? S.rc : S.fw;
+                Walked wk;
+                if (P.forced_ops) { wk.ops = P.forced_ops[rd * 32 + lane]; wk.n = P.forced_n[rd]; wk.err = 0; }
+                else wk = align_strand(P, R, codes, J, tb, bnd);
+                int sc = -1000000;
+                if (wk.err) a.status |= C2B_ST_UNDEFINED;
+                else if (mode == 2) sc = score_milli(columns(P, R, S, codes, J, wk.ops, wk.n, 0, nullptr, nullptr).n_match, wk.n);
+                if (pass) { wr = wk; sr = sc; } else { wf = wk; sf = sc; }
             }
             if (!a.status) {
                 const bool use_rc = (mode == 1) || (mode == 2 && sr > sf);      // strict '>' of CRISPRessoCORE.py:682
@@ -553,7 +563,7 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
     }
     wp::sync();
 
-    if (rec.best_score_milli <= 0) { rec.winner_mask = 0; rec.n_winners = 0; }
+    if (rec.best_score_milli <= 0 && !P.forced_ops) { rec.winner_mask = 0; rec.n_winners = 0; }
     else {
         const bool expand = P.flags & C2B_F_EXPAND_AMBIGUOUS, first = P.flags & C2B_F_ASSIGN_FIRST;
         const bool ambiguous = rec.n_winners > 1 && !first && !expand;     // CRISPRessoCORE.py:780-785

@@ -27,6 +27,16 @@ static rt_err rt_h2d(void *d, const void *h, size_t n, rt_stream s) { return n ?
 static rt_err rt_d2h(void *h, const void *d, size_t n, rt_stream s) { return n ? cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) : cudaSuccess; }
 static rt_err rt_zero(void *d, size_t n, rt_stream s) { return cudaMemsetAsync(d, 0, n, s); }
 static rt_err rt_sync(rt_stream s) { return cudaStreamSynchronize(s); }
+typedef cudaEvent_t rt_event;
+static rt_err rt_event_create(rt_event *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); }
+static rt_err rt_event_destroy(rt_event e) { return cudaEventDestroy(e); }
+static rt_err rt_record(rt_event e, rt_stream s) { return cudaEventRecord(e, s); }
+static rt_err rt_wait(rt_stream s, rt_event e) { return cudaStreamWaitEvent(s, e, 0); }
+static rt_err rt_event_sync(rt_event e) { return cudaEventSynchronize(e); }
+static rt_err rt_stream_create(rt_stream *s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
+static rt_err rt_stream_destroy(rt_stream s) { return cudaStreamDestroy(s); }
+static void *rt_host_alloc(size_t n) { void *p = nullptr; return cudaHostAlloc(&p, n ? n : 16, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
+static void rt_host_free(void *p) { if (p) cudaFreeHost(p); }
 #else
 typedef int rt_err;
 typedef int rt_stream;
@@ -39,6 +49,16 @@ static rt_err rt_h2d(void *d, const void *h, size_t n, rt_stream) { if (n) memcp
 static rt_err rt_d2h(void *h, const void *d, size_t n, rt_stream) { if (n) memcpy(h, d, n); return 0; }
 static rt_err rt_zero(void *d, size_t n, rt_stream) { memset(d, 0, n); return 0; }
 static rt_err rt_sync(rt_stream) { return 0; }
+typedef int rt_event;
+static rt_err rt_event_create(rt_event *e) { *e = 0; return 0; }
+static rt_err rt_event_destroy(rt_event) { return 0; }
+static rt_err rt_record(rt_event, rt_stream) { return 0; }
+static rt_err rt_wait(rt_stream, rt_event) { return 0; }
+static rt_err rt_event_sync(rt_event) { return 0; }
+static rt_err rt_stream_create(rt_stream *s) { *s = 0; return 0; }
+static rt_err rt_stream_destroy(rt_stream) { return 0; }
+static void *rt_host_alloc(size_t n) { return malloc(n ? n : 16); }
+static void rt_host_free(void *p) { free(p); }
 #endif
 
 // ----------------------------------------------------------------------------------------- kernel
@@ -86,8 +106,11 @@ struct c2b_engine {
     DevBuf tb, bnd, ops, work;
     int n_warps = 0, grid = 0;
     int scratch_TS = 0;
-    // staging for the host-pointer API
-    DevBuf s_reads, s_off, s_cnt, s_qw, s_rid, s_recs, s_alns, s_str, s_ed;
+    // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
+    struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed; int64_t *h_off = nullptr; size_t h_off_cap = 0;
+                   rt_event in_done, k_done, out_done; bool used = false; } stage[2];
+    rt_stream s_in = 0, s_out = 0;
+    bool pipe_ready = false;
     double last_ms = 0; int64_t launches = 0;
     const uint64_t *forced_ops = nullptr; const int32_t *forced_n = nullptr;
 #ifndef C2B_EMU
@@ -144,9 +167,15 @@ int c2b_create(int device, c2b_engine **out)
 void c2b_destroy(c2b_engine *e)
 {
     if (!e) return;
-    DevBuf *bufs[] = {&e->tb, &e->bnd, &e->ops, &e->work, &e->s_reads, &e->s_off, &e->s_cnt, &e->s_qw, &e->s_rid,
-                      &e->s_recs, &e->s_alns, &e->s_str, &e->s_ed};
+    DevBuf *bufs[] = {&e->tb, &e->bnd, &e->ops, &e->work};
     for (DevBuf *b : bufs) if (b->p) rt_free(b->p);
+    for (auto &st : e->stage) {
+        DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed};
+        for (DevBuf *b : sb) if (b->p) rt_free(b->p);
+        if (st.h_off) rt_host_free(st.h_off);
+        if (e->pipe_ready) { rt_event_destroy(st.in_done); rt_event_destroy(st.k_done); rt_event_destroy(st.out_done); }
+    }
+    if (e->pipe_ready) { rt_stream_destroy(e->s_in); rt_stream_destroy(e->s_out); }
     if (e->d_tables) rt_free(e->d_tables);
     if (e->d_counts) rt_free(e->d_counts);
 #ifndef C2B_EMU
@@ -295,6 +324,26 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
     if ((rc = ensure(e, e->ops, (size_t)e->n_warps * e->n_refs * 32 * 8))) return rc;
     if ((rc = ensure(e, e->work, 64))) return rc;
     e->scratch_TS = TS;
+#ifndef C2B_EMU
+    {   // Keep the traceback slab (written once, read back by the same warp microseconds later) resident in L2:
+        // persisting window over the slab, everything else on this stream streams through the rest of L2.
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
+            !getenv("C2B_NO_L2_PERSIST")) {
+            const size_t slab = (size_t)e->n_warps * e->max_nrb * TS * 32 * 4;
+            const size_t carve = std::min((size_t)prop.persistingL2CacheMaxSize, slab);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+            cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+            av.accessPolicyWindow.base_ptr = e->tb.p;
+            av.accessPolicyWindow.num_bytes = std::min(slab, (size_t)prop.accessPolicyMaxWindowSize);
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)std::max<size_t>(1, av.accessPolicyWindow.num_bytes));
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            cudaGetLastError();
+        }
+    }
+#endif
     return C2B_OK;
 }
 
@@ -383,45 +432,66 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
         maxJ = std::max(maxJ, L);
     }
     if (maxJ > C2B_MAX_READ_LEN) return fail(e, C2B_E_LIMIT, "c2b_align_batch: read longer than C2B_MAX_READ_LEN");
+    if (!e->pipe_ready) {
+        RTCHK(rt_stream_create(&e->s_in));
+        RTCHK(rt_stream_create(&e->s_out));
+        for (auto &st : e->stage) { RTCHK(rt_event_create(&st.in_done)); RTCHK(rt_event_create(&st.k_done)); RTCHK(rt_event_create(&st.out_done)); }
+        e->pipe_ready = true;
+    }
     const int W = (e->max_I + (int)maxJ + 31) & ~31;
     const int cap = edits ? e->prm.edit_cap : 0;
-    // chunk so that device staging stays bounded (strings dominate: n * n_refs * 2 * W bytes)
-    const int64_t per_read = (int64_t)e->n_refs * (2 * (int64_t)W * (strings ? 1 : 0) + (int64_t)cap * 8 + 32) + 16 + maxJ + 24;
-    int64_t chunk = std::max<int64_t>(1024, (int64_t)(1ll << 31) / per_read);
-    for (int64_t c0 = 0; c0 < n_reads; c0 += chunk) {
+    const int nr = e->n_refs;
+    // Chunks pipeline through two staging sets: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c.
+    const int64_t per_read = (int64_t)nr * (2 * (int64_t)W * (strings ? 1 : 0) + (int64_t)cap * 8 + 32) + 16 + maxJ + 24;
+    int64_t chunk = std::max<int64_t>(4096, std::min<int64_t>((int64_t)(768ll << 20) / per_read, 1 << 17));
+    if (n_reads < 4 * chunk) chunk = std::max<int64_t>(4096, (n_reads + 3) / 4);
+    for (auto &st : e->stage) st.used = false;
+    int rc = C2B_OK;
+    int64_t c0 = 0;
+    for (int ci = 0; c0 < n_reads; ci++, c0 += chunk) {
+        c2b_engine::Stage &st = e->stage[ci & 1];
         const int64_t n = std::min(chunk, n_reads - c0);
         const int64_t b0 = offsets[c0], b1 = offsets[c0 + n];
-        int rc;
-        if ((rc = ensure(e, e->s_reads, (size_t)(b1 - b0) + 16))) return rc;
-        if ((rc = ensure(e, e->s_off, (size_t)(n + 1) * 8))) return rc;
-        if ((rc = ensure(e, e->s_recs, (size_t)n * sizeof(c2b_read_rec)))) return rc;
-        if ((rc = ensure(e, e->s_alns, (size_t)n * e->n_refs * sizeof(c2b_aln_rec)))) return rc;
-        if (strings && (rc = ensure(e, e->s_str, (size_t)n * e->n_refs * 2 * W))) return rc;
-        if (cap && (rc = ensure(e, e->s_ed, (size_t)n * e->n_refs * cap * sizeof(c2b_edit)))) return rc;
-        if (count && (rc = ensure(e, e->s_cnt, (size_t)n * 4))) return rc;
-        if (qweight && (rc = ensure(e, e->s_qw, (size_t)n * 4))) return rc;
-        if (ref_id && (rc = ensure(e, e->s_rid, (size_t)n * 4))) return rc;
-        // offsets are rebased so that the chunk's reads start at 0
-        std::vector<int64_t> off(n + 1);
-        for (int64_t k = 0; k <= n; k++) off[k] = offsets[c0 + k] - b0;
-        RTCHK(rt_h2d(e->s_reads.p, reads + b0, (size_t)(b1 - b0), e->stream));
-        RTCHK(rt_h2d(e->s_off.p, off.data(), (size_t)(n + 1) * 8, e->stream));
-        if (count) RTCHK(rt_h2d(e->s_cnt.p, count + c0, (size_t)n * 4, e->stream));
-        if (qweight) RTCHK(rt_h2d(e->s_qw.p, qweight + c0, (size_t)n * 4, e->stream));
-        if (ref_id) RTCHK(rt_h2d(e->s_rid.p, ref_id + c0, (size_t)n * 4, e->stream));
-        RTCHK(rt_sync(e->stream));      // `off` is a stack-lifetime host buffer
-        rc = c2b_align_batch_device(e, (const uint8_t *)e->s_reads.p, (const int64_t *)e->s_off.p, n, (int32_t)maxJ,
-                                    count ? (const int32_t *)e->s_cnt.p : nullptr, qweight ? (const int32_t *)e->s_qw.p : nullptr,
-                                    ref_id ? (const int32_t *)e->s_rid.p : nullptr, (c2b_read_rec *)e->s_recs.p,
-                                    (c2b_aln_rec *)e->s_alns.p, strings ? (uint8_t *)e->s_str.p : nullptr,
-                                    cap ? (c2b_edit *)e->s_ed.p : nullptr);
+        if (st.used) RTCHK(rt_event_sync(st.out_done));        // set is being reused: the D2H of chunk ci-2 must be done
+        if ((rc = ensure(e, st.reads, (size_t)(b1 - b0) + 16))) return rc;
+        if ((rc = ensure(e, st.off, (size_t)(n + 1) * 8))) return rc;
+        if ((rc = ensure(e, st.recs, (size_t)n * sizeof(c2b_read_rec)))) return rc;
+        if ((rc = ensure(e, st.alns, (size_t)n * nr * sizeof(c2b_aln_rec)))) return rc;
+        if (strings && (rc = ensure(e, st.str, (size_t)n * nr * 2 * W))) return rc;
+        if (cap && (rc = ensure(e, st.ed, (size_t)n * nr * cap * sizeof(c2b_edit)))) return rc;
+        if (count && (rc = ensure(e, st.cnt, (size_t)n * 4))) return rc;
+        if (qweight && (rc = ensure(e, st.qw, (size_t)n * 4))) return rc;
+        if (ref_id && (rc = ensure(e, st.rid, (size_t)n * 4))) return rc;
+        if (st.h_off_cap < (size_t)(n + 1)) {
+            if (st.h_off) rt_host_free(st.h_off);
+            st.h_off = (int64_t *)rt_host_alloc((size_t)(n + 1) * 8); st.h_off_cap = st.h_off ? (size_t)(n + 1) : 0;
+            if (!st.h_off) return fail(e, C2B_E_CUDA, "c2b_align_batch: pinned allocation failed");
+        }
+        for (int64_t k = 0; k <= n; k++) st.h_off[k] = offsets[c0 + k] - b0;      // chunk-relative offsets
+        RTCHK(rt_h2d(st.reads.p, reads + b0, (size_t)(b1 - b0), e->s_in));
+        RTCHK(rt_h2d(st.off.p, st.h_off, (size_t)(n + 1) * 8, e->s_in));
+        if (count) RTCHK(rt_h2d(st.cnt.p, count + c0, (size_t)n * 4, e->s_in));
+        if (qweight) RTCHK(rt_h2d(st.qw.p, qweight + c0, (size_t)n * 4, e->s_in));
+        if (ref_id) RTCHK(rt_h2d(st.rid.p, ref_id + c0, (size_t)n * 4, e->s_in));
+        RTCHK(rt_record(st.in_done, e->s_in));
+        RTCHK(rt_wait(e->stream, st.in_done));
+        rc = c2b_align_batch_device(e, (const uint8_t *)st.reads.p, (const int64_t *)st.off.p, n, (int32_t)maxJ,
+                                    count ? (const int32_t *)st.cnt.p : nullptr, qweight ? (const int32_t *)st.qw.p : nullptr,
+                                    ref_id ? (const int32_t *)st.rid.p : nullptr, (c2b_read_rec *)st.recs.p,
+                                    (c2b_aln_rec *)st.alns.p, strings ? (uint8_t *)st.str.p : nullptr,
+                                    cap ? (c2b_edit *)st.ed.p : nullptr);
         if (rc) return rc;
-        RTCHK(rt_d2h(recs + c0, e->s_recs.p, (size_t)n * sizeof(c2b_read_rec), e->stream));
-        RTCHK(rt_d2h(alns + c0 * e->n_refs, e->s_alns.p, (size_t)n * e->n_refs * sizeof(c2b_aln_rec), e->stream));
-        if (strings) RTCHK(rt_d2h(strings + c0 * e->n_refs * 2 * W, e->s_str.p, (size_t)n * e->n_refs * 2 * W, e->stream));
-        if (cap) RTCHK(rt_d2h(edits + c0 * e->n_refs * cap, e->s_ed.p, (size_t)n * e->n_refs * cap * sizeof(c2b_edit), e->stream));
-        RTCHK(rt_sync(e->stream));
+        RTCHK(rt_record(st.k_done, e->stream));
+        RTCHK(rt_wait(e->s_out, st.k_done));
+        RTCHK(rt_d2h(recs + c0, st.recs.p, (size_t)n * sizeof(c2b_read_rec), e->s_out));
+        RTCHK(rt_d2h(alns + c0 * nr, st.alns.p, (size_t)n * nr * sizeof(c2b_aln_rec), e->s_out));
+        if (strings) RTCHK(rt_d2h(strings + c0 * nr * 2 * W, st.str.p, (size_t)n * nr * 2 * W, e->s_out));
+        if (cap) RTCHK(rt_d2h(edits + c0 * nr * cap, st.ed.p, (size_t)n * nr * cap * sizeof(c2b_edit), e->s_out));
+        RTCHK(rt_record(st.out_done, e->s_out));
+        st.used = true;
     }
+    RTCHK(rt_sync(e->s_out));
+    RTCHK(rt_sync(e->stream));
     return C2B_OK;
 }
 

@@ -79,6 +79,7 @@ C2B_DEV uint32_t ballot(bool p)
 C2B_DEV void sync() { emu::exchange(0, 5, [](int l, int) { return l; }, 0); }
 C2B_DEV int max3(int a, int b, int c) { return std::max(a, std::max(b, c)); }
 C2B_DEV int addmax(int a, int b, int c) { return std::max(a + b, c); }
+C2B_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31)); }
 C2B_DEV int popc(uint32_t x) { return __builtin_popcount(x); }
 C2B_DEV int popcll(uint64_t x) { return __builtin_popcountll(x); }
 C2B_DEV int clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
