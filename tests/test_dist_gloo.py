@@ -1,0 +1,45 @@
+"""N>1 path on CPU: world_size-2 gloo run of the sharded engine + all-reduce of the count block, against the
+oracle's single-process quantification."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds_cover_everything():
+    from crispresso2_b200.dist import shard_bounds, shard_by_cells
+    for n in (0, 1, 7, 64, 1001):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[k][1] == spans[k + 1][0] for k in range(w - 1))
+    lens = np.array([50, 300, 120, 250, 250, 75, 299, 60])
+    parts = [shard_by_cells(lens, r, 3) for r in range(3)]
+    assert sorted(np.concatenate(parts).tolist()) == list(range(8))
+    loads = [int(lens[p].sum()) for p in parts]
+    assert max(loads) - min(loads) <= 300
+
+
+def test_two_ranks_gloo_merge_matches_oracle(tmp_path):
+    out = tmp_path / "merged.json"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "dist_worker.py"), str(out)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.load(open(out))
+    assert got["world"] == 2
+    from crispresso2_b200 import synth
+    from oracle import oracle as O
+    ref = synth.amplicon_setup(got["amp"], guide_start=50)
+    refs = {"Reference": ref}
+    cache, stats, lost = O.process_reads(got["reads"], refs, ["Reference"], O.Params(), O.make_matrix())
+    vec, sca, classes, total = O.count_vectors(cache, refs, ["Reference"], O.Params())
+    for name in O.VECTOR_NAMES:
+        assert got["vectors"][name] == vec["Reference"][name].tolist(), name
+    for name in O.SCALAR_NAMES:
+        assert got["scalars"][name] == sca["Reference"][name], name
