@@ -346,8 +346,6 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_port(amp, ref, reads)
-        elif world > 1:
-            line["cpu_baseline"] = None
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -150,7 +150,8 @@ def test_full_size_properties(eng):
     eng.counts_reset()
     res2 = eng.align_packed(reads[pick].reshape(-1), np.arange(len(pick) + 1, dtype=np.int64) * 250)
     assert (res2.alns[:, 0] == res.alns[pick, 0]).all()
-    assert (res2.strings == res.strings[pick]).all()
+    valid = cols[pick][:, None, None, :]                               # bytes left of W - aln_len are undefined
+    assert ((res2.strings == res.strings[pick]) | ~valid).all()
 
 
 def test_empty_batch_and_bad_symbols(eng):
