@@ -34,11 +34,16 @@ C2B_DEV int lane() { return threadIdx.x & 31; }
 C2B_DEV int shfl_up(int v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 C2B_DEV int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 C2B_DEV uint32_t shflu(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+C2B_DEV uint32_t shflu_up(uint32_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 C2B_DEV int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 C2B_DEV uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 C2B_DEV void sync() { __syncwarp(); }
 C2B_DEV int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 C2B_DEV int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }   // max(a+b, c)
+C2B_DEV uint32_t max3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }      // per signed half
+C2B_DEV uint32_t addmax_2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }  // per half max(a+b, c)
+C2B_DEV uint4 ldg4u(const uint4 *p) { return __ldg(p); }
+C2B_DEV uint2 ldcg2(const uint2 *p) { return __ldcg(p); }
 C2B_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }   // (hi:lo) >> sh
 C2B_DEV int popc(uint32_t x) { return __popc(x); }
 C2B_DEV int popcll(uint64_t x) { return __popcll(x); }
@@ -78,6 +83,12 @@ struct RefDev {
     uint64_t fw_seed[C2B_MAX_SEEDS], rc_seed[C2B_MAX_SEEDS];   // 3 bits per base, first base lowest
     unsigned long long *vec;       // [C2B_NVEC][vstride]
     unsigned long long *scal;      // [C2B_NSCAL]
+    // packed two-reads-per-warp path (16-bit halves, biased scores)
+    int32_t pk_maxJ;               // longest read for which the 16-bit path is proven exact for this reference (0: never)
+    uint32_t pk_XB, pk_YB, pk_M00; // border constants: X[0][j], Y[i][0], M[0][0] in both halves
+    const uint32_t *prof2;         // [nq*nq][Ipad]  halves: 4*(score+2*beta) of read A (low) / read B (high)
+    const uint32_t *cIe2;          // [Ipad]         4*gi[row+1] in both halves
+    const uint32_t *g42;           // [Ipad]         4*gi[row]   in both halves
 };
 
 struct KParams {
@@ -98,11 +109,13 @@ struct KParams {
 };
 
 struct WarpSmem {
-    uint8_t fw[MAXJ];          // read as alphabet codes
-    uint8_t rc[MAXJ];          // reverse complement
-    uint8_t rowinfo[MAXI];     // per reference position: read code of its column, or 8 = deleted
-    uint32_t rowins[MAXI + 4]; // rowins[r]: bases inserted between reference positions r-1 and r
+    uint8_t fw[2][MAXJ];       // read(s) as alphabet codes ([1]: second read of a pair)
+    uint8_t rc[2][MAXJ];       // reverse complement
+    uint8_t combo[MAXJ];       // pair path: codeA*nq + codeB of the strands being aligned
+    uint8_t rowinfo[MAXI];     // per reference position: read code of its column, or 8 = deleted (pair: halves of 512)
+    uint32_t rowins[MAXI + 4]; // rowins[r]: bases inserted between reference positions r-1 and r (pair: halves of 514)
 };
+constexpr int PK_ROWINFO_STRIDE = 512, PK_ROWINS_STRIDE = 514, PK_MAX_ALN = 512;
 
 struct Walked { uint64_t ops; int n; int err; };
 
@@ -264,25 +277,29 @@ C2B_DEV Walked align_strand(const KParams &P, const RefDev &R, const uint8_t *co
 
 // --------------------------------------------------------------------------------------------- columns
 // mode bits: 1 = write strings, 2 = scatter per-reference-position info into shared memory.
+// HALF = false: the warp's 32 lanes hold one read's op stream (lane L: columns 32L..32L+31 from the right).
+// HALF = true : lanes 0-15 hold read A's stream, lanes 16-31 read B's (pair path); every argument is per lane.
 struct ColOut { int n_match; int irregular; };
 
-C2B_DEVNOINL ColOut columns(const KParams &P, const RefDev &R, WarpSmem &S, const uint8_t *codes, int J,
+template <bool HALF>
+C2B_DEVNOINL ColOut columns(const KParams &P, const RefDev &R, uint8_t *rowinfo, uint32_t *rowins, const uint8_t *codes, int J,
                             uint64_t ops, int n, int mode, uint8_t *out_read, uint8_t *out_ref)
 {
     const int lane = wp::lane();
+    const int li = HALF ? (lane & 15) : lane;            // lane index within the group that holds this read
     const uint64_t lo = 0x5555555555555555ull;
     const int ci = 32 - wp::popcll((ops >> 1) & lo);     // ops consuming a reference base (M, J)
     const int cj = 32 - wp::popcll(ops & lo);            // ops consuming a read base (M, I)
     int pk = (ci << 16) | cj;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int v = wp::shfl_up(pk, d); if (lane >= d) pk += v; }
+    for (int d = 1; d < (HALF ? 16 : 32); d <<= 1) { int v = wp::shfl_up(pk, d); if (li >= d) pk += v; }
     pk -= (ci << 16) | cj;                               // exclusive
     int i = R.I - (pk >> 16), j = J - (pk & 0xffff);
     uint32_t wr[8], wf[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) { wr[q] = 0; wf[q] = 0; }
     int match = 0, irr = 0;
-    const int n0 = 32 * lane;
+    const int n0 = 32 * li;
     if (n0 < n) {
 #pragma unroll
         for (int e = 0; e < 32; e++) {
@@ -296,23 +313,23 @@ C2B_DEVNOINL ColOut columns(const KParams &P, const RefDev &R, WarpSmem &S, cons
                 const int byte = 15 - (e & 15), wi = (e >> 4) * 4 + (byte >> 2), sh = 8 * (byte & 3);
                 wr[wi] |= rd << sh; wf[wi] |= rf << sh;
                 if (mode & 2) {
-                    if (op == OP_M) S.rowinfo[i - 1] = (uint8_t)code;
-                    else if (op == OP_J) S.rowinfo[i - 1] = 8;
-                    else if (i > 0 && i < R.I) wp::adds(&S.rowins[i], 1u);
+                    if (op == OP_M) rowinfo[i - 1] = (uint8_t)code;
+                    else if (op == OP_J) rowinfo[i - 1] = 8;
+                    else if (i > 0 && i < R.I) wp::adds(&rowins[i], 1u);
                 }
                 i -= (op != OP_I); j -= (op != OP_J);
             }
         }
         if (mode & 1) {
             // right-aligned slots: column n (from the right) lives at byte W-1-n
-            uint4 *pr = reinterpret_cast<uint4 *>(out_read + P.W - 32 * lane - 16);
-            uint4 *pf = reinterpret_cast<uint4 *>(out_ref + P.W - 32 * lane - 16);
+            uint4 *pr = reinterpret_cast<uint4 *>(out_read + P.W - 32 * li - 16);
+            uint4 *pf = reinterpret_cast<uint4 *>(out_ref + P.W - 32 * li - 16);
             pr[0] = make_uint4(wr[0], wr[1], wr[2], wr[3]); pf[0] = make_uint4(wf[0], wf[1], wf[2], wf[3]);
             if (n0 + 16 < n) { pr[-1] = make_uint4(wr[4], wr[5], wr[6], wr[7]); pf[-1] = make_uint4(wf[4], wf[5], wf[6], wf[7]); }
         }
     }
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) { match += wp::shfl_xor(match, d); irr |= wp::shfl_xor(irr, d); }
+    for (int d = (HALF ? 8 : 16); d >= 1; d >>= 1) { match += wp::shfl_xor(match, d); irr |= wp::shfl_xor(irr, d); }
     ColOut o; o.n_match = match; o.irregular = irr;
     return o;
 }
@@ -333,8 +350,8 @@ struct RowOut {
 
 // PASS 0: scalars + edit list.  PASS 1: per-position count vectors (weight w).
 template <int PASS>
-C2B_DEV void rows_pass(const KParams &P, const RefDev &R, WarpSmem &S, RowOut &o, c2b_edit *ed, long long w,
-                       bool len_vectors)
+C2B_DEV void rows_pass(const KParams &P, const RefDev &R, const uint8_t *rowinfo, const uint32_t *rowins, RowOut &o,
+                       c2b_edit *ed, long long w, bool len_vectors)
 {
     const int lane = wp::lane();
     const uint32_t lt = (1u << lane) - 1u;
@@ -368,15 +385,15 @@ C2B_DEV void rows_pass(const KParams &P, const RefDev &R, WarpSmem &S, RowOut &o
     for (int c = 0; c < nchunks; c++) {
         const int p = 32 * c + lane;
         const bool valid = p < I;
-        const int info = valid ? S.rowinfo[p] : 0;
+        const int info = valid ? rowinfo[p] : 0;
         const bool isdel = valid && info == 8;
         const int rcode = info & 7;
         const uint32_t refc = valid ? R.asc[p] : 0u, readc = P.alpha[rcode];
         const bool differs = valid && !isdel && readc != refc;
         const bool issub = differs && readc != 'N';                         // COREResources.pyx:111
         const bool inc_p = valid && R.incl[p];
-        const uint32_t insr = (valid && p + 1 <= I - 1) ? S.rowins[p + 1] : 0u;   // insertion right of p
-        const uint32_t insl = (valid && p >= 1 && p <= I - 1) ? S.rowins[p] : 0u; // insertion left of p
+        const uint32_t insr = (valid && p + 1 <= I - 1) ? rowins[p + 1] : 0u;   // insertion right of p
+        const uint32_t insl = (valid && p >= 1 && p <= I - 1) ? rowins[p] : 0u; // insertion left of p
         const bool win_r = insr > 0 && inc_p && R.incl[p + 1];                    // both flanks in window (:120)
         const bool win_l = insl > 0 && inc_p && R.incl[p - 1];
         const uint32_t D = wp::ballot(isdel);
@@ -449,7 +466,7 @@ C2B_DEV void rows_pass(const KParams &P, const RefDev &R, WarpSmem &S, RowOut &o
 }
 
 // ------------------------------------------------------------------------------------------ per read
-C2B_DEV int strand_mode(const KParams &P, const RefDev &R, const WarpSmem &S, int J)
+C2B_DEV int strand_mode(const KParams &P, const RefDev &R, const uint8_t *fw, int J)
 {
     // seed test of CRISPRessoCORE.py:656-687: 0 forward only, 1 reverse-complement only, 2 both
     if (P.flags & C2B_F_NO_STRAND_SEARCH) return 0;
@@ -459,7 +476,7 @@ C2B_DEV int strand_mode(const KParams &P, const RefDev &R, const WarpSmem &S, in
     if (ns > 0 && L > 0) {
         for (int p = lane; p + L <= J; p += 32) {
             uint64_t km = 0;
-            for (int c = 0; c < L; c++) km |= (uint64_t)S.fw[p + c] << (3 * c);
+            for (int c = 0; c < L; c++) km |= (uint64_t)fw[p + c] << (3 * c);
             for (int s = 0; s < ns; s++) {
                 if (km == R.fw_seed[s]) hit |= 1u << s;
                 if (km == R.rc_seed[s]) hit |= 1u << (8 + s);
@@ -474,95 +491,59 @@ C2B_DEV int strand_mode(const KParams &P, const RefDev &R, const WarpSmem &S, in
     return 2;
 }
 
-C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_slot)
+// read -> alphabet codes (forward and reverse complement); returns true if a symbol is outside the alphabet
+C2B_DEV bool load_codes(const KParams &P, int64_t off, int J, uint8_t *fw, uint8_t *rc)
 {
     const int lane = wp::lane();
-    const int64_t off = P.offsets[rd];
-    const int J = (int)(P.offsets[rd + 1] - off);
-    uint32_t *tb = P.tb + (int64_t)warp_slot * P.tb_words_per_warp;
-    int32_t *bnd = P.bnd + (int64_t)warp_slot * P.bnd_words_per_warp;
-    uint64_t *opsbuf = P.opsbuf + (int64_t)warp_slot * P.n_refs * 32;
-
-    c2b_read_rec rec; rec.winner_mask = 0; rec.best_score_milli = -1000; rec.best_ref = -1; rec.n_winners = 0;
-    rec.ambiguous = 0; rec.status = 0;
-
-    uint32_t st = 0;
-    if (J < 1 || J > MAXJ || J + 32 > P.TS) st |= C2B_ST_TOO_LONG;
-    else {
-        bool bad = false;
-        for (int p = lane; p < J; p += 32) {
-            const uint8_t ch = P.reads[off + p];
-            int code = 255;
+    bool bad = false;
+    for (int p = lane; p < J; p += 32) {
+        const uint8_t ch = P.reads[off + p];
+        int code = 255;
 #pragma unroll
-            for (int q = 0; q < C2B_MAX_Q; q++) if (q < P.nq && ch == P.alpha[q]) code = q;
-            if (code == 255) { bad = true; code = 0; }
-            S.fw[p] = (uint8_t)code;
-            S.rc[J - 1 - p] = P.comp[code];
-        }
-        if (wp::ballot(bad)) st |= C2B_ST_BAD_CHAR;
+        for (int q = 0; q < C2B_MAX_Q; q++) if (q < P.nq && ch == P.alpha[q]) code = q;
+        if (code == 255) { bad = true; code = 0; }
+        fw[p] = (uint8_t)code;
+        rc[J - 1 - p] = P.comp[code];
     }
-    wp::sync();
+    return wp::ballot(bad) != 0;
+}
 
-    const int r_begin = P.ref_id ? P.ref_id[rd] : 0;
-    const int r_end = P.ref_id ? r_begin + 1 : P.n_refs;
+C2B_DEV void init_aln(c2b_aln_rec &a, uint32_t st)
+{
+    a.n_match = 0; a.aln_len = 0; a.score_milli = -1000; a.strand = 0; a.status = (uint8_t)st; a.n_edits = 0;
+    a.insertion_n = a.deletion_n = a.substitution_n = 0; a.n_ins_all = a.n_ins_win = 0; a.n_del_all = a.n_del_win = 0;
+    a.n_del_pos_all = 0; a.n_sub_all = 0; a.irregular_ends = 0; a.modified = 0;
+}
+
+// best-reference bookkeeping of CRISPRessoCORE.py:697-707
+C2B_DEV void note_score(c2b_read_rec &rec, const RefDev &R, int r, int sc)
+{
+    if (sc > rec.best_score_milli && (double)sc / 1000.0 > R.min_aln) {
+        rec.best_score_milli = sc; rec.winner_mask = 1u << (r & 31); rec.n_winners = 1;
+    } else if (sc == rec.best_score_milli) {
+        rec.winner_mask |= 1u << (r & 31); rec.n_winners++;
+    }
+}
+
+// c2b_aln_rec written by another lane of this warp: read it through L2 (the writer's line may sit stale in L1)
+C2B_DEV c2b_aln_rec load_aln(const c2b_aln_rec *p)
+{
+    union { c2b_aln_rec a; uint64_t q[4]; } u;
+    const uint64_t *s = reinterpret_cast<const uint64_t *>(p);
+    u.q[0] = wp::ldcg64(s); u.q[1] = wp::ldcg64(s + 1); u.q[2] = wp::ldcg64(s + 2); u.q[3] = wp::ldcg64(s + 3);
+    return u.a;
+}
+
+// Classification + counts of one read once its alignments are known (all lanes hold the same `rec`).
+//   single reference tried: the caller already scattered the chosen alignment into rowinfo/rowins;
+//   several references    : op streams are reloaded from opsbuf (lane offset hoff; hoff >= 0: the stream lives in
+//                           16 lanes starting at hoff) and re-scattered per winner.
+C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, const uint8_t *fw, const uint8_t *rc,
+                         uint8_t *rowinfo, uint32_t *rowins, int r_begin, int r_end, const uint64_t *opsbuf, int hoff,
+                         int keep_irr)
+{
+    const int lane = wp::lane();
     const bool multi = (r_end - r_begin) > 1;
-    uint64_t keep_ops = ~0ull; int keep_n = 0, keep_strand = 0, keep_irr = 0;
-
-    for (int r = r_begin; r < r_end; r++) {
-        const RefDev &R = P.refs[r];
-        c2b_aln_rec a;
-        a.n_match = 0; a.aln_len = 0; a.score_milli = -1000; a.strand = 0; a.status = (uint8_t)st; a.n_edits = 0;
-        a.insertion_n = a.deletion_n = a.substitution_n = 0; a.n_ins_all = a.n_ins_win = 0; a.n_del_all = a.n_del_win = 0;
-        a.n_del_pos_all = 0; a.n_sub_all = 0; a.irregular_ends = 0; a.modified = 0;
-        if (!st && (R.I + J > C2B_MAX_ALN_LEN)) a.status |= C2B_ST_TOO_LONG;
-        if (!a.status) {
-            const int mode = P.forced_ops ? 0 : strand_mode(P, R, S, J);
-            Walked wf; wf.ops = ~0ull; wf.n = 0; wf.err = 0;
-            Walked wr = wf;
-            int sf = -1000000, sr = -1000000;
-            for (int pass = 0; pass < 2; pass++) {              // one call site: forward, then reverse complement
-                if (pass == (mode == 1 ? 0 : mode == 0 ? 1 : 2)) continue;
-                const uint8_t *codes = pass ? S.rc : S.fw;
-                Walked wk;
-                if (P.forced_ops) { wk.ops = P.forced_ops[rd * 32 + lane]; wk.n = P.forced_n[rd]; wk.err = 0; }
-                else wk = align_strand(P, R, codes, J, tb, bnd);
-                int sc = -1000000;
-                if (wk.err) a.status |= C2B_ST_UNDEFINED;
-                else if (mode == 2) sc = score_milli(columns(P, R, S, codes, J, wk.ops, wk.n, 0, nullptr, nullptr).n_match, wk.n);
-                if (pass) { wr = wk; sr = sc; } else { wf = wk; sf = sc; }
-            }
-            if (!a.status) {
-                const bool use_rc = (mode == 1) || (mode == 2 && sr > sf);      // strict '>' of CRISPRessoCORE.py:682
-                const Walked &wk = use_rc ? wr : wf;
-                const uint8_t *codes = use_rc ? S.rc : S.fw;
-                uint8_t *o_read = P.strings ? P.strings + ((rd * P.n_refs + r) * 2) * (int64_t)P.W : nullptr;
-                uint8_t *o_ref = o_read ? o_read + P.W : nullptr;
-                int cmode = (o_read ? 1 : 0);
-                if (!multi) {                                   // single reference: scatter now, classify below
-                    for (int p = lane; p <= R.I; p += 32) S.rowins[p] = 0;
-                    wp::sync();
-                    cmode |= 2;
-                }
-                const ColOut co = columns(P, R, S, codes, J, wk.ops, wk.n, cmode, o_read, o_ref);
-                a.n_match = (uint16_t)co.n_match; a.aln_len = (uint16_t)wk.n; a.strand = use_rc;
-                a.score_milli = score_milli(co.n_match, wk.n);
-                a.irregular_ends = (uint8_t)co.irregular;
-                if (multi) opsbuf[r * 32 + lane] = wk.ops;
-                keep_ops = wk.ops; keep_n = wk.n; keep_strand = use_rc; keep_irr = co.irregular;
-                // best-reference bookkeeping (CRISPRessoCORE.py:697-707)
-                const int sc = a.score_milli;
-                if (sc > rec.best_score_milli && (double)sc / 1000.0 > R.min_aln) {
-                    rec.best_score_milli = sc; rec.winner_mask = 1u << (r & 31); rec.n_winners = 1;
-                } else if (sc == rec.best_score_milli) {
-                    rec.winner_mask |= 1u << (r & 31); rec.n_winners++;
-                }
-            }
-        }
-        rec.status |= a.status;
-        if (lane == 0) P.alns[rd * P.n_refs + r] = a;
-    }
-    wp::sync();
-
     if (rec.best_score_milli <= 0 && !P.forced_ops) { rec.winner_mask = 0; rec.n_winners = 0; }
     else {
         const bool expand = P.flags & C2B_F_EXPAND_AMBIGUOUS, first = P.flags & C2B_F_ASSIGN_FIRST;
@@ -575,21 +556,24 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
             if (!((rec.winner_mask >> (r & 31)) & 1u)) continue;
             const RefDev &R = P.refs[r];
             rec.best_ref = (int16_t)r;                          // best_match_name = last winner (:768)
-            uint64_t ops = keep_ops; int n = keep_n, strand = keep_strand, irr = keep_irr;
+            int irr = keep_irr;
             if (multi) {
                 wp::sync();
-                ops = wp::ldcg64(opsbuf + r * 32 + lane);
-                const c2b_aln_rec prev = P.alns[rd * P.n_refs + r];      // written by lane 0 above
-                n = wp::shfl((int)prev.aln_len, 0); strand = wp::shfl((int)prev.strand, 0); irr = wp::shfl((int)prev.irregular_ends, 0);
-                for (int p = lane; p <= R.I; p += 32) S.rowins[p] = 0;
+                uint64_t ops;
+                if (hoff < 0) ops = wp::ldcg64(opsbuf + r * 32 + lane);
+                else ops = lane < 16 ? wp::ldcg64(opsbuf + r * 32 + hoff + lane) : ~0ull;
+                const c2b_aln_rec prev = load_aln(P.alns + rd * P.n_refs + r);
+                const int n = wp::shfl((int)prev.aln_len, 0), strand = wp::shfl((int)prev.strand, 0);
+                irr = wp::shfl((int)prev.irregular_ends, 0);
+                for (int p = lane; p <= R.I; p += 32) rowins[p] = 0;
                 wp::sync();
-                columns(P, R, S, strand ? S.rc : S.fw, J, ops, n, 2, nullptr, nullptr);
+                columns<false>(P, R, rowinfo, rowins, strand ? rc : fw, J, ops, n, 2, nullptr, nullptr);
             }
             wp::sync();
             RowOut o; o.ins_n = o.del_n = o.sub_n = 0; o.n_ins_all = o.n_ins_win = o.n_del_all = o.n_del_win = 0;
             o.n_del_pos = o.n_sub_all = 0; o.nent = 0;
             c2b_edit *ed = P.edits ? P.edits + (rd * P.n_refs + r) * (int64_t)P.edit_cap : nullptr;
-            rows_pass<0>(P, R, S, o, ed, 0, false);
+            rows_pass<0>(P, R, rowinfo, rowins, o, ed, 0, false);
             const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
                        ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
             const bool has_d = !ign_d && o.del_n > 0, has_i = !ign_i && o.ins_n > 0, has_s = !ign_s && o.sub_n > 0;
@@ -604,7 +588,7 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
                 const bool discard = (P.flags & C2B_F_DISCARD_INDEL_READS) && (o.del_n > 0 || o.ins_n > 0);
                 if (discard) { if (lane == 0) wp::addg(SC + C2B_S_DISCARDED, w); }
                 else {
-                    rows_pass<1>(P, R, S, o, nullptr, w, has_d || has_i || has_s);
+                    rows_pass<1>(P, R, rowinfo, rowins, o, nullptr, w, has_d || has_i || has_s);
                     if (lane == 0) {
                         wp::addg(SC + C2B_S_TOTAL, w);
                         wp::addg(SC + (modified ? C2B_S_MODIFIED : C2B_S_UNMODIFIED), w);
@@ -619,7 +603,7 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
                 }
             } else if (ambiguous && nth == 0 && w > 0 && lane == 0 && !overflow) wp::addg(SC + C2B_S_AMBIGUOUS_W, w);
             if (lane == 0) {
-                c2b_aln_rec a = P.alns[rd * P.n_refs + r];
+                c2b_aln_rec a = load_aln(P.alns + rd * P.n_refs + r);
                 a.insertion_n = (uint16_t)o.ins_n; a.deletion_n = (uint16_t)o.del_n; a.substitution_n = (uint16_t)o.sub_n;
                 a.n_ins_all = (uint16_t)o.n_ins_all; a.n_ins_win = (uint16_t)o.n_ins_win;
                 a.n_del_all = (uint16_t)o.n_del_all; a.n_del_win = (uint16_t)o.n_del_win;
@@ -647,6 +631,347 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
         }
     }
     if (lane == 0) P.recs[rd] = rec;
+}
+
+// One read per warp, 32-bit scores: the general path (any length within the build limits, any parameters).
+C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_slot)
+{
+    const int lane = wp::lane();
+    const int64_t off = P.offsets[rd];
+    const int J = (int)(P.offsets[rd + 1] - off);
+    uint32_t *tb = P.tb + (int64_t)warp_slot * P.tb_words_per_warp;
+    int32_t *bnd = P.bnd + (int64_t)warp_slot * P.bnd_words_per_warp;
+    uint64_t *opsbuf = P.opsbuf + (int64_t)warp_slot * P.n_refs * 32;
+
+    c2b_read_rec rec; rec.winner_mask = 0; rec.best_score_milli = -1000; rec.best_ref = -1; rec.n_winners = 0;
+    rec.ambiguous = 0; rec.status = 0;
+    uint32_t st = 0;
+    if (J < 1 || J > MAXJ || J + 32 > P.TS) st |= C2B_ST_TOO_LONG;
+    else if (load_codes(P, off, J, S.fw[0], S.rc[0])) st |= C2B_ST_BAD_CHAR;
+    wp::sync();
+
+    const int r_begin = P.ref_id ? P.ref_id[rd] : 0;
+    const int r_end = P.ref_id ? r_begin + 1 : P.n_refs;
+    const bool multi = (r_end - r_begin) > 1;
+    int keep_irr = 0;
+
+    for (int r = r_begin; r < r_end; r++) {
+        const RefDev &R = P.refs[r];
+        c2b_aln_rec a; init_aln(a, st);
+        if (!st && (R.I + J > C2B_MAX_ALN_LEN)) a.status |= C2B_ST_TOO_LONG;
+        if (!a.status) {
+            const int mode = P.forced_ops ? 0 : strand_mode(P, R, S.fw[0], J);
+            Walked wf; wf.ops = ~0ull; wf.n = 0; wf.err = 0;
+            Walked wr = wf;
+            int sf = -1000000, sr = -1000000;
+            for (int pass = 0; pass < 2; pass++) {              // one call site: forward, then reverse complement
+                if (pass == (mode == 1 ? 0 : mode == 0 ? 1 : 2)) continue;
+                const uint8_t *codes = pass ? S.rc[0] : S.fw[0];
+                Walked wk;
+                if (P.forced_ops) { wk.ops = P.forced_ops[rd * 32 + lane]; wk.n = P.forced_n[rd]; wk.err = 0; }
+                else wk = align_strand(P, R, codes, J, tb, bnd);
+                int sc = -1000000;
+                if (wk.err) a.status |= C2B_ST_UNDEFINED;
+                else if (mode == 2) sc = score_milli(columns<false>(P, R, S.rowinfo, S.rowins, codes, J, wk.ops, wk.n, 0, nullptr, nullptr).n_match, wk.n);
+                if (pass) { wr = wk; sr = sc; } else { wf = wk; sf = sc; }
+            }
+            if (!a.status) {
+                const bool use_rc = (mode == 1) || (mode == 2 && sr > sf);      // strict '>' of CRISPRessoCORE.py:682
+                const Walked &wk = use_rc ? wr : wf;
+                const uint8_t *codes = use_rc ? S.rc[0] : S.fw[0];
+                uint8_t *o_read = P.strings ? P.strings + ((rd * P.n_refs + r) * 2) * (int64_t)P.W : nullptr;
+                uint8_t *o_ref = o_read ? o_read + P.W : nullptr;
+                int cmode = (o_read ? 1 : 0);
+                if (!multi) {                                   // single reference: scatter now, classify below
+                    for (int p = lane; p <= R.I; p += 32) S.rowins[p] = 0;
+                    wp::sync();
+                    cmode |= 2;
+                }
+                const ColOut co = columns<false>(P, R, S.rowinfo, S.rowins, codes, J, wk.ops, wk.n, cmode, o_read, o_ref);
+                a.n_match = (uint16_t)co.n_match; a.aln_len = (uint16_t)wk.n; a.strand = use_rc;
+                a.score_milli = score_milli(co.n_match, wk.n);
+                a.irregular_ends = (uint8_t)co.irregular;
+                if (multi) opsbuf[r * 32 + lane] = wk.ops;
+                keep_irr = co.irregular;
+                note_score(rec, R, r, a.score_milli);
+            }
+        }
+        rec.status |= a.status;
+        if (lane == 0) P.alns[rd * P.n_refs + r] = a;
+    }
+    wp::sync();
+    finish_read(P, rd, rec, J, S.fw[0], S.rc[0], S.rowinfo, S.rowins, r_begin, r_end, opsbuf, -1, keep_irr);
+}
+
+// ------------------------------------------------------------------------------------ paired path (16-bit halves)
+// Two reads of equal length share a warp: every 32-bit register holds read A's value in its low half and read
+// B's in its high half, so each VIMNMX3.S16x2 / VIADDMNMX.S16x2 advances two DP cells.  Scores are biased by
+// beta*(i+j) (beta = -gap_extend; equal for all values compared at one cell, so every decision is unchanged) plus a
+// constant offset, which makes every stored value and every added constant non-negative: plain 32-bit adds then
+// cannot carry between the halves.  Validity (ranges, parameter signs) is decided per reference on the host
+// (RefDev::pk_maxJ); anything else takes the 32-bit path above.
+constexpr uint32_t PK_SENT = 0x01000100u, PK_T2 = 0x00020002u, PK_T1 = 0x00010001u, PK_TM = 0x00030003u;
+
+template <int KSTAR>
+C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint8_t *combo, const int J, const int rb,
+                       uint2 *__restrict__ tb2, const int32_t *bnd_in, int32_t *bnd_out, uint32_t &cM, uint32_t &cX, uint32_t &cY)
+{
+    const int lane = wp::lane();
+    const int nrb = R.nrb, lstar = R.lstar, Ipad = R.Ipad;
+    const bool lastblk = (rb == nrb - 1);
+    const int nl = lastblk ? lstar + 1 : 32;
+    const int r0 = rb * 256 + 8 * lane;
+    const bool islast = lastblk && lane == lstar;
+    const uint32_t d4p = (uint32_t)((4 * (P.go - P.ge)) & 0xffff) * 0x00010001u;
+    const uint32_t XB = R.pk_XB, YB = R.pk_YB;
+
+    uint32_t M[8], X[8], Y[8], cIe[8], g4[8];
+    {
+        const uint4 *pc = reinterpret_cast<const uint4 *>(R.cIe2 + r0);
+        const uint4 *pg = reinterpret_cast<const uint4 *>(R.g42 + r0);
+        uint4 a = wp::ldg4u(pc), b = wp::ldg4u(pc + 1), c = wp::ldg4u(pg), d = wp::ldg4u(pg + 1);
+        cIe[0] = a.x; cIe[1] = a.y; cIe[2] = a.z; cIe[3] = a.w; cIe[4] = b.x; cIe[5] = b.y; cIe[6] = b.z; cIe[7] = b.w;
+        g4[0] = c.x; g4[1] = c.y; g4[2] = c.z; g4[3] = c.w; g4[4] = d.x; g4[5] = d.y; g4[6] = d.z; g4[7] = d.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { M[k] = PK_SENT; X[k] = PK_SENT | PK_T2; Y[k] = YB; }      // column 0
+    uint32_t pM, pX, pY;
+    if (rb == 0) { pM = R.pk_M00; pX = PK_SENT | PK_T2; pY = PK_SENT | PK_T1; }
+    else { pM = PK_SENT; pX = PK_SENT | PK_T2; pY = YB; }
+
+    const int nsteps = J + nl - 1;
+    const uint32_t *__restrict__ prof0 = R.prof2 + r0;
+    uint2 *__restrict__ tbw = tb2 + ((int64_t)rb * P.TS) * 32 + lane;
+    const bool lane_on = lane < nl;
+
+    for (int t = 1; t <= nsteps; t++) {
+        uint32_t uM = wp::shflu_up(M[7], 1), uX = wp::shflu_up(X[7], 1), uY = wp::shflu_up(Y[7], 1);
+        const int j = t - lane;
+        if (lane == 0) {
+            if (rb == 0) { uM = PK_SENT; uX = XB; uY = PK_SENT | PK_T1; }
+            else if (j <= J) { uM = (uint32_t)wp::ldcgi(bnd_in + 3 * j); uX = (uint32_t)wp::ldcgi(bnd_in + 3 * j + 1); uY = (uint32_t)wp::ldcgi(bnd_in + 3 * j + 2); }
+        }
+        if (lane_on && j >= 1 && j <= J) {
+            const int q2 = combo[j - 1];
+            const uint4 *pp = reinterpret_cast<const uint4 *>(prof0 + q2 * Ipad);
+            const uint4 sa = wp::ldg4u(pp), sb = wp::ldg4u(pp + 1);
+            const uint32_t s[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+            const uint32_t dcol = (j == J) ? 0u : d4p;      // free opening in the last column (both reads end together)
+            const uint32_t dsp = islast ? 0u : dcol;
+            uint32_t dM = pM, dX = pX, dY = pY, upM = uM, upY = uY, wT = 0, wIJ = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t dik = (k == KSTAR) ? dsp : dcol;
+                const uint32_t z = wp::max3_2(dM, dY, dX);
+                const uint32_t t2 = z & PK_TM;
+                const uint32_t nm = z - t2 + s[k];                                   // halves stay in [0, 32767]: no carry
+                const uint32_t x = wp::addmax_2(M[k], dik, X[k]) + cIe[k];
+                const uint32_t y = wp::addmax_2(upM + g4[k], dik, upY);              // biased gap_extend is 0
+                wT = wT * 4u + t2;
+                wIJ = wIJ * 4u + (((x & PK_T2) | (y & ~PK_T2)) & PK_TM);
+                dM = M[k]; dX = X[k]; dY = Y[k];
+                M[k] = nm; X[k] = x | PK_T2; Y[k] = y | PK_T1;
+                upM = nm; upY = Y[k];
+            }
+            tbw[(int64_t)t * 32] = make_uint2(wT, wIJ);
+            if (!lastblk && lane == 31) { bnd_out[3 * j] = (int)M[7]; bnd_out[3 * j + 1] = (int)X[7]; bnd_out[3 * j + 2] = (int)Y[7]; }
+        }
+        pM = uM; pX = uX; pY = uY;
+    }
+    if (lastblk) {
+        const int k = (KSTAR < 8) ? KSTAR : 0;
+        cM = wp::shflu(M[k], lstar); cX = wp::shflu(X[k], lstar); cY = wp::shflu(Y[k], lstar);
+    }
+}
+
+C2B_DEV void dp_dispatch2(const KParams &P, const RefDev &R, const uint8_t *combo, int J, int rb, uint2 *tb2,
+                          const int32_t *bi, int32_t *bo, uint32_t &cM, uint32_t &cX, uint32_t &cY)
+{
+    const int ks = (rb == R.nrb - 1) ? R.kstar : 8;
+    switch (ks) {
+    case 0: dp_block2<0>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 1: dp_block2<1>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 2: dp_block2<2>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 3: dp_block2<3>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 4: dp_block2<4>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 5: dp_block2<5>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 6: dp_block2<6>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 7: dp_block2<7>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    default: dp_block2<8>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    }
+}
+
+// Two tracebacks at once: lanes 0-15 walk read A, lanes 16-31 read B (each lane of a half holds the same state).
+// The half's lane L ends up with ops 32L..32L+31 of its read (up to 512 columns).
+C2B_DEV Walked walk2(const KParams &P, const RefDev &R, const int J, const uint2 *__restrict__ tb2, int s)
+{
+    const int lane = wp::lane(), hl = lane & 15, hb = lane & 16;
+    const int TS = P.TS;
+    int i = R.I, j = J, n = 0, err = 0;
+    uint32_t acc = 0, lo = ~0u, hi = ~0u;
+    int wkey = -1, wj = 0; uint32_t wreg = 0;
+#define C2B_PUSH2(op_)                                                                        \
+    do {                                                                                      \
+        acc = wp::funnel_r(acc, (uint32_t)(op_), 2); n++;                                     \
+        if ((n & 15) == 0) { const int ix = (n >> 4) - 1; if (hl == (ix >> 1)) { if (ix & 1) hi = acc; else lo = acc; } } \
+    } while (0)
+    for (;;) {
+        const bool active = i > 0 && j > 0;
+        if (!wp::ballot(active)) break;
+        const int r = active ? i - 1 : 0, key = r >> 3;
+        const bool need = active && (key != wkey || wj - j >= 16);
+        if (wp::ballot(need)) {
+            if (need) {                                     // refill this half's 16-column window of lane-row `key`
+                wkey = key; wj = j;
+                const int cj = j - hl, rb = key >> 5, l = key & 31;
+                uint2 w2 = make_uint2(0u, 0u);
+                if (cj >= 1) w2 = wp::ldcg2(tb2 + ((int64_t)rb * TS + cj + l) * 32 + l);
+                wreg = hb ? ((w2.x & 0xffff0000u) | (w2.y >> 16)) : ((w2.x << 16) | (w2.y & 0xffffu));
+            }
+        }
+        const uint32_t v = wp::shflu(wreg, hb | ((wj - j) & 15)) >> (2 * (7 - (r & 7)));
+        if (active) {
+            const int op = s;
+            s = (s == OP_M) ? (int)((v >> 16) & 3u) : (int)(v & (uint32_t)s);
+            err |= (s == 3);
+            i -= (op != OP_I); j -= (op != OP_J);
+            C2B_PUSH2(op);
+        }
+    }
+    if (j > 0 && s != OP_I) err = 1;
+    if (i > 0 && s != OP_J) err = 1;
+    while (j > 0) { j--; C2B_PUSH2(OP_I); }
+    while (i > 0) { i--; C2B_PUSH2(OP_J); }
+#undef C2B_PUSH2
+    if (n & 15) {
+        const int ix = n >> 4, used = 2 * (n & 15);
+        const uint32_t a = (acc >> (32 - used)) | (~0u << used);
+        if (hl == (ix >> 1)) { if (ix & 1) hi = a; else lo = a; }
+    }
+    Walked out; out.ops = (uint64_t)lo | ((uint64_t)hi << 32); out.n = n; out.err = err;
+    return out;
+}
+
+C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint8_t *combo, int J, uint2 *tb2, int32_t *bnd)
+{
+    uint32_t cM = 0, cX = 0, cY = 0;
+    const int bstride = 3 * (P.TS);
+    const int nrb = R.nrb;
+    for (int rb = 0; rb < nrb; rb++) {
+        dp_dispatch2(P, R, combo, J, rb, tb2, bnd + ((rb + 1) & 1) * bstride, bnd + (rb & 1) * bstride, cM, cX, cY);
+        wp::sync();
+    }
+    const uint32_t s2 = wp::max3_2(cM, cY, cX) & PK_TM;         // start state per half
+    const int s = (wp::lane() & 16) ? (int)(s2 >> 16) : (int)(s2 & 3u);
+    return walk2(P, R, J, tb2, s);
+}
+
+// Two reads (rdA, rdB) of equal length J through the packed path.  Per-lane variables belong to the lane's half.
+C2B_DEV void process_pair(const KParams &P, WarpSmem &S, int64_t rdA, int64_t rdB, int warp_slot)
+{
+    const int lane = wp::lane(), h = lane >> 4, hl = lane & 15;
+    const int64_t myrd = h ? rdB : rdA;
+    const int J = (int)(P.offsets[rdA + 1] - P.offsets[rdA]);
+    uint2 *tb2 = reinterpret_cast<uint2 *>(P.tb + (int64_t)warp_slot * P.tb_words_per_warp);
+    int32_t *bnd = P.bnd + (int64_t)warp_slot * P.bnd_words_per_warp;
+    uint64_t *opsbuf = P.opsbuf + (int64_t)warp_slot * P.n_refs * 32;
+    uint8_t *rowinfo = S.rowinfo + h * PK_ROWINFO_STRIDE;
+    uint32_t *rowins = S.rowins + h * PK_ROWINS_STRIDE;
+
+    c2b_read_rec rec; rec.winner_mask = 0; rec.best_score_milli = -1000; rec.best_ref = -1; rec.n_winners = 0;
+    rec.ambiguous = 0; rec.status = 0;
+    const bool badA = load_codes(P, P.offsets[rdA], J, S.fw[0], S.rc[0]);
+    const bool badB = load_codes(P, P.offsets[rdB], J, S.fw[1], S.rc[1]);
+    const uint32_t st = (h ? badB : badA) ? C2B_ST_BAD_CHAR : 0u;
+    wp::sync();
+
+    const int r_begin = P.ref_id ? P.ref_id[rdA] : 0;
+    const int r_end = P.ref_id ? r_begin + 1 : P.n_refs;
+    const bool multi = (r_end - r_begin) > 1;
+    int keep_irr = 0;
+
+    for (int r = r_begin; r < r_end; r++) {
+        const RefDev &R = P.refs[r];
+        c2b_aln_rec a; init_aln(a, st);
+        const int mA = strand_mode(P, R, S.fw[0], J), mB = strand_mode(P, R, S.fw[1], J);
+        const int mode = h ? mB : mA;
+        const int npass = (mA == 2 || mB == 2) ? 2 : 1;
+        uint64_t bops = ~0ull; int bn = 0, bstrand = 0, bscore = -1000000;
+        for (int pass = 0; pass < npass; pass++) {
+            // strand of each read in this pass: a one-strand read repeats its only strand in pass 1 (result unused)
+            const int sA = (mA == 2) ? pass : (mA == 1), sB = (mB == 2) ? pass : (mB == 1);
+            const uint8_t *cA = sA ? S.rc[0] : S.fw[0], *cB = sB ? S.rc[1] : S.fw[1];
+            wp::sync();
+            for (int p = lane; p < J; p += 32) S.combo[p] = (uint8_t)(cA[p] * P.nq + cB[p]);
+            wp::sync();
+            const Walked wk = align_pair(P, R, S.combo, J, tb2, bnd);
+            const int mystrand = h ? sB : sA;
+            if (wk.err) a.status |= C2B_ST_UNDEFINED;
+            int sc = -1000000;
+            if (wp::ballot(mode == 2)) {
+                const ColOut c0 = columns<true>(P, R, rowinfo, rowins, mystrand ? S.rc[h] : S.fw[h], J, wk.ops, wk.n, 0, nullptr, nullptr);
+                sc = score_milli(c0.n_match, wk.n);
+            }
+            // pass 1 of a both-strand read is its reverse complement: it replaces the forward result only if strictly better
+            if (pass == 0 || (mode == 2 && sc > bscore)) { bops = wk.ops; bn = wk.n; bstrand = mystrand; bscore = sc; }
+        }
+        for (int p = lane; p < 2 * PK_ROWINS_STRIDE; p += 32) S.rowins[p] = 0;
+        wp::sync();
+        uint8_t *o_read = P.strings ? P.strings + ((myrd * P.n_refs + r) * 2) * (int64_t)P.W : nullptr;
+        uint8_t *o_ref = o_read ? o_read + P.W : nullptr;
+        int cmode = (o_read ? 1 : 0) | (multi ? 0 : 2);
+        if (a.status) cmode = 0;
+        const ColOut co = columns<true>(P, R, rowinfo, rowins, bstrand ? S.rc[h] : S.fw[h], J, bops, bn, cmode, o_read, o_ref);
+        if (!a.status) {
+            a.n_match = (uint16_t)co.n_match; a.aln_len = (uint16_t)bn; a.strand = (uint8_t)bstrand;
+            a.score_milli = score_milli(co.n_match, bn);
+            a.irregular_ends = (uint8_t)co.irregular;
+            keep_irr = co.irregular;
+            note_score(rec, R, r, a.score_milli);
+        }
+        if (multi) opsbuf[r * 32 + lane] = bops;
+        rec.status |= a.status;
+        if (hl == 0 && (h == 0 || rdB != rdA)) P.alns[myrd * P.n_refs + r] = a;
+    }
+    wp::sync();
+    // classification runs with the whole warp, one read at a time: broadcast that half's bookkeeping to every lane
+    for (int hh = 0; hh < 2; hh++) {
+        if (hh == 1 && rdB == rdA) break;
+        const int src = 16 * hh;
+        c2b_read_rec rr;
+        rr.winner_mask = wp::shflu(rec.winner_mask, src); rr.best_score_milli = wp::shfl(rec.best_score_milli, src);
+        rr.best_ref = -1; rr.n_winners = (uint8_t)wp::shfl((int)rec.n_winners, src); rr.ambiguous = 0;
+        rr.status = wp::shflu(rec.status, src);
+        const int irr = wp::shfl(keep_irr, src);
+        finish_read(P, hh ? rdB : rdA, rr, J, S.fw[hh], S.rc[hh], S.rowinfo + hh * PK_ROWINFO_STRIDE,
+                    S.rowins + hh * PK_ROWINS_STRIDE, r_begin, r_end, opsbuf, src, irr);
+        wp::sync();
+    }
+}
+
+// Work item w = reads 2w and 2w+1.  Equal lengths inside every reference's proven 16-bit range -> packed pair;
+// otherwise each read takes the 32-bit path.
+C2B_DEV void process_item(const KParams &P, WarpSmem &S, int64_t w, int warp_slot)
+{
+    const int64_t rdA = 2 * w, rdB = 2 * w + 1;
+    const bool haveB = rdB < P.n_reads;
+    bool pair = !P.forced_ops && !(P.flags & C2B_F_NO_PAIRING);
+    if (pair) {
+        const int Ja = (int)(P.offsets[rdA + 1] - P.offsets[rdA]);
+        const int Jb = haveB ? (int)(P.offsets[rdB + 1] - P.offsets[rdB]) : Ja;
+        pair = (Ja == Jb) && Ja >= 1 && Ja + 32 <= P.TS;
+        if (pair && P.ref_id && haveB && P.ref_id[rdA] != P.ref_id[rdB]) pair = false;
+        if (pair) {
+            const int r_begin = P.ref_id ? P.ref_id[rdA] : 0, r_end = P.ref_id ? r_begin + 1 : P.n_refs;
+            for (int r = r_begin; r < r_end; r++) if (Ja > P.refs[r].pk_maxJ) pair = false;
+        }
+    }
+    if (wp::lane() == 0) wp::addg(P.work_counter + (pair ? 1 : 2), 1);      // path statistics (c2b_path_counts)
+    if (pair) process_pair(P, S, rdA, haveB ? rdB : rdA, warp_slot);
+    else {
+        process_read(P, S, rdA, warp_slot);
+        if (haveB) { wp::sync(); process_read(P, S, rdB, warp_slot); }
+    }
 }
 
 }  // namespace c2b

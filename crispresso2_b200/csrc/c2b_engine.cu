@@ -71,11 +71,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) c2b_align_classify_kern
     WarpSmem *S = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
     const int warp_slot = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     for (;;) {
-        unsigned long long rd = 0;
-        if ((threadIdx.x & 31) == 0) rd = wp::fetch_work(P.work_counter);
-        rd = __shfl_sync(0xffffffffu, rd, 0);
-        if (rd >= (unsigned long long)P.n_reads) break;
-        process_read(P, *S, (int64_t)rd, warp_slot);
+        unsigned long long w = 0;
+        if ((threadIdx.x & 31) == 0) w = wp::fetch_work(P.work_counter);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (2 * w >= (unsigned long long)P.n_reads) break;
+        process_item(P, *S, (int64_t)w, warp_slot);       // reads 2w, 2w+1
         __syncwarp();
     }
 }
@@ -225,6 +225,7 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
         max_nrb = std::max(max_nrb, nrb);
         base[r] = bytes;
         bytes += al((size_t)p->nq * Ipad * 4) + 2 * al((size_t)Ipad * 4) + 2 * al(Ipad) + al(Ipad + 1) + al((size_t)(Ipad + 2) * 2);
+        bytes += al((size_t)p->nq * p->nq * Ipad * 4) + 2 * al((size_t)Ipad * 4);      // packed-path tables
     }
     const size_t refs_off = bytes;
     bytes += al(sizeof(RefDev) * n_refs);
@@ -253,6 +254,9 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
         uint8_t *rcode = hb + o; d.rcode = db + o; o += al(Ipad);
         uint8_t *incl = hb + o; d.incl = db + o; o += al(Ipad + 1);
         uint16_t *cum = (uint16_t *)(hb + o); d.cum = (const uint16_t *)(db + o); o += al((size_t)(Ipad + 2) * 2);
+        uint32_t *prof2 = (uint32_t *)(hb + o); d.prof2 = (const uint32_t *)(db + o); o += al((size_t)p->nq * p->nq * Ipad * 4);
+        uint32_t *cIe2 = (uint32_t *)(hb + o); d.cIe2 = (const uint32_t *)(db + o); o += al((size_t)Ipad * 4);
+        uint32_t *g42 = (uint32_t *)(hb + o); d.g42 = (const uint32_t *)(db + o); o += al((size_t)Ipad * 4);
         const int64_t lim = (1ll << 27);
         for (int q = 0; q < p->nq; q++)
             for (int i = 0; i < I; i++) {
@@ -270,6 +274,39 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
             rcode[row] = (uint8_t)code;
         }
         d.gi0_4 = (int32_t)(4 * rf.gap_incentive[0]);
+        {   // packed 16-bit path: biased scores (beta = -gap_extend per unit of i+j) + offset; see DESIGN.md section 6
+            const int64_t go = p->gap_open, ge = p->gap_extend, beta = -ge, OFFu = 512;
+            int64_t gmin = rf.gap_incentive[0], gmax = rf.gap_incentive[0], smin = rf.score_rows[0], smax = rf.score_rows[0];
+            for (int i = 0; i <= I; i++) { gmin = std::min(gmin, rf.gap_incentive[i]); gmax = std::max(gmax, rf.gap_incentive[i]); }
+            for (size_t k = 0; k < (size_t)p->nq * I; k++) { smin = std::min(smin, rf.score_rows[k]); smax = std::max(smax, rf.score_rows[k]); }
+            bool ok = go <= ge && ge <= 0 && gmin >= 0 && gmax <= 64 && smin + 2 * beta >= 0 && smax + 2 * beta <= 1000 &&
+                      (go - ge) > -1900 && 4 * (OFFu + (go - ge)) > 256 + 4 * gmax + 3 + 64 && !(p->flags & C2B_F_NO_PAIRING);
+            d.pk_maxJ = 0;
+            if (ok) {
+                for (int J = 1; J <= C2B_MAX_READ_LEN && I + J <= PK_MAX_ALN; J++) {
+                    const int64_t bound = 4 * ((smax + 2 * beta) * std::min(I, J) + gmax * (I + J + 2) + OFFu) + 3;
+                    if (bound > 32000) break;
+                    d.pk_maxJ = J;
+                }
+            }
+            const uint32_t rep = 0x00010001u;
+            d.pk_XB = (uint32_t)((4 * (rf.gap_incentive[0] + OFFu)) | 2) * rep;
+            d.pk_YB = (uint32_t)((4 * (rf.gap_incentive[0] + OFFu)) | 1) * rep;
+            d.pk_M00 = (uint32_t)(4 * OFFu) * rep;
+            if (d.pk_maxJ > 0) {
+                for (int qa = 0; qa < p->nq; qa++)
+                    for (int qb = 0; qb < p->nq; qb++)
+                        for (int i = 0; i < I; i++) {
+                            const uint32_t a = (uint32_t)(4 * (rf.score_rows[(size_t)qa * I + i] + 2 * beta));
+                            const uint32_t b = (uint32_t)(4 * (rf.score_rows[(size_t)qb * I + i] + 2 * beta));
+                            prof2[((size_t)qa * p->nq + qb) * Ipad + i] = a | (b << 16);
+                        }
+                for (int row = 0; row < I; row++) {
+                    cIe2[row] = (uint32_t)(4 * rf.gap_incentive[row + 1]) * rep;
+                    g42[row] = (uint32_t)(4 * rf.gap_incentive[row]) * rep;
+                }
+            }
+        }
         for (int k = 0; k < rf.n_include; k++) {
             const int64_t v = rf.include_idx[k];
             if (v >= 0 && v < I) incl[v] = 1;
@@ -319,7 +356,7 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
     const int TS = ((maxJ + 32 + 31) & ~31);
     if (TS <= e->scratch_TS) return C2B_OK;
     int rc;
-    if ((rc = ensure(e, e->tb, (size_t)e->n_warps * e->max_nrb * TS * 32 * 4))) return rc;
+    if ((rc = ensure(e, e->tb, (size_t)e->n_warps * e->max_nrb * TS * 64 * 4))) return rc;   // 64: a pair stores two words per lane
     if ((rc = ensure(e, e->bnd, (size_t)e->n_warps * 2 * 3 * TS * 4))) return rc;
     if ((rc = ensure(e, e->ops, (size_t)e->n_warps * e->n_refs * 32 * 8))) return rc;
     if ((rc = ensure(e, e->work, 64))) return rc;
@@ -330,7 +367,7 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
             !getenv("C2B_NO_L2_PERSIST")) {
-            const size_t slab = (size_t)e->n_warps * e->max_nrb * TS * 32 * 4;
+            const size_t slab = (size_t)e->n_warps * e->max_nrb * TS * 64 * 4;
             const size_t carve = std::min((size_t)prop.persistingL2CacheMaxSize, slab);
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
             cudaStreamAttrValue av; memset(&av, 0, sizeof av);
@@ -372,13 +409,13 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     P.flags = e->prm.flags; P.nq = e->prm.nq;
     memcpy(P.alpha, e->prm.alphabet, C2B_MAX_Q); memcpy(P.comp, e->prm.complement, C2B_MAX_Q);
     P.TS = e->scratch_TS;
-    P.tb = (uint32_t *)e->tb.p; P.tb_words_per_warp = (int64_t)e->max_nrb * P.TS * 32;
+    P.tb = (uint32_t *)e->tb.p; P.tb_words_per_warp = (int64_t)e->max_nrb * P.TS * 64;
     P.bnd = (int32_t *)e->bnd.p; P.bnd_words_per_warp = 2 * 3 * (int64_t)P.TS;
     P.opsbuf = (uint64_t *)e->ops.p;
     P.work_counter = (unsigned long long *)e->work.p;
     P.vstride = e->vstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
-    RTCHK(rt_zero(e->work.p, 8, e->stream));
+    RTCHK(rt_zero(e->work.p, 24, e->stream));
 #ifndef C2B_EMU
     cudaEventRecord(e->ev0, e->stream);
     c2b_align_classify_kernel<<<e->grid, WARPS_PER_CTA * 32, sizeof(WarpSmem) * WARPS_PER_CTA, e->stream>>>(P);
@@ -387,7 +424,7 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
 #else
     {
         static WarpSmem S;
-        for (int64_t rd = 0; rd < n_reads; rd++) emu::run_warp([&]() { process_read(P, S, rd, 0); });
+        for (int64_t w = 0; 2 * w < n_reads; w++) emu::run_warp([&]() { process_item(P, S, w, 0); });
     }
 #endif
     e->launches++;
@@ -417,6 +454,17 @@ double c2b_last_kernel_ms(c2b_engine *e)
 }
 
 int64_t c2b_launch_count(const c2b_engine *e) { return e ? e->launches : 0; }
+
+int c2b_path_counts(c2b_engine *e, int64_t *pair_items, int64_t *single_items)
+{
+    if (!e || !e->work.p) return fail(e, C2B_E_STATE, "c2b_path_counts: nothing launched yet");
+    int64_t v[3] = {0, 0, 0};
+    RTCHK(rt_d2h(v, e->work.p, 24, e->stream));
+    RTCHK(rt_sync(e->stream));
+    if (pair_items) *pair_items = v[1];
+    if (single_items) *single_items = v[2];
+    return C2B_OK;
+}
 
 int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads,
                     const int32_t *count, const int32_t *qweight, const int32_t *ref_id,

@@ -215,5 +215,11 @@ class Engine:
     def last_kernel_ms(self):
         return float(self.L.c2b_last_kernel_ms(self.h))
 
+    def path_counts(self):
+        """(pair_items, single_items) of the last launch: how many work items took the packed 16-bit path."""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.L.c2b_path_counts(self.h, C.byref(a), C.byref(b)), "c2b_path_counts")
+        return a.value, b.value
+
     def launch_count(self):
         return int(self.L.c2b_launch_count(self.h))

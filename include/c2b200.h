@@ -42,6 +42,7 @@ extern "C" {
 #define C2B_F_ASSIGN_FIRST         16u
 #define C2B_F_DISCARD_INDEL_READS  32u
 #define C2B_F_NO_STRAND_SEARCH     64u   /* global_align-only mode: forward strand, no seed test */
+#define C2B_F_NO_PAIRING          128u   /* debugging / A-B runs: never use the packed two-reads-per-warp path */
 
 typedef struct {
     int32_t  gap_open;        /* args.needleman_wunsch_gap_open   (Align.pyx:104) */
@@ -181,6 +182,8 @@ int  c2b_sync(c2b_engine *e);
 void *c2b_stream(c2b_engine *e);                    /* cudaStream_t of the engine */
 double c2b_last_kernel_ms(c2b_engine *e);           /* CUDA-event time of the last align kernel launch */
 int64_t c2b_launch_count(const c2b_engine *e);      /* kernels launched by this engine so far */
+/* work items of the LAST launch that took the packed two-reads-per-warp path / the 32-bit one-read path */
+int  c2b_path_counts(c2b_engine *e, int64_t *pair_items, int64_t *single_items);
 
 /* replaces: the count vectors / counters built by the quantification loop (CRISPRessoCORE.py:3841-3907,
  * :3964-4115).  Layout above.  c2b_counts_device exposes the block for an NCCL all-reduce.            */

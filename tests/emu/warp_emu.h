@@ -19,6 +19,8 @@
 #define C2B_DEVNOINL static
 struct int4 { int x, y, z, w; };
 struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t a, uint32_t b) { uint2 r = {a, b}; return r; }
 static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { uint4 r = {a, b, c, d}; return r; }
 
 namespace emu {
@@ -68,6 +70,7 @@ C2B_DEV int lane() { return emu::g_warp->cur; }
 C2B_DEV int shfl_up(int v, int d) { return (int)(uint32_t)emu::exchange((uint32_t)v, 1, [](int l, int a) { return l >= a ? l - a : l; }, d); }
 C2B_DEV int shfl(int v, int src) { return (int)(uint32_t)emu::exchange((uint32_t)v, 2, [](int, int a) { return a & 31; }, src); }
 C2B_DEV uint32_t shflu(uint32_t v, int src) { return (uint32_t)emu::exchange(v, 2, [](int, int a) { return a & 31; }, src); }
+C2B_DEV uint32_t shflu_up(uint32_t v, int d) { return (uint32_t)emu::exchange(v, 1, [](int l, int a) { return l >= a ? l - a : l; }, d); }
 C2B_DEV int shfl_xor(int v, int m) { return (int)(uint32_t)emu::exchange((uint32_t)v, 3, [](int l, int a) { return (l ^ a) & 31; }, m); }
 C2B_DEV uint32_t ballot(bool p)
 {
@@ -79,6 +82,15 @@ C2B_DEV uint32_t ballot(bool p)
 C2B_DEV void sync() { emu::exchange(0, 5, [](int l, int) { return l; }, 0); }
 C2B_DEV int max3(int a, int b, int c) { return std::max(a, std::max(b, c)); }
 C2B_DEV int addmax(int a, int b, int c) { return std::max(a + b, c); }
+static inline int16_t h_lo(uint32_t v) { return (int16_t)(v & 0xffffu); }
+static inline int16_t h_hi(uint32_t v) { return (int16_t)(v >> 16); }
+static inline uint32_t h_pack(int lo, int hi) { return ((uint32_t)(uint16_t)(int16_t)lo) | (((uint32_t)(uint16_t)(int16_t)hi) << 16); }
+C2B_DEV uint32_t max3_2(uint32_t a, uint32_t b, uint32_t c)
+{ return h_pack(std::max<int>(h_lo(a), std::max<int>(h_lo(b), h_lo(c))), std::max<int>(h_hi(a), std::max<int>(h_hi(b), h_hi(c)))); }
+C2B_DEV uint32_t addmax_2(uint32_t a, uint32_t b, uint32_t c)
+{ return h_pack(std::max<int>((int16_t)(h_lo(a) + h_lo(b)), h_lo(c)), std::max<int>((int16_t)(h_hi(a) + h_hi(b)), h_hi(c))); }
+C2B_DEV uint4 ldg4u(const uint4 *p) { return *p; }
+C2B_DEV uint2 ldcg2(const uint2 *p) { return *p; }
 C2B_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31)); }
 C2B_DEV int popc(uint32_t x) { return __builtin_popcount(x); }
 C2B_DEV int popcll(uint64_t x) { return __builtin_popcountll(x); }
