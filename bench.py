@@ -233,6 +233,7 @@ def main():
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
+    pair_items, single_items = eng.path_counts()
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=3)
@@ -331,7 +332,8 @@ def main():
             "config": {"workload": "synthetic 1M x 250 bp reads, 1 amplicon (BASELINE.json configs[1]), every read aligned",
                        "reads_per_gpu_per_step": n, "amplicon_len": AMP_LEN, "read_len": READ_LEN, "parallelism": "read-shard x%d" % world,
                        "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2" % ((h2d + d2h) / 1e9),
-                       "edit_cap": args.edit_cap, "aligned_fraction": aligned_frac, "parity_gate": bool(gate_ok and e2e_gate)},
+                       "edit_cap": args.edit_cap, "aligned_fraction": aligned_frac,
+                       "packed_pair_items": pair_items, "single_items": single_items, "parity_gate": bool(gate_ok and e2e_gate)},
             "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(launches),

@@ -295,37 +295,39 @@ C2B_DEVNOINL ColOut columns(const KParams &P, const RefDev &R, uint8_t *rowinfo,
     for (int d = 1; d < (HALF ? 16 : 32); d <<= 1) { int v = wp::shfl_up(pk, d); if (li >= d) pk += v; }
     pk -= (ci << 16) | cj;                               // exclusive
     int i = R.I - (pk >> 16), j = J - (pk & 0xffff);
-    uint32_t wr[8], wf[8];
-#pragma unroll
-    for (int q = 0; q < 8; q++) { wr[q] = 0; wf[q] = 0; }
     int match = 0, irr = 0;
     const int n0 = 32 * li;
     if (n0 < n) {
+        // Right-aligned slots: column n (from the right) lives at byte W-1-n, so the lane's 32 columns are one
+        // contiguous 32-byte sector, written as 8 aligned words (4 columns each).  The loop is deliberately not
+        // unrolled 32x: this code runs once per read and must not evict the DP loop from the instruction cache.
+        uint32_t *pr = (mode & 1) ? reinterpret_cast<uint32_t *>(out_read + P.W - n0 - 4) : nullptr;
+        uint32_t *pf = (mode & 1) ? reinterpret_cast<uint32_t *>(out_ref + P.W - n0 - 4) : nullptr;
+        uint64_t rest = ops;
+#pragma unroll 1
+        for (int w = 0; w < 8; w++) {
+            uint32_t wr = 0, wf = 0;
 #pragma unroll
-        for (int e = 0; e < 32; e++) {
-            const int op = (int)(ops >> (2 * e)) & 3;
-            if (op != OP_NONE) {
-                const int code = (op != OP_J) ? codes[j - 1] : 0;
-                const uint32_t rd = (op == OP_J) ? (uint32_t)'-' : (uint32_t)P.alpha[code];
-                const uint32_t rf = (op == OP_I) ? (uint32_t)'-' : (uint32_t)R.asc[i - 1];
-                if (op == OP_M && rd == rf) match++;
-                if ((n0 + e == 0 || n0 + e == n - 1) && (op != OP_M || rd != rf)) irr = 1;   // CRISPRessoCORE.py:729-733
-                const int byte = 15 - (e & 15), wi = (e >> 4) * 4 + (byte >> 2), sh = 8 * (byte & 3);
-                wr[wi] |= rd << sh; wf[wi] |= rf << sh;
-                if (mode & 2) {
-                    if (op == OP_M) rowinfo[i - 1] = (uint8_t)code;
-                    else if (op == OP_J) rowinfo[i - 1] = 8;
-                    else if (i > 0 && i < R.I) wp::adds(&rowins[i], 1u);
+            for (int e = 0; e < 4; e++) {
+                const int op = (int)rest & 3;
+                rest >>= 2;
+                if (op != OP_NONE) {
+                    const int code = (op != OP_J) ? codes[j - 1] : 0;
+                    const uint32_t rd = (op == OP_J) ? (uint32_t)'-' : (uint32_t)P.alpha[code];
+                    const uint32_t rf = (op == OP_I) ? (uint32_t)'-' : (uint32_t)R.asc[i - 1];
+                    if (op == OP_M && rd == rf) match++;
+                    const int nn = n0 + 4 * w + e;
+                    if ((nn == 0 || nn == n - 1) && (op != OP_M || rd != rf)) irr = 1;   // CRISPRessoCORE.py:729-733
+                    wr |= rd << (8 * (3 - e)); wf |= rf << (8 * (3 - e));
+                    if (mode & 2) {
+                        if (op == OP_M) rowinfo[i - 1] = (uint8_t)code;
+                        else if (op == OP_J) rowinfo[i - 1] = 8;
+                        else if (i > 0 && i < R.I) wp::adds(&rowins[i], 1u);
+                    }
+                    i -= (op != OP_I); j -= (op != OP_J);
                 }
-                i -= (op != OP_I); j -= (op != OP_J);
             }
-        }
-        if (mode & 1) {
-            // right-aligned slots: column n (from the right) lives at byte W-1-n
-            uint4 *pr = reinterpret_cast<uint4 *>(out_read + P.W - 32 * li - 16);
-            uint4 *pf = reinterpret_cast<uint4 *>(out_ref + P.W - 32 * li - 16);
-            pr[0] = make_uint4(wr[0], wr[1], wr[2], wr[3]); pf[0] = make_uint4(wf[0], wf[1], wf[2], wf[3]);
-            if (n0 + 16 < n) { pr[-1] = make_uint4(wr[4], wr[5], wr[6], wr[7]); pf[-1] = make_uint4(wf[4], wf[5], wf[6], wf[7]); }
+            if ((mode & 1) && n0 + 4 * w < n) { pr[-w] = wr; pf[-w] = wf; }
         }
     }
 #pragma unroll

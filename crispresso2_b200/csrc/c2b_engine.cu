@@ -63,13 +63,13 @@ static void rt_host_free(void *p) { free(p); }
 
 // ----------------------------------------------------------------------------------------- kernel
 #ifndef C2B_EMU
-constexpr int WARPS_PER_CTA = 8;
+constexpr int WARPS_PER_CTA = 8;      // launch-bounds maximum; the launch may use fewer (C2B_WARPS_PER_CTA)
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) c2b_align_classify_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSmem *S = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
-    const int warp_slot = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const int warp_slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     for (;;) {
         unsigned long long w = 0;
         if ((threadIdx.x & 31) == 0) w = wp::fetch_work(P.work_counter);
@@ -104,7 +104,7 @@ struct c2b_engine {
     unsigned long long *d_counts = nullptr; size_t counts_n = 0;
     // scratch
     DevBuf tb, bnd, ops, work;
-    int n_warps = 0, grid = 0;
+    int n_warps = 0, grid = 0, wpc = 8;
     int scratch_TS = 0;
     // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
     struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed; int64_t *h_off = nullptr; size_t h_off_cap = 0;
@@ -155,8 +155,11 @@ int c2b_create(int device, c2b_engine **out)
                                                                             sizeof(WarpSmem) * WARPS_PER_CTA);
     if (r != cudaSuccess) { g_create_err = std::string("c2b_create: ") + cudaGetErrorString(r); delete e; return C2B_E_CUDA; }
     if (occ < 1) occ = 1;
-    e->grid = nsm * occ;                 // persistent: one wave of CTAs, warps pull reads from a counter
-    e->n_warps = e->grid * WARPS_PER_CTA;
+    e->wpc = WARPS_PER_CTA;
+    if (const char *v = getenv("C2B_WARPS_PER_CTA")) { int k = atoi(v); if (k >= 1 && k <= WARPS_PER_CTA) e->wpc = k; }
+    if (const char *v = getenv("C2B_CTAS_PER_SM")) { int k = atoi(v); if (k >= 1 && k <= occ) occ = k; }
+    e->grid = nsm * occ;                 // persistent: one wave of CTAs, warps pull work items from a counter
+    e->n_warps = e->grid * e->wpc;
 #else
     e->grid = 1; e->n_warps = 1;
 #endif
@@ -378,6 +381,10 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
             cudaGetLastError();
+            if (getenv("C2B_VERBOSE"))
+                fprintf(stderr, "[c2b] grid %d x %d warps, traceback slab %.1f MB, persisting L2 max %.1f MB (L2 %.1f MB), window %.1f MB, hitRatio %.2f\n",
+                        e->grid, e->wpc, slab / 1e6, prop.persistingL2CacheMaxSize / 1e6, prop.l2CacheSize / 1e6,
+                        av.accessPolicyWindow.num_bytes / 1e6, av.accessPolicyWindow.hitRatio);
         }
     }
 #endif
@@ -418,7 +425,7 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     RTCHK(rt_zero(e->work.p, 24, e->stream));
 #ifndef C2B_EMU
     cudaEventRecord(e->ev0, e->stream);
-    c2b_align_classify_kernel<<<e->grid, WARPS_PER_CTA * 32, sizeof(WarpSmem) * WARPS_PER_CTA, e->stream>>>(P);
+    c2b_align_classify_kernel<<<e->grid, e->wpc * 32, sizeof(WarpSmem) * e->wpc, e->stream>>>(P);
     cudaEventRecord(e->ev1, e->stream);
     RTCHK(cudaGetLastError());
 #else

@@ -95,3 +95,26 @@ def test_bad_symbols_and_empty(emu):
     assert len(emu.align([]).recs) == 0
     res = emu.align([amp, amp[:50] + "x" + amp[51:]])
     assert res.recs["status"][0] == 0 and res.recs["status"][1] == _lib.ST_BAD_CHAR
+
+
+def test_packed_pair_path_equals_32bit_path(emu):
+    rng = np.random.default_rng(77)
+    amp = synth.random_amplicon(rng, 180)
+    ref = synth.amplicon_setup(amp, guide_start=80)
+    base = synth.synth_reads(rng, amp, 120, 180, sub_rate=0.03, rc_frac=0.1, n_rate=0.004, cut=ref["cut_point"])
+    reads = [r.tobytes().decode() for r in base]
+    for k in range(0, len(reads), 5):
+        reads[k] = reads[k][: 60 + (k % 100)]
+    out = []
+    for flags in (0, _lib.F_NO_PAIRING):
+        emu.configure({"Reference": ref}, ["Reference"], O.make_matrix(), -20, -2, 5, 2, flags, "ACGTN", 40)
+        emu.counts_reset()
+        res = emu.align(reads)
+        out.append((res, emu.counts_raw(), emu.path_counts()))
+    (a, ca, pa), (b, cb, pb) = out
+    assert pa[0] > 10 and pa[1] > 5 and pb[0] == 0
+    assert (a.recs == b.recs).all() and (a.alns == b.alns).all() and (ca == cb).all()
+    for i in range(len(reads)):
+        assert a.pair(i) == b.pair(i)
+        n = int(a.alns[i, 0]["n_edits"])
+        assert (a.edits[i, 0, :n] == b.edits[i, 0, :n]).all()

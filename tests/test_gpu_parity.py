@@ -163,3 +163,31 @@ def test_empty_batch_and_bad_symbols(eng):
     assert len(res.recs) == 0
     res = eng.align([amp, amp[:50] + "x" + amp[51:], amp.lower()[:60]])
     assert res.recs["status"][0] == 0 and res.recs["status"][1] == _lib.ST_BAD_CHAR and res.recs["status"][2] == _lib.ST_BAD_CHAR
+
+
+def test_packed_pair_path_equals_32bit_path(eng):
+    """The two-reads-per-warp 16-bit path and the one-read 32-bit path must agree bit for bit (records, strings,
+    edit lists, count block) -- mixed lengths so that both pairs and singles occur in the default run."""
+    rng = np.random.default_rng(77)
+    amp = synth.random_amplicon(rng, 250)
+    ref = synth.amplicon_setup(amp)
+    base = synth.synth_reads(rng, amp, 40000, 250, sub_rate=0.02, rc_frac=0.05, n_rate=0.002, cut=ref["cut_point"])
+    reads = [r.tobytes().decode() for r in base]
+    for k in range(0, len(reads), 7):                      # every 7th read shortened: breaks some pairs
+        reads[k] = reads[k][: 100 + (k % 140)]
+    buf, off = pack_reads(reads)
+    out = []
+    for flags in (0, _lib.F_NO_PAIRING):
+        eng.configure({"Reference": ref}, ["Reference"], O.make_matrix(), -20, -2, 5, 2, flags, "ACGTN", 24)
+        eng.counts_reset()
+        res = eng.align_packed(buf, off)
+        out.append((res, eng.counts_raw(), eng.path_counts()))
+    (a, ca, pa), (b, cb, pb) = out
+    assert pa[0] > 10000 and pa[1] > 1000 and pb[0] == 0
+    assert (a.recs == b.recs).all() and (a.alns == b.alns).all() and (ca == cb).all()
+    W = a.W
+    cols = np.arange(W)[None, :] >= (W - a.alns[:, 0]["aln_len"].astype(np.int64))[:, None]
+    assert ((a.strings[:, 0] == b.strings[:, 0]) | ~cols[:, None, :]).all()
+    ne = a.alns[:, 0]["n_edits"].astype(np.int64)
+    valid = np.arange(24)[None, :] < np.minimum(ne, 24)[:, None]
+    assert ((a.edits[:, 0] == b.edits[:, 0]) | ~valid).all()
