@@ -82,7 +82,7 @@ class LibraryMissing(ImportError):
 def load(path=None):
     """Loads the engine library.  `path` is a test hook (the CPU warp-emulator build under tests/emu/);
     the product default is the nvcc-built libc2b200.so next to this file."""
-    path = path or DEFAULT_LIB
+    path = path or os.environ.get("C2B200_LIB") or DEFAULT_LIB     # C2B200_LIB: another nvcc build variant (A/B runs)
     if path in _cache:
         return _cache[path]
     if not os.path.exists(path):

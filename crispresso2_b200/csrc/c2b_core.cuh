@@ -217,43 +217,76 @@ C2B_DEV void dp_dispatch(const KParams &P, const RefDev &R, const uint8_t *codes
 }
 
 // ------------------------------------------------------------------------------------------- traceback
-// Warp-uniform walk from (I,J) to (0,0) (Align.pyx:338-421).  Lane L ends up holding ops 32L..32L+31
-// (2 bits each, op n = n-th column from the RIGHT end of the alignment).
-C2B_DEV Walked walk(const KParams &P, const RefDev &R, const int J, const uint32_t *__restrict__ tb, int s)
+// Batched traceback.  The walk of Align.pyx:338-421 moves along one direction per state (M: diagonal, J: up,
+// I: left) and keeps that state while a per-cell bit says "continue" (M: origin tag is M; J/I: the gap extends).
+// A group of G lanes therefore fetches the G next cells of the current direction in one gather, a ballot finds
+// the first cell that breaks the run, and the whole run is consumed in one iteration (a read that matches its
+// amplicon needs I/G iterations instead of I).  PAIR: lanes 0-15 walk read A and lanes 16-31 read B (G = 16,
+// 64-bit slab entries); otherwise the 32 lanes walk one read (G = 32).  Output as before: the group's lane L holds
+// ops 32L..32L+31 (2 bits each, counted from the right end of the alignment).
+template <bool PAIR>
+C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const uint32_t *__restrict__ tb, int s)
 {
     const int lane = wp::lane();
+    const int hl = PAIR ? (lane & 15) : lane, hb = PAIR ? (lane & 16) : 0;
+    const int G = PAIR ? 16 : 32;
+    const uint32_t gmask = PAIR ? 0xffffu : 0xffffffffu;
     const int TS = P.TS;
+    const uint2 *__restrict__ tb2 = reinterpret_cast<const uint2 *>(tb);
     int i = R.I, j = J, n = 0, err = 0;
     uint32_t acc = 0, lo = ~0u, hi = ~0u;
-    int wkey = -1, wj = 0; uint32_t wreg = 0;
-#define C2B_PUSH(op_)                                                                         \
-    do {                                                                                      \
-        acc = wp::funnel_r(acc, (uint32_t)(op_), 2); n++;                                     \
-        if ((n & 15) == 0) { const int ix = (n >> 4) - 1; if (lane == (ix >> 1)) { if (ix & 1) hi = acc; else lo = acc; } } \
-    } while (0)
-    while (i > 0 && j > 0) {
-        const int r = i - 1, key = r >> 3;
-        if (key != wkey || wj - j >= 32) {                 // refill the 32-column window of lane-row `key`
-            wkey = key; wj = j;
-            const int cj = j - lane, rb = key >> 5, l = key & 31;
-            wreg = (cj >= 1) ? wp::ldcg(tb + ((int64_t)rb * TS + cj + l) * 32 + l) : 0u;
+    // append `cnt` (<= 32) copies of op to the stream; acc holds the (n & 15) newest ops in its top bits
+    auto push = [&](int op, int cnt) {
+        const uint32_t pat = (uint32_t)op * 0x55555555u;
+        while (cnt > 0) {
+            const int room = 16 - (n & 15);
+            const int c = cnt < room ? cnt : room;
+            acc = (uint32_t)((((uint64_t)pat << 32) | acc) >> (2 * c));
+            n += c; cnt -= c;
+            if ((n & 15) == 0) { const int ix = (n >> 4) - 1; if (hl == (ix >> 1)) { if (ix & 1) hi = acc; else lo = acc; } }
         }
-        const uint32_t v = wp::shflu(wreg, wj - j) >> (2 * (r & 7));
-        const int op = s;
-        s = (s == OP_M) ? (int)((v >> 16) & 3u) : (int)(v & (uint32_t)s);   // J keeps bit0, I keeps bit1 (= its own code)
-        err |= (s == 3);
-        i -= (op != OP_I); j -= (op != OP_J);
-        C2B_PUSH(op);
+    };
+    for (;;) {
+        const bool active = i > 0 && j > 0;
+        if (!wp::ballot(active)) break;
+        const int di = (s != OP_I), dj = (s != OP_J);
+        const int ci = i - hl * di, cj = j - hl * dj;
+        const bool valid = active && ci >= 1 && cj >= 1;
+        uint32_t v = 0;
+        if (valid) {
+            const int r = ci - 1, key = r >> 3, rb = key >> 5, l = key & 31;
+            const int64_t idx = ((int64_t)rb * TS + cj + l) * 32 + l;
+            if (PAIR) {
+                const uint2 w2 = wp::ldcg2(tb2 + idx);
+                const uint32_t w = hb ? ((w2.x & 0xffff0000u) | (w2.y >> 16)) : ((w2.x << 16) | (w2.y & 0xffffu));
+                v = w >> (2 * (7 - (r & 7)));
+            } else v = wp::ldcg(tb + idx) >> (2 * (r & 7));
+        }
+        const int tag = (int)((v >> 16) & 3u);
+        const bool cont = valid && (s == OP_M ? tag == OP_M : (v & (uint32_t)s) != 0u);
+        const uint32_t bc = (wp::ballot(cont) >> hb) & gmask, bv = (wp::ballot(valid) >> hb) & gmask;
+        const int nvalid = wp::popc(bv);                    // valid lanes are a prefix of the group
+        int f = wp::ffs(~bc) - 1;                           // leading run of "continue" (ffs(0) = 0 -> -1 when all 32 set)
+        if (f < 0 || f > nvalid) f = nvalid;
+        const bool brk = f < nvalid;
+        const int run = brk ? f + 1 : nvalid;
+        const int tagf = wp::shfl(tag, hb + (f < G ? f : G - 1));
+        if (active) {
+            const int news = brk ? (s == OP_M ? tagf : OP_M) : s;
+            push(s, run);
+            i -= run * di; j -= run * dj;
+            err |= (news == 3);
+            s = news;
+        }
     }
-    if (j > 0 && s != OP_I) err = 1;                        // row 0 can only be left along the I border (Align.pyx:153-176)
+    if (j > 0 && s != OP_I) err = 1;                        // row 0 / column 0 can only be left along their own border
     if (i > 0 && s != OP_J) err = 1;
-    while (j > 0) { j--; C2B_PUSH(OP_I); }
-    while (i > 0) { i--; C2B_PUSH(OP_J); }
-#undef C2B_PUSH
+    if (j > 0) { while (j > 0) { const int c = j < 32 ? j : 32; push(OP_I, c); j -= c; } }
+    if (i > 0) { while (i > 0) { const int c = i < 32 ? i : 32; push(OP_J, c); i -= c; } }
     if (n & 15) {
         const int ix = n >> 4, used = 2 * (n & 15);
         const uint32_t a = (acc >> (32 - used)) | (~0u << used);
-        if (lane == (ix >> 1)) { if (ix & 1) hi = a; else lo = a; }
+        if (hl == (ix >> 1)) { if (ix & 1) hi = a; else lo = a; }
     }
     Walked out; out.ops = (uint64_t)lo | ((uint64_t)hi << 32); out.n = n; out.err = err;
     return out;
@@ -272,7 +305,7 @@ C2B_DEV Walked align_strand(const KParams &P, const RefDev &R, const uint8_t *co
         wp::sync();
     }
     const int s = wp::max3(cM, cY, cX) & 3;                     // start state, Align.pyx:349-358
-    return walk(P, R, J, tb, s);
+    return walk_batch<false>(P, R, J, tb, s);
 }
 
 // --------------------------------------------------------------------------------------------- columns
@@ -476,12 +509,18 @@ C2B_DEV int strand_mode(const KParams &P, const RefDev &R, const uint8_t *fw, in
     const int L = R.seed_len, ns = R.nseeds;
     uint32_t hit = 0;                                        // bit s: fw seed s seen ; bit 8+s: rc seed s seen
     if (ns > 0 && L > 0) {
-        for (int p = lane; p + L <= J; p += 32) {
+        // each lane owns 8 consecutive start positions per 256-position block and rolls the packed k-mer along them
+        const uint64_t top = 3 * (uint64_t)(L - 1);
+        for (int base = 8 * lane; base + L <= J; base += 256) {
             uint64_t km = 0;
-            for (int c = 0; c < L; c++) km |= (uint64_t)fw[p + c] << (3 * c);
-            for (int s = 0; s < ns; s++) {
-                if (km == R.fw_seed[s]) hit |= 1u << s;
-                if (km == R.rc_seed[s]) hit |= 1u << (8 + s);
+            for (int c = 0; c < L; c++) km |= (uint64_t)fw[base + c] << (3 * c);
+            for (int e = 0;; e++) {
+                for (int s = 0; s < ns; s++) {
+                    if (km == R.fw_seed[s]) hit |= 1u << s;
+                    if (km == R.rc_seed[s]) hit |= 1u << (8 + s);
+                }
+                if (e == 7 || base + e + 1 + L > J) break;
+                km = (km >> 3) | ((uint64_t)fw[base + e + L] << top);
             }
         }
     }
@@ -542,7 +581,7 @@ C2B_DEV c2b_aln_rec load_aln(const c2b_aln_rec *p)
 //                           16 lanes starting at hoff) and re-scattered per winner.
 C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, const uint8_t *fw, const uint8_t *rc,
                          uint8_t *rowinfo, uint32_t *rowins, int r_begin, int r_end, const uint64_t *opsbuf, int hoff,
-                         int keep_irr)
+                         int keep_irr, const c2b_aln_rec &a_single)
 {
     const int lane = wp::lane();
     const bool multi = (r_end - r_begin) > 1;
@@ -605,7 +644,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
                 }
             } else if (ambiguous && nth == 0 && w > 0 && lane == 0 && !overflow) wp::addg(SC + C2B_S_AMBIGUOUS_W, w);
             if (lane == 0) {
-                c2b_aln_rec a = load_aln(P.alns + rd * P.n_refs + r);
+                c2b_aln_rec a = multi ? load_aln(P.alns + rd * P.n_refs + r) : a_single;   // single reference: still in registers
                 a.insertion_n = (uint16_t)o.ins_n; a.deletion_n = (uint16_t)o.del_n; a.substitution_n = (uint16_t)o.sub_n;
                 a.n_ins_all = (uint16_t)o.n_ins_all; a.n_ins_win = (uint16_t)o.n_ins_win;
                 a.n_del_all = (uint16_t)o.n_del_all; a.n_del_win = (uint16_t)o.n_del_win;
@@ -656,10 +695,11 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
     const int r_end = P.ref_id ? r_begin + 1 : P.n_refs;
     const bool multi = (r_end - r_begin) > 1;
     int keep_irr = 0;
+    c2b_aln_rec a; init_aln(a, st);
 
     for (int r = r_begin; r < r_end; r++) {
         const RefDev &R = P.refs[r];
-        c2b_aln_rec a; init_aln(a, st);
+        init_aln(a, st);
         if (!st && (R.I + J > C2B_MAX_ALN_LEN)) a.status |= C2B_ST_TOO_LONG;
         if (!a.status) {
             const int mode = P.forced_ops ? 0 : strand_mode(P, R, S.fw[0], J);
@@ -702,7 +742,7 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
         if (lane == 0) P.alns[rd * P.n_refs + r] = a;
     }
     wp::sync();
-    finish_read(P, rd, rec, J, S.fw[0], S.rc[0], S.rowinfo, S.rowins, r_begin, r_end, opsbuf, -1, keep_irr);
+    finish_read(P, rd, rec, J, S.fw[0], S.rc[0], S.rowinfo, S.rowins, r_begin, r_end, opsbuf, -1, keep_irr, a);
 }
 
 // ------------------------------------------------------------------------------------ paired path (16-bit halves)
@@ -745,18 +785,34 @@ C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint8_t *combo, 
     const uint32_t *__restrict__ prof0 = R.prof2 + r0;
     uint2 *__restrict__ tbw = tb2 + ((int64_t)rb * P.TS) * 32 + lane;
     const bool lane_on = lane < nl;
+    // the substitution scores of step t+1 are fetched while step t computes (hides the L1 latency of the profile)
+#ifdef C2B_DP_PREFETCH
+    uint4 sa_n = make_uint4(0u, 0u, 0u, 0u), sb_n = sa_n;
+    if (lane == 0 && J >= 1) {
+        const uint4 *pp = reinterpret_cast<const uint4 *>(prof0 + combo[0] * Ipad);
+        sa_n = wp::ldg4u(pp); sb_n = wp::ldg4u(pp + 1);
+    }
+#endif
 
     for (int t = 1; t <= nsteps; t++) {
         uint32_t uM = wp::shflu_up(M[7], 1), uX = wp::shflu_up(X[7], 1), uY = wp::shflu_up(Y[7], 1);
         const int j = t - lane;
+#ifdef C2B_DP_PREFETCH
+        const uint4 sa = sa_n, sb = sb_n;
+        if (lane_on && j >= 0 && j < J) {                   // next step's column j+1 of this lane
+            const uint4 *pp = reinterpret_cast<const uint4 *>(prof0 + combo[j] * Ipad);
+            sa_n = wp::ldg4u(pp); sb_n = wp::ldg4u(pp + 1);
+        }
+#endif
         if (lane == 0) {
             if (rb == 0) { uM = PK_SENT; uX = XB; uY = PK_SENT | PK_T1; }
             else if (j <= J) { uM = (uint32_t)wp::ldcgi(bnd_in + 3 * j); uX = (uint32_t)wp::ldcgi(bnd_in + 3 * j + 1); uY = (uint32_t)wp::ldcgi(bnd_in + 3 * j + 2); }
         }
         if (lane_on && j >= 1 && j <= J) {
-            const int q2 = combo[j - 1];
-            const uint4 *pp = reinterpret_cast<const uint4 *>(prof0 + q2 * Ipad);
+#ifndef C2B_DP_PREFETCH
+            const uint4 *pp = reinterpret_cast<const uint4 *>(prof0 + combo[j - 1] * Ipad);
             const uint4 sa = wp::ldg4u(pp), sb = wp::ldg4u(pp + 1);
+#endif
             const uint32_t s[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
             const uint32_t dcol = (j == J) ? 0u : d4p;      // free opening in the last column (both reads end together)
             const uint32_t dsp = islast ? 0u : dcol;
@@ -803,57 +859,6 @@ C2B_DEV void dp_dispatch2(const KParams &P, const RefDev &R, const uint8_t *comb
     }
 }
 
-// Two tracebacks at once: lanes 0-15 walk read A, lanes 16-31 read B (each lane of a half holds the same state).
-// The half's lane L ends up with ops 32L..32L+31 of its read (up to 512 columns).
-C2B_DEV Walked walk2(const KParams &P, const RefDev &R, const int J, const uint2 *__restrict__ tb2, int s)
-{
-    const int lane = wp::lane(), hl = lane & 15, hb = lane & 16;
-    const int TS = P.TS;
-    int i = R.I, j = J, n = 0, err = 0;
-    uint32_t acc = 0, lo = ~0u, hi = ~0u;
-    int wkey = -1, wj = 0; uint32_t wreg = 0;
-#define C2B_PUSH2(op_)                                                                        \
-    do {                                                                                      \
-        acc = wp::funnel_r(acc, (uint32_t)(op_), 2); n++;                                     \
-        if ((n & 15) == 0) { const int ix = (n >> 4) - 1; if (hl == (ix >> 1)) { if (ix & 1) hi = acc; else lo = acc; } } \
-    } while (0)
-    for (;;) {
-        const bool active = i > 0 && j > 0;
-        if (!wp::ballot(active)) break;
-        const int r = active ? i - 1 : 0, key = r >> 3;
-        const bool need = active && (key != wkey || wj - j >= 16);
-        if (wp::ballot(need)) {
-            if (need) {                                     // refill this half's 16-column window of lane-row `key`
-                wkey = key; wj = j;
-                const int cj = j - hl, rb = key >> 5, l = key & 31;
-                uint2 w2 = make_uint2(0u, 0u);
-                if (cj >= 1) w2 = wp::ldcg2(tb2 + ((int64_t)rb * TS + cj + l) * 32 + l);
-                wreg = hb ? ((w2.x & 0xffff0000u) | (w2.y >> 16)) : ((w2.x << 16) | (w2.y & 0xffffu));
-            }
-        }
-        const uint32_t v = wp::shflu(wreg, hb | ((wj - j) & 15)) >> (2 * (7 - (r & 7)));
-        if (active) {
-            const int op = s;
-            s = (s == OP_M) ? (int)((v >> 16) & 3u) : (int)(v & (uint32_t)s);
-            err |= (s == 3);
-            i -= (op != OP_I); j -= (op != OP_J);
-            C2B_PUSH2(op);
-        }
-    }
-    if (j > 0 && s != OP_I) err = 1;
-    if (i > 0 && s != OP_J) err = 1;
-    while (j > 0) { j--; C2B_PUSH2(OP_I); }
-    while (i > 0) { i--; C2B_PUSH2(OP_J); }
-#undef C2B_PUSH2
-    if (n & 15) {
-        const int ix = n >> 4, used = 2 * (n & 15);
-        const uint32_t a = (acc >> (32 - used)) | (~0u << used);
-        if (hl == (ix >> 1)) { if (ix & 1) hi = a; else lo = a; }
-    }
-    Walked out; out.ops = (uint64_t)lo | ((uint64_t)hi << 32); out.n = n; out.err = err;
-    return out;
-}
-
 C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint8_t *combo, int J, uint2 *tb2, int32_t *bnd)
 {
     uint32_t cM = 0, cX = 0, cY = 0;
@@ -865,7 +870,7 @@ C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint8_t *comb
     }
     const uint32_t s2 = wp::max3_2(cM, cY, cX) & PK_TM;         // start state per half
     const int s = (wp::lane() & 16) ? (int)(s2 >> 16) : (int)(s2 & 3u);
-    return walk2(P, R, J, tb2, s);
+    return walk_batch<true>(P, R, J, reinterpret_cast<const uint32_t *>(tb2), s);
 }
 
 // Two reads (rdA, rdB) of equal length J through the packed path.  Per-lane variables belong to the lane's half.
@@ -891,10 +896,11 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, int64_t rdA, int64_t rd
     const int r_end = P.ref_id ? r_begin + 1 : P.n_refs;
     const bool multi = (r_end - r_begin) > 1;
     int keep_irr = 0;
+    c2b_aln_rec a; init_aln(a, st);
 
     for (int r = r_begin; r < r_end; r++) {
         const RefDev &R = P.refs[r];
-        c2b_aln_rec a; init_aln(a, st);
+        init_aln(a, st);
         const int mA = strand_mode(P, R, S.fw[0], J), mB = strand_mode(P, R, S.fw[1], J);
         const int mode = h ? mB : mA;
         const int npass = (mA == 2 || mB == 2) ? 2 : 1;
@@ -945,8 +951,14 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, int64_t rdA, int64_t rd
         rr.best_ref = -1; rr.n_winners = (uint8_t)wp::shfl((int)rec.n_winners, src); rr.ambiguous = 0;
         rr.status = wp::shflu(rec.status, src);
         const int irr = wp::shfl(keep_irr, src);
+        c2b_aln_rec ah; init_aln(ah, 0);                    // that half's record (used when a single reference was tried)
+        const uint32_t w0 = wp::shflu((uint32_t)a.n_match | ((uint32_t)a.aln_len << 16), src);
+        ah.n_match = (uint16_t)(w0 & 0xffffu); ah.aln_len = (uint16_t)(w0 >> 16);
+        ah.score_milli = wp::shfl(a.score_milli, src);
+        const uint32_t w1 = wp::shflu((uint32_t)a.strand | ((uint32_t)a.status << 8), src);
+        ah.strand = (uint8_t)(w1 & 0xffu); ah.status = (uint8_t)(w1 >> 8);
         finish_read(P, hh ? rdB : rdA, rr, J, S.fw[hh], S.rc[hh], S.rowinfo + hh * PK_ROWINFO_STRIDE,
-                    S.rowins + hh * PK_ROWINS_STRIDE, r_begin, r_end, opsbuf, src, irr);
+                    S.rowins + hh * PK_ROWINS_STRIDE, r_begin, r_end, opsbuf, src, irr, ah);
         wp::sync();
     }
 }

@@ -63,20 +63,36 @@ static void rt_host_free(void *p) { free(p); }
 
 // ----------------------------------------------------------------------------------------- kernel
 #ifndef C2B_EMU
-constexpr int WARPS_PER_CTA = 8;      // launch-bounds maximum; the launch may use fewer (C2B_WARPS_PER_CTA)
+#ifndef C2B_WARPS_PER_CTA
+#define C2B_WARPS_PER_CTA 8
+#endif
+#ifndef C2B_MIN_CTAS_PER_SM
+#define C2B_MIN_CTAS_PER_SM 2
+#endif
+constexpr int WARPS_PER_CTA = C2B_WARPS_PER_CTA;      // launch-bounds maximum; the launch may use fewer (env C2B_WARPS_PER_CTA)
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) c2b_align_classify_kernel(const KParams P)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_align_classify_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSmem *S = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
     const int warp_slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    for (;;) {
-        unsigned long long w = 0;
-        if ((threadIdx.x & 31) == 0) w = wp::fetch_work(P.work_counter);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (2 * w >= (unsigned long long)P.n_reads) break;
+    // work items are fetched one ahead, and the next pair's read bytes are pulled into L2 while this pair computes
+    unsigned long long w = 0;
+    if ((threadIdx.x & 31) == 0) w = wp::fetch_work(P.work_counter);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    while (2 * w < (unsigned long long)P.n_reads) {
+        unsigned long long wn = 0;
+        if ((threadIdx.x & 31) == 0) wn = wp::fetch_work(P.work_counter);
+        wn = __shfl_sync(0xffffffffu, wn, 0);
+        if (2 * wn < (unsigned long long)P.n_reads) {
+            const int64_t last = (int64_t)(2 * wn + 2) < P.n_reads ? (int64_t)(2 * wn + 2) : P.n_reads;
+            const int64_t b0 = P.offsets[2 * wn], b1 = P.offsets[last];
+            const int64_t a = b0 + (int64_t)(threadIdx.x & 31) * 128;
+            if (a < b1) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.reads + a));
+        }
         process_item(P, *S, (int64_t)w, warp_slot);       // reads 2w, 2w+1
         __syncwarp();
+        w = wn;
     }
 }
 #endif
@@ -362,7 +378,9 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
     if ((rc = ensure(e, e->tb, (size_t)e->n_warps * e->max_nrb * TS * 64 * 4))) return rc;   // 64: a pair stores two words per lane
     if ((rc = ensure(e, e->bnd, (size_t)e->n_warps * 2 * 3 * TS * 4))) return rc;
     if ((rc = ensure(e, e->ops, (size_t)e->n_warps * e->n_refs * 32 * 8))) return rc;
+    const bool fresh_work = !e->work.p;
     if ((rc = ensure(e, e->work, 64))) return rc;
+    if (fresh_work) RTCHK(rt_zero(e->work.p, 64, e->stream));
     e->scratch_TS = TS;
 #ifndef C2B_EMU
     {   // Keep the traceback slab (written once, read back by the same warp microseconds later) resident in L2:
@@ -422,7 +440,7 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     P.work_counter = (unsigned long long *)e->work.p;
     P.vstride = e->vstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
-    RTCHK(rt_zero(e->work.p, 24, e->stream));
+    RTCHK(rt_zero(e->work.p, 8, e->stream));              // work counter only; [1],[2] = path statistics (cumulative)
 #ifndef C2B_EMU
     cudaEventRecord(e->ev0, e->stream);
     c2b_align_classify_kernel<<<e->grid, e->wpc * 32, sizeof(WarpSmem) * e->wpc, e->stream>>>(P);
@@ -564,6 +582,7 @@ int c2b_counts_reset(c2b_engine *e)
 {
     if (!e || !e->configured) return fail(e, C2B_E_STATE, "c2b_counts_reset: engine not configured");
     RTCHK(rt_zero(e->d_counts, e->counts_n * 8, e->stream));
+    if (e->work.p) RTCHK(rt_zero(e->work.p, 64, e->stream));
     RTCHK(rt_sync(e->stream));
     return C2B_OK;
 }

@@ -182,7 +182,8 @@ int  c2b_sync(c2b_engine *e);
 void *c2b_stream(c2b_engine *e);                    /* cudaStream_t of the engine */
 double c2b_last_kernel_ms(c2b_engine *e);           /* CUDA-event time of the last align kernel launch */
 int64_t c2b_launch_count(const c2b_engine *e);      /* kernels launched by this engine so far */
-/* work items of the LAST launch that took the packed two-reads-per-warp path / the 32-bit one-read path */
+/* work items (pairs of reads) since the last c2b_counts_reset that took the packed two-reads-per-warp path /
+ * the 32-bit one-read-per-warp path */
 int  c2b_path_counts(c2b_engine *e, int64_t *pair_items, int64_t *single_items);
 
 /* replaces: the count vectors / counters built by the quantification loop (CRISPRessoCORE.py:3841-3907,
