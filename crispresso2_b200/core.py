@@ -150,8 +150,7 @@ def res_flags(res):
 
 
 def align_uniques(engine, uniques, counts, ref_names, refs, flags, weights=None):
-    """One GPU batch over unique reads -> (variants list, BatchResult).  Reads whose edit list overflowed the
-    per-read cap are re-run with a cap that cannot overflow (their counts are only added in the re-run)."""
+    """One GPU batch over unique reads -> (BatchResult, merge weights)."""
     weights = merge_weights(uniques, counts) if weights is None else weights
     res = engine.align(uniques, count=np.asarray(counts, dtype=np.int32), qweight=np.asarray(weights, dtype=np.int32))
     res.flags = flags
@@ -191,12 +190,13 @@ def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_
     over = np.nonzero(res.recs["status"] & _lib.ST_EDIT_OVERFLOW)[0]
     fix = {}
     if len(over):
-        # the kernel leaves overflowed reads out of the count block; re-run them with a cap that cannot overflow
+        # their counts are already in the block (only the edit LIST was truncated): re-run them with a cap that cannot
+        # overflow and zero weights, just to fetch the complete lists
         cap0 = engine.edit_cap
         engine.set_edit_cap(max(engine.ref_lens) + _lib.MAX_READ_LEN)
         sub = [uniques[k] for k in over]
-        r2 = engine.align(sub, count=np.asarray([counts[k] for k in over], dtype=np.int32),
-                          qweight=np.asarray([weights[k] for k in over], dtype=np.int32))
+        zero = np.zeros(len(sub), dtype=np.int32)
+        r2 = engine.align(sub, count=zero, qweight=zero)
         r2.flags = flags
         engine.set_edit_cap(cap0)
         fix = {int(k): (r2, j) for j, k in enumerate(over)}

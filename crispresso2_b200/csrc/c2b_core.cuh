@@ -43,6 +43,7 @@ C2B_DEV int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }   //
 C2B_DEV uint32_t max3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }      // per signed half
 C2B_DEV uint32_t addmax_2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }  // per half max(a+b, c)
 C2B_DEV uint4 ldg4u(const uint4 *p) { return __ldg(p); }
+C2B_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 C2B_DEV uint2 ldcg2(const uint2 *p) { return __ldcg(p); }
 C2B_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }   // (hi:lo) >> sh
 C2B_DEV int popc(uint32_t x) { return __popc(x); }
@@ -277,6 +278,14 @@ C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const 
             i -= run * di; j -= run * dj;
             err |= (news == 3);
             s = news;
+            if (s == OP_M) {                                // pull the window two iterations down the diagonal towards L2
+                const int pi = i - 2 * G - hl, pj = j - 2 * G - hl;
+                if (pi >= 1 && pj >= 1) {
+                    const int r = pi - 1, key = r >> 3, rb = key >> 5, l = key & 31;
+                    const int64_t idx = ((int64_t)rb * TS + pj + l) * 32 + l;
+                    wp::prefetch_l2(PAIR ? (const void *)(tb2 + idx) : (const void *)(tb + idx));
+                }
+            }
         }
     }
     if (j > 0 && s != OP_I) err = 1;                        // row 0 / column 0 can only be left along their own border
@@ -383,15 +392,19 @@ struct RowOut {
     int ins_n, del_n, sub_n, n_ins_all, n_ins_win, n_del_all, n_del_win, n_del_pos, n_sub_all, nent;
 };
 
-// PASS 0: scalars + edit list.  PASS 1: per-position count vectors (weight w).
-template <int PASS>
-C2B_DEV void rows_pass(const KParams &P, const RefDev &R, const uint8_t *rowinfo, const uint32_t *rowins, RowOut &o,
-                       c2b_edit *ed, long long w, bool len_vectors)
+// mode bits of rows_run
+constexpr int RM_SCAL = 1;   // scalars + edit list (COREResources.pyx:108-163)
+constexpr int RM_VEC = 2;    // per-position count vectors, weight w (CRISPRessoCORE.py:4016-4081)
+constexpr int RM_LEN = 4;    // insertion/deletion length vectors (:4104-4115), only for reads that carry a modification
+
+C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *rowinfo, const uint32_t *rowins, RowOut &o,
+                           c2b_edit *ed, long long w, int mode)
 {
     const int lane = wp::lane();
     const uint32_t lt = (1u << lane) - 1u;
     const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
                ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
+    const bool scal = mode & RM_SCAL, vec = mode & RM_VEC, lenv = mode & RM_LEN;
     unsigned long long *V = R.vec;
     const int vs = P.vstride;
     int open_a = -1; uint32_t prevD = 0;
@@ -401,7 +414,7 @@ C2B_DEV void rows_pass(const KParams &P, const RefDev &R, const uint8_t *rowinfo
     auto run = [&](int a, int b) {                         // one deletion run [a,b)  (COREResources.pyx:143-160)
         const int size = b - a;
         const bool hit = (int)R.cum[b] - (int)R.cum[a] > 0;
-        if (PASS == 0) {
+        if (scal) {
             o.n_del_all++; o.n_del_pos += size;
             if (hit) { o.n_del_win++; o.del_n += size; }
             if (lane == 0 && o.nent < P.edit_cap && ed) {
@@ -409,10 +422,11 @@ C2B_DEV void rows_pass(const KParams &P, const RefDev &R, const uint8_t *rowinfo
                 ed[o.nent] = e;
             }
             o.nent++;
-        } else if (hit) {
+        }
+        if (hit && ((vec && !ign_d) || lenv)) {
             for (int p = a + lane; p < b; p += 32) {
-                if (!ign_d) wp::addg(V + (int64_t)C2B_V_DEL * vs + p, w);
-                if (len_vectors) wp::addg(V + (int64_t)C2B_V_DEL_LEN * vs + p, w * size);
+                if (vec && !ign_d) wp::addg(V + (int64_t)C2B_V_DEL * vs + p, w);
+                if (lenv) wp::addg(V + (int64_t)C2B_V_DEL_LEN * vs + p, w * size);
             }
         }
     };
@@ -425,14 +439,16 @@ C2B_DEV void rows_pass(const KParams &P, const RefDev &R, const uint8_t *rowinfo
         const int rcode = info & 7;
         const uint32_t refc = valid ? R.asc[p] : 0u, readc = P.alpha[rcode];
         const bool differs = valid && !isdel && readc != refc;
-        const bool issub = differs && readc != 'N';                         // COREResources.pyx:111
-        const bool inc_p = valid && R.incl[p];
         const uint32_t insr = (valid && p + 1 <= I - 1) ? rowins[p + 1] : 0u;   // insertion right of p
         const uint32_t insl = (valid && p >= 1 && p <= I - 1) ? rowins[p] : 0u; // insertion left of p
+        // a chunk in which the read equals the reference and no deletion is open has nothing to record
+        if (!wp::ballot(isdel || differs || insr > 0 || insl > 0) && !prevD) continue;
+        const bool issub = differs && readc != 'N';                         // COREResources.pyx:111
+        const bool inc_p = valid && R.incl[p];
         const bool win_r = insr > 0 && inc_p && R.incl[p + 1];                    // both flanks in window (:120)
         const bool win_l = insl > 0 && inc_p && R.incl[p - 1];
         const uint32_t D = wp::ballot(isdel);
-        if (PASS == 0) {
+        if (scal) {
             const uint32_t Bs = wp::ballot(issub), Bsw = wp::ballot(issub && inc_p);
             const uint32_t Bi = wp::ballot(insr > 0), Biw = wp::ballot(win_r);
             o.n_sub_all += wp::popc(Bs); o.sub_n += wp::popc(Bsw);
@@ -459,12 +475,11 @@ C2B_DEV void rows_pass(const KParams &P, const RefDev &R, const uint8_t *rowinfo
                 }
                 o.nent += wp::popc(Bi);
             }
-        } else {
+        }
+        if (vec) {
             if (insr > 0) wp::addg(V + (int64_t)C2B_V_ALL_INS_LEFT * vs + p, w);
             if (insr > 0 || insl > 0) wp::addg(V + (int64_t)C2B_V_ALL_INS * vs + p, w);   // a shared flank counts once
             if (!ign_i && (win_r || win_l)) wp::addg(V + (int64_t)C2B_V_INS * vs + p, w);
-            if (len_vectors && (win_r || win_l))
-                wp::addg(V + (int64_t)C2B_V_INS_LEN * vs + p, w * (long long)((win_r ? insr : 0u) + (win_l ? insl : 0u)));
             if (isdel) wp::addg(V + (int64_t)C2B_V_ALL_DEL * vs + p, w);
             if (issub) {
                 wp::addg(V + (int64_t)C2B_V_ALL_SUB * vs + p, w);
@@ -479,6 +494,8 @@ C2B_DEV void rows_pass(const KParams &P, const RefDev &R, const uint8_t *rowinfo
                 if (rc != 255) wp::addg(V + (int64_t)(C2B_V_BASEDEV0 + rc) * vs + p, -w);
             }
         }
+        if (lenv && (win_r || win_l))
+            wp::addg(V + (int64_t)C2B_V_INS_LEN * vs + p, w * (long long)((win_r ? insr : 0u) + (win_l ? insl : 0u)));
         // deletion runs: ends inside this chunk
         const uint32_t Dsh = (D << 1) | prevD;
         const uint32_t Sm = D & ~Dsh;
@@ -537,14 +554,22 @@ C2B_DEV bool load_codes(const KParams &P, int64_t off, int J, uint8_t *fw, uint8
 {
     const int lane = wp::lane();
     bool bad = false;
-    for (int p = lane; p < J; p += 32) {
-        const uint8_t ch = P.reads[off + p];
-        int code = 255;
+    for (int base = 0; base < J; base += 256) {             // 8 symbols per lane per round: all loads first, then use
+        uint8_t ch[8];
 #pragma unroll
-        for (int q = 0; q < C2B_MAX_Q; q++) if (q < P.nq && ch == P.alpha[q]) code = q;
-        if (code == 255) { bad = true; code = 0; }
-        fw[p] = (uint8_t)code;
-        rc[J - 1 - p] = P.comp[code];
+        for (int e = 0; e < 8; e++) { const int p = base + lane + 32 * e; ch[e] = p < J ? P.reads[off + p] : (uint8_t)0; }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int p = base + lane + 32 * e;
+            if (p < J) {
+                int code = 255;
+#pragma unroll
+                for (int q = 0; q < C2B_MAX_Q; q++) if (q < P.nq && ch[e] == (uint8_t)P.alpha[q]) code = q;
+                if (code == 255) { bad = true; code = 0; }
+                fw[p] = (uint8_t)code;
+                rc[J - 1 - p] = P.comp[code];
+            }
+        }
     }
     return wp::ballot(bad) != 0;
 }
@@ -614,22 +639,24 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             RowOut o; o.ins_n = o.del_n = o.sub_n = 0; o.n_ins_all = o.n_ins_win = o.n_del_all = o.n_del_win = 0;
             o.n_del_pos = o.n_sub_all = 0; o.nent = 0;
             c2b_edit *ed = P.edits ? P.edits + (rd * P.n_refs + r) * (int64_t)P.edit_cap : nullptr;
-            rows_pass<0>(P, R, rowinfo, rowins, o, ed, 0, false);
             const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
                        ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
+            // contribution to the count block (CRISPRessoCORE.py:3989-4072); known before the scan unless
+            // --discard_indel_reads is on, in which case the scalars decide and the vectors need a second scan
+            const bool counted = !ambiguous && (!first || nth == 0) && w > 0;
+            const bool two_scans = (P.flags & C2B_F_DISCARD_INDEL_READS) != 0;
+            rows_run(P, R, rowinfo, rowins, o, ed, w, RM_SCAL | ((counted && !two_scans) ? RM_VEC : 0));
             const bool has_d = !ign_d && o.del_n > 0, has_i = !ign_i && o.ins_n > 0, has_s = !ign_s && o.sub_n > 0;
             const bool modified = has_d || has_i || has_s;     // CRISPRessoCORE.py:746-753 (same truth table)
             uint32_t astatus = 0;
-            if (P.edits && o.nent > P.edit_cap) astatus |= C2B_ST_EDIT_OVERFLOW;
-            // contribution to the count block (CRISPRessoCORE.py:3989-4072)
-            const bool overflow = astatus & C2B_ST_EDIT_OVERFLOW;          // caller re-runs these with a larger cap
-            const bool counted = !ambiguous && (!first || nth == 0) && !overflow;
+            if (P.edits && o.nent > P.edit_cap) astatus |= C2B_ST_EDIT_OVERFLOW;     // list truncated; counts are complete
             unsigned long long *SC = R.scal;
-            if (counted && w > 0) {
-                const bool discard = (P.flags & C2B_F_DISCARD_INDEL_READS) && (o.del_n > 0 || o.ins_n > 0);
+            if (counted) {
+                const bool discard = two_scans && (o.del_n > 0 || o.ins_n > 0);
                 if (discard) { if (lane == 0) wp::addg(SC + C2B_S_DISCARDED, w); }
                 else {
-                    rows_pass<1>(P, R, rowinfo, rowins, o, nullptr, w, has_d || has_i || has_s);
+                    const bool lenv = modified && (o.n_ins_win > 0 || o.n_del_win > 0);
+                    if (two_scans || lenv) rows_run(P, R, rowinfo, rowins, o, nullptr, w, (two_scans ? RM_VEC : 0) | (lenv ? RM_LEN : 0));
                     if (lane == 0) {
                         wp::addg(SC + C2B_S_TOTAL, w);
                         wp::addg(SC + (modified ? C2B_S_MODIFIED : C2B_S_UNMODIFIED), w);
@@ -642,7 +669,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
                         if (slot[combo] >= 0) wp::addg(SC + slot[combo], w);
                     }
                 }
-            } else if (ambiguous && nth == 0 && w > 0 && lane == 0 && !overflow) wp::addg(SC + C2B_S_AMBIGUOUS_W, w);
+            } else if (ambiguous && nth == 0 && w > 0 && lane == 0) wp::addg(SC + C2B_S_AMBIGUOUS_W, w);
             if (lane == 0) {
                 c2b_aln_rec a = multi ? load_aln(P.alns + rd * P.n_refs + r) : a_single;   // single reference: still in registers
                 a.insertion_n = (uint16_t)o.ins_n; a.deletion_n = (uint16_t)o.del_n; a.substitution_n = (uint16_t)o.sub_n;
@@ -657,7 +684,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             nth++;
             // aln_stats of the serial process_fastq branch use best_match_name only (:1971-1979): the LAST winner
             const bool is_last = (rec.winner_mask >> (r & 31)) >> 1 == 0;
-            if (is_last && lane == 0 && !overflow) {
+            if (is_last && lane == 0) {
                 const long long total_mods = o.n_ins_all + o.n_del_pos + o.n_sub_all;
                 const long long in_win = o.sub_n + o.del_n + o.ins_n;
                 wp::addg(SC + C2B_S_N_GLOBAL_SUBS, cnt * o.n_sub_all);

@@ -92,7 +92,7 @@ typedef struct {
 
 #define C2B_ST_BAD_CHAR       1u   /* read holds a symbol outside the alphabet */
 #define C2B_ST_UNDEFINED      2u   /* traceback left the zone where the reference is defined */
-#define C2B_ST_EDIT_OVERFLOW  4u   /* more edits than edit_cap: counts excluded, rerun with a larger cap */
+#define C2B_ST_EDIT_OVERFLOW  4u   /* more edits than edit_cap: the LIST is truncated (scalars and counts are complete) */
 #define C2B_ST_TOO_LONG       8u
 
 /* Per read: best-reference selection of get_new_variant_object (CRISPRessoCORE.py:690-716, 780-785). 16 bytes */

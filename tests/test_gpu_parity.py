@@ -130,20 +130,21 @@ def test_full_size_properties(eng):
     V = blk.vectors("Reference")
     tot = blk.scalar("Reference", "TOTAL")
     aligned = res.recs["best_score_milli"] > 0
-    overflow = (res.recs["status"] & _lib.ST_EDIT_OVERFLOW) != 0          # left out of the counts until re-run
+    overflow = (res.recs["status"] & _lib.ST_EDIT_OVERFLOW) != 0          # edit LIST truncated; counts complete
     assert 0 < overflow.sum() < 1000
-    assert tot == int((aligned & ~overflow).sum())
+    assert tot == int(aligned.sum())
     cover = sum(V["all_base_count_" + b] for b in "ACGTN-")
     assert (cover == tot).all()
     assert (V["all_deletion_count"] == V["all_base_count_-"]).all()
     assert blk.scalar("Reference", "MODIFIED") + blk.scalar("Reference", "UNMODIFIED") == tot
-    assert blk.scalar("Reference", "MODIFIED") == int(a["modified"][aligned & ~overflow].sum())
-    # re-running the overflowed reads with a cap that cannot overflow completes the block
+    assert blk.scalar("Reference", "MODIFIED") == int(a["modified"][aligned].sum())
+    # re-running the overflowed reads with a cap that cannot overflow (and zero weights) yields the complete lists
     idx = np.nonzero(overflow)[0]
     eng.set_edit_cap(512)
-    res3 = eng.align_packed(reads[idx].reshape(-1), np.arange(len(idx) + 1, dtype=np.int64) * 250)
+    zero = np.zeros(len(idx), dtype=np.int32)
+    res3 = eng.align_packed(reads[idx].reshape(-1), np.arange(len(idx) + 1, dtype=np.int64) * 250, count=zero, qweight=zero)
     eng.set_edit_cap(8)
-    assert (res3.recs["status"] == 0).all()
+    assert (res3.recs["status"] == 0).all() and (res3.alns[:, 0]["n_edits"] > 8).all()
     assert eng.counts().scalar("Reference", "TOTAL") == int(aligned.sum())
     # (5) batch-composition independence: a shuffled sub-batch reproduces its records bit for bit
     pick = rng.permutation(n)[:50000]
