@@ -55,6 +55,7 @@ C2B_DEV int ldcgi(const int *p) { return __ldcg(p); }
 C2B_DEV uint64_t ldcg64(const uint64_t *p) { return __ldcg((const unsigned long long *)p); }
 C2B_DEV int4 ldg4(const int4 *p) { return __ldg(p); }
 C2B_DEV void addg(unsigned long long *p, long long v) { atomicAdd(p, (unsigned long long)v); }
+C2B_DEV void maxg(unsigned long long *p, unsigned long long v) { atomicMax(p, v); }
 C2B_DEV uint32_t adds(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
 C2B_DEV unsigned long long fetch_work(unsigned long long *p) { return atomicAdd(p, 1ull); }
 }  // namespace wp
@@ -518,7 +519,7 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
 }
 
 // ------------------------------------------------------------------------------------------ per read
-C2B_DEV int strand_mode(const KParams &P, const RefDev &R, const uint8_t *fw, int J)
+C2B_DEVNOINL int strand_mode(const KParams &P, const RefDev &R, const uint8_t *fw, int J)
 {
     // seed test of CRISPRessoCORE.py:656-687: 0 forward only, 1 reverse-complement only, 2 both
     if (P.flags & C2B_F_NO_STRAND_SEARCH) return 0;
@@ -550,7 +551,7 @@ C2B_DEV int strand_mode(const KParams &P, const RefDev &R, const uint8_t *fw, in
 }
 
 // read -> alphabet codes (forward and reverse complement); returns true if a symbol is outside the alphabet
-C2B_DEV bool load_codes(const KParams &P, int64_t off, int J, uint8_t *fw, uint8_t *rc)
+C2B_DEVNOINL bool load_codes(const KParams &P, int64_t off, int J, uint8_t *fw, uint8_t *rc)
 {
     const int lane = wp::lane();
     bool bad = false;
@@ -604,7 +605,7 @@ C2B_DEV c2b_aln_rec load_aln(const c2b_aln_rec *p)
 //   single reference tried: the caller already scattered the chosen alignment into rowinfo/rowins;
 //   several references    : op streams are reloaded from opsbuf (lane offset hoff; hoff >= 0: the stream lives in
 //                           16 lanes starting at hoff) and re-scattered per winner.
-C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, const uint8_t *fw, const uint8_t *rc,
+C2B_DEVNOINL void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, const uint8_t *fw, const uint8_t *rc,
                          uint8_t *rowinfo, uint32_t *rowins, int r_begin, int r_end, const uint64_t *opsbuf, int hoff,
                          int keep_irr, const c2b_aln_rec &a_single)
 {
@@ -761,6 +762,7 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
                 a.score_milli = score_milli(co.n_match, wk.n);
                 a.irregular_ends = (uint8_t)co.irregular;
                 if (multi) opsbuf[r * 32 + lane] = wk.ops;
+                if (lane == 0) wp::maxg(P.work_counter + 1, (unsigned long long)wk.n);   // widest alignment of the launch
                 keep_irr = co.irregular;
                 note_score(rec, R, r, a.score_milli);
             }
@@ -963,6 +965,7 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, int64_t rdA, int64_t rd
             a.irregular_ends = (uint8_t)co.irregular;
             keep_irr = co.irregular;
             note_score(rec, R, r, a.score_milli);
+            if (hl == 0) wp::maxg(P.work_counter + 1, (unsigned long long)bn);
         }
         if (multi) opsbuf[r * 32 + lane] = bops;
         rec.status |= a.status;
@@ -1007,7 +1010,7 @@ C2B_DEV void process_item(const KParams &P, WarpSmem &S, int64_t w, int warp_slo
             for (int r = r_begin; r < r_end; r++) if (Ja > P.refs[r].pk_maxJ) pair = false;
         }
     }
-    if (wp::lane() == 0) wp::addg(P.work_counter + (pair ? 1 : 2), 1);      // path statistics (c2b_path_counts)
+    if (wp::lane() == 0) wp::addg(P.work_counter + (pair ? 2 : 3), 1);      // path statistics (c2b_path_counts)
     if (pair) process_pair(P, S, rdA, haveB ? rdB : rdA, warp_slot);
     else {
         process_read(P, S, rdA, warp_slot);

@@ -26,7 +26,10 @@ static rt_err rt_free(void *p) { return cudaFree(p); }
 static rt_err rt_h2d(void *d, const void *h, size_t n, rt_stream s) { return n ? cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s) : cudaSuccess; }
 static rt_err rt_d2h(void *h, const void *d, size_t n, rt_stream s) { return n ? cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) : cudaSuccess; }
 static rt_err rt_zero(void *d, size_t n, rt_stream s) { return cudaMemsetAsync(d, 0, n, s); }
+static rt_err rt_d2h_2d(void *h, const void *d, size_t pitch, size_t width, size_t rows, rt_stream s)
+{ return (width && rows) ? cudaMemcpy2DAsync(h, pitch, d, pitch, width, rows, cudaMemcpyDeviceToHost, s) : cudaSuccess; }
 static rt_err rt_sync(rt_stream s) { return cudaStreamSynchronize(s); }
+static rt_err cudaMemcpyAsyncOrCopy(void *d, const void *s_, size_t n, rt_stream st) { return cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, st); }
 typedef cudaEvent_t rt_event;
 static rt_err rt_event_create(rt_event *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); }
 static rt_err rt_event_destroy(rt_event e) { return cudaEventDestroy(e); }
@@ -48,7 +51,10 @@ static rt_err rt_free(void *p) { free(p); return 0; }
 static rt_err rt_h2d(void *d, const void *h, size_t n, rt_stream) { if (n) memcpy(d, h, n); return 0; }
 static rt_err rt_d2h(void *h, const void *d, size_t n, rt_stream) { if (n) memcpy(h, d, n); return 0; }
 static rt_err rt_zero(void *d, size_t n, rt_stream) { memset(d, 0, n); return 0; }
+static rt_err rt_d2h_2d(void *h, const void *d, size_t pitch, size_t width, size_t rows, rt_stream)
+{ for (size_t r = 0; r < rows; r++) memcpy((char *)h + r * pitch, (const char *)d + r * pitch, width); return 0; }
 static rt_err rt_sync(rt_stream) { return 0; }
+static rt_err cudaMemcpyAsyncOrCopy(void *d, const void *s_, size_t n, rt_stream) { memcpy(d, s_, n); return 0; }
 typedef int rt_event;
 static rt_err rt_event_create(rt_event *e) { *e = 0; return 0; }
 static rt_err rt_event_destroy(rt_event) { return 0; }
@@ -123,7 +129,7 @@ struct c2b_engine {
     int n_warps = 0, grid = 0, wpc = 8;
     int scratch_TS = 0;
     // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
-    struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed; int64_t *h_off = nullptr; size_t h_off_cap = 0;
+    struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed, maxlen; int64_t *h_off = nullptr; size_t h_off_cap = 0;
                    rt_event in_done, k_done, out_done; bool used = false; } stage[2];
     rt_stream s_in = 0, s_out = 0;
     bool pipe_ready = false;
@@ -189,7 +195,7 @@ void c2b_destroy(c2b_engine *e)
     DevBuf *bufs[] = {&e->tb, &e->bnd, &e->ops, &e->work};
     for (DevBuf *b : bufs) if (b->p) rt_free(b->p);
     for (auto &st : e->stage) {
-        DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed};
+        DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed, &st.maxlen};
         for (DevBuf *b : sb) if (b->p) rt_free(b->p);
         if (st.h_off) rt_host_free(st.h_off);
         if (e->pipe_ready) { rt_event_destroy(st.in_done); rt_event_destroy(st.k_done); rt_event_destroy(st.out_done); }
@@ -440,7 +446,7 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     P.work_counter = (unsigned long long *)e->work.p;
     P.vstride = e->vstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
-    RTCHK(rt_zero(e->work.p, 8, e->stream));              // work counter only; [1],[2] = path statistics (cumulative)
+    RTCHK(rt_zero(e->work.p, 16, e->stream));             // [0] work counter, [1] widest alignment; [2],[3] = path statistics (cumulative)
 #ifndef C2B_EMU
     cudaEventRecord(e->ev0, e->stream);
     c2b_align_classify_kernel<<<e->grid, e->wpc * 32, sizeof(WarpSmem) * e->wpc, e->stream>>>(P);
@@ -483,11 +489,11 @@ int64_t c2b_launch_count(const c2b_engine *e) { return e ? e->launches : 0; }
 int c2b_path_counts(c2b_engine *e, int64_t *pair_items, int64_t *single_items)
 {
     if (!e || !e->work.p) return fail(e, C2B_E_STATE, "c2b_path_counts: nothing launched yet");
-    int64_t v[3] = {0, 0, 0};
-    RTCHK(rt_d2h(v, e->work.p, 24, e->stream));
+    int64_t v[4] = {0, 0, 0, 0};
+    RTCHK(rt_d2h(v, e->work.p, 32, e->stream));
     RTCHK(rt_sync(e->stream));
-    if (pair_items) *pair_items = v[1];
-    if (single_items) *single_items = v[2];
+    if (pair_items) *pair_items = v[2];
+    if (single_items) *single_items = v[3];
     return C2B_OK;
 }
 
@@ -520,6 +526,27 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
     if (n_reads < 4 * chunk) chunk = std::max<int64_t>(4096, (n_reads + 3) / 4);
     for (auto &st : e->stage) st.used = false;
     int rc = C2B_OK;
+    // D2H of a chunk is queued one iteration late: by then its kernel has finished and the widest alignment of the
+    // chunk is known, so only the right-hand `Wt` bytes of every W-byte string slot cross PCIe.
+    struct Pending { bool any = false; int64_t c0 = 0, n = 0; int set = 0; } pend;
+    auto flush = [&](const Pending &q) -> int {
+        c2b_engine::Stage &st = e->stage[q.set];
+        RTCHK(rt_wait(e->s_out, st.k_done));
+        RTCHK(rt_d2h(recs + q.c0, st.recs.p, (size_t)q.n * sizeof(c2b_read_rec), e->s_out));
+        RTCHK(rt_d2h(alns + q.c0 * nr, st.alns.p, (size_t)q.n * nr * sizeof(c2b_aln_rec), e->s_out));
+        if (cap) RTCHK(rt_d2h(edits + q.c0 * nr * cap, st.ed.p, (size_t)q.n * nr * cap * sizeof(c2b_edit), e->s_out));
+        if (strings) {
+            RTCHK(rt_event_sync(st.k_done));
+            long long wmax = 0;
+            RTCHK(rt_d2h(&wmax, (const char *)st.maxlen.p, 8, e->s_out));
+            RTCHK(rt_sync(e->s_out));
+            size_t Wt = ((size_t)wmax + 31) & ~(size_t)31;
+            if (Wt > (size_t)W) Wt = W;
+            RTCHK(rt_d2h_2d(strings + q.c0 * nr * 2 * W + (W - Wt), (const uint8_t *)st.str.p + (W - Wt), W, Wt, (size_t)q.n * nr * 2, e->s_out));
+        }
+        RTCHK(rt_record(st.out_done, e->s_out));
+        return C2B_OK;
+    };
     int64_t c0 = 0;
     for (int ci = 0; c0 < n_reads; ci++, c0 += chunk) {
         c2b_engine::Stage &st = e->stage[ci & 1];
@@ -530,6 +557,7 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
         if ((rc = ensure(e, st.off, (size_t)(n + 1) * 8))) return rc;
         if ((rc = ensure(e, st.recs, (size_t)n * sizeof(c2b_read_rec)))) return rc;
         if ((rc = ensure(e, st.alns, (size_t)n * nr * sizeof(c2b_aln_rec)))) return rc;
+        if ((rc = ensure(e, st.maxlen, 8))) return rc;
         if (strings && (rc = ensure(e, st.str, (size_t)n * nr * 2 * W))) return rc;
         if (cap && (rc = ensure(e, st.ed, (size_t)n * nr * cap * sizeof(c2b_edit)))) return rc;
         if (count && (rc = ensure(e, st.cnt, (size_t)n * 4))) return rc;
@@ -554,15 +582,14 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
                                     (c2b_aln_rec *)st.alns.p, strings ? (uint8_t *)st.str.p : nullptr,
                                     cap ? (c2b_edit *)st.ed.p : nullptr);
         if (rc) return rc;
+        // keep this launch's "widest alignment" before the next launch resets it
+        RTCHK(cudaMemcpyAsyncOrCopy(st.maxlen.p, (const char *)e->work.p + 8, 8, e->stream));
         RTCHK(rt_record(st.k_done, e->stream));
-        RTCHK(rt_wait(e->s_out, st.k_done));
-        RTCHK(rt_d2h(recs + c0, st.recs.p, (size_t)n * sizeof(c2b_read_rec), e->s_out));
-        RTCHK(rt_d2h(alns + c0 * nr, st.alns.p, (size_t)n * nr * sizeof(c2b_aln_rec), e->s_out));
-        if (strings) RTCHK(rt_d2h(strings + c0 * nr * 2 * W, st.str.p, (size_t)n * nr * 2 * W, e->s_out));
-        if (cap) RTCHK(rt_d2h(edits + c0 * nr * cap, st.ed.p, (size_t)n * nr * cap * sizeof(c2b_edit), e->s_out));
-        RTCHK(rt_record(st.out_done, e->s_out));
         st.used = true;
+        if (pend.any && (rc = flush(pend))) return rc;           // chunk ci-1: overlaps this chunk's kernel
+        pend.any = true; pend.c0 = c0; pend.n = n; pend.set = ci & 1;
     }
+    if (pend.any && (rc = flush(pend))) return rc;
     RTCHK(rt_sync(e->s_out));
     RTCHK(rt_sync(e->stream));
     return C2B_OK;

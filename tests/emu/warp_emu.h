@@ -102,6 +102,7 @@ C2B_DEV int ldcgi(const int *p) { return *p; }
 C2B_DEV uint64_t ldcg64(const uint64_t *p) { return *p; }
 C2B_DEV int4 ldg4(const int4 *p) { return *p; }
 C2B_DEV void addg(unsigned long long *p, long long v) { *p += (unsigned long long)v; }
+C2B_DEV void maxg(unsigned long long *p, unsigned long long v) { if (v > *p) *p = v; }
 C2B_DEV uint32_t adds(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
 C2B_DEV unsigned long long fetch_work(unsigned long long *p) { return (*p)++; }
 }  // namespace wp
