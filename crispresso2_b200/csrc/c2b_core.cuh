@@ -519,7 +519,7 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
 }
 
 // ------------------------------------------------------------------------------------------ per read
-C2B_DEVNOINL int strand_mode(const KParams &P, const RefDev &R, const uint8_t *fw, int J)
+C2B_DEV int strand_mode(const KParams &P, const RefDev &R, const uint8_t *fw, int J)
 {
     // seed test of CRISPRessoCORE.py:656-687: 0 forward only, 1 reverse-complement only, 2 both
     if (P.flags & C2B_F_NO_STRAND_SEARCH) return 0;
@@ -551,7 +551,7 @@ C2B_DEVNOINL int strand_mode(const KParams &P, const RefDev &R, const uint8_t *f
 }
 
 // read -> alphabet codes (forward and reverse complement); returns true if a symbol is outside the alphabet
-C2B_DEVNOINL bool load_codes(const KParams &P, int64_t off, int J, uint8_t *fw, uint8_t *rc)
+C2B_DEV bool load_codes(const KParams &P, int64_t off, int J, uint8_t *fw, uint8_t *rc)
 {
     const int lane = wp::lane();
     bool bad = false;
@@ -605,7 +605,7 @@ C2B_DEV c2b_aln_rec load_aln(const c2b_aln_rec *p)
 //   single reference tried: the caller already scattered the chosen alignment into rowinfo/rowins;
 //   several references    : op streams are reloaded from opsbuf (lane offset hoff; hoff >= 0: the stream lives in
 //                           16 lanes starting at hoff) and re-scattered per winner.
-C2B_DEVNOINL void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, const uint8_t *fw, const uint8_t *rc,
+C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, const uint8_t *fw, const uint8_t *rc,
                          uint8_t *rowinfo, uint32_t *rowins, int r_begin, int r_end, const uint64_t *opsbuf, int hoff,
                          int keep_irr, const c2b_aln_rec &a_single)
 {

@@ -524,6 +524,7 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
     const int64_t per_read = (int64_t)nr * (2 * (int64_t)W * (strings ? 1 : 0) + (int64_t)cap * 8 + 32) + 16 + maxJ + 24;
     int64_t chunk = std::max<int64_t>(4096, std::min<int64_t>((int64_t)(768ll << 20) / per_read, 1 << 17));
     if (n_reads < 4 * chunk) chunk = std::max<int64_t>(4096, (n_reads + 3) / 4);
+    if (const char *v = getenv("C2B_CHUNK")) chunk = std::max<int64_t>(2, atoll(v));     // test hook: force many small chunks
     for (auto &st : e->stage) st.used = false;
     int rc = C2B_OK;
     // D2H of a chunk is queued one iteration late: by then its kernel has finished and the widest alignment of the
@@ -547,10 +548,20 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
         RTCHK(rt_record(st.out_done, e->s_out));
         return C2B_OK;
     };
-    int64_t c0 = 0;
-    for (int ci = 0; c0 < n_reads; ci++, c0 += chunk) {
+    // chunk boundaries: a small first chunk (its H2D is exposed) and a small last chunk (its D2H is exposed)
+    std::vector<int64_t> cuts;
+    {
+        const int64_t edge = getenv("C2B_CHUNK") ? std::max<int64_t>(2, chunk / 2) : std::max<int64_t>(4096, chunk / 8);
+        int64_t pos = 0;
+        cuts.push_back(0);
+        if (n_reads > 4 * edge) { pos = edge; cuts.push_back(pos); }
+        const int64_t tail = (n_reads - pos > 2 * edge) ? edge : 0;
+        while (n_reads - tail - pos > 0) { pos += std::min(chunk, n_reads - tail - pos); cuts.push_back(pos); }
+        if (tail) cuts.push_back(n_reads);
+    }
+    for (int ci = 0; ci + 1 < (int)cuts.size(); ci++) {
         c2b_engine::Stage &st = e->stage[ci & 1];
-        const int64_t n = std::min(chunk, n_reads - c0);
+        const int64_t c0 = cuts[ci], n = cuts[ci + 1] - cuts[ci];
         const int64_t b0 = offsets[c0], b1 = offsets[c0 + n];
         if (st.used) RTCHK(rt_event_sync(st.out_done));        // set is being reused: the D2H of chunk ci-2 must be done
         if ((rc = ensure(e, st.reads, (size_t)(b1 - b0) + 16))) return rc;

@@ -93,3 +93,57 @@ def check_against_oracle(engine, refs, ref_names, params, reads, matrix):
         S = block.scalars(r)
         for name in O.SCALAR_NAMES:
             assert S[name] == sca[r][name], (r, name, S[name], sca[r][name])
+
+
+def check_pooled(engine, n_amplicons=6, reads_per=40, seed=21, amp_len=(120, 200)):
+    """Config-4 shape (post-demultiplex Pooled): every read carries the index of its single amplicon (ref_id).
+    Each (amplicon, read) must equal what the oracle computes with that amplicon alone; the count block of
+    amplicon k must equal the oracle's single-amplicon quantification of k's reads."""
+    from crispresso2_b200 import synth, core
+    from crispresso2_b200.engine import pack_reads
+    rng = np.random.default_rng(seed)
+    m = O.make_matrix()
+    refs, names, reads, rid = {}, [], [], []
+    for k in range(n_amplicons):
+        L = int(rng.integers(amp_len[0], amp_len[1] + 1))
+        amp = synth.random_amplicon(rng, L)
+        nm = "amp%d" % k
+        refs[nm] = synth.amplicon_setup(amp, guide_start=L // 2 - 10)
+        names.append(nm)
+        rr = synth.synth_reads(rng, amp, reads_per, L, sub_rate=0.01, rc_frac=0.1, cut=refs[nm]["cut_point"])
+        reads += [r.tobytes().decode() for r in rr]
+        rid += [k] * reads_per
+    order = rng.permutation(len(reads))
+    reads = [reads[i] for i in order]
+    rid = [rid[i] for i in order]
+    engine.configure(refs, names, m, -20, -2, 5, 2, 0, "ACGTN", 64)
+    engine.counts_reset()
+    buf, off = pack_reads(reads)
+    res = engine.align_packed(buf, off, ref_id=np.asarray(rid, dtype=np.int32))
+    params = O.Params()
+    per_amp = {k: [] for k in range(n_amplicons)}
+    for i, s in enumerate(reads):
+        k = rid[i]
+        per_amp[k].append(s)
+        want = O.new_variant(params, s, {names[k]: refs[names[k]]}, [names[k]], m)
+        a = res.alns[i, k]
+        assert (res.pair(i, k)[0], res.pair(i, k)[1], res.score(i, k)) == tuple(want["ref_aln_details"][0][1:]), (i, k)
+        aligned = want["best_match_score"] > 0
+        assert (res.recs[i]["best_score_milli"] > 0) == aligned
+        if aligned:
+            p = want["variant_" + names[k]]
+            assert (int(a["insertion_n"]), int(a["deletion_n"]), int(a["substitution_n"])) == (p["insertion_n"], p["deletion_n"], p["substitution_n"])
+            assert bool(a["modified"]) == (p["classification"] == "MODIFIED")
+    blk = engine.counts()
+    for k in range(n_amplicons):
+        nm = names[k]
+        cache, stats, lost = O.process_reads(per_amp[k], {nm: refs[nm]}, [nm], params, m)
+        # instance-level weights here (no dedup, no rc-merge): compare against the oracle's vectors built the same way
+        for s in cache:
+            cache[s]["count_keep"] = cache[s]["count"]
+        vec, sca, classes, total = O.count_vectors({s: v for s, v in cache.items()}, {nm: refs[nm]}, [nm], params)
+        V = blk.vectors(nm)
+        # rc-merge only moves weight between a read and its reverse complement, which align identically here
+        for name in ("all_deletion_count", "all_substitution_count", "all_insertion_count", "deletion_count", "insertion_count"):
+            assert (V[name] == vec[nm][name]).all(), (nm, name)
+        assert blk.scalar(nm, "TOTAL") == sca[nm]["counts_total"]

@@ -118,3 +118,29 @@ def test_packed_pair_path_equals_32bit_path(emu):
         assert a.pair(i) == b.pair(i)
         n = int(a.alns[i, 0]["n_edits"])
         assert (a.edits[i, 0, :n] == b.edits[i, 0, :n]).all()
+
+
+def test_pooled_ref_id(emu):
+    PU.check_pooled(emu, n_amplicons=4, reads_per=24)
+
+
+def test_chunked_pipeline_equals_one_chunk(emu, monkeypatch):
+    """c2b_align_batch splits a batch into pipelined chunks (uneven first/last); results must not depend on it."""
+    rng = np.random.default_rng(8)
+    amp = synth.random_amplicon(rng, 100)
+    ref = synth.amplicon_setup(amp, guide_start=40)
+    reads = [r.tobytes().decode() for r in synth.synth_reads(rng, amp, 61, 100, sub_rate=0.02, cut=ref["cut_point"])]
+    reads[5] = reads[5][:70]
+    out = []
+    for chunk in (None, "7"):
+        if chunk:
+            monkeypatch.setenv("C2B_CHUNK", chunk)
+        emu.configure({"Reference": ref}, ["Reference"], O.make_matrix(), -20, -2, 5, 2, 0, "ACGTN", 16)
+        emu.counts_reset()
+        res = emu.align(reads)
+        out.append((res, emu.counts_raw()))
+    monkeypatch.delenv("C2B_CHUNK", raising=False)
+    (a, ca), (b, cb) = out
+    assert (a.recs == b.recs).all() and (a.alns == b.alns).all() and (ca == cb).all()
+    for i in range(len(reads)):
+        assert a.pair(i) == b.pair(i)

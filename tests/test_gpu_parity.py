@@ -192,3 +192,8 @@ def test_packed_pair_path_equals_32bit_path(eng):
     ne = a.alns[:, 0]["n_edits"].astype(np.int64)
     valid = np.arange(24)[None, :] < np.minimum(ne, 24)[:, None]
     assert ((a.edits[:, 0] == b.edits[:, 0]) | ~valid).all()
+
+
+def test_pooled_ref_id(eng):
+    """BASELINE configs[3] shape: many amplicons, each read aligned to its own one (ref_id), one launch."""
+    PU.check_pooled(eng, n_amplicons=24, reads_per=120, amp_len=(180, 280))
