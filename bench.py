@@ -234,9 +234,6 @@ def main():
     dev_ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
     pair_items, single_items = eng.path_counts()
-    if sampler:
-        sampler.stop_flag = True
-        sampler.join(timeout=3)
 
     # ---- parity gate on this very batch: a sample of the device results against the oracle ------------
     recs = np.frombuffer(d_recs.cpu().numpy().tobytes(), dtype=_lib.REC_DTYPE)
@@ -291,6 +288,9 @@ def main():
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    if sampler:                                  # sampled across both timed regions (device-resident and end-to-end)
+        sampler.stop_flag = True
+        sampler.join(timeout=3)
     h_al = np.frombuffer(h_alns.tobytes(), dtype=_lib.ALN_DTYPE)
     e2e_gate = bool((h_al["n_match"] == alns["n_match"]).all())
     # the library copies back only the right-hand Wt bytes of each W-byte string slot (Wt = widest alignment, rounded to 32)

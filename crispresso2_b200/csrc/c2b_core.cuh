@@ -54,10 +54,15 @@ C2B_DEV uint32_t ldcg(const uint32_t *p) { return __ldcg(p); }
 C2B_DEV int ldcgi(const int *p) { return __ldcg(p); }
 C2B_DEV uint64_t ldcg64(const uint64_t *p) { return __ldcg((const unsigned long long *)p); }
 C2B_DEV int4 ldg4(const int4 *p) { return __ldg(p); }
-C2B_DEV void addg(unsigned long long *p, long long v) { atomicAdd(p, (unsigned long long)v); }
-C2B_DEV void maxg(unsigned long long *p, unsigned long long v) { atomicMax(p, v); }
-C2B_DEV uint32_t adds(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
-C2B_DEV unsigned long long fetch_work(unsigned long long *p) { return atomicAdd(p, 1ull); }
+// explicit state spaces: a generic-pointer atomicAdd expands into an address-space dispatch at every call site
+C2B_DEV void addg(unsigned long long *p, long long v)
+{ asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"((unsigned long long)v) : "memory"); }
+C2B_DEV void maxg(unsigned long long *p, unsigned long long v)
+{ asm volatile("red.global.max.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory"); }
+C2B_DEV uint32_t adds(uint32_t *p, uint32_t v)
+{ uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory"); return o; }
+C2B_DEV unsigned long long fetch_work(unsigned long long *p)
+{ unsigned long long o; asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(o) : "l"(__cvta_generic_to_global(p)), "l"(1ull) : "memory"); return o; }
 }  // namespace wp
 #else
 #include "warp_emu.h"   // provides C2B_DEV, C2B_DEVNOINL, int4/uint4 and namespace wp
@@ -106,6 +111,7 @@ struct KParams {
     uint64_t *opsbuf;                                         // [warp][n_refs][32] op streams (multi-reference)
     unsigned long long *work_counter;
     int32_t vstride;
+    const uint8_t *lut;               // [256] ASCII -> alphabet code, 255 = not in the alphabet (device memory, L1-resident)
     const uint64_t *forced_ops;       // c2b_classify_aligned: op streams supplied by the caller, [read][32]
     const int32_t *forced_n;
 };
@@ -532,7 +538,9 @@ C2B_DEV int strand_mode(const KParams &P, const RefDev &R, const uint8_t *fw, in
         for (int base = 8 * lane; base + L <= J; base += 256) {
             uint64_t km = 0;
             for (int c = 0; c < L; c++) km |= (uint64_t)fw[base + c] << (3 * c);
+#pragma unroll 1
             for (int e = 0;; e++) {
+#pragma unroll 1
                 for (int s = 0; s < ns; s++) {
                     if (km == R.fw_seed[s]) hit |= 1u << s;
                     if (km == R.rc_seed[s]) hit |= 1u << (8 + s);
@@ -558,18 +566,13 @@ C2B_DEV bool load_codes(const KParams &P, int64_t off, int J, uint8_t *fw, uint8
     for (int base = 0; base < J; base += 256) {             // 8 symbols per lane per round: all loads first, then use
         uint8_t ch[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) { const int p = base + lane + 32 * e; ch[e] = p < J ? P.reads[off + p] : (uint8_t)0; }
+        for (int e = 0; e < 8; e++) { const int p = base + lane + 32 * e; ch[e] = p < J ? P.reads[off + p] : (uint8_t)P.alpha[0]; }
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int p = base + lane + 32 * e;
-            if (p < J) {
-                int code = 255;
-#pragma unroll
-                for (int q = 0; q < C2B_MAX_Q; q++) if (q < P.nq && ch[e] == (uint8_t)P.alpha[q]) code = q;
-                if (code == 255) { bad = true; code = 0; }
-                fw[p] = (uint8_t)code;
-                rc[J - 1 - p] = P.comp[code];
-            }
+            int code = P.lut[ch[e]];
+            if (code == 255) { bad = true; code = 0; }
+            if (p < J) { fw[p] = (uint8_t)code; rc[J - 1 - p] = P.comp[code]; }
         }
     }
     return wp::ballot(bad) != 0;
@@ -916,9 +919,11 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, int64_t rdA, int64_t rd
 
     c2b_read_rec rec; rec.winner_mask = 0; rec.best_score_milli = -1000; rec.best_ref = -1; rec.n_winners = 0;
     rec.ambiguous = 0; rec.status = 0;
-    const bool badA = load_codes(P, P.offsets[rdA], J, S.fw[0], S.rc[0]);
-    const bool badB = load_codes(P, P.offsets[rdB], J, S.fw[1], S.rc[1]);
-    const uint32_t st = (h ? badB : badA) ? C2B_ST_BAD_CHAR : 0u;
+    uint32_t badmask = 0;
+#pragma unroll 1
+    for (int x = 0; x < 2; x++)                            // one copy of the loader in the instruction stream
+        if (load_codes(P, P.offsets[x ? rdB : rdA], J, S.fw[x], S.rc[x])) badmask |= 1u << x;
+    const uint32_t st = ((badmask >> h) & 1u) ? C2B_ST_BAD_CHAR : 0u;
     wp::sync();
 
     const int r_begin = P.ref_id ? P.ref_id[rdA] : 0;
@@ -930,7 +935,10 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, int64_t rdA, int64_t rd
     for (int r = r_begin; r < r_end; r++) {
         const RefDev &R = P.refs[r];
         init_aln(a, st);
-        const int mA = strand_mode(P, R, S.fw[0], J), mB = strand_mode(P, R, S.fw[1], J);
+        int mAB = 0;
+#pragma unroll 1
+        for (int x = 0; x < 2; x++) mAB |= strand_mode(P, R, S.fw[x], J) << (2 * x);
+        const int mA = mAB & 3, mB = mAB >> 2;
         const int mode = h ? mB : mA;
         const int npass = (mA == 2 || mB == 2) ? 2 : 1;
         uint64_t bops = ~0ull; int bn = 0, bstrand = 0, bscore = -1000000;

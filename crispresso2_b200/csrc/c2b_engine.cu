@@ -125,7 +125,7 @@ struct c2b_engine {
     void *d_tables = nullptr; RefDev *d_refs = nullptr;
     unsigned long long *d_counts = nullptr; size_t counts_n = 0;
     // scratch
-    DevBuf tb, bnd, ops, work;
+    DevBuf tb, bnd, ops, work, lut;
     int n_warps = 0, grid = 0, wpc = 8;
     int scratch_TS = 0;
     // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
@@ -192,7 +192,7 @@ int c2b_create(int device, c2b_engine **out)
 void c2b_destroy(c2b_engine *e)
 {
     if (!e) return;
-    DevBuf *bufs[] = {&e->tb, &e->bnd, &e->ops, &e->work};
+    DevBuf *bufs[] = {&e->tb, &e->bnd, &e->ops, &e->work, &e->lut};
     for (DevBuf *b : bufs) if (b->p) rt_free(b->p);
     for (auto &st : e->stage) {
         DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed, &st.maxlen};
@@ -357,6 +357,15 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
     e->d_refs = (RefDev *)((unsigned char *)e->d_tables + refs_off);
     RTCHK(rt_h2d(e->d_tables, blob.data(), bytes, e->stream));
     RTCHK(rt_sync(e->stream));
+    {
+        unsigned char lut[256];
+        memset(lut, 255, sizeof lut);
+        for (int q = 0; q < p->nq; q++) lut[(unsigned char)p->alphabet[q]] = (unsigned char)q;
+        int rc2;
+        if ((rc2 = ensure(e, e->lut, 256))) return rc2;
+        RTCHK(rt_h2d(e->lut.p, lut, 256, e->stream));
+        RTCHK(rt_sync(e->stream));
+    }
     e->max_I = maxI; e->max_nrb = max_nrb;
     e->scratch_TS = 0;
     e->configured = true;
@@ -446,6 +455,7 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     P.work_counter = (unsigned long long *)e->work.p;
     P.vstride = e->vstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
+    P.lut = (const uint8_t *)e->lut.p;
     RTCHK(rt_zero(e->work.p, 16, e->stream));             // [0] work counter, [1] widest alignment; [2],[3] = path statistics (cumulative)
 #ifndef C2B_EMU
     cudaEventRecord(e->ev0, e->stream);
