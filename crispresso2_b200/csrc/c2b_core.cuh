@@ -93,7 +93,8 @@ struct RefDev {
     // packed two-reads-per-warp path (16-bit halves, biased scores)
     int32_t pk_maxJ;               // longest read for which the 16-bit path is proven exact for this reference (0: never)
     uint32_t pk_XB, pk_YB, pk_M00; // border constants: X[0][j], Y[i][0], M[0][0] in both halves
-    const uint32_t *prof2;         // [nq*nq][Ipad]  halves: 4*(score+2*beta) of read A (low) / read B (high)
+    const uint32_t *prof2;         // [nq*nq][nrb][2][32][4]: for base pair q2, row block rb, lane l: words l*4.. of half 0 are
+                                   // rows 8l..8l+3, of half 1 rows 8l+4..8l+7; halves of a word: 4*(score+2*beta) of read A / B
     const uint32_t *cIe2;          // [Ipad]         4*gi[row+1] in both halves
     const uint32_t *g42;           // [Ipad]         4*gi[row]   in both halves
 };
@@ -111,6 +112,8 @@ struct KParams {
     uint64_t *opsbuf;                                         // [warp][n_refs][32] op streams (multi-reference)
     unsigned long long *work_counter;
     int32_t vstride;
+    const uint32_t *stage_src;        // = refs[0].prof2 (global source of the staged tile)
+    int32_t stage_bytes;              // bytes of refs[0].prof2 staged into shared memory by TMA at kernel start (0: none)
     const uint8_t *lut;               // [256] ASCII -> alphabet code, 255 = not in the alphabet (device memory, L1-resident)
     const uint64_t *forced_ops;       // c2b_classify_aligned: op streams supplied by the caller, [read][32]
     const int32_t *forced_n;
@@ -787,7 +790,7 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
 constexpr uint32_t PK_SENT = 0x01000100u, PK_T2 = 0x00020002u, PK_T1 = 0x00010001u, PK_TM = 0x00030003u;
 
 template <int KSTAR>
-C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint8_t *combo, const int J, const int rb,
+C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint32_t *prof, const uint8_t *combo, const int J, const int rb,
                        uint2 *__restrict__ tb2, const int32_t *bnd_in, int32_t *bnd_out, uint32_t &cM, uint32_t &cX, uint32_t &cY)
 {
     const int lane = wp::lane();
@@ -814,37 +817,20 @@ C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint8_t *combo, 
     else { pM = PK_SENT; pX = PK_SENT | PK_T2; pY = YB; }
 
     const int nsteps = J + nl - 1;
-    const uint32_t *__restrict__ prof0 = R.prof2 + r0;
+    const uint32_t *__restrict__ prof0 = prof + rb * 256 + lane * 4;     // shared (TMA-staged) or global copy, same layout
     uint2 *__restrict__ tbw = tb2 + ((int64_t)rb * P.TS) * 32 + lane;
     const bool lane_on = lane < nl;
-    // the substitution scores of step t+1 are fetched while step t computes (hides the L1 latency of the profile)
-#ifdef C2B_DP_PREFETCH
-    uint4 sa_n = make_uint4(0u, 0u, 0u, 0u), sb_n = sa_n;
-    if (lane == 0 && J >= 1) {
-        const uint4 *pp = reinterpret_cast<const uint4 *>(prof0 + combo[0] * Ipad);
-        sa_n = wp::ldg4u(pp); sb_n = wp::ldg4u(pp + 1);
-    }
-#endif
 
     for (int t = 1; t <= nsteps; t++) {
         uint32_t uM = wp::shflu_up(M[7], 1), uX = wp::shflu_up(X[7], 1), uY = wp::shflu_up(Y[7], 1);
         const int j = t - lane;
-#ifdef C2B_DP_PREFETCH
-        const uint4 sa = sa_n, sb = sb_n;
-        if (lane_on && j >= 0 && j < J) {                   // next step's column j+1 of this lane
-            const uint4 *pp = reinterpret_cast<const uint4 *>(prof0 + combo[j] * Ipad);
-            sa_n = wp::ldg4u(pp); sb_n = wp::ldg4u(pp + 1);
-        }
-#endif
         if (lane == 0) {
             if (rb == 0) { uM = PK_SENT; uX = XB; uY = PK_SENT | PK_T1; }
             else if (j <= J) { uM = (uint32_t)wp::ldcgi(bnd_in + 3 * j); uX = (uint32_t)wp::ldcgi(bnd_in + 3 * j + 1); uY = (uint32_t)wp::ldcgi(bnd_in + 3 * j + 2); }
         }
         if (lane_on && j >= 1 && j <= J) {
-#ifndef C2B_DP_PREFETCH
             const uint4 *pp = reinterpret_cast<const uint4 *>(prof0 + combo[j - 1] * Ipad);
-            const uint4 sa = wp::ldg4u(pp), sb = wp::ldg4u(pp + 1);
-#endif
+            const uint4 sa = pp[0], sb = pp[32];            // conflict-free 16-byte accesses (lanes contiguous per half)
             const uint32_t s[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
             const uint32_t dcol = (j == J) ? 0u : d4p;      // free opening in the last column (both reads end together)
             const uint32_t dsp = islast ? 0u : dcol;
@@ -874,30 +860,30 @@ C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint8_t *combo, 
     }
 }
 
-C2B_DEV void dp_dispatch2(const KParams &P, const RefDev &R, const uint8_t *combo, int J, int rb, uint2 *tb2,
+C2B_DEV void dp_dispatch2(const KParams &P, const RefDev &R, const uint32_t *prof, const uint8_t *combo, int J, int rb, uint2 *tb2,
                           const int32_t *bi, int32_t *bo, uint32_t &cM, uint32_t &cX, uint32_t &cY)
 {
     const int ks = (rb == R.nrb - 1) ? R.kstar : 8;
     switch (ks) {
-    case 0: dp_block2<0>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 1: dp_block2<1>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 2: dp_block2<2>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 3: dp_block2<3>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 4: dp_block2<4>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 5: dp_block2<5>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 6: dp_block2<6>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 7: dp_block2<7>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    default: dp_block2<8>(P, R, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 0: dp_block2<0>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 1: dp_block2<1>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 2: dp_block2<2>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 3: dp_block2<3>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 4: dp_block2<4>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 5: dp_block2<5>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 6: dp_block2<6>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 7: dp_block2<7>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    default: dp_block2<8>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
     }
 }
 
-C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint8_t *combo, int J, uint2 *tb2, int32_t *bnd)
+C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint32_t *prof, const uint8_t *combo, int J, uint2 *tb2, int32_t *bnd)
 {
     uint32_t cM = 0, cX = 0, cY = 0;
     const int bstride = 3 * (P.TS);
     const int nrb = R.nrb;
     for (int rb = 0; rb < nrb; rb++) {
-        dp_dispatch2(P, R, combo, J, rb, tb2, bnd + ((rb + 1) & 1) * bstride, bnd + (rb & 1) * bstride, cM, cX, cY);
+        dp_dispatch2(P, R, prof, combo, J, rb, tb2, bnd + ((rb + 1) & 1) * bstride, bnd + (rb & 1) * bstride, cM, cX, cY);
         wp::sync();
     }
     const uint32_t s2 = wp::max3_2(cM, cY, cX) & PK_TM;         // start state per half
@@ -906,7 +892,7 @@ C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint8_t *comb
 }
 
 // Two reads (rdA, rdB) of equal length J through the packed path.  Per-lane variables belong to the lane's half.
-C2B_DEV void process_pair(const KParams &P, WarpSmem &S, int64_t rdA, int64_t rdB, int warp_slot)
+C2B_DEV void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_prof, int64_t rdA, int64_t rdB, int warp_slot)
 {
     const int lane = wp::lane(), h = lane >> 4, hl = lane & 15;
     const int64_t myrd = h ? rdB : rdA;
@@ -949,7 +935,7 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, int64_t rdA, int64_t rd
             wp::sync();
             for (int p = lane; p < J; p += 32) S.combo[p] = (uint8_t)(cA[p] * P.nq + cB[p]);
             wp::sync();
-            const Walked wk = align_pair(P, R, S.combo, J, tb2, bnd);
+            const Walked wk = align_pair(P, R, (r == 0 && staged_prof) ? staged_prof : R.prof2, S.combo, J, tb2, bnd);
             const int mystrand = h ? sB : sA;
             if (wk.err) a.status |= C2B_ST_UNDEFINED;
             int sc = -1000000;
@@ -1003,7 +989,7 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, int64_t rdA, int64_t rd
 
 // Work item w = reads 2w and 2w+1.  Equal lengths inside every reference's proven 16-bit range -> packed pair;
 // otherwise each read takes the 32-bit path.
-C2B_DEV void process_item(const KParams &P, WarpSmem &S, int64_t w, int warp_slot)
+C2B_DEV void process_item(const KParams &P, WarpSmem &S, const uint32_t *staged_prof, int64_t w, int warp_slot)
 {
     const int64_t rdA = 2 * w, rdB = 2 * w + 1;
     const bool haveB = rdB < P.n_reads;
@@ -1019,7 +1005,7 @@ C2B_DEV void process_item(const KParams &P, WarpSmem &S, int64_t w, int warp_slo
         }
     }
     if (wp::lane() == 0) wp::addg(P.work_counter + (pair ? 2 : 3), 1);      // path statistics (c2b_path_counts)
-    if (pair) process_pair(P, S, rdA, haveB ? rdB : rdA, warp_slot);
+    if (pair) process_pair(P, S, staged_prof, rdA, haveB ? rdB : rdA, warp_slot);
     else {
         process_read(P, S, rdA, warp_slot);
         if (haveB) { wp::sync(); process_read(P, S, rdB, warp_slot); }

@@ -79,9 +79,29 @@ constexpr int WARPS_PER_CTA = C2B_WARPS_PER_CTA;      // launch-bounds maximum; 
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_align_classify_kernel(const KParams P)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpSmem *S = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
     const int warp_slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // Reference tile: the packed substitution profile of reference 0 is staged once per CTA into shared memory by the
+    // TMA engine (cp.async.bulk, completion on an mbarrier); every DP step then reads it with two 16-byte LDS.
+    const uint32_t *staged_prof = nullptr;
+    if (P.stage_bytes > 0) {
+        __shared__ __align__(8) unsigned long long mbar;
+        unsigned char *dst = smem_raw + (size_t)(blockDim.x >> 5) * sizeof(WarpSmem);
+        const uint32_t mbar_a = (uint32_t)__cvta_generic_to_shared(&mbar), dst_a = (uint32_t)__cvta_generic_to_shared(dst);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"((uint32_t)P.stage_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst_a), "l"(P.stage_src), "r"((uint32_t)P.stage_bytes), "r"(mbar_a) : "memory");
+        }
+        asm volatile("{\n .reg .pred p;\n C2B_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra C2B_DONE;\n bra C2B_WAIT;\n C2B_DONE:\n}" ::"r"(mbar_a) : "memory");
+        staged_prof = reinterpret_cast<const uint32_t *>(dst);
+    }
     // work items are fetched one ahead, and the next pair's read bytes are pulled into L2 while this pair computes
     unsigned long long w = 0;
     if ((threadIdx.x & 31) == 0) w = wp::fetch_work(P.work_counter);
@@ -96,7 +116,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_a
             const int64_t a = b0 + (int64_t)(threadIdx.x & 31) * 128;
             if (a < b1) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.reads + a));
         }
-        process_item(P, *S, (int64_t)w, warp_slot);       // reads 2w, 2w+1
+        process_item(P, *S, staged_prof, (int64_t)w, warp_slot);       // reads 2w, 2w+1
         __syncwarp();
         w = wn;
     }
@@ -126,7 +146,7 @@ struct c2b_engine {
     unsigned long long *d_counts = nullptr; size_t counts_n = 0;
     // scratch
     DevBuf tb, bnd, ops, work, lut;
-    int n_warps = 0, grid = 0, wpc = 8;
+    int n_warps = 0, grid = 0, wpc = 8, stage_cap = 0;
     int scratch_TS = 0;
     // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
     struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed, maxlen; int64_t *h_off = nullptr; size_t h_off_cap = 0;
@@ -169,12 +189,17 @@ int c2b_create(int device, c2b_engine **out)
     if (r == cudaSuccess) r = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (r == cudaSuccess) r = cudaEventCreate(&e->ev0);
     if (r == cudaSuccess) r = cudaEventCreate(&e->ev1);
-    if (r == cudaSuccess) r = cudaFuncSetAttribute(c2b_align_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)(sizeof(WarpSmem) * WARPS_PER_CTA));
-    int nsm = 0, occ = 0;
+    int nsm = 0, occ = 0, smem_sm = 0;
     if (r == cudaSuccess) r = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    if (r == cudaSuccess) r = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+    // room for a TMA-staged reference tile next to C2B_MIN_CTAS_PER_SM CTAs of per-warp state (1 KB per CTA is reserved by the driver)
+    e->stage_cap = smem_sm / C2B_MIN_CTAS_PER_SM - 1024 - (int)(sizeof(WarpSmem) * WARPS_PER_CTA) - 256;
+    if (e->stage_cap < 0) e->stage_cap = 0;
+    e->stage_cap &= ~127;
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(c2b_align_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(sizeof(WarpSmem) * WARPS_PER_CTA) + e->stage_cap);
     if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c2b_align_classify_kernel, WARPS_PER_CTA * 32,
-                                                                            sizeof(WarpSmem) * WARPS_PER_CTA);
+                                                                            sizeof(WarpSmem) * WARPS_PER_CTA + e->stage_cap);
     if (r != cudaSuccess) { g_create_err = std::string("c2b_create: ") + cudaGetErrorString(r); delete e; return C2B_E_CUDA; }
     if (occ < 1) occ = 1;
     e->wpc = WARPS_PER_CTA;
@@ -324,7 +349,8 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
                         for (int i = 0; i < I; i++) {
                             const uint32_t a = (uint32_t)(4 * (rf.score_rows[(size_t)qa * I + i] + 2 * beta));
                             const uint32_t b = (uint32_t)(4 * (rf.score_rows[(size_t)qb * I + i] + 2 * beta));
-                            prof2[((size_t)qa * p->nq + qb) * Ipad + i] = a | (b << 16);
+                            const int rbk = i >> 8, ln = (i >> 3) & 31, hf = (i >> 2) & 1, wd = i & 3;
+                            prof2[((size_t)qa * p->nq + qb) * Ipad + rbk * 256 + hf * 128 + ln * 4 + wd] = a | (b << 16);
                         }
                 for (int row = 0; row < I; row++) {
                     cIe2[row] = (uint32_t)(4 * rf.gap_incentive[row + 1]) * rep;
@@ -456,16 +482,26 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     P.vstride = e->vstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
     P.lut = (const uint8_t *)e->lut.p;
+    P.stage_bytes = 0; P.stage_src = nullptr;
+#ifndef C2B_EMU
+    {   // stage reference 0's packed profile when it exists and fits beside two CTAs' worth of per-warp state
+        const RefDev &r0 = e->refdev[0];
+        const size_t bytes = (size_t)e->prm.nq * e->prm.nq * r0.Ipad * 4;
+        if (r0.pk_maxJ > 0 && !e->forced_ops && bytes <= (size_t)e->stage_cap && !getenv("C2B_NO_TMA_STAGE")) {
+            P.stage_bytes = (int32_t)bytes; P.stage_src = r0.prof2;
+        }
+    }
+#endif
     RTCHK(rt_zero(e->work.p, 16, e->stream));             // [0] work counter, [1] widest alignment; [2],[3] = path statistics (cumulative)
 #ifndef C2B_EMU
     cudaEventRecord(e->ev0, e->stream);
-    c2b_align_classify_kernel<<<e->grid, e->wpc * 32, sizeof(WarpSmem) * e->wpc, e->stream>>>(P);
+    c2b_align_classify_kernel<<<e->grid, e->wpc * 32, sizeof(WarpSmem) * e->wpc + (size_t)P.stage_bytes, e->stream>>>(P);
     cudaEventRecord(e->ev1, e->stream);
     RTCHK(cudaGetLastError());
 #else
     {
         static WarpSmem S;
-        for (int64_t w = 0; 2 * w < n_reads; w++) emu::run_warp([&]() { process_item(P, S, w, 0); });
+        for (int64_t w = 0; 2 * w < n_reads; w++) emu::run_warp([&]() { process_item(P, S, nullptr, w, 0); });
     }
 #endif
     e->launches++;
