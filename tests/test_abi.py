@@ -42,9 +42,12 @@ def test_struct_sizes_match_header():
 
 
 def test_sass_is_sm100a_with_dpx_ops():
-    """The shipped kernel is native sm_100a code using the DPX integer pipeline (VIMNMX3 / VIADDMNMX)."""
+    """The shipped kernel is native sm_100a code: DPX integer ops (packed 16-bit and 32-bit), warp shuffles, and the
+    TMA bulk copy (UBLKCP) + mbarrier (SYNCS) that stage the reference tile in shared memory."""
     import subprocess
     from crispresso2_b200 import _lib
     out = subprocess.run(["cuobjdump", "-sass", _lib.DEFAULT_LIB], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert "VIMNMX3" in out and "VIADDMNMX" in out and "SHFL" in out
+    assert "VIMNMX3.S16x2" in out and "VIADDMNMX.S16x2" in out
+    assert "UBLKCP" in out and "SYNCS" in out
