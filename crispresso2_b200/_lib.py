@@ -24,6 +24,7 @@ F_ASSIGN_FIRST = 16
 F_DISCARD_INDEL_READS = 32
 F_NO_STRAND_SEARCH = 64
 F_NO_PAIRING = 128
+F_HDR_REF1 = 256
 
 ST_BAD_CHAR = 1
 ST_UNDEFINED = 2
@@ -35,11 +36,13 @@ V_ALL_INS, V_ALL_INS_LEFT, V_ALL_DEL, V_ALL_SUB, V_INS, V_DEL, V_SUB, V_SUBBASE0
 V_BASEDEV0 = V_SUBBASE0 + MAX_Q
 V_INS_LEN = V_BASEDEV0 + MAX_Q + 1
 V_DEL_LEN = V_INS_LEN + 1
-NVEC = V_DEL_LEN + 1
+V_R1_ALL_INS, V_R1_ALL_INS_LEFT, V_R1_ALL_DEL, V_R1_ALL_SUB = V_DEL_LEN + 1, V_DEL_LEN + 2, V_DEL_LEN + 3, V_DEL_LEN + 4
+V_R1_BASEDEV0 = V_DEL_LEN + 5
+NVEC = V_R1_BASEDEV0 + MAX_Q + 1
 SCALARS = ["TOTAL", "MODIFIED", "UNMODIFIED", "DISCARDED", "INS", "DEL", "SUB", "ONLY_INS", "ONLY_DEL", "ONLY_SUB",
            "INS_DEL", "INS_SUB", "DEL_SUB", "INS_DEL_SUB", "AMBIGUOUS_W", "N_GLOBAL_SUBS", "N_SUBS_OUTSIDE_WINDOW",
            "N_MODS_IN_WINDOW", "N_MODS_OUTSIDE_WINDOW", "N_READS_IRREGULAR_ENDS", "N_ALIGNED_UNIQUE",
-           "N_ALIGNED_COUNT"]
+           "N_ALIGNED_COUNT", "REF1_W"]
 NSCAL = len(SCALARS)
 S = {n: k for k, n in enumerate(SCALARS)}
 

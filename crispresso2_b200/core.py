@@ -52,6 +52,8 @@ def _flags(args):
         f |= _lib.F_ASSIGN_FIRST
     if getattr(args, "discard_indel_reads", False):
         f |= _lib.F_DISCARD_INDEL_READS
+    if getattr(args, "expected_hdr_amplicon_seq", "") or getattr(args, "prime_editing_pegRNA_extension_seq", ""):
+        f |= _lib.F_HDR_REF1
     return f
 
 

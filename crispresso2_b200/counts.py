@@ -56,3 +56,28 @@ class CountBlock:
         keys = ["N_GLOBAL_SUBS", "N_SUBS_OUTSIDE_WINDOW", "N_MODS_IN_WINDOW", "N_MODS_OUTSIDE_WINDOW",
                 "N_READS_IRREGULAR_ENDS"]
         return {k: sum(self.scalar(r, k) for r in self.ref_names) for k in keys}
+
+    def vectors_ref1(self, ref):
+        """HDR / prime-editing mode: ref1_all_*_count_vectors[ref] and ref1_all_base_count_vectors[ref + "_" + nuc]
+        (CRISPRessoCORE.py:4195-4272).  For reference 0 they are copies of its own all_* vectors (:4217-4224)."""
+        ref0 = self.ref_names[0]
+        if ref == ref0:
+            V = self.vectors(ref0)
+            out = {"ref1_all_insertion_count": V["all_insertion_count"], "ref1_all_insertion_left_count": V["all_insertion_left_count"],
+                   "ref1_all_deletion_count": V["all_deletion_count"], "ref1_all_substitution_count": V["all_substitution_count"]}
+            for ch in self.alphabet + "-":
+                out["ref1_all_base_count_" + ch] = V["all_base_count_" + ch]
+        else:
+            L = len(self.ref_seqs[0])
+            V = self._vec[ref]
+            f = lambda row: V[row, :L].astype(np.float64)
+            out = {"ref1_all_insertion_count": f(_lib.V_R1_ALL_INS), "ref1_all_insertion_left_count": f(_lib.V_R1_ALL_INS_LEFT),
+                   "ref1_all_deletion_count": f(_lib.V_R1_ALL_DEL), "ref1_all_substitution_count": f(_lib.V_R1_ALL_SUB)}
+            w = self.scalar(ref, "REF1_W")
+            seq0 = np.frombuffer(self.ref_seqs[0].encode(), dtype=np.uint8)
+            for q, ch in enumerate(self.alphabet):
+                out["ref1_all_base_count_" + ch] = f(_lib.V_R1_BASEDEV0 + q) + np.where(seq0 == ord(ch), float(w), 0.0)
+            out["ref1_all_base_count_-"] = f(_lib.V_R1_BASEDEV0 + len(self.alphabet))
+        out["ref1_all_indelsub_count"] = (out["ref1_all_insertion_count"] + out["ref1_all_deletion_count"]
+                                          + out["ref1_all_substitution_count"])
+        return out

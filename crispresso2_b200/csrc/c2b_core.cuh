@@ -406,16 +406,18 @@ struct RowOut {
 constexpr int RM_SCAL = 1;   // scalars + edit list (COREResources.pyx:108-163)
 constexpr int RM_VEC = 2;    // per-position count vectors, weight w (CRISPRessoCORE.py:4016-4081)
 constexpr int RM_LEN = 4;    // insertion/deletion length vectors (:4104-4115), only for reads that carry a modification
+constexpr int RM_REF1 = 8;   // HDR re-projection (:4255-4272): the scattered alignment is the one to reference 0, the
+                             // vectors updated are the ref1_* block of the reference the read was assigned to (Vt)
 
 C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *rowinfo, const uint32_t *rowins, RowOut &o,
-                           c2b_edit *ed, long long w, int mode)
+                           c2b_edit *ed, long long w, int mode, unsigned long long *Vt = nullptr)
 {
     const int lane = wp::lane();
     const uint32_t lt = (1u << lane) - 1u;
     const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
                ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
-    const bool scal = mode & RM_SCAL, vec = mode & RM_VEC, lenv = mode & RM_LEN;
-    unsigned long long *V = R.vec;
+    const bool scal = mode & RM_SCAL, vec = mode & RM_VEC, lenv = mode & RM_LEN, ref1 = mode & RM_REF1;
+    unsigned long long *V = ref1 ? Vt : R.vec;
     const int vs = P.vstride;
     int open_a = -1; uint32_t prevD = 0;
     const int I = R.I;
@@ -502,6 +504,17 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
                 const int rc = R.rcode[p];
                 wp::addg(V + (int64_t)(C2B_V_BASEDEV0 + (isdel ? P.nq : rcode)) * vs + p, w);
                 if (rc != 255) wp::addg(V + (int64_t)(C2B_V_BASEDEV0 + rc) * vs + p, -w);
+            }
+        }
+        if (ref1) {
+            if (insr > 0) wp::addg(V + (int64_t)C2B_V_R1_ALL_INS_LEFT * vs + p, w);
+            if (insr > 0 || insl > 0) wp::addg(V + (int64_t)C2B_V_R1_ALL_INS * vs + p, w);
+            if (isdel) wp::addg(V + (int64_t)C2B_V_R1_ALL_DEL * vs + p, w);
+            if (issub) wp::addg(V + (int64_t)C2B_V_R1_ALL_SUB * vs + p, w);
+            if (isdel || differs) {
+                const int rc = R.rcode[p];
+                wp::addg(V + (int64_t)(C2B_V_R1_BASEDEV0 + (isdel ? P.nq : rcode)) * vs + p, w);
+                if (rc != 255) wp::addg(V + (int64_t)(C2B_V_R1_BASEDEV0 + rc) * vs + p, -w);
             }
         }
         if (lenv && (win_r || win_l))
@@ -703,6 +716,30 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
                 wp::addg(SC + C2B_S_N_ALIGNED_COUNT, cnt);
             }
             wp::sync();
+        }
+        // HDR / prime editing: reads assigned to another reference are also classified on their alignment to reference 0
+        if ((P.flags & C2B_F_HDR_REF1) && multi && r_begin == 0 && !ambiguous && w > 0) {
+            const uint32_t eff = first ? (rec.winner_mask & (0u - rec.winner_mask)) : rec.winner_mask;   // aln_ref_names
+            if (eff != 1u) {                                    // not "aligned to reference 0 only" (:4234)
+                const RefDev &R0 = P.refs[0];
+                uint64_t ops;
+                if (hoff < 0) ops = wp::ldcg64(opsbuf + lane);
+                else ops = lane < 16 ? wp::ldcg64(opsbuf + hoff + lane) : ~0ull;
+                const c2b_aln_rec prev = load_aln(P.alns + rd * P.n_refs);
+                const int n0 = wp::shfl((int)prev.aln_len, 0), strand0 = wp::shfl((int)prev.strand, 0);
+                for (int p = lane; p <= R0.I; p += 32) rowins[p] = 0;
+                wp::sync();
+                columns<false>(P, R0, rowinfo, rowins, strand0 ? rc : fw, J, ops, n0, 2, nullptr, nullptr);
+                wp::sync();
+                RowOut dummy; dummy.ins_n = dummy.del_n = dummy.sub_n = 0; dummy.n_ins_all = dummy.n_ins_win = 0;
+                dummy.n_del_all = dummy.n_del_win = dummy.n_del_pos = dummy.n_sub_all = 0; dummy.nent = 0;
+                for (int r = 1; r < r_end; r++) {
+                    if (!((eff >> (r & 31)) & 1u)) continue;
+                    rows_run(P, R0, rowinfo, rowins, dummy, nullptr, w, RM_REF1, P.refs[r].vec);
+                    if (lane == 0) wp::addg(P.refs[r].scal + C2B_S_REF1_W, w);
+                }
+                wp::sync();
+            }
         }
     }
     if (lane == 0) P.recs[rd] = rec;

@@ -43,6 +43,8 @@ extern "C" {
 #define C2B_F_DISCARD_INDEL_READS  32u
 #define C2B_F_NO_STRAND_SEARCH     64u   /* global_align-only mode: forward strand, no seed test */
 #define C2B_F_NO_PAIRING          128u   /* debugging / A-B runs: never use the packed two-reads-per-warp path */
+#define C2B_F_HDR_REF1            256u   /* args.expected_hdr_amplicon_seq / prime-editing extension set: also build the
+                                            "ref1" re-projection vectors of CRISPRessoCORE.py:4195-4272 */
 
 typedef struct {
     int32_t  gap_open;        /* args.needleman_wunsch_gap_open   (Align.pyx:104) */
@@ -125,7 +127,11 @@ enum {
     C2B_V_BASEDEV0 = C2B_V_SUBBASE0 + C2B_MAX_Q,   /* + code (nq = '-') : all_base_count deviation from "read == ref" */
     C2B_V_INS_LEN = C2B_V_BASEDEV0 + C2B_MAX_Q + 1,
     C2B_V_DEL_LEN,
-    C2B_NVEC
+    /* HDR mode: reads assigned to THIS reference, re-classified on their alignment to reference 0; positions are
+     * reference-0 positions (ref1_all_*_count_vectors[this ref], CRISPRessoCORE.py:4255-4272) */
+    C2B_V_R1_ALL_INS, C2B_V_R1_ALL_INS_LEFT, C2B_V_R1_ALL_DEL, C2B_V_R1_ALL_SUB,
+    C2B_V_R1_BASEDEV0,                 /* + code (nq = '-'): deviation from "read == reference-0 base" */
+    C2B_NVEC = C2B_V_R1_BASEDEV0 + C2B_MAX_Q + 1
 };
 enum {
     C2B_S_TOTAL = 0, C2B_S_MODIFIED, C2B_S_UNMODIFIED, C2B_S_DISCARDED,
@@ -135,6 +141,7 @@ enum {
     /* aln_stats of process_fastq (CRISPRessoCORE.py:1988-1999), accumulated with the dedup count */
     C2B_S_N_GLOBAL_SUBS, C2B_S_N_SUBS_OUTSIDE_WINDOW, C2B_S_N_MODS_IN_WINDOW, C2B_S_N_MODS_OUTSIDE_WINDOW,
     C2B_S_N_READS_IRREGULAR_ENDS, C2B_S_N_ALIGNED_UNIQUE, C2B_S_N_ALIGNED_COUNT,
+    C2B_S_REF1_W,          /* weight re-projected onto reference 0 for this reference (C2B_F_HDR_REF1) */
     C2B_NSCAL
 };
 

@@ -225,6 +225,7 @@ class Params:
         self.assign_ambiguous_alignments_to_first_reference = False
         self.expand_ambiguous_alignments = False
         self.discard_indel_reads = False
+        self.expected_hdr_amplicon_seq = ""
         for k, v in kw.items():
             setattr(self, k, v)
 
@@ -437,6 +438,41 @@ def count_vectors(cache, refs, ref_names, params):
                 for (a, b), sz in zip(p["deletion_coordinates"], p["deletion_sizes"]):
                     V["deletion_length"][list(range(a, b))] += sz * c
     return vec, sca, classes, total
+
+
+def ref1_vectors(cache, refs, ref_names, params):
+    """HDR / prime-editing re-projection (CRISPRessoCORE.py:4195-4272); call AFTER count_vectors (it uses the counts left
+    by the reverse-complement merge).  -> {ref: {name: float64 array over reference-0 positions}} for ref != ref_names[0]."""
+    r0 = ref_names[0]
+    L0 = len(refs[r0]["sequence"])
+    names = ["ref1_all_insertion_count", "ref1_all_insertion_left_count", "ref1_all_deletion_count",
+             "ref1_all_substitution_count"] + ["ref1_all_base_count_" + b for b in "ACGTN-"]
+    out = {r: {n: np.zeros(L0) for n in names} for r in ref_names}
+    for s, v in cache.items():
+        c = v["count"]
+        if c == 0:
+            continue
+        if len(v["aln_ref_names"]) == 1 and v["aln_ref_names"][0] == r0:
+            continue
+        if v["class_name"] == "AMBIGUOUS":
+            continue
+        _, s1, s2, _ = v["ref_aln_details"][0]
+        p = find_indels_substitutions(s1, s2, refs[r0]["include_idxs"])
+        for r in v["aln_ref_names"]:
+            if r == r0:
+                continue
+            V = out[r]
+            V["ref1_all_insertion_count"][p["all_insertion_positions"]] += c
+            V["ref1_all_insertion_left_count"][p["all_insertion_left_positions"]] += c
+            V["ref1_all_deletion_count"][p["all_deletion_positions"]] += c
+            V["ref1_all_substitution_count"][p["all_substitution_positions"]] += c
+            for ch, rp in zip(s1, p["ref_positions"]):
+                if rp >= 0:
+                    V["ref1_all_base_count_" + ch][rp] += c
+    for r in ref_names:
+        out[r]["ref1_all_indelsub_count"] = (out[r]["ref1_all_insertion_count"] + out[r]["ref1_all_deletion_count"]
+                                             + out[r]["ref1_all_substitution_count"])
+    return out
 
 
 # --------------------------------------------------------------------------- compiled reference

@@ -92,6 +92,16 @@ def run_case(name, argv, keep_files):
         return out
 
     CRISPRessoCORE.process_fastq = spy
+    orig_ctx = CRISPRessoCORE.CorePlotContext
+
+    def ctx_spy(*a, **kw):
+        # the HDR "ref1" re-projection vectors (CRISPRessoCORE.py:4195-4272) only leave main() through this object
+        keys = ["ref1_all_insertion_count_vectors", "ref1_all_insertion_left_count_vectors", "ref1_all_deletion_count_vectors",
+                "ref1_all_substitution_count_vectors", "ref1_all_indelsub_count_vectors", "ref1_all_base_count_vectors"]
+        rec["ref1"] = {k: _plain(kw.get(k, {})) for k in keys}
+        return orig_ctx(*a, **kw)
+
+    CRISPRessoCORE.CorePlotContext = ctx_spy
     work = tempfile.mkdtemp(prefix="c2gold_")
     old_argv, old_cwd = sys.argv, os.getcwd()
     try:
@@ -106,6 +116,7 @@ def run_case(name, argv, keep_files):
         sys.argv = old_argv
         os.chdir(old_cwd)
         CRISPRessoCORE.process_fastq = orig
+        CRISPRessoCORE.CorePlotContext = orig_ctx
     run_dirs = [d for d in os.listdir(work) if d.startswith("CRISPResso_on_")]
     assert len(run_dirs) == 1, run_dirs
     rd = os.path.join(work, run_dirs[0])

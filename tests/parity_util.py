@@ -15,7 +15,17 @@ def args_from(params):
     a.prime_editing_pegRNA_scaffold_seq = ""
     a.needleman_wunsch_aln_matrix_loc = "EDNAFULL"
     a.n_processes = "1"
+    if not hasattr(a, "expected_hdr_amplicon_seq"):
+        a.expected_hdr_amplicon_seq = ""
+    a.prime_editing_pegRNA_extension_seq = ""
     return a
+
+
+REF1_KEYS = {"ref1_all_insertion_count_vectors": "ref1_all_insertion_count",
+             "ref1_all_insertion_left_count_vectors": "ref1_all_insertion_left_count",
+             "ref1_all_deletion_count_vectors": "ref1_all_deletion_count",
+             "ref1_all_substitution_count_vectors": "ref1_all_substitution_count",
+             "ref1_all_indelsub_count_vectors": "ref1_all_indelsub_count"}
 
 
 def check_golden_case(engine, case, tmp_path, max_reads=None):
@@ -28,6 +38,9 @@ def check_golden_case(engine, case, tmp_path, max_reads=None):
         for k, s in enumerate(reads):
             fh.write("@r%d\n%s\n+\n%s\n" % (k, s, "I" * len(s)))
     args = args_from(rec["params"])
+    hdr = bool(rec.get("ref1", {}).get("ref1_all_deletion_count_vectors"))
+    if hdr:
+        args.expected_hdr_amplicon_seq = refs[rec["ref_names"][1]]["sequence"]
     cache = {}
     stats, lost = core.process_fastq(str(fq), cache, rec["ref_names"], refs, args, [], str(tmp_path), engine=engine,
                                      aln_matrix=O.make_matrix())
@@ -59,6 +72,12 @@ def check_golden_case(engine, case, tmp_path, max_reads=None):
         nf = G.nuc_freq_rows(G.file_for(rec, r, "Nucleotide_frequency_table.txt"))
         for b in "ACGTN-":
             assert (nf[b] == V["all_base_count_" + b]).all(), (r, b)
+        if hdr and max_reads is None:               # ref1_* vectors captured from the reference's CorePlotContext
+            R1 = block.vectors_ref1(r)
+            for gk, mk in REF1_KEYS.items():
+                assert R1[mk].tolist() == rec["ref1"][gk][r], (r, gk)
+            for b in "ACGTN-":
+                assert R1["ref1_all_base_count_" + b].tolist() == rec["ref1"]["ref1_all_base_count_vectors"][r + "_" + b], (r, b)
 
 
 def check_against_oracle(engine, refs, ref_names, params, reads, matrix):
@@ -93,6 +112,12 @@ def check_against_oracle(engine, refs, ref_names, params, reads, matrix):
         S = block.scalars(r)
         for name in O.SCALAR_NAMES:
             assert S[name] == sca[r][name], (r, name, S[name], sca[r][name])
+    if getattr(params, "expected_hdr_amplicon_seq", ""):
+        want = O.ref1_vectors(cache_o, refs, ref_names, params)
+        for r in ref_names[1:]:
+            R1 = block.vectors_ref1(r)
+            for name, v in want[r].items():
+                assert (R1[name] == v).all(), (r, name)
 
 
 def check_pooled(engine, n_amplicons=6, reads_per=40, seed=21, amp_len=(120, 200)):

@@ -83,7 +83,8 @@ def test_three_amplicons_and_ambiguity_flags(emu):
     reads = []
     for a in (amp, hdr, snp):
         reads += [r.tobytes().decode() for r in synth.synth_reads(rng, a, 40, 120, sub_rate=0.01, rc_frac=0.1, cut=62)]
-    for kw in ({}, {"expand_ambiguous_alignments": True}, {"assign_ambiguous_alignments_to_first_reference": True}):
+    for kw in ({}, {"expand_ambiguous_alignments": True}, {"assign_ambiguous_alignments_to_first_reference": True},
+               {"expected_hdr_amplicon_seq": hdr}, {"expected_hdr_amplicon_seq": hdr, "expand_ambiguous_alignments": True}):
         PU.check_against_oracle(emu, refs, names, O.Params(**kw), reads, O.make_matrix())
 
 
