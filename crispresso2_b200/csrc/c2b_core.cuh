@@ -44,6 +44,10 @@ C2B_DEV uint32_t max3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s1
 C2B_DEV uint32_t addmax_2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }  // per half max(a+b, c)
 C2B_DEV uint4 ldg4u(const uint4 *p) { return __ldg(p); }
 C2B_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// shared-state-space accesses through a 32-bit address kept in a register (no generic-address arithmetic in hot loops)
+C2B_DEV uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+C2B_DEV uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+C2B_DEV uint4 lds_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 C2B_DEV uint2 ldcg2(const uint2 *p) { return __ldcg(p); }
 C2B_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }   // (hi:lo) >> sh
 C2B_DEV int popc(uint32_t x) { return __popc(x); }
@@ -194,7 +198,7 @@ C2B_DEV void dp_block(const KParams &P, const RefDev &R, const uint8_t *codes, c
                 const int x = wp::addmax(M[k], dik, X[k]) + cIe[k];      // gap in reference ("I"), incentive of row i
                 const int y = wp::addmax(upM, dik + g4[k], upY) + ge4;   // gap in read ("J"), incentive of row i-1 on open
                 wT = wp::funnel_r(wT, (uint32_t)z, 2);                   // low two bits of z = origin of M
-                wIJ = wp::funnel_r(wIJ, (uint32_t)((x & 2) | (y & ~2)), 2);   // bit1: I extends, bit0: J extends
+                wIJ = wp::funnel_r(wIJ, (uint32_t)(x | y), 2);   // low bits of x: 00/10 (I extends), of y: 00/01 (J extends)
                 dM = M[k]; dX = X[k]; dY = Y[k];
                 M[k] = nm; X[k] = x | 2; Y[k] = y | 1;
                 upM = nm; upY = Y[k];
@@ -826,7 +830,7 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
 // (RefDev::pk_maxJ); anything else takes the 32-bit path above.
 constexpr uint32_t PK_SENT = 0x01000100u, PK_T2 = 0x00020002u, PK_T1 = 0x00010001u, PK_TM = 0x00030003u;
 
-template <int KSTAR>
+template <int KSTAR, bool STAGED>
 C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint32_t *prof, const uint8_t *combo, const int J, const int rb,
                        uint2 *__restrict__ tb2, const int32_t *bnd_in, int32_t *bnd_out, uint32_t &cM, uint32_t &cX, uint32_t &cY)
 {
@@ -855,7 +859,10 @@ C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint32_t *prof, 
 
     const int nsteps = J + nl - 1;
     const uint32_t *__restrict__ prof0 = prof + rb * 256 + lane * 4;     // shared (TMA-staged) or global copy, same layout
-    uint2 *__restrict__ tbw = tb2 + ((int64_t)rb * P.TS) * 32 + lane;
+    const uint32_t prof_sa = STAGED ? wp::smem_addr(prof0) : 0u;         // 32-bit shared address of the staged tile
+    const uint32_t combo_sa = wp::smem_addr(combo) - 1u;                 // combo[j-1] = [combo_sa + j]
+    const uint32_t qstride = (uint32_t)Ipad * 4u;
+    uint2 *__restrict__ tbp = tb2 + ((int64_t)rb * P.TS + 1) * 32 + lane;   // slab row of step t (advanced by 32 entries per step)
     const bool lane_on = lane < nl;
 
     for (int t = 1; t <= nsteps; t++) {
@@ -881,14 +888,15 @@ C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint32_t *prof, 
                 const uint32_t x = wp::addmax_2(M[k], dik, X[k]) + cIe[k];
                 const uint32_t y = wp::addmax_2(upM + g4[k], dik, upY);              // biased gap_extend is 0
                 wT = wT * 4u + t2;
-                wIJ = wIJ * 4u + (((x & PK_T2) | (y & ~PK_T2)) & PK_TM);
+                wIJ = wIJ * 4u + ((x | y) & PK_TM);     // x's low bits are 00/10 (I extends), y's 00/01 (J extends)
                 dM = M[k]; dX = X[k]; dY = Y[k];
                 M[k] = nm; X[k] = x | PK_T2; Y[k] = y | PK_T1;
                 upM = nm; upY = Y[k];
             }
-            tbw[(int64_t)t * 32] = make_uint2(wT, wIJ);
+            *tbp = make_uint2(wT, wIJ);
             if (!lastblk && lane == 31) { bnd_out[3 * j] = (int)M[7]; bnd_out[3 * j + 1] = (int)X[7]; bnd_out[3 * j + 2] = (int)Y[7]; }
         }
+        tbp += 32;
         pM = uM; pX = uX; pY = uY;
     }
     if (lastblk) {
@@ -897,30 +905,32 @@ C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint32_t *prof, 
     }
 }
 
+template <bool STAGED>
 C2B_DEV void dp_dispatch2(const KParams &P, const RefDev &R, const uint32_t *prof, const uint8_t *combo, int J, int rb, uint2 *tb2,
                           const int32_t *bi, int32_t *bo, uint32_t &cM, uint32_t &cX, uint32_t &cY)
 {
     const int ks = (rb == R.nrb - 1) ? R.kstar : 8;
     switch (ks) {
-    case 0: dp_block2<0>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 1: dp_block2<1>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 2: dp_block2<2>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 3: dp_block2<3>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 4: dp_block2<4>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 5: dp_block2<5>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 6: dp_block2<6>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 7: dp_block2<7>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    default: dp_block2<8>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 0: dp_block2<0, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 1: dp_block2<1, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 2: dp_block2<2, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 3: dp_block2<3, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 4: dp_block2<4, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 5: dp_block2<5, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 6: dp_block2<6, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 7: dp_block2<7, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    default: dp_block2<8, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
     }
 }
 
-C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint32_t *prof, const uint8_t *combo, int J, uint2 *tb2, int32_t *bnd)
+C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint32_t *prof, bool staged, const uint8_t *combo, int J, uint2 *tb2, int32_t *bnd)
 {
     uint32_t cM = 0, cX = 0, cY = 0;
     const int bstride = 3 * (P.TS);
     const int nrb = R.nrb;
     for (int rb = 0; rb < nrb; rb++) {
-        dp_dispatch2(P, R, prof, combo, J, rb, tb2, bnd + ((rb + 1) & 1) * bstride, bnd + (rb & 1) * bstride, cM, cX, cY);
+        if (staged) dp_dispatch2<true>(P, R, prof, combo, J, rb, tb2, bnd + ((rb + 1) & 1) * bstride, bnd + (rb & 1) * bstride, cM, cX, cY);
+        else dp_dispatch2<false>(P, R, prof, combo, J, rb, tb2, bnd + ((rb + 1) & 1) * bstride, bnd + (rb & 1) * bstride, cM, cX, cY);
         wp::sync();
     }
     const uint32_t s2 = wp::max3_2(cM, cY, cX) & PK_TM;         // start state per half
@@ -972,7 +982,8 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_
             wp::sync();
             for (int p = lane; p < J; p += 32) S.combo[p] = (uint8_t)(cA[p] * P.nq + cB[p]);
             wp::sync();
-            const Walked wk = align_pair(P, R, (r == 0 && staged_prof) ? staged_prof : R.prof2, S.combo, J, tb2, bnd);
+            const bool staged = (r == 0 && staged_prof != nullptr);
+            const Walked wk = align_pair(P, R, staged ? staged_prof : R.prof2, staged, S.combo, J, tb2, bnd);
             const int mystrand = h ? sB : sA;
             if (wk.err) a.status |= C2B_ST_UNDEFINED;
             int sc = -1000000;

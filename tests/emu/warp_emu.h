@@ -91,6 +91,11 @@ C2B_DEV uint32_t addmax_2(uint32_t a, uint32_t b, uint32_t c)
 { return h_pack(std::max<int>((int16_t)(h_lo(a) + h_lo(b)), h_lo(c)), std::max<int>((int16_t)(h_hi(a) + h_hi(b)), h_hi(c))); }
 C2B_DEV uint4 ldg4u(const uint4 *p) { return *p; }
 C2B_DEV void prefetch_l2(const void *) {}
+// emulator: "shared addresses" are offsets into a per-thread pointer table
+static thread_local const unsigned char *g_smem_base = nullptr;
+C2B_DEV uint32_t smem_addr(const void *p) { if (!g_smem_base) g_smem_base = (const unsigned char *)p - 4096; return (uint32_t)((const unsigned char *)p - g_smem_base); }
+C2B_DEV uint32_t lds_u8(uint32_t a) { return g_smem_base[a]; }
+C2B_DEV uint4 lds_v4(uint32_t a) { return *reinterpret_cast<const uint4 *>(g_smem_base + a); }
 C2B_DEV uint2 ldcg2(const uint2 *p) { return *p; }
 C2B_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31)); }
 C2B_DEV int popc(uint32_t x) { return __builtin_popcount(x); }
