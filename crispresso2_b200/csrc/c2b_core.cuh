@@ -106,6 +106,7 @@ struct RefDev {
 struct KParams {
     const uint8_t *reads; const int64_t *offsets; int64_t n_reads;
     const int32_t *count, *qweight, *ref_id;
+    const int32_t *pair_order;        // optional: work item w handles reads pair_order[2w], pair_order[2w+1] (equal lengths adjacent)
     c2b_read_rec *recs; c2b_aln_rec *alns; uint8_t *strings; c2b_edit *edits;
     int32_t W, edit_cap;
     const RefDev *refs; int32_t n_refs;
@@ -1039,8 +1040,9 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_
 // otherwise each read takes the 32-bit path.
 C2B_DEV void process_item(const KParams &P, WarpSmem &S, const uint32_t *staged_prof, int64_t w, int warp_slot)
 {
-    const int64_t rdA = 2 * w, rdB = 2 * w + 1;
-    const bool haveB = rdB < P.n_reads;
+    const bool haveB = 2 * w + 1 < P.n_reads;
+    const int64_t rdA = P.pair_order ? P.pair_order[2 * w] : 2 * w;
+    const int64_t rdB = haveB ? (P.pair_order ? P.pair_order[2 * w + 1] : 2 * w + 1) : rdA;
     bool pair = !P.forced_ops && !(P.flags & C2B_F_NO_PAIRING);
     if (pair) {
         const int Ja = (int)(P.offsets[rdA + 1] - P.offsets[rdA]);
@@ -1053,7 +1055,7 @@ C2B_DEV void process_item(const KParams &P, WarpSmem &S, const uint32_t *staged_
         }
     }
     if (wp::lane() == 0) wp::addg(P.work_counter + (pair ? 2 : 3), 1);      // path statistics (c2b_path_counts)
-    if (pair) process_pair(P, S, staged_prof, rdA, haveB ? rdB : rdA, warp_slot);
+    if (pair) process_pair(P, S, staged_prof, rdA, rdB, warp_slot);
     else {
         process_read(P, S, rdA, warp_slot);
         if (haveB) { wp::sync(); process_read(P, S, rdB, warp_slot); }

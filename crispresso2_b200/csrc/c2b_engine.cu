@@ -149,12 +149,13 @@ struct c2b_engine {
     int n_warps = 0, grid = 0, wpc = 8, stage_cap = 0;
     int scratch_TS = 0;
     // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
-    struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed, maxlen; int64_t *h_off = nullptr; size_t h_off_cap = 0;
+    struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed, maxlen, ord; int32_t *h_ord = nullptr; size_t h_ord_cap = 0; int64_t *h_off = nullptr; size_t h_off_cap = 0;
                    rt_event in_done, k_done, out_done; bool used = false; } stage[2];
     rt_stream s_in = 0, s_out = 0;
     bool pipe_ready = false;
     double last_ms = 0; int64_t launches = 0;
     const uint64_t *forced_ops = nullptr; const int32_t *forced_n = nullptr;
+    const int32_t *pair_order = nullptr;
 #ifndef C2B_EMU
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 #endif
@@ -220,7 +221,8 @@ void c2b_destroy(c2b_engine *e)
     DevBuf *bufs[] = {&e->tb, &e->bnd, &e->ops, &e->work, &e->lut};
     for (DevBuf *b : bufs) if (b->p) rt_free(b->p);
     for (auto &st : e->stage) {
-        DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed, &st.maxlen};
+        DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed, &st.maxlen, &st.ord};
+        if (st.h_ord) rt_host_free(st.h_ord);
         for (DevBuf *b : sb) if (b->p) rt_free(b->p);
         if (st.h_off) rt_host_free(st.h_off);
         if (e->pipe_ready) { rt_event_destroy(st.in_done); rt_event_destroy(st.k_done); rt_event_destroy(st.out_done); }
@@ -481,6 +483,7 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     P.work_counter = (unsigned long long *)e->work.p;
     P.vstride = e->vstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
+    P.pair_order = e->pair_order;
     P.lut = (const uint8_t *)e->lut.p;
     P.stage_bytes = 0; P.stage_src = nullptr;
 #ifndef C2B_EMU
@@ -505,6 +508,13 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     }
 #endif
     e->launches++;
+    return C2B_OK;
+}
+
+int c2b_set_pair_order(c2b_engine *e, const int32_t *d_order)
+{
+    if (!e) return C2B_E_ARG;
+    e->pair_order = d_order;
     return C2B_OK;
 }
 
@@ -631,6 +641,31 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
         if (count) RTCHK(rt_h2d(st.cnt.p, count + c0, (size_t)n * 4, e->s_in));
         if (qweight) RTCHK(rt_h2d(st.qw.p, qweight + c0, (size_t)n * 4, e->s_in));
         if (ref_id) RTCHK(rt_h2d(st.rid.p, ref_id + c0, (size_t)n * 4, e->s_in));
+        // pairing order: counting sort of the chunk by (reference id, length) when reads differ, so equal ones are adjacent
+        bool need_order = false;
+        for (int64_t k = 1; k < n && !need_order; k++)
+            need_order = (st.h_off[k + 1] - st.h_off[k] != st.h_off[1] - st.h_off[0]) || (ref_id && ref_id[c0 + k] != ref_id[c0]);
+        e->pair_order = nullptr;
+        if (need_order) {
+            if ((rc = ensure(e, st.ord, (size_t)n * 4))) return rc;
+            if (st.h_ord_cap < (size_t)n) {
+                if (st.h_ord) rt_host_free(st.h_ord);
+                st.h_ord = (int32_t *)rt_host_alloc((size_t)n * 4); st.h_ord_cap = st.h_ord ? (size_t)n : 0;
+                if (!st.h_ord) return fail(e, C2B_E_CUDA, "c2b_align_batch: pinned allocation failed");
+            }
+            const int64_t nb = (int64_t)(C2B_MAX_READ_LEN + 1) * (ref_id ? e->n_refs : 1);
+            std::vector<int64_t> start((size_t)nb + 1, 0);
+            auto key = [&](int64_t k) -> int64_t {
+                const int64_t L = st.h_off[k + 1] - st.h_off[k];
+                const int64_t r = ref_id ? std::min<int64_t>(std::max<int32_t>(ref_id[c0 + k], 0), e->n_refs - 1) : 0;
+                return r * (C2B_MAX_READ_LEN + 1) + L;
+            };
+            for (int64_t k = 0; k < n; k++) start[(size_t)key(k) + 1]++;
+            for (int64_t b = 0; b < nb; b++) start[(size_t)b + 1] += start[(size_t)b];
+            for (int64_t k = 0; k < n; k++) st.h_ord[start[(size_t)key(k)]++] = (int32_t)k;
+            RTCHK(rt_h2d(st.ord.p, st.h_ord, (size_t)n * 4, e->s_in));
+            e->pair_order = (const int32_t *)st.ord.p;
+        }
         RTCHK(rt_record(st.in_done, e->s_in));
         RTCHK(rt_wait(e->stream, st.in_done));
         rc = c2b_align_batch_device(e, (const uint8_t *)st.reads.p, (const int64_t *)st.off.p, n, (int32_t)maxJ,
@@ -638,6 +673,7 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
                                     ref_id ? (const int32_t *)st.rid.p : nullptr, (c2b_read_rec *)st.recs.p,
                                     (c2b_aln_rec *)st.alns.p, strings ? (uint8_t *)st.str.p : nullptr,
                                     cap ? (c2b_edit *)st.ed.p : nullptr);
+        e->pair_order = nullptr;
         if (rc) return rc;
         // keep this launch's "widest alignment" before the next launch resets it
         RTCHK(cudaMemcpyAsyncOrCopy(st.maxlen.p, (const char *)e->work.p + 8, 8, e->stream));

@@ -185,6 +185,11 @@ int  c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t
                             int32_t max_read_len, const int32_t *d_count, const int32_t *d_qweight,
                             const int32_t *d_ref_id, c2b_read_rec *d_recs, c2b_aln_rec *d_alns,
                             uint8_t *d_strings, c2b_edit *d_edits);
+/* Optional pairing order for the next c2b_align_batch_device call(s): a permutation of 0..n_reads-1 (device pointer,
+ * or NULL to clear) in which reads of equal length (and equal ref_id) are adjacent, so that mixed-length batches still
+ * use the packed two-reads-per-warp path.  Results are always written at the reads' own indices.  c2b_align_batch
+ * builds this order itself. */
+int  c2b_set_pair_order(c2b_engine *e, const int32_t *d_order);
 int  c2b_sync(c2b_engine *e);
 void *c2b_stream(c2b_engine *e);                    /* cudaStream_t of the engine */
 double c2b_last_kernel_ms(c2b_engine *e);           /* CUDA-event time of the last align kernel launch */

@@ -186,7 +186,7 @@ def test_packed_pair_path_equals_32bit_path(eng):
         res = eng.align_packed(buf, off)
         out.append((res, eng.counts_raw(), eng.path_counts()))
     (a, ca, pa), (b, cb, pb) = out
-    assert pa[0] > 10000 and pa[1] > 1000 and pb[0] == 0
+    assert pa[0] > 15000 and pb[0] == 0 and pb[1] == 20000          # the pairing order puts equal lengths side by side
     assert (a.recs == b.recs).all() and (a.alns == b.alns).all() and (ca == cb).all()
     W = a.W
     cols = np.arange(W)[None, :] >= (W - a.alns[:, 0]["aln_len"].astype(np.int64))[:, None]
@@ -199,3 +199,17 @@ def test_packed_pair_path_equals_32bit_path(eng):
 def test_pooled_ref_id(eng):
     """BASELINE configs[3] shape: many amplicons, each read aligned to its own one (ref_id), one launch."""
     PU.check_pooled(eng, n_amplicons=24, reads_per=120, amp_len=(180, 280))
+
+
+def test_long_amplicon_three_row_blocks(eng):
+    rng = np.random.default_rng(12)
+    amp = synth.random_amplicon(rng, 610)
+    ref = synth.amplicon_setup(amp, guide_start=300, window_size=5)
+    reads = []
+    for k in range(200):
+        L = int(rng.integers(150, 401))
+        s0 = int(rng.integers(0, 610 - L))
+        s = synth.synth_reads(rng, amp, 1, 610, sub_rate=0.02, cut=ref["cut_point"])[0].tobytes().decode()
+        reads.append(s[s0:s0 + L])
+    reads.append(amp[100:500])
+    PU.check_against_oracle(eng, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
