@@ -554,20 +554,26 @@ C2B_DEV int strand_mode(const KParams &P, const RefDev &R, const uint8_t *fw, in
     const int L = R.seed_len, ns = R.nseeds;
     uint32_t hit = 0;                                        // bit s: fw seed s seen ; bit 8+s: rc seed s seen
     if (ns > 0 && L > 0) {
-        // each lane owns 8 consecutive start positions per 256-position block and rolls the packed k-mer along them
+        // each lane owns 8 consecutive start positions per 256-position block: roll the packed k-mer along them into
+        // registers first, then compare every seed (loaded once) against the 8 k-mers
         const uint64_t top = 3 * (uint64_t)(L - 1);
         for (int base = 8 * lane; base + L <= J; base += 256) {
-            uint64_t km = 0;
-            for (int c = 0; c < L; c++) km |= (uint64_t)fw[base + c] << (3 * c);
+            uint64_t km[8];
+            uint64_t cur = 0;
+            for (int c = 0; c < L; c++) cur |= (uint64_t)fw[base + c] << (3 * c);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                km[e] = (base + e + L <= J) ? cur : ~0ull;                 // ~0 never equals a seed
+                if (e < 7 && base + e + L < J) cur = (cur >> 3) | ((uint64_t)fw[base + e + L] << top);
+            }
 #pragma unroll 1
-            for (int e = 0;; e++) {
-#pragma unroll 1
-                for (int s = 0; s < ns; s++) {
-                    if (km == R.fw_seed[s]) hit |= 1u << s;
-                    if (km == R.rc_seed[s]) hit |= 1u << (8 + s);
-                }
-                if (e == 7 || base + e + 1 + L > J) break;
-                km = (km >> 3) | ((uint64_t)fw[base + e + L] << top);
+            for (int s = 0; s < ns; s++) {
+                const uint64_t f = R.fw_seed[s], r = R.rc_seed[s];
+                bool hf = false, hr = false;
+#pragma unroll
+                for (int e = 0; e < 8; e++) { hf |= (km[e] == f); hr |= (km[e] == r); }
+                if (hf && f != ~0ull) hit |= 1u << s;
+                if (hr && r != ~0ull) hit |= 1u << (8 + s);
             }
         }
     }
