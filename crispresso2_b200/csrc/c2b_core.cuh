@@ -113,6 +113,7 @@ struct KParams {
     int32_t go, ge, seed_count, seed_min; uint32_t flags; int32_t nq;
     uint8_t alpha[C2B_MAX_Q]; uint8_t comp[C2B_MAX_Q];
     uint32_t *tb; int64_t tb_words_per_warp; int32_t TS;      // TS = steps stride per row block (maxJ + 32)
+    uint32_t *tbb; int64_t tbb_words_per_warp;                // banded slab of the packed path (PK_BAND_SLOTS slots per lane)
     int32_t *bnd; int64_t bnd_words_per_warp;                 // 2 x 3 x (maxJ+1): row-block boundary rows
     uint64_t *opsbuf;                                         // [warp][n_refs][32] op streams (multi-reference)
     unsigned long long *work_counter;
@@ -132,6 +133,12 @@ struct WarpSmem {
     uint32_t rowins[MAXI + 4]; // rowins[r]: bases inserted between reference positions r-1 and r (pair: halves of 514)
 };
 constexpr int PK_ROWINFO_STRIDE = 512, PK_ROWINS_STRIDE = 514, PK_MAX_ALN = 512;
+// Banded traceback slab of the packed path.  Lane l (rows 8l+1..8l+8) keeps only the PK_BAND_SLOTS wavefront steps around
+// its own diagonal (step t -> slot t - 9l + PK_BAND_B): cells whose column is within about -29..+27 of their row.  The DP
+// itself is unchanged (every cell is computed); if the traceback ever needs a cell outside the band, the pair is simply
+// re-run with the full slab.  The banded slabs of the whole grid (16 KB per warp, 39 MB) stay resident in L2.
+constexpr int PK_BAND_SLOTS = 64, PK_BAND_B = 28, PK_BAND_MAXD = 8;
+struct SlabMode { int slope, off, ns; };          // slot = t - slope*lane + off, kept iff 0 <= slot < ns
 
 struct Walked { uint64_t ops; int n; int err; };
 
@@ -241,7 +248,7 @@ C2B_DEV void dp_dispatch(const KParams &P, const RefDev &R, const uint8_t *codes
 // 64-bit slab entries); otherwise the 32 lanes walk one read (G = 32).  Output as before: the group's lane L holds
 // ops 32L..32L+31 (2 bits each, counted from the right end of the alignment).
 template <bool PAIR>
-C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const uint32_t *__restrict__ tb, int s)
+C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const uint32_t *__restrict__ tb, int s, const SlabMode sm)
 {
     const int lane = wp::lane();
     const int hl = PAIR ? (lane & 15) : lane, hb = PAIR ? (lane & 16) : 0;
@@ -269,31 +276,40 @@ C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const 
         const int ci = i - hl * di, cj = j - hl * dj;
         const bool valid = active && ci >= 1 && cj >= 1;
         uint32_t v = 0;
+        bool inband = valid;
         if (valid) {
             const int r = ci - 1, key = r >> 3, rb = key >> 5, l = key & 31;
-            const int64_t idx = ((int64_t)rb * TS + cj + l) * 32 + l;
-            if (PAIR) {
-                const uint2 w2 = wp::ldcg2(tb2 + idx);
-                const uint32_t w = hb ? ((w2.x & 0xffff0000u) | (w2.y >> 16)) : ((w2.x << 16) | (w2.y & 0xffffu));
-                v = w >> (2 * (7 - (r & 7)));
-            } else v = wp::ldcg(tb + idx) >> (2 * (r & 7));
+            const int slot = cj + l - sm.slope * l + sm.off;
+            inband = (unsigned)slot < (unsigned)sm.ns;
+            if (inband) {
+                const int64_t idx = ((int64_t)rb * TS + slot) * 32 + l;
+                if (PAIR) {
+                    const uint2 w2 = wp::ldcg2(tb2 + idx);
+                    const uint32_t w = hb ? ((w2.x & 0xffff0000u) | (w2.y >> 16)) : ((w2.x << 16) | (w2.y & 0xffffu));
+                    v = w >> (2 * (7 - (r & 7)));
+                } else v = wp::ldcg(tb + idx) >> (2 * (r & 7));
+            }
         }
         const int tag = (int)((v >> 16) & 3u);
         const bool cont = valid && (s == OP_M ? tag == OP_M : (v & (uint32_t)s) != 0u);
         const uint32_t bc = (wp::ballot(cont) >> hb) & gmask, bv = (wp::ballot(valid) >> hb) & gmask;
-        const int nvalid = wp::popc(bv);                    // valid lanes are a prefix of the group
+        const uint32_t bo = (wp::ballot(valid && !inband) >> hb) & gmask;      // cells the banded slab did not keep
+        int nvalid = wp::popc(bv);                          // valid lanes are a prefix of the group
+        if (bo) { const int fo = wp::ffs(bo) - 1; if (fo < nvalid) nvalid = fo; }
+        const bool miss = active && nvalid == 0;            // the banded slab did not keep the next cell: caller re-runs with the full slab
         int f = wp::ffs(~bc) - 1;                           // leading run of "continue" (ffs(0) = 0 -> -1 when all 32 set)
         if (f < 0 || f > nvalid) f = nvalid;
         const bool brk = f < nvalid;
         const int run = brk ? f + 1 : nvalid;
         const int tagf = wp::shfl(tag, hb + (f < G ? f : G - 1));
-        if (active) {
+        if (miss) { err |= 4; i = 0; j = 0; }
+        else if (active) {
             const int news = brk ? (s == OP_M ? tagf : OP_M) : s;
             push(s, run);
             i -= run * di; j -= run * dj;
             err |= (news == 3);
             s = news;
-            if (s == OP_M) {                                // pull the window two iterations down the diagonal towards L2
+            if (s == OP_M && sm.slope == 0) {               // full slab: pull the window two iterations down the diagonal towards L2
                 const int pi = i - 2 * G - hl, pj = j - 2 * G - hl;
                 if (pi >= 1 && pj >= 1) {
                     const int r = pi - 1, key = r >> 3, rb = key >> 5, l = key & 31;
@@ -329,7 +345,8 @@ C2B_DEV Walked align_strand(const KParams &P, const RefDev &R, const uint8_t *co
         wp::sync();
     }
     const int s = wp::max3(cM, cY, cX) & 3;                     // start state, Align.pyx:349-358
-    return walk_batch<false>(P, R, J, tb, s);
+    const SlabMode full = {0, 0, P.TS};
+    return walk_batch<false>(P, R, J, tb, s, full);
 }
 
 // --------------------------------------------------------------------------------------------- columns
@@ -839,7 +856,7 @@ constexpr uint32_t PK_SENT = 0x01000100u, PK_T2 = 0x00020002u, PK_T1 = 0x0001000
 
 template <int KSTAR, bool STAGED>
 C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint32_t *prof, const uint8_t *combo, const int J, const int rb,
-                       uint2 *__restrict__ tb2, const int32_t *bnd_in, int32_t *bnd_out, uint32_t &cM, uint32_t &cX, uint32_t &cY)
+                       uint2 *__restrict__ tb2, const SlabMode sm, const int32_t *bnd_in, int32_t *bnd_out, uint32_t &cM, uint32_t &cX, uint32_t &cY)
 {
     const int lane = wp::lane();
     const int nrb = R.nrb, lstar = R.lstar, Ipad = R.Ipad;
@@ -869,7 +886,8 @@ C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint32_t *prof, 
     const uint32_t prof_sa = STAGED ? wp::smem_addr(prof0) : 0u;         // 32-bit shared address of the staged tile
     const uint32_t combo_sa = wp::smem_addr(combo) - 1u;                 // combo[j-1] = [combo_sa + j]
     const uint32_t qstride = (uint32_t)Ipad * 4u;
-    uint2 *__restrict__ tbp = tb2 + ((int64_t)rb * P.TS + 1) * 32 + lane;   // slab row of step t (advanced by 32 entries per step)
+    int slot = 1 - sm.slope * lane + sm.off;                             // slab slot of step t = 1 for this lane
+    uint2 *__restrict__ tbp = tb2 + ((int64_t)rb * P.TS + slot) * 32 + lane;   // advanced by one slot (32 entries) per step
     const bool lane_on = lane < nl;
 
     for (int t = 1; t <= nsteps; t++) {
@@ -900,10 +918,10 @@ C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint32_t *prof, 
                 M[k] = nm; X[k] = x | PK_T2; Y[k] = y | PK_T1;
                 upM = nm; upY = Y[k];
             }
-            *tbp = make_uint2(wT, wIJ);
+            if ((unsigned)slot < (unsigned)sm.ns) *tbp = make_uint2(wT, wIJ);
             if (!lastblk && lane == 31) { bnd_out[3 * j] = (int)M[7]; bnd_out[3 * j + 1] = (int)X[7]; bnd_out[3 * j + 2] = (int)Y[7]; }
         }
-        tbp += 32;
+        tbp += 32; slot++;
         pM = uM; pX = uX; pY = uY;
     }
     if (lastblk) {
@@ -914,35 +932,45 @@ C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint32_t *prof, 
 
 template <bool STAGED>
 C2B_DEV void dp_dispatch2(const KParams &P, const RefDev &R, const uint32_t *prof, const uint8_t *combo, int J, int rb, uint2 *tb2,
-                          const int32_t *bi, int32_t *bo, uint32_t &cM, uint32_t &cX, uint32_t &cY)
+                          const SlabMode sm, const int32_t *bi, int32_t *bo, uint32_t &cM, uint32_t &cX, uint32_t &cY)
 {
     const int ks = (rb == R.nrb - 1) ? R.kstar : 8;
     switch (ks) {
-    case 0: dp_block2<0, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 1: dp_block2<1, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 2: dp_block2<2, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 3: dp_block2<3, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 4: dp_block2<4, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 5: dp_block2<5, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 6: dp_block2<6, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    case 7: dp_block2<7, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
-    default: dp_block2<8, STAGED>(P, R, prof, combo, J, rb, tb2, bi, bo, cM, cX, cY); break;
+    case 0: dp_block2<0, STAGED>(P, R, prof, combo, J, rb, tb2, sm, bi, bo, cM, cX, cY); break;
+    case 1: dp_block2<1, STAGED>(P, R, prof, combo, J, rb, tb2, sm, bi, bo, cM, cX, cY); break;
+    case 2: dp_block2<2, STAGED>(P, R, prof, combo, J, rb, tb2, sm, bi, bo, cM, cX, cY); break;
+    case 3: dp_block2<3, STAGED>(P, R, prof, combo, J, rb, tb2, sm, bi, bo, cM, cX, cY); break;
+    case 4: dp_block2<4, STAGED>(P, R, prof, combo, J, rb, tb2, sm, bi, bo, cM, cX, cY); break;
+    case 5: dp_block2<5, STAGED>(P, R, prof, combo, J, rb, tb2, sm, bi, bo, cM, cX, cY); break;
+    case 6: dp_block2<6, STAGED>(P, R, prof, combo, J, rb, tb2, sm, bi, bo, cM, cX, cY); break;
+    case 7: dp_block2<7, STAGED>(P, R, prof, combo, J, rb, tb2, sm, bi, bo, cM, cX, cY); break;
+    default: dp_block2<8, STAGED>(P, R, prof, combo, J, rb, tb2, sm, bi, bo, cM, cX, cY); break;
     }
 }
 
-C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint32_t *prof, bool staged, const uint8_t *combo, int J, uint2 *tb2, int32_t *bnd)
+C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint32_t *prof, bool staged, const uint8_t *combo, int J,
+                          uint2 *tb_full, uint2 *tb_band, int32_t *bnd)
 {
-    uint32_t cM = 0, cX = 0, cY = 0;
     const int bstride = 3 * (P.TS);
     const int nrb = R.nrb;
-    for (int rb = 0; rb < nrb; rb++) {
-        if (staged) dp_dispatch2<true>(P, R, prof, combo, J, rb, tb2, bnd + ((rb + 1) & 1) * bstride, bnd + (rb & 1) * bstride, cM, cX, cY);
-        else dp_dispatch2<false>(P, R, prof, combo, J, rb, tb2, bnd + ((rb + 1) & 1) * bstride, bnd + (rb & 1) * bstride, cM, cX, cY);
-        wp::sync();
+    const int d = J - R.I;
+    bool band = tb_band != nullptr && nrb == 1 && d >= -PK_BAND_MAXD && d <= PK_BAND_MAXD;
+    for (;;) {
+        const SlabMode sm = band ? SlabMode{9, PK_BAND_B, PK_BAND_SLOTS} : SlabMode{0, 0, P.TS};
+        uint2 *tb2 = band ? tb_band : tb_full;
+        uint32_t cM = 0, cX = 0, cY = 0;
+        for (int rb = 0; rb < nrb; rb++) {
+            if (staged) dp_dispatch2<true>(P, R, prof, combo, J, rb, tb2, sm, bnd + ((rb + 1) & 1) * bstride, bnd + (rb & 1) * bstride, cM, cX, cY);
+            else dp_dispatch2<false>(P, R, prof, combo, J, rb, tb2, sm, bnd + ((rb + 1) & 1) * bstride, bnd + (rb & 1) * bstride, cM, cX, cY);
+            wp::sync();
+        }
+        const uint32_t s2 = wp::max3_2(cM, cY, cX) & PK_TM;         // start state per half
+        const int s = (wp::lane() & 16) ? (int)(s2 >> 16) : (int)(s2 & 3u);
+        const Walked wk = walk_batch<true>(P, R, J, reinterpret_cast<const uint32_t *>(tb2), s, sm);
+        if (!band || !wp::ballot((wk.err & 4) != 0)) return wk;
+        band = false;                                               // a traceback left the band: once more with the full slab
+        if (wp::lane() == 0) wp::addg(P.work_counter + 4, 1);
     }
-    const uint32_t s2 = wp::max3_2(cM, cY, cX) & PK_TM;         // start state per half
-    const int s = (wp::lane() & 16) ? (int)(s2 >> 16) : (int)(s2 & 3u);
-    return walk_batch<true>(P, R, J, reinterpret_cast<const uint32_t *>(tb2), s);
 }
 
 // Two reads (rdA, rdB) of equal length J through the packed path.  Per-lane variables belong to the lane's half.
@@ -952,6 +980,7 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_
     const int64_t myrd = h ? rdB : rdA;
     const int J = (int)(P.offsets[rdA + 1] - P.offsets[rdA]);
     uint2 *tb2 = reinterpret_cast<uint2 *>(P.tb + (int64_t)warp_slot * P.tb_words_per_warp);
+    uint2 *tbb = P.tbb ? reinterpret_cast<uint2 *>(P.tbb + (int64_t)warp_slot * P.tbb_words_per_warp) : nullptr;
     int32_t *bnd = P.bnd + (int64_t)warp_slot * P.bnd_words_per_warp;
     uint64_t *opsbuf = P.opsbuf + (int64_t)warp_slot * P.n_refs * 32;
     uint8_t *rowinfo = S.rowinfo + h * PK_ROWINFO_STRIDE;
@@ -990,7 +1019,7 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_
             for (int p = lane; p < J; p += 32) S.combo[p] = (uint8_t)(cA[p] * P.nq + cB[p]);
             wp::sync();
             const bool staged = (r == 0 && staged_prof != nullptr);
-            const Walked wk = align_pair(P, R, staged ? staged_prof : R.prof2, staged, S.combo, J, tb2, bnd);
+            const Walked wk = align_pair(P, R, staged ? staged_prof : R.prof2, staged, S.combo, J, tb2, tbb, bnd);
             const int mystrand = h ? sB : sA;
             if (wk.err) a.status |= C2B_ST_UNDEFINED;
             int sc = -1000000;

@@ -145,7 +145,7 @@ struct c2b_engine {
     void *d_tables = nullptr; RefDev *d_refs = nullptr;
     unsigned long long *d_counts = nullptr; size_t counts_n = 0;
     // scratch
-    DevBuf tb, bnd, ops, work, lut;
+    DevBuf tb, tbb, bnd, ops, work, lut;
     int n_warps = 0, grid = 0, wpc = 8, stage_cap = 0;
     int scratch_TS = 0;
     // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
@@ -156,6 +156,7 @@ struct c2b_engine {
     double last_ms = 0; int64_t launches = 0;
     const uint64_t *forced_ops = nullptr; const int32_t *forced_n = nullptr;
     const int32_t *pair_order = nullptr;
+    int64_t band_reruns = 0;
 #ifndef C2B_EMU
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 #endif
@@ -218,7 +219,7 @@ int c2b_create(int device, c2b_engine **out)
 void c2b_destroy(c2b_engine *e)
 {
     if (!e) return;
-    DevBuf *bufs[] = {&e->tb, &e->bnd, &e->ops, &e->work, &e->lut};
+    DevBuf *bufs[] = {&e->tb, &e->tbb, &e->bnd, &e->ops, &e->work, &e->lut};
     for (DevBuf *b : bufs) if (b->p) rt_free(b->p);
     for (auto &st : e->stage) {
         DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed, &st.maxlen, &st.ord};
@@ -419,6 +420,7 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
     if (TS <= e->scratch_TS) return C2B_OK;
     int rc;
     if ((rc = ensure(e, e->tb, (size_t)e->n_warps * e->max_nrb * TS * 64 * 4))) return rc;   // 64: a pair stores two words per lane
+    if ((rc = ensure(e, e->tbb, (size_t)e->n_warps * PK_BAND_SLOTS * 64 * 4))) return rc;                // banded slabs (packed path)
     if ((rc = ensure(e, e->bnd, (size_t)e->n_warps * 2 * 3 * TS * 4))) return rc;
     if ((rc = ensure(e, e->ops, (size_t)e->n_warps * e->n_refs * 32 * 8))) return rc;
     const bool fresh_work = !e->work.p;
@@ -431,11 +433,11 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
             !getenv("C2B_NO_L2_PERSIST")) {
-            const size_t slab = (size_t)e->n_warps * e->max_nrb * TS * 64 * 4;
+            const size_t slab = (size_t)e->n_warps * PK_BAND_SLOTS * 64 * 4;      // the banded slabs: the hot set
             const size_t carve = std::min((size_t)prop.persistingL2CacheMaxSize, slab);
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
             cudaStreamAttrValue av; memset(&av, 0, sizeof av);
-            av.accessPolicyWindow.base_ptr = e->tb.p;
+            av.accessPolicyWindow.base_ptr = e->tbb.p;
             av.accessPolicyWindow.num_bytes = std::min(slab, (size_t)prop.accessPolicyMaxWindowSize);
             av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)std::max<size_t>(1, av.accessPolicyWindow.num_bytes));
             av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -443,7 +445,7 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
             cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
             cudaGetLastError();
             if (getenv("C2B_VERBOSE"))
-                fprintf(stderr, "[c2b] grid %d x %d warps, traceback slab %.1f MB, persisting L2 max %.1f MB (L2 %.1f MB), window %.1f MB, hitRatio %.2f\n",
+                fprintf(stderr, "[c2b] grid %d x %d warps, banded traceback slabs %.1f MB, persisting L2 max %.1f MB (L2 %.1f MB), window %.1f MB, hitRatio %.2f\n",
                         e->grid, e->wpc, slab / 1e6, prop.persistingL2CacheMaxSize / 1e6, prop.l2CacheSize / 1e6,
                         av.accessPolicyWindow.num_bytes / 1e6, av.accessPolicyWindow.hitRatio);
         }
@@ -478,6 +480,7 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     memcpy(P.alpha, e->prm.alphabet, C2B_MAX_Q); memcpy(P.comp, e->prm.complement, C2B_MAX_Q);
     P.TS = e->scratch_TS;
     P.tb = (uint32_t *)e->tb.p; P.tb_words_per_warp = (int64_t)e->max_nrb * P.TS * 64;
+    P.tbb = getenv("C2B_NO_BAND") ? nullptr : (uint32_t *)e->tbb.p; P.tbb_words_per_warp = (int64_t)PK_BAND_SLOTS * 64;
     P.bnd = (int32_t *)e->bnd.p; P.bnd_words_per_warp = 2 * 3 * (int64_t)P.TS;
     P.opsbuf = (uint64_t *)e->ops.p;
     P.work_counter = (unsigned long long *)e->work.p;
@@ -510,6 +513,8 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     e->launches++;
     return C2B_OK;
 }
+
+int64_t c2b_band_reruns(c2b_engine *e) { return e ? e->band_reruns : 0; }
 
 int c2b_set_pair_order(c2b_engine *e, const int32_t *d_order)
 {
@@ -545,8 +550,9 @@ int64_t c2b_launch_count(const c2b_engine *e) { return e ? e->launches : 0; }
 int c2b_path_counts(c2b_engine *e, int64_t *pair_items, int64_t *single_items)
 {
     if (!e || !e->work.p) return fail(e, C2B_E_STATE, "c2b_path_counts: nothing launched yet");
-    int64_t v[4] = {0, 0, 0, 0};
-    RTCHK(rt_d2h(v, e->work.p, 32, e->stream));
+    int64_t v[5] = {0, 0, 0, 0, 0};
+    RTCHK(rt_d2h(v, e->work.p, 40, e->stream));
+    e->band_reruns = v[4];
     RTCHK(rt_sync(e->stream));
     if (pair_items) *pair_items = v[2];
     if (single_items) *single_items = v[3];

@@ -221,5 +221,9 @@ class Engine:
         self._check(self.L.c2b_path_counts(self.h, C.byref(a), C.byref(b)), "c2b_path_counts")
         return a.value, b.value
 
+    def band_reruns(self):
+        """pairs re-run with the full traceback slab since the last counts_reset (call path_counts() first)"""
+        return int(self.L.c2b_band_reruns(self.h))
+
     def launch_count(self):
         return int(self.L.c2b_launch_count(self.h))

@@ -197,6 +197,8 @@ int64_t c2b_launch_count(const c2b_engine *e);      /* kernels launched by this 
 /* work items (pairs of reads) since the last c2b_counts_reset that took the packed two-reads-per-warp path /
  * the 32-bit one-read-per-warp path */
 int  c2b_path_counts(c2b_engine *e, int64_t *pair_items, int64_t *single_items);
+/* packed pairs whose traceback left the banded slab and were re-run with the full slab (as of the last c2b_path_counts) */
+int64_t c2b_band_reruns(c2b_engine *e);
 
 /* replaces: the count vectors / counters built by the quantification loop (CRISPRessoCORE.py:3841-3907,
  * :3964-4115).  Layout above.  c2b_counts_device exposes the block for an NCCL all-reduce.            */

@@ -172,3 +172,25 @@ def check_pooled(engine, n_amplicons=6, reads_per=40, seed=21, amp_len=(120, 200
         for name in ("all_deletion_count", "all_substitution_count", "all_insertion_count", "deletion_count", "insertion_count"):
             assert (V[name] == vec[nm][name]).all(), (nm, name)
         assert blk.scalar(nm, "TOTAL") == sca[nm]["counts_total"]
+
+
+def check_band_fallback(engine, n=24, seed=31):
+    """Packed path with the banded traceback slab: alignments that wander off the diagonal (40-60 bp deletions, random
+    reads) must trigger the full-slab re-run and still equal the oracle."""
+    from crispresso2_b200 import synth
+    rng = np.random.default_rng(seed)
+    amp = synth.random_amplicon(rng, 250)
+    ref = synth.amplicon_setup(amp)
+    reads = []
+    for k in range(n):
+        if k % 3 == 0:
+            d = int(rng.integers(40, 61)); a = int(rng.integers(60, 150))
+            s = amp[:a] + amp[a + d:] + "".join(rng.choice(list("ACGT"), d))
+        elif k % 3 == 1:
+            s = "".join(rng.choice(list("ACGT"), 250))
+        else:
+            s = amp
+        reads.append(s[:250])
+    check_against_oracle(engine, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
+    pairs, singles = engine.path_counts()
+    assert pairs > 0 and engine.band_reruns() > 0

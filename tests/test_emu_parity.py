@@ -160,3 +160,7 @@ def test_long_amplicon_three_row_blocks(emu):
         reads.append(s[s0:s0 + L])
     reads.append(amp[100:500])
     PU.check_against_oracle(emu, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
+
+
+def test_banded_slab_falls_back_to_full_slab(emu):
+    PU.check_band_fallback(emu, n=24)

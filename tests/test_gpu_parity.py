@@ -213,3 +213,7 @@ def test_long_amplicon_three_row_blocks(eng):
         reads.append(s[s0:s0 + L])
     reads.append(amp[100:500])
     PU.check_against_oracle(eng, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
+
+
+def test_banded_slab_falls_back_to_full_slab(eng):
+    PU.check_band_fallback(eng, n=3000)
