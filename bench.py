@@ -337,7 +337,7 @@ def main():
                        "reads_per_gpu_per_step": n, "amplicon_len": AMP_LEN, "read_len": READ_LEN, "parallelism": "read-shard x%d" % world,
                        "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2" % ((h2d + d2h) / 1e9),
                        "edit_cap": args.edit_cap, "aligned_fraction": aligned_frac,
-                       "packed_pair_items": pair_items, "single_items": single_items, "band_reruns": eng.band_reruns(), "parity_gate": bool(gate_ok and e2e_gate)},
+                       "packed_pair_items": pair_items, "single_items": single_items, "band_reruns": eng.band_reruns(), "ring_pairs": eng.ring_counts()[0], "ring_fallbacks": eng.ring_counts()[1], "parity_gate": bool(gate_ok and e2e_gate)},
             "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(launches),

@@ -25,6 +25,7 @@ F_DISCARD_INDEL_READS = 32
 F_NO_STRAND_SEARCH = 64
 F_NO_PAIRING = 128
 F_HDR_REF1 = 256
+F_NO_RING = 512
 
 ST_BAD_CHAR = 1
 ST_UNDEFINED = 2
@@ -71,7 +72,7 @@ EDIT_DTYPE = np.dtype([("a", "<u2"), ("b", "<u2"), ("type", "u1"), ("in_window",
 assert ALN_DTYPE.itemsize == 32 and REC_DTYPE.itemsize == 16 and EDIT_DTYPE.itemsize == 8
 
 EXPORTS = ["c2b_create", "c2b_destroy", "c2b_last_error", "c2b_configure", "c2b_set_edit_cap", "c2b_string_width", "c2b_align_batch",
-           "c2b_align_batch_device", "c2b_set_pair_order", "c2b_sync", "c2b_stream", "c2b_last_kernel_ms", "c2b_launch_count", "c2b_path_counts", "c2b_band_reruns",
+           "c2b_align_batch_device", "c2b_set_pair_order", "c2b_sync", "c2b_stream", "c2b_last_kernel_ms", "c2b_launch_count", "c2b_path_counts", "c2b_band_reruns", "c2b_ring_counts",
            "c2b_counts_layout", "c2b_counts_reset", "c2b_counts_read", "c2b_counts_device", "c2b_global_align",
            "c2b_classify_aligned", "c2b_host_alloc", "c2b_host_free"]
 
@@ -123,6 +124,8 @@ def load(path=None):
     L.c2b_path_counts.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.c2b_band_reruns.restype = i64
     L.c2b_band_reruns.argtypes = [vp]
+    L.c2b_ring_counts.restype = C.c_int
+    L.c2b_ring_counts.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.c2b_counts_layout.restype = C.c_int
     L.c2b_counts_layout.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.c2b_counts_reset.restype = C.c_int

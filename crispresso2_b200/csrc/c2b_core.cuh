@@ -38,6 +38,7 @@ C2B_DEV uint32_t shflu_up(uint32_t v, int d) { return __shfl_up_sync(0xffffffffu
 C2B_DEV int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 C2B_DEV uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 C2B_DEV void sync() { __syncwarp(); }
+C2B_DEV void cta_sync() { __syncthreads(); }
 C2B_DEV int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 C2B_DEV int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }   // max(a+b, c)
 C2B_DEV uint32_t max3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }      // per signed half
@@ -101,6 +102,8 @@ struct RefDev {
                                    // rows 8l..8l+3, of half 1 rows 8l+4..8l+7; halves of a word: 4*(score+2*beta) of read A / B
     const uint32_t *cIe2;          // [Ipad]         4*gi[row+1] in both halves
     const uint32_t *g42;           // [Ipad]         4*gi[row]   in both halves
+    // ring-banded path (four pairs per warp): score bound of any alignment that leaves the band, see ring_bound()
+    int32_t rg_ok, rg_smax, rg_gmax, rg_gsum;
 };
 
 struct KParams {
@@ -114,6 +117,7 @@ struct KParams {
     uint8_t alpha[C2B_MAX_Q]; uint8_t comp[C2B_MAX_Q];
     uint32_t *tb; int64_t tb_words_per_warp; int32_t TS;      // TS = steps stride per row block (maxJ + 32)
     uint32_t *tbb; int64_t tbb_words_per_warp;                // banded slab of the packed path (PK_BAND_SLOTS slots per lane)
+    uint32_t *tbq;                                            // slab of the ring-banded path: [step][lane] uint2, TS steps per warp
     int32_t *bnd; int64_t bnd_words_per_warp;                 // 2 x 3 x (maxJ+1): row-block boundary rows
     uint64_t *opsbuf;                                         // [warp][n_refs][32] op streams (multi-reference)
     unsigned long long *work_counter;
@@ -121,6 +125,7 @@ struct KParams {
     const uint32_t *stage_src;        // = refs[0].prof2 (global source of the staged tile)
     int32_t stage_bytes;              // bytes of refs[0].prof2 staged into shared memory by TMA at kernel start (0: none)
     const uint8_t *lut;               // [256] ASCII -> alphabet code, 255 = not in the alphabet (device memory, L1-resident)
+    int32_t phase_sync;               // 1: the warps of a CTA walk through the per-group phases in step (instruction-cache locality)
     const uint64_t *forced_ops;       // c2b_classify_aligned: op streams supplied by the caller, [read][32]
     const int32_t *forced_n;
 };
@@ -133,12 +138,19 @@ struct WarpSmem {
     uint32_t rowins[MAXI + 4]; // rowins[r]: bases inserted between reference positions r-1 and r (pair: halves of 514)
 };
 constexpr int PK_ROWINFO_STRIDE = 512, PK_ROWINS_STRIDE = 514, PK_MAX_ALN = 512;
+// Ring-banded path: four pairs per warp, eight lanes each.  A group's lane r (0..7) plays the virtual lanes r, r+8, r+16, ...
+// (virtual lane L = rows 8L+1..8L+8) one after the other, each for the RG_NS wavefront steps around its diagonal
+// (step t -> slot t - 9L + RG_B); cells with column - row in [-(RG_B+1), RG_NS-RG_B-9] are always inside the band.
+constexpr int RG_NS = 72, RG_B = 32, RG_MAXD = 8, RG_COMBO = 272;
+constexpr int RG_DLO = RG_B + 1, RG_DHI = RG_NS - RG_B - 9;
+struct QuadSmem { uint8_t combo[4][RG_COMBO]; };
 // Banded traceback slab of the packed path.  Lane l (rows 8l+1..8l+8) keeps only the PK_BAND_SLOTS wavefront steps around
 // its own diagonal (step t -> slot t - 9l + PK_BAND_B): cells whose column is within about -29..+27 of their row.  The DP
 // itself is unchanged (every cell is computed); if the traceback ever needs a cell outside the band, the pair is simply
 // re-run with the full slab.  The banded slabs of the whole grid (16 KB per warp, 39 MB) stay resident in L2.
 constexpr int PK_BAND_SLOTS = 64, PK_BAND_B = 28, PK_BAND_MAXD = 8;
-struct SlabMode { int slope, off, ns; };          // slot = t - slope*lane + off, kept iff 0 <= slot < ns
+// slot = t - slope*lane + off, kept iff 0 <= slot < ns.  Entry index: (slot, lane); ring slabs: (t, gb + (lane & 7)).
+struct SlabMode { int slope, off, ns, ring, gb; };
 
 struct Walked { uint64_t ops; int n; int err; };
 
@@ -282,7 +294,7 @@ C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const 
             const int slot = cj + l - sm.slope * l + sm.off;
             inband = (unsigned)slot < (unsigned)sm.ns;
             if (inband) {
-                const int64_t idx = ((int64_t)rb * TS + slot) * 32 + l;
+                const int64_t idx = sm.ring ? (int64_t)(cj + l) * 32 + sm.gb + (l & 7) : ((int64_t)rb * TS + slot) * 32 + l;
                 if (PAIR) {
                     const uint2 w2 = wp::ldcg2(tb2 + idx);
                     const uint32_t w = hb ? ((w2.x & 0xffff0000u) | (w2.y >> 16)) : ((w2.x << 16) | (w2.y & 0xffffu));
@@ -345,7 +357,7 @@ C2B_DEV Walked align_strand(const KParams &P, const RefDev &R, const uint8_t *co
         wp::sync();
     }
     const int s = wp::max3(cM, cY, cX) & 3;                     // start state, Align.pyx:349-358
-    const SlabMode full = {0, 0, P.TS};
+    const SlabMode full = {0, 0, P.TS, 0, 0};
     return walk_batch<false>(P, R, J, tb, s, full);
 }
 
@@ -956,7 +968,7 @@ C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint32_t *pro
     const int d = J - R.I;
     bool band = tb_band != nullptr && nrb == 1 && d >= -PK_BAND_MAXD && d <= PK_BAND_MAXD;
     for (;;) {
-        const SlabMode sm = band ? SlabMode{9, PK_BAND_B, PK_BAND_SLOTS} : SlabMode{0, 0, P.TS};
+        const SlabMode sm = band ? SlabMode{9, PK_BAND_B, PK_BAND_SLOTS, 0, 0} : SlabMode{0, 0, P.TS, 0, 0};
         uint2 *tb2 = band ? tb_band : tb_full;
         uint32_t cM = 0, cX = 0, cY = 0;
         for (int rb = 0; rb < nrb; rb++) {
@@ -973,9 +985,129 @@ C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint32_t *pro
     }
 }
 
-// Two reads (rdA, rdB) of equal length J through the packed path.  Per-lane variables belong to the lane's half.
-C2B_DEV void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_prof, int64_t rdA, int64_t rdB, int warp_slot)
+
+// ------------------------------------------------------------------------------------ ring-banded path (four pairs per warp)
+// Same packed arithmetic as dp_block2, but only the cells of a diagonal band are computed.  The warp is split into four
+// rings of eight lanes, one pair of reads each.  Ring lane r plays virtual lanes r, r+8, r+16, ... (virtual lane L owns
+// rows 8L+1..8L+8 and, at step t, column t-L) for RG_NS consecutive steps each; lane edges travel around the ring by
+// shuffle, so the lower row block starts while the upper one is still running and no lane idles.  Cells outside the
+// band read as the sentinel (never above the true value), hence every banded value is <= the full-matrix value and equal
+// to it along any path that stays inside the band: if the banded score beats ring_bound() -- an upper bound on the score
+// of every alignment that leaves the band -- the full-matrix traceback lies inside the band and the banded traceback
+// reproduces it cell for cell (ties included).  Otherwise the pair takes align_pair() over the full matrix.
+// Slab: entry (t, physical lane), one coalesced 256-byte row per step.
+template <bool STAGED>
+C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *prof, const uint8_t *combo, const int J, const int nsteps,
+                          uint2 *__restrict__ tbq, uint32_t *fin)
 {
+    const int lane = wp::lane(), r8 = lane & 7;
+    const int src = (lane & 24) | ((lane + 7) & 7);                      // ring predecessor
+    const int lstar = R.lstar;
+    const uint32_t combo_sa = wp::smem_addr(combo) - 1u;                 // combo[j-1] = [combo_sa + j]
+    const uint32_t qstride = (uint32_t)R.Ipad * 4u;
+
+    uint32_t M[8], X[8], Y[8], cIe[8], g40, dI[8];                       // g4[k] = 4*gi[row] = cIe[k-1]; g40: the row above the lane's first
+    int L = r8, slot = 1 - 9 * r8 + RG_B;                                // slot of step t = 1
+    uint32_t prof_sa = 0; const uint32_t *prof0 = prof;
+    auto enter = [&](int Lv) {                                           // constants and left-of-band state of virtual lane Lv
+        const int row0 = 8 * (Lv <= lstar ? Lv : lstar);                 // past the last row block: inert, any valid rows
+        const uint4 *pc = reinterpret_cast<const uint4 *>(R.cIe2 + row0);
+        const uint4 a = wp::ldg4u(pc), b = wp::ldg4u(pc + 1);
+        cIe[0] = a.x; cIe[1] = a.y; cIe[2] = a.z; cIe[3] = a.w; cIe[4] = b.x; cIe[5] = b.y; cIe[6] = b.z; cIe[7] = b.w;
+        g40 = R.g42[row0];
+        const uint32_t y0 = (8 * Lv - RG_B <= 0) ? R.pk_YB : (PK_SENT | PK_T1);   // window starts at column 0: the border column
+        const uint32_t d4p = (uint32_t)((4 * (P.go - P.ge)) & 0xffff) * 0x00010001u;
+        const int klast = R.I - 8 * Lv - 1;                              // row I is this lane's row klast (if 0 <= klast < 8)
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            M[k] = PK_SENT; X[k] = PK_SENT | PK_T2; Y[k] = y0;
+            dI[k] = (k == klast) ? 0u : d4p;                             // free opening in the last row
+        }
+        if (STAGED) prof_sa = wp::smem_addr(prof) + (uint32_t)Lv * 16u; else prof0 = prof + Lv * 4;
+    };
+    enter(L);
+    uint32_t pM = R.pk_M00, pX = PK_SENT | PK_T2, pY = PK_SENT | PK_T1;  // diagonal of (1,1); other lanes: carried below
+    uint2 *__restrict__ tbp = tbq + 32 + lane;                           // entry of step t = 1
+
+    for (int t = 1; t <= nsteps; t++) {
+        uint32_t uM = wp::shflu(M[7], src), uX = wp::shflu(X[7], src), uY = wp::shflu(Y[7], src);
+        if (L == 0) { uM = PK_SENT; uX = R.pk_XB; uY = PK_SENT | PK_T1; }     // row 0
+        const int j = t - L;
+        if (slot >= 0 && L <= lstar && j >= 1 && j <= J) {
+            uint32_t s[8];
+            if (STAGED) {
+                const uint32_t a = prof_sa + wp::lds_u8(combo_sa + (uint32_t)j) * qstride;
+                const uint4 sa = wp::lds_v4(a), sb = wp::lds_v4(a + 512u);
+                s[0] = sa.x; s[1] = sa.y; s[2] = sa.z; s[3] = sa.w; s[4] = sb.x; s[5] = sb.y; s[6] = sb.z; s[7] = sb.w;
+            } else {
+                const uint4 *pp = reinterpret_cast<const uint4 *>(prof0 + combo[j - 1] * R.Ipad);
+                const uint4 sa = wp::ldg4u(pp), sb = wp::ldg4u(pp + 32);
+                s[0] = sa.x; s[1] = sa.y; s[2] = sa.z; s[3] = sa.w; s[4] = sb.x; s[5] = sb.y; s[6] = sb.z; s[7] = sb.w;
+            }
+            const uint32_t cm = (j == J) ? 0u : 0xffffffffu;             // free opening in the last column
+            // the row above leaves the band RG_NS-8 slots into the window (its diagonal neighbour one slot later)
+            const bool lateU = slot >= RG_NS - 8, lateP = slot > RG_NS - 8;
+            uint32_t dM = lateP ? PK_SENT : pM, dX = lateP ? (PK_SENT | PK_T2) : pX, dY = lateP ? (PK_SENT | PK_T1) : pY;
+            uint32_t upM = lateU ? PK_SENT : uM, upY = lateU ? (PK_SENT | PK_T1) : uY, wT = 0, wIJ = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t dik = dI[k] & cm;
+                const uint32_t z = wp::max3_2(dM, dY, dX);
+                const uint32_t t2 = z & PK_TM;
+                const uint32_t nm = z - t2 + s[k];
+                const uint32_t x = wp::addmax_2(M[k], dik, X[k]) + cIe[k];
+                const uint32_t y = wp::addmax_2(upM + (k ? cIe[k ? k - 1 : 0] : g40), dik, upY);
+                wT = wT * 4u + t2;
+                wIJ = wIJ * 4u + ((x | y) & PK_TM);
+                dM = M[k]; dX = X[k]; dY = Y[k];
+                M[k] = nm; X[k] = x | PK_T2; Y[k] = y | PK_T1;
+                upM = nm; upY = Y[k];
+            }
+            *tbp = make_uint2(wT, wIJ);
+            if (j == J && L == lstar) {                                  // cell (I, J): the three final values
+                const int kstar = R.kstar;
+#pragma unroll
+                for (int k = 0; k < 8; k++) if (k == kstar) { fin[3 * lane] = M[k]; fin[3 * lane + 1] = X[k]; fin[3 * lane + 2] = Y[k]; }
+            }
+        }
+        tbp += 32;
+        pM = uM; pX = uX; pY = uY;                                       // raw: a lane entering its next window needs the uncapped edge
+        if (++slot == RG_NS) { L += 8; slot = 0; enter(L); }
+    }
+}
+
+// Upper bound on the score of any alignment of a J-long read that visits a cell with column - row outside
+// [-RG_DLO, RG_DHI].  Such a path holds at least nh >= RG_DHI+1 read-only columns (and nv = nh - (J-I) reference-only
+// ones) or nv >= RG_DLO+1 reference-only columns (and nh = nv + (J-I)); a gap column scores at most gap_extend (+ the
+// largest incentive for read-only columns; reference-only runs collect each row's incentive at most once, gsum in
+// total), a diagonal column at most smax.  The host proves the bound decreasing in the free count (RefDev::rg_ok).
+C2B_DEV int ring_bound(const KParams &P, const RefDev &R, int J)
+{
+    const int I = R.I, D = J - I, ge = P.ge, smax = R.rg_smax, gmax = R.rg_gmax;
+    int U = -(1 << 28);
+    {
+        int nh = RG_DHI + 1; if (nh < D) nh = D;
+        const int nv = nh - D;
+        if (nh <= J && nv <= I) { const int u = smax * (J - nh) + nh * (ge + gmax) + nv * ge + R.rg_gsum; if (u > U) U = u; }
+    }
+    {
+        int nv = RG_DLO + 1; if (nv < -D) nv = -D;
+        const int nh = nv + D;
+        if (nv <= I && nh <= J && nh >= 0) { const int u = smax * (I - nv) + nh * (ge + gmax) + nv * ge + R.rg_gsum; if (u > U) U = u; }
+    }
+    return U;
+}
+
+struct RingCtx { const uint2 *tbq; int gb; int modes; int s2; };   // a pair whose DP was done by dp_ring: slab, ring base lane, strand modes, start states
+constexpr int PAIR_PHASES = 5, GROUP_PHASES = 2 + 4 * PAIR_PHASES;      // CTA barriers per process_pair(phased) / per work group
+
+// Two reads (rdA, rdB) of equal length J through the packed path.  Per-lane variables belong to the lane's half.
+C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_prof, int64_t rdA, int64_t rdB, int warp_slot,
+                          const RingCtx *ring, const bool phased)
+{
+    // phased: called once per pair of a work group by every warp of the CTA -- PAIR_PHASES CTA barriers keep the warps in the
+    // same stretch of code (the per-read path is larger than the instruction cache)
+    if (phased) wp::cta_sync();
     const int lane = wp::lane(), h = lane >> 4, hl = lane & 15;
     const int64_t myrd = h ? rdB : rdA;
     const int J = (int)(P.offsets[rdA + 1] - P.offsets[rdA]);
@@ -1005,8 +1137,11 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_
         const RefDev &R = P.refs[r];
         init_aln(a, st);
         int mAB = 0;
+        if (ring) mAB = ring->modes;
+        else {
 #pragma unroll 1
-        for (int x = 0; x < 2; x++) mAB |= strand_mode(P, R, S.fw[x], J) << (2 * x);
+            for (int x = 0; x < 2; x++) mAB |= strand_mode(P, R, S.fw[x], J) << (2 * x);
+        }
         const int mA = mAB & 3, mB = mAB >> 2;
         const int mode = h ? mB : mA;
         const int npass = (mA == 2 || mB == 2) ? 2 : 1;
@@ -1016,10 +1151,19 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_
             const int sA = (mA == 2) ? pass : (mA == 1), sB = (mB == 2) ? pass : (mB == 1);
             const uint8_t *cA = sA ? S.rc[0] : S.fw[0], *cB = sB ? S.rc[1] : S.fw[1];
             wp::sync();
-            for (int p = lane; p < J; p += 32) S.combo[p] = (uint8_t)(cA[p] * P.nq + cB[p]);
-            wp::sync();
-            const bool staged = (r == 0 && staged_prof != nullptr);
-            const Walked wk = align_pair(P, R, staged ? staged_prof : R.prof2, staged, S.combo, J, tb2, tbb, bnd);
+            if (phased && pass == 0) wp::cta_sync();
+            Walked wk; wk.err = 4;
+            if (ring) {                                     // DP already done by dp_ring: walk its slab
+                const int s0 = (lane & 16) ? (ring->s2 >> 16) : (ring->s2 & 3);
+                wk = walk_batch<true>(P, R, J, reinterpret_cast<const uint32_t *>(ring->tbq), s0, SlabMode{9, RG_B, RG_NS, 1, ring->gb});
+                if (wp::ballot((wk.err & 4) != 0)) { wk.err = 4; if (lane == 0) wp::addg(P.work_counter + 6, 1); }
+            }
+            if (wk.err & 4) {
+                for (int p = lane; p < J; p += 32) S.combo[p] = (uint8_t)(cA[p] * P.nq + cB[p]);
+                wp::sync();
+                const bool staged = (r == 0 && staged_prof != nullptr);
+                wk = align_pair(P, R, staged ? staged_prof : R.prof2, staged, S.combo, J, tb2, tbb, bnd);
+            }
             const int mystrand = h ? sB : sA;
             if (wk.err) a.status |= C2B_ST_UNDEFINED;
             int sc = -1000000;
@@ -1032,6 +1176,7 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_
         }
         for (int p = lane; p < 2 * PK_ROWINS_STRIDE; p += 32) S.rowins[p] = 0;
         wp::sync();
+        if (phased) wp::cta_sync();
         uint8_t *o_read = P.strings ? P.strings + ((myrd * P.n_refs + r) * 2) * (int64_t)P.W : nullptr;
         uint8_t *o_ref = o_read ? o_read + P.W : nullptr;
         int cmode = (o_read ? 1 : 0) | (multi ? 0 : 2);
@@ -1052,6 +1197,7 @@ C2B_DEV void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_
     wp::sync();
     // classification runs with the whole warp, one read at a time: broadcast that half's bookkeeping to every lane
     for (int hh = 0; hh < 2; hh++) {
+        if (phased) wp::cta_sync();
         if (hh == 1 && rdB == rdA) break;
         const int src = 16 * hh;
         c2b_read_rec rr;
@@ -1090,10 +1236,111 @@ C2B_DEV void process_item(const KParams &P, WarpSmem &S, const uint32_t *staged_
         }
     }
     if (wp::lane() == 0) wp::addg(P.work_counter + (pair ? 2 : 3), 1);      // path statistics (c2b_path_counts)
-    if (pair) process_pair(P, S, staged_prof, rdA, rdB, warp_slot);
+    if (pair) process_pair(P, S, staged_prof, rdA, rdB, warp_slot, nullptr, false);
     else {
         process_read(P, S, rdA, warp_slot);
         if (haveB) { wp::sync(); process_read(P, S, rdB, warp_slot); }
+    }
+}
+
+
+// Four equal-length pairs against one reference: strands and base-pair codes per pair, one ring-banded DP for all
+// four, then every pair continues through process_pair (walk + classification) -- with the ring's slab if its score
+// proves the band sufficient, over the full matrix otherwise.
+C2B_DEV void process_quad(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint32_t *staged_prof, int64_t first, int warp_slot)
+{
+    const int lane = wp::lane(), g = lane >> 3;
+    uint2 *tbq = reinterpret_cast<uint2 *>(P.tbq + (int64_t)warp_slot * P.TS * 64);
+    if (P.phase_sync) wp::cta_sync();
+    uint32_t okmask = 0, modes = 0;
+    int Jg = 0, Jmax = 0;
+    const int64_t rd0 = P.pair_order ? P.pair_order[2 * first] : 2 * first;
+    const int r = P.ref_id ? P.ref_id[rd0] : 0;
+    const RefDev &R = P.refs[r];
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        const int64_t rdA = P.pair_order ? P.pair_order[2 * (first + q)] : 2 * (first + q);
+        const int64_t rdB = P.pair_order ? P.pair_order[2 * (first + q) + 1] : 2 * (first + q) + 1;
+        const int J = (int)(P.offsets[rdA + 1] - P.offsets[rdA]);
+        bool bad = false;
+#pragma unroll 1
+        for (int x = 0; x < 2; x++) bad |= load_codes(P, P.offsets[x ? rdB : rdA], J, S.fw[x], S.rc[x]);
+        wp::sync();
+        int mAB = 0;
+#pragma unroll 1
+        for (int x = 0; x < 2; x++) mAB |= strand_mode(P, R, S.fw[x], J) << (2 * x);
+        const int mA = mAB & 3, mB = mAB >> 2;
+        if (!bad && mA != 2 && mB != 2) {                   // a read that needs both strands takes the full path
+            const uint8_t *cA = mA ? S.rc[0] : S.fw[0], *cB = mB ? S.rc[1] : S.fw[1];
+            for (int p = lane; p < J; p += 32) Q.combo[q][p] = (uint8_t)(cA[p] * P.nq + cB[p]);
+            okmask |= 1u << q; modes |= (uint32_t)mAB << (4 * q);
+            if (g == q) Jg = J;
+            if (J > Jmax) Jmax = J;
+        }
+        wp::sync();
+    }
+    uint32_t passmask = 0, s2 = 0;
+    if (P.phase_sync) wp::cta_sync();
+    if (okmask) {
+        const bool staged = (r == 0 && staged_prof != nullptr);
+        uint32_t *fin = S.rowins;                            // 32 x 3 words: each ring's final lane leaves M, X, Y of cell (I, J)
+        if (staged) dp_ring<true>(P, R, staged_prof, Q.combo[g], Jg, Jmax + R.lstar, tbq, fin);
+        else dp_ring<false>(P, R, R.prof2, Q.combo[g], Jg, Jmax + R.lstar, tbq, fin);
+        wp::sync();
+        const int fl = 3 * ((lane & 24) | (R.lstar & 7));
+        const uint32_t cM = Jg > 0 ? fin[fl] : PK_SENT, cX = Jg > 0 ? fin[fl + 1] : PK_SENT, cY = Jg > 0 ? fin[fl + 2] : PK_SENT;
+        wp::sync();
+        const uint32_t z = wp::max3_2(cM, cY, cX);
+        s2 = z & PK_TM;
+        // biased value = 4*(score + beta*(I+J) + 512) + tag: both reads must beat the out-of-band bound
+        const int thr = ring_bound(P, R, Jg) + 512 - P.ge * (R.I + Jg);
+        const bool pass = Jg > 0 && (int)((z & 0xffffu) >> 2) > thr && (int)(z >> 18) > thr;
+        const uint32_t b = wp::ballot(pass);
+        passmask = (b & 1u) | ((b >> 7) & 2u) | ((b >> 14) & 4u) | ((b >> 21) & 8u);
+    }
+    if (lane == 0) {
+        wp::addg(P.work_counter + 2, 4);
+        wp::addg(P.work_counter + 5, wp::popc(passmask));
+        wp::addg(P.work_counter + 6, 4 - wp::popc(passmask));
+    }
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        const int64_t rdA = P.pair_order ? P.pair_order[2 * (first + q)] : 2 * (first + q);
+        const int64_t rdB = P.pair_order ? P.pair_order[2 * (first + q) + 1] : 2 * (first + q) + 1;
+        RingCtx rc; rc.tbq = tbq; rc.gb = 8 * q; rc.modes = (int)((modes >> (4 * q)) & 15u); rc.s2 = (int)wp::shflu(s2, 8 * q);
+        process_pair(P, S, staged_prof, rdA, rdB, warp_slot, ((passmask >> q) & 1u) ? &rc : nullptr, P.phase_sync != 0);
+        wp::sync();
+    }
+}
+
+// Work group wq = work items 4wq..4wq+3 (reads 8wq..8wq+7): four pairs through the ring-banded path when all of them
+// qualify, otherwise item by item.
+C2B_DEV void process_group(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint32_t *staged_prof, int64_t wq, int warp_slot)
+{
+    const int lane = wp::lane();
+    const int64_t first = 4 * wq;
+    bool quad = !P.forced_ops && !(P.flags & (C2B_F_NO_PAIRING | C2B_F_NO_RING)) && P.tbq != nullptr &&
+                2 * first + 7 < P.n_reads && (P.ref_id != nullptr || P.n_refs == 1);
+    if (quad) {
+        const int x = lane & 7;
+        const int64_t rd = P.pair_order ? P.pair_order[2 * first + x] : 2 * first + x;
+        const int Jx = (int)(P.offsets[rd + 1] - P.offsets[rd]);
+        const int rx = P.ref_id ? P.ref_id[rd] : 0;
+        const int r0 = wp::shfl(rx, 0);
+        const RefDev &R = P.refs[r0];
+        const bool ok = rx == r0 && Jx == wp::shfl_xor(Jx, 1) && R.rg_ok && Jx >= 1 && Jx <= R.pk_maxJ && Jx <= RG_COMBO &&
+                        Jx - R.I <= RG_MAXD && R.I - Jx <= RG_MAXD && Jx + 32 <= P.TS;
+        quad = wp::ballot(ok) == 0xffffffffu;
+    }
+    if (quad) process_quad(P, S, Q, staged_prof, first, warp_slot);
+    else {
+#pragma unroll 1
+        for (int q = 0; q < 4; q++)
+            if (2 * (first + q) < P.n_reads) { process_item(P, S, staged_prof, first + q, warp_slot); wp::sync(); }
+        if (P.phase_sync) {                                 // keep the CTA's barrier count per group the same on every path
+#pragma unroll 1
+            for (int b = 0; b < GROUP_PHASES; b++) wp::cta_sync();
+        }
     }
 }
 

@@ -81,13 +81,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_a
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpSmem *S = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
+    QuadSmem *Q = reinterpret_cast<QuadSmem *>(smem_raw + (size_t)(blockDim.x >> 5) * sizeof(WarpSmem)) + (threadIdx.x >> 5);
     const int warp_slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     // Reference tile: the packed substitution profile of reference 0 is staged once per CTA into shared memory by the
     // TMA engine (cp.async.bulk, completion on an mbarrier); every DP step then reads it with two 16-byte LDS.
     const uint32_t *staged_prof = nullptr;
     if (P.stage_bytes > 0) {
         __shared__ __align__(8) unsigned long long mbar;
-        unsigned char *dst = smem_raw + (size_t)(blockDim.x >> 5) * sizeof(WarpSmem);
+        unsigned char *dst = smem_raw + (((size_t)(blockDim.x >> 5) * (sizeof(WarpSmem) + sizeof(QuadSmem)) + 127) & ~(size_t)127);
         const uint32_t mbar_a = (uint32_t)__cvta_generic_to_shared(&mbar), dst_a = (uint32_t)__cvta_generic_to_shared(dst);
         if (threadIdx.x == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
@@ -102,23 +103,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_a
         asm volatile("{\n .reg .pred p;\n C2B_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra C2B_DONE;\n bra C2B_WAIT;\n C2B_DONE:\n}" ::"r"(mbar_a) : "memory");
         staged_prof = reinterpret_cast<const uint32_t *>(dst);
     }
-    // work items are fetched one ahead, and the next pair's read bytes are pulled into L2 while this pair computes
-    unsigned long long w = 0;
-    if ((threadIdx.x & 31) == 0) w = wp::fetch_work(P.work_counter);
-    w = __shfl_sync(0xffffffffu, w, 0);
-    while (2 * w < (unsigned long long)P.n_reads) {
-        unsigned long long wn = 0;
-        if ((threadIdx.x & 31) == 0) wn = wp::fetch_work(P.work_counter);
-        wn = __shfl_sync(0xffffffffu, wn, 0);
-        if (2 * wn < (unsigned long long)P.n_reads) {
-            const int64_t last = (int64_t)(2 * wn + 2) < P.n_reads ? (int64_t)(2 * wn + 2) : P.n_reads;
-            const int64_t b0 = P.offsets[2 * wn], b1 = P.offsets[last];
-            const int64_t a = b0 + (int64_t)(threadIdx.x & 31) * 128;
-            if (a < b1) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.reads + a));
-        }
-        process_item(P, *S, staged_prof, (int64_t)w, warp_slot);       // reads 2w, 2w+1
+    // Work groups (8 reads each) are handed out per CTA, one per warp, so that the loop count -- and with it the number
+    // of CTA barriers executed by process_group's phases -- is the same for every warp of the CTA.
+    __shared__ unsigned long long next_base;
+    const unsigned long long wpc = blockDim.x >> 5, total = ((unsigned long long)P.n_reads + 7) / 8;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) next_base = atomicAdd(P.work_counter, wpc);
+        __syncthreads();
+        const unsigned long long base = next_base;
+        if (base >= total) break;
+        const unsigned long long w = base + (threadIdx.x >> 5);
+        if (w < total) process_group(P, *S, *Q, staged_prof, (int64_t)w, warp_slot);  // reads 8w .. 8w+7
+        else if (P.phase_sync) for (int b = 0; b < GROUP_PHASES; b++) __syncthreads();
         __syncwarp();
-        w = wn;
     }
 }
 #endif
@@ -145,7 +143,7 @@ struct c2b_engine {
     void *d_tables = nullptr; RefDev *d_refs = nullptr;
     unsigned long long *d_counts = nullptr; size_t counts_n = 0;
     // scratch
-    DevBuf tb, tbb, bnd, ops, work, lut;
+    DevBuf tb, tbb, tbq, bnd, ops, work, lut;
     int n_warps = 0, grid = 0, wpc = 8, stage_cap = 0;
     int scratch_TS = 0;
     // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
@@ -156,7 +154,7 @@ struct c2b_engine {
     double last_ms = 0; int64_t launches = 0;
     const uint64_t *forced_ops = nullptr; const int32_t *forced_n = nullptr;
     const int32_t *pair_order = nullptr;
-    int64_t band_reruns = 0;
+    int64_t band_reruns = 0, ring_pairs = 0, ring_fallbacks = 0;
 #ifndef C2B_EMU
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 #endif
@@ -195,13 +193,13 @@ int c2b_create(int device, c2b_engine **out)
     if (r == cudaSuccess) r = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
     if (r == cudaSuccess) r = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     // room for a TMA-staged reference tile next to C2B_MIN_CTAS_PER_SM CTAs of per-warp state (1 KB per CTA is reserved by the driver)
-    e->stage_cap = smem_sm / C2B_MIN_CTAS_PER_SM - 1024 - (int)(sizeof(WarpSmem) * WARPS_PER_CTA) - 256;
+    e->stage_cap = smem_sm / C2B_MIN_CTAS_PER_SM - 1024 - (int)((sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA) - 256;
     if (e->stage_cap < 0) e->stage_cap = 0;
     e->stage_cap &= ~127;
     if (r == cudaSuccess) r = cudaFuncSetAttribute(c2b_align_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)(sizeof(WarpSmem) * WARPS_PER_CTA) + e->stage_cap);
+                                                   (int)((sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA) + 128 + e->stage_cap);
     if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c2b_align_classify_kernel, WARPS_PER_CTA * 32,
-                                                                            sizeof(WarpSmem) * WARPS_PER_CTA + e->stage_cap);
+                                                                            (sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA + 128 + e->stage_cap);
     if (r != cudaSuccess) { g_create_err = std::string("c2b_create: ") + cudaGetErrorString(r); delete e; return C2B_E_CUDA; }
     if (occ < 1) occ = 1;
     e->wpc = WARPS_PER_CTA;
@@ -219,7 +217,7 @@ int c2b_create(int device, c2b_engine **out)
 void c2b_destroy(c2b_engine *e)
 {
     if (!e) return;
-    DevBuf *bufs[] = {&e->tb, &e->tbb, &e->bnd, &e->ops, &e->work, &e->lut};
+    DevBuf *bufs[] = {&e->tb, &e->tbb, &e->tbq, &e->bnd, &e->ops, &e->work, &e->lut};
     for (DevBuf *b : bufs) if (b->p) rt_free(b->p);
     for (auto &st : e->stage) {
         DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed, &st.maxlen, &st.ord};
@@ -346,6 +344,12 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
             d.pk_XB = (uint32_t)((4 * (rf.gap_incentive[0] + OFFu)) | 2) * rep;
             d.pk_YB = (uint32_t)((4 * (rf.gap_incentive[0] + OFFu)) | 1) * rep;
             d.pk_M00 = (uint32_t)(4 * OFFu) * rep;
+            {   // ring-banded path: the out-of-band score bound (ring_bound) must be decreasing in the number of gap columns
+                int64_t gsum = 0;
+                for (int i = 0; i <= I; i++) gsum += rf.gap_incentive[i];
+                d.rg_smax = (int32_t)smax; d.rg_gmax = (int32_t)gmax; d.rg_gsum = (int32_t)std::min<int64_t>(gsum, 1 << 24);
+                d.rg_ok = d.pk_maxJ > 0 && nrb == 1 && smax >= 0 && 2 * ge + gmax <= smax && gsum < (1 << 24) && !(p->flags & C2B_F_NO_RING);
+            }
             if (d.pk_maxJ > 0) {
                 for (int qa = 0; qa < p->nq; qa++)
                     for (int qb = 0; qb < p->nq; qb++)
@@ -421,6 +425,7 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
     int rc;
     if ((rc = ensure(e, e->tb, (size_t)e->n_warps * e->max_nrb * TS * 64 * 4))) return rc;   // 64: a pair stores two words per lane
     if ((rc = ensure(e, e->tbb, (size_t)e->n_warps * PK_BAND_SLOTS * 64 * 4))) return rc;                // banded slabs (packed path)
+    if ((rc = ensure(e, e->tbq, (size_t)e->n_warps * TS * 64 * 4))) return rc;                           // ring-banded path: (step, lane) entries
     if ((rc = ensure(e, e->bnd, (size_t)e->n_warps * 2 * 3 * TS * 4))) return rc;
     if ((rc = ensure(e, e->ops, (size_t)e->n_warps * e->n_refs * 32 * 8))) return rc;
     const bool fresh_work = !e->work.p;
@@ -481,11 +486,13 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     P.TS = e->scratch_TS;
     P.tb = (uint32_t *)e->tb.p; P.tb_words_per_warp = (int64_t)e->max_nrb * P.TS * 64;
     P.tbb = getenv("C2B_NO_BAND") ? nullptr : (uint32_t *)e->tbb.p; P.tbb_words_per_warp = (int64_t)PK_BAND_SLOTS * 64;
+    P.tbq = getenv("C2B_NO_RING") ? nullptr : (uint32_t *)e->tbq.p;
     P.bnd = (int32_t *)e->bnd.p; P.bnd_words_per_warp = 2 * 3 * (int64_t)P.TS;
     P.opsbuf = (uint64_t *)e->ops.p;
     P.work_counter = (unsigned long long *)e->work.p;
     P.vstride = e->vstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
+    P.phase_sync = getenv("C2B_NO_PHASE_SYNC") ? 0 : 1;
     P.pair_order = e->pair_order;
     P.lut = (const uint8_t *)e->lut.p;
     P.stage_bytes = 0; P.stage_src = nullptr;
@@ -501,13 +508,13 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     RTCHK(rt_zero(e->work.p, 16, e->stream));             // [0] work counter, [1] widest alignment; [2],[3] = path statistics (cumulative)
 #ifndef C2B_EMU
     cudaEventRecord(e->ev0, e->stream);
-    c2b_align_classify_kernel<<<e->grid, e->wpc * 32, sizeof(WarpSmem) * e->wpc + (size_t)P.stage_bytes, e->stream>>>(P);
+    c2b_align_classify_kernel<<<e->grid, e->wpc * 32, (sizeof(WarpSmem) + sizeof(QuadSmem)) * e->wpc + 128 + (size_t)P.stage_bytes, e->stream>>>(P);
     cudaEventRecord(e->ev1, e->stream);
     RTCHK(cudaGetLastError());
 #else
     {
-        static WarpSmem S;
-        for (int64_t w = 0; 2 * w < n_reads; w++) emu::run_warp([&]() { process_item(P, S, nullptr, w, 0); });
+        static WarpSmem S; static QuadSmem Q;
+        for (int64_t w = 0; 8 * w < n_reads; w++) emu::run_warp([&]() { process_group(P, S, Q, nullptr, w, 0); });
     }
 #endif
     e->launches++;
@@ -550,12 +557,20 @@ int64_t c2b_launch_count(const c2b_engine *e) { return e ? e->launches : 0; }
 int c2b_path_counts(c2b_engine *e, int64_t *pair_items, int64_t *single_items)
 {
     if (!e || !e->work.p) return fail(e, C2B_E_STATE, "c2b_path_counts: nothing launched yet");
-    int64_t v[5] = {0, 0, 0, 0, 0};
-    RTCHK(rt_d2h(v, e->work.p, 40, e->stream));
-    e->band_reruns = v[4];
+    int64_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    RTCHK(rt_d2h(v, e->work.p, 64, e->stream));
     RTCHK(rt_sync(e->stream));
+    e->band_reruns = v[4]; e->ring_pairs = v[5]; e->ring_fallbacks = v[6];
     if (pair_items) *pair_items = v[2];
     if (single_items) *single_items = v[3];
+    return C2B_OK;
+}
+
+int c2b_ring_counts(c2b_engine *e, int64_t *ring_pairs, int64_t *ring_fallbacks)
+{
+    if (!e) return C2B_E_ARG;
+    if (ring_pairs) *ring_pairs = e->ring_pairs;
+    if (ring_fallbacks) *ring_fallbacks = e->ring_fallbacks;
     return C2B_OK;
 }
 

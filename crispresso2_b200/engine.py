@@ -225,5 +225,12 @@ class Engine:
         """pairs re-run with the full traceback slab since the last counts_reset (call path_counts() first)"""
         return int(self.L.c2b_band_reruns(self.h))
 
+    def ring_counts(self):
+        """(pairs aligned by the ring-banded DP, pairs of ring-eligible groups that took the full matrix) since the last
+        counts_reset (call path_counts() first)"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self.L.c2b_ring_counts(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def launch_count(self):
         return int(self.L.c2b_launch_count(self.h))

@@ -43,6 +43,7 @@ extern "C" {
 #define C2B_F_DISCARD_INDEL_READS  32u
 #define C2B_F_NO_STRAND_SEARCH     64u   /* global_align-only mode: forward strand, no seed test */
 #define C2B_F_NO_PAIRING          128u   /* debugging / A-B runs: never use the packed two-reads-per-warp path */
+#define C2B_F_NO_RING             512u   /* debugging / A-B runs: never use the ring-banded four-pairs-per-warp path */
 #define C2B_F_HDR_REF1            256u   /* args.expected_hdr_amplicon_seq / prime-editing extension set: also build the
                                             "ref1" re-projection vectors of CRISPRessoCORE.py:4195-4272 */
 
@@ -199,6 +200,9 @@ int64_t c2b_launch_count(const c2b_engine *e);      /* kernels launched by this 
 int  c2b_path_counts(c2b_engine *e, int64_t *pair_items, int64_t *single_items);
 /* packed pairs whose traceback left the banded slab and were re-run with the full slab (as of the last c2b_path_counts) */
 int64_t c2b_band_reruns(c2b_engine *e);
+/* pairs aligned by the ring-banded DP (four pairs per warp, band proven sufficient by a score bound) / pairs of
+ * ring-eligible groups that fell back to the full matrix (as of the last c2b_path_counts) */
+int  c2b_ring_counts(c2b_engine *e, int64_t *ring_pairs, int64_t *ring_fallbacks);
 
 /* replaces: the count vectors / counters built by the quantification loop (CRISPRessoCORE.py:3841-3907,
  * :3964-4115).  Layout above.  c2b_counts_device exposes the block for an NCCL all-reduce.            */

@@ -194,3 +194,59 @@ def check_band_fallback(engine, n=24, seed=31):
     check_against_oracle(engine, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
     pairs, singles = engine.path_counts()
     assert pairs > 0 and engine.band_reruns() > 0
+
+
+def check_ring_equals_full(engine, n=96, I=250, seed=41, oracle_subset=0):
+    """Ring-banded DP (four pairs per warp, only a diagonal band computed, result kept iff the score beats the
+    out-of-band bound) against the full-matrix packed path: identical records, alignments, strings, edit lists and
+    count block.  Reads are built to straddle the bound: deletions of 1..48 bp, insertions of 1..40 bp, heavy
+    substitution loads, random reads."""
+    from crispresso2_b200 import synth, _lib
+    from crispresso2_b200.engine import pack_reads
+    rng = np.random.default_rng(seed)
+    amp = synth.random_amplicon(rng, I)
+    ref = synth.amplicon_setup(amp, guide_start=max(1, I // 2 - 10))
+    acgt = list("ACGT")
+    reads = []
+    for k in range(n):
+        kind = k % 6
+        if kind == 0:
+            d = int(rng.integers(1, 49)); a = int(rng.integers(20, max(21, I - d - 20)))
+            s = amp[:a] + amp[a + d:] + "".join(rng.choice(acgt, d))
+        elif kind == 1:
+            d = int(rng.integers(1, 41)); a = int(rng.integers(20, I - 20))
+            s = amp[:a] + "".join(rng.choice(acgt, d)) + amp[a:]
+        elif kind == 2:
+            s = list(amp)
+            for p in rng.choice(I, int(rng.integers(5, 60)), replace=False):
+                s[p] = acgt[int(rng.integers(0, 4))]
+            s = "".join(s)
+        elif kind == 3:
+            s = "".join(rng.choice(acgt, I))
+        elif kind == 4:
+            d = int(rng.integers(25, 40)); a = int(rng.integers(20, I // 2))      # long deletion and long insertion
+            s = amp[:a] + amp[a + d:I - 30] + "".join(rng.choice(acgt, d)) + amp[I - 30:]
+        else:
+            s = synth.synth_reads(rng, amp, 1, I, sub_rate=0.01, cut=ref["cut_point"])[0].tobytes().decode()
+        reads.append(s[:I].ljust(I, "A"))
+    buf, off = pack_reads(reads)
+    out = []
+    for flags in (0, _lib.F_NO_RING):
+        engine.configure({"Reference": ref}, ["Reference"], O.make_matrix(), -20, -2, 5, 2, flags, "ACGTN", 40)
+        engine.counts_reset()
+        res = engine.align_packed(buf, off)
+        pc = engine.path_counts()
+        out.append((res, engine.counts_raw(), pc, engine.ring_counts()))
+    (a, ca, pa, ra), (b, cb, pb, rb) = out
+    assert ra[0] > 0 and ra[1] > 0, ra                    # both the ring result and the full-matrix fallback occurred
+    assert rb == (0, 0)
+    assert (a.recs == b.recs).all() and (a.alns == b.alns).all() and (ca == cb).all()
+    W = a.W
+    cols = np.arange(W)[None, :] >= (W - a.alns[:, 0]["aln_len"].astype(np.int64))[:, None]
+    assert ((a.strings[:, 0] == b.strings[:, 0]) | ~cols[:, None, :]).all()
+    ne = a.alns[:, 0]["n_edits"].astype(np.int64)
+    valid = np.arange(a.edits.shape[2])[None, :] < np.minimum(ne, a.edits.shape[2])[:, None]
+    assert ((a.edits[:, 0] == b.edits[:, 0]) | ~valid).all()
+    if oracle_subset:
+        check_against_oracle(engine, {"Reference": ref}, ["Reference"], O.Params(), reads[:oracle_subset], O.make_matrix())
+    return ra

@@ -121,6 +121,11 @@ def test_packed_pair_path_equals_32bit_path(emu):
         assert (a.edits[i, 0, :n] == b.edits[i, 0, :n]).all()
 
 
+@pytest.mark.parametrize("I", [250, 131])
+def test_ring_banded_path_equals_full_matrix(emu, I):
+    PU.check_ring_equals_full(emu, n=96, I=I, seed=40 + I, oracle_subset=48)
+
+
 def test_pooled_ref_id(emu):
     PU.check_pooled(emu, n_amplicons=4, reads_per=24)
 

@@ -196,6 +196,11 @@ def test_packed_pair_path_equals_32bit_path(eng):
     assert ((a.edits[:, 0] == b.edits[:, 0]) | ~valid).all()
 
 
+@pytest.mark.parametrize("I", [250, 256, 131, 64])
+def test_ring_banded_path_equals_full_matrix(eng, I):
+    PU.check_ring_equals_full(eng, n=24000, I=I, seed=40 + I, oracle_subset=400)
+
+
 def test_pooled_ref_id(eng):
     """BASELINE configs[3] shape: many amplicons, each read aligned to its own one (ref_id), one launch."""
     PU.check_pooled(eng, n_amplicons=24, reads_per=120, amp_len=(180, 280))
