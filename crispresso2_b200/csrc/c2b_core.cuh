@@ -38,7 +38,14 @@ C2B_DEV uint32_t shflu_up(uint32_t v, int d) { return __shfl_up_sync(0xffffffffu
 C2B_DEV int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 C2B_DEV uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 C2B_DEV void sync() { __syncwarp(); }
-C2B_DEV void cta_sync() { __syncthreads(); }
+// barrier among the g warps of this warp's phase set: named barrier 1 + set index.  g > 0: sets of g consecutive warps;
+// g < 0: |g| warps strided by the number of sets (warps w, w + nsets, ...: with four sets, the warps of one sub-partition)
+C2B_DEV void grp_sync(int g)
+{
+    const int w = (int)(threadIdx.x >> 5), n = g > 0 ? g : -g;
+    const int set = g > 0 ? w / n : w % ((int)(blockDim.x >> 5) / n);
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + set), "r"(32 * n) : "memory");
+}
 C2B_DEV int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 C2B_DEV int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }   // max(a+b, c)
 C2B_DEV uint32_t max3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }      // per signed half
@@ -125,7 +132,8 @@ struct KParams {
     const uint32_t *stage_src;        // = refs[0].prof2 (global source of the staged tile)
     int32_t stage_bytes;              // bytes of refs[0].prof2 staged into shared memory by TMA at kernel start (0: none)
     const uint8_t *lut;               // [256] ASCII -> alphabet code, 255 = not in the alphabet (device memory, L1-resident)
-    int32_t phase_sync;               // 1: the warps of a CTA walk through the per-group phases in step (instruction-cache locality)
+    int32_t phase_sync;               // g > 0: sets of g consecutive warps of a CTA walk through the per-group phases in step
+                                      // (instruction-cache locality; g divides the CTA's warp count); 0: free-running warps
     const uint64_t *forced_ops;       // c2b_classify_aligned: op streams supplied by the caller, [read][32]
     const int32_t *forced_n;
 };
@@ -143,13 +151,19 @@ constexpr int PK_ROWINFO_STRIDE = 512, PK_ROWINS_STRIDE = 514, PK_MAX_ALN = 512;
 // (step t -> slot t - 9L + RG_B); cells with column - row in [-(RG_B+1), RG_NS-RG_B-9] are always inside the band.
 constexpr int RG_NS = 72, RG_B = 32, RG_MAXD = 8, RG_COMBO = 272;
 constexpr int RG_DLO = RG_B + 1, RG_DHI = RG_NS - RG_B - 9;
-struct QuadSmem { uint8_t combo[4][RG_COMBO]; };
+struct QuadSmem {                                  // per warp; the op streams take the place of the base-pair codes once the DP is done
+    union {
+        uint8_t combo[4][RG_COMBO];
+        struct { uint64_t ops[4][32]; int32_t n[4][2], err[4][2]; } wk;
+    };
+};
 // Banded traceback slab of the packed path.  Lane l (rows 8l+1..8l+8) keeps only the PK_BAND_SLOTS wavefront steps around
 // its own diagonal (step t -> slot t - 9l + PK_BAND_B): cells whose column is within about -29..+27 of their row.  The DP
 // itself is unchanged (every cell is computed); if the traceback ever needs a cell outside the band, the pair is simply
 // re-run with the full slab.  The banded slabs of the whole grid (16 KB per warp, 39 MB) stay resident in L2.
 constexpr int PK_BAND_SLOTS = 64, PK_BAND_B = 28, PK_BAND_MAXD = 8;
-// slot = t - slope*lane + off, kept iff 0 <= slot < ns.  Entry index: (slot, lane); ring slabs: (t, gb + (lane & 7)).
+// slot = t - slope*lane + off, kept iff 0 <= slot < ns.  Entry index: slot*32 + lane; ring slabs: (gb + (lane & 7))*TS + t,
+// i.e. a lane's steps are consecutive (a diagonal run of the walk touches two or three 32-byte sectors).
 struct SlabMode { int slope, off, ns, ring, gb; };
 
 struct Walked { uint64_t ops; int n; int err; };
@@ -294,7 +308,7 @@ C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const 
             const int slot = cj + l - sm.slope * l + sm.off;
             inband = (unsigned)slot < (unsigned)sm.ns;
             if (inband) {
-                const int64_t idx = sm.ring ? (int64_t)(cj + l) * 32 + sm.gb + (l & 7) : ((int64_t)rb * TS + slot) * 32 + l;
+                const int64_t idx = sm.ring ? (int64_t)(sm.gb + (l & 7)) * TS + cj + l : ((int64_t)rb * TS + slot) * 32 + l;
                 if (PAIR) {
                     const uint2 w2 = wp::ldcg2(tb2 + idx);
                     const uint32_t w = hb ? ((w2.x & 0xffff0000u) | (w2.y >> 16)) : ((w2.x << 16) | (w2.y & 0xffffu));
@@ -321,7 +335,13 @@ C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const 
             i -= run * di; j -= run * dj;
             err |= (news == 3);
             s = news;
-            if (s == OP_M && sm.slope == 0) {               // full slab: pull the window two iterations down the diagonal towards L2
+            if (s == OP_M && sm.ring) {                     // ring slab: the next but one window (two lanes' worth of consecutive entries)
+                const int pi = i - 2 * G - hl, pj = j - 2 * G - hl;
+                if (pi >= 1 && pj >= 1 && (hl & 3) == 0) {
+                    const int l = (pi - 1) >> 3;
+                    wp::prefetch_l2(tb2 + (int64_t)(sm.gb + (l & 7)) * TS + pj + l);
+                }
+            } else if (s == OP_M && sm.slope == 0) {        // full slab: pull the window two iterations down the diagonal towards L2
                 const int pi = i - 2 * G - hl, pj = j - 2 * G - hl;
                 if (pi >= 1 && pj >= 1) {
                     const int r = pi - 1, key = r >> 3, rb = key >> 5, l = key & 31;
@@ -895,9 +915,6 @@ C2B_DEV void dp_block2(const KParams &P, const RefDev &R, const uint32_t *prof, 
 
     const int nsteps = J + nl - 1;
     const uint32_t *__restrict__ prof0 = prof + rb * 256 + lane * 4;     // shared (TMA-staged) or global copy, same layout
-    const uint32_t prof_sa = STAGED ? wp::smem_addr(prof0) : 0u;         // 32-bit shared address of the staged tile
-    const uint32_t combo_sa = wp::smem_addr(combo) - 1u;                 // combo[j-1] = [combo_sa + j]
-    const uint32_t qstride = (uint32_t)Ipad * 4u;
     int slot = 1 - sm.slope * lane + sm.off;                             // slab slot of step t = 1 for this lane
     uint2 *__restrict__ tbp = tb2 + ((int64_t)rb * P.TS + slot) * 32 + lane;   // advanced by one slot (32 entries) per step
     const bool lane_on = lane < nl;
@@ -1027,7 +1044,9 @@ C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *pro
     };
     enter(L);
     uint32_t pM = R.pk_M00, pX = PK_SENT | PK_T2, pY = PK_SENT | PK_T1;  // diagonal of (1,1); other lanes: carried below
-    uint2 *__restrict__ tbp = tbq + 32 + lane;                           // entry of step t = 1
+    uint2 *__restrict__ tbp = tbq + (int64_t)lane * P.TS;                // this lane's entries; step t -> entry t, written two at a time
+    uint32_t hT = 0, hIJ = 0;                                            // an even step's entry, held until the odd step
+    bool pend = false;
 
     for (int t = 1; t <= nsteps; t++) {
         uint32_t uM = wp::shflu(M[7], src), uX = wp::shflu(X[7], src), uY = wp::shflu(Y[7], src);
@@ -1063,17 +1082,19 @@ C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *pro
                 M[k] = nm; X[k] = x | PK_T2; Y[k] = y | PK_T1;
                 upM = nm; upY = Y[k];
             }
-            *tbp = make_uint2(wT, wIJ);
+            if (t & 1) *reinterpret_cast<uint4 *>(tbp + (t - 1)) = make_uint4(hT, hIJ, wT, wIJ);
+            hT = wT; hIJ = wIJ; pend = !(t & 1);
             if (j == J && L == lstar) {                                  // cell (I, J): the three final values
                 const int kstar = R.kstar;
 #pragma unroll
                 for (int k = 0; k < 8; k++) if (k == kstar) { fin[3 * lane] = M[k]; fin[3 * lane + 1] = X[k]; fin[3 * lane + 2] = Y[k]; }
             }
         }
-        tbp += 32;
+        else if (pend) { tbp[t - 1] = make_uint2(hT, hIJ); pend = false; }     // the active stretch ended on an even step
         pM = uM; pX = uX; pY = uY;                                       // raw: a lane entering its next window needs the uncapped edge
         if (++slot == RG_NS) { L += 8; slot = 0; enter(L); }
     }
+    if (pend) tbp[nsteps] = make_uint2(hT, hIJ);
 }
 
 // Upper bound on the score of any alignment of a J-long read that visits a cell with column - row outside
@@ -1098,8 +1119,8 @@ C2B_DEV int ring_bound(const KParams &P, const RefDev &R, int J)
     return U;
 }
 
-struct RingCtx { const uint2 *tbq; int gb; int modes; int s2; };   // a pair whose DP was done by dp_ring: slab, ring base lane, strand modes, start states
-constexpr int PAIR_PHASES = 5, GROUP_PHASES = 2 + 4 * PAIR_PHASES;      // CTA barriers per process_pair(phased) / per work group
+struct RingCtx { const uint64_t *ops; const int32_t *n, *err; int modes; };   // a pair aligned by dp_ring: its walked op streams, lengths, strand modes
+constexpr int PAIR_PHASES = 5, GROUP_PHASES = 3 + 4 * PAIR_PHASES;      // barriers per process_pair(phased) / per work group
 
 // Two reads (rdA, rdB) of equal length J through the packed path.  Per-lane variables belong to the lane's half.
 C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_prof, int64_t rdA, int64_t rdB, int warp_slot,
@@ -1107,7 +1128,7 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
 {
     // phased: called once per pair of a work group by every warp of the CTA -- PAIR_PHASES CTA barriers keep the warps in the
     // same stretch of code (the per-read path is larger than the instruction cache)
-    if (phased) wp::cta_sync();
+    if (phased) wp::grp_sync(P.phase_sync);
     const int lane = wp::lane(), h = lane >> 4, hl = lane & 15;
     const int64_t myrd = h ? rdB : rdA;
     const int J = (int)(P.offsets[rdA + 1] - P.offsets[rdA]);
@@ -1151,13 +1172,9 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
             const int sA = (mA == 2) ? pass : (mA == 1), sB = (mB == 2) ? pass : (mB == 1);
             const uint8_t *cA = sA ? S.rc[0] : S.fw[0], *cB = sB ? S.rc[1] : S.fw[1];
             wp::sync();
-            if (phased && pass == 0) wp::cta_sync();
+            if (phased && pass == 0) wp::grp_sync(P.phase_sync);
             Walked wk; wk.err = 4;
-            if (ring) {                                     // DP already done by dp_ring: walk its slab
-                const int s0 = (lane & 16) ? (ring->s2 >> 16) : (ring->s2 & 3);
-                wk = walk_batch<true>(P, R, J, reinterpret_cast<const uint32_t *>(ring->tbq), s0, SlabMode{9, RG_B, RG_NS, 1, ring->gb});
-                if (wp::ballot((wk.err & 4) != 0)) { wk.err = 4; if (lane == 0) wp::addg(P.work_counter + 6, 1); }
-            }
+            if (ring) { wk.ops = ring->ops[lane]; wk.n = ring->n[h]; wk.err = ring->err[h]; }   // aligned and walked by process_quad
             if (wk.err & 4) {
                 for (int p = lane; p < J; p += 32) S.combo[p] = (uint8_t)(cA[p] * P.nq + cB[p]);
                 wp::sync();
@@ -1176,7 +1193,7 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
         }
         for (int p = lane; p < 2 * PK_ROWINS_STRIDE; p += 32) S.rowins[p] = 0;
         wp::sync();
-        if (phased) wp::cta_sync();
+        if (phased) wp::grp_sync(P.phase_sync);
         uint8_t *o_read = P.strings ? P.strings + ((myrd * P.n_refs + r) * 2) * (int64_t)P.W : nullptr;
         uint8_t *o_ref = o_read ? o_read + P.W : nullptr;
         int cmode = (o_read ? 1 : 0) | (multi ? 0 : 2);
@@ -1197,7 +1214,7 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
     wp::sync();
     // classification runs with the whole warp, one read at a time: broadcast that half's bookkeeping to every lane
     for (int hh = 0; hh < 2; hh++) {
-        if (phased) wp::cta_sync();
+        if (phased) wp::grp_sync(P.phase_sync);
         if (hh == 1 && rdB == rdA) break;
         const int src = 16 * hh;
         c2b_read_rec rr;
@@ -1251,7 +1268,7 @@ C2B_DEV void process_quad(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint
 {
     const int lane = wp::lane(), g = lane >> 3;
     uint2 *tbq = reinterpret_cast<uint2 *>(P.tbq + (int64_t)warp_slot * P.TS * 64);
-    if (P.phase_sync) wp::cta_sync();
+    if (P.phase_sync) wp::grp_sync(P.phase_sync);
     uint32_t okmask = 0, modes = 0;
     int Jg = 0, Jmax = 0;
     const int64_t rd0 = P.pair_order ? P.pair_order[2 * first] : 2 * first;
@@ -1280,7 +1297,7 @@ C2B_DEV void process_quad(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint
         wp::sync();
     }
     uint32_t passmask = 0, s2 = 0;
-    if (P.phase_sync) wp::cta_sync();
+    if (P.phase_sync) wp::grp_sync(P.phase_sync);
     if (okmask) {
         const bool staged = (r == 0 && staged_prof != nullptr);
         uint32_t *fin = S.rowins;                            // 32 x 3 words: each ring's final lane leaves M, X, Y of cell (I, J)
@@ -1298,6 +1315,22 @@ C2B_DEV void process_quad(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint
         const uint32_t b = wp::ballot(pass);
         passmask = (b & 1u) | ((b >> 7) & 2u) | ((b >> 14) & 4u) | ((b >> 21) & 8u);
     }
+    if (P.phase_sync) wp::grp_sync(P.phase_sync);
+    // the four tracebacks while the slab is still warm in L2; the op streams replace the base-pair codes in shared memory
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        if (!((passmask >> q) & 1u)) continue;
+        const uint32_t sq = wp::shflu(s2, 8 * q);
+        const int Jq = wp::shfl(Jg, 8 * q);
+        const int s0 = (lane & 16) ? (int)(sq >> 16) : (int)(sq & 3u);
+        const Walked wk = walk_batch<true>(P, R, Jq, reinterpret_cast<const uint32_t *>(tbq), s0, SlabMode{9, RG_B, RG_NS, 1, 8 * q});
+        if (wp::ballot((wk.err & 4) != 0)) passmask &= ~(1u << q);       // cannot happen when the bound holds; full matrix then
+        else {
+            Q.wk.ops[q][lane] = wk.ops;
+            if ((lane & 15) == 0) { Q.wk.n[q][lane >> 4] = wk.n; Q.wk.err[q][lane >> 4] = wk.err; }
+        }
+    }
+    wp::sync();
     if (lane == 0) {
         wp::addg(P.work_counter + 2, 4);
         wp::addg(P.work_counter + 5, wp::popc(passmask));
@@ -1307,7 +1340,7 @@ C2B_DEV void process_quad(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint
     for (int q = 0; q < 4; q++) {
         const int64_t rdA = P.pair_order ? P.pair_order[2 * (first + q)] : 2 * (first + q);
         const int64_t rdB = P.pair_order ? P.pair_order[2 * (first + q) + 1] : 2 * (first + q) + 1;
-        RingCtx rc; rc.tbq = tbq; rc.gb = 8 * q; rc.modes = (int)((modes >> (4 * q)) & 15u); rc.s2 = (int)wp::shflu(s2, 8 * q);
+        RingCtx rc; rc.ops = Q.wk.ops[q]; rc.n = Q.wk.n[q]; rc.err = Q.wk.err[q]; rc.modes = (int)((modes >> (4 * q)) & 15u);
         process_pair(P, S, staged_prof, rdA, rdB, warp_slot, ((passmask >> q) & 1u) ? &rc : nullptr, P.phase_sync != 0);
         wp::sync();
     }
@@ -1339,7 +1372,7 @@ C2B_DEV void process_group(const KParams &P, WarpSmem &S, QuadSmem &Q, const uin
             if (2 * (first + q) < P.n_reads) { process_item(P, S, staged_prof, first + q, warp_slot); wp::sync(); }
         if (P.phase_sync) {                                 // keep the CTA's barrier count per group the same on every path
 #pragma unroll 1
-            for (int b = 0; b < GROUP_PHASES; b++) wp::cta_sync();
+            for (int b = 0; b < GROUP_PHASES; b++) wp::grp_sync(P.phase_sync);
         }
     }
 }

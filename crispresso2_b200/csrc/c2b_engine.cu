@@ -103,20 +103,35 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_a
         asm volatile("{\n .reg .pred p;\n C2B_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra C2B_DONE;\n bra C2B_WAIT;\n C2B_DONE:\n}" ::"r"(mbar_a) : "memory");
         staged_prof = reinterpret_cast<const uint32_t *>(dst);
     }
-    // Work groups (8 reads each) are handed out per CTA, one per warp, so that the loop count -- and with it the number
-    // of CTA barriers executed by process_group's phases -- is the same for every warp of the CTA.
-    __shared__ unsigned long long next_base;
-    const unsigned long long wpc = blockDim.x >> 5, total = ((unsigned long long)P.n_reads + 7) / 8;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) next_base = atomicAdd(P.work_counter, wpc);
-        __syncthreads();
-        const unsigned long long base = next_base;
-        if (base >= total) break;
-        const unsigned long long w = base + (threadIdx.x >> 5);
+    // Work groups (8 reads each) are handed out per phase set (g consecutive warps, one group per warp), one hand-out
+    // ahead, so that the loop count -- and with it the number of barriers executed by process_group's phases -- is the
+    // same for every warp of the set, and the next group's read bytes are on their way to L2 while this one computes.
+    __shared__ unsigned long long next_base[WARPS_PER_CTA];
+    const int gs = P.phase_sync, g = gs > 0 ? gs : gs < 0 ? -gs : 1, wib = threadIdx.x >> 5, nsets = (int)(blockDim.x >> 5) / g;
+    const int set = gs < 0 ? wib % nsets : wib / g, wis = gs < 0 ? wib / nsets : wib % g;
+    const unsigned long long total = ((unsigned long long)P.n_reads + 7) / 8;
+    auto hand_out = [&]() -> unsigned long long {
+        if (wis == 0 && (threadIdx.x & 31) == 0) next_base[set] = atomicAdd(P.work_counter, (unsigned long long)g);
+        if (g > 1) wp::grp_sync(gs); else __syncwarp();
+        const unsigned long long b = next_base[set];
+        if (g > 1) wp::grp_sync(gs); else __syncwarp();
+        return b;
+    };
+    unsigned long long base = hand_out();
+    while (base < total) {
+        const unsigned long long nb = hand_out();
+        const unsigned long long wn = nb + wis;
+        if (wn < total && !P.pair_order) {
+            const int64_t last = (int64_t)(8 * wn + 8) < P.n_reads ? (int64_t)(8 * wn + 8) : P.n_reads;
+            const int64_t b0 = P.offsets[8 * wn], b1 = P.offsets[last];
+            const int64_t a = b0 + (int64_t)(threadIdx.x & 31) * 128;
+            if (a < b1) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.reads + a));
+        }
+        const unsigned long long w = base + wis;
         if (w < total) process_group(P, *S, *Q, staged_prof, (int64_t)w, warp_slot);  // reads 8w .. 8w+7
-        else if (P.phase_sync) for (int b = 0; b < GROUP_PHASES; b++) __syncthreads();
+        else if (P.phase_sync) for (int b = 0; b < GROUP_PHASES; b++) wp::grp_sync(gs);
         __syncwarp();
+        base = nb;
     }
 }
 #endif
@@ -194,6 +209,12 @@ int c2b_create(int device, c2b_engine **out)
     if (r == cudaSuccess) r = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     // room for a TMA-staged reference tile next to C2B_MIN_CTAS_PER_SM CTAs of per-warp state (1 KB per CTA is reserved by the driver)
     e->stage_cap = smem_sm / C2B_MIN_CTAS_PER_SM - 1024 - (int)((sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA) - 256;
+    {   // ... and within the per-block opt-in limit
+        int optin = 0;
+        if (r == cudaSuccess) r = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        const int fixed = (int)((sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA) + 128;
+        if (e->stage_cap > optin - fixed) e->stage_cap = optin - fixed;
+    }
     if (e->stage_cap < 0) e->stage_cap = 0;
     e->stage_cap &= ~127;
     if (r == cudaSuccess) r = cudaFuncSetAttribute(c2b_align_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -425,7 +446,7 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
     int rc;
     if ((rc = ensure(e, e->tb, (size_t)e->n_warps * e->max_nrb * TS * 64 * 4))) return rc;   // 64: a pair stores two words per lane
     if ((rc = ensure(e, e->tbb, (size_t)e->n_warps * PK_BAND_SLOTS * 64 * 4))) return rc;                // banded slabs (packed path)
-    if ((rc = ensure(e, e->tbq, (size_t)e->n_warps * TS * 64 * 4))) return rc;                           // ring-banded path: (step, lane) entries
+    if ((rc = ensure(e, e->tbq, (size_t)e->n_warps * TS * 64 * 4 + 64))) return rc;                           // ring-banded path: (step, lane) entries
     if ((rc = ensure(e, e->bnd, (size_t)e->n_warps * 2 * 3 * TS * 4))) return rc;
     if ((rc = ensure(e, e->ops, (size_t)e->n_warps * e->n_refs * 32 * 8))) return rc;
     const bool fresh_work = !e->work.p;
@@ -492,7 +513,9 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     P.work_counter = (unsigned long long *)e->work.p;
     P.vstride = e->vstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
-    P.phase_sync = getenv("C2B_NO_PHASE_SYNC") ? 0 : 1;
+    P.phase_sync = 4;                                     // warps per phase set (C2B_PHASE_WARPS: 0/1 = free-running, 2, 4, 8)
+    if (const char *v = getenv("C2B_PHASE_WARPS")) { const int k = atoi(v), a = k < 0 ? -k : k; P.phase_sync = (a == 2 || a == 4 || a == 8 || a == 16) ? k : 0; }
+    { const int a = P.phase_sync < 0 ? -P.phase_sync : P.phase_sync; if (a > e->wpc || (a && e->wpc % a)) P.phase_sync = 0; }
     P.pair_order = e->pair_order;
     P.lut = (const uint8_t *)e->lut.p;
     P.stage_bytes = 0; P.stage_src = nullptr;
