@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Runs the UNMODIFIED reference `CRISPResso` main() (imported from /root/reference through the stubs of
+tests/golden/gen_golden.py) either as-is or with its module-global `process_fastq` (CRISPRessoCORE.py:1735,
+resolved at :3750) re-bound to crispresso2_b200.core.process_fastq -- the one-line integration of
+INTEGRATION.md section 2.  Used by tests/test_cli_dropin.py, which diffs the two output folders byte for byte.
+
+usage: cli_dropin_runner.py <reference|b200> <engine-lib-or-'default'> <outdir> <vectors.json> -- <CRISPResso argv>
+
+In b200 mode the count vectors / counters the reference's own quantification loop built (CRISPRessoCORE.py:3964-4303,
+captured from the CorePlotContext it constructs at :4836) are also compared here with the engine's count block and
+the outcome is written to <vectors.json>.
+
+TEST INFRASTRUCTURE: needs /root/reference and oracle/_ref; never runs on the GPU box.
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+sys.path.insert(0, HERE)
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    mode, lib, outdir, vec_json = sys.argv[1:5]
+    argv = sys.argv[sys.argv.index("--") + 1:]
+    import gen_golden as GG                                  # installs the stubs, imports the reference CORE
+    CORE = GG.CRISPRessoCORE
+    report = {"mode": mode, "mismatch": [], "checked": 0}
+    if mode == "b200":
+        from crispresso2_b200 import core
+        from crispresso2_b200.engine import Engine
+        eng = Engine(lib_path=None if lib == "default" else lib)
+        state = {}
+
+        def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory):
+            loc = os.path.join(CORE._ROOT, args.needleman_wunsch_aln_matrix_loc)      # CRISPRessoCORE.py:1811
+            m = core.read_matrix(loc)
+            out = core.process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_remove,
+                                     output_directory, engine=eng, aln_matrix=m)
+            state["block"] = core.quantify(variantCache)
+            state["ref_names"] = list(ref_names)
+            return out
+
+        CORE.process_fastq = process_fastq
+        orig_ctx = CORE.CorePlotContext
+
+        def ctx_spy(*a, **kw):
+            blk = state["block"]
+            bad = report["mismatch"]
+
+            def cmp(name, got, want):
+                report["checked"] += 1
+                if not np.array_equal(np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)):
+                    bad.append(name)
+
+            for r in state["ref_names"]:
+                V = blk.vectors(r)
+                S = blk.scalars(r)
+                for ours, theirs in (("all_insertion_count", "all_insertion_count_vectors"),
+                                     ("all_insertion_left_count", "all_insertion_left_count_vectors"),
+                                     ("all_deletion_count", "all_deletion_count_vectors"),
+                                     ("all_substitution_count", "all_substitution_count_vectors"),
+                                     ("insertion_count", "insertion_count_vectors"),
+                                     ("deletion_count", "deletion_count_vectors"),
+                                     ("substitution_count", "substitution_count_vectors")):
+                    cmp(r + ":" + theirs, V[ours], kw[theirs][r])
+                for ch in "ACGTN":
+                    cmp(r + ":all_substitution_base_" + ch, V["all_substitution_base_" + ch],
+                        kw["all_substitution_base_vectors"][r + "_" + ch])
+                for ch in "ACGTN-":
+                    cmp(r + ":all_base_count_" + ch, V["all_base_count_" + ch], kw["all_base_count_vectors"][r + "_" + ch])
+                for ours, theirs in (("counts_total", "counts_total"), ("counts_modified", "counts_modified"),
+                                     ("counts_unmodified", "counts_unmodified"), ("counts_discarded", "counts_discarded"),
+                                     ("counts_insertion", "counts_insertion"), ("counts_deletion", "counts_deletion"),
+                                     ("counts_substitution", "counts_substitution")):
+                    cmp(r + ":" + theirs, [S[ours]], [kw[theirs][r]])
+                if hasattr(blk, "extras"):
+                    X = blk.extras(r, kw["args"], kw["refs"][r] if r in kw["refs"] else None)
+                    for theirs, got in X.items():
+                        want = kw[theirs][r]
+                        if isinstance(want, dict) or hasattr(want, "items"):
+                            report["checked"] += 1
+                            w = {int(k): int(v) for k, v in want.items() if v != 0}
+                            g = {int(k): int(v) for k, v in got.items() if v != 0}
+                            if w != g:
+                                bad.append(r + ":" + theirs)
+                        else:
+                            cmp(r + ":" + theirs, np.atleast_1d(got), np.atleast_1d(want))
+                if "ref1_all_deletion_count_vectors" in kw and kw["ref1_all_deletion_count_vectors"]:
+                    R1 = blk.vectors_ref1(r)
+                    for k in ("insertion", "insertion_left", "deletion", "substitution", "indelsub"):
+                        cmp(r + ":ref1_all_%s" % k, R1["ref1_all_%s_count" % k], kw["ref1_all_%s_count_vectors" % k][r])
+                    for ch in "ACGTN-":
+                        cmp(r + ":ref1_base_" + ch, R1["ref1_all_base_count_" + ch], kw["ref1_all_base_count_vectors"][r + "_" + ch])
+            if hasattr(blk, "class_counts"):
+                report["checked"] += 1
+                if dict(blk.class_counts()) != {k: int(v) for k, v in kw["class_counts"].items()}:
+                    bad.append("class_counts")
+            return orig_ctx(*a, **kw)
+
+        CORE.CorePlotContext = ctx_spy
+    os.makedirs(outdir, exist_ok=True)
+    os.chdir(outdir)
+    sys.argv = ["CRISPResso"] + argv + ["--suppress_plots", "--suppress_report", "-o", outdir]
+    try:
+        CORE.main()
+    except SystemExit as e:
+        if e.code not in (0, None):
+            raise
+    with open(vec_json, "w") as fh:
+        json.dump(report, fh)
+
+
+if __name__ == "__main__":
+    main()
