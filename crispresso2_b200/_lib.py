@@ -39,11 +39,15 @@ V_INS_LEN = V_BASEDEV0 + MAX_Q + 1
 V_DEL_LEN = V_INS_LEN + 1
 V_R1_ALL_INS, V_R1_ALL_INS_LEFT, V_R1_ALL_DEL, V_R1_ALL_SUB = V_DEL_LEN + 1, V_DEL_LEN + 2, V_DEL_LEN + 3, V_DEL_LEN + 4
 V_R1_BASEDEV0 = V_DEL_LEN + 5
-NVEC = V_R1_BASEDEV0 + MAX_Q + 1
+V_INS_NONCODING = V_R1_BASEDEV0 + MAX_Q + 1
+V_DEL_NONCODING, V_SUB_NONCODING = V_INS_NONCODING + 1, V_INS_NONCODING + 2
+NVEC = V_INS_NONCODING + 3
+H_INS_N, H_DEL_N, H_SUB_N, H_EFF_LEN, H_INFRAME, H_FRAMESHIFT, NHIST = range(7)
 SCALARS = ["TOTAL", "MODIFIED", "UNMODIFIED", "DISCARDED", "INS", "DEL", "SUB", "ONLY_INS", "ONLY_DEL", "ONLY_SUB",
            "INS_DEL", "INS_SUB", "DEL_SUB", "INS_DEL_SUB", "AMBIGUOUS_W", "N_GLOBAL_SUBS", "N_SUBS_OUTSIDE_WINDOW",
            "N_MODS_IN_WINDOW", "N_MODS_OUTSIDE_WINDOW", "N_READS_IRREGULAR_ENDS", "N_ALIGNED_UNIQUE",
-           "N_ALIGNED_COUNT", "REF1_W"]
+           "N_ALIGNED_COUNT", "REF1_W", "CLASS_MODIFIED", "CLASS_UNMODIFIED", "MOD_FRAMESHIFT", "MOD_NON_FRAMESHIFT",
+           "NON_MOD_NON_FRAMESHIFT", "SPLICING_MODIFIED"]
 NSCAL = len(SCALARS)
 S = {n: k for k, n in enumerate(SCALARS)}
 
@@ -58,7 +62,7 @@ class Ref(C.Structure):
     _fields_ = [("seq", C.c_char_p), ("len", C.c_int32), ("gap_incentive", C.c_void_p),
                 ("include_idx", C.c_void_p), ("n_include", C.c_int32), ("min_aln_score", C.c_double),
                 ("score_rows", C.c_void_p), ("fw_seeds", C.POINTER(C.c_char_p)), ("rc_seeds", C.POINTER(C.c_char_p)),
-                ("n_seeds", C.c_int32)]
+                ("n_seeds", C.c_int32), ("tot_exon_len_mod", C.c_int32), ("coding_mask", C.c_void_p)]
 
 
 ALN_DTYPE = np.dtype([("n_match", "<u2"), ("aln_len", "<u2"), ("score_milli", "<i4"), ("strand", "u1"),
@@ -73,7 +77,7 @@ assert ALN_DTYPE.itemsize == 32 and REC_DTYPE.itemsize == 16 and EDIT_DTYPE.item
 
 EXPORTS = ["c2b_create", "c2b_destroy", "c2b_last_error", "c2b_configure", "c2b_set_edit_cap", "c2b_string_width", "c2b_align_batch",
            "c2b_align_batch_device", "c2b_set_pair_order", "c2b_sync", "c2b_stream", "c2b_last_kernel_ms", "c2b_launch_count", "c2b_path_counts", "c2b_band_reruns", "c2b_ring_counts",
-           "c2b_counts_layout", "c2b_counts_reset", "c2b_counts_read", "c2b_counts_device", "c2b_global_align",
+           "c2b_counts_layout", "c2b_counts_hist_layout", "c2b_counts_reset", "c2b_counts_read", "c2b_counts_device", "c2b_global_align",
            "c2b_classify_aligned", "c2b_host_alloc", "c2b_host_free"]
 
 _cache = {}
@@ -128,6 +132,8 @@ def load(path=None):
     L.c2b_ring_counts.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.c2b_counts_layout.restype = C.c_int
     L.c2b_counts_layout.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.c2b_counts_hist_layout.restype = C.c_int
+    L.c2b_counts_hist_layout.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.c2b_counts_reset.restype = C.c_int
     L.c2b_counts_reset.argtypes = [vp]
     L.c2b_counts_read.restype = C.c_int

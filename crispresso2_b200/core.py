@@ -207,6 +207,7 @@ def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_
                         "N_GLOBAL_SUBS", "N_SUBS_OUTSIDE_WINDOW", "N_MODS_IN_WINDOW", "N_MODS_OUTSIDE_WINDOW",
                         "N_READS_IRREGULAR_ENDS", "READ_LENGTH"], 0)
     not_aligned = {}
+    class_extra = {}
     for k, seq in enumerate(uniques):                       # CRISPRessoCORE.py:1956-1981
         c = counts[k]
         st["N_TOT_READS"] += c
@@ -219,6 +220,8 @@ def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_
             not_aligned[seq] = v
             continue
         variantCache[seq] = v
+        if "&" in v["class_name"] and weights[k] > 0:       # joined labels (--expand_ambiguous_alignments): host-side class count
+            class_extra[v["class_name"]] = class_extra.get(v["class_name"], 0) + int(weights[k])
         st["N_COMPUTED_ALN"] += 1
         st["N_CACHED_ALN"] += c - 1
         p = v["variant_" + v["best_match_name"]]
@@ -237,6 +240,7 @@ def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_
     for key, val in dev.items():
         if val != st[key]:
             raise EngineError("device aln_stats disagree with per-read records for %s: %d != %d" % (key, val, st[key]))
+    block.class_extra = class_extra
     _blocks[id(variantCache)] = block
     return st, not_aligned
 

@@ -8,16 +8,21 @@ from . import _lib
 
 
 class CountBlock:
-    def __init__(self, raw, ref_names, ref_seqs, alphabet, n_vec, stride, n_scal):
+    def __init__(self, raw, ref_names, ref_seqs, alphabet, n_vec, stride, n_scal, n_hist=0, hstride=0, hist_zero=0,
+                 flags=0):
         self.raw = raw
         self.ref_names, self.ref_seqs, self.alphabet = list(ref_names), list(ref_seqs), alphabet
         self.n_vec, self.stride, self.n_scal = n_vec, stride, n_scal
-        per = n_vec * stride + n_scal
-        self._vec, self._scal = {}, {}
+        self.n_hist, self.hstride, self.hist_zero, self.flags = n_hist, hstride, hist_zero, flags
+        self.class_extra = {}         # joined class labels of --expand_ambiguous_alignments reads (core.process_fastq)
+        nv, nh = n_vec * stride, n_hist * hstride
+        per = nv + nh + n_scal
+        self._vec, self._scal, self._hist = {}, {}, {}
         for k, name in enumerate(ref_names):
             blk = raw[k * per:(k + 1) * per]
-            self._vec[name] = blk[:n_vec * stride].reshape(n_vec, stride)
-            self._scal[name] = blk[n_vec * stride:]
+            self._vec[name] = blk[:nv].reshape(n_vec, stride)
+            self._hist[name] = blk[nv:nv + nh].reshape(n_hist, hstride)
+            self._scal[name] = blk[nv + nh:]
 
     def scalar(self, ref, name):
         return int(self._scal[ref][_lib.S[name]])
@@ -31,7 +36,63 @@ class CountBlock:
                 "counts_only_deletion": g("ONLY_DEL"), "counts_only_substitution": g("ONLY_SUB"),
                 "counts_insertion_and_deletion": g("INS_DEL"), "counts_insertion_and_substitution": g("INS_SUB"),
                 "counts_deletion_and_substitution": g("DEL_SUB"),
-                "counts_insertion_and_deletion_and_substitution": g("INS_DEL_SUB")}
+                "counts_insertion_and_deletion_and_substitution": g("INS_DEL_SUB"),
+                "counts_modified_frameshift": g("MOD_FRAMESHIFT"), "counts_modified_non_frameshift": g("MOD_NON_FRAMESHIFT"),
+                "counts_non_modified_non_frameshift": g("NON_MOD_NON_FRAMESHIFT"),
+                "counts_splicing_sites_modified": g("SPLICING_MODIFIED")}
+
+    def class_counts(self):
+        """class_counts of CRISPRessoCORE.py:3984-3986 (classes with a non-zero weight, like the reference's dict)."""
+        out = {}
+        amb = 0
+        for r in self.ref_names:
+            for lab, key in (("_MODIFIED", "CLASS_MODIFIED"), ("_UNMODIFIED", "CLASS_UNMODIFIED")):
+                v = self.scalar(r, key)
+                if v:
+                    out[r + lab] = v
+            amb += self.scalar(r, "AMBIGUOUS_W")
+        if amb:
+            out["AMBIGUOUS"] = amb
+        for k, v in self.class_extra.items():
+            out[k] = out.get(k, 0) + v
+        return out
+
+    def size_histograms(self, ref):
+        """inserted_n_dicts / deleted_n_dicts / substituted_n_dicts / effective_len_dicts of :4020-4043 as Counters with
+        the reference's key sets.  The device does not store the commonest bucket (key 0, or len(ref) for the effective
+        length): it is counts_total minus the stored ones."""
+        from collections import Counter
+        H = self._hist[ref]
+        total = self.scalar(ref, "TOTAL")
+        L = len(self.ref_seqs[self.ref_names.index(ref)])
+        out = {}
+        for name, row, ignored, hub in (("inserted_n", _lib.H_INS_N, self.flags & _lib.F_IGNORE_INSERTIONS, 0),
+                                        ("deleted_n", _lib.H_DEL_N, self.flags & _lib.F_IGNORE_DELETIONS, 0),
+                                        ("substituted_n", _lib.H_SUB_N, self.flags & _lib.F_IGNORE_SUBSTITUTIONS, 0),
+                                        ("effective_len", _lib.H_EFF_LEN, 0, L)):
+            c = Counter()
+            if not ignored:
+                nz = np.nonzero(H[row])[0]
+                for k in nz:
+                    c[int(k)] = int(H[row, k])
+                rest = total - int(H[row].sum())
+                if rest:
+                    c[hub] = rest
+            out[name] = c
+        return out
+
+    def frame_histograms(self, ref):
+        """hists_inframe[ref], hists_frameshift[ref] (:3903-3906, :4134-4177): Counters, key 0 always present."""
+        from collections import Counter
+        H = self._hist[ref]
+        out = []
+        for row in (_lib.H_INFRAME, _lib.H_FRAMESHIFT):
+            c = Counter()
+            c[0] = 0
+            for k in np.nonzero(H[row])[0]:
+                c[int(k) - self.hist_zero] = int(H[row, k])
+            out.append(c)
+        return out[0], out[1]
 
     def vectors(self, ref):
         """float64 vectors under the names of oracle.VECTOR_NAMES (the reference keeps float64 too, :3865)"""
@@ -42,7 +103,9 @@ class CountBlock:
         out = {"all_insertion_count": f(_lib.V_ALL_INS), "all_insertion_left_count": f(_lib.V_ALL_INS_LEFT),
                "all_deletion_count": f(_lib.V_ALL_DEL), "all_substitution_count": f(_lib.V_ALL_SUB),
                "insertion_count": f(_lib.V_INS), "deletion_count": f(_lib.V_DEL), "substitution_count": f(_lib.V_SUB),
-               "insertion_length": f(_lib.V_INS_LEN), "deletion_length": f(_lib.V_DEL_LEN)}
+               "insertion_length": f(_lib.V_INS_LEN), "deletion_length": f(_lib.V_DEL_LEN),
+               "insertion_count_noncoding": f(_lib.V_INS_NONCODING), "deletion_count_noncoding": f(_lib.V_DEL_NONCODING),
+               "substitution_count_noncoding": f(_lib.V_SUB_NONCODING)}
         total = self.scalar(ref, "TOTAL")
         seq = np.frombuffer(self.ref_seqs[k].encode(), dtype=np.uint8)
         for q, ch in enumerate(self.alphabet):

@@ -97,8 +97,11 @@ struct RefDev {
     const int32_t *g4;             // [Ipad]      4*gi[row]                 (incentive of the row above, "i-1")
     const uint8_t *asc;            // [Ipad]      reference ASCII
     const uint8_t *rcode;          // [Ipad]      reference base as alphabet code, 255 if not in alphabet
-    const uint8_t *incl;           // [Ipad+1]    1 inside the quantification window
+    const uint8_t *incl;           // [Ipad+1]    bit 0: inside the quantification window; bit 1: exon position; bit 2: splicing position
     const uint16_t *cum;           // [Ipad+2]    cum[p] = #window positions < p
+    const uint16_t *cumx, *cums;   // [Ipad+2]    same prefix counts for exon / splicing positions (coding only)
+    int32_t coding, tem, hist_zero;   // refs[..]['contains_coding_seq'], sum(exon_len_mods), bucket of key 0 in the frame histograms
+    unsigned long long *hist;      // [C2B_NHIST][hstride]
     uint64_t fw_seed[C2B_MAX_SEEDS], rc_seed[C2B_MAX_SEEDS];   // 3 bits per base, first base lowest
     unsigned long long *vec;       // [C2B_NVEC][vstride]
     unsigned long long *scal;      // [C2B_NSCAL]
@@ -128,7 +131,7 @@ struct KParams {
     int32_t *bnd; int64_t bnd_words_per_warp;                 // 2 x 3 x (maxJ+1): row-block boundary rows
     uint64_t *opsbuf;                                         // [warp][n_refs][32] op streams (multi-reference)
     unsigned long long *work_counter;
-    int32_t vstride;
+    int32_t vstride, hstride;
     const uint32_t *stage_src;        // = refs[0].prof2 (global source of the staged tile)
     int32_t stage_bytes;              // bytes of refs[0].prof2 staged into shared memory by TMA at kernel start (0: none)
     const uint8_t *lut;               // [256] ASCII -> alphabet code, 255 = not in the alphabet (device memory, L1-resident)
@@ -454,12 +457,17 @@ C2B_DEV int score_milli(int m, int n)
 // ------------------------------------------------------------------------------------------------ rows
 struct RowOut {
     int ins_n, del_n, sub_n, n_ins_all, n_ins_win, n_del_all, n_del_win, n_del_pos, n_sub_all, nent;
+    // --coding_seq (CRISPRessoCORE.py:4104-4131): bases inserted by window insertions with a flank in an exon, any such
+    // insertion, deleted exon positions of window deletions, any window substitution in an exon, any window edit on a
+    // splicing position
+    int x_ins_len, x_ins_any, x_del_cnt, x_sub_any, x_splice;
 };
 
 // mode bits of rows_run
 constexpr int RM_SCAL = 1;   // scalars + edit list (COREResources.pyx:108-163)
 constexpr int RM_VEC = 2;    // per-position count vectors, weight w (CRISPRessoCORE.py:4016-4081)
 constexpr int RM_LEN = 4;    // insertion/deletion length vectors (:4104-4115), only for reads that carry a modification
+constexpr int RM_NONCOD = 16; // --coding_seq: window edit positions of a modified read that touches no exon (:4166-4170)
 constexpr int RM_REF1 = 8;   // HDR re-projection (:4255-4272): the scattered alignment is the one to reference 0, the
                              // vectors updated are the ref1_* block of the reference the read was assigned to (Vt)
 
@@ -471,6 +479,7 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
     const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
                ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
     const bool scal = mode & RM_SCAL, vec = mode & RM_VEC, lenv = mode & RM_LEN, ref1 = mode & RM_REF1;
+    const bool noncod = mode & RM_NONCOD, xcod = scal && R.coding;
     unsigned long long *V = ref1 ? Vt : R.vec;
     const int vs = P.vstride;
     int open_a = -1; uint32_t prevD = 0;
@@ -488,11 +497,16 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
                 ed[o.nent] = e;
             }
             o.nent++;
+            if (xcod && hit) {                                 // exon / splicing positions in deletion_positions (:4117-4127)
+                o.x_del_cnt += (int)R.cumx[b] - (int)R.cumx[a];
+                if ((int)R.cums[b] - (int)R.cums[a] > 0) o.x_splice = 1;
+            }
         }
-        if (hit && ((vec && !ign_d) || lenv)) {
+        if (hit && ((vec && !ign_d) || lenv || noncod)) {
             for (int p = a + lane; p < b; p += 32) {
                 if (vec && !ign_d) wp::addg(V + (int64_t)C2B_V_DEL * vs + p, w);
                 if (lenv) wp::addg(V + (int64_t)C2B_V_DEL_LEN * vs + p, w * size);
+                if (noncod) wp::addg(V + (int64_t)C2B_V_DEL_NONCODING * vs + p, w);
             }
         }
     };
@@ -510,9 +524,11 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
         // a chunk in which the read equals the reference and no deletion is open has nothing to record
         if (!wp::ballot(isdel || differs || insr > 0 || insl > 0) && !prevD) continue;
         const bool issub = differs && readc != 'N';                         // COREResources.pyx:111
-        const bool inc_p = valid && R.incl[p];
-        const bool win_r = insr > 0 && inc_p && R.incl[p + 1];                    // both flanks in window (:120)
-        const bool win_l = insl > 0 && inc_p && R.incl[p - 1];
+        const uint32_t mk = valid ? R.incl[p] : 0u;
+        const bool inc_p = mk & 1u;
+        const uint32_t mk1 = insr > 0 ? R.incl[p + 1] : 0u;
+        const bool win_r = insr > 0 && inc_p && (mk1 & 1u);                       // both flanks in window (:120)
+        const bool win_l = insl > 0 && inc_p && (R.incl[p - 1] & 1u);
         const uint32_t D = wp::ballot(isdel);
         if (scal) {
             const uint32_t Bs = wp::ballot(issub), Bsw = wp::ballot(issub && inc_p);
@@ -541,6 +557,21 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
                 }
                 o.nent += wp::popc(Bi);
             }
+            if (xcod) {                                        // CRISPRessoCORE.py:4104-4131, per-position form
+                const bool xi = win_r && ((mk | mk1) & 2u);    // window insertion with a flank in an exon
+                if (wp::ballot(xi)) {
+                    int v = xi ? (int)insr : 0;
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) v += wp::shfl_xor(v, d);
+                    o.x_ins_len += v; o.x_ins_any = 1;
+                }
+                if (wp::ballot(issub && inc_p && (mk & 2u))) o.x_sub_any = 1;
+                if (wp::ballot((issub && inc_p && (mk & 4u)) || (win_r && ((mk | mk1) & 4u)))) o.x_splice = 1;
+            }
+        }
+        if (noncod) {
+            if (win_r || win_l) wp::addg(V + (int64_t)C2B_V_INS_NONCODING * vs + p, w);
+            if (issub && inc_p) wp::addg(V + (int64_t)C2B_V_SUB_NONCODING * vs + p, w);
         }
         if (vec) {
             if (insr > 0) wp::addg(V + (int64_t)C2B_V_ALL_INS_LEFT * vs + p, w);
@@ -718,6 +749,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             wp::sync();
             RowOut o; o.ins_n = o.del_n = o.sub_n = 0; o.n_ins_all = o.n_ins_win = o.n_del_all = o.n_del_win = 0;
             o.n_del_pos = o.n_sub_all = 0; o.nent = 0;
+            o.x_ins_len = o.x_ins_any = o.x_del_cnt = o.x_sub_any = o.x_splice = 0;
             c2b_edit *ed = P.edits ? P.edits + (rd * P.n_refs + r) * (int64_t)P.edit_cap : nullptr;
             const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
                        ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
@@ -735,9 +767,42 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
                 const bool discard = two_scans && (o.del_n > 0 || o.ins_n > 0);
                 if (discard) { if (lane == 0) wp::addg(SC + C2B_S_DISCARDED, w); }
                 else {
-                    const bool lenv = modified && (o.n_ins_win > 0 || o.n_del_win > 0);
-                    if (two_scans || lenv) rows_run(P, R, rowinfo, rowins, o, nullptr, w, (two_scans ? RM_VEC : 0) | (lenv ? RM_LEN : 0));
+                    // the block of CRISPRessoCORE.py:4085-4171 is entered by modified reads, and by every read of a reference
+                    // whose exons changed length (tot_exon_len_mod != 0)
+                    const bool entered = modified || R.tem != 0;
+                    const bool lenv = entered && (o.n_ins_win > 0 || o.n_del_win > 0);
+                    // --coding_seq (:4117-4171); lane 0 adds the counters below
+                    int frame_slot = -1, frame_row = 0, frame_key = 0; bool noncod = false;
+                    if (R.coding && entered) {
+                        const int lm = o.x_ins_len - o.x_del_cnt;                 // sum(length_modified_positions_exons)
+                        const bool exmod = o.x_ins_any || o.x_del_cnt > 0 || o.x_sub_any;
+                        if (R.tem != 0 || (exmod && (o.x_ins_any || o.x_del_cnt > 0))) {
+                            frame_key = lm + R.tem;
+                            const bool inframe = frame_key % 3 == 0;
+                            frame_slot = inframe ? C2B_S_MOD_NON_FRAMESHIFT : C2B_S_MOD_FRAMESHIFT;
+                            frame_row = inframe ? C2B_H_INFRAME : C2B_H_FRAMESHIFT;
+                        } else if (exmod) { frame_slot = C2B_S_MOD_NON_FRAMESHIFT; frame_row = C2B_H_INFRAME; frame_key = 0; }
+                        else {
+                            frame_slot = C2B_S_NON_MOD_NON_FRAMESHIFT; frame_row = C2B_H_INFRAME; frame_key = 0;
+                            noncod = o.n_ins_win > 0 || o.n_del_win > 0 || o.sub_n > 0;
+                        }
+                    }
+                    if (two_scans || lenv || noncod)
+                        rows_run(P, R, rowinfo, rowins, o, nullptr, w, (two_scans ? RM_VEC : 0) | (lenv ? RM_LEN : 0) | (noncod ? RM_NONCOD : 0));
                     if (lane == 0) {
+                        unsigned long long *H = R.hist;
+                        const int hs = P.hstride;
+                        // Counters keyed by size (:4020-4043); the commonest bucket (0 / len(ref)) is implied, see c2b200.h
+                        if (!ign_i && o.ins_n > 0) wp::addg(H + (int64_t)C2B_H_INS_N * hs + o.ins_n, w);
+                        if (!ign_d && o.del_n > 0) wp::addg(H + (int64_t)C2B_H_DEL_N * hs + o.del_n, w);
+                        if (!ign_s && o.sub_n > 0) wp::addg(H + (int64_t)C2B_H_SUB_N * hs + o.sub_n, w);
+                        const int eff = R.I + (ign_i ? 0 : o.ins_n) - (ign_d ? 0 : o.del_n);
+                        if (eff != R.I) wp::addg(H + (int64_t)C2B_H_EFF_LEN * hs + eff, w);
+                        if (frame_slot >= 0) {
+                            wp::addg(SC + frame_slot, w);
+                            wp::addg(H + (int64_t)frame_row * hs + R.hist_zero + frame_key, w);
+                            if (o.x_splice) wp::addg(SC + C2B_S_SPLICING_MODIFIED, w);
+                        }
                         wp::addg(SC + C2B_S_TOTAL, w);
                         wp::addg(SC + (modified ? C2B_S_MODIFIED : C2B_S_UNMODIFIED), w);
                         if (has_i) wp::addg(SC + C2B_S_INS, w);
@@ -750,6 +815,9 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
                     }
                 }
             } else if (ambiguous && nth == 0 && w > 0 && lane == 0) wp::addg(SC + C2B_S_AMBIGUOUS_W, w);
+            // class_counts (:3984-3986): the class of a read with one label is its first winner's
+            if (nth == 0 && w > 0 && !ambiguous && lane == 0 && !(expand && rec.n_winners > 1))
+                wp::addg(SC + (modified ? C2B_S_CLASS_MODIFIED : C2B_S_CLASS_UNMODIFIED), w);
             if (lane == 0) {
                 c2b_aln_rec a = multi ? load_aln(P.alns + rd * P.n_refs + r) : a_single;   // single reference: still in registers
                 a.insertion_n = (uint16_t)o.ins_n; a.deletion_n = (uint16_t)o.del_n; a.substitution_n = (uint16_t)o.sub_n;
@@ -793,6 +861,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
                 wp::sync();
                 RowOut dummy; dummy.ins_n = dummy.del_n = dummy.sub_n = 0; dummy.n_ins_all = dummy.n_ins_win = 0;
                 dummy.n_del_all = dummy.n_del_win = dummy.n_del_pos = dummy.n_sub_all = 0; dummy.nent = 0;
+                dummy.x_ins_len = dummy.x_ins_any = dummy.x_del_cnt = dummy.x_sub_any = dummy.x_splice = 0;
                 for (int r = 1; r < r_end; r++) {
                     if (!((eff >> (r & 31)) & 1u)) continue;
                     rows_run(P, R0, rowinfo, rowins, dummy, nullptr, w, RM_REF1, P.refs[r].vec);

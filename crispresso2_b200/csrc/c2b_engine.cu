@@ -152,7 +152,7 @@ struct c2b_engine {
     std::string err;
     bool configured = false;
     c2b_params prm;
-    int n_refs = 0, max_I = 0, max_nrb = 1, vstride = 0;
+    int n_refs = 0, max_I = 0, max_nrb = 1, vstride = 0, hstride = 0, hist_zero = 0;
     std::vector<RefHost> refs;
     std::vector<RefDev> refdev;         // host mirror (device pointers inside)
     void *d_tables = nullptr; RefDev *d_refs = nullptr;
@@ -296,7 +296,7 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
         const int nrb = (rf.len + 255) / 256, Ipad = nrb * 256;
         max_nrb = std::max(max_nrb, nrb);
         base[r] = bytes;
-        bytes += al((size_t)p->nq * Ipad * 4) + 2 * al((size_t)Ipad * 4) + 2 * al(Ipad) + al(Ipad + 1) + al((size_t)(Ipad + 2) * 2);
+        bytes += al((size_t)p->nq * Ipad * 4) + 2 * al((size_t)Ipad * 4) + 2 * al(Ipad) + al(Ipad + 1) + 3 * al((size_t)(Ipad + 2) * 2);
         bytes += al((size_t)p->nq * p->nq * Ipad * 4) + 2 * al((size_t)Ipad * 4);      // packed-path tables
     }
     const size_t refs_off = bytes;
@@ -305,7 +305,16 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
     if (e->d_tables) { rt_free(e->d_tables); e->d_tables = nullptr; }
     RTCHK(rt_malloc(&e->d_tables, bytes));
     e->vstride = (maxI + 31) & ~31;
-    e->counts_n = (size_t)n_refs * (C2B_NVEC * (size_t)e->vstride + C2B_NSCAL);
+    {   // histogram buckets: sizes 0..I, effective lengths 0..I+J, frame keys -I+tem..J+tem around hist_zero
+        int max_tem = 0;
+        for (int r = 0; r < n_refs; r++) max_tem = std::max(max_tem, std::abs((int)refs[r].tot_exon_len_mod));
+        if (max_tem > 4 * C2B_MAX_REF_LEN) return fail(e, C2B_E_LIMIT, "c2b_configure: tot_exon_len_mod out of range");
+        e->hist_zero = maxI + max_tem;
+        const int need = std::max(e->hist_zero + C2B_MAX_READ_LEN + max_tem, std::min(maxI + C2B_MAX_READ_LEN, C2B_MAX_ALN_LEN)) + 1;
+        e->hstride = (need + 31) & ~31;
+    }
+    const size_t per_ref = C2B_NVEC * (size_t)e->vstride + C2B_NHIST * (size_t)e->hstride + C2B_NSCAL;
+    e->counts_n = (size_t)n_refs * per_ref;
     if (e->d_counts) { rt_free(e->d_counts); e->d_counts = nullptr; }
     RTCHK(rt_malloc((void **)&e->d_counts, e->counts_n * 8));
     RTCHK(rt_zero(e->d_counts, e->counts_n * 8, e->stream));
@@ -326,6 +335,8 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
         uint8_t *rcode = hb + o; d.rcode = db + o; o += al(Ipad);
         uint8_t *incl = hb + o; d.incl = db + o; o += al(Ipad + 1);
         uint16_t *cum = (uint16_t *)(hb + o); d.cum = (const uint16_t *)(db + o); o += al((size_t)(Ipad + 2) * 2);
+        uint16_t *cumx = (uint16_t *)(hb + o); d.cumx = (const uint16_t *)(db + o); o += al((size_t)(Ipad + 2) * 2);
+        uint16_t *cums = (uint16_t *)(hb + o); d.cums = (const uint16_t *)(db + o); o += al((size_t)(Ipad + 2) * 2);
         uint32_t *prof2 = (uint32_t *)(hb + o); d.prof2 = (const uint32_t *)(db + o); o += al((size_t)p->nq * p->nq * Ipad * 4);
         uint32_t *cIe2 = (uint32_t *)(hb + o); d.cIe2 = (const uint32_t *)(db + o); o += al((size_t)Ipad * 4);
         uint32_t *g42 = (uint32_t *)(hb + o); d.g42 = (const uint32_t *)(db + o); o += al((size_t)Ipad * 4);
@@ -392,6 +403,14 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
         }
         cum[0] = 0;
         for (int q = 0; q <= Ipad; q++) cum[q + 1] = (uint16_t)(cum[q] + (q < I && incl[q] ? 1 : 0));
+        d.coding = rf.coding_mask != nullptr; d.tem = rf.tot_exon_len_mod; d.hist_zero = e->hist_zero;
+        if (rf.coding_mask)
+            for (int q = 0; q < I; q++) incl[q] |= (uint8_t)((rf.coding_mask[q] & 3) << 1);   // after cum[]: bit 0 stays the window
+        cumx[0] = cums[0] = 0;
+        for (int q = 0; q <= Ipad; q++) {
+            cumx[q + 1] = (uint16_t)(cumx[q] + (q < I && (incl[q] & 2) ? 1 : 0));
+            cums[q + 1] = (uint16_t)(cums[q] + (q < I && (incl[q] & 4) ? 1 : 0));
+        }
         const int ns = std::min({(int)rf.n_seeds, (int)p->seed_count, (int)C2B_MAX_SEEDS});
         if (rf.n_seeds > 0 && std::min((int)rf.n_seeds, (int)p->seed_count) > C2B_MAX_SEEDS)
             return fail(e, C2B_E_LIMIT, "c2b_configure: more seeds than C2B_MAX_SEEDS");
@@ -404,8 +423,9 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
             d.seed_len = (int)f.size();
             d.fw_seed[s] = pack_seed(*p, f); d.rc_seed[s] = pack_seed(*p, c);
         }
-        d.vec = e->d_counts + (size_t)r * (C2B_NVEC * (size_t)e->vstride + C2B_NSCAL);
-        d.scal = d.vec + C2B_NVEC * (size_t)e->vstride;
+        d.vec = e->d_counts + (size_t)r * per_ref;
+        d.hist = d.vec + C2B_NVEC * (size_t)e->vstride;
+        d.scal = d.hist + C2B_NHIST * (size_t)e->hstride;
     }
     memcpy(blob.data() + refs_off, e->refdev.data(), sizeof(RefDev) * n_refs);
     e->d_refs = (RefDev *)((unsigned char *)e->d_tables + refs_off);
@@ -511,7 +531,7 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     P.bnd = (int32_t *)e->bnd.p; P.bnd_words_per_warp = 2 * 3 * (int64_t)P.TS;
     P.opsbuf = (uint64_t *)e->ops.p;
     P.work_counter = (unsigned long long *)e->work.p;
-    P.vstride = e->vstride;
+    P.vstride = e->vstride; P.hstride = e->hstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
     P.phase_sync = 4;                                     // warps per phase set (C2B_PHASE_WARPS: 0/1 = free-running, 2, 4, 8)
     if (const char *v = getenv("C2B_PHASE_WARPS")) { const int k = atoi(v), a = k < 0 ? -k : k; P.phase_sync = (a == 2 || a == 4 || a == 8 || a == 16) ? k : 0; }
@@ -739,6 +759,15 @@ int c2b_counts_layout(const c2b_engine *e, int32_t *n_refs, int32_t *n_vec, int3
     if (n_vec) *n_vec = C2B_NVEC;
     if (stride) *stride = e->vstride;
     if (n_scal) *n_scal = C2B_NSCAL;
+    return C2B_OK;
+}
+
+int c2b_counts_hist_layout(const c2b_engine *e, int32_t *n_hist, int32_t *hstride, int32_t *hist_zero)
+{
+    if (!e || !e->configured) return C2B_E_STATE;
+    if (n_hist) *n_hist = C2B_NHIST;
+    if (hstride) *hstride = e->hstride;
+    if (hist_zero) *hist_zero = e->hist_zero;
     return C2B_OK;
 }
 

@@ -116,12 +116,23 @@ class Engine:
             arr[k].min_aln_score = float(ref.get("min_aln_score", 0))
             arr[k].score_rows = rows.ctypes.data
             arr[k].fw_seeds, arr[k].rc_seeds, arr[k].n_seeds = fw, rc, ns
-            keep.append((sb, gi, inc, rows, fw, rc))
+            # --coding_seq inputs of the quantification loop (CRISPRessoCORE.py:4083-4087); absent keys = no coding sequence
+            arr[k].tot_exon_len_mod = int(sum(ref.get("exon_len_mods", []) or []))
+            cmask = None
+            if ref.get("contains_coding_seq", False):
+                cmask = np.zeros(len(sb), dtype=np.uint8)
+                ex = np.asarray(sorted(set(ref.get("exon_positions", []))), dtype=np.int64)
+                sp = np.asarray(sorted(set(ref.get("splicing_positions", []))), dtype=np.int64)
+                cmask[ex[(ex >= 0) & (ex < len(sb))]] |= 1
+                cmask[sp[(sp >= 0) & (sp < len(sb))]] |= 2
+                arr[k].coding_mask = cmask.ctypes.data
+            keep.append((sb, gi, inc, rows, fw, rc, cmask))
         self._check(self.L.c2b_configure(self.h, C.byref(p), len(ref_names), arr), "c2b_configure")
         self.n_refs, self.alphabet, self.edit_cap = len(ref_names), alphabet, int(edit_cap)
         self.ref_names = list(ref_names)
         self.ref_lens = [len(refs[n]["sequence"]) for n in ref_names]
         self.ref_seqs = [refs[n]["sequence"] for n in ref_names]
+        self.flags = int(flags)
         return self
 
     def set_edit_cap(self, cap):
@@ -191,9 +202,15 @@ class Engine:
     def counts_reset(self):
         self._check(self.L.c2b_counts_reset(self.h), "c2b_counts_reset")
 
+    def hist_layout(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self.L.c2b_counts_hist_layout(self.h, C.byref(a), C.byref(b), C.byref(c)), "c2b_counts_hist_layout")
+        return a.value, b.value, c.value
+
     def counts_raw(self):
         nr, nv, st, ns = self.counts_layout()
-        out = np.zeros(nr * (nv * st + ns), dtype=np.int64)
+        nh, hs, _ = self.hist_layout()
+        out = np.zeros(nr * (nv * st + nh * hs + ns), dtype=np.int64)
         self._check(self.L.c2b_counts_read(self.h, out.ctypes.data, out.size), "c2b_counts_read")
         return out
 
@@ -207,7 +224,8 @@ class Engine:
         from .counts import CountBlock
         nr, nv, st, ns = self.counts_layout()
         raw = self.counts_raw() if raw is None else np.asarray(raw, dtype=np.int64)
-        return CountBlock(raw, self.ref_names, self.ref_seqs, self.alphabet, nv, st, ns)
+        nh, hs, hz = self.hist_layout()
+        return CountBlock(raw, self.ref_names, self.ref_seqs, self.alphabet, nv, st, ns, nh, hs, hz, self.flags)
 
     def sync(self):
         self._check(self.L.c2b_sync(self.h), "c2b_sync")

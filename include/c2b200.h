@@ -72,6 +72,10 @@ typedef struct {
     const char *const *fw_seeds;   /* refs[name]['fw_seeds'][:seed_count] */
     const char *const *rc_seeds;   /* refs[name]['rc_seeds'][:seed_count] */
     int32_t        n_seeds;
+    /* --coding_seq quantification (CRISPRessoCORE.py:4083-4180); all optional */
+    int32_t        tot_exon_len_mod;   /* sum(refs[name]['exon_len_mods']) */
+    const uint8_t *coding_mask;    /* NULL when refs[name]['contains_coding_seq'] is false; else [len] bytes:
+                                      bit 0 = position in refs[name]['exon_positions'], bit 1 = in ['splicing_positions'] */
 } c2b_ref;
 
 /* Per (read, reference) alignment result: what global_align returns (Align.pyx:422-434) plus, when the
@@ -119,8 +123,9 @@ typedef struct {
     uint8_t  pad;
 } c2b_edit;
 
-/* Count block: int64 [n_refs][C2B_NVEC][stride] followed by [n_refs][C2B_NSCAL] scalars.
- * Vectors follow CRISPRessoCORE.py:3865-3896 / the table in SURVEY.md 3.4. */
+/* Count block: per reference r one chunk of int64: [C2B_NVEC][stride] vectors, [C2B_NHIST][hstride] histograms,
+ * [C2B_NSCAL] scalars; chunks follow each other.  Vectors follow CRISPRessoCORE.py:3865-3896 / the table in
+ * SURVEY.md 3.4. */
 enum {
     C2B_V_ALL_INS = 0, C2B_V_ALL_INS_LEFT, C2B_V_ALL_DEL, C2B_V_ALL_SUB,
     C2B_V_INS, C2B_V_DEL, C2B_V_SUB,
@@ -132,7 +137,22 @@ enum {
      * reference-0 positions (ref1_all_*_count_vectors[this ref], CRISPRessoCORE.py:4255-4272) */
     C2B_V_R1_ALL_INS, C2B_V_R1_ALL_INS_LEFT, C2B_V_R1_ALL_DEL, C2B_V_R1_ALL_SUB,
     C2B_V_R1_BASEDEV0,                 /* + code (nq = '-'): deviation from "read == reference-0 base" */
-    C2B_NVEC = C2B_V_R1_BASEDEV0 + C2B_MAX_Q + 1
+    /* --coding_seq: window edits of modified reads that touch no exon (CRISPRessoCORE.py:4166-4171) */
+    C2B_V_INS_NONCODING = C2B_V_R1_BASEDEV0 + C2B_MAX_Q + 1, C2B_V_DEL_NONCODING, C2B_V_SUB_NONCODING,
+    C2B_NVEC
+};
+/* Histograms keyed by a small integer (the reference's Counters, CRISPRessoCORE.py:3898-3906).  Bucket index =
+ * key for the first four rows, key + hist_zero for the two frame rows.  The most common bucket of the first four rows
+ * is NOT stored (it would be one hot address for every unedited read): key 0 of INS_N / DEL_N / SUB_N and key
+ * len(ref) of EFF_LEN equal counts_total minus the sum of the stored buckets (crispresso2_b200/counts.py). */
+enum {
+    C2B_H_INS_N = 0,       /* inserted_n_dicts[ref][insertion_n]        (:4020, unless ignore_insertions)    */
+    C2B_H_DEL_N,           /* deleted_n_dicts[ref][deletion_n]          (:4031, unless ignore_deletions)     */
+    C2B_H_SUB_N,           /* substituted_n_dicts[ref][substitution_n]  (:4043, unless ignore_substitutions) */
+    C2B_H_EFF_LEN,         /* effective_len_dicts[ref][len - deletion_n + insertion_n]   (:4037)             */
+    C2B_H_INFRAME,         /* hists_inframe[ref][effective_length]      (:4144-4177)                         */
+    C2B_H_FRAMESHIFT,      /* hists_frameshift[ref][effective_length]                                        */
+    C2B_NHIST
 };
 enum {
     C2B_S_TOTAL = 0, C2B_S_MODIFIED, C2B_S_UNMODIFIED, C2B_S_DISCARDED,
@@ -143,6 +163,12 @@ enum {
     C2B_S_N_GLOBAL_SUBS, C2B_S_N_SUBS_OUTSIDE_WINDOW, C2B_S_N_MODS_IN_WINDOW, C2B_S_N_MODS_OUTSIDE_WINDOW,
     C2B_S_N_READS_IRREGULAR_ENDS, C2B_S_N_ALIGNED_UNIQUE, C2B_S_N_ALIGNED_COUNT,
     C2B_S_REF1_W,          /* weight re-projected onto reference 0 for this reference (C2B_F_HDR_REF1) */
+    /* class_counts (CRISPRessoCORE.py:3984-3986) of reads whose class_name is "<this ref>_MODIFIED" / "_UNMODIFIED"
+     * (one best reference, or several with assign-first); "AMBIGUOUS" = sum of C2B_S_AMBIGUOUS_W; the joined labels of
+     * --expand_ambiguous_alignments reads with several best references are derived from the read records on the host */
+    C2B_S_CLASS_MODIFIED, C2B_S_CLASS_UNMODIFIED,
+    /* --coding_seq counters (:4134-4171) */
+    C2B_S_MOD_FRAMESHIFT, C2B_S_MOD_NON_FRAMESHIFT, C2B_S_NON_MOD_NON_FRAMESHIFT, C2B_S_SPLICING_MODIFIED,
     C2B_NSCAL
 };
 
@@ -207,6 +233,9 @@ int  c2b_ring_counts(c2b_engine *e, int64_t *ring_pairs, int64_t *ring_fallbacks
 /* replaces: the count vectors / counters built by the quantification loop (CRISPRessoCORE.py:3841-3907,
  * :3964-4115).  Layout above.  c2b_counts_device exposes the block for an NCCL all-reduce.            */
 int  c2b_counts_layout(const c2b_engine *e, int32_t *n_refs, int32_t *n_vec, int32_t *stride, int32_t *n_scal);
+/* histogram section of each reference's chunk: C2B_NHIST rows of hstride buckets; hist_zero = bucket of key 0 in the
+ * two frame rows */
+int  c2b_counts_hist_layout(const c2b_engine *e, int32_t *n_hist, int32_t *hstride, int32_t *hist_zero);
 int  c2b_counts_reset(c2b_engine *e);
 int  c2b_counts_read(c2b_engine *e, int64_t *out, size_t n_int64);
 int  c2b_counts_device(c2b_engine *e, void **d_ptr, size_t *n_int64);

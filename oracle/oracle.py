@@ -361,19 +361,30 @@ VECTOR_NAMES = [
     "all_base_count_A", "all_base_count_C", "all_base_count_G", "all_base_count_T", "all_base_count_N",
     "all_base_count_-",
     "insertion_length", "deletion_length",
+    "insertion_count_noncoding", "deletion_count_noncoding", "substitution_count_noncoding",
 ]
 SCALAR_NAMES = ["counts_total", "counts_modified", "counts_unmodified", "counts_discarded", "counts_insertion",
                 "counts_deletion", "counts_substitution", "counts_only_insertion", "counts_only_deletion",
                 "counts_only_substitution", "counts_insertion_and_deletion", "counts_insertion_and_substitution",
-                "counts_deletion_and_substitution", "counts_insertion_and_deletion_and_substitution"]
+                "counts_deletion_and_substitution", "counts_insertion_and_deletion_and_substitution",
+                "counts_modified_frameshift", "counts_modified_non_frameshift", "counts_non_modified_non_frameshift",
+                "counts_splicing_sites_modified"]
 
 
-def count_vectors(cache, refs, ref_names, params):
-    """Quantification loop (CRISPRessoCORE.py:3964-4081 + :4104-4115): per-position vectors and scalar
-    counters.  Mutates cache[...]['count'] through the reverse-complement merge exactly like the reference.
-    -> (vectors[ref][name] float64 arrays, scalars[ref][name] ints, class_counts, N_TOTAL)"""
+def count_vectors(cache, refs, ref_names, params, extras=None):
+    """Quantification loop (CRISPRessoCORE.py:3964-4181): per-position vectors and scalar counters, including the
+    --coding_seq frameshift / splicing logic (:4083-4180).  Mutates cache[...]['count'] through the
+    reverse-complement merge exactly like the reference.
+    -> (vectors[ref][name] float64 arrays, scalars[ref][name] ints, class_counts, N_TOTAL)
+    If `extras` is a dict it receives extras[ref] = the reference's Counters: inserted_n, deleted_n, substituted_n,
+    effective_len (:4020-4043), hists_inframe, hists_frameshift (:3903-3906, :4134-4177)."""
+    from collections import Counter
     vec = {r: {n: np.zeros(len(refs[r]["sequence"])) for n in VECTOR_NAMES} for r in ref_names}
     sca = {r: dict.fromkeys(SCALAR_NAMES, 0) for r in ref_names}
+    ext = {r: {"inserted_n": Counter(), "deleted_n": Counter(), "substituted_n": Counter(), "effective_len": Counter(),
+               "hists_inframe": Counter({0: 0}), "hists_frameshift": Counter({0: 0})} for r in ref_names}
+    if extras is not None:
+        extras.update(ext)
     classes = {}
     total = 0
     for s in cache:
@@ -401,19 +412,27 @@ def count_vectors(cache, refs, ref_names, params):
             has_i = has_d = has_s = False
             V["all_insertion_count"][p["all_insertion_positions"]] += c        # repeated index counted once
             V["all_insertion_left_count"][p["all_insertion_left_positions"]] += c
+            X = ext[r]
+            eff_len = len(refs[r]["sequence"])
             if not params.ignore_insertions:
+                X["inserted_n"][p["insertion_n"]] += c
+                eff_len += p["insertion_n"]
                 V["insertion_count"][p["insertion_positions"]] += c
                 if p["insertion_n"] > 0:
                     S["counts_insertion"] += c
                     has_i = True
             V["all_deletion_count"][p["all_deletion_positions"]] += c
             if not params.ignore_deletions:
+                X["deleted_n"][p["deletion_n"]] += c
+                eff_len -= p["deletion_n"]
                 V["deletion_count"][p["deletion_positions"]] += c
                 if p["deletion_n"] > 0:
                     S["counts_deletion"] += c
                     has_d = True
+            X["effective_len"][eff_len] += c
             V["all_substitution_count"][p["all_substitution_positions"]] += c
             if not params.ignore_substitutions:
+                X["substituted_n"][p["substitution_n"]] += c
                 V["substitution_count"][p["substitution_positions"]] += c
                 if p["substitution_n"] > 0:
                     S["counts_substitution"] += c
@@ -431,12 +450,61 @@ def count_vectors(cache, refs, ref_names, params):
             for ch, rp in zip(p["aln_seq"], p["ref_positions"]):
                 if rp >= 0:
                     V["all_base_count_" + ch][rp] += c
-            if has_i or has_d or has_s:
+            # :4083-4180.  (The `elif tot_exon_len_mod != 0` arm at :4173 is unreachable: the `if` above it already
+            # holds `or tot_exon_len_mod != 0`.)
+            tem = sum(refs[r].get("exon_len_mods", []) or [])
+            if has_i or has_d or has_s or tem != 0:
+                coding = refs[r].get("contains_coding_seq", False)
+                exons = set(refs[r].get("exon_positions", []))
+                splice = set(refs[r].get("splicing_positions", []))
+                len_mods = []
+                exons_modified = spliced = False
                 for (a, b), sz in zip(p["insertion_coordinates"], p["insertion_sizes"]):
                     V["insertion_length"][a] += sz * c
                     V["insertion_length"][b] += sz * c
+                    if coding and exons.intersection((a, b)):
+                        exons_modified = True
+                        len_mods.append(sz)
                 for (a, b), sz in zip(p["deletion_coordinates"], p["deletion_sizes"]):
                     V["deletion_length"][list(range(a, b))] += sz * c
+                if coding:
+                    hit = exons.intersection(p["deletion_positions"])
+                    if hit:
+                        exons_modified = True
+                        len_mods.append(-len(hit))
+                    if exons.intersection(p["substitution_positions"]):
+                        exons_modified = True
+                    if (splice.intersection(p["deletion_positions"]) or splice.intersection(p["insertion_positions"])
+                            or splice.intersection(p["substitution_positions"])):
+                        spliced = True
+                    if spliced:
+                        S["counts_splicing_sites_modified"] += c
+                    if tem != 0:
+                        eff = sum(len_mods) + tem
+                        if eff % 3 == 0:
+                            S["counts_modified_non_frameshift"] += c
+                            X["hists_inframe"][eff] += c
+                        else:
+                            S["counts_modified_frameshift"] += c
+                            X["hists_frameshift"][eff] += c
+                    elif exons_modified:
+                        if not len_mods:
+                            S["counts_modified_non_frameshift"] += c
+                            X["hists_inframe"][0] += c
+                        else:
+                            eff = sum(len_mods)
+                            if eff % 3 == 0:
+                                S["counts_modified_non_frameshift"] += c
+                                X["hists_inframe"][eff] += c
+                            else:
+                                S["counts_modified_frameshift"] += c
+                                X["hists_frameshift"][eff] += c
+                    else:
+                        S["counts_non_modified_non_frameshift"] += c
+                        V["insertion_count_noncoding"][p["insertion_positions"]] += c
+                        V["deletion_count_noncoding"][p["deletion_positions"]] += c
+                        V["substitution_count_noncoding"][p["substitution_positions"]] += c
+                        X["hists_inframe"][0] += c
     return vec, sca, classes, total
 
 

@@ -77,28 +77,43 @@ def main():
                                      ("counts_insertion", "counts_insertion"), ("counts_deletion", "counts_deletion"),
                                      ("counts_substitution", "counts_substitution")):
                     cmp(r + ":" + theirs, [S[ours]], [kw[theirs][r]])
-                if hasattr(blk, "extras"):
-                    X = blk.extras(r, kw["args"], kw["refs"][r] if r in kw["refs"] else None)
-                    for theirs, got in X.items():
-                        want = kw[theirs][r]
-                        if isinstance(want, dict) or hasattr(want, "items"):
-                            report["checked"] += 1
-                            w = {int(k): int(v) for k, v in want.items() if v != 0}
-                            g = {int(k): int(v) for k, v in got.items() if v != 0}
-                            if w != g:
-                                bad.append(r + ":" + theirs)
-                        else:
-                            cmp(r + ":" + theirs, np.atleast_1d(got), np.atleast_1d(want))
+                for ours, theirs in (("insertion_count_noncoding", "insertion_count_vectors_noncoding"),
+                                     ("deletion_count_noncoding", "deletion_count_vectors_noncoding"),
+                                     ("substitution_count_noncoding", "substitution_count_vectors_noncoding")):
+                    cmp(r + ":" + theirs, V[ours], kw[theirs][r])
+                for name in ("counts_modified_frameshift", "counts_modified_non_frameshift",
+                             "counts_non_modified_non_frameshift", "counts_splicing_sites_modified"):
+                    cmp(r + ":" + name, [S[name]], [kw[name][r]])
+                if S["counts_total"] > 0:                   # length vectors leave main() as per-position means (:4394-4404)
+                    for ln, ct, theirs in (("insertion_length", "insertion_count", "insertion_length_vectors"),
+                                           ("deletion_length", "deletion_count", "deletion_length_vectors")):
+                        mean = np.zeros(len(V[ln]))
+                        mask = V[ct] > 0
+                        mean[mask] = V[ln][mask] / V[ct][mask]
+                        cmp(r + ":" + theirs, mean, kw[theirs][r])
+                inframe, frameshift = blk.frame_histograms(r)
+                for got, theirs in ((inframe, "hists_inframe"), (frameshift, "hists_frameshift")):
+                    report["checked"] += 1
+                    if dict(got) != {int(k): int(v) for k, v in kw[theirs][r].items()}:
+                        bad.append(r + ":" + theirs)
+                # the size Counters leave main() only as the plot arrays of :4348-4377
+                H = blk.size_histograms(r)
+                rr = kw["refs"][r]
+                for key, xs, ys in (("substituted_n", "x_bins_mut", "y_values_mut"), ("inserted_n", "x_bins_ins", "y_values_ins"),
+                                    ("deleted_n", "x_bins_del", "y_values_del")):
+                    cmp(r + ":" + ys, [H[key][int(x)] for x in rr[xs]], rr[ys])
+                    cmp(r + ":" + xs, np.arange(max(15, max(list(H[key].keys()) or [0])) + 1), rr[xs])
+                L = len(rr["sequence"])
+                cmp(r + ":hdensity", [H["effective_len"][int(x) + L] for x in rr["hlengths"]], rr["hdensity"])
                 if "ref1_all_deletion_count_vectors" in kw and kw["ref1_all_deletion_count_vectors"]:
                     R1 = blk.vectors_ref1(r)
                     for k in ("insertion", "insertion_left", "deletion", "substitution", "indelsub"):
                         cmp(r + ":ref1_all_%s" % k, R1["ref1_all_%s_count" % k], kw["ref1_all_%s_count_vectors" % k][r])
                     for ch in "ACGTN-":
                         cmp(r + ":ref1_base_" + ch, R1["ref1_all_base_count_" + ch], kw["ref1_all_base_count_vectors"][r + "_" + ch])
-            if hasattr(blk, "class_counts"):
-                report["checked"] += 1
-                if dict(blk.class_counts()) != {k: int(v) for k, v in kw["class_counts"].items()}:
-                    bad.append("class_counts")
+            report["checked"] += 1
+            if dict(blk.class_counts()) != {k: int(v) for k, v in kw["class_counts"].items()}:
+                bad.append("class_counts")
             return orig_ctx(*a, **kw)
 
         CORE.CorePlotContext = ctx_spy

@@ -103,8 +103,10 @@ def check_against_oracle(engine, refs, ref_names, params, reads, matrix):
         for r in want["aln_ref_names"]:
             bad = G.payload_equal(want["variant_" + r], got["variant_" + r])
             assert not bad, (s, r, bad)
-    vec, sca, classes, total = O.count_vectors(cache_o, refs, ref_names, params)
+    extras = {}
+    vec, sca, classes, total = O.count_vectors(cache_o, refs, ref_names, params, extras)
     block = core.quantify(cache)
+    assert block.class_counts() == classes, (block.class_counts(), classes)
     for r in ref_names:
         V = block.vectors(r)
         for name in O.VECTOR_NAMES:
@@ -112,6 +114,12 @@ def check_against_oracle(engine, refs, ref_names, params, reads, matrix):
         S = block.scalars(r)
         for name in O.SCALAR_NAMES:
             assert S[name] == sca[r][name], (r, name, S[name], sca[r][name])
+        H = block.size_histograms(r)
+        for name in ("inserted_n", "deleted_n", "substituted_n", "effective_len"):
+            assert dict(H[name]) == dict(extras[r][name]), (r, name, H[name], extras[r][name])
+        inframe, frameshift = block.frame_histograms(r)
+        assert dict(inframe) == dict(extras[r]["hists_inframe"]), (r, inframe, extras[r]["hists_inframe"])
+        assert dict(frameshift) == dict(extras[r]["hists_frameshift"]), (r, frameshift, extras[r]["hists_frameshift"])
     if getattr(params, "expected_hdr_amplicon_seq", ""):
         want = O.ref1_vectors(cache_o, refs, ref_names, params)
         for r in ref_names[1:]:
@@ -250,3 +258,35 @@ def check_ring_equals_full(engine, n=96, I=250, seed=41, oracle_subset=0):
     if oracle_subset:
         check_against_oracle(engine, {"Reference": ref}, ["Reference"], O.Params(), reads[:oracle_subset], O.make_matrix())
     return ra
+
+
+def check_coding_seq(engine, n_reads=60, seed=9):
+    """--coding_seq quantification (CRISPRessoCORE.py:4083-4180): exon / splicing position sets, a second reference
+    whose exons changed length (tot_exon_len_mod != 0), wide window so that window edits fall in and out of the exons."""
+    from crispresso2_b200 import synth
+    rng = np.random.default_rng(seed)
+    amp = synth.random_amplicon(rng, 160)
+    hdr = amp[:70] + "TG" + amp[70:]                       # HDR allele: 2-bp insertion inside the first exon
+    wt = synth.amplicon_setup(amp, guide_start=55, window_size=25)
+    hd = synth.amplicon_setup(hdr, guide_start=55, window_size=25)
+    exon = list(range(40, 82)) + list(range(110, 130))
+    wt.update(contains_coding_seq=True, exon_positions=exon, exon_len_mods=[0, 0],
+              splicing_positions=[38, 39, 82, 83, 108, 109, 130, 131])
+    exon_h = list(range(40, 84)) + list(range(112, 132))
+    hd.update(contains_coding_seq=True, exon_positions=exon_h, exon_len_mods=[2, 0],
+              splicing_positions=[38, 39, 84, 85, 110, 111, 132, 133])
+    refs = {"WT": wt, "HDR": hd}
+    reads = []
+    for a, cut in ((amp, wt["cut_point"]), (hdr, hd["cut_point"])):
+        reads += [r.tobytes().decode() for r in synth.synth_reads(rng, a, n_reads, len(a), sub_rate=0.02, rc_frac=0.1,
+                                                                    del_frac=0.35, ins_frac=0.25, cut=cut)]
+    m = O.make_matrix()
+    for kw in ({"expected_hdr_amplicon_seq": hdr}, {"expected_hdr_amplicon_seq": hdr, "ignore_substitutions": True},
+               {"expected_hdr_amplicon_seq": hdr, "discard_indel_reads": True},
+               {"expected_hdr_amplicon_seq": hdr, "ignore_insertions": True, "ignore_deletions": True}):
+        check_against_oracle(engine, refs, ["WT", "HDR"], O.Params(**kw), reads, m)
+    far = {"WT": dict(wt, exon_positions=list(range(5, 30)) + list(range(135, 150)), splicing_positions=[3, 4, 30, 31, 62, 63])}
+    check_against_oracle(engine, far, ["WT"], O.Params(), reads[:n_reads], m)    # edits near the cut touch no exon
+    nc = {"WT": dict(wt, contains_coding_seq=False, exon_positions=[], exon_len_mods=[], splicing_positions=[])}
+    check_against_oracle(engine, {"WT": wt}, ["WT"], O.Params(), reads[:n_reads], m)
+    check_against_oracle(engine, nc, ["WT"], O.Params(), reads[:n_reads], m)

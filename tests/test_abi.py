@@ -38,7 +38,7 @@ def test_missing_library_fails_loudly(tmp_path):
 def test_struct_sizes_match_header():
     from crispresso2_b200 import _lib
     assert _lib.ALN_DTYPE.itemsize == 32 and _lib.REC_DTYPE.itemsize == 16 and _lib.EDIT_DTYPE.itemsize == 8
-    assert _lib.NVEC == 39 and _lib.NSCAL == 23
+    assert _lib.NVEC == 42 and _lib.NSCAL == 29 and _lib.NHIST == 6
 
 
 def test_sass_is_sm100a_with_dpx_ops():

@@ -169,3 +169,7 @@ def test_long_amplicon_three_row_blocks(emu):
 
 def test_banded_slab_falls_back_to_full_slab(emu):
     PU.check_band_fallback(emu, n=24)
+
+
+def test_coding_seq_frameshift_splicing_and_size_histograms(emu):
+    PU.check_coding_seq(emu, n_reads=60)

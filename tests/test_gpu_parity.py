@@ -222,3 +222,7 @@ def test_long_amplicon_three_row_blocks(eng):
 
 def test_banded_slab_falls_back_to_full_slab(eng):
     PU.check_band_fallback(eng, n=3000)
+
+
+def test_coding_seq_frameshift_splicing_and_size_histograms(eng):
+    PU.check_coding_seq(eng, n_reads=400)
