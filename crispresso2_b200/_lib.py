@@ -78,7 +78,10 @@ assert ALN_DTYPE.itemsize == 32 and REC_DTYPE.itemsize == 16 and EDIT_DTYPE.item
 EXPORTS = ["c2b_create", "c2b_destroy", "c2b_last_error", "c2b_configure", "c2b_set_edit_cap", "c2b_string_width", "c2b_align_batch",
            "c2b_align_batch_device", "c2b_set_pair_order", "c2b_sync", "c2b_stream", "c2b_last_kernel_ms", "c2b_launch_count", "c2b_path_counts", "c2b_band_reruns", "c2b_ring_counts",
            "c2b_counts_layout", "c2b_counts_hist_layout", "c2b_counts_reset", "c2b_counts_read", "c2b_counts_device", "c2b_global_align",
-           "c2b_classify_aligned", "c2b_host_alloc", "c2b_host_free"]
+           "c2b_classify_aligned", "c2b_host_alloc", "c2b_host_free",
+           "c2b_fastq_dedup", "c2b_fastq_dedup_buffer", "c2b_fastq_n_reads", "c2b_fastq_n_unique", "c2b_fastq_max_len",
+           "c2b_fastq_seqs", "c2b_fastq_offsets", "c2b_fastq_counts", "c2b_fastq_first_index", "c2b_fastq_free",
+           "c2b_fastq_last_error"]
 
 _cache = {}
 
@@ -149,5 +152,18 @@ def load(path=None):
     L.c2b_host_alloc.argtypes = [C.c_size_t]
     L.c2b_host_free.restype = None
     L.c2b_host_free.argtypes = [vp]
+    L.c2b_fastq_dedup.restype = C.c_int
+    L.c2b_fastq_dedup.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+    L.c2b_fastq_dedup_buffer.restype = C.c_int
+    L.c2b_fastq_dedup_buffer.argtypes = [vp, C.c_size_t, i32, C.POINTER(vp)]
+    for name, rt in (("c2b_fastq_n_reads", i64), ("c2b_fastq_n_unique", i64), ("c2b_fastq_max_len", i32),
+                     ("c2b_fastq_seqs", vp), ("c2b_fastq_offsets", vp), ("c2b_fastq_counts", vp),
+                     ("c2b_fastq_first_index", vp)):
+        getattr(L, name).restype = rt
+        getattr(L, name).argtypes = [vp]
+    L.c2b_fastq_free.restype = None
+    L.c2b_fastq_free.argtypes = [vp]
+    L.c2b_fastq_last_error.restype = C.c_char_p
+    L.c2b_fastq_last_error.argtypes = []
     _cache[path] = L
     return L

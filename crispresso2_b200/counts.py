@@ -46,8 +46,8 @@ class CountBlock:
         out = {}
         amb = 0
         for r in self.ref_names:
-            for lab, key in (("_MODIFIED", "CLASS_MODIFIED"), ("_UNMODIFIED", "CLASS_UNMODIFIED")):
-                v = self.scalar(r, key)
+            for lab, key, base in (("_MODIFIED", "CLASS_MODIFIED", "MODIFIED"), ("_UNMODIFIED", "CLASS_UNMODIFIED", "UNMODIFIED")):
+                v = self.scalar(r, base) + self.scalar(r, key)          # counts_* plus the signed deviation (c2b200.h)
                 if v:
                     out[r + lab] = v
             amb += self.scalar(r, "AMBIGUOUS_W")

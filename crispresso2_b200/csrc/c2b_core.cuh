@@ -76,6 +76,7 @@ C2B_DEV uint32_t adds(uint32_t *p, uint32_t v)
 C2B_DEV unsigned long long fetch_work(unsigned long long *p)
 { unsigned long long o; asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(o) : "l"(__cvta_generic_to_global(p)), "l"(1ull) : "memory"); return o; }
 }  // namespace wp
+
 #else
 #include "warp_emu.h"   // provides C2B_DEV, C2B_DEVNOINL, int4/uint4 and namespace wp
 #endif
@@ -457,17 +458,16 @@ C2B_DEV int score_milli(int m, int n)
 // ------------------------------------------------------------------------------------------------ rows
 struct RowOut {
     int ins_n, del_n, sub_n, n_ins_all, n_ins_win, n_del_all, n_del_win, n_del_pos, n_sub_all, nent;
-    // --coding_seq (CRISPRessoCORE.py:4104-4131): bases inserted by window insertions with a flank in an exon, any such
-    // insertion, deleted exon positions of window deletions, any window substitution in an exon, any window edit on a
-    // splicing position
-    int x_ins_len, x_ins_any, x_del_cnt, x_sub_any, x_splice;
 };
+// --coding_seq (CRISPRessoCORE.py:4104-4131): bases inserted by window insertions with a flank in an exon, any such
+// insertion, deleted exon positions of window deletions, any window substitution in an exon, any window edit on a
+// splicing position
+struct CodOut { int ins_len, ins_any, del_cnt, sub_any, splice; };
 
 // mode bits of rows_run
 constexpr int RM_SCAL = 1;   // scalars + edit list (COREResources.pyx:108-163)
 constexpr int RM_VEC = 2;    // per-position count vectors, weight w (CRISPRessoCORE.py:4016-4081)
 constexpr int RM_LEN = 4;    // insertion/deletion length vectors (:4104-4115), only for reads that carry a modification
-constexpr int RM_NONCOD = 16; // --coding_seq: window edit positions of a modified read that touches no exon (:4166-4170)
 constexpr int RM_REF1 = 8;   // HDR re-projection (:4255-4272): the scattered alignment is the one to reference 0, the
                              // vectors updated are the ref1_* block of the reference the read was assigned to (Vt)
 
@@ -479,7 +479,6 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
     const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
                ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
     const bool scal = mode & RM_SCAL, vec = mode & RM_VEC, lenv = mode & RM_LEN, ref1 = mode & RM_REF1;
-    const bool noncod = mode & RM_NONCOD, xcod = scal && R.coding;
     unsigned long long *V = ref1 ? Vt : R.vec;
     const int vs = P.vstride;
     int open_a = -1; uint32_t prevD = 0;
@@ -497,16 +496,11 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
                 ed[o.nent] = e;
             }
             o.nent++;
-            if (xcod && hit) {                                 // exon / splicing positions in deletion_positions (:4117-4127)
-                o.x_del_cnt += (int)R.cumx[b] - (int)R.cumx[a];
-                if ((int)R.cums[b] - (int)R.cums[a] > 0) o.x_splice = 1;
-            }
         }
-        if (hit && ((vec && !ign_d) || lenv || noncod)) {
+        if (hit && ((vec && !ign_d) || lenv)) {
             for (int p = a + lane; p < b; p += 32) {
                 if (vec && !ign_d) wp::addg(V + (int64_t)C2B_V_DEL * vs + p, w);
                 if (lenv) wp::addg(V + (int64_t)C2B_V_DEL_LEN * vs + p, w * size);
-                if (noncod) wp::addg(V + (int64_t)C2B_V_DEL_NONCODING * vs + p, w);
             }
         }
     };
@@ -524,10 +518,8 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
         // a chunk in which the read equals the reference and no deletion is open has nothing to record
         if (!wp::ballot(isdel || differs || insr > 0 || insl > 0) && !prevD) continue;
         const bool issub = differs && readc != 'N';                         // COREResources.pyx:111
-        const uint32_t mk = valid ? R.incl[p] : 0u;
-        const bool inc_p = mk & 1u;
-        const uint32_t mk1 = insr > 0 ? R.incl[p + 1] : 0u;
-        const bool win_r = insr > 0 && inc_p && (mk1 & 1u);                       // both flanks in window (:120)
+        const bool inc_p = valid && (R.incl[p] & 1u);
+        const bool win_r = insr > 0 && inc_p && (R.incl[p + 1] & 1u);             // both flanks in window (:120)
         const bool win_l = insl > 0 && inc_p && (R.incl[p - 1] & 1u);
         const uint32_t D = wp::ballot(isdel);
         if (scal) {
@@ -557,21 +549,6 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
                 }
                 o.nent += wp::popc(Bi);
             }
-            if (xcod) {                                        // CRISPRessoCORE.py:4104-4131, per-position form
-                const bool xi = win_r && ((mk | mk1) & 2u);    // window insertion with a flank in an exon
-                if (wp::ballot(xi)) {
-                    int v = xi ? (int)insr : 0;
-#pragma unroll
-                    for (int d = 16; d >= 1; d >>= 1) v += wp::shfl_xor(v, d);
-                    o.x_ins_len += v; o.x_ins_any = 1;
-                }
-                if (wp::ballot(issub && inc_p && (mk & 2u))) o.x_sub_any = 1;
-                if (wp::ballot((issub && inc_p && (mk & 4u)) || (win_r && ((mk | mk1) & 4u)))) o.x_splice = 1;
-            }
-        }
-        if (noncod) {
-            if (win_r || win_l) wp::addg(V + (int64_t)C2B_V_INS_NONCODING * vs + p, w);
-            if (issub && inc_p) wp::addg(V + (int64_t)C2B_V_SUB_NONCODING * vs + p, w);
         }
         if (vec) {
             if (insr > 0) wp::addg(V + (int64_t)C2B_V_ALL_INS_LEFT * vs + p, w);
@@ -623,6 +600,133 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
         prevD = D >> 31;
     }
     if (prevD) run(open_a, I);
+}
+
+// --coding_seq part of the quantification loop (CRISPRessoCORE.py:4104-4171), kept out of rows_run so that the hot
+// per-read code does not grow: a second scan of the same row-space view, run only for reads of a reference with a
+// coding sequence that enter that block.  add_noncoding = false: fill `c`; true: add the window edit positions of a
+// read that touches no exon to the *_noncoding vectors (:4166-4170).
+C2B_DEVNOINL void rows_coding(const KParams &P, const RefDev &R, const uint8_t *rowinfo, const uint32_t *rowins, CodOut &c,
+                              long long w, bool add_noncoding)
+{
+    const int lane = wp::lane();
+    unsigned long long *V = R.vec;
+    const int vs = P.vstride, I = R.I;
+    const int nchunks = (I + 32) >> 5;
+    int open_a = -1; uint32_t prevD = 0;
+    auto run = [&](int a, int b) {
+        if ((int)R.cum[b] - (int)R.cum[a] <= 0) return;        // deletion_positions holds runs that touch the window
+        if (!add_noncoding) {
+            c.del_cnt += (int)R.cumx[b] - (int)R.cumx[a];
+            if ((int)R.cums[b] - (int)R.cums[a] > 0) c.splice = 1;
+        } else for (int p = a + lane; p < b; p += 32) wp::addg(V + (int64_t)C2B_V_DEL_NONCODING * vs + p, w);
+    };
+    for (int ch = 0; ch < nchunks; ch++) {
+        const int p = 32 * ch + lane;
+        const bool valid = p < I;
+        const int info = valid ? rowinfo[p] : 0;
+        const bool isdel = valid && info == 8;
+        const uint32_t refc = valid ? R.asc[p] : 0u, readc = P.alpha[info & 7];
+        const bool issub = valid && !isdel && readc != refc && readc != 'N';
+        const uint32_t insr = (valid && p + 1 <= I - 1) ? rowins[p + 1] : 0u;
+        const uint32_t insl = (valid && p >= 1 && p <= I - 1) ? rowins[p] : 0u;
+        const uint32_t mk = valid ? R.incl[p] : 0u, mk1 = insr > 0 ? R.incl[p + 1] : 0u;
+        const bool inc_p = mk & 1u;
+        const bool win_r = insr > 0 && inc_p && (mk1 & 1u);
+        const bool win_l = insl > 0 && inc_p && (R.incl[p - 1] & 1u);
+        if (!add_noncoding) {
+            const bool xi = win_r && ((mk | mk1) & 2u);        // window insertion with a flank in an exon
+            if (wp::ballot(xi)) {
+                int v = xi ? (int)insr : 0;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) v += wp::shfl_xor(v, d);
+                c.ins_len += v; c.ins_any = 1;
+            }
+            if (wp::ballot(issub && inc_p && (mk & 2u))) c.sub_any = 1;
+            if (wp::ballot((issub && inc_p && (mk & 4u)) || (win_r && ((mk | mk1) & 4u)))) c.splice = 1;
+        } else {
+            if (win_r || win_l) wp::addg(V + (int64_t)C2B_V_INS_NONCODING * vs + p, w);
+            if (issub && inc_p) wp::addg(V + (int64_t)C2B_V_SUB_NONCODING * vs + p, w);
+        }
+        const uint32_t D = wp::ballot(isdel);
+        const uint32_t Dsh = (D << 1) | prevD;
+        const uint32_t Sm = D & ~Dsh;
+        uint32_t E = ~D & Dsh;
+        uint32_t Erem = E;
+        while (Erem) {
+            const int eb = wp::ffs(Erem) - 1;
+            Erem &= Erem - 1;
+            const uint32_t below = Sm & ((1u << eb) - 1u);
+            run(below ? 32 * ch + (31 - wp::clz(below)) : open_a, 32 * ch + eb);
+        }
+        if (D >> 31) {
+            const int hs = Sm ? 31 - wp::clz(Sm) : -1, he = E ? 31 - wp::clz(E) : -1;
+            if (hs > he) open_a = 32 * ch + hs;
+        }
+        prevD = D >> 31;
+    }
+    if (prevD) run(open_a, I);
+}
+
+// Frameshift / splicing decision of CRISPRessoCORE.py:4117-4171 for one counted read of a coding reference.
+C2B_DEVNOINL void coding_update(const KParams &P, const RefDev &R, const uint8_t *rowinfo, const uint32_t *rowins,
+                                bool has_window_edits, long long w)
+{
+    CodOut c; c.ins_len = c.ins_any = c.del_cnt = c.sub_any = c.splice = 0;
+    rows_coding(P, R, rowinfo, rowins, c, w, false);
+    const int lm = c.ins_len - c.del_cnt;                     // sum(length_modified_positions_exons)
+    const bool exmod = c.ins_any || c.del_cnt > 0 || c.sub_any;
+    int slot, row, key = 0;
+    if (R.tem != 0 || (exmod && (c.ins_any || c.del_cnt > 0))) {
+        key = lm + R.tem;
+        const bool inframe = key % 3 == 0;
+        slot = inframe ? C2B_S_MOD_NON_FRAMESHIFT : C2B_S_MOD_FRAMESHIFT;
+        row = inframe ? C2B_H_INFRAME : C2B_H_FRAMESHIFT;
+    } else if (exmod) { slot = C2B_S_MOD_NON_FRAMESHIFT; row = C2B_H_INFRAME; }
+    else {
+        slot = C2B_S_NON_MOD_NON_FRAMESHIFT; row = C2B_H_INFRAME;
+        if (has_window_edits) rows_coding(P, R, rowinfo, rowins, c, w, true);
+    }
+    if (wp::lane() == 0) {
+        wp::addg(R.scal + slot, w);
+        wp::addg(R.hist + (int64_t)row * P.hstride + R.hist_zero + key, w);
+        if (c.splice) wp::addg(R.scal + C2B_S_SPLICING_MODIFIED, w);
+    }
+}
+
+// What only edited reads (or reads of a reference whose exons changed length) add to the count block once they are
+// counted: the size Counters (CRISPRessoCORE.py:4020-4043; the commonest bucket is implied, see c2b200.h), the
+// insertion/deletion/substitution class counters (:4022-4072) and the --coding_seq decision.  Out of line on purpose:
+// two thirds of the reads never get here and the per-read code must stay small (instruction cache).
+#ifdef C2B_X_INLINE_EDITED
+C2B_DEV
+#else
+C2B_DEVNOINL
+#endif
+void edited_update(const KParams &P, const RefDev &R, const uint8_t *rowinfo, const uint32_t *rowins,
+                                const RowOut &o, long long w)
+{
+    const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
+               ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
+    if (R.coding) coding_update(P, R, rowinfo, rowins, o.n_ins_win > 0 || o.n_del_win > 0 || o.sub_n > 0, w);
+    if (wp::lane() != 0) return;
+    const bool has_d = !ign_d && o.del_n > 0, has_i = !ign_i && o.ins_n > 0, has_s = !ign_s && o.sub_n > 0;
+    unsigned long long *H = R.hist, *SC = R.scal;
+    const int hs = P.hstride;
+#ifndef C2B_X_NOHIST
+    if (has_i) wp::addg(H + (int64_t)C2B_H_INS_N * hs + o.ins_n, w);
+    if (has_d) wp::addg(H + (int64_t)C2B_H_DEL_N * hs + o.del_n, w);
+    if (has_s) wp::addg(H + (int64_t)C2B_H_SUB_N * hs + o.sub_n, w);
+    const int eff = R.I + (has_i ? o.ins_n : 0) - (has_d ? o.del_n : 0);
+    if (eff != R.I) wp::addg(H + (int64_t)C2B_H_EFF_LEN * hs + eff, w);
+#endif
+    if (has_i) wp::addg(SC + C2B_S_INS, w);
+    if (has_d) wp::addg(SC + C2B_S_DEL, w);
+    if (has_s) wp::addg(SC + C2B_S_SUB, w);
+    const int combo = (has_i ? 4 : 0) | (has_d ? 2 : 0) | (has_s ? 1 : 0);
+    const int slot[8] = {-1, C2B_S_ONLY_SUB, C2B_S_ONLY_DEL, C2B_S_DEL_SUB, C2B_S_ONLY_INS, C2B_S_INS_SUB,
+                         C2B_S_INS_DEL, C2B_S_INS_DEL_SUB};
+    if (slot[combo] >= 0) wp::addg(SC + slot[combo], w);
 }
 
 // ------------------------------------------------------------------------------------------ per read
@@ -711,6 +815,16 @@ C2B_DEV c2b_aln_rec load_aln(const c2b_aln_rec *p)
     return u.a;
 }
 
+// one out-of-line copy: the per-read path calls this a dozen times and must stay small (instruction cache)
+#ifdef C2B_X_INLINE_SC
+C2B_DEV void sc_add(unsigned long long *SC, int slot, long long v) { wp::addg(SC + slot, v); }
+#else
+C2B_DEVNOINL void sc_add(unsigned long long *SC, int slot, long long v)
+{
+    if (v != 0) wp::addg(SC + slot, v);
+}
+#endif
+
 // Classification + counts of one read once its alignments are known (all lanes hold the same `rec`).
 //   single reference tried: the caller already scattered the chosen alignment into rowinfo/rowins;
 //   several references    : op streams are reloaded from opsbuf (lane offset hoff; hoff >= 0: the stream lives in
@@ -749,7 +863,6 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             wp::sync();
             RowOut o; o.ins_n = o.del_n = o.sub_n = 0; o.n_ins_all = o.n_ins_win = o.n_del_all = o.n_del_win = 0;
             o.n_del_pos = o.n_sub_all = 0; o.nent = 0;
-            o.x_ins_len = o.x_ins_any = o.x_del_cnt = o.x_sub_any = o.x_splice = 0;
             c2b_edit *ed = P.edits ? P.edits + (rd * P.n_refs + r) * (int64_t)P.edit_cap : nullptr;
             const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
                        ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
@@ -765,59 +878,27 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             unsigned long long *SC = R.scal;
             if (counted) {
                 const bool discard = two_scans && (o.del_n > 0 || o.ins_n > 0);
-                if (discard) { if (lane == 0) wp::addg(SC + C2B_S_DISCARDED, w); }
+                if (discard) { if (lane == 0) sc_add(SC, C2B_S_DISCARDED, w); }
                 else {
                     // the block of CRISPRessoCORE.py:4085-4171 is entered by modified reads, and by every read of a reference
                     // whose exons changed length (tot_exon_len_mod != 0)
                     const bool entered = modified || R.tem != 0;
                     const bool lenv = entered && (o.n_ins_win > 0 || o.n_del_win > 0);
-                    // --coding_seq (:4117-4171); lane 0 adds the counters below
-                    int frame_slot = -1, frame_row = 0, frame_key = 0; bool noncod = false;
-                    if (R.coding && entered) {
-                        const int lm = o.x_ins_len - o.x_del_cnt;                 // sum(length_modified_positions_exons)
-                        const bool exmod = o.x_ins_any || o.x_del_cnt > 0 || o.x_sub_any;
-                        if (R.tem != 0 || (exmod && (o.x_ins_any || o.x_del_cnt > 0))) {
-                            frame_key = lm + R.tem;
-                            const bool inframe = frame_key % 3 == 0;
-                            frame_slot = inframe ? C2B_S_MOD_NON_FRAMESHIFT : C2B_S_MOD_FRAMESHIFT;
-                            frame_row = inframe ? C2B_H_INFRAME : C2B_H_FRAMESHIFT;
-                        } else if (exmod) { frame_slot = C2B_S_MOD_NON_FRAMESHIFT; frame_row = C2B_H_INFRAME; frame_key = 0; }
-                        else {
-                            frame_slot = C2B_S_NON_MOD_NON_FRAMESHIFT; frame_row = C2B_H_INFRAME; frame_key = 0;
-                            noncod = o.n_ins_win > 0 || o.n_del_win > 0 || o.sub_n > 0;
-                        }
-                    }
-                    if (two_scans || lenv || noncod)
-                        rows_run(P, R, rowinfo, rowins, o, nullptr, w, (two_scans ? RM_VEC : 0) | (lenv ? RM_LEN : 0) | (noncod ? RM_NONCOD : 0));
+                    if (two_scans || lenv) rows_run(P, R, rowinfo, rowins, o, nullptr, w, (two_scans ? RM_VEC : 0) | (lenv ? RM_LEN : 0));
+                    if (entered) edited_update(P, R, rowinfo, rowins, o, w);     // everything only edited reads add (out of line)
                     if (lane == 0) {
-                        unsigned long long *H = R.hist;
-                        const int hs = P.hstride;
-                        // Counters keyed by size (:4020-4043); the commonest bucket (0 / len(ref)) is implied, see c2b200.h
-                        if (!ign_i && o.ins_n > 0) wp::addg(H + (int64_t)C2B_H_INS_N * hs + o.ins_n, w);
-                        if (!ign_d && o.del_n > 0) wp::addg(H + (int64_t)C2B_H_DEL_N * hs + o.del_n, w);
-                        if (!ign_s && o.sub_n > 0) wp::addg(H + (int64_t)C2B_H_SUB_N * hs + o.sub_n, w);
-                        const int eff = R.I + (ign_i ? 0 : o.ins_n) - (ign_d ? 0 : o.del_n);
-                        if (eff != R.I) wp::addg(H + (int64_t)C2B_H_EFF_LEN * hs + eff, w);
-                        if (frame_slot >= 0) {
-                            wp::addg(SC + frame_slot, w);
-                            wp::addg(H + (int64_t)frame_row * hs + R.hist_zero + frame_key, w);
-                            if (o.x_splice) wp::addg(SC + C2B_S_SPLICING_MODIFIED, w);
-                        }
-                        wp::addg(SC + C2B_S_TOTAL, w);
-                        wp::addg(SC + (modified ? C2B_S_MODIFIED : C2B_S_UNMODIFIED), w);
-                        if (has_i) wp::addg(SC + C2B_S_INS, w);
-                        if (has_d) wp::addg(SC + C2B_S_DEL, w);
-                        if (has_s) wp::addg(SC + C2B_S_SUB, w);
-                        const int combo = (has_i ? 4 : 0) | (has_d ? 2 : 0) | (has_s ? 1 : 0);
-                        const int slot[8] = {-1, C2B_S_ONLY_SUB, C2B_S_ONLY_DEL, C2B_S_DEL_SUB, C2B_S_ONLY_INS, C2B_S_INS_SUB,
-                                             C2B_S_INS_DEL, C2B_S_INS_DEL_SUB};
-                        if (slot[combo] >= 0) wp::addg(SC + slot[combo], w);
+                        sc_add(SC, C2B_S_TOTAL, w);
+                        sc_add(SC, modified ? C2B_S_MODIFIED : C2B_S_UNMODIFIED, w);
                     }
                 }
-            } else if (ambiguous && nth == 0 && w > 0 && lane == 0) wp::addg(SC + C2B_S_AMBIGUOUS_W, w);
-            // class_counts (:3984-3986): the class of a read with one label is its first winner's
-            if (nth == 0 && w > 0 && !ambiguous && lane == 0 && !(expand && rec.n_winners > 1))
-                wp::addg(SC + (modified ? C2B_S_CLASS_MODIFIED : C2B_S_CLASS_UNMODIFIED), w);
+            } else if (ambiguous && nth == 0 && w > 0 && lane == 0) sc_add(SC, C2B_S_AMBIGUOUS_W, w);
+            // class_counts (:3984-3986) as a deviation from counts_modified / counts_unmodified: a discarded read still has
+            // its class; a counted winner of an --expand_ambiguous_alignments read with several winners has a joined label
+            // (derived on the host) instead
+            if (counted && lane == 0 && (two_scans || expand)) {
+                const bool discarded = two_scans && (o.del_n > 0 || o.ins_n > 0), joined = expand && rec.n_winners > 1;
+                if (discarded != joined) sc_add(SC, modified ? C2B_S_CLASS_MODIFIED : C2B_S_CLASS_UNMODIFIED, discarded ? w : -w);
+            }
             if (lane == 0) {
                 c2b_aln_rec a = multi ? load_aln(P.alns + rd * P.n_refs + r) : a_single;   // single reference: still in registers
                 a.insertion_n = (uint16_t)o.ins_n; a.deletion_n = (uint16_t)o.del_n; a.substitution_n = (uint16_t)o.sub_n;
@@ -835,13 +916,13 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             if (is_last && lane == 0) {
                 const long long total_mods = o.n_ins_all + o.n_del_pos + o.n_sub_all;
                 const long long in_win = o.sub_n + o.del_n + o.ins_n;
-                wp::addg(SC + C2B_S_N_GLOBAL_SUBS, cnt * o.n_sub_all);
-                wp::addg(SC + C2B_S_N_SUBS_OUTSIDE_WINDOW, cnt * (o.n_sub_all - o.sub_n));
-                wp::addg(SC + C2B_S_N_MODS_IN_WINDOW, cnt * in_win);
-                wp::addg(SC + C2B_S_N_MODS_OUTSIDE_WINDOW, cnt * (total_mods - in_win));
-                if (irr) wp::addg(SC + C2B_S_N_READS_IRREGULAR_ENDS, cnt);
-                wp::addg(SC + C2B_S_N_ALIGNED_UNIQUE, 1);
-                wp::addg(SC + C2B_S_N_ALIGNED_COUNT, cnt);
+                sc_add(SC, C2B_S_N_GLOBAL_SUBS, cnt * o.n_sub_all);
+                sc_add(SC, C2B_S_N_SUBS_OUTSIDE_WINDOW, cnt * (o.n_sub_all - o.sub_n));
+                sc_add(SC, C2B_S_N_MODS_IN_WINDOW, cnt * in_win);
+                sc_add(SC, C2B_S_N_MODS_OUTSIDE_WINDOW, cnt * (total_mods - in_win));
+                if (irr) sc_add(SC, C2B_S_N_READS_IRREGULAR_ENDS, cnt);
+                sc_add(SC, C2B_S_N_ALIGNED_UNIQUE, 1);
+                sc_add(SC, C2B_S_N_ALIGNED_COUNT, cnt);
             }
             wp::sync();
         }
@@ -861,7 +942,6 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
                 wp::sync();
                 RowOut dummy; dummy.ins_n = dummy.del_n = dummy.sub_n = 0; dummy.n_ins_all = dummy.n_ins_win = 0;
                 dummy.n_del_all = dummy.n_del_win = dummy.n_del_pos = dummy.n_sub_all = 0; dummy.nent = 0;
-                dummy.x_ins_len = dummy.x_ins_any = dummy.x_del_cnt = dummy.x_sub_any = dummy.x_splice = 0;
                 for (int r = 1; r < r_end; r++) {
                     if (!((eff >> (r & 31)) & 1u)) continue;
                     rows_run(P, R0, rowinfo, rowins, dummy, nullptr, w, RM_REF1, P.refs[r].vec);

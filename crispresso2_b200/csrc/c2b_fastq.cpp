@@ -1,0 +1,304 @@
+// c2b_fastq.cpp -- native FASTQ ingest + exact de-duplication for the engine's front end (host code, no CUDA).
+//
+// Replaces the Python loop of process_fastq that reads the FASTQ four lines at a time and counts identical
+// sequences in variantCache (reference: CRISPResso2/CRISPRessoCORE.py:1820-1849).  Semantics kept bit for bit:
+//   * text-mode universal newlines: "\n", "\r\n" and a lone "\r" all end a line;
+//   * a record starts at every line that exists (even an empty one) and consumes the next three lines, present or not;
+//   * the sequence is line 2 with leading/trailing ASCII whitespace removed (str.strip()); a missing line is "";
+//   * unique sequences are reported in first-seen order with their multiplicities.
+// Output is already in the packed layout c2b_align_batch takes (bytes + int64 offsets + int32 counts).
+//
+// Parallel plan: (1) split the buffer at line boundaries and index line starts per thread; (2) hash every record's
+// sequence (threads over record ranges); (3) shard the hash space: shard s owns the records with hash % P == s and
+// walks them in file order through an open-addressing table (full byte compare on hash match -- exact, no
+// probabilistic step); (4) merge the shards' (first index, count) lists by first index.
+#include "c2b200.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct Seq { const uint8_t *p; uint32_t len; };
+
+inline bool is_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f); }   // str.strip() on ASCII
+
+inline uint64_t hash_bytes(const uint8_t *p, size_t n)
+{
+    // 64-bit multiply-xorshift over 8-byte words; only used to place keys -- equality is decided by memcmp
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xff51afd7ed558ccdull);
+    while (n >= 8) {
+        uint64_t w; memcpy(&w, p, 8);
+        h = (h ^ w) * 0xff51afd7ed558ccdull; h ^= h >> 32;
+        p += 8; n -= 8;
+    }
+    uint64_t w = 0;
+    if (n) memcpy(&w, p, n);
+    h = (h ^ w) * 0xc4ceb9fe1a85ec53ull; h ^= h >> 29;
+    h *= 0x9E3779B97F4A7C15ull; h ^= h >> 32;
+    return h;
+}
+
+bool read_plain(const char *path, std::vector<uint8_t> &buf, std::string &err)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) { err = std::string("cannot open ") + path; return false; }
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (n < 0) { fclose(f); err = "cannot size file"; return false; }
+    buf.resize((size_t)n);
+    size_t got = n ? fread(buf.data(), 1, (size_t)n, f) : 0;
+    fclose(f);
+    if (got != (size_t)n) { err = "short read"; return false; }
+    return true;
+}
+
+bool read_gz(const char *path, std::vector<uint8_t> &buf, std::string &err)
+{
+    gzFile g = gzopen(path, "rb");
+    if (!g) { err = std::string("cannot open ") + path; return false; }
+    gzbuffer(g, 1 << 20);
+    size_t used = 0;
+    buf.resize(64 << 20);
+    for (;;) {
+        if (buf.size() - used < (16u << 20)) buf.resize(buf.size() * 2);
+        int n = gzread(g, buf.data() + used, (unsigned)std::min<size_t>(buf.size() - used, 1u << 30));
+        if (n < 0) { int e; err = gzerror(g, &e); gzclose(g); return false; }
+        if (n == 0) break;
+        used += (size_t)n;
+    }
+    gzclose(g);
+    buf.resize(used);
+    return true;
+}
+
+}  // namespace
+
+struct c2b_fastq {
+    std::vector<uint8_t> seqs;
+    std::vector<int64_t> offsets;
+    std::vector<int32_t> counts;
+    std::vector<int64_t> first_index;
+    int64_t n_reads = 0;
+    int32_t max_len = 0;
+    std::string err;
+};
+
+static std::string g_fastq_err;
+
+extern "C" {
+
+const char *c2b_fastq_last_error(void) { return g_fastq_err.c_str(); }
+
+int c2b_fastq_dedup_buffer(const uint8_t *data, size_t n, int32_t n_threads, c2b_fastq **out)
+{
+    if (!out || (n && !data)) return C2B_E_ARG;
+    c2b_fastq *F = new c2b_fastq();
+    const bool verbose = getenv("C2B_FASTQ_VERBOSE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!verbose) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[c2b_fastq] %-10s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
+    int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    T = std::max(1, std::min(T, 64));
+    if (n < (1u << 20)) T = 1;
+
+    // (1) line starts.  Thread t scans [cut[t], cut[t+1]); cuts sit just after a line terminator.
+    std::vector<size_t> cut(T + 1, 0);
+    cut[T] = n;
+    for (int t = 1; t < T; t++) {
+        size_t p = std::max(cut[t - 1], n / T * t);
+        while (p < n && data[p] != '\n' && data[p] != '\r') p++;
+        if (p < n) p += (data[p] == '\r' && p + 1 < n && data[p + 1] == '\n') ? 2 : 1;
+        cut[t] = std::min(p, n);
+    }
+    std::vector<std::vector<uint64_t>> starts(T);          // per thread: line start offsets and content lengths
+    std::vector<std::vector<uint32_t>> lens(T);
+    auto scan = [&](int t) {
+        size_t p = cut[t];
+        const size_t e = cut[t + 1];
+        auto &S = starts[t]; auto &L = lens[t];
+        S.reserve((e - p) / 60 + 16); L.reserve((e - p) / 60 + 16);
+        while (p < e) {
+            const uint8_t *q = data + p;
+            const uint8_t *nl = (const uint8_t *)memchr(q, '\n', e - p);
+            const size_t a = nl ? (size_t)(nl - data) : e;
+            const uint8_t *cr = (const uint8_t *)memchr(q, '\r', a - p);     // first CR before that LF
+            if (cr) {                                                         // "\r\n" pair, or a lone '\r' (universal newlines)
+                const size_t b = (size_t)(cr - data);
+                S.push_back(p); L.push_back((uint32_t)(b - p));
+                p = (nl && b + 1 == a) ? a + 1 : b + 1;
+            } else {
+                S.push_back(p); L.push_back((uint32_t)(a - p));
+                p = nl ? a + 1 : e;
+            }
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(scan, t);
+        scan(0);
+        for (auto &x : th) x.join();
+    }
+    lap("lines");
+    std::vector<size_t> line_base(T + 1, 0);
+    for (int t = 0; t < T; t++) line_base[t + 1] = line_base[t] + starts[t].size();
+    const size_t n_lines = line_base[T];
+    const int64_t n_rec = (int64_t)((n_lines + 3) / 4);
+    F->n_reads = n_rec;
+    auto line_at = [&](size_t k, Seq &s) {
+        int t = (int)(std::upper_bound(line_base.begin(), line_base.end(), k) - line_base.begin()) - 1;
+        const size_t j = k - line_base[t];
+        s.p = data + starts[t][j]; s.len = lens[t][j];
+    };
+
+    // (2) sequences (line 2 of every record, stripped) and their hashes
+    std::vector<Seq> seq((size_t)n_rec);
+    std::vector<uint64_t> hv((size_t)n_rec);
+    auto hash_range = [&](int t) {
+        const int64_t a = n_rec * t / T, b = n_rec * (t + 1) / T;
+        for (int64_t r = a; r < b; r++) {
+            Seq s; s.p = data; s.len = 0;
+            const size_t k = (size_t)r * 4 + 1;
+            if (k < n_lines) {
+                line_at(k, s);
+                while (s.len && is_space(s.p[0])) { s.p++; s.len--; }
+                while (s.len && is_space(s.p[s.len - 1])) s.len--;
+            }
+            seq[(size_t)r] = s;
+            hv[(size_t)r] = hash_bytes(s.p, s.len);
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(hash_range, t);
+        hash_range(0);
+        for (auto &x : th) x.join();
+    }
+
+    lap("hash");
+    // (3) sharded exact dedup in file order
+    struct Ent { int64_t first; int32_t count; };
+    std::vector<std::vector<Ent>> found(T);
+    auto shard = [&](int s) {
+        size_t mine = 0;
+        for (int64_t r = 0; r < n_rec; r++) mine += ((hv[(size_t)r] >> 40) % (uint64_t)T) == (uint64_t)s;
+        size_t cap = 64;
+        while (cap < mine * 2 + 8) cap <<= 1;
+        std::vector<int32_t> slot(cap, -1);                // index into found[s]
+        auto &E = found[s];
+        for (int64_t r = 0; r < n_rec; r++) {
+            const uint64_t h = hv[(size_t)r];
+            if (((h >> 40) % (uint64_t)T) != (uint64_t)s) continue;
+            size_t k = (size_t)h & (cap - 1);
+            for (;;) {
+                const int32_t e = slot[k];
+                if (e < 0) { slot[k] = (int32_t)E.size(); E.push_back({r, 1}); break; }
+                const Seq &a = seq[(size_t)E[(size_t)e].first], &b = seq[(size_t)r];
+                if (hv[(size_t)E[(size_t)e].first] == h && a.len == b.len && memcmp(a.p, b.p, a.len) == 0) { E[(size_t)e].count++; break; }
+                k = (k + 1) & (cap - 1);
+            }
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(shard, t);
+        shard(0);
+        for (auto &x : th) x.join();
+    }
+
+    lap("dedup");
+    // (4) merge by first index (every shard list is already ascending)
+    size_t nu = 0;
+    for (auto &E : found) nu += E.size();
+    std::vector<Ent> all;
+    all.reserve(nu);
+    for (auto &E : found) all.insert(all.end(), E.begin(), E.end());
+    if (T > 1) std::sort(all.begin(), all.end(), [](const Ent &a, const Ent &b) { return a.first < b.first; });
+    F->offsets.resize(nu + 1);
+    F->counts.resize(nu);
+    F->first_index.resize(nu);
+    int64_t tot = 0;
+    for (size_t u = 0; u < nu; u++) {
+        F->offsets[u] = tot;
+        tot += seq[(size_t)all[u].first].len;
+        F->counts[u] = all[u].count;
+        F->first_index[u] = all[u].first;
+        F->max_len = std::max<int32_t>(F->max_len, (int32_t)seq[(size_t)all[u].first].len);
+    }
+    F->offsets[nu] = tot;
+    F->seqs.resize((size_t)tot + 16);
+    auto copy_range = [&](int t) {
+        const size_t a = nu * t / T, b = nu * (t + 1) / T;
+        for (size_t u = a; u < b; u++) {
+            const Seq &s = seq[(size_t)all[u].first];
+            memcpy(F->seqs.data() + F->offsets[u], s.p, s.len);
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(copy_range, t);
+        copy_range(0);
+        for (auto &x : th) x.join();
+    }
+    lap("emit");
+    *out = F;
+    return C2B_OK;
+}
+
+int c2b_fastq_dedup(const char *path, int32_t n_threads, c2b_fastq **out)
+{
+    if (!path || !out) return C2B_E_ARG;
+    std::vector<uint8_t> buf;
+    std::string err;
+    const size_t L = strlen(path);
+    const bool gz = L > 3 && strcmp(path + L - 3, ".gz") == 0;            // CRISPRessoCORE.py:1820
+    auto t0 = std::chrono::steady_clock::now();
+    if (!gz) {                                             // plain file: map it, no copy
+        int fd = open(path, O_RDONLY);
+        if (fd < 0) { g_fastq_err = std::string("c2b_fastq_dedup: cannot open ") + path; return C2B_E_ARG; }
+        struct stat st;
+        if (fstat(fd, &st) == 0 && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                const int rc = c2b_fastq_dedup_buffer((const uint8_t *)m, (size_t)st.st_size, n_threads, out);
+                munmap(m, (size_t)st.st_size);
+                close(fd);
+                return rc;
+            }
+        }
+        close(fd);
+    }
+    if (!(gz ? read_gz(path, buf, err) : read_plain(path, buf, err))) { g_fastq_err = "c2b_fastq_dedup: " + err; return C2B_E_ARG; }
+    if (getenv("C2B_FASTQ_VERBOSE"))
+        fprintf(stderr, "[c2b_fastq] read       %.3f s (%zu bytes)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), buf.size());
+    return c2b_fastq_dedup_buffer(buf.data(), buf.size(), n_threads, out);
+}
+
+int64_t c2b_fastq_n_reads(const c2b_fastq *f) { return f ? f->n_reads : 0; }
+int64_t c2b_fastq_n_unique(const c2b_fastq *f) { return f ? (int64_t)f->counts.size() : 0; }
+int32_t c2b_fastq_max_len(const c2b_fastq *f) { return f ? f->max_len : 0; }
+const uint8_t *c2b_fastq_seqs(const c2b_fastq *f) { return f ? f->seqs.data() : nullptr; }
+const int64_t *c2b_fastq_offsets(const c2b_fastq *f) { return f ? f->offsets.data() : nullptr; }
+const int32_t *c2b_fastq_counts(const c2b_fastq *f) { return f ? f->counts.data() : nullptr; }
+const int64_t *c2b_fastq_first_index(const c2b_fastq *f) { return f ? f->first_index.data() : nullptr; }
+void c2b_fastq_free(c2b_fastq *f) { delete f; }
+
+}  // extern "C"

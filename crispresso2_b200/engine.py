@@ -53,6 +53,7 @@ def pack_reads(reads):
 class Engine:
     def __init__(self, device=0, lib_path=None):
         self.L = _lib.load(lib_path)
+        self.lib_path = lib_path
         h = C.c_void_p()
         rc = self.L.c2b_create(int(device), C.byref(h))
         if rc != 0:

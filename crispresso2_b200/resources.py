@@ -45,6 +45,65 @@ def ref_positions_from(aln_ref):
     return out.tolist()
 
 
+def ref_positions_fast(aln_ref):
+    """Same list as ref_positions_from; plain range when the aligned reference holds no gap (the common case)."""
+    if "-" not in aln_ref:
+        return list(range(len(aln_ref)))
+    return ref_positions_from(aln_ref)
+
+
+def payload_from_lists(insertion_n, deletion_n, substitution_n, edits, aln_ref):
+    """Batch fast path of payload_from_device: `edits` is a list of plain tuples (a, b, type, in_window, base, pad) --
+    EDIT_DTYPE rows after one .tolist() per batch -- already cut to the alignment's n_edits.  Same lists, built with
+    plain Python on the (usually 0-3) entries instead of numpy masks."""
+    all_sub_pos, all_sub_val, sub_pos, sub_val = [], [], [], []
+    all_ins_left, all_ins_pos, ins_coords, ins_pos, ins_sizes = [], [], [], [], []
+    all_del_coords, all_del_pos, del_coords, del_pos, del_sizes = [], [], [], [], []
+    for a, b, t, inw, base, _ in edits:
+        if t == 1:
+            all_sub_pos.append(a)
+            all_sub_val.append(chr(base))
+            if inw:
+                sub_pos.append(a)
+                sub_val.append(chr(base))
+        elif t == 2:
+            all_ins_left.append(a)
+            all_ins_pos.append(a)
+            all_ins_pos.append(a + 1)
+            if inw:
+                ins_coords.append((a, a + 1))
+                ins_pos.append(a)
+                ins_pos.append(a + 1)
+                ins_sizes.append(b)
+        else:
+            all_del_coords.append((a, b))
+            all_del_pos.extend(range(a, b))
+            if inw:
+                del_coords.append((a, b))
+                del_pos.extend(range(a, b))
+                del_sizes.append(b - a)
+    p = ResultsSlotsDict.__new__(ResultsSlotsDict)
+    p.all_insertion_positions = all_ins_pos
+    p.all_insertion_left_positions = all_ins_left
+    p.insertion_positions = ins_pos
+    p.insertion_coordinates = ins_coords
+    p.insertion_sizes = ins_sizes
+    p.insertion_n = insertion_n
+    p.all_deletion_positions = all_del_pos
+    p.all_deletion_coordinates = all_del_coords
+    p.deletion_positions = del_pos
+    p.deletion_coordinates = del_coords
+    p.deletion_sizes = del_sizes
+    p.deletion_n = deletion_n
+    p.all_substitution_positions = all_sub_pos
+    p.substitution_positions = sub_pos
+    p.all_substitution_values = np.array(all_sub_val)
+    p.substitution_values = np.array(sub_val)
+    p.substitution_n = substitution_n
+    p.ref_positions = ref_positions_fast(aln_ref)
+    return p
+
+
 def payload_from_device(aln, edits, aln_read, aln_ref):
     """aln: one ALN_DTYPE record; edits: EDIT_DTYPE array (at least aln['n_edits'] valid entries)."""
     n = int(aln["n_edits"])

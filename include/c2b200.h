@@ -163,9 +163,10 @@ enum {
     C2B_S_N_GLOBAL_SUBS, C2B_S_N_SUBS_OUTSIDE_WINDOW, C2B_S_N_MODS_IN_WINDOW, C2B_S_N_MODS_OUTSIDE_WINDOW,
     C2B_S_N_READS_IRREGULAR_ENDS, C2B_S_N_ALIGNED_UNIQUE, C2B_S_N_ALIGNED_COUNT,
     C2B_S_REF1_W,          /* weight re-projected onto reference 0 for this reference (C2B_F_HDR_REF1) */
-    /* class_counts (CRISPRessoCORE.py:3984-3986) of reads whose class_name is "<this ref>_MODIFIED" / "_UNMODIFIED"
-     * (one best reference, or several with assign-first); "AMBIGUOUS" = sum of C2B_S_AMBIGUOUS_W; the joined labels of
-     * --expand_ambiguous_alignments reads with several best references are derived from the read records on the host */
+    /* class_counts (CRISPRessoCORE.py:3984-3986): class_counts["<ref>_MODIFIED"] = counts_modified + C2B_S_CLASS_MODIFIED
+     * (signed deviation: + reads discarded by --discard_indel_reads, which keep their class; - winners of
+     * --expand_ambiguous_alignments reads with several best references, whose joined label is derived from the read
+     * records on the host); likewise _UNMODIFIED; "AMBIGUOUS" = sum of C2B_S_AMBIGUOUS_W */
     C2B_S_CLASS_MODIFIED, C2B_S_CLASS_UNMODIFIED,
     /* --coding_seq counters (:4134-4171) */
     C2B_S_MOD_FRAMESHIFT, C2B_S_MOD_NON_FRAMESHIFT, C2B_S_NON_MOD_NON_FRAMESHIFT, C2B_S_SPLICING_MODIFIED,
@@ -254,6 +255,24 @@ int  c2b_global_align(c2b_engine *e, const char *read, int32_t read_len, const c
 int  c2b_classify_aligned(c2b_engine *e, const char *read_al, const char *ref_al, int32_t n_cols,
                           const char *alphabet, int32_t nq, const int64_t *include_idx, int32_t n_include,
                           c2b_aln_rec *out, c2b_edit *edits);
+
+/* replaces: the FASTQ read + de-duplication loop of process_fastq (CRISPRessoCORE.py:1820-1849): four lines per
+ * record (text-mode universal newlines), sequence = line 2 stripped of surrounding whitespace, identical sequences
+ * counted, unique sequences kept in first-seen order.  Host code (threads), exact (hash placement + byte compare).
+ * The result is in the packed layout c2b_align_batch takes: seqs/offsets[n_unique+1]/counts[n_unique].
+ * path ending in ".gz" is inflated with zlib.  n_threads <= 0: all hardware threads.                  */
+typedef struct c2b_fastq c2b_fastq;
+int  c2b_fastq_dedup(const char *path, int32_t n_threads, c2b_fastq **out);
+int  c2b_fastq_dedup_buffer(const uint8_t *data, size_t n_bytes, int32_t n_threads, c2b_fastq **out);
+int64_t c2b_fastq_n_reads(const c2b_fastq *f);            /* num_reads of :1830 */
+int64_t c2b_fastq_n_unique(const c2b_fastq *f);
+int32_t c2b_fastq_max_len(const c2b_fastq *f);
+const uint8_t *c2b_fastq_seqs(const c2b_fastq *f);
+const int64_t *c2b_fastq_offsets(const c2b_fastq *f);
+const int32_t *c2b_fastq_counts(const c2b_fastq *f);
+const int64_t *c2b_fastq_first_index(const c2b_fastq *f); /* record index of each unique sequence's first occurrence */
+void c2b_fastq_free(c2b_fastq *f);
+const char *c2b_fastq_last_error(void);
 
 /* pinned host memory (cudaHostAlloc) for callers that want full-speed host<->device copies */
 void *c2b_host_alloc(size_t n_bytes);
