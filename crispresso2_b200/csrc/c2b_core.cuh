@@ -42,9 +42,11 @@ C2B_DEV void sync() { __syncwarp(); }
 // g < 0: |g| warps strided by the number of sets (warps w, w + nsets, ...: with four sets, the warps of one sub-partition)
 C2B_DEV void grp_sync(int g)
 {
-    const int w = (int)(threadIdx.x >> 5), n = g > 0 ? g : -g;
-    const int set = g > 0 ? w / n : w % ((int)(blockDim.x >> 5) / n);
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + set), "r"(32 * n) : "memory");
+    // |g| and the number of sets are powers of two (checked by the host): shifts, not the integer divisions that used to
+    // be inlined at every one of the dozen phase barriers
+    const int w = (int)(threadIdx.x >> 5), n = g > 0 ? g : -g, sh = 31 - __clz(n);
+    const int set = g > 0 ? (w >> sh) : (w & (((int)(blockDim.x >> 5) >> sh) - 1));
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + set), "r"(32 << sh) : "memory");
 }
 C2B_DEV int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 C2B_DEV int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }   // max(a+b, c)
@@ -131,7 +133,8 @@ struct KParams {
     uint32_t *tbq;                                            // slab of the ring-banded path: [step][lane] uint2, TS steps per warp
     int32_t *bnd; int64_t bnd_words_per_warp;                 // 2 x 3 x (maxJ+1): row-block boundary rows
     uint64_t *opsbuf;                                         // [warp][n_refs][32] op streams (multi-reference)
-    unsigned long long *work_counter;
+    unsigned long long *work_counter;      // [0] work hand-out counter, [1] widest alignment of this launch
+    unsigned long long *stats;             // cumulative path statistics (c2b_path_counts), indices 2..6
     int32_t vstride, hstride;
     const uint32_t *stage_src;        // = refs[0].prof2 (global source of the staged tile)
     int32_t stage_bytes;              // bytes of refs[0].prof2 staged into shared memory by TMA at kernel start (0: none)
@@ -449,9 +452,11 @@ C2B_DEVNOINL ColOut columns(const KParams &P, const RefDev &R, uint8_t *rowinfo,
 // exact round(100*m/n, 3)*1000 with Python's round-half-even (ties are exactly representable)
 C2B_DEV int score_milli(int m, int n)
 {
-    const long long num = 100000ll * m;
-    long long q = num / n; const long long r = num - q * n;
-    if (2 * r > n || (2 * r == n && (q & 1))) q++;
+    // m <= n <= C2B_MAX_ALN_LEN = 1024: 100000*m < 2^27, so 32-bit unsigned arithmetic is exact (and the division is a
+    // fraction of the 64-bit one's code)
+    const uint32_t num = 100000u * (uint32_t)m, d = (uint32_t)n;
+    uint32_t q = num / d; const uint32_t r = num - q * d;
+    if (2u * r > d || (2u * r == d && (q & 1u))) q++;
     return (int)q;
 }
 
@@ -698,10 +703,10 @@ C2B_DEVNOINL void coding_update(const KParams &P, const RefDev &R, const uint8_t
 // counted: the size Counters (CRISPRessoCORE.py:4020-4043; the commonest bucket is implied, see c2b200.h), the
 // insertion/deletion/substitution class counters (:4022-4072) and the --coding_seq decision.  Out of line on purpose:
 // two thirds of the reads never get here and the per-read code must stay small (instruction cache).
-#ifdef C2B_X_INLINE_EDITED
-C2B_DEV
-#else
+#ifdef C2B_X_NOINLINE_EDITED
 C2B_DEVNOINL
+#else
+C2B_DEV                       // measured both ways (profiles/r01k_variants.md): inline is 0.5 ms per 1 M reads faster
 #endif
 void edited_update(const KParams &P, const RefDev &R, const uint8_t *rowinfo, const uint32_t *rowins,
                                 const RowOut &o, long long w)
@@ -815,8 +820,7 @@ C2B_DEV c2b_aln_rec load_aln(const c2b_aln_rec *p)
     return u.a;
 }
 
-// one out-of-line copy: the per-read path calls this a dozen times and must stay small (instruction cache)
-#ifdef C2B_X_INLINE_SC
+#ifndef C2B_X_NOINLINE_SC
 C2B_DEV void sc_add(unsigned long long *SC, int slot, long long v) { wp::addg(SC + slot, v); }
 #else
 C2B_DEVNOINL void sc_add(unsigned long long *SC, int slot, long long v)
@@ -824,6 +828,25 @@ C2B_DEVNOINL void sc_add(unsigned long long *SC, int slot, long long v)
     if (v != 0) wp::addg(SC + slot, v);
 }
 #endif
+
+// Several references were tried: reload the op stream of the read's alignment to reference r (kept in opsbuf; lane offset
+// hoff >= 0: the stream lives in 16 lanes starting at hoff) and scatter it into the row-space view again.  -> irregular_ends
+C2B_DEVNOINL int rescatter(const KParams &P, const RefDev &R, int64_t rd, int r, const uint64_t *opsbuf, int hoff,
+                           uint8_t *rowinfo, uint32_t *rowins, const uint8_t *fw, const uint8_t *rc, int J)
+{
+    const int lane = wp::lane();
+    wp::sync();
+    uint64_t ops;
+    if (hoff < 0) ops = wp::ldcg64(opsbuf + r * 32 + lane);
+    else ops = lane < 16 ? wp::ldcg64(opsbuf + r * 32 + hoff + lane) : ~0ull;
+    const c2b_aln_rec prev = load_aln(P.alns + rd * P.n_refs + r);
+    const int n = wp::shfl((int)prev.aln_len, 0), strand = wp::shfl((int)prev.strand, 0);
+    const int irr = wp::shfl((int)prev.irregular_ends, 0);
+    for (int p = lane; p <= R.I; p += 32) rowins[p] = 0;
+    wp::sync();
+    columns<false>(P, R, rowinfo, rowins, strand ? rc : fw, J, ops, n, 2, nullptr, nullptr);
+    return irr;
+}
 
 // Classification + counts of one read once its alignments are known (all lanes hold the same `rec`).
 //   single reference tried: the caller already scattered the chosen alignment into rowinfo/rowins;
@@ -848,18 +871,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             const RefDev &R = P.refs[r];
             rec.best_ref = (int16_t)r;                          // best_match_name = last winner (:768)
             int irr = keep_irr;
-            if (multi) {
-                wp::sync();
-                uint64_t ops;
-                if (hoff < 0) ops = wp::ldcg64(opsbuf + r * 32 + lane);
-                else ops = lane < 16 ? wp::ldcg64(opsbuf + r * 32 + hoff + lane) : ~0ull;
-                const c2b_aln_rec prev = load_aln(P.alns + rd * P.n_refs + r);
-                const int n = wp::shfl((int)prev.aln_len, 0), strand = wp::shfl((int)prev.strand, 0);
-                irr = wp::shfl((int)prev.irregular_ends, 0);
-                for (int p = lane; p <= R.I; p += 32) rowins[p] = 0;
-                wp::sync();
-                columns<false>(P, R, rowinfo, rowins, strand ? rc : fw, J, ops, n, 2, nullptr, nullptr);
-            }
+            if (multi) irr = rescatter(P, R, rd, r, opsbuf, hoff, rowinfo, rowins, fw, rc, J);
             wp::sync();
             RowOut o; o.ins_n = o.del_n = o.sub_n = 0; o.n_ins_all = o.n_ins_win = o.n_del_all = o.n_del_win = 0;
             o.n_del_pos = o.n_sub_all = 0; o.nent = 0;
@@ -931,14 +943,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             const uint32_t eff = first ? (rec.winner_mask & (0u - rec.winner_mask)) : rec.winner_mask;   // aln_ref_names
             if (eff != 1u) {                                    // not "aligned to reference 0 only" (:4234)
                 const RefDev &R0 = P.refs[0];
-                uint64_t ops;
-                if (hoff < 0) ops = wp::ldcg64(opsbuf + lane);
-                else ops = lane < 16 ? wp::ldcg64(opsbuf + hoff + lane) : ~0ull;
-                const c2b_aln_rec prev = load_aln(P.alns + rd * P.n_refs);
-                const int n0 = wp::shfl((int)prev.aln_len, 0), strand0 = wp::shfl((int)prev.strand, 0);
-                for (int p = lane; p <= R0.I; p += 32) rowins[p] = 0;
-                wp::sync();
-                columns<false>(P, R0, rowinfo, rowins, strand0 ? rc : fw, J, ops, n0, 2, nullptr, nullptr);
+                rescatter(P, R0, rd, 0, opsbuf, hoff, rowinfo, rowins, fw, rc, J);
                 wp::sync();
                 RowOut dummy; dummy.ins_n = dummy.del_n = dummy.sub_n = 0; dummy.n_ins_all = dummy.n_ins_win = 0;
                 dummy.n_del_all = dummy.n_del_win = dummy.n_del_pos = dummy.n_sub_all = 0; dummy.nent = 0;
@@ -1147,7 +1152,7 @@ C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint32_t *pro
         const Walked wk = walk_batch<true>(P, R, J, reinterpret_cast<const uint32_t *>(tb2), s, sm);
         if (!band || !wp::ballot((wk.err & 4) != 0)) return wk;
         band = false;                                               // a traceback left the band: once more with the full slab
-        if (wp::lane() == 0) wp::addg(P.work_counter + 4, 1);
+        if (wp::lane() == 0) wp::addg(P.stats + 4, 1);
     }
 }
 
@@ -1269,7 +1274,14 @@ C2B_DEV int ring_bound(const KParams &P, const RefDev &R, int J)
 }
 
 struct RingCtx { const uint64_t *ops; const int32_t *n, *err; int modes; };   // a pair aligned by dp_ring: its walked op streams, lengths, strand modes
-constexpr int PAIR_PHASES = 5, GROUP_PHASES = 3 + 4 * PAIR_PHASES;      // barriers per process_pair(phased) / per work group
+#if defined(C2B_X_ONE_CLASSIFY_BARRIER) && defined(C2B_X_NO_PASS_BARRIER)
+constexpr int PAIR_PHASES = 3;
+#elif defined(C2B_X_ONE_CLASSIFY_BARRIER) || defined(C2B_X_NO_PASS_BARRIER)
+constexpr int PAIR_PHASES = 4;
+#else
+constexpr int PAIR_PHASES = 5;
+#endif
+constexpr int GROUP_PHASES = 3 + 4 * PAIR_PHASES;      // barriers per process_pair(phased) / per work group
 
 // Two reads (rdA, rdB) of equal length J through the packed path.  Per-lane variables belong to the lane's half.
 C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_prof, int64_t rdA, int64_t rdB, int warp_slot,
@@ -1321,7 +1333,9 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
             const int sA = (mA == 2) ? pass : (mA == 1), sB = (mB == 2) ? pass : (mB == 1);
             const uint8_t *cA = sA ? S.rc[0] : S.fw[0], *cB = sB ? S.rc[1] : S.fw[1];
             wp::sync();
+#ifndef C2B_X_NO_PASS_BARRIER
             if (phased && pass == 0) wp::grp_sync(P.phase_sync);
+#endif
             Walked wk; wk.err = 4;
             if (ring) { wk.ops = ring->ops[lane]; wk.n = ring->n[h]; wk.err = ring->err[h]; }   // aligned and walked by process_quad
             if (wk.err & 4) {
@@ -1361,9 +1375,15 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
         if (hl == 0 && (h == 0 || rdB != rdA)) P.alns[myrd * P.n_refs + r] = a;
     }
     wp::sync();
-    // classification runs with the whole warp, one read at a time: broadcast that half's bookkeeping to every lane
+    // classification runs with the whole warp, one read at a time: broadcast that half's bookkeeping to every lane.
+    // (The compiler unrolls this loop into two copies of finish_read; forcing one copy, or making finish_read and the
+    // loaders out-of-line calls, shrank the kernel by 20 % and made it 3-5 % SLOWER -- profiles/r01k_variants.md.)
     for (int hh = 0; hh < 2; hh++) {
+#ifndef C2B_X_ONE_CLASSIFY_BARRIER
         if (phased) wp::grp_sync(P.phase_sync);
+#else
+        if (phased && hh == 0) wp::grp_sync(P.phase_sync);
+#endif
         if (hh == 1 && rdB == rdA) break;
         const int src = 16 * hh;
         c2b_read_rec rr;
@@ -1401,7 +1421,7 @@ C2B_DEV void process_item(const KParams &P, WarpSmem &S, const uint32_t *staged_
             for (int r = r_begin; r < r_end; r++) if (Ja > P.refs[r].pk_maxJ) pair = false;
         }
     }
-    if (wp::lane() == 0) wp::addg(P.work_counter + (pair ? 2 : 3), 1);      // path statistics (c2b_path_counts)
+    if (wp::lane() == 0) wp::addg(P.stats + (pair ? 2 : 3), 1);      // path statistics (c2b_path_counts)
     if (pair) process_pair(P, S, staged_prof, rdA, rdB, warp_slot, nullptr, false);
     else {
         process_read(P, S, rdA, warp_slot);
@@ -1481,9 +1501,9 @@ C2B_DEV void process_quad(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint
     }
     wp::sync();
     if (lane == 0) {
-        wp::addg(P.work_counter + 2, 4);
-        wp::addg(P.work_counter + 5, wp::popc(passmask));
-        wp::addg(P.work_counter + 6, 4 - wp::popc(passmask));
+        wp::addg(P.stats + 2, 4);
+        wp::addg(P.stats + 5, wp::popc(passmask));
+        wp::addg(P.stats + 6, 4 - wp::popc(passmask));
     }
 #pragma unroll 1
     for (int q = 0; q < 4; q++) {

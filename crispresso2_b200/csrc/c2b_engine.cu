@@ -164,7 +164,10 @@ struct c2b_engine {
     // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
     struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed, maxlen, ord; int32_t *h_ord = nullptr; size_t h_ord_cap = 0; int64_t *h_off = nullptr; size_t h_off_cap = 0;
                    rt_event in_done, k_done, out_done; bool used = false; } stage[2];
-    rt_stream s_in = 0, s_out = 0;
+    rt_stream s_in = 0, s_out = 0, stream2 = 0;     // stream2: second compute stream, kernels of odd chunks
+    rt_event fork_ev = 0;                           // orders stream2 after what is already queued on `stream`
+    size_t set_tb = 0, set_tbb = 0, set_tbq = 0, set_bnd = 0, set_ops = 0;   // bytes per scratch set (two sets: kernels of
+                                                    // consecutive chunks overlap their tail / head on the two streams)
     bool pipe_ready = false;
     double last_ms = 0; int64_t launches = 0;
     const uint64_t *forced_ops = nullptr; const int32_t *forced_n = nullptr;
@@ -202,6 +205,8 @@ int c2b_create(int device, c2b_engine **out)
 #ifndef C2B_EMU
     cudaError_t r = cudaSetDevice(device);
     if (r == cudaSuccess) r = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (r == cudaSuccess) r = cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking);
+    if (r == cudaSuccess) r = cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming);
     if (r == cudaSuccess) r = cudaEventCreate(&e->ev0);
     if (r == cudaSuccess) r = cudaEventCreate(&e->ev1);
     int nsm = 0, occ = 0, smem_sm = 0;
@@ -254,6 +259,8 @@ void c2b_destroy(c2b_engine *e)
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream2) cudaStreamDestroy(e->stream2);
+    if (e->fork_ev) cudaEventDestroy(e->fork_ev);
 #endif
     delete e;
 }
@@ -459,19 +466,28 @@ int c2b_string_width(const c2b_engine *e, int32_t max_read_len)
     return (e->max_I + max_read_len + 31) & ~31;
 }
 
+// work block (u64): [2..6] cumulative path statistics; set s: [8 + 8 s] work hand-out counter, [9 + 8 s] widest alignment
+constexpr size_t WORK_BYTES = 24 * 8;
+
 static int ensure_scratch(c2b_engine *e, int maxJ)
 {
     const int TS = ((maxJ + 32 + 31) & ~31);
     if (TS <= e->scratch_TS) return C2B_OK;
     int rc;
-    if ((rc = ensure(e, e->tb, (size_t)e->n_warps * e->max_nrb * TS * 64 * 4))) return rc;   // 64: a pair stores two words per lane
-    if ((rc = ensure(e, e->tbb, (size_t)e->n_warps * PK_BAND_SLOTS * 64 * 4))) return rc;                // banded slabs (packed path)
-    if ((rc = ensure(e, e->tbq, (size_t)e->n_warps * TS * 64 * 4 + 64))) return rc;                           // ring-banded path: (step, lane) entries
-    if ((rc = ensure(e, e->bnd, (size_t)e->n_warps * 2 * 3 * TS * 4))) return rc;
-    if ((rc = ensure(e, e->ops, (size_t)e->n_warps * e->n_refs * 32 * 8))) return rc;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    e->set_tb = al((size_t)e->n_warps * e->max_nrb * TS * 64 * 4);      // 64: a pair stores two words per lane
+    e->set_tbb = al((size_t)e->n_warps * PK_BAND_SLOTS * 64 * 4);        // banded slabs (packed path)
+    e->set_tbq = al((size_t)e->n_warps * TS * 64 * 4 + 64);              // ring-banded path: (step, lane) entries
+    e->set_bnd = al((size_t)e->n_warps * 2 * 3 * TS * 4);
+    e->set_ops = al((size_t)e->n_warps * e->n_refs * 32 * 8);
+    if ((rc = ensure(e, e->tb, 2 * e->set_tb))) return rc;
+    if ((rc = ensure(e, e->tbb, 2 * e->set_tbb))) return rc;
+    if ((rc = ensure(e, e->tbq, 2 * e->set_tbq))) return rc;
+    if ((rc = ensure(e, e->bnd, 2 * e->set_bnd))) return rc;
+    if ((rc = ensure(e, e->ops, 2 * e->set_ops))) return rc;
     const bool fresh_work = !e->work.p;
-    if ((rc = ensure(e, e->work, 64))) return rc;
-    if (fresh_work) RTCHK(rt_zero(e->work.p, 64, e->stream));
+    if ((rc = ensure(e, e->work, WORK_BYTES))) return rc;
+    if (fresh_work) RTCHK(rt_zero(e->work.p, WORK_BYTES, e->stream));
     e->scratch_TS = TS;
 #ifndef C2B_EMU
     {   // Keep the traceback slab (written once, read back by the same warp microseconds later) resident in L2:
@@ -479,7 +495,7 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
             !getenv("C2B_NO_L2_PERSIST")) {
-            const size_t slab = (size_t)e->n_warps * PK_BAND_SLOTS * 64 * 4;      // the banded slabs: the hot set
+            const size_t slab = 2 * e->set_tbb;                                   // the banded slabs (both sets): the hot set
             const size_t carve = std::min((size_t)prop.persistingL2CacheMaxSize, slab);
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
             cudaStreamAttrValue av; memset(&av, 0, sizeof av);
@@ -489,6 +505,7 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
             av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            if (e->stream2) cudaStreamSetAttribute(e->stream2, cudaStreamAttributeAccessPolicyWindow, &av);
             cudaGetLastError();
             if (getenv("C2B_VERBOSE"))
                 fprintf(stderr, "[c2b] grid %d x %d warps, banded traceback slabs %.1f MB, persisting L2 max %.1f MB (L2 %.1f MB), window %.1f MB, hitRatio %.2f\n",
@@ -500,10 +517,12 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
     return C2B_OK;
 }
 
-int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t *d_offsets, int64_t n_reads,
-                           int32_t max_read_len, const int32_t *d_count, const int32_t *d_qweight,
-                           const int32_t *d_ref_id, c2b_read_rec *d_recs, c2b_aln_rec *d_alns,
-                           uint8_t *d_strings, c2b_edit *d_edits)
+// One launch on compute stream `cs` using scratch set `set` (0 or 1).  Launches that may overlap in time must use
+// different sets; launches on the same stream are ordered.
+static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_reads, const int64_t *d_offsets, int64_t n_reads,
+                     int32_t max_read_len, const int32_t *d_count, const int32_t *d_qweight,
+                     const int32_t *d_ref_id, c2b_read_rec *d_recs, c2b_aln_rec *d_alns,
+                     uint8_t *d_strings, c2b_edit *d_edits)
 {
     if (!e || !e->configured) return fail(e, C2B_E_STATE, "c2b_align_batch: engine not configured");
     if (n_reads < 0 || !d_recs || !d_alns || (n_reads && (!d_reads || !d_offsets))) return fail(e, C2B_E_ARG, "c2b_align_batch: bad argument");
@@ -525,17 +544,23 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
     P.flags = e->prm.flags; P.nq = e->prm.nq;
     memcpy(P.alpha, e->prm.alphabet, C2B_MAX_Q); memcpy(P.comp, e->prm.complement, C2B_MAX_Q);
     P.TS = e->scratch_TS;
-    P.tb = (uint32_t *)e->tb.p; P.tb_words_per_warp = (int64_t)e->max_nrb * P.TS * 64;
-    P.tbb = getenv("C2B_NO_BAND") ? nullptr : (uint32_t *)e->tbb.p; P.tbb_words_per_warp = (int64_t)PK_BAND_SLOTS * 64;
-    P.tbq = getenv("C2B_NO_RING") ? nullptr : (uint32_t *)e->tbq.p;
-    P.bnd = (int32_t *)e->bnd.p; P.bnd_words_per_warp = 2 * 3 * (int64_t)P.TS;
-    P.opsbuf = (uint64_t *)e->ops.p;
-    P.work_counter = (unsigned long long *)e->work.p;
+    auto at = [&](const DevBuf &b, size_t per_set) { return (char *)b.p + (size_t)set * per_set; };
+    P.tb = (uint32_t *)at(e->tb, e->set_tb); P.tb_words_per_warp = (int64_t)e->max_nrb * P.TS * 64;
+    P.tbb = getenv("C2B_NO_BAND") ? nullptr : (uint32_t *)at(e->tbb, e->set_tbb); P.tbb_words_per_warp = (int64_t)PK_BAND_SLOTS * 64;
+    P.tbq = getenv("C2B_NO_RING") ? nullptr : (uint32_t *)at(e->tbq, e->set_tbq);
+    P.bnd = (int32_t *)at(e->bnd, e->set_bnd); P.bnd_words_per_warp = 2 * 3 * (int64_t)P.TS;
+    P.opsbuf = (uint64_t *)at(e->ops, e->set_ops);
+    P.stats = (unsigned long long *)e->work.p;
+    P.work_counter = P.stats + 8 + 8 * set;
     P.vstride = e->vstride; P.hstride = e->hstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
     P.phase_sync = 4;                                     // warps per phase set (C2B_PHASE_WARPS: 0/1 = free-running, 2, 4, 8)
     if (const char *v = getenv("C2B_PHASE_WARPS")) { const int k = atoi(v), a = k < 0 ? -k : k; P.phase_sync = (a == 2 || a == 4 || a == 8 || a == 16) ? k : 0; }
-    { const int a = P.phase_sync < 0 ? -P.phase_sync : P.phase_sync; if (a > e->wpc || (a && e->wpc % a)) P.phase_sync = 0; }
+    {   // grp_sync wants |g| and the number of sets to be powers of two
+        const int a = P.phase_sync < 0 ? -P.phase_sync : P.phase_sync;
+        const int nsets = a ? e->wpc / a : 0;
+        if (a > e->wpc || (a && e->wpc % a) || (P.phase_sync < 0 && (nsets & (nsets - 1)))) P.phase_sync = 0;
+    }
     P.pair_order = e->pair_order;
     P.lut = (const uint8_t *)e->lut.p;
     P.stage_bytes = 0; P.stage_src = nullptr;
@@ -548,11 +573,11 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
         }
     }
 #endif
-    RTCHK(rt_zero(e->work.p, 16, e->stream));             // [0] work counter, [1] widest alignment; [2],[3] = path statistics (cumulative)
+    RTCHK(rt_zero(P.work_counter, 16, cs));               // this set's work counter and widest alignment
 #ifndef C2B_EMU
-    cudaEventRecord(e->ev0, e->stream);
-    c2b_align_classify_kernel<<<e->grid, e->wpc * 32, (sizeof(WarpSmem) + sizeof(QuadSmem)) * e->wpc + 128 + (size_t)P.stage_bytes, e->stream>>>(P);
-    cudaEventRecord(e->ev1, e->stream);
+    cudaEventRecord(e->ev0, cs);
+    c2b_align_classify_kernel<<<e->grid, e->wpc * 32, (sizeof(WarpSmem) + sizeof(QuadSmem)) * e->wpc + 128 + (size_t)P.stage_bytes, cs>>>(P);
+    cudaEventRecord(e->ev1, cs);
     RTCHK(cudaGetLastError());
 #else
     {
@@ -562,6 +587,15 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
 #endif
     e->launches++;
     return C2B_OK;
+}
+
+int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t *d_offsets, int64_t n_reads,
+                           int32_t max_read_len, const int32_t *d_count, const int32_t *d_qweight,
+                           const int32_t *d_ref_id, c2b_read_rec *d_recs, c2b_aln_rec *d_alns,
+                           uint8_t *d_strings, c2b_edit *d_edits)
+{
+    return launch_on(e, e ? e->stream : 0, 0, d_reads, d_offsets, n_reads, max_read_len, d_count, d_qweight, d_ref_id, d_recs,
+                     d_alns, d_strings, d_edits);
 }
 
 int64_t c2b_band_reruns(c2b_engine *e) { return e ? e->band_reruns : 0; }
@@ -679,6 +713,15 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
         while (n_reads - tail - pos > 0) { pos += std::min(chunk, n_reads - tail - pos); cuts.push_back(pos); }
         if (tail) cuts.push_back(n_reads);
     }
+    // Optional (C2B_TWO_STREAMS=1): kernels of consecutive chunks on two compute streams.  Measured r01k: 42.7 ms per
+    // 1 M reads against 35.7 ms on one stream -- two resident persistent grids slow each other more than the
+    // launch tails cost -- so one stream is the default.
+    bool two_streams = false;
+#ifndef C2B_EMU
+    two_streams = e->stream2 && getenv("C2B_TWO_STREAMS");
+#endif
+    if ((rc = ensure_scratch(e, (int)maxJ))) return rc;       // allocations / memsets on `stream` happen before the fork
+    if (two_streams) { RTCHK(rt_record(e->fork_ev, e->stream)); RTCHK(rt_wait(e->stream2, e->fork_ev)); }
     for (int ci = 0; ci + 1 < (int)cuts.size(); ci++) {
         c2b_engine::Stage &st = e->stage[ci & 1];
         const int64_t c0 = cuts[ci], n = cuts[ci + 1] - cuts[ci];
@@ -731,8 +774,13 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
             e->pair_order = (const int32_t *)st.ord.p;
         }
         RTCHK(rt_record(st.in_done, e->s_in));
-        RTCHK(rt_wait(e->stream, st.in_done));
-        rc = c2b_align_batch_device(e, (const uint8_t *)st.reads.p, (const int64_t *)st.off.p, n, (int32_t)maxJ,
+        // kernels of consecutive chunks go to two compute streams with their own scratch sets: chunk ci+1's CTAs fill
+        // the SMs as chunk ci's CTAs run out of work, instead of waiting for its slowest warp (same-stream launches
+        // of one chunk parity stay ordered, so at most two launches -- of different sets -- are ever resident)
+        const int set = two_streams ? (ci & 1) : 0;
+        rt_stream cs = set ? e->stream2 : e->stream;
+        RTCHK(rt_wait(cs, st.in_done));
+        rc = launch_on(e, cs, set, (const uint8_t *)st.reads.p, (const int64_t *)st.off.p, n, (int32_t)maxJ,
                                     count ? (const int32_t *)st.cnt.p : nullptr, qweight ? (const int32_t *)st.qw.p : nullptr,
                                     ref_id ? (const int32_t *)st.rid.p : nullptr, (c2b_read_rec *)st.recs.p,
                                     (c2b_aln_rec *)st.alns.p, strings ? (uint8_t *)st.str.p : nullptr,
@@ -740,8 +788,8 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
         e->pair_order = nullptr;
         if (rc) return rc;
         // keep this launch's "widest alignment" before the next launch resets it
-        RTCHK(cudaMemcpyAsyncOrCopy(st.maxlen.p, (const char *)e->work.p + 8, 8, e->stream));
-        RTCHK(rt_record(st.k_done, e->stream));
+        RTCHK(cudaMemcpyAsyncOrCopy(st.maxlen.p, (const char *)e->work.p + (9 + 8 * set) * 8, 8, cs));
+        RTCHK(rt_record(st.k_done, cs));
         st.used = true;
         if (pend.any && (rc = flush(pend))) return rc;           // chunk ci-1: overlaps this chunk's kernel
         pend.any = true; pend.c0 = c0; pend.n = n; pend.set = ci & 1;
@@ -749,6 +797,7 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
     if (pend.any && (rc = flush(pend))) return rc;
     RTCHK(rt_sync(e->s_out));
     RTCHK(rt_sync(e->stream));
+    if (two_streams) RTCHK(rt_sync(e->stream2));
     return C2B_OK;
 }
 
@@ -775,7 +824,7 @@ int c2b_counts_reset(c2b_engine *e)
 {
     if (!e || !e->configured) return fail(e, C2B_E_STATE, "c2b_counts_reset: engine not configured");
     RTCHK(rt_zero(e->d_counts, e->counts_n * 8, e->stream));
-    if (e->work.p) RTCHK(rt_zero(e->work.p, 64, e->stream));
+    if (e->work.p) RTCHK(rt_zero(e->work.p, WORK_BYTES, e->stream));
     RTCHK(rt_sync(e->stream));
     return C2B_OK;
 }

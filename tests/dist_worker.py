@@ -38,7 +38,8 @@ def main():
         blk = eng.counts(raw=merged)
         V = blk.vectors("Reference")
         with open(out_path, "w") as fh:
-            json.dump({"world": world, "vectors": {k: v.tolist() for k, v in V.items()}, "scalars": blk.scalars("Reference"),
+            json.dump({"world": world, "vectors": {k: v.tolist() for k, v in V.items()}, "scalars": blk.scalars("Reference"), "classes": blk.class_counts(),
+                       "sizes": {k: {str(a): b for a, b in v.items()} for k, v in blk.size_histograms("Reference").items()},
                        "amp": amp, "reads": reads}, fh)
     dist.barrier()
     dist.destroy_process_group()

@@ -38,7 +38,11 @@ def test_two_ranks_gloo_merge_matches_oracle(tmp_path):
     ref = synth.amplicon_setup(got["amp"], guide_start=50)
     refs = {"Reference": ref}
     cache, stats, lost = O.process_reads(got["reads"], refs, ["Reference"], O.Params(), O.make_matrix())
-    vec, sca, classes, total = O.count_vectors(cache, refs, ["Reference"], O.Params())
+    extras = {}
+    vec, sca, classes, total = O.count_vectors(cache, refs, ["Reference"], O.Params(), extras)
+    assert got["classes"] == classes
+    for name in ("inserted_n", "deleted_n", "substituted_n", "effective_len"):
+        assert got["sizes"][name] == {str(a): b for a, b in extras["Reference"][name].items()}, name
     for name in O.VECTOR_NAMES:
         assert got["vectors"][name] == vec["Reference"][name].tolist(), name
     for name in O.SCALAR_NAMES:
