@@ -894,6 +894,21 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
                 else {
                     // the block of CRISPRessoCORE.py:4085-4171 is entered by modified reads, and by every read of a reference
                     // whose exons changed length (tot_exon_len_mod != 0)
+#ifdef C2B_X_BISECT_R01J      /* measurement only: the r01j body (no size Counters, no --coding_seq, no class deviation) */
+                    const bool lenv = modified && (o.n_ins_win > 0 || o.n_del_win > 0);
+                    if (two_scans || lenv) rows_run(P, R, rowinfo, rowins, o, nullptr, w, (two_scans ? RM_VEC : 0) | (lenv ? RM_LEN : 0));
+                    if (lane == 0) {
+                        wp::addg(SC + C2B_S_TOTAL, w);
+                        wp::addg(SC + (modified ? C2B_S_MODIFIED : C2B_S_UNMODIFIED), w);
+                        if (has_i) wp::addg(SC + C2B_S_INS, w);
+                        if (has_d) wp::addg(SC + C2B_S_DEL, w);
+                        if (has_s) wp::addg(SC + C2B_S_SUB, w);
+                        const int combo = (has_i ? 4 : 0) | (has_d ? 2 : 0) | (has_s ? 1 : 0);
+                        const int slot[8] = {-1, C2B_S_ONLY_SUB, C2B_S_ONLY_DEL, C2B_S_DEL_SUB, C2B_S_ONLY_INS, C2B_S_INS_SUB,
+                                             C2B_S_INS_DEL, C2B_S_INS_DEL_SUB};
+                        if (slot[combo] >= 0) wp::addg(SC + slot[combo], w);
+                    }
+#else
                     const bool entered = modified || R.tem != 0;
                     const bool lenv = entered && (o.n_ins_win > 0 || o.n_del_win > 0);
                     if (two_scans || lenv) rows_run(P, R, rowinfo, rowins, o, nullptr, w, (two_scans ? RM_VEC : 0) | (lenv ? RM_LEN : 0));
@@ -902,15 +917,18 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
                         sc_add(SC, C2B_S_TOTAL, w);
                         sc_add(SC, modified ? C2B_S_MODIFIED : C2B_S_UNMODIFIED, w);
                     }
+#endif
                 }
             } else if (ambiguous && nth == 0 && w > 0 && lane == 0) sc_add(SC, C2B_S_AMBIGUOUS_W, w);
             // class_counts (:3984-3986) as a deviation from counts_modified / counts_unmodified: a discarded read still has
             // its class; a counted winner of an --expand_ambiguous_alignments read with several winners has a joined label
             // (derived on the host) instead
+#ifndef C2B_X_BISECT_R01J
             if (counted && lane == 0 && (two_scans || expand)) {
                 const bool discarded = two_scans && (o.del_n > 0 || o.ins_n > 0), joined = expand && rec.n_winners > 1;
                 if (discarded != joined) sc_add(SC, modified ? C2B_S_CLASS_MODIFIED : C2B_S_CLASS_UNMODIFIED, discarded ? w : -w);
             }
+#endif
             if (lane == 0) {
                 c2b_aln_rec a = multi ? load_aln(P.alns + rd * P.n_refs + r) : a_single;   // single reference: still in registers
                 a.insertion_n = (uint16_t)o.ins_n; a.deletion_n = (uint16_t)o.del_n; a.substitution_n = (uint16_t)o.sub_n;

@@ -140,6 +140,14 @@ def test_full_size_properties(eng):
     assert (V["all_deletion_count"] == V["all_base_count_-"]).all()
     assert blk.scalar("Reference", "MODIFIED") + blk.scalar("Reference", "UNMODIFIED") == tot
     assert blk.scalar("Reference", "MODIFIED") == int(a["modified"][aligned].sum())
+    # size Counters and class_counts recomputed from the per-read records (every read has weight 1 here)
+    H = blk.size_histograms("Reference")
+    for key, col in (("inserted_n", a["insertion_n"]), ("deleted_n", a["deletion_n"]), ("substituted_n", a["substitution_n"]),
+                     ("effective_len", 250 + a["insertion_n"].astype(np.int64) - a["deletion_n"].astype(np.int64))):
+        want = np.bincount(np.asarray(col[aligned], dtype=np.int64))
+        assert dict(H[key]) == {int(k): int(v) for k, v in enumerate(want) if v}, key
+    assert blk.class_counts() == {"Reference_MODIFIED": int(a["modified"][aligned].sum()),
+                                  "Reference_UNMODIFIED": int((a["modified"][aligned] == 0).sum())}
     # re-running the overflowed reads with a cap that cannot overflow (and zero weights) yields the complete lists
     idx = np.nonzero(overflow)[0]
     eng.set_edit_cap(512)
