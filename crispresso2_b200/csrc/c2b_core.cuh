@@ -126,6 +126,7 @@ struct KParams {
     c2b_read_rec *recs; c2b_aln_rec *alns; uint8_t *strings; c2b_edit *edits;
     int32_t W, edit_cap;
     const RefDev *refs; int32_t n_refs;
+    int32_t out_refs, ops_refs;       // output slots per read (1 when ref_id is given: compact Pooled layout, else n_refs); opsbuf refs per warp
     int32_t go, ge, seed_count, seed_min; uint32_t flags; int32_t nq;
     uint8_t alpha[C2B_MAX_Q]; uint8_t comp[C2B_MAX_Q];
     uint32_t *tb; int64_t tb_words_per_warp; int32_t TS;      // TS = steps stride per row block (maxJ + 32)
@@ -133,6 +134,7 @@ struct KParams {
     uint32_t *tbq;                                            // slab of the ring-banded path: [step][lane] uint2, TS steps per warp
     int32_t *bnd; int64_t bnd_words_per_warp;                 // 2 x 3 x (maxJ+1): row-block boundary rows
     uint64_t *opsbuf;                                         // [warp][n_refs][32] op streams (multi-reference)
+    uint64_t *rgops;                                          // [warp][RG_MAX_REFS][4 pairs][RG_OPS_STRIDE]: walked op streams of the multi-reference ring path
     unsigned long long *work_counter;      // [0] work hand-out counter, [1] widest alignment of this launch
     unsigned long long *stats;             // cumulative path statistics (c2b_path_counts), indices 2..6
     int32_t vstride, hstride;
@@ -144,6 +146,9 @@ struct KParams {
     const uint64_t *forced_ops;       // c2b_classify_aligned: op streams supplied by the caller, [read][32]
     const int32_t *forced_n;
 };
+
+// output slot of (read, reference): [read][ref] -- or [read][0] when every read carries its single reference (ref_id)
+C2B_DEV int64_t oslot(const KParams &P, int64_t rd, int r) { return rd * P.out_refs + (P.ref_id ? 0 : r); }
 
 struct WarpSmem {
     uint8_t fw[2][MAXJ];       // read(s) as alphabet codes ([1]: second read of a pair)
@@ -157,6 +162,7 @@ constexpr int PK_ROWINFO_STRIDE = 512, PK_ROWINS_STRIDE = 514, PK_MAX_ALN = 512;
 // (virtual lane L = rows 8L+1..8L+8) one after the other, each for the RG_NS wavefront steps around its diagonal
 // (step t -> slot t - 9L + RG_B); cells with column - row in [-(RG_B+1), RG_NS-RG_B-9] are always inside the band.
 constexpr int RG_NS = 72, RG_B = 32, RG_MAXD = 8, RG_COMBO = 272;
+constexpr int RG_MAX_REFS = 4, RG_OPS_STRIDE = 36;          // multi-reference ring path: references per read; u64 per (reference, pair): 32 op words + (n, err) of each half
 constexpr int RG_DLO = RG_B + 1, RG_DHI = RG_NS - RG_B - 9;
 struct QuadSmem {                                  // per warp; the op streams take the place of the base-pair codes once the DP is done
     union {
@@ -839,7 +845,7 @@ C2B_DEVNOINL int rescatter(const KParams &P, const RefDev &R, int64_t rd, int r,
     uint64_t ops;
     if (hoff < 0) ops = wp::ldcg64(opsbuf + r * 32 + lane);
     else ops = lane < 16 ? wp::ldcg64(opsbuf + r * 32 + hoff + lane) : ~0ull;
-    const c2b_aln_rec prev = load_aln(P.alns + rd * P.n_refs + r);
+    const c2b_aln_rec prev = load_aln(P.alns + oslot(P, rd, r));
     const int n = wp::shfl((int)prev.aln_len, 0), strand = wp::shfl((int)prev.strand, 0);
     const int irr = wp::shfl((int)prev.irregular_ends, 0);
     for (int p = lane; p <= R.I; p += 32) rowins[p] = 0;
@@ -875,7 +881,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             wp::sync();
             RowOut o; o.ins_n = o.del_n = o.sub_n = 0; o.n_ins_all = o.n_ins_win = o.n_del_all = o.n_del_win = 0;
             o.n_del_pos = o.n_sub_all = 0; o.nent = 0;
-            c2b_edit *ed = P.edits ? P.edits + (rd * P.n_refs + r) * (int64_t)P.edit_cap : nullptr;
+            c2b_edit *ed = P.edits ? P.edits + oslot(P, rd, r) * (int64_t)P.edit_cap : nullptr;
             const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
                        ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
             // contribution to the count block (CRISPRessoCORE.py:3989-4072); known before the scan unless
@@ -930,14 +936,14 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             }
 #endif
             if (lane == 0) {
-                c2b_aln_rec a = multi ? load_aln(P.alns + rd * P.n_refs + r) : a_single;   // single reference: still in registers
+                c2b_aln_rec a = multi ? load_aln(P.alns + oslot(P, rd, r)) : a_single;   // single reference: still in registers
                 a.insertion_n = (uint16_t)o.ins_n; a.deletion_n = (uint16_t)o.del_n; a.substitution_n = (uint16_t)o.sub_n;
                 a.n_ins_all = (uint16_t)o.n_ins_all; a.n_ins_win = (uint16_t)o.n_ins_win;
                 a.n_del_all = (uint16_t)o.n_del_all; a.n_del_win = (uint16_t)o.n_del_win;
                 a.n_del_pos_all = (uint16_t)o.n_del_pos; a.n_sub_all = (uint16_t)o.n_sub_all;
                 a.n_edits = (uint16_t)o.nent; a.modified = modified; a.status |= (uint8_t)astatus;
                 a.irregular_ends = (uint8_t)irr;
-                P.alns[rd * P.n_refs + r] = a;
+                P.alns[oslot(P, rd, r)] = a;
             }
             rec.status |= astatus;
             nth++;
@@ -985,7 +991,7 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
     const int J = (int)(P.offsets[rd + 1] - off);
     uint32_t *tb = P.tb + (int64_t)warp_slot * P.tb_words_per_warp;
     int32_t *bnd = P.bnd + (int64_t)warp_slot * P.bnd_words_per_warp;
-    uint64_t *opsbuf = P.opsbuf + (int64_t)warp_slot * P.n_refs * 32;
+    uint64_t *opsbuf = P.opsbuf + (int64_t)warp_slot * P.ops_refs * 32;
 
     c2b_read_rec rec; rec.winner_mask = 0; rec.best_score_milli = -1000; rec.best_ref = -1; rec.n_winners = 0;
     rec.ambiguous = 0; rec.status = 0;
@@ -1024,7 +1030,7 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
                 const bool use_rc = (mode == 1) || (mode == 2 && sr > sf);      // strict '>' of CRISPRessoCORE.py:682
                 const Walked &wk = use_rc ? wr : wf;
                 const uint8_t *codes = use_rc ? S.rc[0] : S.fw[0];
-                uint8_t *o_read = P.strings ? P.strings + ((rd * P.n_refs + r) * 2) * (int64_t)P.W : nullptr;
+                uint8_t *o_read = P.strings ? P.strings + (oslot(P, rd, r) * 2) * (int64_t)P.W : nullptr;
                 uint8_t *o_ref = o_read ? o_read + P.W : nullptr;
                 int cmode = (o_read ? 1 : 0);
                 if (!multi) {                                   // single reference: scatter now, classify below
@@ -1043,7 +1049,7 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
             }
         }
         rec.status |= a.status;
-        if (lane == 0) P.alns[rd * P.n_refs + r] = a;
+        if (lane == 0) P.alns[oslot(P, rd, r)] = a;
     }
     wp::sync();
     finish_read(P, rd, rec, J, S.fw[0], S.rc[0], S.rowinfo, S.rowins, r_begin, r_end, opsbuf, -1, keep_irr, a);
@@ -1291,7 +1297,10 @@ C2B_DEV int ring_bound(const KParams &P, const RefDev &R, int J)
     return U;
 }
 
-struct RingCtx { const uint64_t *ops; const int32_t *n, *err; int modes; };   // a pair aligned by dp_ring: its walked op streams, lengths, strand modes
+// A pair aligned by dp_ring: its walked op streams, lengths, strand modes.  ref_stride == 0: one reference, streams in shared
+// memory (ops/n/err).  ref_stride > 0: several references tried, reference k's block (RG_OPS_STRIDE u64, global scratch,
+// written by this warp) starts at ops + k * ref_stride; refmask bit k = the band held for reference k.
+struct RingCtx { const uint64_t *ops; const int32_t *n, *err; int modes; int ref_stride; uint32_t refmask; };
 #if defined(C2B_X_ONE_CLASSIFY_BARRIER) && defined(C2B_X_NO_PASS_BARRIER)
 constexpr int PAIR_PHASES = 3;
 #elif defined(C2B_X_ONE_CLASSIFY_BARRIER) || defined(C2B_X_NO_PASS_BARRIER)
@@ -1314,7 +1323,7 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
     uint2 *tb2 = reinterpret_cast<uint2 *>(P.tb + (int64_t)warp_slot * P.tb_words_per_warp);
     uint2 *tbb = P.tbb ? reinterpret_cast<uint2 *>(P.tbb + (int64_t)warp_slot * P.tbb_words_per_warp) : nullptr;
     int32_t *bnd = P.bnd + (int64_t)warp_slot * P.bnd_words_per_warp;
-    uint64_t *opsbuf = P.opsbuf + (int64_t)warp_slot * P.n_refs * 32;
+    uint64_t *opsbuf = P.opsbuf + (int64_t)warp_slot * P.ops_refs * 32;
     uint8_t *rowinfo = S.rowinfo + h * PK_ROWINFO_STRIDE;
     uint32_t *rowins = S.rowins + h * PK_ROWINS_STRIDE;
 
@@ -1355,7 +1364,13 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
             if (phased && pass == 0) wp::grp_sync(P.phase_sync);
 #endif
             Walked wk; wk.err = 4;
-            if (ring) { wk.ops = ring->ops[lane]; wk.n = ring->n[h]; wk.err = ring->err[h]; }   // aligned and walked by process_quad
+            if (ring && ring->ref_stride == 0) { wk.ops = ring->ops[lane]; wk.n = ring->n[h]; wk.err = ring->err[h]; }   // aligned and walked by process_quad
+            else if (ring && ((ring->refmask >> (r - r_begin)) & 1u)) {
+                const uint64_t *o = ring->ops + (int64_t)(r - r_begin) * ring->ref_stride;
+                wk.ops = wp::ldcg64(o + lane);
+                const uint64_t mt = wp::ldcg64(o + 32 + h);
+                wk.n = (int)(uint32_t)mt; wk.err = (int)(mt >> 32);
+            }
             if (wk.err & 4) {
                 for (int p = lane; p < J; p += 32) S.combo[p] = (uint8_t)(cA[p] * P.nq + cB[p]);
                 wp::sync();
@@ -1375,7 +1390,7 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
         for (int p = lane; p < 2 * PK_ROWINS_STRIDE; p += 32) S.rowins[p] = 0;
         wp::sync();
         if (phased) wp::grp_sync(P.phase_sync);
-        uint8_t *o_read = P.strings ? P.strings + ((myrd * P.n_refs + r) * 2) * (int64_t)P.W : nullptr;
+        uint8_t *o_read = P.strings ? P.strings + (oslot(P, myrd, r) * 2) * (int64_t)P.W : nullptr;
         uint8_t *o_ref = o_read ? o_read + P.W : nullptr;
         int cmode = (o_read ? 1 : 0) | (multi ? 0 : 2);
         if (a.status) cmode = 0;
@@ -1390,7 +1405,7 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
         }
         if (multi) opsbuf[r * 32 + lane] = bops;
         rec.status |= a.status;
-        if (hl == 0 && (h == 0 || rdB != rdA)) P.alns[myrd * P.n_refs + r] = a;
+        if (hl == 0 && (h == 0 || rdB != rdA)) P.alns[oslot(P, myrd, r)] = a;
     }
     wp::sync();
     // classification runs with the whole warp, one read at a time: broadcast that half's bookkeeping to every lane.
@@ -1528,7 +1543,103 @@ C2B_DEV void process_quad(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint
         const int64_t rdA = P.pair_order ? P.pair_order[2 * (first + q)] : 2 * (first + q);
         const int64_t rdB = P.pair_order ? P.pair_order[2 * (first + q) + 1] : 2 * (first + q) + 1;
         RingCtx rc; rc.ops = Q.wk.ops[q]; rc.n = Q.wk.n[q]; rc.err = Q.wk.err[q]; rc.modes = (int)((modes >> (4 * q)) & 15u);
+        rc.ref_stride = 0; rc.refmask = 1u;
         process_pair(P, S, staged_prof, rdA, rdB, warp_slot, ((passmask >> q) & 1u) ? &rc : nullptr, P.phase_sync != 0);
+        wp::sync();
+    }
+}
+
+// Ring-banded path when every read is tried against several references (HDR mode, 2..RG_MAX_REFS amplicons): the four pairs'
+// combined codes are built once (a pair qualifies only if every reference's seed test picks the same single strand), then
+// each reference in turn runs dp_ring over the same codes and its tracebacks, leaving the walked op streams in global
+// scratch (rgops); process_pair picks them up per reference and falls back to the full matrix where the band did not hold.
+C2B_DEVNOINL void process_quad_multi(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint32_t *staged_prof, int64_t first, int warp_slot)
+{
+    const int lane = wp::lane(), g = lane >> 3;
+    uint2 *tbq = reinterpret_cast<uint2 *>(P.tbq + (int64_t)warp_slot * P.TS * 64);
+    uint64_t *rgo = P.rgops + (int64_t)warp_slot * RG_MAX_REFS * 4 * RG_OPS_STRIDE;
+    if (P.phase_sync) wp::grp_sync(P.phase_sync);
+    uint32_t okmask = 0, modes = 0;
+    int Jg = 0, Jmax = 0;
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        const int64_t rdA = P.pair_order ? P.pair_order[2 * (first + q)] : 2 * (first + q);
+        const int64_t rdB = P.pair_order ? P.pair_order[2 * (first + q) + 1] : 2 * (first + q) + 1;
+        const int J = (int)(P.offsets[rdA + 1] - P.offsets[rdA]);
+        bool bad = false;
+#pragma unroll 1
+        for (int x = 0; x < 2; x++) bad |= load_codes(P, P.offsets[x ? rdB : rdA], J, S.fw[x], S.rc[x]);
+        wp::sync();
+        int mAB = 0; bool agree = true;
+#pragma unroll 1
+        for (int r = 0; r < P.n_refs; r++) {
+            int m = 0;
+#pragma unroll 1
+            for (int x = 0; x < 2; x++) m |= strand_mode(P, P.refs[r], S.fw[x], J) << (2 * x);
+            if (r == 0) mAB = m; else agree = agree && (m == mAB);
+        }
+        const int mA = mAB & 3, mB = mAB >> 2;
+        if (!bad && agree && mA != 2 && mB != 2) {
+            const uint8_t *cA = mA ? S.rc[0] : S.fw[0], *cB = mB ? S.rc[1] : S.fw[1];
+            for (int p = lane; p < J; p += 32) Q.combo[q][p] = (uint8_t)(cA[p] * P.nq + cB[p]);
+            okmask |= 1u << q; modes |= (uint32_t)mAB << (4 * q);
+            if (g == q) Jg = J;
+            if (J > Jmax) Jmax = J;
+        }
+        wp::sync();
+    }
+    if (P.phase_sync) wp::grp_sync(P.phase_sync);
+    uint32_t passall = 0;                                   // bit 4k + q: the band held for pair q against reference k
+    int npass = 0;
+#pragma unroll 1
+    for (int k = 0; k < P.n_refs && okmask; k++) {
+        const RefDev &R = P.refs[k];
+        const bool staged = (k == 0 && staged_prof != nullptr);
+        uint32_t *fin = S.rowins;
+        if (staged) dp_ring<true>(P, R, staged_prof, Q.combo[g], Jg, Jmax + R.lstar, tbq, fin);
+        else dp_ring<false>(P, R, R.prof2, Q.combo[g], Jg, Jmax + R.lstar, tbq, fin);
+        wp::sync();
+        const int fl = 3 * ((lane & 24) | (R.lstar & 7));
+        const uint32_t cM = Jg > 0 ? fin[fl] : PK_SENT, cX = Jg > 0 ? fin[fl + 1] : PK_SENT, cY = Jg > 0 ? fin[fl + 2] : PK_SENT;
+        wp::sync();
+        const uint32_t z = wp::max3_2(cM, cY, cX);
+        const uint32_t s2 = z & PK_TM;
+        const int thr = ring_bound(P, R, Jg) + 512 - P.ge * (R.I + Jg);
+        const bool pass = Jg > 0 && (int)((z & 0xffffu) >> 2) > thr && (int)(z >> 18) > thr;
+        const uint32_t b = wp::ballot(pass);
+        uint32_t passmask = (b & 1u) | ((b >> 7) & 2u) | ((b >> 14) & 4u) | ((b >> 21) & 8u);
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            if (!((passmask >> q) & 1u)) continue;
+            const uint32_t sq = wp::shflu(s2, 8 * q);
+            const int Jq = wp::shfl(Jg, 8 * q);
+            const int s0 = (lane & 16) ? (int)(sq >> 16) : (int)(sq & 3u);
+            const Walked wk = walk_batch<true>(P, R, Jq, reinterpret_cast<const uint32_t *>(tbq), s0, SlabMode{9, RG_B, RG_NS, 1, 8 * q});
+            if (wp::ballot((wk.err & 4) != 0)) passmask &= ~(1u << q);
+            else {
+                uint64_t *o = rgo + (int64_t)(k * 4 + q) * RG_OPS_STRIDE;
+                o[lane] = wk.ops;
+                if ((lane & 15) == 0) o[32 + (lane >> 4)] = (uint64_t)(uint32_t)wk.n | ((uint64_t)(uint32_t)wk.err << 32);
+            }
+        }
+        passall |= passmask << (4 * k);
+        npass += wp::popc(passmask);
+        wp::sync();
+    }
+    if (P.phase_sync) wp::grp_sync(P.phase_sync);
+    if (lane == 0) {
+        wp::addg(P.stats + 2, 4);
+        wp::addg(P.stats + 5, npass);
+        wp::addg(P.stats + 6, 4 * P.n_refs - npass);
+    }
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        const int64_t rdA = P.pair_order ? P.pair_order[2 * (first + q)] : 2 * (first + q);
+        const int64_t rdB = P.pair_order ? P.pair_order[2 * (first + q) + 1] : 2 * (first + q) + 1;
+        RingCtx rc; rc.ops = rgo + (int64_t)q * RG_OPS_STRIDE; rc.n = nullptr; rc.err = nullptr;
+        rc.modes = (int)((modes >> (4 * q)) & 15u); rc.ref_stride = 4 * RG_OPS_STRIDE; rc.refmask = 0;
+        for (int k = 0; k < P.n_refs; k++) rc.refmask |= ((passall >> (4 * k + q)) & 1u) << k;
+        process_pair(P, S, staged_prof, rdA, rdB, warp_slot, ((okmask >> q) & 1u) ? &rc : nullptr, P.phase_sync != 0);
         wp::sync();
     }
 }
@@ -1539,20 +1650,26 @@ C2B_DEV void process_group(const KParams &P, WarpSmem &S, QuadSmem &Q, const uin
 {
     const int lane = wp::lane();
     const int64_t first = 4 * wq;
+    const bool multi = P.ref_id == nullptr && P.n_refs > 1;
     bool quad = !P.forced_ops && !(P.flags & (C2B_F_NO_PAIRING | C2B_F_NO_RING)) && P.tbq != nullptr &&
-                2 * first + 7 < P.n_reads && (P.ref_id != nullptr || P.n_refs == 1);
+                2 * first + 7 < P.n_reads && (!multi || (P.n_refs <= RG_MAX_REFS && P.rgops != nullptr));
     if (quad) {
         const int x = lane & 7;
         const int64_t rd = P.pair_order ? P.pair_order[2 * first + x] : 2 * first + x;
         const int Jx = (int)(P.offsets[rd + 1] - P.offsets[rd]);
         const int rx = P.ref_id ? P.ref_id[rd] : 0;
         const int r0 = wp::shfl(rx, 0);
-        const RefDev &R = P.refs[r0];
-        const bool ok = rx == r0 && Jx == wp::shfl_xor(Jx, 1) && R.rg_ok && Jx >= 1 && Jx <= R.pk_maxJ && Jx <= RG_COMBO &&
-                        Jx - R.I <= RG_MAXD && R.I - Jx <= RG_MAXD && Jx + 32 <= P.TS;
+        const int Jn = wp::shfl_xor(Jx, 1);                 // unconditional: every lane takes part in the exchange
+        bool ok = rx == r0 && Jx == Jn && Jx >= 1 && Jx <= RG_COMBO && Jx + 32 <= P.TS;
+        const int k0 = multi ? 0 : r0, k1 = multi ? P.n_refs : r0 + 1;
+        for (int k = k0; k < k1; k++) {                     // every reference the reads are tried against must admit the band
+            const RefDev &R = P.refs[k];
+            ok = ok && R.rg_ok && Jx <= R.pk_maxJ && Jx - R.I <= RG_MAXD && R.I - Jx <= RG_MAXD;
+        }
         quad = wp::ballot(ok) == 0xffffffffu;
     }
-    if (quad) process_quad(P, S, Q, staged_prof, first, warp_slot);
+    if (quad && multi) process_quad_multi(P, S, Q, staged_prof, first, warp_slot);
+    else if (quad) process_quad(P, S, Q, staged_prof, first, warp_slot);
     else {
 #pragma unroll 1
         for (int q = 0; q < 4; q++)

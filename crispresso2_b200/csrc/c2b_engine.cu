@@ -158,7 +158,7 @@ struct c2b_engine {
     void *d_tables = nullptr; RefDev *d_refs = nullptr;
     unsigned long long *d_counts = nullptr; size_t counts_n = 0;
     // scratch
-    DevBuf tb, tbb, tbq, bnd, ops, work, lut;
+    DevBuf tb, tbb, tbq, bnd, ops, rgo, work, lut;
     int n_warps = 0, grid = 0, wpc = 8, stage_cap = 0;
     int scratch_TS = 0;
     // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
@@ -166,7 +166,7 @@ struct c2b_engine {
                    rt_event in_done, k_done, out_done; bool used = false; } stage[2];
     rt_stream s_in = 0, s_out = 0, stream2 = 0;     // stream2: second compute stream, kernels of odd chunks
     rt_event fork_ev = 0;                           // orders stream2 after what is already queued on `stream`
-    size_t set_tb = 0, set_tbb = 0, set_tbq = 0, set_bnd = 0, set_ops = 0;   // bytes per scratch set (two sets: kernels of
+    size_t set_tb = 0, set_tbb = 0, set_tbq = 0, set_bnd = 0, set_ops = 0, set_rgo = 0;   // bytes per scratch set (two sets: kernels of
                                                     // consecutive chunks overlap their tail / head on the two streams)
     bool pipe_ready = false;
     double last_ms = 0; int64_t launches = 0;
@@ -243,7 +243,7 @@ int c2b_create(int device, c2b_engine **out)
 void c2b_destroy(c2b_engine *e)
 {
     if (!e) return;
-    DevBuf *bufs[] = {&e->tb, &e->tbb, &e->tbq, &e->bnd, &e->ops, &e->work, &e->lut};
+    DevBuf *bufs[] = {&e->tb, &e->tbb, &e->tbq, &e->bnd, &e->ops, &e->rgo, &e->work, &e->lut};
     for (DevBuf *b : bufs) if (b->p) rt_free(b->p);
     for (auto &st : e->stage) {
         DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed, &st.maxlen, &st.ord};
@@ -282,7 +282,7 @@ static uint64_t pack_seed(const c2b_params &p, const std::string &s)
 int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_ref *refs)
 {
     if (!e || !p || !refs || n_refs < 1) return fail(e, C2B_E_ARG, "c2b_configure: bad argument");
-    if (n_refs > C2B_MAX_REFS) return fail(e, C2B_E_LIMIT, "c2b_configure: more than C2B_MAX_REFS references");
+    if (n_refs > C2B_MAX_POOLED_REFS) return fail(e, C2B_E_LIMIT, "c2b_configure: more than C2B_MAX_POOLED_REFS references");
     if (p->nq < 1 || p->nq > C2B_MAX_Q) return fail(e, C2B_E_ARG, "c2b_configure: alphabet size out of range");
     if (p->seed_count < 0 || p->edit_cap < 0) return fail(e, C2B_E_ARG, "c2b_configure: negative seed_count/edit_cap");
     e->configured = false;
@@ -479,12 +479,14 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
     e->set_tbb = al((size_t)e->n_warps * PK_BAND_SLOTS * 64 * 4);        // banded slabs (packed path)
     e->set_tbq = al((size_t)e->n_warps * TS * 64 * 4 + 64);              // ring-banded path: (step, lane) entries
     e->set_bnd = al((size_t)e->n_warps * 2 * 3 * TS * 4);
-    e->set_ops = al((size_t)e->n_warps * e->n_refs * 32 * 8);
+    e->set_ops = al((size_t)e->n_warps * std::min(e->n_refs, (int)C2B_MAX_REFS) * 32 * 8);
     if ((rc = ensure(e, e->tb, 2 * e->set_tb))) return rc;
     if ((rc = ensure(e, e->tbb, 2 * e->set_tbb))) return rc;
     if ((rc = ensure(e, e->tbq, 2 * e->set_tbq))) return rc;
     if ((rc = ensure(e, e->bnd, 2 * e->set_bnd))) return rc;
     if ((rc = ensure(e, e->ops, 2 * e->set_ops))) return rc;
+    e->set_rgo = al((size_t)e->n_warps * RG_MAX_REFS * 4 * RG_OPS_STRIDE * 8);
+    if ((rc = ensure(e, e->rgo, 2 * e->set_rgo))) return rc;
     const bool fresh_work = !e->work.p;
     if ((rc = ensure(e, e->work, WORK_BYTES))) return rc;
     if (fresh_work) RTCHK(rt_zero(e->work.p, WORK_BYTES, e->stream));
@@ -530,6 +532,8 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
     if (max_read_len > C2B_MAX_READ_LEN) return fail(e, C2B_E_LIMIT, "c2b_align_batch: read longer than C2B_MAX_READ_LEN");
     if ((int64_t)std::abs((long long)e->prm.gap_open) * max_read_len * e->max_I >= (1ll << 28))
         return fail(e, C2B_E_LIMIT, "c2b_align_batch: gap_open * lengths exceeds the int32 score range");
+    if (!d_ref_id && e->n_refs > C2B_MAX_REFS)
+        return fail(e, C2B_E_LIMIT, "c2b_align_batch: more than C2B_MAX_REFS references need a per-read ref_id");
     int rc = ensure_scratch(e, max_read_len);
     if (rc) return rc;
     if (n_reads == 0) return C2B_OK;
@@ -540,6 +544,7 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
     P.W = (e->max_I + max_read_len + 31) & ~31; P.edit_cap = d_edits ? e->prm.edit_cap : 0;
     if (P.edit_cap == 0) P.edits = nullptr;
     P.refs = e->d_refs; P.n_refs = e->n_refs;
+    P.out_refs = d_ref_id ? 1 : e->n_refs; P.ops_refs = std::min(e->n_refs, (int)C2B_MAX_REFS);
     P.go = e->prm.gap_open; P.ge = e->prm.gap_extend; P.seed_count = e->prm.seed_count; P.seed_min = e->prm.seed_min;
     P.flags = e->prm.flags; P.nq = e->prm.nq;
     memcpy(P.alpha, e->prm.alphabet, C2B_MAX_Q); memcpy(P.comp, e->prm.complement, C2B_MAX_Q);
@@ -550,6 +555,7 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
     P.tbq = getenv("C2B_NO_RING") ? nullptr : (uint32_t *)at(e->tbq, e->set_tbq);
     P.bnd = (int32_t *)at(e->bnd, e->set_bnd); P.bnd_words_per_warp = 2 * 3 * (int64_t)P.TS;
     P.opsbuf = (uint64_t *)at(e->ops, e->set_ops);
+    P.rgops = getenv("C2B_NO_MULTI_RING") ? nullptr : (uint64_t *)at(e->rgo, e->set_rgo);
     P.stats = (unsigned long long *)e->work.p;
     P.work_counter = P.stats + 8 + 8 * set;
     P.vstride = e->vstride; P.hstride = e->hstride;
@@ -561,6 +567,8 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
         const int nsets = a ? e->wpc / a : 0;
         if (a > e->wpc || (a && e->wpc % a) || (P.phase_sync < 0 && (nsets & (nsets - 1)))) P.phase_sync = 0;
     }
+    // several references per read: the per-pair barrier count depends on the number of references, so warps run free
+    if (e->n_refs > 1 && !d_ref_id) P.phase_sync = 0;
     P.pair_order = e->pair_order;
     P.lut = (const uint8_t *)e->lut.p;
     P.stage_bytes = 0; P.stage_src = nullptr;
@@ -673,7 +681,7 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
     }
     const int W = (e->max_I + (int)maxJ + 31) & ~31;
     const int cap = edits ? e->prm.edit_cap : 0;
-    const int nr = e->n_refs;
+    const int nr = ref_id ? 1 : e->n_refs;                 // output slots per read (compact when ref_id is given)
     // Chunks pipeline through two staging sets: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c.
     const int64_t per_read = (int64_t)nr * (2 * (int64_t)W * (strings ? 1 : 0) + (int64_t)cap * 8 + 32) + 16 + maxJ + 24;
     int64_t chunk = std::max<int64_t>(4096, std::min<int64_t>((int64_t)(768ll << 20) / per_read, 1 << 17));

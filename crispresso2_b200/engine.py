@@ -21,9 +21,9 @@ class BatchResult:
     """Views over one batch's outputs.
 
     recs    : REC_DTYPE  [n]
-    alns    : ALN_DTYPE  [n, n_refs]
-    strings : uint8      [n, n_refs, 2, W]   (right-aligned; [.., 0, :] read, [.., 1, :] reference) or None
-    edits   : EDIT_DTYPE [n, n_refs, cap] or None
+    alns    : ALN_DTYPE  [n, R]            R = n_refs, or 1 when the batch carried a per-read ref_id (Pooled)
+    strings : uint8      [n, R, 2, W]      (right-aligned; [.., 0, :] read, [.., 1, :] reference) or None
+    edits   : EDIT_DTYPE [n, R, cap] or None
     """
 
     def __init__(self, recs, alns, strings, edits, W):
@@ -151,10 +151,11 @@ class Engine:
         n = len(off) - 1
         maxj = int(np.max(np.diff(off))) if n else 1
         W = self.string_width(max(maxj, 1))
+        nr = 1 if ref_id is not None else self.n_refs      # Pooled (per-read ref_id): compact outputs, [read][0]
         recs = np.zeros(n, dtype=_lib.REC_DTYPE)
-        alns = np.zeros((n, self.n_refs), dtype=_lib.ALN_DTYPE)
-        sarr = np.zeros((n, self.n_refs, 2, W), dtype=np.uint8) if strings else None
-        earr = np.zeros((n, self.n_refs, self.edit_cap), dtype=_lib.EDIT_DTYPE) if (edits and self.edit_cap) else None
+        alns = np.zeros((n, nr), dtype=_lib.ALN_DTYPE)
+        sarr = np.zeros((n, nr, 2, W), dtype=np.uint8) if strings else None
+        earr = np.zeros((n, nr, self.edit_cap), dtype=_lib.EDIT_DTYPE) if (edits and self.edit_cap) else None
 
         def ptr(a, dt=None):
             if a is None:

@@ -25,7 +25,8 @@ extern "C" {
 #define C2B_MAX_REF_LEN  1024   /* amplicon length limit of this build */
 #define C2B_MAX_READ_LEN 512
 #define C2B_MAX_ALN_LEN  1024   /* I + J */
-#define C2B_MAX_REFS     32
+#define C2B_MAX_REFS     32     /* references tried per read (ref_id == NULL) */
+#define C2B_MAX_POOLED_REFS 1024 /* references per configuration when every read names its own (ref_id, Pooled) */
 
 /* status codes */
 #define C2B_OK            0
@@ -189,9 +190,11 @@ int  c2b_set_edit_cap(c2b_engine *e, int32_t edit_cap);
 
 /* Output geometry for a batch whose longest read is max_read_len:
  *   string width W (multiple of 16): every aligned string is right-aligned in a W-byte slot;
- *   alns    : n_reads * n_refs records, [read][ref]
- *   strings : n_reads * n_refs * 2 * W bytes, [read][ref][0 = read, 1 = reference][W]
- *   edits   : n_reads * n_refs * edit_cap entries                                                  */
+ *   alns    : n_reads * R records, [read][ref]
+ *   strings : n_reads * R * 2 * W bytes, [read][ref][0 = read, 1 = reference][W]
+ *   edits   : n_reads * R * edit_cap entries
+ * R = n_refs when every reference is tried (ref_id == NULL); R = 1 when ref_id is given (Pooled: each read is aligned
+ * to its own amplicon only, so the outputs are compact [read][0]).                                   */
 int  c2b_string_width(const c2b_engine *e, int32_t max_read_len);
 
 /* replaces: the serial loop of process_fastq over unique reads (CRISPRessoCORE.py:1956-1981), i.e. one
@@ -201,7 +204,8 @@ int  c2b_string_width(const c2b_engine *e, int32_t max_read_len);
  *   reads/offsets : packed ASCII reads, offsets[n_reads+1]
  *   count         : dedup multiplicity per read (variant_count of :1957)          (NULL = 1)
  *   qweight       : count after the reverse-complement merge of :3971-3975        (NULL = count)
- *   ref_id        : NULL = try every reference; else the single reference index of each read (Pooled)
+ *   ref_id        : NULL = try every reference (at most C2B_MAX_REFS configured); else the single reference index of
+ *                   each read (Pooled; up to C2B_MAX_POOLED_REFS configured; outputs are [read][0])
  *   strings/edits may be NULL (not produced).                                                         */
 int  c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads,
                      const int32_t *count, const int32_t *qweight, const int32_t *ref_id,

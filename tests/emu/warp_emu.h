@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <execinfo.h>
 #include <ucontext.h>
 
 #define C2B_DEV static inline
@@ -58,7 +59,11 @@ inline uint64_t exchange(uint64_t v, int kind, int src_lane_fn(int, int), int ar
     yield();
     for (int q = 0; q < 32; q++) {
         if (w->cnt[q] < w->cnt[l]) { fprintf(stderr, "warp_emu: lane %d did not reach a collective (kind %d) that lane %d executes\n", q, kind, l); abort(); }
-        if (w->tag[b][q] != kind) { fprintf(stderr, "warp_emu: divergent collective (lane %d kind %d vs %d)\n", q, w->tag[b][q], kind); abort(); }
+        if (w->tag[b][q] != kind) {
+            fprintf(stderr, "warp_emu: divergent collective (lane %d kind %d vs lane %d kind %d)\n", q, w->tag[b][q], l, kind);
+            void *bt[24]; const int nbt = backtrace(bt, 24); backtrace_symbols_fd(bt, nbt, 2);     // call path of lane l (build with -O0 -g -rdynamic)
+            abort();
+        }
     }
     const int s = src_lane_fn(l, arg);
     return w->slot[b][s];

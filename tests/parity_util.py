@@ -159,8 +159,9 @@ def check_pooled(engine, n_amplicons=6, reads_per=40, seed=21, amp_len=(120, 200
         k = rid[i]
         per_amp[k].append(s)
         want = O.new_variant(params, s, {names[k]: refs[names[k]]}, [names[k]], m)
-        a = res.alns[i, k]
-        assert (res.pair(i, k)[0], res.pair(i, k)[1], res.score(i, k)) == tuple(want["ref_aln_details"][0][1:]), (i, k)
+        a = res.alns[i, 0]                              # compact Pooled layout: [read][0]
+        assert int(res.recs[i]["best_ref"]) == (k if want["best_match_score"] > 0 else -1)
+        assert (res.pair(i, 0)[0], res.pair(i, 0)[1], res.score(i, 0)) == tuple(want["ref_aln_details"][0][1:]), (i, k)
         aligned = want["best_match_score"] > 0
         assert (res.recs[i]["best_score_milli"] > 0) == aligned
         if aligned:

@@ -128,6 +128,7 @@ def test_ring_banded_path_equals_full_matrix(emu, I):
 
 def test_pooled_ref_id(emu):
     PU.check_pooled(emu, n_amplicons=4, reads_per=24)
+    PU.check_pooled(emu, n_amplicons=40, reads_per=3, seed=5)          # more references than C2B_MAX_REFS: Pooled only
 
 
 def test_chunked_pipeline_equals_one_chunk(emu, monkeypatch):
@@ -173,3 +174,18 @@ def test_banded_slab_falls_back_to_full_slab(emu):
 
 def test_coding_seq_frameshift_splicing_and_size_histograms(emu):
     PU.check_coding_seq(emu, n_reads=60)
+
+
+def test_small_odd_batches_keep_the_warp_convergent(emu):
+    """Tiny, ragged batches (odd read counts, mixed amplicons inside a work group, mixed lengths): the emulator aborts on
+    any collective that not every lane reaches, which on the GPU would be undefined behaviour."""
+    for seed in range(6):
+        PU.check_pooled(emu, n_amplicons=2 + seed, reads_per=1 + seed % 4, seed=100 + seed)
+    rng = np.random.default_rng(2)
+    amp = synth.random_amplicon(rng, 150)
+    ref = synth.amplicon_setup(amp, guide_start=60)
+    for n in (1, 2, 3, 5, 7, 9, 15, 17):
+        reads = [r.tobytes().decode() for r in synth.synth_reads(rng, amp, n, 150, sub_rate=0.02, rc_frac=0.2, cut=ref["cut_point"])]
+        for k in range(0, n, 3):
+            reads[k] = reads[k][: 40 + 13 * k]
+        PU.check_against_oracle(emu, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())

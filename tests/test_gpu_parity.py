@@ -212,6 +212,7 @@ def test_ring_banded_path_equals_full_matrix(eng, I):
 def test_pooled_ref_id(eng):
     """BASELINE configs[3] shape: many amplicons, each read aligned to its own one (ref_id), one launch."""
     PU.check_pooled(eng, n_amplicons=24, reads_per=120, amp_len=(180, 280))
+    PU.check_pooled(eng, n_amplicons=96, reads_per=24, amp_len=(180, 280), seed=8)   # configs[3]: 96 amplicons in one configuration
 
 
 def test_long_amplicon_three_row_blocks(eng):

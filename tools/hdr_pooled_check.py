@@ -14,12 +14,17 @@ def run(name, refs, names, reads, ref_id, flags, sample_check):
     n = len(reads)
     eng = Engine(0)
     eng.configure(refs, names, m, -20, -2, 5, 2, flags, 'ACGTN', 8)
-    L, nr = eng.L, len(names)
+    L = eng.L
+    nr = 1 if ref_id is not None else len(names)        # Pooled: compact outputs [read][0]
     J = reads.shape[1]
     W = eng.string_width(J)
     d_reads = torch.from_numpy(reads.reshape(-1)).to(dev)
     d_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * J
     d_rid = torch.from_numpy(ref_id).to(dev) if ref_id is not None else None
+    d_ord = None
+    if ref_id is not None:                               # pairing order: reads of one amplicon adjacent (c2b_align_batch does this itself)
+        d_ord = torch.from_numpy(np.argsort(ref_id, kind='stable').astype(np.int32)).to(dev)
+        L.c2b_set_pair_order(eng.h, d_ord.data_ptr())
     d_recs = torch.empty(n * 16, dtype=torch.uint8, device=dev)
     d_alns = torch.empty(n * nr * 32, dtype=torch.uint8, device=dev)
     d_str = torch.empty(n * nr * 2 * W, dtype=torch.uint8, device=dev)
@@ -37,9 +42,9 @@ def run(name, refs, names, reads, ref_id, flags, sample_check):
     recs = np.frombuffer(d_recs.cpu().numpy().tobytes(), dtype=_lib.REC_DTYPE)
     alns = np.frombuffer(d_alns.cpu().numpy().tobytes(), dtype=_lib.ALN_DTYPE).reshape(n, nr)
     bad = sample_check(recs, alns)
-    dps = n * (nr if ref_id is None else 1)
+    dps = n * nr
     print('%-44s %8d reads x %2d refs: kernel %.1f ms -> %.2f M reads/s (%.2f M alignments/s), paths %s ring %s, aligned %.3f, parity sample %s'
-          % (name, n, nr, k, n / k / 1e3, dps / k / 1e3, eng.path_counts(), eng.ring_counts(), (recs['best_score_milli'] > 0).mean(),
+          % (name, n, len(names), k, n / k / 1e3, dps / k / 1e3, eng.path_counts(), eng.ring_counts(), (recs['best_score_milli'] > 0).mean(),
              'OK' if not bad else 'MISMATCH %s' % bad[:3]))
 
 
@@ -93,32 +98,15 @@ order = rng.permutation(len(reads))
 reads, rid = reads[order], rid[order]
 
 
-def check_pooled(recs, alns):
+def chk_pooled(recs, alns):
     bad = []
     p1 = O.Params()
     for i in range(0, 300):
         nm = names[rid[i]]
         v = O.new_variant(p1, reads[i].tobytes().decode(), {nm: refs[nm]}, [nm], m)
-        if int(alns[i, rid[i]]['score_milli']) != int(round(v['aln_scores'][0] * 1000)):
+        if int(alns[i, 0]['score_milli']) != int(round(v['aln_scores'][0] * 1000)) or int(recs[i]['best_ref']) != (rid[i] if v['best_match_score'] > 0 else -1):
             bad.append((i, nm))
     return bad
 
 
-# the engine holds at most C2B_MAX_REFS = 32 references per configuration: 96 amplicons = 3 configurations of 32
-for part in range(3):
-    sel = (rid // 32) == part
-    sub_names = names[32 * part: 32 * part + 32]
-    sub_refs = {k: refs[k] for k in sub_names}
-    rsub, ridsub = reads[sel], (rid[sel] - 32 * part).astype(np.int32)
-
-    def chk(recs, alns, rsub=rsub, ridsub=ridsub, sub_names=sub_names, sub_refs=sub_refs):
-        bad = []
-        p1 = O.Params()
-        for i in range(0, 100):
-            nm = sub_names[ridsub[i]]
-            v = O.new_variant(p1, rsub[i].tobytes().decode(), {nm: sub_refs[nm]}, [nm], m)
-            if int(alns[i, ridsub[i]]['score_milli']) != int(round(v['aln_scores'][0] * 1000)):
-                bad.append((i, nm))
-        return bad
-
-    run('configs[3] Pooled, amplicons %d-%d' % (32 * part, 32 * part + 31), sub_refs, sub_names, rsub, ridsub, 0, chk)
+run('configs[3] Pooled, 96 amplicons, one configuration', refs, names, reads, rid, 0, chk_pooled)
