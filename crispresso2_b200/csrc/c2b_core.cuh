@@ -858,16 +858,20 @@ C2B_DEVNOINL int rescatter(const KParams &P, const RefDev &R, int64_t rd, int r,
 //   single reference tried: the caller already scattered the chosen alignment into rowinfo/rowins;
 //   several references    : op streams are reloaded from opsbuf (lane offset hoff; hoff >= 0: the stream lives in
 //                           16 lanes starting at hoff) and re-scattered per winner.
+// ONE: one candidate reference per read (a single amplicon, or Pooled ref_id) -- a compile-time fact of the launch, so that
+// the lean kernel carries none of the several-references code (loops over winners, re-scatter, HDR re-projection).
+template <bool ONE>
 C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, const uint8_t *fw, const uint8_t *rc,
                          uint8_t *rowinfo, uint32_t *rowins, int r_begin, int r_end, const uint64_t *opsbuf, int hoff,
                          int keep_irr, const c2b_aln_rec &a_single)
 {
     const int lane = wp::lane();
-    const bool multi = (r_end - r_begin) > 1;
+    const bool multi = !ONE && (r_end - r_begin) > 1;
+    if (ONE) r_end = r_begin + 1;
     if (rec.best_score_milli <= 0 && !P.forced_ops) { rec.winner_mask = 0; rec.n_winners = 0; }
     else {
         const bool expand = P.flags & C2B_F_EXPAND_AMBIGUOUS, first = P.flags & C2B_F_ASSIGN_FIRST;
-        const bool ambiguous = rec.n_winners > 1 && !first && !expand;     // CRISPRessoCORE.py:780-785
+        const bool ambiguous = !ONE && rec.n_winners > 1 && !first && !expand;     // CRISPRessoCORE.py:780-785
         rec.ambiguous = ambiguous;
         const long long cnt = P.count ? P.count[rd] : 1;
         const long long w = P.qweight ? P.qweight[rd] : cnt;
@@ -931,7 +935,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             // (derived on the host) instead
 #ifndef C2B_X_BISECT_R01J
             if (counted && lane == 0 && (two_scans || expand)) {
-                const bool discarded = two_scans && (o.del_n > 0 || o.ins_n > 0), joined = expand && rec.n_winners > 1;
+                const bool discarded = two_scans && (o.del_n > 0 || o.ins_n > 0), joined = !ONE && expand && rec.n_winners > 1;
                 if (discarded != joined) sc_add(SC, modified ? C2B_S_CLASS_MODIFIED : C2B_S_CLASS_UNMODIFIED, discarded ? w : -w);
             }
 #endif
@@ -963,7 +967,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             wp::sync();
         }
         // HDR / prime editing: reads assigned to another reference are also classified on their alignment to reference 0
-        if ((P.flags & C2B_F_HDR_REF1) && multi && r_begin == 0 && !ambiguous && w > 0) {
+        if (!ONE && (P.flags & C2B_F_HDR_REF1) && multi && r_begin == 0 && !ambiguous && w > 0) {
             const uint32_t eff = first ? (rec.winner_mask & (0u - rec.winner_mask)) : rec.winner_mask;   // aln_ref_names
             if (eff != 1u) {                                    // not "aligned to reference 0 only" (:4234)
                 const RefDev &R0 = P.refs[0];
@@ -984,6 +988,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
 }
 
 // One read per warp, 32-bit scores: the general path (any length within the build limits, any parameters).
+template <bool ONE>
 C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_slot)
 {
     const int lane = wp::lane();
@@ -1001,8 +1006,8 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
     wp::sync();
 
     const int r_begin = P.ref_id ? P.ref_id[rd] : 0;
-    const int r_end = P.ref_id ? r_begin + 1 : P.n_refs;
-    const bool multi = (r_end - r_begin) > 1;
+    const int r_end = (ONE || P.ref_id) ? r_begin + 1 : P.n_refs;
+    const bool multi = !ONE && (r_end - r_begin) > 1;
     int keep_irr = 0;
     c2b_aln_rec a; init_aln(a, st);
 
@@ -1052,7 +1057,7 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
         if (lane == 0) P.alns[oslot(P, rd, r)] = a;
     }
     wp::sync();
-    finish_read(P, rd, rec, J, S.fw[0], S.rc[0], S.rowinfo, S.rowins, r_begin, r_end, opsbuf, -1, keep_irr, a);
+    finish_read<ONE>(P, rd, rec, J, S.fw[0], S.rc[0], S.rowinfo, S.rowins, r_begin, r_end, opsbuf, -1, keep_irr, a);
 }
 
 // ------------------------------------------------------------------------------------ paired path (16-bit halves)
@@ -1301,16 +1306,14 @@ C2B_DEV int ring_bound(const KParams &P, const RefDev &R, int J)
 // memory (ops/n/err).  ref_stride > 0: several references tried, reference k's block (RG_OPS_STRIDE u64, global scratch,
 // written by this warp) starts at ops + k * ref_stride; refmask bit k = the band held for reference k.
 struct RingCtx { const uint64_t *ops; const int32_t *n, *err; int modes; int ref_stride; uint32_t refmask; };
-#if defined(C2B_X_ONE_CLASSIFY_BARRIER) && defined(C2B_X_NO_PASS_BARRIER)
-constexpr int PAIR_PHASES = 3;
-#elif defined(C2B_X_ONE_CLASSIFY_BARRIER) || defined(C2B_X_NO_PASS_BARRIER)
-constexpr int PAIR_PHASES = 4;
-#else
-constexpr int PAIR_PHASES = 5;
-#endif
-constexpr int GROUP_PHASES = 3 + 4 * PAIR_PHASES;      // barriers per process_pair(phased) / per work group
+// Barriers per work group when the warps of a phase set move in step: 3 in process_quad / process_quad_multi, and per pair one
+// at entry, two per reference tried (before its alignment pass and before its columns) and two for the classify steps.
+// The same count for every warp of a launch (it depends on the configuration only), so warps on other paths execute that
+// many empty barriers.
+C2B_DEV int group_phases(const KParams &P) { const int nr = P.ref_id ? 1 : P.n_refs; return 3 + 4 * (3 + 2 * nr); }
 
 // Two reads (rdA, rdB) of equal length J through the packed path.  Per-lane variables belong to the lane's half.
+template <bool ONE>
 C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *staged_prof, int64_t rdA, int64_t rdB, int warp_slot,
                           const RingCtx *ring, const bool phased)
 {
@@ -1337,8 +1340,8 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
     wp::sync();
 
     const int r_begin = P.ref_id ? P.ref_id[rdA] : 0;
-    const int r_end = P.ref_id ? r_begin + 1 : P.n_refs;
-    const bool multi = (r_end - r_begin) > 1;
+    const int r_end = (ONE || P.ref_id) ? r_begin + 1 : P.n_refs;
+    const bool multi = !ONE && (r_end - r_begin) > 1;
     int keep_irr = 0;
     c2b_aln_rec a; init_aln(a, st);
 
@@ -1360,12 +1363,10 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
             const int sA = (mA == 2) ? pass : (mA == 1), sB = (mB == 2) ? pass : (mB == 1);
             const uint8_t *cA = sA ? S.rc[0] : S.fw[0], *cB = sB ? S.rc[1] : S.fw[1];
             wp::sync();
-#ifndef C2B_X_NO_PASS_BARRIER
             if (phased && pass == 0) wp::grp_sync(P.phase_sync);
-#endif
             Walked wk; wk.err = 4;
-            if (ring && ring->ref_stride == 0) { wk.ops = ring->ops[lane]; wk.n = ring->n[h]; wk.err = ring->err[h]; }   // aligned and walked by process_quad
-            else if (ring && ((ring->refmask >> (r - r_begin)) & 1u)) {
+            if (ring && (ONE || ring->ref_stride == 0)) { wk.ops = ring->ops[lane]; wk.n = ring->n[h]; wk.err = ring->err[h]; }   // aligned and walked by process_quad
+            else if (!ONE && ring && ((ring->refmask >> (r - r_begin)) & 1u)) {
                 const uint64_t *o = ring->ops + (int64_t)(r - r_begin) * ring->ref_stride;
                 wk.ops = wp::ldcg64(o + lane);
                 const uint64_t mt = wp::ldcg64(o + 32 + h);
@@ -1412,11 +1413,7 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
     // (The compiler unrolls this loop into two copies of finish_read; forcing one copy, or making finish_read and the
     // loaders out-of-line calls, shrank the kernel by 20 % and made it 3-5 % SLOWER -- profiles/r01k_variants.md.)
     for (int hh = 0; hh < 2; hh++) {
-#ifndef C2B_X_ONE_CLASSIFY_BARRIER
         if (phased) wp::grp_sync(P.phase_sync);
-#else
-        if (phased && hh == 0) wp::grp_sync(P.phase_sync);
-#endif
         if (hh == 1 && rdB == rdA) break;
         const int src = 16 * hh;
         c2b_read_rec rr;
@@ -1430,7 +1427,7 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
         ah.score_milli = wp::shfl(a.score_milli, src);
         const uint32_t w1 = wp::shflu((uint32_t)a.strand | ((uint32_t)a.status << 8), src);
         ah.strand = (uint8_t)(w1 & 0xffu); ah.status = (uint8_t)(w1 >> 8);
-        finish_read(P, hh ? rdB : rdA, rr, J, S.fw[hh], S.rc[hh], S.rowinfo + hh * PK_ROWINFO_STRIDE,
+        finish_read<ONE>(P, hh ? rdB : rdA, rr, J, S.fw[hh], S.rc[hh], S.rowinfo + hh * PK_ROWINFO_STRIDE,
                     S.rowins + hh * PK_ROWINS_STRIDE, r_begin, r_end, opsbuf, src, irr, ah);
         wp::sync();
     }
@@ -1438,6 +1435,7 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
 
 // Work item w = reads 2w and 2w+1.  Equal lengths inside every reference's proven 16-bit range -> packed pair;
 // otherwise each read takes the 32-bit path.
+template <bool ONE>
 C2B_DEV void process_item(const KParams &P, WarpSmem &S, const uint32_t *staged_prof, int64_t w, int warp_slot)
 {
     const bool haveB = 2 * w + 1 < P.n_reads;
@@ -1455,10 +1453,10 @@ C2B_DEV void process_item(const KParams &P, WarpSmem &S, const uint32_t *staged_
         }
     }
     if (wp::lane() == 0) wp::addg(P.stats + (pair ? 2 : 3), 1);      // path statistics (c2b_path_counts)
-    if (pair) process_pair(P, S, staged_prof, rdA, rdB, warp_slot, nullptr, false);
+    if (pair) process_pair<ONE>(P, S, staged_prof, rdA, rdB, warp_slot, nullptr, false);
     else {
-        process_read(P, S, rdA, warp_slot);
-        if (haveB) { wp::sync(); process_read(P, S, rdB, warp_slot); }
+        process_read<ONE>(P, S, rdA, warp_slot);
+        if (haveB) { wp::sync(); process_read<ONE>(P, S, rdB, warp_slot); }
     }
 }
 
@@ -1544,7 +1542,7 @@ C2B_DEV void process_quad(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint
         const int64_t rdB = P.pair_order ? P.pair_order[2 * (first + q) + 1] : 2 * (first + q) + 1;
         RingCtx rc; rc.ops = Q.wk.ops[q]; rc.n = Q.wk.n[q]; rc.err = Q.wk.err[q]; rc.modes = (int)((modes >> (4 * q)) & 15u);
         rc.ref_stride = 0; rc.refmask = 1u;
-        process_pair(P, S, staged_prof, rdA, rdB, warp_slot, ((passmask >> q) & 1u) ? &rc : nullptr, P.phase_sync != 0);
+        process_pair<true>(P, S, staged_prof, rdA, rdB, warp_slot, ((passmask >> q) & 1u) ? &rc : nullptr, P.phase_sync != 0);
         wp::sync();
     }
 }
@@ -1639,18 +1637,19 @@ C2B_DEVNOINL void process_quad_multi(const KParams &P, WarpSmem &S, QuadSmem &Q,
         RingCtx rc; rc.ops = rgo + (int64_t)q * RG_OPS_STRIDE; rc.n = nullptr; rc.err = nullptr;
         rc.modes = (int)((modes >> (4 * q)) & 15u); rc.ref_stride = 4 * RG_OPS_STRIDE; rc.refmask = 0;
         for (int k = 0; k < P.n_refs; k++) rc.refmask |= ((passall >> (4 * k + q)) & 1u) << k;
-        process_pair(P, S, staged_prof, rdA, rdB, warp_slot, ((okmask >> q) & 1u) ? &rc : nullptr, P.phase_sync != 0);
+        process_pair<false>(P, S, staged_prof, rdA, rdB, warp_slot, ((okmask >> q) & 1u) ? &rc : nullptr, P.phase_sync != 0);
         wp::sync();
     }
 }
 
 // Work group wq = work items 4wq..4wq+3 (reads 8wq..8wq+7): four pairs through the ring-banded path when all of them
 // qualify, otherwise item by item.
+template <bool ONE>
 C2B_DEV void process_group(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint32_t *staged_prof, int64_t wq, int warp_slot)
 {
     const int lane = wp::lane();
     const int64_t first = 4 * wq;
-    const bool multi = P.ref_id == nullptr && P.n_refs > 1;
+    const bool multi = !ONE && P.ref_id == nullptr && P.n_refs > 1;
     bool quad = !P.forced_ops && !(P.flags & (C2B_F_NO_PAIRING | C2B_F_NO_RING)) && P.tbq != nullptr &&
                 2 * first + 7 < P.n_reads && (!multi || (P.n_refs <= RG_MAX_REFS && P.rgops != nullptr));
     if (quad) {
@@ -1668,15 +1667,15 @@ C2B_DEV void process_group(const KParams &P, WarpSmem &S, QuadSmem &Q, const uin
         }
         quad = wp::ballot(ok) == 0xffffffffu;
     }
-    if (quad && multi) process_quad_multi(P, S, Q, staged_prof, first, warp_slot);
+    if (!ONE && quad && multi) process_quad_multi(P, S, Q, staged_prof, first, warp_slot);
     else if (quad) process_quad(P, S, Q, staged_prof, first, warp_slot);
     else {
 #pragma unroll 1
         for (int q = 0; q < 4; q++)
-            if (2 * (first + q) < P.n_reads) { process_item(P, S, staged_prof, first + q, warp_slot); wp::sync(); }
+            if (2 * (first + q) < P.n_reads) { process_item<ONE>(P, S, staged_prof, first + q, warp_slot); wp::sync(); }
         if (P.phase_sync) {                                 // keep the CTA's barrier count per group the same on every path
 #pragma unroll 1
-            for (int b = 0; b < GROUP_PHASES; b++) wp::grp_sync(P.phase_sync);
+            for (int b = group_phases(P); b > 0; b--) wp::grp_sync(P.phase_sync);
         }
     }
 }

@@ -77,6 +77,9 @@ static void rt_host_free(void *p) { free(p); }
 #endif
 constexpr int WARPS_PER_CTA = C2B_WARPS_PER_CTA;      // launch-bounds maximum; the launch may use fewer (env C2B_WARPS_PER_CTA)
 
+// ONE: every read has one candidate reference (a single amplicon configured, or Pooled ref_id): the lean instantiation
+// carries none of the several-references code.  The host picks the instantiation per launch.
+template <bool ONE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_align_classify_kernel(const KParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -128,8 +131,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_a
             if (a < b1) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.reads + a));
         }
         const unsigned long long w = base + wis;
-        if (w < total) process_group(P, *S, *Q, staged_prof, (int64_t)w, warp_slot);  // reads 8w .. 8w+7
-        else if (P.phase_sync) for (int b = 0; b < GROUP_PHASES; b++) wp::grp_sync(gs);
+        if (w < total) process_group<ONE>(P, *S, *Q, staged_prof, (int64_t)w, warp_slot);  // reads 8w .. 8w+7
+        else if (P.phase_sync) for (int b = group_phases(P); b > 0; b--) wp::grp_sync(gs);
         __syncwarp();
         base = nb;
     }
@@ -222,10 +225,15 @@ int c2b_create(int device, c2b_engine **out)
     }
     if (e->stage_cap < 0) e->stage_cap = 0;
     e->stage_cap &= ~127;
-    if (r == cudaSuccess) r = cudaFuncSetAttribute(c2b_align_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)((sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA) + 128 + e->stage_cap);
-    if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c2b_align_classify_kernel, WARPS_PER_CTA * 32,
-                                                                            (sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA + 128 + e->stage_cap);
+    const int dyn_smem = (int)((sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA) + 128 + e->stage_cap;
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(c2b_align_classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(c2b_align_classify_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+    if (r == cudaSuccess) {       // both instantiations must fit the same persistent grid
+        int occ1 = 0, occ0 = 0;
+        r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, c2b_align_classify_kernel<true>, WARPS_PER_CTA * 32, dyn_smem);
+        if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, c2b_align_classify_kernel<false>, WARPS_PER_CTA * 32, dyn_smem);
+        occ = std::min(occ1, occ0);
+    }
     if (r != cudaSuccess) { g_create_err = std::string("c2b_create: ") + cudaGetErrorString(r); delete e; return C2B_E_CUDA; }
     if (occ < 1) occ = 1;
     e->wpc = WARPS_PER_CTA;
@@ -567,8 +575,7 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
         const int nsets = a ? e->wpc / a : 0;
         if (a > e->wpc || (a && e->wpc % a) || (P.phase_sync < 0 && (nsets & (nsets - 1)))) P.phase_sync = 0;
     }
-    // several references per read: the per-pair barrier count depends on the number of references, so warps run free
-    if (e->n_refs > 1 && !d_ref_id) P.phase_sync = 0;
+    if (e->n_refs > 1 && !d_ref_id && getenv("C2B_NO_MULTI_PHASE")) P.phase_sync = 0;     // A/B switch: free-running warps in multi-reference mode
     P.pair_order = e->pair_order;
     P.lut = (const uint8_t *)e->lut.p;
     P.stage_bytes = 0; P.stage_src = nullptr;
@@ -584,13 +591,29 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
     RTCHK(rt_zero(P.work_counter, 16, cs));               // this set's work counter and widest alignment
 #ifndef C2B_EMU
     cudaEventRecord(e->ev0, cs);
-    c2b_align_classify_kernel<<<e->grid, e->wpc * 32, (sizeof(WarpSmem) + sizeof(QuadSmem)) * e->wpc + 128 + (size_t)P.stage_bytes, cs>>>(P);
+    {
+        const size_t smem = (sizeof(WarpSmem) + sizeof(QuadSmem)) * e->wpc + 128 + (size_t)P.stage_bytes;
+        const bool one = (e->n_refs == 1 || d_ref_id != nullptr) && !getenv("C2B_GENERIC_KERNEL");      // one candidate reference per read
+        if (one) c2b_align_classify_kernel<true><<<e->grid, e->wpc * 32, smem, cs>>>(P);
+        else c2b_align_classify_kernel<false><<<e->grid, e->wpc * 32, smem, cs>>>(P);
+    }
     cudaEventRecord(e->ev1, cs);
     RTCHK(cudaGetLastError());
 #else
     {
         static WarpSmem S; static QuadSmem Q;
-        for (int64_t w = 0; 8 * w < n_reads; w++) emu::run_warp([&]() { process_group(P, S, Q, nullptr, w, 0); });
+        for (int64_t w = 0; 8 * w < n_reads; w++) {
+            wp::g_grp_syncs = 0;
+            const bool one = (e->n_refs == 1 || d_ref_id != nullptr) && !getenv("C2B_GENERIC_KERNEL");
+            if (one) emu::run_warp([&]() { process_group<true>(P, S, Q, nullptr, w, 0); });
+            else emu::run_warp([&]() { process_group<false>(P, S, Q, nullptr, w, 0); });
+            // every path through a work group must execute the same number of phase barriers (a mismatch deadlocks the GPU)
+            if (w == 0 && getenv("C2B_EMU_VERBOSE")) fprintf(stderr, "warp_emu: phase_sync %d, %ld barriers in group 0 (expected %d)\n", P.phase_sync, wp::g_grp_syncs, group_phases(P));
+            if (P.phase_sync && wp::g_grp_syncs != group_phases(P)) {
+                fprintf(stderr, "warp_emu: work group %lld executed %ld phase barriers, expected %d\n", (long long)w, wp::g_grp_syncs, group_phases(P));
+                abort();
+            }
+        }
     }
 #endif
     e->launches++;

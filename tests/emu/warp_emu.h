@@ -85,7 +85,8 @@ C2B_DEV uint32_t ballot(bool p)
     return m;
 }
 C2B_DEV void sync() { emu::exchange(0, 5, [](int l, int) { return l; }, 0); }
-C2B_DEV void grp_sync(int) {}                  // the emulator runs one warp at a time
+static thread_local long g_grp_syncs = 0;       // phase barriers executed by lane 0 (the engine checks the count per work group)
+C2B_DEV void grp_sync(int) { if (emu::g_warp->cur == 0) g_grp_syncs++; }      // the emulator runs one warp at a time
 C2B_DEV int max3(int a, int b, int c) { return std::max(a, std::max(b, c)); }
 C2B_DEV int addmax(int a, int b, int c) { return std::max(a + b, c); }
 static inline int16_t h_lo(uint32_t v) { return (int16_t)(v & 0xffffu); }

@@ -78,6 +78,8 @@ def check_hdr(recs, alns):
 
 
 run('configs[2] HDR mode, 3 amplicons', refs, names, reads, None, _lib.F_HDR_REF1, check_hdr)
+if len(sys.argv) > 1 and sys.argv[1] == 'hdr':
+    sys.exit(0)
 
 # ---- configs[3]: 96 amplicons (len U[180,280]), reads carry the index of their amplicon (post-demultiplex Pooled)
 rng = np.random.default_rng(11)
