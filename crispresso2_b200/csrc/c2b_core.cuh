@@ -136,7 +136,13 @@ struct KParams {
     uint64_t *opsbuf;                                         // [warp][n_refs][32] op streams (multi-reference)
     uint64_t *rgops;                                          // [warp][RG_MAX_REFS][4 pairs][RG_OPS_STRIDE]: walked op streams of the multi-reference ring path
     unsigned long long *work_counter;      // [0] work hand-out counter, [1] widest alignment of this launch
-    unsigned long long *stats;             // cumulative path statistics (c2b_path_counts), indices 2..6
+    unsigned long long *stats;             // cumulative path statistics (c2b_path_counts), indices 2..6; [7]: streaming wait timed out
+    // streamed launch (c2b_align_batch): ONE persistent launch covers the whole host batch while its read bytes are still
+    // arriving chunk by chunk; nullptr = everything is resident at launch
+    const unsigned long long *avail;       // number of work groups whose read bytes are resident (grows; written by H2D copies)
+    const unsigned long long *chunk_end;   // [n_chunks] end group (exclusive) of every chunk
+    unsigned long long *chunk_done;        // [n_chunks] groups completed; [n_chunks + c]: widest alignment of chunk c
+    int32_t n_chunks;
     int32_t vstride, hstride;
     const uint32_t *stage_src;        // = refs[0].prof2 (global source of the staged tile)
     int32_t stage_bytes;              // bytes of refs[0].prof2 staged into shared memory by TMA at kernel start (0: none)

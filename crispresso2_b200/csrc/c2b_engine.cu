@@ -109,29 +109,74 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_a
     // Work groups (8 reads each) are handed out per phase set (g consecutive warps, one group per warp), one hand-out
     // ahead, so that the loop count -- and with it the number of barriers executed by process_group's phases -- is the
     // same for every warp of the set, and the next group's read bytes are on their way to L2 while this one computes.
-    __shared__ unsigned long long next_base[WARPS_PER_CTA];
+    __shared__ unsigned long long next_base[2 * WARPS_PER_CTA];   // [set]: next hand-out; [WARPS_PER_CTA + set]: wait timed out
     const int gs = P.phase_sync, g = gs > 0 ? gs : gs < 0 ? -gs : 1, wib = threadIdx.x >> 5, nsets = (int)(blockDim.x >> 5) / g;
     const int set = gs < 0 ? wib % nsets : wib / g, wis = gs < 0 ? wib / nsets : wib % g;
     const unsigned long long total = ((unsigned long long)P.n_reads + 7) / 8;
-    auto hand_out = [&]() -> unsigned long long {
-        if (wis == 0 && (threadIdx.x & 31) == 0) next_base[set] = atomicAdd(P.work_counter, (unsigned long long)g);
+    // Streamed launch: before a set starts on work groups base..base+g-1 its leader waits until their read bytes have
+    // arrived (P.avail is advanced by the copy stream after each chunk's H2D).  A wait longer than 20 s is reported in
+    // stats[7] and ends the launch instead of hanging the GPU.
+    auto hand_out = [&](unsigned long long cur) -> unsigned long long {
+        if (wis == 0 && (threadIdx.x & 31) == 0) {
+            unsigned long long nxt = atomicAdd(P.work_counter, (unsigned long long)g);
+            if (P.avail && cur < total) {
+                const unsigned long long need = cur + g < total ? cur + g : total;
+                unsigned long long t0 = 0, have;
+                for (;;) {
+                    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(have) : "l"(P.avail));
+                    if (have >= need) break;
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (!t0) t0 = now;
+                    if (now - t0 > 20000000000ull) { atomicExch(P.stats + 7, 1ull); nxt = ~0ull; next_base[WARPS_PER_CTA + set] = 1; break; }
+                    __nanosleep(400);
+                }
+            }
+            next_base[set] = nxt;
+        }
         if (g > 1) wp::grp_sync(gs); else __syncwarp();
         const unsigned long long b = next_base[set];
         if (g > 1) wp::grp_sync(gs); else __syncwarp();
         return b;
     };
-    unsigned long long base = hand_out();
+    if (threadIdx.x < 2 * WARPS_PER_CTA) next_base[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long base = hand_out(~0ull);              // nothing to wait for yet
+    int chunk = 0;
     while (base < total) {
-        const unsigned long long nb = hand_out();
+        const unsigned long long nb = hand_out(base);        // next hand-out; returns once `base` itself is resident
+        if (next_base[WARPS_PER_CTA + set]) break;            // the wait timed out
         const unsigned long long wn = nb + wis;
-        if (wn < total && !P.pair_order) {
+        if (wn < total && !P.pair_order && !P.avail) {
             const int64_t last = (int64_t)(8 * wn + 8) < P.n_reads ? (int64_t)(8 * wn + 8) : P.n_reads;
             const int64_t b0 = P.offsets[8 * wn], b1 = P.offsets[last];
             const int64_t a = b0 + (int64_t)(threadIdx.x & 31) * 128;
             if (a < b1) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.reads + a));
         }
         const unsigned long long w = base + wis;
-        if (w < total) process_group<ONE>(P, *S, *Q, staged_prof, (int64_t)w, warp_slot);  // reads 8w .. 8w+7
+        if (w < total) {
+            process_group<ONE>(P, *S, *Q, staged_prof, (int64_t)w, warp_slot);  // reads 8w .. 8w+7
+            if (P.chunk_done) {                              // streamed launch: tell the host that this group's outputs are complete
+                __syncwarp();
+                while (w >= P.chunk_end[chunk]) chunk++;
+                const int lane = threadIdx.x & 31;
+                unsigned long long wmax = 0;
+                if (lane < 8 && 8 * (int64_t)w + lane < P.n_reads) {
+                    const int64_t rd = P.pair_order ? P.pair_order[8 * (int64_t)w + lane] : 8 * (int64_t)w + lane;   // the reads this group aligned
+                    for (int r = 0; r < P.out_refs; r++) {
+                        const unsigned long long v = *reinterpret_cast<const volatile uint16_t *>(&P.alns[rd * P.out_refs + r].aln_len);
+                        wmax = v > wmax ? v : wmax;
+                    }
+                }
+#pragma unroll
+                for (int d = 4; d >= 1; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, wmax, d); wmax = o > wmax ? o : wmax; }
+                if (lane == 0) {
+                    atomicMax(P.chunk_done + P.n_chunks + chunk, wmax);
+                    __threadfence();
+                    atomicAdd(P.chunk_done + chunk, 1ull);
+                }
+            }
+        }
         else if (P.phase_sync) for (int b = group_phases(P); b > 0; b--) wp::grp_sync(gs);
         __syncwarp();
         base = nb;
@@ -172,8 +217,12 @@ struct c2b_engine {
     size_t set_tb = 0, set_tbb = 0, set_tbq = 0, set_bnd = 0, set_ops = 0, set_rgo = 0;   // bytes per scratch set (two sets: kernels of
                                                     // consecutive chunks overlap their tail / head on the two streams)
     bool pipe_ready = false;
+    // streamed launch (one persistent launch per host batch): whole-batch device buffers + control block
+    struct Streamed { DevBuf reads, off, cnt, qw, rid, ord, recs, alns, str, ed, ctl; unsigned long long *h_ctl = nullptr; size_t h_ctl_cap = 0;
+                      int64_t *h_off = nullptr; size_t h_off_cap = 0; int32_t *h_ord = nullptr; size_t h_ord_cap = 0; rt_stream s_poll = 0; bool ready = false; } sm;
     double last_ms = 0; int64_t launches = 0;
     const uint64_t *forced_ops = nullptr; const int32_t *forced_n = nullptr;
+    const unsigned long long *k_avail = nullptr, *k_chunk_end = nullptr; unsigned long long *k_chunk_done = nullptr; int k_n_chunks = 0;   // streamed launch (set around launch_on)
     const int32_t *pair_order = nullptr;
     int64_t band_reruns = 0, ring_pairs = 0, ring_fallbacks = 0;
 #ifndef C2B_EMU
@@ -261,6 +310,14 @@ void c2b_destroy(c2b_engine *e)
         if (e->pipe_ready) { rt_event_destroy(st.in_done); rt_event_destroy(st.k_done); rt_event_destroy(st.out_done); }
     }
     if (e->pipe_ready) { rt_stream_destroy(e->s_in); rt_stream_destroy(e->s_out); }
+    {
+        DevBuf *mb[] = {&e->sm.reads, &e->sm.off, &e->sm.cnt, &e->sm.qw, &e->sm.rid, &e->sm.ord, &e->sm.recs, &e->sm.alns, &e->sm.str, &e->sm.ed, &e->sm.ctl};
+        for (DevBuf *b : mb) if (b->p) rt_free(b->p);
+        if (e->sm.h_ctl) rt_host_free(e->sm.h_ctl);
+        if (e->sm.h_off) rt_host_free(e->sm.h_off);
+        if (e->sm.h_ord) rt_host_free(e->sm.h_ord);
+        if (e->sm.ready) rt_stream_destroy(e->sm.s_poll);
+    }
     if (e->d_tables) rt_free(e->d_tables);
     if (e->d_counts) rt_free(e->d_counts);
 #ifndef C2B_EMU
@@ -568,6 +625,7 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
     P.work_counter = P.stats + 8 + 8 * set;
     P.vstride = e->vstride; P.hstride = e->hstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
+    P.avail = e->k_avail; P.chunk_end = e->k_chunk_end; P.chunk_done = e->k_chunk_done; P.n_chunks = e->k_n_chunks;
     P.phase_sync = 4;                                     // warps per phase set (C2B_PHASE_WARPS: 0/1 = free-running, 2, 4, 8)
     if (const char *v = getenv("C2B_PHASE_WARPS")) { const int k = atoi(v), a = k < 0 ? -k : k; P.phase_sync = (a == 2 || a == 4 || a == 8 || a == 16) ? k : 0; }
     {   // grp_sync wants |g| and the number of sets to be powers of two
@@ -682,6 +740,160 @@ int c2b_ring_counts(c2b_engine *e, int64_t *ring_pairs, int64_t *ring_fallbacks)
     return C2B_OK;
 }
 
+#ifndef C2B_EMU
+// C2B_STREAMED=1 / =0 forces the streamed launch on / off; default below.
+static bool streamed_default(const c2b_engine *) { const char *v = getenv("C2B_STREAMED"); return v ? atoi(v) != 0 : false; }
+
+// Host batch through ONE persistent launch: the kernel starts at once and takes work groups as their read bytes arrive
+// (chunked H2D on the copy stream, each followed by an 8-byte update of the "groups resident" mark the kernel polls);
+// every finished group bumps its chunk's counter, the host polls those and queues each chunk's D2H as soon as the chunk is
+// complete.  No launch head/tail per chunk, copies of both directions overlap the kernel.
+static int align_batch_streamed(c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads, int64_t maxJ,
+                                const int32_t *count, const int32_t *qweight, const int32_t *ref_id,
+                                c2b_read_rec *recs, c2b_aln_rec *alns, uint8_t *strings, c2b_edit *edits)
+{
+    c2b_engine::Streamed &m = e->sm;
+    int rc;
+    if (!m.ready) { RTCHK(rt_stream_create(&m.s_poll)); m.ready = true; }
+    const int W = (e->max_I + (int)maxJ + 31) & ~31;
+    const int cap = edits ? e->prm.edit_cap : 0;
+    const int nr = ref_id ? 1 : e->n_refs;
+    const int64_t b0 = offsets[0], nbytes = offsets[n_reads] - b0;
+    // chunk boundaries at multiples of 64 reads (whole hand-outs of a phase set); small first and last chunks
+    int64_t chunk = 1 << 16;
+    if (const char *v = getenv("C2B_STREAM_CHUNK")) chunk = std::max<int64_t>(64, atoll(v) / 64 * 64);
+    std::vector<int64_t> cuts;
+    cuts.push_back(0);
+    {
+        const int64_t edge = std::max<int64_t>(64, chunk / 8 / 64 * 64);
+        int64_t pos = 0;
+        if (n_reads > 4 * edge) { pos = edge; cuts.push_back(pos); }
+        const int64_t tail = (n_reads - pos > 2 * edge) ? edge : 0;
+        const int64_t body_end = (n_reads - tail) / 64 * 64;
+        while (pos < body_end) { pos = std::min(pos + chunk, body_end); cuts.push_back(pos); }
+        if (pos < n_reads) cuts.push_back(n_reads);
+    }
+    const int nc = (int)cuts.size() - 1;
+    if ((rc = ensure_scratch(e, (int)maxJ))) return rc;
+    if ((rc = ensure(e, m.reads, (size_t)nbytes + 256))) return rc;
+    if ((rc = ensure(e, m.off, (size_t)(n_reads + 1) * 8))) return rc;
+    if ((rc = ensure(e, m.recs, (size_t)n_reads * sizeof(c2b_read_rec)))) return rc;
+    if ((rc = ensure(e, m.alns, (size_t)n_reads * nr * sizeof(c2b_aln_rec)))) return rc;
+    if (strings && (rc = ensure(e, m.str, (size_t)n_reads * nr * 2 * W))) return rc;
+    if (cap && (rc = ensure(e, m.ed, (size_t)n_reads * nr * cap * sizeof(c2b_edit)))) return rc;
+    if (count && (rc = ensure(e, m.cnt, (size_t)n_reads * 4))) return rc;
+    if (qweight && (rc = ensure(e, m.qw, (size_t)n_reads * 4))) return rc;
+    if (ref_id && (rc = ensure(e, m.rid, (size_t)n_reads * 4))) return rc;
+    // control block (u64): [0] groups resident, [8 .. 8+nc) chunk end groups, [8+nc .. 8+2nc) groups done, [8+2nc .. 8+3nc) widest alignment
+    const size_t ctl_n = 8 + 3 * (size_t)nc;
+    if ((rc = ensure(e, m.ctl, ctl_n * 8))) return rc;
+    const size_t pin_n = 2 * ctl_n + (size_t)nc + 8;       // pinned: initial image | per-chunk "resident" marks | poll buffer
+    if (m.h_ctl_cap < pin_n) {
+        if (m.h_ctl) rt_host_free(m.h_ctl);
+        m.h_ctl = (unsigned long long *)rt_host_alloc(pin_n * 8); m.h_ctl_cap = m.h_ctl ? pin_n : 0;
+        if (!m.h_ctl) return fail(e, C2B_E_CUDA, "c2b_align_batch: pinned allocation failed");
+    }
+    if (m.h_off_cap < (size_t)(n_reads + 1)) {
+        if (m.h_off) rt_host_free(m.h_off);
+        m.h_off = (int64_t *)rt_host_alloc((size_t)(n_reads + 1) * 8); m.h_off_cap = m.h_off ? (size_t)(n_reads + 1) : 0;
+        if (!m.h_off) return fail(e, C2B_E_CUDA, "c2b_align_batch: pinned allocation failed");
+    }
+    bool need_order = false;
+    {
+        const int64_t L0 = offsets[1] - offsets[0];
+        for (int64_t k = 0; k <= n_reads; k++) m.h_off[k] = offsets[k] - b0;
+        for (int64_t k = 1; k < n_reads && !need_order; k++)
+            need_order = (offsets[k + 1] - offsets[k] != L0) || (ref_id && ref_id[k] != ref_id[0]);
+    }
+    // everything but the read bytes is small (8 + 12 bytes per read) and goes up before the launch
+    RTCHK(rt_h2d(m.off.p, m.h_off, (size_t)(n_reads + 1) * 8, e->stream));
+    if (count) RTCHK(rt_h2d(m.cnt.p, count, (size_t)n_reads * 4, e->stream));
+    if (qweight) RTCHK(rt_h2d(m.qw.p, qweight, (size_t)n_reads * 4, e->stream));
+    if (ref_id) RTCHK(rt_h2d(m.rid.p, ref_id, (size_t)n_reads * 4, e->stream));
+    e->pair_order = nullptr;
+    if (need_order) {                                      // per chunk: counting sort by (reference id, length); global indices
+        if ((rc = ensure(e, m.ord, (size_t)n_reads * 4))) return rc;
+        if (m.h_ord_cap < (size_t)n_reads) {
+            if (m.h_ord) rt_host_free(m.h_ord);
+            m.h_ord = (int32_t *)rt_host_alloc((size_t)n_reads * 4); m.h_ord_cap = m.h_ord ? (size_t)n_reads : 0;
+            if (!m.h_ord) return fail(e, C2B_E_CUDA, "c2b_align_batch: pinned allocation failed");
+        }
+        const int64_t nb = (int64_t)(C2B_MAX_READ_LEN + 1) * (ref_id ? e->n_refs : 1);
+        std::vector<int64_t> start((size_t)nb + 1);
+        auto key = [&](int64_t k) -> int64_t {
+            const int64_t L = offsets[k + 1] - offsets[k];
+            const int64_t r = ref_id ? std::min<int64_t>(std::max<int32_t>(ref_id[k], 0), e->n_refs - 1) : 0;
+            return r * (C2B_MAX_READ_LEN + 1) + L;
+        };
+        for (int c = 0; c < nc; c++) {
+            std::fill(start.begin(), start.end(), 0);
+            for (int64_t k = cuts[c]; k < cuts[c + 1]; k++) start[(size_t)key(k) + 1]++;
+            for (int64_t b = 0; b < nb; b++) start[(size_t)b + 1] += start[(size_t)b];
+            for (int64_t k = cuts[c]; k < cuts[c + 1]; k++) m.h_ord[cuts[c] + start[(size_t)key(k)]++] = (int32_t)k;
+        }
+        RTCHK(rt_h2d(m.ord.p, m.h_ord, (size_t)n_reads * 4, e->stream));
+        e->pair_order = (const int32_t *)m.ord.p;
+    }
+    unsigned long long *h = m.h_ctl;
+    for (size_t k = 0; k < ctl_n; k++) h[k] = 0;
+    for (int c = 0; c < nc; c++) h[8 + c] = (unsigned long long)((cuts[c + 1] + 7) / 8);
+    RTCHK(rt_h2d(m.ctl.p, h, ctl_n * 8, e->stream));
+    unsigned long long *d_ctl = (unsigned long long *)m.ctl.p;
+    // the copy stream starts after the control block, offsets and per-read arrays are in place (queued above on `stream`)
+    RTCHK(rt_record(e->fork_ev, e->stream));
+    RTCHK(rt_wait(e->s_in, e->fork_ev));
+    // launch: the kernel spins until the first chunk's bytes are there
+    e->k_avail = d_ctl; e->k_chunk_end = d_ctl + 8; e->k_chunk_done = d_ctl + 8 + nc; e->k_n_chunks = nc;
+    rc = launch_on(e, e->stream, 0, (const uint8_t *)m.reads.p, (const int64_t *)m.off.p, n_reads, (int32_t)maxJ,
+                   count ? (const int32_t *)m.cnt.p : nullptr, qweight ? (const int32_t *)m.qw.p : nullptr,
+                   ref_id ? (const int32_t *)m.rid.p : nullptr, (c2b_read_rec *)m.recs.p, (c2b_aln_rec *)m.alns.p,
+                   strings ? (uint8_t *)m.str.p : nullptr, cap ? (c2b_edit *)m.ed.p : nullptr);
+    e->k_avail = nullptr; e->k_chunk_end = nullptr; e->k_chunk_done = nullptr; e->k_n_chunks = 0;
+    e->pair_order = nullptr;
+    if (rc) return rc;
+    unsigned long long *h_avail = h + ctl_n;               // pinned, one slot per chunk
+    for (int c = 0; c < nc; c++) {
+        const int64_t a = m.h_off[cuts[c]];
+        int64_t b = m.h_off[cuts[c + 1]];
+        if (c + 1 < nc) b = std::min<int64_t>((b + 127) & ~(int64_t)127, nbytes);    // whole 128-byte lines: no line is half-written when first read
+        RTCHK(rt_h2d((uint8_t *)m.reads.p + a, reads + b0 + a, (size_t)(b - a), e->s_in));
+        h_avail[c] = (unsigned long long)((cuts[c + 1] + 7) / 8);
+        RTCHK(rt_h2d(d_ctl, &h_avail[c], 8, e->s_in));
+    }
+    // completion: poll the per-chunk counters, copy each chunk out as soon as it is whole
+    unsigned long long *h_poll = h + ctl_n + nc + 8;        // third part of the pinned block
+    for (int c = 0; c < nc; c++) {
+        const unsigned long long want = (unsigned long long)((cuts[c + 1] + 7) / 8 - (cuts[c] + 7) / 8);
+        int idle = 0;
+        for (;;) {
+            RTCHK(rt_d2h(h_poll, d_ctl, ctl_n * 8, m.s_poll));
+            RTCHK(rt_sync(m.s_poll));
+            if (h_poll[8 + nc + c] >= want) break;
+            if (cudaStreamQuery(e->stream) == cudaSuccess && ++idle > 2)
+                return fail(e, C2B_E_CUDA, "c2b_align_batch: streamed launch ended before all chunks were complete");
+        }
+        const int64_t c0 = cuts[c], n = cuts[c + 1] - cuts[c];
+        RTCHK(rt_d2h(recs + c0, (c2b_read_rec *)m.recs.p + c0, (size_t)n * sizeof(c2b_read_rec), e->s_out));
+        RTCHK(rt_d2h(alns + c0 * nr, (c2b_aln_rec *)m.alns.p + c0 * nr, (size_t)n * nr * sizeof(c2b_aln_rec), e->s_out));
+        if (cap) RTCHK(rt_d2h(edits + c0 * nr * cap, (c2b_edit *)m.ed.p + c0 * nr * cap, (size_t)n * nr * cap * sizeof(c2b_edit), e->s_out));
+        if (strings) {
+            size_t Wt = ((size_t)h_poll[8 + 2 * nc + c] + 31) & ~(size_t)31;
+            if (Wt > (size_t)W) Wt = W;
+            RTCHK(rt_d2h_2d(strings + c0 * nr * 2 * W + (W - Wt), (const uint8_t *)m.str.p + c0 * nr * 2 * W + (W - Wt), W, Wt, (size_t)n * nr * 2, e->s_out));
+        }
+    }
+    RTCHK(rt_sync(e->s_out));
+    RTCHK(rt_sync(e->stream));
+    {   // stats[7]: a wait inside the kernel timed out
+        unsigned long long flag = 0;
+        RTCHK(rt_d2h(&flag, (const char *)e->work.p + 7 * 8, 8, e->stream));
+        RTCHK(rt_sync(e->stream));
+        if (flag) return fail(e, C2B_E_CUDA, "c2b_align_batch: streamed launch timed out waiting for input");
+    }
+    return C2B_OK;
+}
+#endif
+
 int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads,
                     const int32_t *count, const int32_t *qweight, const int32_t *ref_id,
                     c2b_read_rec *recs, c2b_aln_rec *alns, uint8_t *strings, c2b_edit *edits)
@@ -702,6 +914,10 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
         for (auto &st : e->stage) { RTCHK(rt_event_create(&st.in_done)); RTCHK(rt_event_create(&st.k_done)); RTCHK(rt_event_create(&st.out_done)); }
         e->pipe_ready = true;
     }
+#ifndef C2B_EMU
+    if (n_reads >= (1 << 16) && n_reads <= (4 << 20) && streamed_default(e))
+        return align_batch_streamed(e, reads, offsets, n_reads, maxJ, count, qweight, ref_id, recs, alns, strings, edits);
+#endif
     const int W = (e->max_I + (int)maxJ + 31) & ~31;
     const int cap = edits ? e->prm.edit_cap : 0;
     const int nr = ref_id ? 1 : e->n_refs;                 // output slots per read (compact when ref_id is given)

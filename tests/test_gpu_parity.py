@@ -235,3 +235,41 @@ def test_banded_slab_falls_back_to_full_slab(eng):
 
 def test_coding_seq_frameshift_splicing_and_size_histograms(eng):
     PU.check_coding_seq(eng, n_reads=400)
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_streamed_launch_equals_chunked_launches(eng, monkeypatch, mixed):
+    """Host-buffer batches of >= 64 Ki reads go through one persistent launch fed chunk by chunk (read bytes arrive while
+    the kernel runs, finished chunks leave while it runs; C2B_STREAMED=1); C2B_STREAMED=0 is the launch-per-chunk pipeline.  Same
+    records, alignments, strings, edit lists and count block."""
+    rng = np.random.default_rng(12)
+    amp = synth.random_amplicon(rng, 250)
+    ref = synth.amplicon_setup(amp)
+    n = 150_001
+    reads = synth.synth_reads_fast(rng, amp, n, 250, sub_rate=0.01, cut=ref["cut_point"])
+    if mixed:
+        lens = rng.integers(200, 251, size=n)
+        lens[rng.random(n) < 0.7] = 250
+    else:
+        lens = np.full(n, 250)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    buf = reads[np.arange(250)[None, :] < lens[:, None]]
+    cnt = rng.integers(1, 4, size=n).astype(np.int32)
+    out = []
+    for streamed in ("1", "0"):
+        monkeypatch.setenv("C2B_STREAMED", streamed)
+        eng.configure({"Reference": ref}, ["Reference"], O.make_matrix(), -20, -2, 5, 2, 0, "ACGTN", 8)
+        eng.counts_reset()
+        res = eng.align_packed(buf, off, count=cnt, qweight=cnt)
+        out.append((res, eng.counts_raw()))
+    monkeypatch.delenv("C2B_STREAMED", raising=False)
+    (a, ca), (b, cb) = out
+    assert (a.recs == b.recs).all() and (a.alns == b.alns).all() and (ca == cb).all()
+    assert (a.recs["best_score_milli"] > 0).mean() > 0.9
+    W = a.W
+    valid = (np.arange(W)[None, :] >= (W - a.alns[:, 0]["aln_len"].astype(np.int64))[:, None])[:, None, None, :]
+    assert ((a.strings == b.strings) | ~valid).all()
+    ne = a.alns[:, 0]["n_edits"].astype(np.int64)
+    slot = np.arange(a.edits.shape[2])[None, :] < np.minimum(ne, a.edits.shape[2])[:, None]
+    assert (a.edits[:, 0][slot] == b.edits[:, 0][slot]).all()
