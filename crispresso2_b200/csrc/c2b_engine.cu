@@ -5,6 +5,7 @@
 //        -Iinclude -o crispresso2_b200/libc2b200.so crispresso2_b200/csrc/c2b_engine.cu
 // The same file compiles with g++ -DC2B_EMU against tests/emu/warp_emu.h (CPU-only logic tests).
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_a
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                     if (!t0) t0 = now;
                     if (now - t0 > 20000000000ull) { atomicExch(P.stats + 7, 1ull); nxt = ~0ull; next_base[WARPS_PER_CTA + set] = 1; break; }
-                    __nanosleep(400);
+                    __nanosleep(1000);
                 }
             }
             next_base[set] = nxt;
@@ -865,10 +866,13 @@ static int align_batch_streamed(c2b_engine *e, const uint8_t *reads, const int64
     for (int c = 0; c < nc; c++) {
         const unsigned long long want = (unsigned long long)((cuts[c + 1] + 7) / 8 - (cuts[c] + 7) / 8);
         int idle = 0;
+        const auto t_wait = std::chrono::steady_clock::now();
         for (;;) {
             RTCHK(rt_d2h(h_poll, d_ctl, ctl_n * 8, m.s_poll));
             RTCHK(rt_sync(m.s_poll));
             if (h_poll[8 + nc + c] >= want) break;
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_wait).count() > 120.0)
+                return fail(e, C2B_E_CUDA, "c2b_align_batch: streamed launch made no progress for 120 s");
             if (cudaStreamQuery(e->stream) == cudaSuccess && ++idle > 2)
                 return fail(e, C2B_E_CUDA, "c2b_align_batch: streamed launch ended before all chunks were complete");
         }

@@ -237,6 +237,7 @@ def test_coding_seq_frameshift_splicing_and_size_histograms(eng):
     PU.check_coding_seq(eng, n_reads=400)
 
 
+@pytest.mark.timeout(600)
 @pytest.mark.parametrize("mixed", [False, True])
 def test_streamed_launch_equals_chunked_launches(eng, monkeypatch, mixed):
     """Host-buffer batches of >= 64 Ki reads go through one persistent launch fed chunk by chunk (read bytes arrive while
