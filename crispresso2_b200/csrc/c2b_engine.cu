@@ -80,7 +80,9 @@ constexpr int WARPS_PER_CTA = C2B_WARPS_PER_CTA;      // launch-bounds maximum; 
 
 // ONE: every read has one candidate reference (a single amplicon configured, or Pooled ref_id): the lean instantiation
 // carries none of the several-references code.  The host picks the instantiation per launch.
-template <bool ONE>
+// STREAM: the batch's read bytes arrive while the kernel runs (c2b_align_batch, streamed launch); the resident-batch
+// instantiations keep the plain work loop (the streaming additions alone cost 10 ms per million reads when compiled in).
+template <bool ONE, bool STREAM>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_align_classify_kernel(const KParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -110,6 +112,35 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_a
     // Work groups (8 reads each) are handed out per phase set (g consecutive warps, one group per warp), one hand-out
     // ahead, so that the loop count -- and with it the number of barriers executed by process_group's phases -- is the
     // same for every warp of the set, and the next group's read bytes are on their way to L2 while this one computes.
+    if constexpr (!STREAM) {
+    __shared__ unsigned long long next_base[WARPS_PER_CTA];
+    const int gs = P.phase_sync, g = gs > 0 ? gs : gs < 0 ? -gs : 1, wib = threadIdx.x >> 5, nsets = (int)(blockDim.x >> 5) / g;
+    const int set = gs < 0 ? wib % nsets : wib / g, wis = gs < 0 ? wib / nsets : wib % g;
+    const unsigned long long total = ((unsigned long long)P.n_reads + 7) / 8;
+    auto hand_out = [&]() -> unsigned long long {
+        if (wis == 0 && (threadIdx.x & 31) == 0) next_base[set] = atomicAdd(P.work_counter, (unsigned long long)g);
+        if (g > 1) wp::grp_sync(gs); else __syncwarp();
+        const unsigned long long b = next_base[set];
+        if (g > 1) wp::grp_sync(gs); else __syncwarp();
+        return b;
+    };
+    unsigned long long base = hand_out();
+    while (base < total) {
+        const unsigned long long nb = hand_out();
+        const unsigned long long wn = nb + wis;
+        if (wn < total && !P.pair_order) {
+            const int64_t last = (int64_t)(8 * wn + 8) < P.n_reads ? (int64_t)(8 * wn + 8) : P.n_reads;
+            const int64_t b0 = P.offsets[8 * wn], b1 = P.offsets[last];
+            const int64_t a = b0 + (int64_t)(threadIdx.x & 31) * 128;
+            if (a < b1) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.reads + a));
+        }
+        const unsigned long long w = base + wis;
+        if (w < total) process_group<ONE>(P, *S, *Q, staged_prof, (int64_t)w, warp_slot);  // reads 8w .. 8w+7
+        else if (P.phase_sync) for (int b = group_phases(P); b > 0; b--) wp::grp_sync(gs);
+        __syncwarp();
+        base = nb;
+    }
+    } else {
     __shared__ unsigned long long next_base[2 * WARPS_PER_CTA];   // [set]: next hand-out; [WARPS_PER_CTA + set]: wait timed out
     const int gs = P.phase_sync, g = gs > 0 ? gs : gs < 0 ? -gs : 1, wib = threadIdx.x >> 5, nsets = (int)(blockDim.x >> 5) / g;
     const int set = gs < 0 ? wib % nsets : wib / g, wis = gs < 0 ? wib / nsets : wib % g;
@@ -181,6 +212,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_a
         else if (P.phase_sync) for (int b = group_phases(P); b > 0; b--) wp::grp_sync(gs);
         __syncwarp();
         base = nb;
+    }
     }
 }
 #endif
@@ -276,13 +308,16 @@ int c2b_create(int device, c2b_engine **out)
     if (e->stage_cap < 0) e->stage_cap = 0;
     e->stage_cap &= ~127;
     const int dyn_smem = (int)((sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA) + 128 + e->stage_cap;
-    if (r == cudaSuccess) r = cudaFuncSetAttribute(c2b_align_classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
-    if (r == cudaSuccess) r = cudaFuncSetAttribute(c2b_align_classify_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
-    if (r == cudaSuccess) {       // both instantiations must fit the same persistent grid
-        int occ1 = 0, occ0 = 0;
-        r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, c2b_align_classify_kernel<true>, WARPS_PER_CTA * 32, dyn_smem);
-        if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, c2b_align_classify_kernel<false>, WARPS_PER_CTA * 32, dyn_smem);
-        occ = std::min(occ1, occ0);
+    {
+        const void *kernels[4] = {(const void *)c2b_align_classify_kernel<true, false>, (const void *)c2b_align_classify_kernel<false, false>,
+                                  (const void *)c2b_align_classify_kernel<true, true>, (const void *)c2b_align_classify_kernel<false, true>};
+        occ = 1 << 20;
+        for (const void *k : kernels) {                    // all instantiations must fit the same persistent grid
+            int o = 0;
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+            if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k, WARPS_PER_CTA * 32, dyn_smem);
+            occ = std::min(occ, o);
+        }
     }
     if (r != cudaSuccess) { g_create_err = std::string("c2b_create: ") + cudaGetErrorString(r); delete e; return C2B_E_CUDA; }
     if (occ < 1) occ = 1;
@@ -653,8 +688,11 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
     {
         const size_t smem = (sizeof(WarpSmem) + sizeof(QuadSmem)) * e->wpc + 128 + (size_t)P.stage_bytes;
         const bool one = (e->n_refs == 1 || d_ref_id != nullptr) && !getenv("C2B_GENERIC_KERNEL");      // one candidate reference per read
-        if (one) c2b_align_classify_kernel<true><<<e->grid, e->wpc * 32, smem, cs>>>(P);
-        else c2b_align_classify_kernel<false><<<e->grid, e->wpc * 32, smem, cs>>>(P);
+        const bool stream = P.avail != nullptr;
+        if (one && !stream) c2b_align_classify_kernel<true, false><<<e->grid, e->wpc * 32, smem, cs>>>(P);
+        else if (!stream) c2b_align_classify_kernel<false, false><<<e->grid, e->wpc * 32, smem, cs>>>(P);
+        else if (one) c2b_align_classify_kernel<true, true><<<e->grid, e->wpc * 32, smem, cs>>>(P);
+        else c2b_align_classify_kernel<false, true><<<e->grid, e->wpc * 32, smem, cs>>>(P);
     }
     cudaEventRecord(e->ev1, cs);
     RTCHK(cudaGetLastError());
