@@ -153,6 +153,15 @@ def test_chunked_pipeline_equals_one_chunk(emu, monkeypatch):
         assert a.pair(i) == b.pair(i)
 
 
+def test_chunked_pipeline_with_per_read_amplicon(emu, monkeypatch):
+    """Pooled batches (compact [read][0] outputs) through several pipelined chunks."""
+    monkeypatch.setenv("C2B_CHUNK", "10")
+    try:
+        PU.check_pooled(emu, n_amplicons=5, reads_per=9, seed=33)
+    finally:
+        monkeypatch.delenv("C2B_CHUNK", raising=False)
+
+
 def test_long_amplicon_three_row_blocks(emu):
     """A 610-bp amplicon (three 256-row blocks on the 32-bit path) with 150..400-bp reads."""
     rng = np.random.default_rng(12)
