@@ -298,7 +298,9 @@ int c2b_create(int device, c2b_engine **out)
     if (r == cudaSuccess) r = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
     if (r == cudaSuccess) r = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     // room for a TMA-staged reference tile next to C2B_MIN_CTAS_PER_SM CTAs of per-warp state (1 KB per CTA is reserved by the driver)
-    e->stage_cap = smem_sm / C2B_MIN_CTAS_PER_SM - 1024 - (int)((sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA) - 256;
+    // ... and the kernels' static shared memory (up to 1.3 KB: hand-out slots, mbarrier) -- if the sum is a byte too large the
+    // occupancy query answers 1 CTA per SM and the persistent grid silently halves (r01k: 37 ms instead of 27)
+    e->stage_cap = smem_sm / C2B_MIN_CTAS_PER_SM - 1024 - (int)((sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA) - 2048;
     {   // ... and within the per-block opt-in limit
         int optin = 0;
         if (r == cudaSuccess) r = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -321,6 +323,8 @@ int c2b_create(int device, c2b_engine **out)
     }
     if (r != cudaSuccess) { g_create_err = std::string("c2b_create: ") + cudaGetErrorString(r); delete e; return C2B_E_CUDA; }
     if (occ < 1) occ = 1;
+    if (occ < C2B_MIN_CTAS_PER_SM && !getenv("C2B_CTAS_PER_SM"))
+        fprintf(stderr, "[c2b] warning: only %d CTA(s) of the align kernel fit an SM (built for %d)\n", occ, C2B_MIN_CTAS_PER_SM);
     e->wpc = WARPS_PER_CTA;
     if (const char *v = getenv("C2B_WARPS_PER_CTA")) { int k = atoi(v); if (k >= 1 && k <= WARPS_PER_CTA) e->wpc = k; }
     if (const char *v = getenv("C2B_CTAS_PER_SM")) { int k = atoi(v); if (k >= 1 && k <= occ) occ = k; }
@@ -957,8 +961,19 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
         e->pipe_ready = true;
     }
 #ifndef C2B_EMU
-    if (n_reads >= (1 << 16) && n_reads <= (4 << 20) && streamed_default(e))
-        return align_batch_streamed(e, reads, offsets, n_reads, maxJ, count, qweight, ref_id, recs, alns, strings, edits);
+    if (n_reads >= (1 << 16) && streamed_default(e)) {
+        // one persistent launch per slice of up to 4 Mi reads (whole-slice device buffers: about 1.2 KB per read)
+        const int64_t slice = 4 << 20;
+        const int64_t Wb = (e->max_I + (int)maxJ + 31) & ~31, nrb = ref_id ? 1 : e->n_refs, capb = edits ? e->prm.edit_cap : 0;
+        for (int64_t k = 0; k < n_reads; k += slice) {
+            const int64_t n = std::min(slice, n_reads - k);
+            const int rc2 = align_batch_streamed(e, reads, offsets + k, n, maxJ, count ? count + k : nullptr, qweight ? qweight + k : nullptr,
+                                                 ref_id ? ref_id + k : nullptr, recs + k, alns + k * nrb,
+                                                 strings ? strings + k * nrb * 2 * Wb : nullptr, edits ? edits + k * nrb * capb : nullptr);
+            if (rc2) return rc2;
+        }
+        return C2B_OK;
+    }
 #endif
     const int W = (e->max_I + (int)maxJ + 31) & ~31;
     const int cap = edits ? e->prm.edit_cap : 0;
