@@ -81,7 +81,7 @@ constexpr int WARPS_PER_CTA = C2B_WARPS_PER_CTA;      // launch-bounds maximum; 
 // ONE: every read has one candidate reference (a single amplicon configured, or Pooled ref_id): the lean instantiation
 // carries none of the several-references code.  The host picks the instantiation per launch.
 // STREAM: the batch's read bytes arrive while the kernel runs (c2b_align_batch, streamed launch); the resident-batch
-// instantiations keep the plain work loop (the streaming additions alone cost 10 ms per million reads when compiled in).
+// instantiations keep the plain work loop, without the availability wait and the per-group completion signalling.
 template <bool ONE, bool STREAM>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_align_classify_kernel(const KParams P)
 {
