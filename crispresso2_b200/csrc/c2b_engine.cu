@@ -887,15 +887,11 @@ static int align_batch_streamed(c2b_engine *e, const uint8_t *reads, const int64
     // the copy stream starts after the control block, offsets and per-read arrays are in place (queued above on `stream`)
     RTCHK(rt_record(e->fork_ev, e->stream));
     RTCHK(rt_wait(e->s_in, e->fork_ev));
-    // launch: the kernel spins until the first chunk's bytes are there
-    e->k_avail = d_ctl; e->k_chunk_end = d_ctl + 8; e->k_chunk_done = d_ctl + 8 + nc; e->k_n_chunks = nc;
-    rc = launch_on(e, e->stream, 0, (const uint8_t *)m.reads.p, (const int64_t *)m.off.p, n_reads, (int32_t)maxJ,
-                   count ? (const int32_t *)m.cnt.p : nullptr, qweight ? (const int32_t *)m.qw.p : nullptr,
-                   ref_id ? (const int32_t *)m.rid.p : nullptr, (c2b_read_rec *)m.recs.p, (c2b_aln_rec *)m.alns.p,
-                   strings ? (uint8_t *)m.str.p : nullptr, cap ? (c2b_edit *)m.ed.p : nullptr);
-    e->k_avail = nullptr; e->k_chunk_end = nullptr; e->k_chunk_done = nullptr; e->k_n_chunks = 0;
-    e->pair_order = nullptr;
-    if (rc) return rc;
+    // All copies are queued BEFORE the launch: with pinned host buffers they are asynchronous and overlap the kernel just the
+    // same, and nothing the kernel waits for depends on host code that runs after the launch call -- a launch that blocks
+    // the host (CUDA_LAUNCH_BLOCKING, a profiler serialising kernels) would otherwise leave the kernel waiting for
+    // copies that are never issued.  (Pageable host buffers make cudaMemcpyAsync synchronous: correct, but the upload then
+    // precedes the kernel instead of overlapping it -- use c2b_host_alloc.)
     unsigned long long *h_avail = h + ctl_n;               // pinned, one slot per chunk
     for (int c = 0; c < nc; c++) {
         const int64_t a = m.h_off[cuts[c]];
@@ -905,6 +901,15 @@ static int align_batch_streamed(c2b_engine *e, const uint8_t *reads, const int64
         h_avail[c] = (unsigned long long)((cuts[c + 1] + 7) / 8);
         RTCHK(rt_h2d(d_ctl, &h_avail[c], 8, e->s_in));
     }
+    // launch: work groups whose bytes have not arrived yet are waited for inside the kernel
+    e->k_avail = d_ctl; e->k_chunk_end = d_ctl + 8; e->k_chunk_done = d_ctl + 8 + nc; e->k_n_chunks = nc;
+    rc = launch_on(e, e->stream, 0, (const uint8_t *)m.reads.p, (const int64_t *)m.off.p, n_reads, (int32_t)maxJ,
+                   count ? (const int32_t *)m.cnt.p : nullptr, qweight ? (const int32_t *)m.qw.p : nullptr,
+                   ref_id ? (const int32_t *)m.rid.p : nullptr, (c2b_read_rec *)m.recs.p, (c2b_aln_rec *)m.alns.p,
+                   strings ? (uint8_t *)m.str.p : nullptr, cap ? (c2b_edit *)m.ed.p : nullptr);
+    e->k_avail = nullptr; e->k_chunk_end = nullptr; e->k_chunk_done = nullptr; e->k_n_chunks = 0;
+    e->pair_order = nullptr;
+    if (rc) return rc;
     // completion: poll the per-chunk counters, copy each chunk out as soon as it is whole
     unsigned long long *h_poll = h + ctl_n + nc + 8;        // third part of the pinned block
     for (int c = 0; c < nc; c++) {
