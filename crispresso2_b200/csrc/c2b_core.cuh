@@ -314,27 +314,6 @@ C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const 
             if ((n & 15) == 0) { const int ix = (n >> 4) - 1; if (hl == (ix >> 1)) { if (ix & 1) hi = acc; else lo = acc; } }
         }
     };
-    // Slab word of cell (ci, cj) for this lane, or "not kept" (-1): the one address computation of the walk.
-    auto cell_index = [&](int ci, int cj) -> int64_t {
-        if (ci < 1 || cj < 1) return -1;
-        const int r = ci - 1, key = r >> 3, rb = key >> 5, l = key & 31;
-        const int slot = cj + l - sm.slope * l + sm.off;
-        if ((unsigned)slot >= (unsigned)sm.ns) return -1;
-        return sm.ring ? (int64_t)(sm.gb + (l & 7)) * TS + cj + l : ((int64_t)rb * TS + slot) * 32 + l;
-    };
-    // While the walk runs down the diagonal (state M, whole windows of G cells) the next windows are known in advance:
-    // their slab words are loaded two windows ahead into registers (qA: the window the next iteration reads, qB, qC the two
-    // after it), so the L2 latency of a window overlaps the processing of the ones before it instead of heading every
-    // iteration's dependency chain.  Any other step (a break in the run, a gap state) drops the queue and reloads.
-    uint2 qA = make_uint2(0u, 0u), qB = qA, qC = qA;
-    bool queued = false;
-    auto fetch = [&](int ti, int tj) -> uint2 {
-        const int64_t idx = cell_index(ti - hl, tj - hl);
-        uint2 w = make_uint2(0u, 0u);
-        if (idx >= 0) { if (PAIR) w = wp::ldcg2(tb2 + idx); else w.x = wp::ldcg(tb + idx); }
-        return w;
-    };
-    if (s == OP_M && i > 0 && j > 0) { qA = fetch(i, j); qB = fetch(i - G, j - G); qC = fetch(i - 2 * G, j - 2 * G); queued = true; }
     for (;;) {
         const bool active = i > 0 && j > 0;
         if (!wp::ballot(active)) break;
@@ -344,15 +323,16 @@ C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const 
         uint32_t v = 0;
         bool inband = valid;
         if (valid) {
-            const int64_t idx = cell_index(ci, cj);
-            inband = idx >= 0;
+            const int r = ci - 1, key = r >> 3, rb = key >> 5, l = key & 31;
+            const int slot = cj + l - sm.slope * l + sm.off;
+            inband = (unsigned)slot < (unsigned)sm.ns;
             if (inband) {
-                const int r = ci - 1;
+                const int64_t idx = sm.ring ? (int64_t)(sm.gb + (l & 7)) * TS + cj + l : ((int64_t)rb * TS + slot) * 32 + l;
                 if (PAIR) {
-                    const uint2 w2 = (queued && s == OP_M) ? qA : wp::ldcg2(tb2 + idx);
+                    const uint2 w2 = wp::ldcg2(tb2 + idx);
                     const uint32_t w = hb ? ((w2.x & 0xffff0000u) | (w2.y >> 16)) : ((w2.x << 16) | (w2.y & 0xffffu));
                     v = w >> (2 * (7 - (r & 7)));
-                } else v = ((queued && s == OP_M) ? qA.x : wp::ldcg(tb + idx)) >> (2 * (r & 7));
+                } else v = wp::ldcg(tb + idx) >> (2 * (r & 7));
             }
         }
         const int tag = (int)((v >> 16) & 3u);
@@ -367,21 +347,28 @@ C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const 
         const bool brk = f < nvalid;
         const int run = brk ? f + 1 : nvalid;
         const int tagf = wp::shfl(tag, hb + (f < G ? f : G - 1));
-        if (miss) { err |= 4; i = 0; j = 0; queued = false; }
+        if (miss) { err |= 4; i = 0; j = 0; }
         else if (active) {
             const int news = brk ? (s == OP_M ? tagf : OP_M) : s;
-            const bool whole = queued && s == OP_M && news == OP_M && run == G;     // a whole window down the diagonal
             push(s, run);
             i -= run * di; j -= run * dj;
             err |= (news == 3);
             s = news;
-            if (s == OP_M && i > 0 && j > 0) {
-                if (whole) { qA = qB; qB = qC; }
-                else { qA = fetch(i, j); qB = fetch(i - G, j - G); }
-                qC = fetch(i - 2 * G, j - 2 * G);
-                queued = true;
-            } else queued = false;
-        } else queued = false;
+            if (s == OP_M && sm.ring) {                     // ring slab: the next but one window (two lanes' worth of consecutive entries)
+                const int pi = i - 2 * G - hl, pj = j - 2 * G - hl;
+                if (pi >= 1 && pj >= 1 && (hl & 3) == 0) {
+                    const int l = (pi - 1) >> 3;
+                    wp::prefetch_l2(tb2 + (int64_t)(sm.gb + (l & 7)) * TS + pj + l);
+                }
+            } else if (s == OP_M && sm.slope == 0) {        // full slab: pull the window two iterations down the diagonal towards L2
+                const int pi = i - 2 * G - hl, pj = j - 2 * G - hl;
+                if (pi >= 1 && pj >= 1) {
+                    const int r = pi - 1, key = r >> 3, rb = key >> 5, l = key & 31;
+                    const int64_t idx = ((int64_t)rb * TS + pj + l) * 32 + l;
+                    wp::prefetch_l2(PAIR ? (const void *)(tb2 + idx) : (const void *)(tb + idx));
+                }
+            }
+        }
     }
     if (j > 0 && s != OP_I) err = 1;                        // row 0 / column 0 can only be left along their own border
     if (i > 0 && s != OP_J) err = 1;
