@@ -143,6 +143,10 @@ struct KParams {
     const unsigned long long *chunk_end;   // [n_chunks] end group (exclusive) of every chunk
     unsigned long long *chunk_done;        // [n_chunks] groups completed; [n_chunks + c]: widest alignment of chunk c
     int32_t n_chunks;
+#ifdef C2B_X_REF0
+    int32_t use_ref0;                      // one reference configured: its descriptor rides in the kernel parameters (constant bank)
+    RefDev ref0;
+#endif
     int32_t vstride, hstride;
     const uint32_t *stage_src;        // = refs[0].prof2 (global source of the staged tile)
     int32_t stage_bytes;              // bytes of refs[0].prof2 staged into shared memory by TMA at kernel start (0: none)
@@ -155,6 +159,12 @@ struct KParams {
 
 // output slot of (read, reference): [read][ref] -- or [read][0] when every read carries its single reference (ref_id)
 C2B_DEV int64_t oslot(const KParams &P, int64_t rd, int r) { return rd * P.out_refs + (P.ref_id ? 0 : r); }
+
+#ifdef C2B_X_REF0
+C2B_DEV const RefDev &refdev(const KParams &P, int r) { return P.use_ref0 ? P.ref0 : P.refs[r]; }
+#else
+C2B_DEV const RefDev &refdev(const KParams &P, int r) { return P.refs[r]; }
+#endif
 
 struct WarpSmem {
     uint8_t fw[2][MAXJ];       // read(s) as alphabet codes ([1]: second read of a pair)
@@ -884,7 +894,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
         int nth = 0;
         for (int r = r_begin; r < r_end; r++) {
             if (!((rec.winner_mask >> (r & 31)) & 1u)) continue;
-            const RefDev &R = P.refs[r];
+            const RefDev &R = refdev(P, r);
             rec.best_ref = (int16_t)r;                          // best_match_name = last winner (:768)
             int irr = keep_irr;
             if (multi) irr = rescatter(P, R, rd, r, opsbuf, hoff, rowinfo, rowins, fw, rc, J);
@@ -1018,7 +1028,7 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
     c2b_aln_rec a; init_aln(a, st);
 
     for (int r = r_begin; r < r_end; r++) {
-        const RefDev &R = P.refs[r];
+        const RefDev &R = refdev(P, r);
         init_aln(a, st);
         if (!st && (R.I + J > C2B_MAX_ALN_LEN)) a.status |= C2B_ST_TOO_LONG;
         if (!a.status) {
@@ -1352,7 +1362,7 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
     c2b_aln_rec a; init_aln(a, st);
 
     for (int r = r_begin; r < r_end; r++) {
-        const RefDev &R = P.refs[r];
+        const RefDev &R = refdev(P, r);
         init_aln(a, st);
         int mAB = 0;
         if (ring) mAB = ring->modes;
@@ -1455,7 +1465,7 @@ C2B_DEV void process_item(const KParams &P, WarpSmem &S, const uint32_t *staged_
         if (pair && P.ref_id && haveB && P.ref_id[rdA] != P.ref_id[rdB]) pair = false;
         if (pair) {
             const int r_begin = P.ref_id ? P.ref_id[rdA] : 0, r_end = P.ref_id ? r_begin + 1 : P.n_refs;
-            for (int r = r_begin; r < r_end; r++) if (Ja > P.refs[r].pk_maxJ) pair = false;
+            for (int r = r_begin; r < r_end; r++) if (Ja > refdev(P, r).pk_maxJ) pair = false;
         }
     }
     if (wp::lane() == 0) wp::addg(P.stats + (pair ? 2 : 3), 1);      // path statistics (c2b_path_counts)
@@ -1479,7 +1489,7 @@ C2B_DEV void process_quad(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint
     int Jg = 0, Jmax = 0;
     const int64_t rd0 = P.pair_order ? P.pair_order[2 * first] : 2 * first;
     const int r = P.ref_id ? P.ref_id[rd0] : 0;
-    const RefDev &R = P.refs[r];
+    const RefDev &R = refdev(P, r);
 #pragma unroll 1
     for (int q = 0; q < 4; q++) {
         const int64_t rdA = P.pair_order ? P.pair_order[2 * (first + q)] : 2 * (first + q);
@@ -1597,7 +1607,7 @@ C2B_DEVNOINL void process_quad_multi(const KParams &P, WarpSmem &S, QuadSmem &Q,
     int npass = 0;
 #pragma unroll 1
     for (int k = 0; k < P.n_refs && okmask; k++) {
-        const RefDev &R = P.refs[k];
+        const RefDev &R = refdev(P, k);
         const bool staged = (k == 0 && staged_prof != nullptr);
         uint32_t *fin = S.rowins;
         if (staged) dp_ring<true>(P, R, staged_prof, Q.combo[g], Jg, Jmax + R.lstar, tbq, fin);
@@ -1668,7 +1678,7 @@ C2B_DEV void process_group(const KParams &P, WarpSmem &S, QuadSmem &Q, const uin
         bool ok = rx == r0 && Jx == Jn && Jx >= 1 && Jx <= RG_COMBO && Jx + 32 <= P.TS;
         const int k0 = multi ? 0 : r0, k1 = multi ? P.n_refs : r0 + 1;
         for (int k = k0; k < k1; k++) {                     // every reference the reads are tried against must admit the band
-            const RefDev &R = P.refs[k];
+            const RefDev &R = refdev(P, k);
             ok = ok && R.rg_ok && Jx <= R.pk_maxJ && Jx - R.I <= RG_MAXD && R.I - Jx <= RG_MAXD;
         }
         quad = wp::ballot(ok) == 0xffffffffu;
