@@ -143,10 +143,6 @@ struct KParams {
     const unsigned long long *chunk_end;   // [n_chunks] end group (exclusive) of every chunk
     unsigned long long *chunk_done;        // [n_chunks] groups completed; [n_chunks + c]: widest alignment of chunk c
     int32_t n_chunks;
-#ifdef C2B_X_REF0
-    int32_t use_ref0;                      // one reference configured: its descriptor rides in the kernel parameters (constant bank)
-    RefDev ref0;
-#endif
     int32_t vstride, hstride;
     const uint32_t *stage_src;        // = refs[0].prof2 (global source of the staged tile)
     int32_t stage_bytes;              // bytes of refs[0].prof2 staged into shared memory by TMA at kernel start (0: none)
@@ -160,11 +156,8 @@ struct KParams {
 // output slot of (read, reference): [read][ref] -- or [read][0] when every read carries its single reference (ref_id)
 C2B_DEV int64_t oslot(const KParams &P, int64_t rd, int r) { return rd * P.out_refs + (P.ref_id ? 0 : r); }
 
-#ifdef C2B_X_REF0
-C2B_DEV const RefDev &refdev(const KParams &P, int r) { return P.use_ref0 ? P.ref0 : P.refs[r]; }
-#else
+// (A copy of the single reference's descriptor inside the kernel parameters was tried: no gain, 25.85 against 25.55 ms.)
 C2B_DEV const RefDev &refdev(const KParams &P, int r) { return P.refs[r]; }
-#endif
 
 struct WarpSmem {
     uint8_t fw[2][MAXJ];       // read(s) as alphabet codes ([1]: second read of a pair)

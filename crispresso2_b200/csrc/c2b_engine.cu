@@ -668,10 +668,6 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
     P.vstride = e->vstride; P.hstride = e->hstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
     P.avail = e->k_avail; P.chunk_end = e->k_chunk_end; P.chunk_done = e->k_chunk_done; P.n_chunks = e->k_n_chunks;
-#ifdef C2B_X_REF0
-    P.use_ref0 = (e->n_refs == 1 && !getenv("C2B_NO_REF0")) ? 1 : 0;
-    if (P.use_ref0) P.ref0 = e->refdev[0];
-#endif
     P.phase_sync = 4;                                     // warps per phase set (C2B_PHASE_WARPS: 0/1 = free-running, 2, 4, 8)
     if (const char *v = getenv("C2B_PHASE_WARPS")) { const int k = atoi(v), a = k < 0 ? -k : k; P.phase_sync = (a == 2 || a == 4 || a == 8 || a == 16) ? k : 0; }
     {   // grp_sync wants |g| and the number of sets to be powers of two
