@@ -288,6 +288,96 @@ def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_
     return st, not_aligned
 
 
+def process_fastq_sharded(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory,
+                          engine=None, aln_matrix=None, group=None):
+    """process_fastq for one process per GPU (torch.distributed initialised): every rank reads and de-duplicates the FASTQ,
+    aligns its contiguous slice of the unique reads (the reference's own sharding rule, CRISPRessoCORE.py:1172-1195), then
+    the count blocks are summed with ONE all-reduce (NCCL on the device block; gloo on the CPU test path) and the per-read
+    variants and statistics are gathered, so that every rank returns exactly what the single-process call returns --
+    same variantCache (keys in first-seen order), same aln_stats, same count block behind quantify()."""
+    import torch.distributed as dist
+    from . import dist as cdist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory,
+                             engine=engine, aln_matrix=aln_matrix)
+    _unsupported(args)
+    if aln_matrix is None:
+        aln_matrix = read_matrix(args.needleman_wunsch_aln_matrix_loc)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    engine = engine or get_engine()
+    dd = fastq.dedup_file(fastq_filename, lib_path=engine.lib_path)
+    for seq, c in zip(dd.uniques, dd.counts.tolist()):
+        variantCache[seq] = variantCache.get(seq, 0) + c
+    configure_engine(engine, args, refs, ref_names, aln_matrix)
+    engine.counts_reset()
+    uniques = list(variantCache.keys())
+    counts = [variantCache[s] for s in uniques]
+    flags = _flags(args)
+    weights = merge_weights(uniques, counts)                # needs the global unique table: before sharding
+    lo, hi = cdist.shard_bounds(len(uniques), rank, world)
+    mine = uniques[lo:hi]
+    local = []                                              # (variant or None) per unique of this shard
+    if mine:
+        res, _ = align_uniques(engine, mine, counts[lo:hi], ref_names, refs, flags, weights=weights[lo:hi])
+        over = np.nonzero(res.recs["status"] & _lib.ST_EDIT_OVERFLOW)[0]
+        fix = {}
+        if len(over):
+            cap0 = engine.edit_cap
+            engine.set_edit_cap(max(engine.ref_lens) + _lib.MAX_READ_LEN)
+            zero = np.zeros(len(over), dtype=np.int32)
+            r2 = engine.align([mine[k] for k in over], count=zero, qweight=zero)
+            r2.flags = flags
+            engine.set_edit_cap(cap0)
+            fix = {int(k): (r2, j) for j, k in enumerate(over)}
+        for k, seq in enumerate(mine):
+            rr, kk = fix.get(k, (res, k))
+            v = _variant_from(rr, kk, seq, ref_names, refs)
+            v["count"] = counts[lo + k]
+            local.append(v)
+    merged = cdist.allreduce_counts(engine, group)          # the path's one collective on device data
+    parts = [None] * world
+    dist.all_gather_object(parts, local, group=group)
+    st = dict.fromkeys(["N_TOT_READS", "N_CACHED_ALN", "N_CACHED_NOTALN", "N_COMPUTED_ALN", "N_COMPUTED_NOTALN",
+                        "N_GLOBAL_SUBS", "N_SUBS_OUTSIDE_WINDOW", "N_MODS_IN_WINDOW", "N_MODS_OUTSIDE_WINDOW",
+                        "N_READS_IRREGULAR_ENDS", "READ_LENGTH"], 0)
+    not_aligned, class_extra = {}, {}
+    k = 0
+    for part in parts:                                      # rank order = unique order: the serial loop of :1956-1981
+        for v in part:
+            seq, c = uniques[k], counts[k]
+            st["N_TOT_READS"] += c
+            if v["best_match_score"] <= 0:
+                st["N_COMPUTED_NOTALN"] += 1
+                st["N_CACHED_NOTALN"] += c - 1
+                not_aligned[seq] = v
+            else:
+                variantCache[seq] = v
+                if "&" in v["class_name"] and weights[k] > 0:
+                    class_extra[v["class_name"]] = class_extra.get(v["class_name"], 0) + int(weights[k])
+                st["N_COMPUTED_ALN"] += 1
+                st["N_CACHED_ALN"] += c - 1
+                p = v["variant_" + v["best_match_name"]]
+                if st["READ_LENGTH"] == 0:
+                    st["READ_LENGTH"] = len(p["aln_seq"])
+                st["N_GLOBAL_SUBS"] += (p["substitution_n"] + p["substitutions_outside_window"]) * c
+                st["N_SUBS_OUTSIDE_WINDOW"] += p["substitutions_outside_window"] * c
+                st["N_MODS_IN_WINDOW"] += p["mods_in_window"] * c
+                st["N_MODS_OUTSIDE_WINDOW"] += p["mods_outside_window"] * c
+                if p["irregular_ends"]:
+                    st["N_READS_IRREGULAR_ENDS"] += c
+            k += 1
+    assert k == len(uniques)
+    for seq in not_aligned:
+        del variantCache[seq]
+    block = engine.counts(raw=merged)
+    for key, val in block.aln_stats_partial().items():
+        if val != st[key]:
+            raise EngineError("device aln_stats disagree with per-read records for %s: %d != %d" % (key, val, st[key]))
+    block.class_extra = class_extra
+    _blocks[id(variantCache)] = block
+    return st, not_aligned
+
+
 def quantify(variantCache):
     """Count block accumulated on the device by the process_fastq call that filled this variantCache."""
     return _blocks[id(variantCache)]

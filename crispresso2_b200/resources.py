@@ -36,6 +36,13 @@ class ResultsSlotsDict:
     def __dict__(self):
         return {k: getattr(self, k) for k in self.__slots__ if hasattr(self, k)}
 
+    def __reduce__(self):                      # picklable (ranks exchange payloads in core.process_fastq_sharded)
+        return (_rebuild_slots, (self.__dict__,))
+
+
+def _rebuild_slots(state):
+    return ResultsSlotsDict(**state)
+
 
 def ref_positions_from(aln_ref):
     """ref_positions list (COREResources.pyx:109-133) from the aligned reference string."""

@@ -7,6 +7,8 @@ import sys
 
 import numpy as np
 
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -47,3 +49,34 @@ def test_two_ranks_gloo_merge_matches_oracle(tmp_path):
         assert got["vectors"][name] == vec["Reference"][name].tolist(), name
     for name in O.SCALAR_NAMES:
         assert got["scalars"][name] == sca["Reference"][name], name
+
+
+def test_process_fastq_sharded_over_two_ranks_equals_single_process(tmp_path):
+    """The drop-in process_fastq with unique reads sharded over 2 ranks (gloo; count block all-reduced, variants gathered):
+    every rank must hold what the reference's serial loop produces -- checked on the HDR golden fixture."""
+    import golden_util as G
+    import parity_util as PU
+    rec = G.load("synth_hdr")
+    fq = tmp_path / "hdr.fastq"
+    with open(fq, "w") as fh:
+        for k, s in enumerate(rec["reads"]):
+            fh.write("@r%d\n%s\n+\n%s\n" % (k, s, "I" * len(s)))
+    out = tmp_path / "sharded.json"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "tests", "dist_worker2.py"), str(fq), str(out)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = json.load(open(out))
+    assert got["stats"] == rec["aln_stats"]
+    assert got["keys"] == list(rec["variants"].keys())
+    assert got["lost"] == sorted(rec["not_aligned"])
+    assert got["classes"] == {s: v["class_name"] for s, v in rec["variants"].items()}
+    assert got["payload_ok"]
+    refs = G.refs_from(rec)
+    for rname in rec["ref_names"]:
+        seq = refs[rname]["sequence"]
+        V = {k: np.asarray(v) for k, v in got["vec"][rname].items()}
+        tot = int(V["all_base_count_A"][0] + V["all_base_count_C"][0] + V["all_base_count_G"][0] + V["all_base_count_T"][0]
+                  + V["all_base_count_N"][0] + V["all_base_count_-"][0])
+        assert G.mod_count_text(seq, V, tot) == G.file_for(rec, rname, "Modification_count_vectors.txt")
