@@ -302,3 +302,122 @@ const int64_t *c2b_fastq_first_index(const c2b_fastq *f) { return f ? f->first_i
 void c2b_fastq_free(c2b_fastq *f) { delete f; }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ quality filter
+// Replaces: filterFastqs.filterFastqs for single-end input (reference: CRISPResso2/filterFastqs.py:29-229, called at
+// CRISPRessoCORE.py:3716-3717).  Binary-mode semantics of the reference: lines end at '\n' only, every line is
+// rstrip()ped of ASCII whitespace, processing stops at the first record whose id line is empty; quality = byte - 33 in
+// uint8 arithmetic (wraps below 33); a record is kept iff min(q) >= min_bp_qual_in_read (when set) and
+// mean(q) >= min_av_read_qual (when set; exact integer test sum >= thr * n); with min_bp_qual_or_N set, bases with
+// q < thr become 'N'.  Output: id, sequence, plus line, quality, each followed by '\n'; a ".gz" output is written as
+// one gzip member per worker thread (a valid multi-member gzip file).
+namespace {
+
+inline bool is_bspace(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }     // bytes.rstrip()
+
+struct Line { const uint8_t *p; uint32_t len; };
+
+bool gz_member(const std::string &in, std::string &out)
+{
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (deflateInit2(&zs, 6, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    out.resize(deflateBound(&zs, (uLong)in.size()) + 64);
+    zs.next_in = (Bytef *)in.data(); zs.avail_in = (uInt)in.size();
+    zs.next_out = (Bytef *)&out[0]; zs.avail_out = (uInt)out.size();
+    const int rc = deflate(&zs, Z_FINISH);
+    const size_t n = zs.total_out;
+    deflateEnd(&zs);
+    if (rc != Z_STREAM_END) return false;
+    out.resize(n);
+    return true;
+}
+
+}  // namespace
+
+extern "C" int c2b_fastq_filter(const char *path_in, const char *path_out, int32_t min_bp_qual_in_read, int32_t min_av_read_qual,
+                                int32_t min_bp_qual_or_N, int32_t n_threads, int64_t *n_in, int64_t *n_out)
+{
+    if (!path_in || !path_out) return C2B_E_ARG;
+    std::vector<uint8_t> buf;
+    std::string err;
+    const size_t Li = strlen(path_in), Lo = strlen(path_out);
+    const bool gz_in = Li > 3 && strcmp(path_in + Li - 3, ".gz") == 0, gz_out = Lo > 3 && strcmp(path_out + Lo - 3, ".gz") == 0;
+    if (!(gz_in ? read_gz(path_in, buf, err) : read_plain(path_in, buf, err))) { g_fastq_err = "c2b_fastq_filter: " + err; return C2B_E_ARG; }
+    const uint8_t *data = buf.data();
+    const size_t n = buf.size();
+    // lines (split at '\n' only), right-stripped
+    std::vector<Line> lines;
+    lines.reserve(n / 60 + 16);
+    for (size_t p = 0; p < n;) {
+        const uint8_t *nl = (const uint8_t *)memchr(data + p, '\n', n - p);
+        size_t e = nl ? (size_t)(nl - data) : n;
+        size_t q = e;
+        while (q > p && is_bspace(data[q - 1])) q--;
+        lines.push_back({data + p, (uint32_t)(q - p)});
+        p = nl ? e + 1 : n;
+    }
+    // records up to the first empty id line
+    int64_t n_rec = 0;
+    while ((size_t)(4 * n_rec) < lines.size() && lines[(size_t)(4 * n_rec)].len > 0) n_rec++;
+    auto line_or_empty = [&](size_t k) -> Line { return k < lines.size() ? lines[k] : Line{data, 0}; };
+    int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    T = std::max(1, std::min(T, 64));
+    if (n_rec < 4096) T = 1;
+    std::vector<std::string> outs(T);
+    std::vector<int64_t> kept(T, 0);
+    std::vector<int> fail_code(T, 0);
+    auto work = [&](int t) {
+        const int64_t a = n_rec * t / T, b = n_rec * (t + 1) / T;
+        std::string &o = outs[t];
+        o.reserve((size_t)(b - a) * 560);
+        std::string masked;
+        for (int64_t r = a; r < b; r++) {
+            const Line id = lines[(size_t)(4 * r)], sq = line_or_empty((size_t)(4 * r + 1)), pl = line_or_empty((size_t)(4 * r + 2)),
+                       ql = line_or_empty((size_t)(4 * r + 3));
+            if (min_bp_qual_in_read) {
+                if (ql.len == 0) { fail_code[t] = 1; return; }            // numpy.min of an empty array raises in the reference
+                uint8_t mn = 255;
+                for (uint32_t k = 0; k < ql.len; k++) mn = std::min<uint8_t>(mn, (uint8_t)(ql.p[k] - 33));
+                if ((int)mn < min_bp_qual_in_read) continue;
+            }
+            if (min_av_read_qual) {
+                if (ql.len == 0) continue;                                 // mean of nothing is nan: the comparison fails
+                uint64_t sum = 0;
+                for (uint32_t k = 0; k < ql.len; k++) sum += (uint8_t)(ql.p[k] - 33);
+                if ((int64_t)sum < (int64_t)min_av_read_qual * (int64_t)ql.len) continue;
+            }
+            o.append((const char *)id.p, id.len); o.push_back('\n');
+            if (min_bp_qual_or_N) {
+                if (sq.len != ql.len) { fail_code[t] = 2; return; }       // boolean index of another length: IndexError in the reference
+                masked.assign((const char *)sq.p, sq.len);
+                for (uint32_t k = 0; k < ql.len; k++) if ((int)(uint8_t)(ql.p[k] - 33) < min_bp_qual_or_N) masked[k] = 'N';
+                o.append(masked);
+            } else o.append((const char *)sq.p, sq.len);
+            o.push_back('\n');
+            o.append((const char *)pl.p, pl.len); o.push_back('\n');
+            o.append((const char *)ql.p, ql.len); o.push_back('\n');
+            kept[t]++;
+        }
+        if (gz_out) { std::string z; if (!gz_member(o, z)) { fail_code[t] = 3; return; } o.swap(z); }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+    }
+    for (int t = 0; t < T; t++) if (fail_code[t]) {
+        g_fastq_err = fail_code[t] == 1 ? "c2b_fastq_filter: empty quality line" : fail_code[t] == 2 ? "c2b_fastq_filter: sequence and quality lengths differ" : "c2b_fastq_filter: deflate failed";
+        return fail_code[t] == 3 ? C2B_E_STATE : (fail_code[t] == 1 ? C2B_E_LIMIT : C2B_E_ARG);
+    }
+    FILE *f = fopen(path_out, "wb");
+    if (!f) { g_fastq_err = std::string("c2b_fastq_filter: cannot write ") + path_out; return C2B_E_ARG; }
+    int64_t tot = 0;
+    for (int t = 0; t < T; t++) { if (!outs[t].empty()) fwrite(outs[t].data(), 1, outs[t].size(), f); tot += kept[t]; }
+    if (gz_out && n_rec == 0) { std::string z, e2; gz_member(e2, z); fwrite(z.data(), 1, z.size(), f); }   // an empty but valid gzip file
+    fclose(f);
+    if (n_in) *n_in = n_rec;
+    if (n_out) *n_out = tot;
+    return C2B_OK;
+}

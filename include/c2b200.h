@@ -278,6 +278,14 @@ const int64_t *c2b_fastq_first_index(const c2b_fastq *f); /* record index of eac
 void c2b_fastq_free(c2b_fastq *f);
 const char *c2b_fastq_last_error(void);
 
+/* replaces: filterFastqs.filterFastqs for single-end input (CRISPResso2/filterFastqs.py:29-229, called at
+ * CRISPRessoCORE.py:3716-3717): keep a record iff min(q) >= min_bp_qual_in_read and mean(q) >= min_av_read_qual (each when
+ * non-zero), mask bases with q < min_bp_qual_or_N as 'N'; q = byte - 33 (uint8).  Same record/line rules as the reference's
+ * binary-mode reader; ".gz" in/out handled.  Returns C2B_E_LIMIT for an empty quality line under the min filter (ValueError in
+ * the reference) and C2B_E_ARG for a sequence/quality length mismatch under masking (IndexError in the reference).          */
+int  c2b_fastq_filter(const char *path_in, const char *path_out, int32_t min_bp_qual_in_read, int32_t min_av_read_qual,
+                      int32_t min_bp_qual_or_N, int32_t n_threads, int64_t *n_in, int64_t *n_out);
+
 /* pinned host memory (cudaHostAlloc) for callers that want full-speed host<->device copies */
 void *c2b_host_alloc(size_t n_bytes);
 void  c2b_host_free(void *p);

@@ -45,6 +45,11 @@ def main():
             return out
 
         CORE.process_fastq = process_fastq
+        # quality filtering before the path (CRISPRessoCORE.py:3716-3717 imports the module and calls filterFastqs): native too
+        import functools
+        from CRISPResso2 import filterFastqs as FF
+        from crispresso2_b200 import filter_fastqs
+        FF.filterFastqs = functools.partial(filter_fastqs.filterFastqs, lib_path=None if lib == "default" else lib)
         orig_ctx = CORE.CorePlotContext
 
         def ctx_spy(*a, **kw):
