@@ -14,7 +14,10 @@ What is restated here (reference file:line, all under /root/reference):
   new_variant                    CRISPResso2/CRISPRessoCORE.py:627-798  (get_new_variant_object, minus the
                                  prime-editing scaffold branch :789-796 and the legacy insertion switch)
   process_reads                  CRISPResso2/CRISPRessoCORE.py:1956-2000 (serial branch of process_fastq)
-  count_vectors                  CRISPResso2/CRISPRessoCORE.py:3964-4081, 4183-4192 (no --coding_seq logic)
+  count_vectors                  CRISPResso2/CRISPRessoCORE.py:3964-4181 (vectors, counters, the size Counters and the
+                                 --coding_seq frameshift / splicing block), pinned against the reference's own
+                                 CorePlotContext arguments by tests/test_cli_dropin.py
+  ref1_vectors                   CRISPResso2/CRISPRessoCORE.py:4195-4272 (HDR re-projection)
 """
 import ctypes as C
 import os
