@@ -106,9 +106,9 @@ class _BatchLists:
 
     def __init__(self, res):
         self.res = res
-        self.raw = res.strings.tobytes() if res.strings is not None else None
         self.W, self.nref = res.W, res.alns.shape[1]
         self.lo = self.hi = 0
+        self.text = None
 
     def block(self, i):
         if not (self.lo <= i < self.hi):
@@ -118,13 +118,13 @@ class _BatchLists:
             self.recs = r.recs[self.lo:self.hi].tolist()     # (winner_mask, best_score_milli, best_ref, n_winners, ambiguous, status)
             self.alns = r.alns[self.lo:self.hi].tolist()     # [read][ref] -> ALN_DTYPE field order
             self.edits = r.edits[self.lo:self.hi].tolist() if r.edits is not None else None
+            # one decode per block; bytes left of an alignment are undefined, hence latin-1 (never fails, 1 char per byte)
+            self.text = r.strings[self.lo:self.hi].tobytes().decode("latin-1") if r.strings is not None else None
         return i - self.lo
 
     def pair(self, i, r, n):
-        base = ((i * self.nref + r) * 2) * self.W
-        a = self.raw[base + self.W - n: base + self.W].decode()
-        b = self.raw[base + 2 * self.W - n: base + 2 * self.W].decode()
-        return a, b
+        base = (((i - self.lo) * self.nref + r) * 2) * self.W
+        return self.text[base + self.W - n: base + self.W], self.text[base + 2 * self.W - n: base + 2 * self.W]
 
 
 # ALN_DTYPE field positions (crispresso2_b200/_lib.py)

@@ -53,10 +53,23 @@ def ref_positions_from(aln_ref):
 
 
 def ref_positions_fast(aln_ref):
-    """Same list as ref_positions_from; plain range when the aligned reference holds no gap (the common case)."""
-    if "-" not in aln_ref:
+    """Same list as ref_positions_from, built from the gap runs of the aligned reference (usually none or one): ranges for
+    the stretches of reference bases, -idx (or -1 before the first base) repeated over each run (COREResources.pyx:109-133)."""
+    k = aln_ref.find("-")
+    if k < 0:
         return list(range(len(aln_ref)))
-    return ref_positions_from(aln_ref)
+    out, idx, pos, n = [], 0, 0, len(aln_ref)
+    while k >= 0:
+        out.extend(range(idx, idx + k - pos))
+        idx += k - pos
+        e = k
+        while e < n and aln_ref[e] == "-":
+            e += 1
+        out.extend([-idx if idx else -1] * (e - k))
+        pos = e
+        k = aln_ref.find("-", e)
+    out.extend(range(idx, idx + n - pos))
+    return out
 
 
 def payload_from_lists(insertion_n, deletion_n, substitution_n, edits, aln_ref):
