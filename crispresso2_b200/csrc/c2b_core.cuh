@@ -46,7 +46,8 @@ C2B_DEV void grp_sync(int g)
     // be inlined at every one of the dozen phase barriers
     const int w = (int)(threadIdx.x >> 5), n = g > 0 ? g : -g, sh = 31 - __clz(n);
     const int set = g > 0 ? (w >> sh) : (w & (((int)(blockDim.x >> 5) >> sh) - 1));
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + set), "r"(32 << sh) : "memory");
+    // barrier.sync without .aligned (bar.sync is the aligned form): a warp may arrive not fully converged
+    asm volatile("barrier.sync %0, %1;" ::"r"(1 + set), "r"(32 << sh) : "memory");
 }
 C2B_DEV int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 C2B_DEV int addmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }   // max(a+b, c)
