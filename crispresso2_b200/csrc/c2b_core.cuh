@@ -40,7 +40,12 @@ C2B_DEV uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 C2B_DEV void sync() { __syncwarp(); }
 // barrier among the g warps of this warp's phase set: named barrier 1 + set index.  g > 0: sets of g consecutive warps;
 // g < 0: |g| warps strided by the number of sets (warps w, w + nsets, ...: with four sets, the warps of one sub-partition)
-C2B_DEV void grp_sync(int g)
+#ifdef C2B_X_INLINE_BARRIER
+C2B_DEV
+#else
+__device__ __noinline__        // ONE barrier instruction in the binary: every warp of a set waits at the same PC whatever path it is on
+#endif
+void grp_sync(int g)
 {
     // |g| and the number of sets are powers of two (checked by the host): shifts, not the integer divisions that used to
     // be inlined at every one of the dozen phase barriers
