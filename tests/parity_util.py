@@ -291,3 +291,55 @@ def check_coding_seq(engine, n_reads=60, seed=9):
     nc = {"WT": dict(wt, contains_coding_seq=False, exon_positions=[], exon_len_mods=[], splicing_positions=[])}
     check_against_oracle(engine, {"WT": wt}, ["WT"], O.Params(), reads[:n_reads], m)
     check_against_oracle(engine, nc, ["WT"], O.Params(), reads[:n_reads], m)
+
+
+def check_random_config(engine, seed):
+    """One random configuration against the oracle: 1-3 amplicons (WT / HDR-like / SNP allele), random guide position, window
+    size and excluded ends, optional coding-sequence masks with exon length changes, 3-70 reads of assorted lengths drawn from
+    the alleles (deletions, insertions, substitutions, N, reverse complements), random ignore / discard / ambiguity / HDR flags."""
+    from crispresso2_b200 import synth
+    m = O.make_matrix()
+    rng = np.random.default_rng(seed)
+    L = int(rng.integers(60, 270))
+    amp = synth.random_amplicon(rng, L)
+    nref = int(rng.integers(1, 4))
+    gs = int(rng.integers(20, max(21, L - 45)))
+    wsize = int(rng.choice([1, 1, 3, 10, 25]))
+    refs, names, seqs = {}, [], []
+    for k in range(nref):
+        s = list(amp)
+        if k == 1:                                   # HDR-like: small substitution + insertion
+            p = gs + 10
+            s[p] = "A" if s[p] != "A" else "C"
+            ins = "".join(rng.choice(list("ACGT"), int(rng.integers(0, 7))))
+            s = s[:p + 2] + list(ins) + s[p + 2:]
+        elif k == 2:                                 # a few SNPs
+            for p in rng.choice(len(s), size=4, replace=False):
+                s[p] = "G" if s[p] != "G" else "T"
+        s = "".join(s)
+        nm = "R%d" % k
+        refs[nm] = synth.amplicon_setup(s, guide_start=min(gs, len(s) - 40), window_size=wsize,
+                                        exclude_left=int(rng.integers(0, 16)), exclude_right=int(rng.integers(0, 16)))
+        if rng.random() < 0.4:
+            ex = sorted(set(rng.integers(0, len(s), size=int(rng.integers(5, 60))).tolist()))
+            refs[nm].update(contains_coding_seq=True, exon_positions=ex, splicing_positions=sorted(set(rng.integers(0, len(s), size=6).tolist())),
+                            exon_len_mods=[int(rng.choice([0, 0, 0, 2, -3]))])
+        names.append(nm); seqs.append(s)
+    reads = []
+    nreads = int(rng.integers(3, 70))
+    for _ in range(nreads):
+        k = int(rng.integers(0, nref))
+        s = seqs[k]
+        rl = int(rng.choice([len(s), len(s), len(amp), int(rng.integers(30, 300))]))
+        r = synth.synth_reads(rng, s, 1, rl, sub_rate=float(rng.choice([0.0, 0.01, 0.05])), del_frac=0.3, ins_frac=0.2,
+                              rc_frac=float(rng.choice([0.0, 0.3])), n_rate=float(rng.choice([0.0, 0.01])), cut=refs[names[k]]["cut_point"])[0].tobytes().decode()
+        reads.append(r)
+    kw = {}
+    for f in ("ignore_substitutions", "ignore_insertions", "ignore_deletions", "discard_indel_reads"):
+        if rng.random() < 0.2: kw[f] = True
+    if nref > 1:
+        u = rng.random()
+        if u < 0.3: kw["expand_ambiguous_alignments"] = True
+        elif u < 0.5: kw["assign_ambiguous_alignments_to_first_reference"] = True
+        if rng.random() < 0.6: kw["expected_hdr_amplicon_seq"] = seqs[1]
+    check_against_oracle(engine, refs, names, O.Params(**kw), reads, m)

@@ -198,3 +198,8 @@ def test_small_odd_batches_keep_the_warp_convergent(emu):
         for k in range(0, n, 3):
             reads[k] = reads[k][: 40 + 13 * k]
         PU.check_against_oracle(emu, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
+
+
+def test_random_configurations_against_oracle(emu):
+    for seed in range(20):
+        PU.check_random_config(emu, seed)

@@ -274,3 +274,8 @@ def test_streamed_launch_equals_chunked_launches(eng, monkeypatch, mixed):
     ne = a.alns[:, 0]["n_edits"].astype(np.int64)
     slot = np.arange(a.edits.shape[2])[None, :] < np.minimum(ne, a.edits.shape[2])[:, None]
     assert (a.edits[:, 0][slot] == b.edits[:, 0][slot]).all()
+
+
+def test_random_configurations_against_oracle(eng):
+    for seed in range(100, 160):
+        PU.check_random_config(eng, seed)
