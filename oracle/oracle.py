@@ -212,6 +212,60 @@ def find_indels_substitutions(read_al, ref_al, include_idx):
     }
 
 
+def find_indels_substitutions_legacy(read_al, ref_al, include_idx):
+    """Restatement of COREResources.pyx:190-315 (`--use_legacy_insertion_quantification`), kept for the next round: the device path
+    does not build it yet.  Differences from the current function: a window insertion needs only ONE flank in the window
+    (:284); deletion coordinates come from alignment columns with two end rules -- a run starting in column 0 or 1 is reported
+    from reference position 0 (:252-254), a run reaching the last column ends at the last reference index, not one past it
+    (:255-257); sizes are column counts; deletion_n / insertion_n are numpy sums (0.0 for an empty list)."""
+    import re
+    ref_positions, all_sub_pos, sub_pos, all_sub_val, sub_val = [], [], [], [], []
+    inc = set(int(v) for v in include_idx)
+    idx = 0
+    for k, c in enumerate(ref_al):
+        if c in "ATCGN":
+            ref_positions.append(idx)
+            if ref_al[k] != read_al[k] and read_al[k] != "-" and read_al[k] != "N":
+                all_sub_pos.append(idx)
+                all_sub_val.append(read_al[k])
+                if idx in inc:
+                    sub_pos.append(idx)
+                    sub_val.append(read_al[k])
+            idx += 1
+        else:
+            ref_positions.append(-1 if idx == 0 else -idx)
+    all_del_pos, del_pos, del_coords, all_del_coords, del_sizes = [], [], [], [], []
+    all_ins_pos, all_ins_left, ins_pos, ins_coords, ins_sizes = [], [], [], [], []
+    for mt in re.finditer("-+", read_al):
+        st, en = mt.span()
+        ref_st = ref_positions[st] if st - 1 > 0 else 0
+        ref_en = ref_positions[en] if en < len(ref_positions) else idx - 1
+        all_del_pos.extend(range(ref_st, ref_en))
+        all_del_coords.append((ref_st, ref_en))
+        if inc.intersection(range(ref_st, ref_en)):
+            del_pos.extend(range(ref_st, ref_en))
+            del_coords.append((ref_st, ref_en))
+            del_sizes.append(en - st)
+    for mt in re.finditer("-+", ref_al):
+        st, en = mt.span()
+        if st == 0 or en == len(ref_al):
+            continue
+        ref_st, ref_en = ref_positions[st - 1], ref_positions[en]
+        all_ins_left.append(ref_st)
+        all_ins_pos.extend([ref_st, ref_en])
+        if ref_st in inc or ref_en in inc:
+            ins_coords.append((ref_st, ref_en))
+            ins_pos.extend([ref_st, ref_en])
+            ins_sizes.append(en - st)
+    return {"all_insertion_positions": all_ins_pos, "all_insertion_left_positions": all_ins_left,
+            "insertion_positions": ins_pos, "insertion_coordinates": ins_coords, "insertion_sizes": ins_sizes,
+            "insertion_n": np.sum(ins_sizes), "all_deletion_positions": all_del_pos, "deletion_positions": del_pos,
+            "deletion_coordinates": del_coords, "all_deletion_coordinates": all_del_coords, "deletion_sizes": del_sizes,
+            "deletion_n": np.sum(del_sizes), "all_substitution_positions": all_sub_pos, "substitution_positions": sub_pos,
+            "all_substitution_values": np.array(all_sub_val), "substitution_values": np.array(sub_val),
+            "substitution_n": len(sub_pos), "ref_positions": ref_positions}
+
+
 # --------------------------------------------------------------------------- per-read logic
 
 class Params:

@@ -124,3 +124,46 @@ def test_live_fuzz_against_compiled_reference(ednafull):
         w = R.find_indels_substitutions(want[0], want[1], inc).__dict__
         g = O.find_indels_substitutions(want[0], want[1], inc)
         assert not G.payload_equal({k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in w.items()}, g)
+
+
+def test_legacy_classification_restatement_against_compiled_reference():
+    """oracle.find_indels_substitutions_legacy (checker for a future device path) == the reference's compiled function on real
+    alignments (random reads aligned by the reference's own global_align)."""
+    mods = O.ref_modules()
+    if mods is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    A, R = mods
+    import random
+    rng = random.Random(5)
+    m = A.make_matrix()
+    n = 0
+    for _ in range(400):
+        I = rng.choice([20, 41, 80, 150])
+        ref = "".join(rng.choice("ACGT") for _ in range(I))
+        read = list(ref)
+        for _k in range(rng.randrange(0, 4)):
+            p = rng.randrange(len(read))
+            u = rng.random()
+            if u < 0.4:
+                del read[p:p + rng.randrange(1, 9)]
+            elif u < 0.7:
+                read[p:p] = [rng.choice("ACGT") for _q in range(rng.randrange(1, 7))]
+            else:
+                read[p] = rng.choice("ACGTN")
+        read = "".join(read)
+        if len(read) < 3:
+            continue
+        gi = np.zeros(I + 1, dtype=np.int64)
+        gi[rng.randrange(I + 1)] = 1
+        s1, s2, _ = A.global_align(read, ref, matrix=m, gap_incentive=gi, gap_open=-20, gap_extend=-2)
+        inc = sorted(rng.sample(range(I), rng.randrange(0, min(I, 10))))
+        want = R.find_indels_substitutions_legacy(s1, s2, inc)
+        got = O.find_indels_substitutions_legacy(s1, s2, inc)
+        for k, v in want.items():
+            g = got[k]
+            if isinstance(v, np.ndarray):
+                assert list(v) == list(g), (k, s1, s2)
+            else:
+                assert v == g and type(v) is type(g), (k, v, g, s1, s2)
+        n += 1
+    assert n > 300
