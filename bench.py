@@ -339,7 +339,9 @@ def main():
                        "edit_cap": args.edit_cap, "aligned_fraction": aligned_frac,
                        "packed_pair_items": pair_items, "single_items": single_items, "band_reruns": eng.band_reruns(), "ring_pairs": eng.ring_counts()[0], "ring_fallbacks": eng.ring_counts()[1], "parity_gate": bool(gate_ok and e2e_gate)},
             "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "pipeline": ("launch per chunk" if os.environ.get("C2B_STREAMED") == "0" else
+                                 "one persistent launch per batch, read bytes streamed in behind it (c2b_align_batch)")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
