@@ -92,3 +92,50 @@ def write_fastq(path, reads):
         for k, r in enumerate(reads):
             s = r.tobytes().decode() if not isinstance(r, str) else r
             fh.write("@r%d\n%s\n+\n%s\n" % (k, s, "I" * len(s)))
+
+
+# ------------------------------------------------------------------------------------------ BASELINE.json configs[2..4]
+def hdr_workload(arng, rng, n_reads):
+    """configs[2]: WT + HDR (WT with a 3-bp substitution + 6-bp insertion near the cut) + a third allele with
+    5 SNPs; reads drawn 60/30/10 %.  -> (refs, ref_names, uint8 [n_reads, 250])"""
+    amp = random_amplicon(arng, 250)
+    hdr = amp[:120] + "TGA" + amp[123:127] + "ACGTAC" + amp[127:]
+    snp = list(amp)
+    for p in (30, 80, 140, 190, 230):
+        snp[p] = "A" if snp[p] != "A" else "C"
+    snp = "".join(snp)
+    refs = {"WT": amplicon_setup(amp), "HDR": amplicon_setup(hdr), "SNP": amplicon_setup(snp)}
+    parts = [synth_reads_fast(rng, a, int(n_reads * f), 250, cut=126) for a, f in ((amp, 0.6), (hdr, 0.3), (snp, 0.1))]
+    reads = np.concatenate(parts)
+    if len(reads) < n_reads:
+        reads = np.concatenate([reads, synth_reads_fast(rng, amp, n_reads - len(reads), 250, cut=126)])
+    return refs, ["WT", "HDR", "SNP"], reads[rng.permutation(n_reads)]
+
+
+def pooled_workload(arng, rng, n_reads, n_amplicons=96):
+    """configs[3]: n_amplicons independent random amplicons (length U[180,280]), reads of 250 bp carrying the index of their
+    amplicon (post-demultiplex Pooled).  -> (refs, ref_names, packed uint8, int64 offsets, int32 ref_id)"""
+    refs, names, parts, rid = {}, [], [], []
+    per = -(-n_reads // n_amplicons)
+    for k in range(n_amplicons):
+        Lk = int(arng.integers(180, 281))
+        a = random_amplicon(arng, Lk)
+        nm = "amp%d" % k
+        refs[nm] = amplicon_setup(a, guide_start=Lk // 2 - 10)
+        names.append(nm)
+        parts.append(synth_reads_fast(rng, a, per, 250, cut=refs[nm]["cut_point"], n_templates=1024))
+        rid += [k] * per
+    reads = np.concatenate(parts)
+    rid = np.asarray(rid, dtype=np.int32)
+    order = rng.permutation(len(reads))[:n_reads]
+    reads, rid = reads[order], rid[order]
+    return refs, names, reads.reshape(-1), np.arange(n_reads + 1, dtype=np.int64) * 250, np.ascontiguousarray(rid)
+
+
+def mixed_length_reads(rng, amplicon, n_reads, lo=50, hi=300, cut=None):
+    """configs[4]: read lengths U[lo, hi], truncated copies of edited amplicon reads.  -> (packed uint8, int64 offsets)"""
+    base = synth_reads_fast(rng, amplicon, n_reads, hi, cut=cut)
+    lens = rng.integers(lo, hi + 1, size=n_reads)
+    off = np.zeros(n_reads + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    return base[np.arange(hi)[None, :] < lens[:, None]], off

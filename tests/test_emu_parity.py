@@ -203,3 +203,33 @@ def test_small_odd_batches_keep_the_warp_convergent(emu):
 def test_random_configurations_against_oracle(emu):
     for seed in range(20):
         PU.check_random_config(emu, seed)
+
+
+def test_batch_gate_matches_and_catches_corruption(emu):
+    """oracle/batch_gate.py (the >=100k-read gate bench.py and the GPU tests run) on a small emulator batch: a clean batch
+    passes on every field and on the count block; a batch with one flipped output byte / one changed scalar is caught."""
+    from oracle import batch_gate as BG
+    rng = np.random.default_rng(3)
+    amp = synth.random_amplicon(rng, 250)
+    ref = synth.amplicon_setup(amp)
+    refs, names = {"Reference": ref}, ["Reference"]
+    reads = synth.synth_reads(rng, amp, 96, 250, sub_rate=0.01, rc_frac=0.1, n_rate=0.002, cut=ref["cut_point"])
+    emu.configure(refs, names, O.make_matrix(), -20, -2, 5, 2, 0, "ACGTN", 64)
+    emu.counts_reset()
+    off = np.arange(len(reads) + 1, dtype=np.int64) * 250
+    res = emu.align_packed(reads.reshape(-1), off)
+    summ, quant = BG.run(reads.reshape(-1), off, refs, names, O.Params(), O.make_matrix(), res.recs, res.alns, res.strings,
+                         res.edits, res.W, n_workers=2)
+    assert summ["n"] == 96 and summ["n_bad"] == 0, summ
+    assert BG.compare_block(emu.counts(), quant[None], names) == []
+    k = int(np.nonzero(res.recs["best_score_milli"] > 0)[0][5])
+    s2 = res.strings.copy()
+    s2[k, 0, 0, res.W - 3] = ord("A") if s2[k, 0, 0, res.W - 3] != ord("A") else ord("C")
+    summ2, _ = BG.run(reads.reshape(-1), off, refs, names, O.Params(), O.make_matrix(), res.recs, res.alns, s2, res.edits,
+                      res.W, n_workers=2)
+    assert summ2["n_bad"] == 1
+    a2 = res.alns.copy()
+    a2[k, 0]["substitution_n"] += 1
+    summ3, _ = BG.run(reads.reshape(-1), off, refs, names, O.Params(), O.make_matrix(), res.recs, a2, res.strings, res.edits,
+                      res.W, n_workers=2)
+    assert summ3["n_bad"] == 1

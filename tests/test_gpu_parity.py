@@ -156,6 +156,21 @@ def test_full_size_properties(eng):
     eng.set_edit_cap(8)
     assert (res3.recs["status"] == 0).all() and (res3.alns[:, 0]["n_edits"] > 8).all()
     assert eng.counts().scalar("Reference", "TOTAL") == int(aligned.sum())
+    # (4b) the first 131 072 reads against the oracle, every field of every read + the count block of that sub-batch
+    # (SURVEY.md 8d asks for >= 100k reads per config; oracle/batch_gate.py spreads them over the host cores)
+    from oracle import batch_gate as BG
+    G = 1 << 17
+    eng.set_edit_cap(64)
+    eng.counts_reset()
+    resg = eng.align_packed(reads[:G].reshape(-1), off[:G + 1])
+    summ, quant = BG.run(reads[:G].reshape(-1), off[:G + 1], {"Reference": ref}, ["Reference"], O.Params(), O.make_matrix(),
+                         resg.recs, resg.alns, resg.strings, resg.edits, resg.W)
+    assert summ["n"] == G and summ["n_bad"] == 0, summ
+    assert BG.compare_block(eng.counts(), quant[None], ["Reference"]) == []
+    for f in _lib.ALN_DTYPE.names:                                      # and the 1M-read launch gave the same records
+        if f not in ("n_edits", "status"):
+            assert (resg.alns[:, 0][f] == a[:G][f]).all(), f
+    eng.set_edit_cap(8)
     # (5) batch-composition independence: a shuffled sub-batch reproduces its records bit for bit
     pick = rng.permutation(n)[:50000]
     eng.counts_reset()
