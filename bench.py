@@ -586,7 +586,8 @@ def parity_gate(eng, w, args, recs, alns, d_str, d_ed, W, R, dev):
         if f in ("n_edits", "status"):
             continue
         same = same and bool((ta[f] == ga[f]).all())
-    same = same and bool(((ta["status"] & ~_lib.ST_EDIT_OVERFLOW) == (ga["status"] & ~_lib.ST_EDIT_OVERFLOW)).all())
+    keep = np.uint8(0xff ^ _lib.ST_EDIT_OVERFLOW)
+    same = same and bool(((ta["status"] & keep) == (ga["status"] & keep)).all())
     for f in ("winner_mask", "best_score_milli", "best_ref", "n_winners", "ambiguous"):
         same = same and bool((recs[:G][f] == res.recs[f]).all())
     cols = np.arange(W)[None, None, None, :] >= (W - ga["aln_len"].astype(np.int64))[:, :, None, None]

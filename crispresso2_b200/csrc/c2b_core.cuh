@@ -83,6 +83,8 @@ C2B_DEV uint32_t adds(uint32_t *p, uint32_t v)
 { uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory"); return o; }
 C2B_DEV unsigned long long fetch_work(unsigned long long *p)
 { unsigned long long o; asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(o) : "l"(__cvta_generic_to_global(p)), "l"(1ull) : "memory"); return o; }
+C2B_DEV unsigned long long fetch_add(unsigned long long *p, unsigned long long v)
+{ unsigned long long o; asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(o) : "l"(__cvta_generic_to_global(p)), "l"(v) : "memory"); return o; }
 }  // namespace wp
 
 #else
@@ -141,14 +143,15 @@ struct KParams {
     int32_t *bnd; int64_t bnd_words_per_warp;                 // 2 x 3 x (maxJ+1): row-block boundary rows
     uint64_t *opsbuf;                                         // [warp][n_refs][32] op streams (multi-reference)
     uint64_t *rgops;                                          // [warp][RG_MAX_REFS][4 pairs][RG_OPS_STRIDE]: walked op streams of the multi-reference ring path
-    unsigned long long *work_counter;      // [0] work hand-out counter, [1] widest alignment of this launch
-    unsigned long long *stats;             // cumulative path statistics (c2b_path_counts), indices 2..6; [7]: streaming wait timed out
-    // streamed launch (c2b_align_batch): ONE persistent launch covers the whole host batch while its read bytes are still
-    // arriving chunk by chunk; nullptr = everything is resident at launch
-    const unsigned long long *avail;       // number of work groups whose read bytes are resident (grows; written by H2D copies)
-    const unsigned long long *chunk_end;   // [n_chunks] end group (exclusive) of every chunk
-    unsigned long long *chunk_done;        // [n_chunks] groups completed; [n_chunks + c]: widest alignment of chunk c
-    int32_t n_chunks;
+    unsigned long long *work_counter;      // work hand-out counter of this launch
+    unsigned long long *widest;            // widest alignment of this batch (all kernels of the launch sequence)
+    // two-kernel form (c2b_split.cuh): op streams and their meta word per (read, reference) slot, written by the ALIGN kernel
+    // (and by the general kernel for the pairs it aligns), read by the CLASSIFY kernel and copied out as the compact output
+    uint64_t *gops; uint32_t *gmeta; int32_t NW;            // NW = W / 32 words of 32 ops per slot
+    int32_t *left; unsigned long long *left_n;              // ALIGN kernel: pairs left over for the general kernel, and their count
+    const unsigned long long *n_dev;                        // general kernel over the left-over list: *n_dev reads (entries of pair_order)
+    int32_t discard_slab;                                   // ALIGN kernel: drop the dead slab lines from L2 instead of writing them back
+    unsigned long long *stats;             // cumulative path statistics (c2b_path_counts), indices 2..6
     int32_t vstride, hstride;
     const uint32_t *stage_src;        // = refs[0].prof2 (global source of the staged tile)
     int32_t stage_bytes;              // bytes of refs[0].prof2 staged into shared memory by TMA at kernel start (0: none)
@@ -161,6 +164,8 @@ struct KParams {
 
 // output slot of (read, reference): [read][ref] -- or [read][0] when every read carries its single reference (ref_id)
 C2B_DEV int64_t oslot(const KParams &P, int64_t rd, int r) { return rd * P.out_refs + (P.ref_id ? 0 : r); }
+// number of reads of this launch: a host constant, or (general kernel over the ALIGN kernel's left-over list) a device value
+C2B_DEV int64_t nreads(const KParams &P) { return P.n_dev ? (int64_t)*P.n_dev : P.n_reads; }
 
 // (A copy of the single reference's descriptor inside the kernel parameters was tried: no gain, 25.85 against 25.55 ms.)
 C2B_DEV const RefDev &refdev(const KParams &P, int r) { return P.refs[r]; }
@@ -1063,7 +1068,11 @@ C2B_DEV void process_read(const KParams &P, WarpSmem &S, int64_t rd, int warp_sl
                 a.score_milli = score_milli(co.n_match, wk.n);
                 a.irregular_ends = (uint8_t)co.irregular;
                 if (multi) opsbuf[r * 32 + lane] = wk.ops;
-                if (lane == 0) wp::maxg(P.work_counter + 1, (unsigned long long)wk.n);   // widest alignment of the launch
+                if (P.gops && !P.forced_ops) {
+                    if (lane < P.NW) P.gops[oslot(P, rd, r) * P.NW + lane] = wk.ops;
+                    if (lane == 0) P.gmeta[oslot(P, rd, r)] = (uint32_t)wk.n | ((uint32_t)use_rc << 16) | (2u << 24);
+                }
+                if (lane == 0) wp::maxg(P.widest, (unsigned long long)wk.n);   // widest alignment of the launch
                 keep_irr = co.irregular;
                 note_score(rec, R, r, a.score_milli);
             }
@@ -1417,9 +1426,13 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
             a.irregular_ends = (uint8_t)co.irregular;
             keep_irr = co.irregular;
             note_score(rec, R, r, a.score_milli);
-            if (hl == 0) wp::maxg(P.work_counter + 1, (unsigned long long)bn);
+            if (hl == 0) wp::maxg(P.widest, (unsigned long long)bn);
         }
         if (multi) opsbuf[r * 32 + lane] = bops;
+        if (P.gops && !a.status && (h == 0 || rdB != rdA)) {
+            if (hl < P.NW) P.gops[oslot(P, myrd, r) * P.NW + hl] = bops;
+            if (hl == 0) P.gmeta[oslot(P, myrd, r)] = (uint32_t)bn | ((uint32_t)bstrand << 16) | (2u << 24);
+        }
         rec.status |= a.status;
         if (hl == 0 && (h == 0 || rdB != rdA)) P.alns[oslot(P, myrd, r)] = a;
     }
@@ -1453,7 +1466,7 @@ C2B_DEVNOINL void process_pair(const KParams &P, WarpSmem &S, const uint32_t *st
 template <bool ONE>
 C2B_DEV void process_item(const KParams &P, WarpSmem &S, const uint32_t *staged_prof, int64_t w, int warp_slot)
 {
-    const bool haveB = 2 * w + 1 < P.n_reads;
+    const bool haveB = 2 * w + 1 < nreads(P);
     const int64_t rdA = P.pair_order ? P.pair_order[2 * w] : 2 * w;
     const int64_t rdB = haveB ? (P.pair_order ? P.pair_order[2 * w + 1] : 2 * w + 1) : rdA;
     bool pair = !P.forced_ops && !(P.flags & C2B_F_NO_PAIRING);
@@ -1471,7 +1484,7 @@ C2B_DEV void process_item(const KParams &P, WarpSmem &S, const uint32_t *staged_
     if (pair) process_pair<ONE>(P, S, staged_prof, rdA, rdB, warp_slot, nullptr, false);
     else {
         process_read<ONE>(P, S, rdA, warp_slot);
-        if (haveB) { wp::sync(); process_read<ONE>(P, S, rdB, warp_slot); }
+        if (haveB && rdB != rdA) { wp::sync(); process_read<ONE>(P, S, rdB, warp_slot); }   // (rdA, rdA): a single read on the left-over list
     }
 }
 
@@ -1666,7 +1679,7 @@ C2B_DEV void process_group(const KParams &P, WarpSmem &S, QuadSmem &Q, const uin
     const int64_t first = 4 * wq;
     const bool multi = !ONE && P.ref_id == nullptr && P.n_refs > 1;
     bool quad = !P.forced_ops && !(P.flags & (C2B_F_NO_PAIRING | C2B_F_NO_RING)) && P.tbq != nullptr &&
-                2 * first + 7 < P.n_reads && (!multi || (P.n_refs <= RG_MAX_REFS && P.rgops != nullptr));
+                2 * first + 7 < nreads(P) && (!multi || (P.n_refs <= RG_MAX_REFS && P.rgops != nullptr));
     if (quad) {
         const int x = lane & 7;
         const int64_t rd = P.pair_order ? P.pair_order[2 * first + x] : 2 * first + x;
@@ -1687,7 +1700,7 @@ C2B_DEV void process_group(const KParams &P, WarpSmem &S, QuadSmem &Q, const uin
     else {
 #pragma unroll 1
         for (int q = 0; q < 4; q++)
-            if (2 * (first + q) < P.n_reads) { process_item<ONE>(P, S, staged_prof, first + q, warp_slot); wp::sync(); }
+            if (2 * (first + q) < nreads(P)) { process_item<ONE>(P, S, staged_prof, first + q, warp_slot); wp::sync(); }
         if (P.phase_sync) {                                 // keep the CTA's barrier count per group the same on every path
 #pragma unroll 1
             for (int b = group_phases(P); b > 0; b--) wp::grp_sync(P.phase_sync);

@@ -5,14 +5,22 @@
 //        -Iinclude -o crispresso2_b200/libc2b200.so crispresso2_b200/csrc/c2b_engine.cu
 // The same file compiles with g++ -DC2B_EMU against tests/emu/warp_emu.h (CPU-only logic tests).
 #include <algorithm>
+#ifndef C2B_EMU
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+#include <cctype>
+#endif
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "c2b_core.cuh"
+#include "c2b_split.cuh"
 
 using namespace c2b;
 
@@ -77,48 +85,51 @@ static void rt_host_free(void *p) { free(p); }
 #define C2B_MIN_CTAS_PER_SM 2
 #endif
 constexpr int WARPS_PER_CTA = C2B_WARPS_PER_CTA;      // launch-bounds maximum; the launch may use fewer (env C2B_WARPS_PER_CTA)
+constexpr int B_WARPS_PER_CTA = 4;                    // CLASSIFY kernel
 
-// ONE: every read has one candidate reference (a single amplicon configured, or Pooled ref_id): the lean instantiation
-// carries none of the several-references code.  The host picks the instantiation per launch.
+// TMA-staged reference tile: the packed substitution profile of reference 0, once per CTA (cp.async.bulk + mbarrier);
+// every DP step then reads it with two 16-byte LDS.  -> shared-memory address of the tile, or nullptr
+__device__ __forceinline__ const uint32_t *stage_profile(const KParams &P, unsigned char *dst)
+{
+    if (P.stage_bytes <= 0) return nullptr;
+    __shared__ __align__(8) unsigned long long mbar;
+    const uint32_t mbar_a = (uint32_t)__cvta_generic_to_shared(&mbar), dst_a = (uint32_t)__cvta_generic_to_shared(dst);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"((uint32_t)P.stage_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst_a), "l"(P.stage_src), "r"((uint32_t)P.stage_bytes), "r"(mbar_a) : "memory");
+    }
+    asm volatile("{\n .reg .pred p;\n C2B_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra C2B_DONE;\n bra C2B_WAIT;\n C2B_DONE:\n}" ::"r"(mbar_a) : "memory");
+    return reinterpret_cast<const uint32_t *>(dst);
+}
+
+// GENERAL kernel: the whole per-read path in one launch (any length within the build limits, any parameters; full-matrix
+// DP paths of c2b_core.cuh).  Since r02 it runs after the ALIGN / CLASSIFY pair, over the pairs ALIGN left over (P.n_dev,
+// P.pair_order = the left-over list), or alone when the two-kernel form does not apply.
+// ONE: every read has one candidate reference (a single amplicon configured, or Pooled ref_id).
 // P is a __grid_constant__: the out-of-line device functions take it by reference, and without the qualifier every launch
-// copied the 330-byte struct to each thread's local memory and read its fields back with LDL (r01k: 27.3 -> 25.7 ms).
-// STREAM: the batch's read bytes arrive while the kernel runs (c2b_align_batch, streamed launch); the resident-batch
-// instantiations keep the plain work loop, without the availability wait and the per-group completion signalling.
-template <bool ONE, bool STREAM>
+// copied the struct to each thread's local memory and read its fields back with LDL (r01k: 27.3 -> 25.7 ms).
+template <bool ONE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_align_classify_kernel(const __grid_constant__ KParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpSmem *S = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
     QuadSmem *Q = reinterpret_cast<QuadSmem *>(smem_raw + (size_t)(blockDim.x >> 5) * sizeof(WarpSmem)) + (threadIdx.x >> 5);
     const int warp_slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    // Reference tile: the packed substitution profile of reference 0 is staged once per CTA into shared memory by the
-    // TMA engine (cp.async.bulk, completion on an mbarrier); every DP step then reads it with two 16-byte LDS.
-    const uint32_t *staged_prof = nullptr;
-    if (P.stage_bytes > 0) {
-        __shared__ __align__(8) unsigned long long mbar;
-        unsigned char *dst = smem_raw + (((size_t)(blockDim.x >> 5) * (sizeof(WarpSmem) + sizeof(QuadSmem)) + 127) & ~(size_t)127);
-        const uint32_t mbar_a = (uint32_t)__cvta_generic_to_shared(&mbar), dst_a = (uint32_t)__cvta_generic_to_shared(dst);
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"((uint32_t)P.stage_bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst_a), "l"(P.stage_src), "r"((uint32_t)P.stage_bytes), "r"(mbar_a) : "memory");
-        }
-        asm volatile("{\n .reg .pred p;\n C2B_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra C2B_DONE;\n bra C2B_WAIT;\n C2B_DONE:\n}" ::"r"(mbar_a) : "memory");
-        staged_prof = reinterpret_cast<const uint32_t *>(dst);
-    }
+    const uint32_t *staged_prof = stage_profile(P, smem_raw + (((size_t)(blockDim.x >> 5) * (sizeof(WarpSmem) + sizeof(QuadSmem)) + 127) & ~(size_t)127));
     // Work groups (8 reads each) are handed out per phase set (g consecutive warps, one group per warp), one hand-out
     // ahead, so that the loop count -- and with it the number of barriers executed by process_group's phases -- is the
     // same for every warp of the set, and the next group's read bytes are on their way to L2 while this one computes.
-    if constexpr (!STREAM) {
     __shared__ unsigned long long next_base[WARPS_PER_CTA];
     const int gs = P.phase_sync, g = gs > 0 ? gs : gs < 0 ? -gs : 1, wib = threadIdx.x >> 5, nsets = (int)(blockDim.x >> 5) / g;
     const int set = gs < 0 ? wib % nsets : wib / g, wis = gs < 0 ? wib / nsets : wib % g;
-    const unsigned long long total = ((unsigned long long)P.n_reads + 7) / 8;
+    const int64_t nrd = nreads(P);
+    const unsigned long long total = ((unsigned long long)nrd + 7) / 8;
     auto hand_out = [&]() -> unsigned long long {
         if (wis == 0 && (threadIdx.x & 31) == 0) next_base[set] = atomicAdd(P.work_counter, (unsigned long long)g);
         if (g > 1) wp::grp_sync(gs); else __syncwarp();
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_a
         const unsigned long long nb = hand_out();
         const unsigned long long wn = nb + wis;
         if (wn < total && !P.pair_order) {
-            const int64_t last = (int64_t)(8 * wn + 8) < P.n_reads ? (int64_t)(8 * wn + 8) : P.n_reads;
+            const int64_t last = (int64_t)(8 * wn + 8) < nrd ? (int64_t)(8 * wn + 8) : nrd;
             const int64_t b0 = P.offsets[8 * wn], b1 = P.offsets[last];
             const int64_t a = b0 + (int64_t)(threadIdx.x & 31) * 128;
             if (a < b1) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.reads + a));
@@ -142,79 +153,45 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_a
         __syncwarp();
         base = nb;
     }
-    } else {
-    __shared__ unsigned long long next_base[2 * WARPS_PER_CTA];   // [set]: next hand-out; [WARPS_PER_CTA + set]: wait timed out
-    const int gs = P.phase_sync, g = gs > 0 ? gs : gs < 0 ? -gs : 1, wib = threadIdx.x >> 5, nsets = (int)(blockDim.x >> 5) / g;
-    const int set = gs < 0 ? wib % nsets : wib / g, wis = gs < 0 ? wib / nsets : wib % g;
-    const unsigned long long total = ((unsigned long long)P.n_reads + 7) / 8;
-    // Streamed launch: before a set starts on work groups base..base+g-1 its leader waits until their read bytes have
-    // arrived (P.avail is advanced by the copy stream after each chunk's H2D).  A wait longer than 20 s is reported in
-    // stats[7] and ends the launch instead of hanging the GPU.
-    auto hand_out = [&](unsigned long long cur) -> unsigned long long {
-        if (wis == 0 && (threadIdx.x & 31) == 0) {
-            unsigned long long nxt = atomicAdd(P.work_counter, (unsigned long long)g);
-            if (P.avail && cur < total) {
-                const unsigned long long need = cur + g < total ? cur + g : total;
-                unsigned long long t0 = 0, have;
-                for (;;) {
-                    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(have) : "l"(P.avail));
-                    if (have >= need) break;
-                    unsigned long long now;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                    if (!t0) t0 = now;
-                    if (now - t0 > 20000000000ull) { atomicExch(P.stats + 7, 1ull); nxt = ~0ull; next_base[WARPS_PER_CTA + set] = 1; break; }
-                    __nanosleep(1000);
-                }
-            }
-            next_base[set] = nxt;
+}
+
+// ALIGN kernel (c2b_split.cuh: align_group): persistent, free-running warps pull work groups of 8 reads from a counter.
+#ifndef C2B_A_MIN_CTAS
+#define C2B_A_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_A_MIN_CTAS) c2b_align_kernel(const __grid_constant__ KParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ASmem *S = reinterpret_cast<ASmem *>(smem_raw) + (threadIdx.x >> 5);
+    const int nw = blockDim.x >> 5;
+    const int warp_slot = blockIdx.x * nw + (threadIdx.x >> 5);
+    const uint32_t *staged_prof = stage_profile(P, smem_raw + (((size_t)nw * sizeof(ASmem) + 127) & ~(size_t)127));
+    const unsigned total = (unsigned)((P.n_reads + 7) / 8);
+    const unsigned ahead = gridDim.x * nw;
+    for (;;) {
+        unsigned w = 0;
+        if ((threadIdx.x & 31) == 0) w = (unsigned)atomicAdd(P.work_counter, 1ull);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= total) break;
+        if (w + ahead < total && !P.pair_order) {           // the group this warp is likely to get next: bytes towards L2
+            const int64_t g = (int64_t)w + ahead;
+            const int64_t last = 8 * g + 8 < P.n_reads ? 8 * g + 8 : P.n_reads;
+            const int64_t a = P.offsets[8 * g] + (int64_t)(threadIdx.x & 31) * 128;
+            if (a < P.offsets[last]) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.reads + a));
         }
-        if (g > 1) wp::grp_sync(gs); else __syncwarp();
-        const unsigned long long b = next_base[set];
-        if (g > 1) wp::grp_sync(gs); else __syncwarp();
-        return b;
-    };
-    if (threadIdx.x < 2 * WARPS_PER_CTA) next_base[threadIdx.x] = 0;
-    __syncthreads();
-    unsigned long long base = hand_out(~0ull);              // nothing to wait for yet
-    int chunk = 0;
-    while (base < total) {
-        const unsigned long long nb = hand_out(base);        // next hand-out; returns once `base` itself is resident
-        if (next_base[WARPS_PER_CTA + set]) break;            // the wait timed out
-        const unsigned long long wn = nb + wis;
-        if (wn < total && !P.pair_order && !P.avail) {
-            const int64_t last = (int64_t)(8 * wn + 8) < P.n_reads ? (int64_t)(8 * wn + 8) : P.n_reads;
-            const int64_t b0 = P.offsets[8 * wn], b1 = P.offsets[last];
-            const int64_t a = b0 + (int64_t)(threadIdx.x & 31) * 128;
-            if (a < b1) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.reads + a));
-        }
-        const unsigned long long w = base + wis;
-        if (w < total) {
-            process_group<ONE>(P, *S, *Q, staged_prof, (int64_t)w, warp_slot);  // reads 8w .. 8w+7
-            if (P.chunk_done) {                              // streamed launch: tell the host that this group's outputs are complete
-                __syncwarp();
-                while (w >= P.chunk_end[chunk]) chunk++;
-                const int lane = threadIdx.x & 31;
-                unsigned long long wmax = 0;
-                if (lane < 8 && 8 * (int64_t)w + lane < P.n_reads) {
-                    const int64_t rd = P.pair_order ? P.pair_order[8 * (int64_t)w + lane] : 8 * (int64_t)w + lane;   // the reads this group aligned
-                    for (int r = 0; r < P.out_refs; r++) {
-                        const unsigned long long v = *reinterpret_cast<const volatile uint16_t *>(&P.alns[rd * P.out_refs + r].aln_len);
-                        wmax = v > wmax ? v : wmax;
-                    }
-                }
-#pragma unroll
-                for (int d = 4; d >= 1; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, wmax, d); wmax = o > wmax ? o : wmax; }
-                if (lane == 0) {
-                    atomicMax(P.chunk_done + P.n_chunks + chunk, wmax);
-                    __threadfence();
-                    atomicAdd(P.chunk_done + chunk, 1ull);
-                }
-            }
-        }
-        else if (P.phase_sync) for (int b = group_phases(P); b > 0; b--) wp::grp_sync(gs);
+        align_group(P, *S, staged_prof, (int64_t)w, warp_slot);
         __syncwarp();
-        base = nb;
     }
+}
+
+// CLASSIFY kernel (c2b_split.cuh: classify_read): one aligned read per warp, reads strided over the grid.
+template <bool ONE>
+__global__ void __launch_bounds__(B_WARPS_PER_CTA * 32) c2b_classify_kernel(const __grid_constant__ KParams P)
+{
+    const int64_t nw = (int64_t)gridDim.x * B_WARPS_PER_CTA;
+    for (int64_t rd = (int64_t)blockIdx.x * B_WARPS_PER_CTA + (threadIdx.x >> 5); rd < P.n_reads; rd += nw) {
+        classify_read<ONE>(P, rd);
+        __syncwarp();
     }
 }
 #endif
@@ -242,22 +219,22 @@ struct c2b_engine {
     unsigned long long *d_counts = nullptr; size_t counts_n = 0;
     // scratch
     DevBuf tb, tbb, tbq, bnd, ops, rgo, work, lut;
+    DevBuf gops, gmeta, left;          // device-pointer API: op streams / meta words / left-over list of the last launch
     int n_warps = 0, grid = 0, wpc = 8, stage_cap = 0;
+    int grid_a = 0, grid_b = 0, stage_cap_a = 0;       // ALIGN / CLASSIFY kernels
+    int split_ok = 0, split_all = 0;                   // configuration admits the two-kernel form (some / all references)
+    int numa_node = -1;                                // NUMA node of the device (-1: unknown / single node)
     int scratch_TS = 0;
     // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
-    struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed, maxlen, ord; int32_t *h_ord = nullptr; size_t h_ord_cap = 0; int64_t *h_off = nullptr; size_t h_off_cap = 0;
+    struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed, maxlen, ord, gops, gmeta, left; int32_t *h_ord = nullptr; size_t h_ord_cap = 0; int64_t *h_off = nullptr; size_t h_off_cap = 0;
                    rt_event in_done, k_done, out_done; bool used = false; } stage[2];
     rt_stream s_in = 0, s_out = 0, stream2 = 0;     // stream2: second compute stream, kernels of odd chunks
     rt_event fork_ev = 0;                           // orders stream2 after what is already queued on `stream`
     size_t set_tb = 0, set_tbb = 0, set_tbq = 0, set_bnd = 0, set_ops = 0, set_rgo = 0;   // bytes per scratch set (two sets: kernels of
                                                     // consecutive chunks overlap their tail / head on the two streams)
     bool pipe_ready = false;
-    // streamed launch (one persistent launch per host batch): whole-batch device buffers + control block
-    struct Streamed { DevBuf reads, off, cnt, qw, rid, ord, recs, alns, str, ed, ctl; unsigned long long *h_ctl = nullptr; size_t h_ctl_cap = 0;
-                      int64_t *h_off = nullptr; size_t h_off_cap = 0; int32_t *h_ord = nullptr; size_t h_ord_cap = 0; rt_stream s_poll = 0; bool ready = false; } sm;
     double last_ms = 0; int64_t launches = 0;
     const uint64_t *forced_ops = nullptr; const int32_t *forced_n = nullptr;
-    const unsigned long long *k_avail = nullptr, *k_chunk_end = nullptr; unsigned long long *k_chunk_done = nullptr; int k_n_chunks = 0;   // streamed launch (set around launch_on)
     const int32_t *pair_order = nullptr;
     int64_t band_reruns = 0, ring_pairs = 0, ring_fallbacks = 0;
 #ifndef C2B_EMU
@@ -284,6 +261,53 @@ static int ensure(c2b_engine *e, DevBuf &b, size_t n)
 
 extern "C" {
 
+#ifndef C2B_EMU
+// Host side of a rank: run on, and allocate pinned memory from, the NUMA node the GPU hangs off.  On the two-socket
+// hosts this engine targets, ranks whose pinned buffers sit on the other socket push every H2D / D2H byte through the
+// socket interconnect (r01: e2e efficiency 0.55 at 8 GPUs with un-placed buffers).  Binds the CALLING thread (threads it
+// creates later inherit it) unless the process already restricted its CPUs to one node or C2B_NO_NUMA_BIND is set.
+static int numa_bind_for_device(int device)
+{
+    if (getenv("C2B_NO_NUMA_BIND")) return -1;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return -1;
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[256];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return -1;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return -1;
+    char list[4096] = {0};
+    if (!fgets(list, sizeof list, f)) { fclose(f); return -1; }
+    fclose(f);
+    cpu_set_t want, have;
+    CPU_ZERO(&want);
+    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int lo = 0, hi = 0;
+        if (sscanf(tok, "%d-%d", &lo, &hi) == 2) { for (int c = lo; c <= hi && c < CPU_SETSIZE; c++) CPU_SET(c, &want); }
+        else if (sscanf(tok, "%d", &lo) == 1 && lo < CPU_SETSIZE) CPU_SET(lo, &want);
+    }
+    if (sched_getaffinity(0, sizeof have, &have) != 0) return node;
+    cpu_set_t both;
+    CPU_AND(&both, &want, &have);
+    if (CPU_COUNT(&both) == 0) return node;                 // the caller pinned us elsewhere: leave it
+    if (CPU_COUNT(&both) < CPU_COUNT(&have)) sched_setaffinity(0, sizeof both, &both);
+    // memory policy of this thread: prefer the device's node (pinned allocations made by this thread follow it)
+    unsigned long mask[16] = {0};
+    if (node < (int)(sizeof mask * 8)) {
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof mask * 8);
+    }
+    return node;
+}
+#endif
+
 int c2b_create(int device, c2b_engine **out)
 {
     if (!out) return C2B_E_ARG;
@@ -291,47 +315,68 @@ int c2b_create(int device, c2b_engine **out)
     e->device = device;
 #ifndef C2B_EMU
     cudaError_t r = cudaSetDevice(device);
+    if (r == cudaSuccess) e->numa_node = numa_bind_for_device(device);
     if (r == cudaSuccess) r = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (r == cudaSuccess) r = cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking);
     if (r == cudaSuccess) r = cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming);
     if (r == cudaSuccess) r = cudaEventCreate(&e->ev0);
     if (r == cudaSuccess) r = cudaEventCreate(&e->ev1);
-    int nsm = 0, occ = 0, smem_sm = 0;
+    int nsm = 0, occ = 0, smem_sm = 0, optin = 0;
     if (r == cudaSuccess) r = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
     if (r == cudaSuccess) r = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+    if (r == cudaSuccess) r = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     // room for a TMA-staged reference tile next to C2B_MIN_CTAS_PER_SM CTAs of per-warp state (1 KB per CTA is reserved by the driver)
-    // ... and the kernels' static shared memory (up to 1.3 KB: hand-out slots, mbarrier) -- if the sum is a byte too large the
+    // ... and the kernels' static shared memory (hand-out slots, mbarrier) -- if the sum is a byte too large the
     // occupancy query answers 1 CTA per SM and the persistent grid silently halves (r01k: 37 ms instead of 27)
-    e->stage_cap = smem_sm / C2B_MIN_CTAS_PER_SM - 1024 - (int)((sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA) - 2048;
-    {   // ... and within the per-block opt-in limit
-        int optin = 0;
-        if (r == cudaSuccess) r = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-        const int fixed = (int)((sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA) + 128;
-        if (e->stage_cap > optin - fixed) e->stage_cap = optin - fixed;
-    }
-    if (e->stage_cap < 0) e->stage_cap = 0;
-    e->stage_cap &= ~127;
+    auto tile_room = [&](size_t per_warp, int ctas) {
+        int cap = smem_sm / ctas - 1024 - (int)(per_warp * WARPS_PER_CTA) - 2048;
+        const int fixed = (int)(per_warp * WARPS_PER_CTA) + 128;
+        if (cap > optin - fixed) cap = optin - fixed;
+        if (cap < 0) cap = 0;
+        return cap & ~127;
+    };
+    e->stage_cap = tile_room(sizeof(WarpSmem) + sizeof(QuadSmem), C2B_MIN_CTAS_PER_SM);
     const int dyn_smem = (int)((sizeof(WarpSmem) + sizeof(QuadSmem)) * WARPS_PER_CTA) + 128 + e->stage_cap;
     {
-        const void *kernels[4] = {(const void *)c2b_align_classify_kernel<true, false>, (const void *)c2b_align_classify_kernel<false, false>,
-                                  (const void *)c2b_align_classify_kernel<true, true>, (const void *)c2b_align_classify_kernel<false, true>};
+        const void *kernels[2] = {(const void *)c2b_align_classify_kernel<true>, (const void *)c2b_align_classify_kernel<false>};
         occ = 1 << 20;
-        for (const void *k : kernels) {                    // all instantiations must fit the same persistent grid
+        for (const void *k : kernels) {                    // both instantiations must fit the same persistent grid
             int o = 0;
             if (r == cudaSuccess) r = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
             if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k, WARPS_PER_CTA * 32, dyn_smem);
             occ = std::min(occ, o);
         }
     }
+    // ALIGN kernel: its own (smaller) per-warp state; CTAs per SM from the occupancy query, optionally capped (C2B_A_CTAS_PER_SM)
+    int occ_a = 0, occ_b = 0;
+    e->stage_cap_a = tile_room(sizeof(ASmem), C2B_A_MIN_CTAS);
+    const int dyn_a = (int)(sizeof(ASmem) * WARPS_PER_CTA) + 128 + e->stage_cap_a;
+    if (r == cudaSuccess) r = cudaFuncSetAttribute((const void *)c2b_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_a);
+    if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, (const void *)c2b_align_kernel, WARPS_PER_CTA * 32, dyn_a);
+    if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, (const void *)c2b_classify_kernel<true>, B_WARPS_PER_CTA * 32, 0);
+    {
+        int o = 0;
+        if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)c2b_classify_kernel<false>, B_WARPS_PER_CTA * 32, 0);
+        occ_b = std::min(occ_b, o);
+    }
     if (r != cudaSuccess) { g_create_err = std::string("c2b_create: ") + cudaGetErrorString(r); delete e; return C2B_E_CUDA; }
     if (occ < 1) occ = 1;
+    if (occ_a < 1) occ_a = 1;
+    if (occ_b < 1) occ_b = 1;
     if (occ < C2B_MIN_CTAS_PER_SM && !getenv("C2B_CTAS_PER_SM"))
-        fprintf(stderr, "[c2b] warning: only %d CTA(s) of the align kernel fit an SM (built for %d)\n", occ, C2B_MIN_CTAS_PER_SM);
+        fprintf(stderr, "[c2b] warning: only %d CTA(s) of the general kernel fit an SM (built for %d)\n", occ, C2B_MIN_CTAS_PER_SM);
     e->wpc = WARPS_PER_CTA;
     if (const char *v = getenv("C2B_WARPS_PER_CTA")) { int k = atoi(v); if (k >= 1 && k <= WARPS_PER_CTA) e->wpc = k; }
     if (const char *v = getenv("C2B_CTAS_PER_SM")) { int k = atoi(v); if (k >= 1 && k <= occ) occ = k; }
+    if (const char *v = getenv("C2B_A_CTAS_PER_SM")) { int k = atoi(v); if (k >= 1 && k <= occ_a) occ_a = k; }
+    if (occ_a > C2B_A_MIN_CTAS) occ_a = C2B_A_MIN_CTAS;
     e->grid = nsm * occ;                 // persistent: one wave of CTAs, warps pull work items from a counter
-    e->n_warps = e->grid * e->wpc;
+    e->grid_a = nsm * occ_a;
+    e->grid_b = nsm * std::min(occ_b, 8);
+    e->n_warps = std::max(e->grid, e->grid_a) * e->wpc;  // scratch slabs are per resident warp of whichever kernel is larger
+    if (getenv("C2B_VERBOSE"))
+        fprintf(stderr, "[c2b] device %d (NUMA node %d): general kernel %d CTAs/SM, ALIGN %d CTAs/SM (tile room %d B), CLASSIFY %d CTAs/SM x %d warps\n",
+                device, e->numa_node, occ, occ_a, e->stage_cap_a, std::min(occ_b, 8), B_WARPS_PER_CTA);
 #else
     e->grid = 1; e->n_warps = 1;
 #endif
@@ -342,24 +387,16 @@ int c2b_create(int device, c2b_engine **out)
 void c2b_destroy(c2b_engine *e)
 {
     if (!e) return;
-    DevBuf *bufs[] = {&e->tb, &e->tbb, &e->tbq, &e->bnd, &e->ops, &e->rgo, &e->work, &e->lut};
+    DevBuf *bufs[] = {&e->tb, &e->tbb, &e->tbq, &e->bnd, &e->ops, &e->rgo, &e->work, &e->lut, &e->gops, &e->gmeta, &e->left};
     for (DevBuf *b : bufs) if (b->p) rt_free(b->p);
     for (auto &st : e->stage) {
-        DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed, &st.maxlen, &st.ord};
+        DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed, &st.maxlen, &st.ord, &st.gops, &st.gmeta, &st.left};
         if (st.h_ord) rt_host_free(st.h_ord);
         for (DevBuf *b : sb) if (b->p) rt_free(b->p);
         if (st.h_off) rt_host_free(st.h_off);
         if (e->pipe_ready) { rt_event_destroy(st.in_done); rt_event_destroy(st.k_done); rt_event_destroy(st.out_done); }
     }
     if (e->pipe_ready) { rt_stream_destroy(e->s_in); rt_stream_destroy(e->s_out); }
-    {
-        DevBuf *mb[] = {&e->sm.reads, &e->sm.off, &e->sm.cnt, &e->sm.qw, &e->sm.rid, &e->sm.ord, &e->sm.recs, &e->sm.alns, &e->sm.str, &e->sm.ed, &e->sm.ctl};
-        for (DevBuf *b : mb) if (b->p) rt_free(b->p);
-        if (e->sm.h_ctl) rt_host_free(e->sm.h_ctl);
-        if (e->sm.h_off) rt_host_free(e->sm.h_off);
-        if (e->sm.h_ord) rt_host_free(e->sm.h_ord);
-        if (e->sm.ready) rt_stream_destroy(e->sm.s_poll);
-    }
     if (e->d_tables) rt_free(e->d_tables);
     if (e->d_counts) rt_free(e->d_counts);
 #ifndef C2B_EMU
@@ -437,6 +474,7 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
         const c2b_ref &rf = refs[r];
         const int I = rf.len, nrb = (I + 255) / 256, Ipad = nrb * 256;
         RefDev &d = e->refdev[r];
+        e->refs[r].seq.assign(rf.seq, (size_t)rf.len);
         d.I = I; d.nrb = nrb; d.Ipad = Ipad; d.kstar = (I - 1) & 7; d.lstar = ((I - 1) >> 3) & 31;
         d.min_aln = rf.min_aln_score;
         unsigned char *hb = blob.data() + base[r];
@@ -555,6 +593,13 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
         RTCHK(rt_sync(e->stream));
     }
     e->max_I = maxI; e->max_nrb = max_nrb;
+    {   // two-kernel form (c2b_split.cuh): the ring-banded DP must be admissible -- for one reference at least when every
+        // read has one candidate, for all of them when every read is tried against every reference
+        int n_ok = 0;
+        for (int r = 0; r < n_refs; r++) n_ok += (e->refdev[r].rg_ok && !e->refdev[r].coding) ? 1 : 0;
+        e->split_ok = !(p->flags & (C2B_F_NO_PAIRING | C2B_F_NO_RING)) && n_ok > 0;
+        e->split_all = n_ok == n_refs;
+    }
     e->scratch_TS = 0;
     e->configured = true;
     return C2B_OK;
@@ -626,15 +671,18 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
     return C2B_OK;
 }
 
-// One launch on compute stream `cs` using scratch set `set` (0 or 1).  Launches that may overlap in time must use
-// different sets; launches on the same stream are ordered.
+// One batch on compute stream `cs` using scratch set `set` (0 or 1): the ALIGN / CLASSIFY pair followed by the general
+// kernel over what ALIGN left over -- or the general kernel alone where the two-kernel form does not apply.  Launches that
+// may overlap in time must use different sets; launches on the same stream are ordered.
+// d_gops / d_gmeta / d_left: op streams [n_reads * R * W/32] u64, meta words [n_reads * R], left-over list [n_reads + 8] i32.
 static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_reads, const int64_t *d_offsets, int64_t n_reads,
                      int32_t max_read_len, const int32_t *d_count, const int32_t *d_qweight,
                      const int32_t *d_ref_id, c2b_read_rec *d_recs, c2b_aln_rec *d_alns,
-                     uint8_t *d_strings, c2b_edit *d_edits)
+                     uint8_t *d_strings, c2b_edit *d_edits, uint64_t *d_gops, uint32_t *d_gmeta, int32_t *d_left)
 {
     if (!e || !e->configured) return fail(e, C2B_E_STATE, "c2b_align_batch: engine not configured");
     if (n_reads < 0 || !d_recs || !d_alns || (n_reads && (!d_reads || !d_offsets))) return fail(e, C2B_E_ARG, "c2b_align_batch: bad argument");
+    if (n_reads >= (1ll << 31)) return fail(e, C2B_E_LIMIT, "c2b_align_batch: more than 2^31 reads in one batch");
     if (max_read_len < 1) max_read_len = 1;
     if (max_read_len > C2B_MAX_READ_LEN) return fail(e, C2B_E_LIMIT, "c2b_align_batch: read longer than C2B_MAX_READ_LEN");
     if ((int64_t)std::abs((long long)e->prm.gap_open) * max_read_len * e->max_I >= (1ll << 28))
@@ -664,54 +712,75 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
     P.opsbuf = (uint64_t *)at(e->ops, e->set_ops);
     P.rgops = getenv("C2B_NO_MULTI_RING") ? nullptr : (uint64_t *)at(e->rgo, e->set_rgo);
     P.stats = (unsigned long long *)e->work.p;
-    P.work_counter = P.stats + 8 + 8 * set;
+    unsigned long long *wk = P.stats + 8 + 8 * set;       // [0] ALIGN / general hand-out counter, [1] widest alignment, [2] general kernel's counter after ALIGN, [3] left-over count
+    P.work_counter = wk; P.widest = wk + 1;
     P.vstride = e->vstride; P.hstride = e->hstride;
     P.forced_ops = e->forced_ops; P.forced_n = e->forced_n;
-    P.avail = e->k_avail; P.chunk_end = e->k_chunk_end; P.chunk_done = e->k_chunk_done; P.n_chunks = e->k_n_chunks;
-    P.phase_sync = 4;                                     // warps per phase set (C2B_PHASE_WARPS: 0/1 = free-running, 2, 4, 8)
-    if (const char *v = getenv("C2B_PHASE_WARPS")) { const int k = atoi(v), a = k < 0 ? -k : k; P.phase_sync = (a == 2 || a == 4 || a == 8 || a == 16) ? k : 0; }
-    {   // grp_sync wants |g| and the number of sets to be powers of two
-        const int a = P.phase_sync < 0 ? -P.phase_sync : P.phase_sync;
-        const int nsets = a ? e->wpc / a : 0;
-        if (a > e->wpc || (a && e->wpc % a) || (P.phase_sync < 0 && (nsets & (nsets - 1)))) P.phase_sync = 0;
-    }
-    if (e->n_refs > 1 && !d_ref_id && getenv("C2B_NO_MULTI_PHASE")) P.phase_sync = 0;     // A/B switch: free-running warps in multi-reference mode
+    P.gops = d_gops; P.gmeta = d_gmeta; P.NW = P.W / 32;
     P.pair_order = e->pair_order;
     P.lut = (const uint8_t *)e->lut.p;
     P.stage_bytes = 0; P.stage_src = nullptr;
-#ifndef C2B_EMU
-    {   // stage reference 0's packed profile when it exists and fits beside two CTAs' worth of per-warp state
-        const RefDev &r0 = e->refdev[0];
-        const size_t bytes = (size_t)e->prm.nq * e->prm.nq * r0.Ipad * 4;
-        if (r0.pk_maxJ > 0 && !e->forced_ops && bytes <= (size_t)e->stage_cap && !getenv("C2B_NO_TMA_STAGE")) {
-            P.stage_bytes = (int32_t)bytes; P.stage_src = r0.prof2;
-        }
+    // two-kernel form: the configuration admits the ring-banded DP, op-stream buffers were supplied, nothing forces the
+    // general kernel (caller-supplied op streams, the A/B switches)
+    const bool split = e->split_ok && d_gops && d_gmeta && d_left && P.tbq && !e->forced_ops && !getenv("C2B_NO_SPLIT") &&
+                       (e->n_refs == 1 || d_ref_id != nullptr || (e->n_refs <= RG_MAX_REFS && e->split_all));
+    P.phase_sync = 0;
+    if (!split) {                                         // one-kernel form: warps of a phase set move in step (C2B_PHASE_WARPS: 0/1 = free-running, 2, 4, 8)
+        P.phase_sync = 4;
+        if (const char *v = getenv("C2B_PHASE_WARPS")) { const int k = atoi(v), a = k < 0 ? -k : k; P.phase_sync = (a == 2 || a == 4 || a == 8 || a == 16) ? k : 0; }
+        const int a = P.phase_sync < 0 ? -P.phase_sync : P.phase_sync;
+        const int nsets = a ? e->wpc / a : 0;
+        if (a > e->wpc || (a && e->wpc % a) || (P.phase_sync < 0 && (nsets & (nsets - 1)))) P.phase_sync = 0;
+        if (e->n_refs > 1 && !d_ref_id && getenv("C2B_NO_MULTI_PHASE")) P.phase_sync = 0;
     }
-#endif
-    RTCHK(rt_zero(P.work_counter, 16, cs));               // this set's work counter and widest alignment
+    const bool one = (e->n_refs == 1 || d_ref_id != nullptr) && !getenv("C2B_GENERIC_KERNEL");      // one candidate reference per read
+    RTCHK(rt_zero(wk, 32, cs));                           // this set's counters and widest alignment
+    if (d_gmeta) RTCHK(rt_zero(d_gmeta, (size_t)n_reads * P.out_refs * 4, cs));
 #ifndef C2B_EMU
+    const RefDev &r0 = e->refdev[0];
+    const size_t tile = (size_t)e->prm.nq * e->prm.nq * r0.Ipad * 4;        // reference 0's packed profile
+    const bool can_stage = r0.pk_maxJ > 0 && !e->forced_ops && !getenv("C2B_NO_TMA_STAGE");
     cudaEventRecord(e->ev0, cs);
+    if (split) {
+        KParams A = P;
+        A.left = d_left; A.left_n = wk + 3;
+        A.discard_slab = getenv("C2B_NO_DISCARD") ? 0 : 1;
+        if (can_stage && tile <= (size_t)e->stage_cap_a) { A.stage_bytes = (int32_t)tile; A.stage_src = r0.prof2; }
+        const size_t smem_a = sizeof(ASmem) * e->wpc + 128 + (size_t)A.stage_bytes;
+        c2b_align_kernel<<<e->grid_a, e->wpc * 32, smem_a, cs>>>(A);
+        if (one) c2b_classify_kernel<true><<<e->grid_b, B_WARPS_PER_CTA * 32, 0, cs>>>(P);
+        else c2b_classify_kernel<false><<<e->grid_b, B_WARPS_PER_CTA * 32, 0, cs>>>(P);
+        // the general kernel over ALIGN's left-over pairs (free-running warps, no ring-banded attempt)
+        P.pair_order = d_left; P.n_dev = wk + 3; P.work_counter = wk + 2; P.tbq = nullptr; P.rgops = nullptr;
+        e->launches += 2;
+    }
     {
+        if (can_stage && tile <= (size_t)e->stage_cap) { P.stage_bytes = (int32_t)tile; P.stage_src = r0.prof2; }
         const size_t smem = (sizeof(WarpSmem) + sizeof(QuadSmem)) * e->wpc + 128 + (size_t)P.stage_bytes;
-        const bool one = (e->n_refs == 1 || d_ref_id != nullptr) && !getenv("C2B_GENERIC_KERNEL");      // one candidate reference per read
-        const bool stream = P.avail != nullptr;
-        if (one && !stream) c2b_align_classify_kernel<true, false><<<e->grid, e->wpc * 32, smem, cs>>>(P);
-        else if (!stream) c2b_align_classify_kernel<false, false><<<e->grid, e->wpc * 32, smem, cs>>>(P);
-        else if (one) c2b_align_classify_kernel<true, true><<<e->grid, e->wpc * 32, smem, cs>>>(P);
-        else c2b_align_classify_kernel<false, true><<<e->grid, e->wpc * 32, smem, cs>>>(P);
+        if (one) c2b_align_classify_kernel<true><<<e->grid, e->wpc * 32, smem, cs>>>(P);
+        else c2b_align_classify_kernel<false><<<e->grid, e->wpc * 32, smem, cs>>>(P);
     }
     cudaEventRecord(e->ev1, cs);
     RTCHK(cudaGetLastError());
 #else
     {
-        static WarpSmem S; static QuadSmem Q;
-        for (int64_t w = 0; 8 * w < n_reads; w++) {
+        static WarpSmem S; static QuadSmem Q; static ASmem AS;
+        if (split) {
+            KParams A = P;
+            A.left = d_left; A.left_n = wk + 3;
+            for (int64_t w = 0; 8 * w < n_reads; w++) emu::run_warp([&]() { align_group(A, AS, nullptr, w, 0); });
+            for (int64_t rd = 0; rd < n_reads; rd++) {
+                if (one) emu::run_warp([&]() { classify_read<true>(P, rd); });
+                else emu::run_warp([&]() { classify_read<false>(P, rd); });
+            }
+            P.pair_order = d_left; P.n_dev = wk + 3; P.work_counter = wk + 2; P.tbq = nullptr; P.rgops = nullptr;
+        }
+        const int64_t nrd = P.n_dev ? (int64_t)*P.n_dev : n_reads;
+        for (int64_t w = 0; 8 * w < nrd; w++) {
             wp::g_grp_syncs = 0;
-            const bool one = (e->n_refs == 1 || d_ref_id != nullptr) && !getenv("C2B_GENERIC_KERNEL");
             if (one) emu::run_warp([&]() { process_group<true>(P, S, Q, nullptr, w, 0); });
             else emu::run_warp([&]() { process_group<false>(P, S, Q, nullptr, w, 0); });
             // every path through a work group must execute the same number of phase barriers (a mismatch deadlocks the GPU)
-            if (w == 0 && getenv("C2B_EMU_VERBOSE")) fprintf(stderr, "warp_emu: phase_sync %d, %ld barriers in group 0 (expected %d)\n", P.phase_sync, wp::g_grp_syncs, group_phases(P));
             if (P.phase_sync && wp::g_grp_syncs != group_phases(P)) {
                 fprintf(stderr, "warp_emu: work group %lld executed %ld phase barriers, expected %d\n", (long long)w, wp::g_grp_syncs, group_phases(P));
                 abort();
@@ -723,13 +792,36 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
     return C2B_OK;
 }
 
+// op-stream buffers of the device-pointer API (engine-owned, sized for the batch)
+static int ensure_ops(c2b_engine *e, DevBuf &gops, DevBuf &gmeta, DevBuf &left, int64_t n_reads, int nr, int W)
+{
+    int rc;
+    if ((rc = ensure(e, gops, (size_t)n_reads * nr * (W / 32) * 8))) return rc;
+    if ((rc = ensure(e, gmeta, (size_t)n_reads * nr * 4))) return rc;
+    if ((rc = ensure(e, left, (size_t)(n_reads + 8) * 4))) return rc;
+    return C2B_OK;
+}
+
 int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t *d_offsets, int64_t n_reads,
                            int32_t max_read_len, const int32_t *d_count, const int32_t *d_qweight,
                            const int32_t *d_ref_id, c2b_read_rec *d_recs, c2b_aln_rec *d_alns,
                            uint8_t *d_strings, c2b_edit *d_edits)
 {
-    return launch_on(e, e ? e->stream : 0, 0, d_reads, d_offsets, n_reads, max_read_len, d_count, d_qweight, d_ref_id, d_recs,
-                     d_alns, d_strings, d_edits);
+    if (!e || !e->configured) return fail(e, C2B_E_STATE, "c2b_align_batch_device: engine not configured");
+    if (max_read_len < 1) max_read_len = 1;
+    const int W = (e->max_I + max_read_len + 31) & ~31, nr = d_ref_id ? 1 : e->n_refs;
+    int rc = ensure_ops(e, e->gops, e->gmeta, e->left, n_reads, nr, W);
+    if (rc) return rc;
+    return launch_on(e, e->stream, 0, d_reads, d_offsets, n_reads, max_read_len, d_count, d_qweight, d_ref_id, d_recs,
+                     d_alns, d_strings, d_edits, (uint64_t *)e->gops.p, (uint32_t *)e->gmeta.p, (int32_t *)e->left.p);
+}
+
+int c2b_ops_device(c2b_engine *e, void **d_ops, void **d_meta)
+{
+    if (!e) return C2B_E_ARG;
+    if (d_ops) *d_ops = e->gops.p;
+    if (d_meta) *d_meta = e->gmeta.p;
+    return C2B_OK;
 }
 
 int64_t c2b_band_reruns(c2b_engine *e) { return e ? e->band_reruns : 0; }
@@ -785,174 +877,17 @@ int c2b_ring_counts(c2b_engine *e, int64_t *ring_pairs, int64_t *ring_fallbacks)
     return C2B_OK;
 }
 
-#ifndef C2B_EMU
-// C2B_STREAMED=1 / =0 forces the streamed launch on / off; default on (r01k: e2e 30.6 ms against 34.5 ms per 1 M reads).
-static bool streamed_default(const c2b_engine *) { const char *v = getenv("C2B_STREAMED"); return v ? atoi(v) != 0 : true; }
-
-// Host batch through ONE persistent launch: the kernel starts at once and takes work groups as their read bytes arrive
-// (chunked H2D on the copy stream, each followed by an 8-byte update of the "groups resident" mark the kernel polls);
-// every finished group bumps its chunk's counter, the host polls those and queues each chunk's D2H as soon as the chunk is
-// complete.  No launch head/tail per chunk, copies of both directions overlap the kernel.
-static int align_batch_streamed(c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads, int64_t maxJ,
-                                const int32_t *count, const int32_t *qweight, const int32_t *ref_id,
-                                c2b_read_rec *recs, c2b_aln_rec *alns, uint8_t *strings, c2b_edit *edits)
-{
-    c2b_engine::Streamed &m = e->sm;
-    int rc;
-    if (!m.ready) { RTCHK(rt_stream_create(&m.s_poll)); m.ready = true; }
-    const int W = (e->max_I + (int)maxJ + 31) & ~31;
-    const int cap = edits ? e->prm.edit_cap : 0;
-    const int nr = ref_id ? 1 : e->n_refs;
-    const int64_t b0 = offsets[0], nbytes = offsets[n_reads] - b0;
-    // chunk boundaries at multiples of 64 reads (whole hand-outs of a phase set); small first and last chunks
-    int64_t chunk = 1 << 16;
-    if (const char *v = getenv("C2B_STREAM_CHUNK")) chunk = std::max<int64_t>(64, atoll(v) / 64 * 64);
-    std::vector<int64_t> cuts;
-    cuts.push_back(0);
-    {
-        const int64_t edge = std::max<int64_t>(64, chunk / 8 / 64 * 64);
-        int64_t pos = 0;
-        if (n_reads > 4 * edge) { pos = edge; cuts.push_back(pos); }
-        const int64_t tail = (n_reads - pos > 2 * edge) ? edge : 0;
-        const int64_t body_end = (n_reads - tail) / 64 * 64;
-        while (pos < body_end) { pos = std::min(pos + chunk, body_end); cuts.push_back(pos); }
-        if (pos < n_reads) cuts.push_back(n_reads);
-    }
-    const int nc = (int)cuts.size() - 1;
-    if ((rc = ensure_scratch(e, (int)maxJ))) return rc;
-    if ((rc = ensure(e, m.reads, (size_t)nbytes + 256))) return rc;
-    if ((rc = ensure(e, m.off, (size_t)(n_reads + 1) * 8))) return rc;
-    if ((rc = ensure(e, m.recs, (size_t)n_reads * sizeof(c2b_read_rec)))) return rc;
-    if ((rc = ensure(e, m.alns, (size_t)n_reads * nr * sizeof(c2b_aln_rec)))) return rc;
-    if (strings && (rc = ensure(e, m.str, (size_t)n_reads * nr * 2 * W))) return rc;
-    if (cap && (rc = ensure(e, m.ed, (size_t)n_reads * nr * cap * sizeof(c2b_edit)))) return rc;
-    if (count && (rc = ensure(e, m.cnt, (size_t)n_reads * 4))) return rc;
-    if (qweight && (rc = ensure(e, m.qw, (size_t)n_reads * 4))) return rc;
-    if (ref_id && (rc = ensure(e, m.rid, (size_t)n_reads * 4))) return rc;
-    // control block (u64): [0] groups resident, [8 .. 8+nc) chunk end groups, [8+nc .. 8+2nc) groups done, [8+2nc .. 8+3nc) widest alignment
-    const size_t ctl_n = 8 + 3 * (size_t)nc;
-    if ((rc = ensure(e, m.ctl, ctl_n * 8))) return rc;
-    const size_t pin_n = 2 * ctl_n + (size_t)nc + 8;       // pinned: initial image | per-chunk "resident" marks | poll buffer
-    if (m.h_ctl_cap < pin_n) {
-        if (m.h_ctl) rt_host_free(m.h_ctl);
-        m.h_ctl = (unsigned long long *)rt_host_alloc(pin_n * 8); m.h_ctl_cap = m.h_ctl ? pin_n : 0;
-        if (!m.h_ctl) return fail(e, C2B_E_CUDA, "c2b_align_batch: pinned allocation failed");
-    }
-    if (m.h_off_cap < (size_t)(n_reads + 1)) {
-        if (m.h_off) rt_host_free(m.h_off);
-        m.h_off = (int64_t *)rt_host_alloc((size_t)(n_reads + 1) * 8); m.h_off_cap = m.h_off ? (size_t)(n_reads + 1) : 0;
-        if (!m.h_off) return fail(e, C2B_E_CUDA, "c2b_align_batch: pinned allocation failed");
-    }
-    bool need_order = false;
-    {
-        const int64_t L0 = offsets[1] - offsets[0];
-        for (int64_t k = 0; k <= n_reads; k++) m.h_off[k] = offsets[k] - b0;
-        for (int64_t k = 1; k < n_reads && !need_order; k++)
-            need_order = (offsets[k + 1] - offsets[k] != L0) || (ref_id && ref_id[k] != ref_id[0]);
-    }
-    // everything but the read bytes is small (8 + 12 bytes per read) and goes up before the launch
-    RTCHK(rt_h2d(m.off.p, m.h_off, (size_t)(n_reads + 1) * 8, e->stream));
-    if (count) RTCHK(rt_h2d(m.cnt.p, count, (size_t)n_reads * 4, e->stream));
-    if (qweight) RTCHK(rt_h2d(m.qw.p, qweight, (size_t)n_reads * 4, e->stream));
-    if (ref_id) RTCHK(rt_h2d(m.rid.p, ref_id, (size_t)n_reads * 4, e->stream));
-    e->pair_order = nullptr;
-    if (need_order) {                                      // per chunk: counting sort by (reference id, length); global indices
-        if ((rc = ensure(e, m.ord, (size_t)n_reads * 4))) return rc;
-        if (m.h_ord_cap < (size_t)n_reads) {
-            if (m.h_ord) rt_host_free(m.h_ord);
-            m.h_ord = (int32_t *)rt_host_alloc((size_t)n_reads * 4); m.h_ord_cap = m.h_ord ? (size_t)n_reads : 0;
-            if (!m.h_ord) return fail(e, C2B_E_CUDA, "c2b_align_batch: pinned allocation failed");
-        }
-        const int64_t nb = (int64_t)(C2B_MAX_READ_LEN + 1) * (ref_id ? e->n_refs : 1);
-        std::vector<int64_t> start((size_t)nb + 1);
-        auto key = [&](int64_t k) -> int64_t {
-            const int64_t L = offsets[k + 1] - offsets[k];
-            const int64_t r = ref_id ? std::min<int64_t>(std::max<int32_t>(ref_id[k], 0), e->n_refs - 1) : 0;
-            return r * (C2B_MAX_READ_LEN + 1) + L;
-        };
-        for (int c = 0; c < nc; c++) {
-            std::fill(start.begin(), start.end(), 0);
-            for (int64_t k = cuts[c]; k < cuts[c + 1]; k++) start[(size_t)key(k) + 1]++;
-            for (int64_t b = 0; b < nb; b++) start[(size_t)b + 1] += start[(size_t)b];
-            for (int64_t k = cuts[c]; k < cuts[c + 1]; k++) m.h_ord[cuts[c] + start[(size_t)key(k)]++] = (int32_t)k;
-        }
-        RTCHK(rt_h2d(m.ord.p, m.h_ord, (size_t)n_reads * 4, e->stream));
-        e->pair_order = (const int32_t *)m.ord.p;
-    }
-    unsigned long long *h = m.h_ctl;
-    for (size_t k = 0; k < ctl_n; k++) h[k] = 0;
-    for (int c = 0; c < nc; c++) h[8 + c] = (unsigned long long)((cuts[c + 1] + 7) / 8);
-    RTCHK(rt_h2d(m.ctl.p, h, ctl_n * 8, e->stream));
-    unsigned long long *d_ctl = (unsigned long long *)m.ctl.p;
-    // the copy stream starts after the control block, offsets and per-read arrays are in place (queued above on `stream`)
-    RTCHK(rt_record(e->fork_ev, e->stream));
-    RTCHK(rt_wait(e->s_in, e->fork_ev));
-    // All copies are queued BEFORE the launch: with pinned host buffers they are asynchronous and overlap the kernel just the
-    // same, and nothing the kernel waits for depends on host code that runs after the launch call -- a launch that blocks
-    // the host (CUDA_LAUNCH_BLOCKING, a profiler serialising kernels) would otherwise leave the kernel waiting for
-    // copies that are never issued.  (Pageable host buffers make cudaMemcpyAsync synchronous: correct, but the upload then
-    // precedes the kernel instead of overlapping it -- use c2b_host_alloc.)
-    unsigned long long *h_avail = h + ctl_n;               // pinned, one slot per chunk
-    for (int c = 0; c < nc; c++) {
-        const int64_t a = m.h_off[cuts[c]];
-        int64_t b = m.h_off[cuts[c + 1]];
-        if (c + 1 < nc) b = std::min<int64_t>((b + 127) & ~(int64_t)127, nbytes);    // whole 128-byte lines: no line is half-written when first read
-        RTCHK(rt_h2d((uint8_t *)m.reads.p + a, reads + b0 + a, (size_t)(b - a), e->s_in));
-        h_avail[c] = (unsigned long long)((cuts[c + 1] + 7) / 8);
-        RTCHK(rt_h2d(d_ctl, &h_avail[c], 8, e->s_in));
-    }
-    // launch: work groups whose bytes have not arrived yet are waited for inside the kernel
-    e->k_avail = d_ctl; e->k_chunk_end = d_ctl + 8; e->k_chunk_done = d_ctl + 8 + nc; e->k_n_chunks = nc;
-    rc = launch_on(e, e->stream, 0, (const uint8_t *)m.reads.p, (const int64_t *)m.off.p, n_reads, (int32_t)maxJ,
-                   count ? (const int32_t *)m.cnt.p : nullptr, qweight ? (const int32_t *)m.qw.p : nullptr,
-                   ref_id ? (const int32_t *)m.rid.p : nullptr, (c2b_read_rec *)m.recs.p, (c2b_aln_rec *)m.alns.p,
-                   strings ? (uint8_t *)m.str.p : nullptr, cap ? (c2b_edit *)m.ed.p : nullptr);
-    e->k_avail = nullptr; e->k_chunk_end = nullptr; e->k_chunk_done = nullptr; e->k_n_chunks = 0;
-    e->pair_order = nullptr;
-    if (rc) return rc;
-    // completion: poll the per-chunk counters, copy each chunk out as soon as it is whole
-    unsigned long long *h_poll = h + ctl_n + nc + 8;        // third part of the pinned block
-    for (int c = 0; c < nc; c++) {
-        const unsigned long long want = (unsigned long long)((cuts[c + 1] + 7) / 8 - (cuts[c] + 7) / 8);
-        int idle = 0;
-        const auto t_wait = std::chrono::steady_clock::now();
-        for (;;) {
-            RTCHK(rt_d2h(h_poll, d_ctl, ctl_n * 8, m.s_poll));
-            RTCHK(rt_sync(m.s_poll));
-            if (h_poll[8 + nc + c] >= want) break;
-            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_wait).count() > 120.0)
-                return fail(e, C2B_E_CUDA, "c2b_align_batch: streamed launch made no progress for 120 s");
-            if (cudaStreamQuery(e->stream) == cudaSuccess && ++idle > 2)
-                return fail(e, C2B_E_CUDA, "c2b_align_batch: streamed launch ended before all chunks were complete");
-        }
-        const int64_t c0 = cuts[c], n = cuts[c + 1] - cuts[c];
-        RTCHK(rt_d2h(recs + c0, (c2b_read_rec *)m.recs.p + c0, (size_t)n * sizeof(c2b_read_rec), e->s_out));
-        RTCHK(rt_d2h(alns + c0 * nr, (c2b_aln_rec *)m.alns.p + c0 * nr, (size_t)n * nr * sizeof(c2b_aln_rec), e->s_out));
-        if (cap) RTCHK(rt_d2h(edits + c0 * nr * cap, (c2b_edit *)m.ed.p + c0 * nr * cap, (size_t)n * nr * cap * sizeof(c2b_edit), e->s_out));
-        if (strings) {
-            size_t Wt = ((size_t)h_poll[8 + 2 * nc + c] + 31) & ~(size_t)31;
-            if (Wt > (size_t)W) Wt = W;
-            RTCHK(rt_d2h_2d(strings + c0 * nr * 2 * W + (W - Wt), (const uint8_t *)m.str.p + c0 * nr * 2 * W + (W - Wt), W, Wt, (size_t)n * nr * 2, e->s_out));
-        }
-    }
-    RTCHK(rt_sync(e->s_out));
-    RTCHK(rt_sync(e->stream));
-    {   // stats[7]: a wait inside the kernel timed out
-        unsigned long long flag = 0;
-        RTCHK(rt_d2h(&flag, (const char *)e->work.p + 7 * 8, 8, e->stream));
-        RTCHK(rt_sync(e->stream));
-        if (flag) return fail(e, C2B_E_CUDA, "c2b_align_batch: streamed launch timed out waiting for input");
-    }
-    return C2B_OK;
-}
-#endif
-
-int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads,
-                    const int32_t *count, const int32_t *qweight, const int32_t *ref_id,
-                    c2b_read_rec *recs, c2b_aln_rec *alns, uint8_t *strings, c2b_edit *edits)
+// Host buffers in, host buffers out: chunks pipeline through two staging sets and three streams -- H2D of chunk c+1 and
+// D2H of chunk c-1 overlap the kernels of chunk c.  strings (two W-byte slots per (read, reference)) and / or the compact
+// form (ops: W/32 words of 32 two-bit ops per slot, meta: one word per slot) are produced as requested; of either only the
+// part the chunk's widest alignment needs crosses PCIe.
+static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads,
+                            const int32_t *count, const int32_t *qweight, const int32_t *ref_id,
+                            c2b_read_rec *recs, c2b_aln_rec *alns, uint8_t *strings, uint64_t *ops, uint32_t *meta, c2b_edit *edits)
 {
     if (!e || !e->configured) return fail(e, C2B_E_STATE, "c2b_align_batch: engine not configured");
     if (n_reads < 0 || !recs || !alns || (n_reads && (!reads || !offsets))) return fail(e, C2B_E_ARG, "c2b_align_batch: bad argument");
+    if ((ops == nullptr) != (meta == nullptr)) return fail(e, C2B_E_ARG, "c2b_align_batch: ops and meta go together");
     if (n_reads == 0) return C2B_OK;
     int64_t maxJ = 1;
     for (int64_t r = 0; r < n_reads; r++) {
@@ -967,33 +902,17 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
         for (auto &st : e->stage) { RTCHK(rt_event_create(&st.in_done)); RTCHK(rt_event_create(&st.k_done)); RTCHK(rt_event_create(&st.out_done)); }
         e->pipe_ready = true;
     }
-#ifndef C2B_EMU
-    if (n_reads >= (1 << 16) && streamed_default(e)) {
-        // one persistent launch per slice of up to 4 Mi reads (whole-slice device buffers: about 1.2 KB per read)
-        const int64_t slice = 4 << 20;
-        const int64_t Wb = (e->max_I + (int)maxJ + 31) & ~31, nrb = ref_id ? 1 : e->n_refs, capb = edits ? e->prm.edit_cap : 0;
-        for (int64_t k = 0; k < n_reads; k += slice) {
-            const int64_t n = std::min(slice, n_reads - k);
-            const int rc2 = align_batch_streamed(e, reads, offsets + k, n, maxJ, count ? count + k : nullptr, qweight ? qweight + k : nullptr,
-                                                 ref_id ? ref_id + k : nullptr, recs + k, alns + k * nrb,
-                                                 strings ? strings + k * nrb * 2 * Wb : nullptr, edits ? edits + k * nrb * capb : nullptr);
-            if (rc2) return rc2;
-        }
-        return C2B_OK;
-    }
-#endif
-    const int W = (e->max_I + (int)maxJ + 31) & ~31;
+    const int W = (e->max_I + (int)maxJ + 31) & ~31, NW = W / 32;
     const int cap = edits ? e->prm.edit_cap : 0;
     const int nr = ref_id ? 1 : e->n_refs;                 // output slots per read (compact when ref_id is given)
-    // Chunks pipeline through two staging sets: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c.
-    const int64_t per_read = (int64_t)nr * (2 * (int64_t)W * (strings ? 1 : 0) + (int64_t)cap * 8 + 32) + 16 + maxJ + 24;
+    const int64_t per_read = (int64_t)nr * (2 * (int64_t)W * (strings ? 1 : 0) + NW * 8 + (int64_t)cap * 8 + 36) + 16 + maxJ + 28;
     int64_t chunk = std::max<int64_t>(4096, std::min<int64_t>((int64_t)(768ll << 20) / per_read, 1 << 17));
     if (n_reads < 4 * chunk) chunk = std::max<int64_t>(4096, (n_reads + 3) / 4);
     if (const char *v = getenv("C2B_CHUNK")) chunk = std::max<int64_t>(2, atoll(v));     // test hook: force many small chunks
     for (auto &st : e->stage) st.used = false;
     int rc = C2B_OK;
-    // D2H of a chunk is queued one iteration late: by then its kernel has finished and the widest alignment of the
-    // chunk is known, so only the right-hand `Wt` bytes of every W-byte string slot cross PCIe.
+    // D2H of a chunk is queued one iteration late: by then its kernels have finished and the widest alignment of the
+    // chunk is known, so only the right-hand `Wt` bytes of every W-byte string slot (the first Wt/32 op words) cross PCIe.
     struct Pending { bool any = false; int64_t c0 = 0, n = 0; int set = 0; } pend;
     auto flush = [&](const Pending &q) -> int {
         c2b_engine::Stage &st = e->stage[q.set];
@@ -1001,14 +920,16 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
         RTCHK(rt_d2h(recs + q.c0, st.recs.p, (size_t)q.n * sizeof(c2b_read_rec), e->s_out));
         RTCHK(rt_d2h(alns + q.c0 * nr, st.alns.p, (size_t)q.n * nr * sizeof(c2b_aln_rec), e->s_out));
         if (cap) RTCHK(rt_d2h(edits + q.c0 * nr * cap, st.ed.p, (size_t)q.n * nr * cap * sizeof(c2b_edit), e->s_out));
-        if (strings) {
+        if (meta) RTCHK(rt_d2h(meta + q.c0 * nr, st.gmeta.p, (size_t)q.n * nr * 4, e->s_out));
+        if (strings || ops) {
             RTCHK(rt_event_sync(st.k_done));
             long long wmax = 0;
             RTCHK(rt_d2h(&wmax, (const char *)st.maxlen.p, 8, e->s_out));
             RTCHK(rt_sync(e->s_out));
             size_t Wt = ((size_t)wmax + 31) & ~(size_t)31;
             if (Wt > (size_t)W) Wt = W;
-            RTCHK(rt_d2h_2d(strings + q.c0 * nr * 2 * W + (W - Wt), (const uint8_t *)st.str.p + (W - Wt), W, Wt, (size_t)q.n * nr * 2, e->s_out));
+            if (strings) RTCHK(rt_d2h_2d(strings + q.c0 * nr * 2 * W + (W - Wt), (const uint8_t *)st.str.p + (W - Wt), W, Wt, (size_t)q.n * nr * 2, e->s_out));
+            if (ops) RTCHK(rt_d2h_2d(ops + q.c0 * nr * NW, st.gops.p, (size_t)NW * 8, Wt / 32 * 8, (size_t)q.n * nr, e->s_out));
         }
         RTCHK(rt_record(st.out_done, e->s_out));
         return C2B_OK;
@@ -1024,15 +945,7 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
         while (n_reads - tail - pos > 0) { pos += std::min(chunk, n_reads - tail - pos); cuts.push_back(pos); }
         if (tail) cuts.push_back(n_reads);
     }
-    // Optional (C2B_TWO_STREAMS=1): kernels of consecutive chunks on two compute streams.  Measured r01k: 42.7 ms per
-    // 1 M reads against 35.7 ms on one stream -- two resident persistent grids slow each other more than the
-    // launch tails cost -- so one stream is the default.
-    bool two_streams = false;
-#ifndef C2B_EMU
-    two_streams = e->stream2 && getenv("C2B_TWO_STREAMS");
-#endif
-    if ((rc = ensure_scratch(e, (int)maxJ))) return rc;       // allocations / memsets on `stream` happen before the fork
-    if (two_streams) { RTCHK(rt_record(e->fork_ev, e->stream)); RTCHK(rt_wait(e->stream2, e->fork_ev)); }
+    if ((rc = ensure_scratch(e, (int)maxJ))) return rc;
     for (int ci = 0; ci + 1 < (int)cuts.size(); ci++) {
         c2b_engine::Stage &st = e->stage[ci & 1];
         const int64_t c0 = cuts[ci], n = cuts[ci + 1] - cuts[ci];
@@ -1048,6 +961,7 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
         if (count && (rc = ensure(e, st.cnt, (size_t)n * 4))) return rc;
         if (qweight && (rc = ensure(e, st.qw, (size_t)n * 4))) return rc;
         if (ref_id && (rc = ensure(e, st.rid, (size_t)n * 4))) return rc;
+        if ((rc = ensure_ops(e, st.gops, st.gmeta, st.left, n, nr, W))) return rc;
         if (st.h_off_cap < (size_t)(n + 1)) {
             if (st.h_off) rt_host_free(st.h_off);
             st.h_off = (int64_t *)rt_host_alloc((size_t)(n + 1) * 8); st.h_off_cap = st.h_off ? (size_t)(n + 1) : 0;
@@ -1085,30 +999,103 @@ int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets,
             e->pair_order = (const int32_t *)st.ord.p;
         }
         RTCHK(rt_record(st.in_done, e->s_in));
-        // kernels of consecutive chunks go to two compute streams with their own scratch sets: chunk ci+1's CTAs fill
-        // the SMs as chunk ci's CTAs run out of work, instead of waiting for its slowest warp (same-stream launches
-        // of one chunk parity stay ordered, so at most two launches -- of different sets -- are ever resident)
-        const int set = two_streams ? (ci & 1) : 0;
-        rt_stream cs = set ? e->stream2 : e->stream;
+        rt_stream cs = e->stream;
         RTCHK(rt_wait(cs, st.in_done));
-        rc = launch_on(e, cs, set, (const uint8_t *)st.reads.p, (const int64_t *)st.off.p, n, (int32_t)maxJ,
-                                    count ? (const int32_t *)st.cnt.p : nullptr, qweight ? (const int32_t *)st.qw.p : nullptr,
-                                    ref_id ? (const int32_t *)st.rid.p : nullptr, (c2b_read_rec *)st.recs.p,
-                                    (c2b_aln_rec *)st.alns.p, strings ? (uint8_t *)st.str.p : nullptr,
-                                    cap ? (c2b_edit *)st.ed.p : nullptr);
+        rc = launch_on(e, cs, 0, (const uint8_t *)st.reads.p, (const int64_t *)st.off.p, n, (int32_t)maxJ,
+                       count ? (const int32_t *)st.cnt.p : nullptr, qweight ? (const int32_t *)st.qw.p : nullptr,
+                       ref_id ? (const int32_t *)st.rid.p : nullptr, (c2b_read_rec *)st.recs.p,
+                       (c2b_aln_rec *)st.alns.p, strings ? (uint8_t *)st.str.p : nullptr,
+                       cap ? (c2b_edit *)st.ed.p : nullptr, (uint64_t *)st.gops.p, (uint32_t *)st.gmeta.p, (int32_t *)st.left.p);
         e->pair_order = nullptr;
         if (rc) return rc;
-        // keep this launch's "widest alignment" before the next launch resets it
-        RTCHK(cudaMemcpyAsyncOrCopy(st.maxlen.p, (const char *)e->work.p + (9 + 8 * set) * 8, 8, cs));
+        // keep this batch's "widest alignment" before the next launch sequence resets it
+        RTCHK(cudaMemcpyAsyncOrCopy(st.maxlen.p, (const char *)e->work.p + 9 * 8, 8, cs));
         RTCHK(rt_record(st.k_done, cs));
         st.used = true;
-        if (pend.any && (rc = flush(pend))) return rc;           // chunk ci-1: overlaps this chunk's kernel
+        if (pend.any && (rc = flush(pend))) return rc;           // chunk ci-1: overlaps this chunk's kernels
         pend.any = true; pend.c0 = c0; pend.n = n; pend.set = ci & 1;
     }
     if (pend.any && (rc = flush(pend))) return rc;
     RTCHK(rt_sync(e->s_out));
     RTCHK(rt_sync(e->stream));
-    if (two_streams) RTCHK(rt_sync(e->stream2));
+    return C2B_OK;
+}
+
+int c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads,
+                    const int32_t *count, const int32_t *qweight, const int32_t *ref_id,
+                    c2b_read_rec *recs, c2b_aln_rec *alns, uint8_t *strings, c2b_edit *edits)
+{
+    return align_batch_host(e, reads, offsets, n_reads, count, qweight, ref_id, recs, alns, strings, nullptr, nullptr, edits);
+}
+
+int c2b_align_batch_compact(c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads,
+                            const int32_t *count, const int32_t *qweight, const int32_t *ref_id,
+                            c2b_read_rec *recs, c2b_aln_rec *alns, uint64_t *ops, uint32_t *meta, c2b_edit *edits)
+{
+    if (!ops || !meta) return fail(e, C2B_E_ARG, "c2b_align_batch_compact: ops / meta missing");
+    return align_batch_host(e, reads, offsets, n_reads, count, qweight, ref_id, recs, alns, nullptr, ops, meta, edits);
+}
+
+int c2b_ops_words(const c2b_engine *e, int32_t max_read_len)
+{
+    if (!e || !e->configured) return C2B_E_STATE;
+    return ((e->max_I + max_read_len + 31) & ~31) / 32;
+}
+
+// Aligned strings of one (read, reference) slot from its op stream: host code, no device work.  Column q from the RIGHT
+// end of the alignment is op (ops[q >> 5] >> 2 (q & 31)) & 3: 0 = both consume, 1 = gap in the read, 2 = gap in the
+// reference.  strand 1: the read was aligned as its reverse complement (engine's complement table).
+int c2b_expand_alignment(const c2b_engine *e, const uint64_t *ops, uint32_t meta, const char *read, int32_t read_len,
+                         const char *ref, int32_t ref_len, char *out_read, char *out_ref)
+{
+    if (!e || !ops || !read || !ref || !out_read || !out_ref) return C2B_E_ARG;
+    const int n = (int)(meta & 0xffffu), strand = (int)((meta >> 16) & 1u);
+    unsigned char comp[256];
+    if (strand) {
+        for (int c = 0; c < 256; c++) comp[c] = (unsigned char)c;
+        for (int q = 0; q < e->prm.nq; q++) comp[(unsigned char)e->prm.alphabet[q]] = (unsigned char)e->prm.alphabet[e->prm.complement[q]];
+    }
+    int i = ref_len, j = read_len;
+    for (int q = 0; q < n; q++) {
+        const int op = (int)((ops[q >> 5] >> (2 * (q & 31))) & 3ull);
+        char rd = '-', rf = '-';
+        if (op != OP_J) { if (j < 1) return C2B_E_ARG; j--; rd = strand ? (char)comp[(unsigned char)read[read_len - 1 - j]] : read[j]; }
+        if (op != OP_I) { if (i < 1) return C2B_E_ARG; i--; rf = ref[i]; }
+        if (op == OP_NONE) return C2B_E_ARG;
+        out_read[n - 1 - q] = rd; out_ref[n - 1 - q] = rf;
+    }
+    return (i == 0 && j == 0) ? C2B_OK : C2B_E_ARG;
+}
+
+// Batch form: strings[n_reads][R][2][W], right-aligned like c2b_align_batch's, from the compact outputs; host threads.
+int c2b_expand_batch(const c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads, const int32_t *ref_id,
+                     const uint64_t *ops, const uint32_t *meta, int32_t max_read_len, uint8_t *strings, int32_t n_threads)
+{
+    if (!e || !e->configured || !reads || !offsets || !ops || !meta || !strings) return C2B_E_ARG;
+    const int W = (e->max_I + max_read_len + 31) & ~31, NW = W / 32, nr = ref_id ? 1 : e->n_refs;
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n_reads / 1024));
+    std::vector<int> bad((size_t)n_threads, 0);
+    auto work = [&](int t) {
+        const int64_t lo = n_reads * t / n_threads, hi = n_reads * (t + 1) / n_threads;
+        for (int64_t rd = lo; rd < hi; rd++)
+            for (int k = 0; k < nr; k++) {
+                const int r = ref_id ? ref_id[rd] : k;
+                const int64_t slot = rd * nr + k;
+                const uint32_t m = meta[slot];
+                const int n = (int)(m & 0xffffu);
+                if ((m >> 24) == 0 || n == 0 || n > W) continue;      // no alignment in this slot
+                uint8_t *o = strings + slot * 2 * (int64_t)W;
+                const RefHost &R = e->refs[(size_t)r];
+                if (c2b_expand_alignment(e, ops + slot * NW, m, (const char *)reads + offsets[rd], (int32_t)(offsets[rd + 1] - offsets[rd]),
+                                         R.seq.data(), (int32_t)R.seq.size(), (char *)o + W - n, (char *)o + 2 * W - n)) bad[(size_t)t]++;
+            }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    for (int b : bad) if (b) return C2B_E_ARG;
     return C2B_OK;
 }
 

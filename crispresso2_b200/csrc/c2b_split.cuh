@@ -1,0 +1,564 @@
+// c2b_split.cuh -- the hot path as two lean kernels (r02): ALIGN (ring-banded DP + traceback -> op streams in HBM) and
+// CLASSIFY (op streams -> aligned strings, find_indels_substitutions, per-read quantification), with the general kernel
+// of c2b_core.cuh (c2b_align_classify_kernel: full-matrix paths, any length, --coding_seq, forced op streams) run
+// afterwards over the pairs the ALIGN kernel could not prove exact in the band.
+//
+// Why: the one-kernel form carried 80 KB of hot per-read code against a 32 KB instruction cache and kept its warps in step
+// with 23 named barriers per work group (issue slots 47 % busy, profiles/r01k_ncu_full_summary.md).  Split, every kernel's
+// loop fits the cache, no warp waits for another, and the classification is re-formulated in COLUMN space: one alignment
+// column per lane, 32 columns per step, reference / read indices from two ballots (no shared-memory scatter, no second
+// row-space scan, no per-lane serial loop over 32 columns).
+//
+//   align_group    reference: CRISPResso2/CRISPResso2Align.pyx:142-421 (DP + traceback), CRISPRessoCORE.py:656-687 (strands)
+//   colscan0       reference: Align.pyx:338-434 (the two aligned strings, matchCount), CRISPRessoCORE.py:729-733 (irregular ends)
+//   colscan1       reference: CRISPRessoCOREResources.pyx:68-187 + the per-read body of CRISPRessoCORE.py:3989-4115
+//   classify_read  reference: CRISPRessoCORE.py:690-798 (best reference, classification), :4195-4272 (HDR re-projection)
+#pragma once
+#include "c2b_core.cuh"
+
+namespace c2b {
+
+constexpr uint32_t GM_NONE = 0, GM_ALIGNED = 1;        // gmeta state: 0 = not aligned by the ALIGN kernel (general kernel's job)
+
+C2B_DEV uint32_t gmeta_pack(int n, int strand, uint32_t state) { return (uint32_t)n | ((uint32_t)strand << 16) | (state << 24); }
+
+struct ASmem {                                         // ALIGN kernel, per warp
+    uint8_t fw[2][RG_COMBO], rc[2][RG_COMBO];          // the two reads of the pair being prepared, as alphabet codes
+    uint8_t combo[4][RG_COMBO];                        // base-pair codes of the four pairs
+    uint32_t fin[96];                                  // M, X, Y of cell (I, J) per lane
+};
+
+C2B_DEV int64_t read_at(const KParams &P, int64_t idx) { return P.pair_order ? (int64_t)P.pair_order[idx] : idx; }
+
+C2B_DEV void leftover_pair(const KParams &P, int64_t rdA, int64_t rdB)
+{
+    if (wp::lane() == 0) {
+        const unsigned long long pos = wp::fetch_add(P.left_n, 2ull);
+        P.left[pos] = (int32_t)rdA; P.left[pos + 1] = (int32_t)rdB;
+    }
+}
+
+// read -> alphabet codes for reads of at most RG_COMBO symbols; true if a symbol is outside the alphabet
+C2B_DEV bool load_codes_a(const KParams &P, int64_t off, int J, uint8_t *fw, uint8_t *rc)
+{
+    const int lane = wp::lane();
+    bool bad = false;
+    for (int base = 0; base < J; base += 128) {
+        uint8_t ch[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const int p = base + lane + 32 * e; ch[e] = p < J ? P.reads[off + p] : (uint8_t)P.alpha[0]; }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int p = base + lane + 32 * e;
+            int code = P.lut[ch[e]];
+            if (code == 255) { bad = true; code = 0; }
+            if (p < J) { fw[p] = (uint8_t)code; rc[J - 1 - p] = P.comp[code]; }
+        }
+    }
+    return wp::ballot(bad) != 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- ALIGN
+// Work group wq = reads 8wq..8wq+7 (four pairs).  Eligible groups (equal lengths per pair, every candidate reference admits
+// the band) run the ring-banded DP once per candidate reference and walk the four tracebacks; a pair whose two scores beat
+// the out-of-band bound for EVERY candidate reference leaves its op streams in P.gops and is marked GM_ALIGNED; every other
+// pair goes to the left-over list of the general kernel.
+C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof, int64_t wq, int warp_slot)
+{
+    const int lane = wp::lane(), g = lane >> 3;
+    const int64_t first = 4 * wq;
+    const bool multi = P.ref_id == nullptr && P.n_refs > 1;
+    bool quad = P.tbq != nullptr && 2 * first + 7 < P.n_reads && (!multi || P.n_refs <= RG_MAX_REFS);
+    int r0 = 0;
+    if (quad) {
+        const int x = lane & 7;
+        const int64_t rd = read_at(P, 2 * first + x);
+        const int Jx = (int)(P.offsets[rd + 1] - P.offsets[rd]);
+        const int rx = P.ref_id ? P.ref_id[rd] : 0;
+        r0 = wp::shfl(rx, 0);
+        const int Jn = wp::shfl_xor(Jx, 1);
+        bool ok = rx == r0 && Jx == Jn && Jx >= 1 && Jx <= RG_COMBO && Jx + 32 <= P.TS;
+        const int k0 = multi ? 0 : r0, k1 = multi ? P.n_refs : r0 + 1;
+        for (int k = k0; k < k1; k++) {
+            const RefDev &R = refdev(P, k);
+            ok = ok && R.rg_ok && !R.coding && Jx <= R.pk_maxJ && Jx - R.I <= RG_MAXD && R.I - Jx <= RG_MAXD;
+        }
+        quad = wp::ballot(ok) == 0xffffffffu;
+    }
+    if (!quad) {
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            if (2 * (first + q) >= P.n_reads) break;
+            const int64_t rdA = read_at(P, 2 * (first + q));
+            const int64_t rdB = 2 * (first + q) + 1 < P.n_reads ? read_at(P, 2 * (first + q) + 1) : rdA;
+            leftover_pair(P, rdA, rdB);
+        }
+        return;
+    }
+    const int k0 = multi ? 0 : r0, k1 = multi ? P.n_refs : r0 + 1;
+    uint2 *tbq = reinterpret_cast<uint2 *>(P.tbq + (int64_t)warp_slot * P.TS * 64);
+    uint32_t okmask = 0, modes = 0;
+    int Jg = 0, Jmax = 0;
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        const int64_t rdA = read_at(P, 2 * (first + q)), rdB = read_at(P, 2 * (first + q) + 1);
+        const int J = (int)(P.offsets[rdA + 1] - P.offsets[rdA]);
+        bool bad = false;
+#pragma unroll 1
+        for (int x = 0; x < 2; x++) bad |= load_codes_a(P, P.offsets[x ? rdB : rdA], J, S.fw[x], S.rc[x]);
+        wp::sync();
+        int mAB = 0; bool agree = true;
+#pragma unroll 1
+        for (int k = k0; k < k1; k++) {                     // every candidate reference's seed test must pick the same single strand
+            int m = 0;
+#pragma unroll 1
+            for (int x = 0; x < 2; x++) m |= strand_mode(P, refdev(P, k), S.fw[x], J) << (2 * x);
+            if (k == k0) mAB = m; else agree = agree && (m == mAB);
+        }
+        const int mA = mAB & 3, mB = mAB >> 2;
+        if (!bad && agree && mA != 2 && mB != 2) {           // a read that needs both strands takes the general kernel
+            const uint8_t *cA = mA ? S.rc[0] : S.fw[0], *cB = mB ? S.rc[1] : S.fw[1];
+            for (int p = lane; p < J; p += 32) S.combo[q][p] = (uint8_t)(cA[p] * P.nq + cB[p]);
+            okmask |= 1u << q; modes |= (uint32_t)mAB << (4 * q);
+            if (g == q) Jg = J;
+            if (J > Jmax) Jmax = J;
+        }
+        wp::sync();
+    }
+    uint32_t good = okmask;                                  // pairs whose band held for every reference so far
+    int npass = 0, ntried = 0;
+#pragma unroll 1
+    for (int k = k0; k < k1 && good; k++) {
+        const RefDev &R = refdev(P, k);
+        const bool staged = (k == 0 && staged_prof != nullptr);
+        if (staged) dp_ring<true>(P, R, staged_prof, S.combo[g], Jg, Jmax + R.lstar, tbq, S.fin);
+        else dp_ring<false>(P, R, R.prof2, S.combo[g], Jg, Jmax + R.lstar, tbq, S.fin);
+        wp::sync();
+        const int fl = 3 * ((lane & 24) | (R.lstar & 7));
+        const uint32_t cM = Jg > 0 ? S.fin[fl] : PK_SENT, cX = Jg > 0 ? S.fin[fl + 1] : PK_SENT, cY = Jg > 0 ? S.fin[fl + 2] : PK_SENT;
+        wp::sync();
+        const uint32_t z = wp::max3_2(cM, cY, cX);
+        const uint32_t s2 = z & PK_TM;
+        // biased value = 4*(score + beta*(I+J) + 512) + tag: both reads must beat the out-of-band bound (ring_bound)
+        const int thr = ring_bound(P, R, Jg) + 512 - P.ge * (R.I + Jg);
+        const bool pass = Jg > 0 && (int)((z & 0xffffu) >> 2) > thr && (int)(z >> 18) > thr;
+        const uint32_t b = wp::ballot(pass);
+        uint32_t passmask = ((b & 1u) | ((b >> 7) & 2u) | ((b >> 14) & 4u) | ((b >> 21) & 8u)) & good;
+        ntried += wp::popc(good);
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            if (!((passmask >> q) & 1u)) continue;
+            const uint32_t sq = wp::shflu(s2, 8 * q);
+            const int Jq = wp::shfl(Jg, 8 * q);
+            const int s0 = (lane & 16) ? (int)(sq >> 16) : (int)(sq & 3u);
+            const Walked wk = walk_batch<true>(P, R, Jq, reinterpret_cast<const uint32_t *>(tbq), s0, SlabMode{9, RG_B, RG_NS, 1, 8 * q});
+            if (wp::ballot(wk.err != 0)) { passmask &= ~(1u << q); continue; }    // cannot happen when the bound holds; general kernel then
+            const int h = lane >> 4, hl = lane & 15;
+            const int64_t rd = read_at(P, 2 * (first + q) + h);
+            const int64_t slot = oslot(P, rd, k);
+            if (hl < P.NW) P.gops[slot * P.NW + hl] = wk.ops;
+            if (hl == 0) {
+                const int mode = (int)((modes >> (4 * q + 2 * h)) & 3u);
+                P.gmeta[slot] = gmeta_pack(wk.n, mode == 1, GM_NONE);        // state is set below, once every reference passed
+            }
+        }
+        npass += wp::popc(passmask);
+        good &= passmask;
+        wp::sync();
+    }
+#ifndef C2B_EMU
+    // the slab is dead now: drop its lines from L2 instead of writing them back to HBM (10 KB per read otherwise)
+    if (P.discard_slab) {
+        const char *base = reinterpret_cast<const char *>(tbq);
+        const int64_t bytes = (int64_t)P.TS * 64 * 4;
+        for (int64_t o = (int64_t)lane * 128; o < bytes; o += 32 * 128)
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + o) : "memory");
+    }
+#endif
+    if (lane == 0) {
+        wp::addg(P.stats + 2, wp::popc(good));
+        wp::addg(P.stats + 5, npass);
+        wp::addg(P.stats + 6, ntried - npass + (k1 - k0) * (4 - wp::popc(okmask)));
+    }
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        const int64_t rdA = read_at(P, 2 * (first + q)), rdB = read_at(P, 2 * (first + q) + 1);
+        if ((good >> q) & 1u) {
+            const int64_t rd = (lane & 1) ? rdB : rdA;
+            const int k = k0 + (lane >> 1);
+            if (k < k1) { const int64_t slot = oslot(P, rd, k); P.gmeta[slot] = (P.gmeta[slot] & 0x00ffffffu) | (GM_ALIGNED << 24); }
+        } else leftover_pair(P, rdA, rdB);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- CLASSIFY
+// One alignment per warp, one column per lane, 32 columns per step, left to right.  Column c (from the left) is op number
+// n-1-c of the stream (the walk emits right to left).  With bI / bJ the ballots of the insertion / deletion columns of a
+// step, lane l's reference index is i0 + l - popc(bI below l) and its read index j0 + l - popc(bJ below l).
+struct ColCtx {
+    const uint64_t *ops;           // P.gops + slot * NW
+    const uint8_t *rd;             // P.reads + offset of the read
+    int n, J, strand;
+    uint32_t mmis, mI, mJ;         // lane m: ballots of step m (mismatching M columns, I columns, J columns) -- filled by colscan0
+};
+struct ColDec { int op, i, j; uint32_t rdc, rfc, bI, bJ; bool valid; };
+
+C2B_DEV ColDec col_decode(const KParams &P, const RefDev &R, const ColCtx &c, int m, int i0, int j0)
+{
+    const int lane = wp::lane();
+    const uint32_t lt = (1u << lane) - 1u;
+    ColDec d;
+    const int col = 32 * m + lane;
+    d.valid = col < c.n;
+    const int q = c.n - 1 - col;
+    d.op = OP_NONE;
+    if (d.valid) d.op = (int)((wp::ldcg64(c.ops + (q >> 5)) >> (2 * (q & 31))) & 3ull);
+    d.bI = wp::ballot(d.op == OP_I); d.bJ = wp::ballot(d.op == OP_J);
+    d.i = i0 + lane - wp::popc(d.bI & lt);
+    d.j = j0 + lane - wp::popc(d.bJ & lt);
+    d.rdc = '-'; d.rfc = '-';
+    if (d.valid && d.op != OP_J) {
+        uint32_t ch = c.rd[c.strand ? c.J - 1 - d.j : d.j];
+        if (c.strand) ch = P.alpha[P.comp[P.lut[ch]]];
+        d.rdc = ch;
+    }
+    if (d.valid && d.op != OP_I) d.rfc = R.asc[d.i];
+    return d;
+}
+
+// Pass 0: the two aligned strings (right-aligned in their W-byte slots), matchCount, irregular ends, and the per-step ballots
+// pass 1 uses to skip steps in which the read equals the reference.
+C2B_DEV ColOut colscan0(const KParams &P, const RefDev &R, ColCtx &c, uint8_t *o_read, uint8_t *o_ref)
+{
+    const int lane = wp::lane();
+    int i0 = 0, j0 = 0, match = 0;
+    uint32_t irr = 0;
+    c.mmis = c.mI = c.mJ = 0;
+    const int nsteps = (c.n + 31) >> 5;
+    uint8_t *pr = o_read ? o_read + P.W - c.n + lane : nullptr;
+    uint8_t *pf = o_ref ? o_ref + P.W - c.n + lane : nullptr;
+#pragma unroll 1
+    for (int m = 0; m < nsteps; m++) {
+        const ColDec d = col_decode(P, R, c, m, i0, j0);
+        const bool eq = d.valid && d.op == OP_M && d.rdc == d.rfc;
+        const uint32_t Beq = wp::ballot(eq), Bmis = wp::ballot(d.valid && d.op == OP_M && d.rdc != d.rfc);
+        match += wp::popc(Beq);
+        const int col = 32 * m + lane;
+        irr |= wp::ballot(d.valid && (col == 0 || col == c.n - 1) && !eq);
+        if (pr && d.valid) { pr[32 * m] = (uint8_t)d.rdc; pf[32 * m] = (uint8_t)d.rfc; }
+        if (lane == m) { c.mmis = Bmis; c.mI = d.bI; c.mJ = d.bJ; }
+        const int nv = c.n - 32 * m < 32 ? c.n - 32 * m : 32;
+        i0 += nv - wp::popc(d.bI); j0 += nv - wp::popc(d.bJ);
+    }
+    ColOut o; o.n_match = match; o.irregular = irr != 0;
+    return o;
+}
+
+// Pass 1: find_indels_substitutions + the per-read quantification, same mode bits and outputs as rows_run (c2b_core.cuh),
+// evaluated over alignment columns.  Insertion / deletion runs are closed in the step that holds their first column to the
+// right (state carried across steps); flank positions shared by two insertions count once (numpy's fancy-index +=).
+C2B_DEV void colscan1(const KParams &P, const RefDev &R, const ColCtx &c, RowOut &o, c2b_edit *ed, long long w, int mode,
+                      unsigned long long *Vt = nullptr)
+{
+    const int lane = wp::lane();
+    const uint32_t lt = (1u << lane) - 1u;
+    const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
+               ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
+    const bool scal = mode & RM_SCAL, vec = mode & RM_VEC, lenv = mode & RM_LEN, ref1 = mode & RM_REF1;
+    unsigned long long *V = ref1 ? Vt : R.vec;
+    const int vs = P.vstride, I = R.I;
+    int i0 = 0, j0 = 0;
+    int del_a = -1;                  // start of the deletion run that is open at the step boundary (-1: none)
+    int ins_len = 0;                 // length so far of the insertion run that is open at the step boundary
+    int flank_all = -1, flank_win = -1;      // right flank of the last insertion counted in ALL_INS / INS
+    const int nsteps = (c.n + 31) >> 5;
+
+    auto del_run = [&](int a, int b) {                     // one deletion run [a,b)  (COREResources.pyx:143-160)
+        const int size = b - a;
+        const bool hit = (int)R.cum[b] - (int)R.cum[a] > 0;
+        if (scal) {
+            o.n_del_all++; o.n_del_pos += size;
+            if (hit) { o.n_del_win++; o.del_n += size; }
+            if (lane == 0 && o.nent < P.edit_cap && ed) {
+                c2b_edit e; e.a = (uint16_t)a; e.b = (uint16_t)b; e.type = 3; e.in_window = hit; e.base = 0; e.pad = 0;
+                ed[o.nent] = e;
+            }
+            o.nent++;
+        }
+        if (hit && ((vec && !ign_d) || lenv)) {
+            for (int p = a + lane; p < b; p += 32) {
+                if (vec && !ign_d) wp::addg(V + (int64_t)C2B_V_DEL * vs + p, w);
+                if (lenv) wp::addg(V + (int64_t)C2B_V_DEL_LEN * vs + p, w * size);
+            }
+        }
+    };
+    auto ins_run = [&](int p1, int size) {                 // insertion of `size` bases between reference positions p1-1 and p1
+        if (p1 < 1 || p1 > I - 1) return;                  // before the first / after the last reference base: not an insertion (:117)
+        const int p = p1 - 1;
+        const bool win = (R.incl[p] & 1u) && (R.incl[p1] & 1u);      // both flanks in the window (:120)
+        if (scal) {
+            o.n_ins_all++;
+            if (win) { o.n_ins_win++; o.ins_n += size; }
+            if (lane == 0 && o.nent < P.edit_cap && ed) {
+                c2b_edit e; e.a = (uint16_t)p; e.b = (uint16_t)size; e.type = 2; e.in_window = win; e.base = 0; e.pad = 0;
+                ed[o.nent] = e;
+            }
+            o.nent++;
+        }
+        if (lane == 0) {
+            if (vec) {
+                wp::addg(V + (int64_t)C2B_V_ALL_INS_LEFT * vs + p, w);
+                if (p != flank_all) wp::addg(V + (int64_t)C2B_V_ALL_INS * vs + p, w);
+                wp::addg(V + (int64_t)C2B_V_ALL_INS * vs + p1, w);
+                if (win && !ign_i) {
+                    if (p != flank_win) wp::addg(V + (int64_t)C2B_V_INS * vs + p, w);
+                    wp::addg(V + (int64_t)C2B_V_INS * vs + p1, w);
+                }
+            }
+            if (ref1) {
+                wp::addg(V + (int64_t)C2B_V_R1_ALL_INS_LEFT * vs + p, w);
+                if (p != flank_all) wp::addg(V + (int64_t)C2B_V_R1_ALL_INS * vs + p, w);
+                wp::addg(V + (int64_t)C2B_V_R1_ALL_INS * vs + p1, w);
+            }
+            if (lenv && win) {
+                wp::addg(V + (int64_t)C2B_V_INS_LEN * vs + p, w * size);
+                wp::addg(V + (int64_t)C2B_V_INS_LEN * vs + p1, w * size);
+            }
+        }
+        flank_all = p1;
+        if (win) flank_win = p1;
+    };
+
+#pragma unroll 1
+    for (int m = 0; m < nsteps; m++) {
+        const int nv = c.n - 32 * m < 32 ? c.n - 32 * m : 32;
+        const uint32_t any = wp::shflu(c.mmis | c.mI | c.mJ, m);
+        if (!any && del_a < 0 && ins_len == 0) { i0 += nv; j0 += nv; continue; }      // the read equals the reference here
+        const ColDec d = col_decode(P, R, c, m, i0, j0);
+        const int p = d.i;
+        const bool isM = d.valid && d.op == OP_M, isdel = d.valid && d.op == OP_J;
+        const bool differs = isM && d.rdc != d.rfc;
+        const bool issub = differs && d.rdc != 'N';                                  // COREResources.pyx:111
+        const bool inc_p = (isM || isdel) && (R.incl[p] & 1u);
+        int rcode = 0;
+        if (differs) rcode = P.lut[d.rdc];
+        if (scal) {
+            const uint32_t Bs = wp::ballot(issub), Bsw = wp::ballot(issub && inc_p);
+            o.n_sub_all += wp::popc(Bs); o.sub_n += wp::popc(Bsw);
+            if (Bs) {
+                const int idx = o.nent + wp::popc(Bs & lt);
+                if (issub && idx < P.edit_cap && ed) {
+                    c2b_edit e; e.a = (uint16_t)p; e.b = 0; e.type = 1; e.in_window = inc_p; e.base = (uint8_t)d.rdc; e.pad = 0;
+                    ed[idx] = e;
+                }
+                o.nent += wp::popc(Bs);
+            }
+        }
+        if (vec) {
+            if (isdel) wp::addg(V + (int64_t)C2B_V_ALL_DEL * vs + p, w);
+            if (issub) {
+                wp::addg(V + (int64_t)C2B_V_ALL_SUB * vs + p, w);
+                if (!ign_s) {
+                    wp::addg(V + (int64_t)(C2B_V_SUBBASE0 + rcode) * vs + p, w);
+                    if (inc_p) wp::addg(V + (int64_t)C2B_V_SUB * vs + p, w);
+                }
+            }
+            if (isdel || differs) {                       // all_base_count_vectors as deviation from "read == ref"
+                const int rc = R.rcode[p];
+                wp::addg(V + (int64_t)(C2B_V_BASEDEV0 + (isdel ? P.nq : rcode)) * vs + p, w);
+                if (rc != 255) wp::addg(V + (int64_t)(C2B_V_BASEDEV0 + rc) * vs + p, -w);
+            }
+        }
+        if (ref1) {
+            if (isdel) wp::addg(V + (int64_t)C2B_V_R1_ALL_DEL * vs + p, w);
+            if (issub) wp::addg(V + (int64_t)C2B_V_R1_ALL_SUB * vs + p, w);
+            if (isdel || differs) {
+                const int rc = R.rcode[p];
+                wp::addg(V + (int64_t)(C2B_V_R1_BASEDEV0 + (isdel ? P.nq : rcode)) * vs + p, w);
+                if (rc != 255) wp::addg(V + (int64_t)(C2B_V_R1_BASEDEV0 + rc) * vs + p, -w);
+            }
+        }
+        // runs: a set bit of E* marks the first column to the right of a run (the column past the alignment closes a
+        // run that reaches its end); ref index of lane x of this step = i0 + x - popc(bI below x)
+        const uint32_t vmask = nv == 32 ? 0xffffffffu : ((1u << nv) - 1u);
+        auto ref_at = [&](int x) { return i0 + x - wp::popc(d.bI & ((1u << x) - 1u)); };
+        uint32_t events;
+        {
+            const uint32_t D = d.bJ, Dsh = (D << 1) | (del_a >= 0 ? 1u : 0u);
+            const uint32_t Ds = D & ~Dsh, De = ~D & Dsh;                 // starts / first column after a run
+            const uint32_t Iw = d.bI, Ish = (Iw << 1) | (ins_len > 0 ? 1u : 0u);
+            const uint32_t Is = Iw & ~Ish, Ie = ~Iw & Ish;
+            events = De | Ie;
+            // close runs in column order (deletion and insertion runs never touch, Align.pyx:394-413)
+            uint32_t rem = events;
+            // a run that ends exactly at the alignment's end inside this step closes at column nv (bit nv, if nv < 32)
+            while (rem) {
+                const int eb = wp::ffs(rem) - 1;
+                rem &= rem - 1;
+                if ((De >> eb) & 1u) {
+                    const uint32_t below = Ds & ((1u << eb) - 1u);
+                    const int a = below ? ref_at(31 - wp::clz(below)) : del_a;
+                    del_run(a, ref_at(eb));
+                    del_a = -1;
+                } else {
+                    const uint32_t below = Is & ((1u << eb) - 1u);
+                    const int sb = below ? 31 - wp::clz(below) : -1;
+                    const int size = sb >= 0 ? eb - sb : ins_len + eb;
+                    ins_run(ref_at(eb), size);
+                    ins_len = 0;
+                }
+            }
+            // runs still open at the end of the step
+            if ((D >> 31) & 1u) { if (del_a < 0) { const uint32_t s = Ds; del_a = ref_at(31 - wp::clz(s)); } }
+            if ((Iw >> 31) & 1u) {
+                const uint32_t s = Is;
+                if (ins_len > 0 && !s) ins_len += 32;                                  // the whole step is one run
+                else ins_len = 32 - (31 - wp::clz(s));
+            }
+            (void)vmask;
+        }
+        i0 += nv - wp::popc(d.bI); j0 += nv - wp::popc(d.bJ);
+    }
+    if (del_a >= 0) del_run(del_a, I);                     // a deletion that reaches the end of the alignment
+    // an insertion run that reaches the end of the alignment lies after the last reference base: not counted
+}
+
+// Classification + counts of one read whose alignments to references r_begin..r_end-1 were produced by the ALIGN kernel:
+// the body of finish_read (c2b_core.cuh) over column scans instead of the shared-memory row view.
+template <bool ONE>
+C2B_DEV void classify_read(const KParams &P, int64_t rd)
+{
+    const int lane = wp::lane();
+    const int r_begin = P.ref_id ? P.ref_id[rd] : 0;
+    const int r_end = (ONE || P.ref_id) ? r_begin + 1 : P.n_refs;
+    {   // handled by the ALIGN kernel?  (all candidate references or none)
+        const uint32_t m0 = wp::ldcg(P.gmeta + oslot(P, rd, r_begin));
+        if ((m0 >> 24) != GM_ALIGNED) return;
+    }
+    const int64_t off = P.offsets[rd];
+    const int J = (int)(P.offsets[rd + 1] - off);
+    const bool multi = !ONE && (r_end - r_begin) > 1;
+
+    c2b_read_rec rec; rec.winner_mask = 0; rec.best_score_milli = -1000; rec.best_ref = -1; rec.n_winners = 0;
+    rec.ambiguous = 0; rec.status = 0;
+    ColCtx cx[ONE ? 1 : RG_MAX_REFS];
+    c2b_aln_rec a; init_aln(a, 0);
+    int keep_irr = 0;
+#pragma unroll 1
+    for (int r = r_begin; r < r_end; r++) {
+        const RefDev &R = refdev(P, r);
+        const int64_t slot = oslot(P, rd, r);
+        ColCtx &c = cx[ONE ? 0 : r - r_begin];
+        const uint32_t gm = wp::ldcg(P.gmeta + slot);
+        c.ops = P.gops + slot * P.NW; c.rd = P.reads + off; c.n = (int)(gm & 0xffffu); c.J = J; c.strand = (int)((gm >> 16) & 1u);
+        uint8_t *o_read = P.strings ? P.strings + (slot * 2) * (int64_t)P.W : nullptr;
+        const ColOut co = colscan0(P, R, c, o_read, o_read ? o_read + P.W : nullptr);
+        init_aln(a, 0);
+        a.n_match = (uint16_t)co.n_match; a.aln_len = (uint16_t)c.n; a.strand = (uint8_t)c.strand;
+        a.score_milli = score_milli(co.n_match, c.n);
+        a.irregular_ends = (uint8_t)co.irregular;
+        keep_irr = co.irregular;
+        note_score(rec, R, r, a.score_milli);
+        if (lane == 0) {
+            wp::maxg(P.work_counter + 1, (unsigned long long)c.n);       // widest alignment of the launch
+            if (multi) P.alns[slot] = a;
+        }
+    }
+    if (multi) wp::sync();
+    if (rec.best_score_milli <= 0) {
+        rec.winner_mask = 0; rec.n_winners = 0;
+        if (lane == 0) { if (!multi) P.alns[oslot(P, rd, r_begin)] = a; P.recs[rd] = rec; }
+        return;
+    }
+    const bool expand = P.flags & C2B_F_EXPAND_AMBIGUOUS, first = P.flags & C2B_F_ASSIGN_FIRST;
+    const bool ambiguous = !ONE && rec.n_winners > 1 && !first && !expand;     // CRISPRessoCORE.py:780-785
+    rec.ambiguous = ambiguous;
+    const long long cnt = P.count ? P.count[rd] : 1;
+    const long long w = P.qweight ? P.qweight[rd] : cnt;
+    const bool ign_s = P.flags & C2B_F_IGNORE_SUBSTITUTIONS, ign_i = P.flags & C2B_F_IGNORE_INSERTIONS,
+               ign_d = P.flags & C2B_F_IGNORE_DELETIONS;
+    const bool two_scans = (P.flags & C2B_F_DISCARD_INDEL_READS) != 0;
+    int nth = 0;
+#pragma unroll 1
+    for (int r = r_begin; r < r_end; r++) {
+        if (!((rec.winner_mask >> (r & 31)) & 1u)) continue;
+        const RefDev &R = refdev(P, r);
+        const ColCtx &c = cx[ONE ? 0 : r - r_begin];
+        rec.best_ref = (int16_t)r;                          // best_match_name = last winner (:768)
+        RowOut o; o.ins_n = o.del_n = o.sub_n = 0; o.n_ins_all = o.n_ins_win = o.n_del_all = o.n_del_win = 0;
+        o.n_del_pos = o.n_sub_all = 0; o.nent = 0;
+        c2b_edit *ed = P.edits ? P.edits + oslot(P, rd, r) * (int64_t)P.edit_cap : nullptr;
+        const bool counted = !ambiguous && (!first || nth == 0) && w > 0;
+        // with no ignore_* flag a window indel makes the read MODIFIED, so the length vectors (:4104-4115) can be updated in
+        // the same scan; otherwise (and under --discard_indel_reads) the scalars decide first
+        const bool len_inline = counted && !two_scans && !ign_i && !ign_d;
+        colscan1(P, R, c, o, ed, w, RM_SCAL | ((counted && !two_scans) ? RM_VEC : 0) | (len_inline ? RM_LEN : 0));
+        const bool has_d = !ign_d && o.del_n > 0, has_i = !ign_i && o.ins_n > 0, has_s = !ign_s && o.sub_n > 0;
+        const bool modified = has_d || has_i || has_s;     // CRISPRessoCORE.py:746-753 (same truth table)
+        uint32_t astatus = 0;
+        if (P.edits && o.nent > P.edit_cap) astatus |= C2B_ST_EDIT_OVERFLOW;
+        unsigned long long *SC = R.scal;
+        if (counted) {
+            const bool discard = two_scans && (o.del_n > 0 || o.ins_n > 0);
+            if (discard) { if (lane == 0) sc_add(SC, C2B_S_DISCARDED, w); }
+            else {
+                const bool entered = modified || R.tem != 0;
+                const bool lenv = !len_inline && entered && (o.n_ins_win > 0 || o.n_del_win > 0);
+                if (two_scans || lenv) colscan1(P, R, c, o, nullptr, w, (two_scans ? RM_VEC : 0) | (lenv ? RM_LEN : 0));
+                if (entered) edited_update(P, R, nullptr, nullptr, o, w);      // references with a coding sequence never get here
+                if (lane == 0) {
+                    sc_add(SC, C2B_S_TOTAL, w);
+                    sc_add(SC, modified ? C2B_S_MODIFIED : C2B_S_UNMODIFIED, w);
+                }
+            }
+        } else if (ambiguous && nth == 0 && w > 0 && lane == 0) sc_add(SC, C2B_S_AMBIGUOUS_W, w);
+        if (counted && lane == 0 && (two_scans || expand)) {
+            const bool discarded = two_scans && (o.del_n > 0 || o.ins_n > 0), joined = !ONE && expand && rec.n_winners > 1;
+            if (discarded != joined) sc_add(SC, modified ? C2B_S_CLASS_MODIFIED : C2B_S_CLASS_UNMODIFIED, discarded ? w : -w);
+        }
+        int irr = keep_irr;
+        if (lane == 0) {
+            c2b_aln_rec b = multi ? load_aln(P.alns + oslot(P, rd, r)) : a;
+            b.insertion_n = (uint16_t)o.ins_n; b.deletion_n = (uint16_t)o.del_n; b.substitution_n = (uint16_t)o.sub_n;
+            b.n_ins_all = (uint16_t)o.n_ins_all; b.n_ins_win = (uint16_t)o.n_ins_win;
+            b.n_del_all = (uint16_t)o.n_del_all; b.n_del_win = (uint16_t)o.n_del_win;
+            b.n_del_pos_all = (uint16_t)o.n_del_pos; b.n_sub_all = (uint16_t)o.n_sub_all;
+            b.n_edits = (uint16_t)o.nent; b.modified = modified; b.status |= (uint8_t)astatus;
+            irr = b.irregular_ends;
+            P.alns[oslot(P, rd, r)] = b;
+        }
+        irr = wp::shfl(irr, 0);
+        rec.status |= astatus;
+        nth++;
+        // aln_stats of the serial process_fastq branch use best_match_name only (:1971-1979): the LAST winner
+        const bool is_last = (rec.winner_mask >> (r & 31)) >> 1 == 0;
+        if (is_last && lane == 0) {
+            const long long total_mods = o.n_ins_all + o.n_del_pos + o.n_sub_all;
+            const long long in_win = o.sub_n + o.del_n + o.ins_n;
+            sc_add(SC, C2B_S_N_GLOBAL_SUBS, cnt * o.n_sub_all);
+            sc_add(SC, C2B_S_N_SUBS_OUTSIDE_WINDOW, cnt * (o.n_sub_all - o.sub_n));
+            sc_add(SC, C2B_S_N_MODS_IN_WINDOW, cnt * in_win);
+            sc_add(SC, C2B_S_N_MODS_OUTSIDE_WINDOW, cnt * (total_mods - in_win));
+            if (irr) sc_add(SC, C2B_S_N_READS_IRREGULAR_ENDS, cnt);
+            sc_add(SC, C2B_S_N_ALIGNED_UNIQUE, 1);
+            sc_add(SC, C2B_S_N_ALIGNED_COUNT, cnt);
+        }
+    }
+    // HDR / prime editing: reads assigned to another reference are also classified on their alignment to reference 0
+    if (!ONE && (P.flags & C2B_F_HDR_REF1) && multi && r_begin == 0 && !ambiguous && w > 0) {
+        const uint32_t eff = first ? (rec.winner_mask & (0u - rec.winner_mask)) : rec.winner_mask;   // aln_ref_names
+        if (eff != 1u) {                                    // not "aligned to reference 0 only" (:4234)
+            const RefDev &R0 = P.refs[0];
+            RowOut dummy; dummy.ins_n = dummy.del_n = dummy.sub_n = 0; dummy.n_ins_all = dummy.n_ins_win = 0;
+            dummy.n_del_all = dummy.n_del_win = dummy.n_del_pos = dummy.n_sub_all = 0; dummy.nent = 0;
+            for (int r = 1; r < r_end; r++) {
+                if (!((eff >> (r & 31)) & 1u)) continue;
+                colscan1(P, R0, cx[0], dummy, nullptr, w, RM_REF1, P.refs[r].vec);
+                if (lane == 0) wp::addg(P.refs[r].scal + C2B_S_REF1_W, w);
+            }
+        }
+    }
+    if (lane == 0) P.recs[rd] = rec;
+}
+
+}  // namespace c2b

@@ -211,6 +211,26 @@ int  c2b_align_batch(c2b_engine *e, const uint8_t *reads, const int64_t *offsets
                      const int32_t *count, const int32_t *qweight, const int32_t *ref_id,
                      c2b_read_rec *recs, c2b_aln_rec *alns, uint8_t *strings, c2b_edit *edits);
 
+/* Compact form of c2b_align_batch: instead of the two W-byte aligned strings per (read, reference) slot the alignment itself
+ * comes back -- what Align.pyx:338-421's traceback decides, before :422-432 spell it out as strings:
+ *   ops  : n_reads * R * NW words (NW = c2b_ops_words()); column q counted from the RIGHT end of the alignment is op
+ *          (ops[slot * NW + (q >> 5)] >> 2 * (q & 31)) & 3 : 0 read base over reference base, 1 gap in the read (deletion),
+ *          2 gap in the reference (insertion), 3 past the alignment's left end
+ *   meta : n_reads * R words: bits 0-15 alignment columns, bit 16 strand ('-' = the read was aligned as its reverse
+ *          complement), bits 24-31 non-zero when the slot holds an alignment
+ * c2b_expand_alignment / c2b_expand_batch rebuild the strings on the host (bit-identical to c2b_align_batch's); 5 to 8 times
+ * fewer bytes cross PCIe.                                                           */
+int  c2b_align_batch_compact(c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads,
+                             const int32_t *count, const int32_t *qweight, const int32_t *ref_id,
+                             c2b_read_rec *recs, c2b_aln_rec *alns, uint64_t *ops, uint32_t *meta, c2b_edit *edits);
+int  c2b_ops_words(const c2b_engine *e, int32_t max_read_len);
+/* out_read / out_ref receive (meta & 0xffff) characters each, left to right as global_align returns them (Align.pyx:422-434) */
+int  c2b_expand_alignment(const c2b_engine *e, const uint64_t *ops, uint32_t meta, const char *read, int32_t read_len,
+                          const char *ref, int32_t ref_len, char *out_read, char *out_ref);
+/* strings: n_reads * R * 2 * W bytes, right-aligned slots as c2b_align_batch writes them; host threads (n_threads <= 0: all) */
+int  c2b_expand_batch(const c2b_engine *e, const uint8_t *reads, const int64_t *offsets, int64_t n_reads, const int32_t *ref_id,
+                      const uint64_t *ops, const uint32_t *meta, int32_t max_read_len, uint8_t *strings, int32_t n_threads);
+
 /* Same, with every pointer a DEVICE pointer on the engine's device and no copies; the launch is queued on
  * the engine's stream.  max_read_len must bound the reads.  Use c2b_sync() before reading results.     */
 int  c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t *d_offsets, int64_t n_reads,
@@ -222,6 +242,8 @@ int  c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t
  * use the packed two-reads-per-warp path.  Results are always written at the reads' own indices.  c2b_align_batch
  * builds this order itself. */
 int  c2b_set_pair_order(c2b_engine *e, const int32_t *d_order);
+/* op streams / meta words (layout of c2b_align_batch_compact) of the last c2b_align_batch_device call, device pointers */
+int  c2b_ops_device(c2b_engine *e, void **d_ops, void **d_meta);
 int  c2b_sync(c2b_engine *e);
 void *c2b_stream(c2b_engine *e);                    /* cudaStream_t of the engine */
 double c2b_last_kernel_ms(c2b_engine *e);           /* CUDA-event time of the last align kernel launch */

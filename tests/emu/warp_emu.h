@@ -117,4 +117,5 @@ C2B_DEV void addg(unsigned long long *p, long long v) { *p += (unsigned long lon
 C2B_DEV void maxg(unsigned long long *p, unsigned long long v) { if (v > *p) *p = v; }
 C2B_DEV uint32_t adds(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
 C2B_DEV unsigned long long fetch_work(unsigned long long *p) { return (*p)++; }
+C2B_DEV unsigned long long fetch_add(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }
 }  // namespace wp

@@ -214,9 +214,8 @@ def test_packed_pair_path_equals_32bit_path(eng):
     W = a.W
     cols = np.arange(W)[None, :] >= (W - a.alns[:, 0]["aln_len"].astype(np.int64))[:, None]
     assert ((a.strings[:, 0] == b.strings[:, 0]) | ~cols[:, None, :]).all()
-    ne = a.alns[:, 0]["n_edits"].astype(np.int64)
-    valid = np.arange(24)[None, :] < np.minimum(ne, 24)[:, None]
-    assert ((a.edits[:, 0] == b.edits[:, 0]) | ~valid).all()
+    (ea, fa), (eb, fb) = PU.edits_canonical(a), PU.edits_canonical(b)
+    assert (fa == fb).all() and (ea[fa] == eb[fb]).all()
 
 
 @pytest.mark.parametrize("I", [250, 256, 131, 64])
@@ -254,10 +253,9 @@ def test_coding_seq_frameshift_splicing_and_size_histograms(eng):
 
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("mixed", [False, True])
-def test_streamed_launch_equals_chunked_launches(eng, monkeypatch, mixed):
-    """Host-buffer batches of >= 64 Ki reads go through one persistent launch fed chunk by chunk (read bytes arrive while
-    the kernel runs, finished chunks leave while it runs; C2B_STREAMED=1); C2B_STREAMED=0 is the launch-per-chunk pipeline.  Same
-    records, alignments, strings, edit lists and count block."""
+def test_split_kernels_equal_general_kernel_and_chunking(eng, monkeypatch, mixed):
+    """The two-kernel form (ALIGN + CLASSIFY + general kernel over the left-overs, chunks of 128 Ki reads) against the general
+    kernel alone (C2B_NO_SPLIT=1) with a different chunking: same records, strings, edit lists and count block."""
     rng = np.random.default_rng(12)
     amp = synth.random_amplicon(rng, 250)
     ref = synth.amplicon_setup(amp)
@@ -273,22 +271,24 @@ def test_streamed_launch_equals_chunked_launches(eng, monkeypatch, mixed):
     buf = reads[np.arange(250)[None, :] < lens[:, None]]
     cnt = rng.integers(1, 4, size=n).astype(np.int32)
     out = []
-    for streamed in ("1", "0"):
-        monkeypatch.setenv("C2B_STREAMED", streamed)
+    for mode in ("split", "general"):
+        if mode == "general":
+            monkeypatch.setenv("C2B_NO_SPLIT", "1")
+            monkeypatch.setenv("C2B_CHUNK", "40000")
         eng.configure({"Reference": ref}, ["Reference"], O.make_matrix(), -20, -2, 5, 2, 0, "ACGTN", 8)
         eng.counts_reset()
         res = eng.align_packed(buf, off, count=cnt, qweight=cnt)
         out.append((res, eng.counts_raw()))
-    monkeypatch.delenv("C2B_STREAMED", raising=False)
+    monkeypatch.delenv("C2B_NO_SPLIT", raising=False)
+    monkeypatch.delenv("C2B_CHUNK", raising=False)
     (a, ca), (b, cb) = out
     assert (a.recs == b.recs).all() and (a.alns == b.alns).all() and (ca == cb).all()
     assert (a.recs["best_score_milli"] > 0).mean() > 0.9
     W = a.W
     valid = (np.arange(W)[None, :] >= (W - a.alns[:, 0]["aln_len"].astype(np.int64))[:, None])[:, None, None, :]
     assert ((a.strings == b.strings) | ~valid).all()
-    ne = a.alns[:, 0]["n_edits"].astype(np.int64)
-    slot = np.arange(a.edits.shape[2])[None, :] < np.minimum(ne, a.edits.shape[2])[:, None]
-    assert (a.edits[:, 0][slot] == b.edits[:, 0][slot]).all()
+    (ea, fa), (eb, fb) = PU.edits_canonical(a), PU.edits_canonical(b)
+    assert (fa == fb).all() and (ea[fa] == eb[fb]).all()
 
 
 def test_random_configurations_against_oracle(eng):
