@@ -119,7 +119,8 @@ class _BatchLists:
             self.alns = r.alns[self.lo:self.hi].tolist()     # [read][ref] -> ALN_DTYPE field order
             self.edits = r.edits[self.lo:self.hi].tolist() if r.edits is not None else None
             # one decode per block; bytes left of an alignment are undefined, hence latin-1 (never fails, 1 char per byte)
-            self.text = r.strings[self.lo:self.hi].tobytes().decode("latin-1") if r.strings is not None else None
+            self.text = (r.strings_block(self.lo, self.hi).tobytes().decode("latin-1")
+                         if (r.strings is not None or r.ops is not None) else None)
         return i - self.lo
 
     def pair(self, i, r, n):
@@ -179,12 +180,12 @@ def _variant_from(res, i, seq, ref_names, refs):
         v["variant_" + name] = p
         v["best_match_name"] = name
     v["class_name"] = "&".join(labels)
-    if len(winners) > 1:
-        if ambiguous:
-            v["class_name"] = "AMBIGUOUS"
-        elif len(labels) > 1 and not (res_flags(res) & _lib.F_EXPAND_AMBIGUOUS):
+    if len(winners) > 1:                                     # CRISPRessoCORE.py:780-785: assign-first is tested first
+        if res_flags(res) & _lib.F_ASSIGN_FIRST:
             v["class_name"] = labels[0]
             v["aln_ref_names"] = [ref_names[winners[0]]]
+        elif not (res_flags(res) & _lib.F_EXPAND_AMBIGUOUS):
+            v["class_name"] = "AMBIGUOUS"
     return v
 
 
@@ -192,23 +193,147 @@ def res_flags(res):
     return getattr(res, "flags", 0)
 
 
-def align_uniques(engine, uniques, counts, ref_names, refs, flags, weights=None, packed=None):
+def merge_weights_packed(buf, off, counts, member=None, lib_path=None):
+    """merge_weights for packed unique reads, natively (c2b_rc_merge_weights: host threads, exact)."""
+    L = _lib.load(lib_path)
+    n = len(off) - 1
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    w = np.zeros(n, dtype=np.int32)
+    mem = None if member is None else np.ascontiguousarray(member, dtype=np.uint8)
+    rc = L.c2b_rc_merge_weights(buf.ctypes.data if len(buf) else None, off.ctypes.data, n, counts.ctypes.data,
+                                mem.ctypes.data if mem is not None else None, w.ctypes.data, 0)
+    if rc != 0:
+        raise EngineError("c2b_rc_merge_weights failed (%d)" % rc)
+    return w
+
+
+_OK_SYMBOL = np.zeros(256, dtype=bool)
+_OK_SYMBOL[list(b"ACGTN")] = True
+
+
+def screen_reads(buf, off):
+    """-> bool mask of unique reads outside the engine's contract: empty, longer than MAX_READ_LEN, or holding a symbol
+    other than A C G T N (lower case and IUPAC codes included: the reference indexes its score table with them -- lower case
+    out of bounds, Align.pyx:212 -- and its quantification loop raises KeyError on them at CRISPRessoCORE.py:4081)."""
+    lens = np.diff(off)
+    bad = (lens < 1) | (lens > _lib.MAX_READ_LEN)
+    odd = np.nonzero(~_OK_SYMBOL[buf])[0]
+    if len(odd):
+        bad[np.unique(np.searchsorted(off, odd, side="right") - 1)] = True
+    return bad
+
+
+def align_uniques(engine, uniques, counts, ref_names, refs, flags, weights=None, packed=None, compact=False):
     """One GPU batch over unique reads -> (BatchResult, merge weights).  `packed` = (bytes, offsets) of `uniques`
     when the caller already holds them in the engine's layout."""
-    weights = merge_weights(uniques, counts) if weights is None else weights
     buf, off = packed if packed is not None else pack_reads(uniques)
-    res = engine.align_packed(buf, off, count=np.asarray(counts, dtype=np.int32), qweight=np.asarray(weights, dtype=np.int32))
+    if weights is None:
+        weights = merge_weights_packed(buf, off, counts, lib_path=engine.lib_path)
+    res = engine.align_packed(buf, off, count=np.asarray(counts, dtype=np.int32), qweight=np.asarray(weights, dtype=np.int32),
+                              compact=compact)
     res.flags = flags
     st = res.recs["status"]
     hard = st & ~np.uint32(_lib.ST_EDIT_OVERFLOW)
     if hard.any():
         k = int(np.nonzero(hard)[0][0])
-        raise EngineError("read %d (%r...) outside the engine's contract: status %d" % (k, uniques[k][:30], int(st[k])))
+        raise EngineError("read %d outside the engine's contract: status %d" % (k, int(st[k])))
     return res, weights
 
 
+def _complete_edit_lists(engine, res, buf, off, flags, ref_id=None):
+    """Reads whose edit list overflowed the batch's cap: their counts are already in the block (only the LIST was
+    truncated), so they are re-run with zero weights and a cap sized from the largest list, in slices of bounded memory.
+    -> {read index: (BatchResult, index)}"""
+    over = np.nonzero(res.recs["status"] & _lib.ST_EDIT_OVERFLOW)[0]
+    if not len(over):
+        return {}
+    cap0 = engine.edit_cap
+    need = int(res.alns["n_edits"][over].max())
+    engine.set_edit_cap(need)
+    fix = {}
+    nr = res.alns.shape[1]
+    step = max(1, (256 << 20) // max(1, nr * need * 8))
+    try:
+        for a in range(0, len(over), step):
+            idx = over[a:a + step]
+            lens = (off[idx + 1] - off[idx]).astype(np.int64)
+            o2 = np.zeros(len(idx) + 1, dtype=np.int64)
+            np.cumsum(lens, out=o2[1:])
+            b2 = np.concatenate([buf[off[k]:off[k + 1]] for k in idx]) if len(idx) else np.zeros(0, np.uint8)
+            zero = np.zeros(len(idx), dtype=np.int32)
+            r2 = engine.align_packed(b2, o2, count=zero, qweight=zero, ref_id=None if ref_id is None else ref_id[idx], compact=True)
+            r2.flags = flags
+            for j, k in enumerate(idx.tolist()):
+                fix[k] = (r2, j)
+    finally:
+        engine.set_edit_cap(cap0)
+    return fix
+
+
+_STAT_KEYS = ["N_TOT_READS", "N_CACHED_ALN", "N_CACHED_NOTALN", "N_COMPUTED_ALN", "N_COMPUTED_NOTALN", "N_GLOBAL_SUBS",
+              "N_SUBS_OUTSIDE_WINDOW", "N_MODS_IN_WINDOW", "N_MODS_OUTSIDE_WINDOW", "N_READS_IRREGULAR_ENDS", "READ_LENGTH"]
+
+
+def _serial_stats(res, counts, n_extra_notaln=0, extra_count=0):
+    """aln_stats of the serial branch (CRISPRessoCORE.py:1956-1999) from the per-read records, vectorised: the statistics of
+    an aligned unique read are those of its best_match_name (the LAST winner)."""
+    c = np.asarray(counts, dtype=np.int64)
+    aligned = res.recs["best_score_milli"] > 0
+    st = dict.fromkeys(_STAT_KEYS, 0)
+    st["N_TOT_READS"] = int(c.sum()) + int(extra_count)
+    st["N_COMPUTED_ALN"] = int(aligned.sum())
+    st["N_CACHED_ALN"] = int((c[aligned] - 1).sum())
+    st["N_COMPUTED_NOTALN"] = int((~aligned).sum()) + int(n_extra_notaln)
+    st["N_CACHED_NOTALN"] = int((c[~aligned] - 1).sum()) + int(extra_count) - int(n_extra_notaln)
+    if aligned.any():
+        idx = np.nonzero(aligned)[0]
+        col = res.recs["best_ref"][idx].astype(np.int64) if res.alns.shape[1] > 1 else np.zeros(len(idx), dtype=np.int64)
+        a = res.alns[idx, col]
+        ca = c[idx]
+        n_sub_all, sub_n = a["n_sub_all"].astype(np.int64), a["substitution_n"].astype(np.int64)
+        in_win = sub_n + a["deletion_n"].astype(np.int64) + a["insertion_n"].astype(np.int64)
+        total = a["n_ins_all"].astype(np.int64) + a["n_del_pos_all"].astype(np.int64) + n_sub_all
+        st["N_GLOBAL_SUBS"] = int((n_sub_all * ca).sum())
+        st["N_SUBS_OUTSIDE_WINDOW"] = int(((n_sub_all - sub_n) * ca).sum())
+        st["N_MODS_IN_WINDOW"] = int((in_win * ca).sum())
+        st["N_MODS_OUTSIDE_WINDOW"] = int(((total - in_win) * ca).sum())
+        st["N_READS_IRREGULAR_ENDS"] = int((ca * (a["irregular_ends"] != 0)).sum())
+        st["READ_LENGTH"] = int(a["aln_len"][0])
+    return st, aligned
+
+
+def _joined_classes(res, weights, ref_names, flags):
+    """class_counts entries of reads with several best references under --expand_ambiguous_alignments: their label is the
+    '&'-joined list of '<ref>_<classification>' (CRISPRessoCORE.py:762-785), grouped here by (winner set, classifications)."""
+    if not (flags & _lib.F_EXPAND_AMBIGUOUS) or (flags & _lib.F_ASSIGN_FIRST) or res.alns.shape[1] < 2:
+        return {}
+    w = np.asarray(weights, dtype=np.int64)
+    pick = np.nonzero((res.recs["n_winners"] > 1) & (res.recs["best_score_milli"] > 0) & (w > 0))[0]
+    out = {}
+    if not len(pick):
+        return out
+    mask = res.recs["winner_mask"][pick].astype(np.int64)
+    mod = np.zeros(len(pick), dtype=np.int64)
+    for r in range(res.alns.shape[1]):
+        mod |= (res.alns[pick, r]["modified"].astype(np.int64) != 0).astype(np.int64) << r
+    key = mask | ((mod & mask) << 32)
+    for kv in np.unique(key):
+        m, md = int(kv) & 0xffffffff, int(kv) >> 32
+        label = "&".join(ref_names[r] + ("_MODIFIED" if (md >> r) & 1 else "_UNMODIFIED") for r in range(len(ref_names)) if (m >> r) & 1)
+        out[label] = int(w[pick][key == kv].sum())
+    return out
+
+
 def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory,
-                  engine=None, aln_matrix=None):
+                  engine=None, aln_matrix=None, on_out_of_contract="not_aligned"):
+    """Drop-in for CRISPRessoCORE.process_fastq (:1735-2000).  The per-unique-read dicts are LazyVariant objects (lazy.py):
+    nothing per read is built in Python until somebody reads it.
+    on_out_of_contract: what to do with unique reads the engine cannot take (empty, > 512 bp, symbols outside ACGTN):
+    "not_aligned" (default) files them under not_aligned_variants with best_match_score -1 and logs their number; "error"
+    raises EngineError before anything is launched."""
+    from . import lazy
     _unsupported(args)
     if aln_matrix is None:
         loc = args.needleman_wunsch_aln_matrix_loc
@@ -219,163 +344,165 @@ def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_
     # FASTQ read + dedup of CRISPRessoCORE.py:1820-1849, done natively (c2b_fastq_dedup: threads, exact); the packed
     # unique sequences feed the batch call directly
     dd = fastq.dedup_file(fastq_filename, lib_path=engine.lib_path)
-    packed = None
     if not variantCache:
-        variantCache.update(zip(dd.uniques, dd.counts.tolist()))
-        packed = (dd.buf, dd.off)
+        buf, off, counts = dd.buf, dd.off, dd.counts
+        keys = lazy.make_keys(buf, off)
     else:                                                   # caller pre-seeded the cache: same += semantics, same key order
         for seq, c in zip(dd.uniques, dd.counts.tolist()):
             variantCache[seq] = variantCache.get(seq, 0) + c
+        keys = list(variantCache.keys())
+        counts = np.asarray([variantCache[s] for s in keys], dtype=np.int32)
+        buf, off = pack_reads([s.encode("utf-8", errors="surrogateescape") for s in keys])
+    return _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, refs, args, aln_matrix, on_out_of_contract)
+
+
+def _result_arrays(res):
+    return {"recs": res.recs, "alns": res.alns, "ops": res.ops, "meta": res.meta, "edits": res.edits, "W": res.W,
+            "buf": res._buf, "off": res._off}
+
+
+def _result_from(engine, d, flags):
+    from .engine import BatchResult
+    r = BatchResult(d["recs"], d["alns"], None, d["edits"], d["W"], ops=d["ops"], meta=d["meta"], engine=engine, buf=d["buf"], off=d["off"])
+    r.flags = flags
+    return r
+
+
+def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, refs, args, aln_matrix, on_out_of_contract,
+                     group=None):
+    """The batch over the unique reads and everything after it.  With a torch.distributed `group` (one process per GPU) every
+    rank aligns its contiguous slice of the unique reads (the reference's own sharding rule, CRISPRessoCORE.py:1172-1195), the
+    count blocks meet in ONE all-reduce, the compact per-read results are gathered, and every rank ends with what the
+    single-process call produces."""
+    from . import lazy
+    import logging
+    n = len(keys)
+    flags = _flags(args)
     configure_engine(engine, args, refs, ref_names, aln_matrix)
     engine.counts_reset()
-    uniques = list(variantCache.keys())
-    counts = [variantCache[s] for s in uniques]
-    flags = _flags(args)
-    res, weights = align_uniques(engine, uniques, counts, ref_names, refs, flags, packed=packed)
-    over = np.nonzero(res.recs["status"] & _lib.ST_EDIT_OVERFLOW)[0]
-    fix = {}
-    if len(over):
-        # their counts are already in the block (only the edit LIST was truncated): re-run them with a cap that cannot
-        # overflow and zero weights, just to fetch the complete lists
-        cap0 = engine.edit_cap
-        engine.set_edit_cap(max(engine.ref_lens) + _lib.MAX_READ_LEN)
-        sub = [uniques[k] for k in over]
-        zero = np.zeros(len(sub), dtype=np.int32)
-        r2 = engine.align(sub, count=zero, qweight=zero)
-        r2.flags = flags
-        engine.set_edit_cap(cap0)
-        fix = {int(k): (r2, j) for j, k in enumerate(over)}
-
-    st = dict.fromkeys(["N_TOT_READS", "N_CACHED_ALN", "N_CACHED_NOTALN", "N_COMPUTED_ALN", "N_COMPUTED_NOTALN",
-                        "N_GLOBAL_SUBS", "N_SUBS_OUTSIDE_WINDOW", "N_MODS_IN_WINDOW", "N_MODS_OUTSIDE_WINDOW",
-                        "N_READS_IRREGULAR_ENDS", "READ_LENGTH"], 0)
+    bad = screen_reads(buf, off) if n else np.zeros(0, dtype=bool)
+    n_bad = int(bad.sum())
+    if n_bad:
+        k = int(np.nonzero(bad)[0][0])
+        msg = ("%d unique read(s) (%d reads) are outside the engine's contract (empty, longer than %d bp, or symbols other than "
+               "ACGTN), first: %r" % (n_bad, int(counts[bad].sum()), _lib.MAX_READ_LEN, keys[k][:40]))
+        if on_out_of_contract == "error":
+            raise EngineError(msg)
+        logging.getLogger("CRISPResso2").warning("crispresso2_b200: %s -- filed under not-aligned reads", msg)
+        good = np.nonzero(~bad)[0]
+        lens = (off[good + 1] - off[good]).astype(np.int64)
+        o2 = np.zeros(len(good) + 1, dtype=np.int64)
+        np.cumsum(lens, out=o2[1:])
+        keep = np.repeat(~bad, np.diff(off))
+        buf_g, off_g, counts_g = buf[keep], o2, np.ascontiguousarray(counts[good])
+        keys_g = [keys[k] for k in good.tolist()]
+    else:
+        buf_g, off_g, counts_g, keys_g = buf, off, counts, keys
+    ng = len(keys_g)
+    weights = merge_weights_packed(buf_g, off_g, counts_g, lib_path=engine.lib_path)     # needs the global unique table: before sharding
+    if group is None:
+        res, _ = align_uniques(engine, None, counts_g, ref_names, refs, flags, weights=weights, packed=(buf_g, off_g), compact=True)
+        parts = [(0, res, _complete_edit_lists(engine, res, buf_g, off_g, flags))]
+        raw = None
+    else:
+        import torch.distributed as dist
+        from . import dist as cdist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        lo, hi = cdist.shard_bounds(ng, rank, world)
+        mine = None
+        if hi > lo:
+            b0, b1 = int(off_g[lo]), int(off_g[hi])
+            sb, so = np.ascontiguousarray(buf_g[b0:b1]), np.ascontiguousarray(off_g[lo:hi + 1] - b0)
+            res, _ = align_uniques(engine, None, counts_g[lo:hi], ref_names, refs, flags, weights=weights[lo:hi], packed=(sb, so), compact=True)
+            fix = _complete_edit_lists(engine, res, sb, so, flags)
+            mine = {"lo": lo, "res": _result_arrays(res), "fix": {k: (_result_arrays(r2), j) for k, (r2, j) in fix.items()}}
+        raw = cdist.allreduce_counts(engine, group)          # the path's one collective on device data
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        parts = []
+        for g in gathered:
+            if g is None:
+                continue
+            cache_r2 = {}
+            fx = {}
+            for k, (d, j) in g["fix"].items():
+                if id(d) not in cache_r2:
+                    cache_r2[id(d)] = _result_from(engine, d, flags)
+                fx[k] = (cache_r2[id(d)], j)
+            parts.append((g["lo"], _result_from(engine, g["res"], flags), fx))
+    # serial-branch statistics, part by part (rank order = unique order)
+    st = dict.fromkeys(_STAT_KEYS, 0)
+    aligned = np.zeros(ng, dtype=bool)
+    extra = {}
+    for lo, res, _fx in parts:
+        hi = lo + len(res.recs)
+        s1, al = _serial_stats(res, counts_g[lo:hi])
+        aligned[lo:hi] = al
+        for key, val in s1.items():
+            if key == "READ_LENGTH":
+                st[key] = st[key] or val
+            else:
+                st[key] += val
+        for lab, val in _joined_classes(res, weights[lo:hi], ref_names, flags).items():
+            extra[lab] = extra.get(lab, 0) + val
+    if n_bad:
+        cb = int(counts[bad].sum())
+        st["N_TOT_READS"] += cb
+        st["N_COMPUTED_NOTALN"] += n_bad
+        st["N_CACHED_NOTALN"] += cb - n_bad
+    src = lazy.BatchSource(None, keys_g, ref_names, refs, parts=parts)
+    cls = src.lazy_class()
     not_aligned = {}
-    class_extra = {}
-    for k, seq in enumerate(uniques):                       # CRISPRessoCORE.py:1956-1981
-        c = counts[k]
-        st["N_TOT_READS"] += c
-        rr, kk = fix.get(k, (res, k))
-        v = _variant_from(rr, kk, seq, ref_names, refs)
-        v["count"] = c
-        if v["best_match_score"] <= 0:
-            st["N_COMPUTED_NOTALN"] += 1
-            st["N_CACHED_NOTALN"] += c - 1
-            not_aligned[seq] = v
-            continue
-        variantCache[seq] = v
-        if "&" in v["class_name"] and weights[k] > 0:       # joined labels (--expand_ambiguous_alignments): host-side class count
-            class_extra[v["class_name"]] = class_extra.get(v["class_name"], 0) + int(weights[k])
-        st["N_COMPUTED_ALN"] += 1
-        st["N_CACHED_ALN"] += c - 1
-        p = v["variant_" + v["best_match_name"]]
-        if st["READ_LENGTH"] == 0:
-            st["READ_LENGTH"] = len(p["aln_seq"])
-        st["N_GLOBAL_SUBS"] += (p["substitution_n"] + p["substitutions_outside_window"]) * c
-        st["N_SUBS_OUTSIDE_WINDOW"] += p["substitutions_outside_window"] * c
-        st["N_MODS_IN_WINDOW"] += p["mods_in_window"] * c
-        st["N_MODS_OUTSIDE_WINDOW"] += p["mods_outside_window"] * c
-        if p["irregular_ends"]:
-            st["N_READS_IRREGULAR_ENDS"] += c
+    sel = aligned.astype(np.uint8)
+    lazy.fill_cache(variantCache, keys_g, sel, counts_g, cls, 1)          # pre-seeded cache: counts replaced in place, order kept
+    lazy.fill_cache(not_aligned, keys_g, sel, counts_g, cls, 0)
     for seq in not_aligned:
-        del variantCache[seq]
-    block = engine.counts()
+        variantCache.pop(seq, None)
+    if n_bad:
+        for k in np.nonzero(bad)[0].tolist():
+            not_aligned[keys[k]] = {"count": int(counts[k]), "aln_scores": [], "ref_aln_details": [], "best_match_score": -1}
+            variantCache.pop(keys[k], None)
+    block = engine.counts(raw=raw)
     dev = block.aln_stats_partial()                         # the kernel's own sums must agree with the records
     for key, val in dev.items():
         if val != st[key]:
             raise EngineError("device aln_stats disagree with per-read records for %s: %d != %d" % (key, val, st[key]))
-    block.class_extra = class_extra
+    block.class_extra = extra
     _blocks[id(variantCache)] = block
     return st, not_aligned
 
 
 def process_fastq_sharded(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory,
-                          engine=None, aln_matrix=None, group=None):
-    """process_fastq for one process per GPU (torch.distributed initialised): every rank reads and de-duplicates the FASTQ,
-    aligns its contiguous slice of the unique reads (the reference's own sharding rule, CRISPRessoCORE.py:1172-1195), then
-    the count blocks are summed with ONE all-reduce (NCCL on the device block; gloo on the CPU test path) and the per-read
-    variants and statistics are gathered, so that every rank returns exactly what the single-process call returns --
-    same variantCache (keys in first-seen order), same aln_stats, same count block behind quantify()."""
+                          engine=None, aln_matrix=None, group=None, on_out_of_contract="not_aligned"):
+    """process_fastq for one process per GPU (torch.distributed initialised): same arguments, same results on every rank.
+    Without an explicit engine the rank uses the GPU named by LOCAL_RANK (torchrun) -- never all ranks on device 0."""
     import torch.distributed as dist
-    from . import dist as cdist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory,
-                             engine=engine, aln_matrix=aln_matrix)
+                             engine=engine, aln_matrix=aln_matrix, on_out_of_contract=on_out_of_contract)
+    from . import lazy
     _unsupported(args)
     if aln_matrix is None:
         aln_matrix = read_matrix(args.needleman_wunsch_aln_matrix_loc)
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    engine = engine or get_engine()
+    if engine is None:
+        dev = int(os.environ.get("LOCAL_RANK", "0"))
+        if dist.get_backend(group) == "nccl":
+            import torch
+            torch.cuda.set_device(dev)
+        engine = get_engine(dev)
     dd = fastq.dedup_file(fastq_filename, lib_path=engine.lib_path)
-    for seq, c in zip(dd.uniques, dd.counts.tolist()):
-        variantCache[seq] = variantCache.get(seq, 0) + c
-    configure_engine(engine, args, refs, ref_names, aln_matrix)
-    engine.counts_reset()
-    uniques = list(variantCache.keys())
-    counts = [variantCache[s] for s in uniques]
-    flags = _flags(args)
-    weights = merge_weights(uniques, counts)                # needs the global unique table: before sharding
-    lo, hi = cdist.shard_bounds(len(uniques), rank, world)
-    mine = uniques[lo:hi]
-    local = []                                              # (variant or None) per unique of this shard
-    if mine:
-        res, _ = align_uniques(engine, mine, counts[lo:hi], ref_names, refs, flags, weights=weights[lo:hi])
-        over = np.nonzero(res.recs["status"] & _lib.ST_EDIT_OVERFLOW)[0]
-        fix = {}
-        if len(over):
-            cap0 = engine.edit_cap
-            engine.set_edit_cap(max(engine.ref_lens) + _lib.MAX_READ_LEN)
-            zero = np.zeros(len(over), dtype=np.int32)
-            r2 = engine.align([mine[k] for k in over], count=zero, qweight=zero)
-            r2.flags = flags
-            engine.set_edit_cap(cap0)
-            fix = {int(k): (r2, j) for j, k in enumerate(over)}
-        for k, seq in enumerate(mine):
-            rr, kk = fix.get(k, (res, k))
-            v = _variant_from(rr, kk, seq, ref_names, refs)
-            v["count"] = counts[lo + k]
-            local.append(v)
-    merged = cdist.allreduce_counts(engine, group)          # the path's one collective on device data
-    parts = [None] * world
-    dist.all_gather_object(parts, local, group=group)
-    st = dict.fromkeys(["N_TOT_READS", "N_CACHED_ALN", "N_CACHED_NOTALN", "N_COMPUTED_ALN", "N_COMPUTED_NOTALN",
-                        "N_GLOBAL_SUBS", "N_SUBS_OUTSIDE_WINDOW", "N_MODS_IN_WINDOW", "N_MODS_OUTSIDE_WINDOW",
-                        "N_READS_IRREGULAR_ENDS", "READ_LENGTH"], 0)
-    not_aligned, class_extra = {}, {}
-    k = 0
-    for part in parts:                                      # rank order = unique order: the serial loop of :1956-1981
-        for v in part:
-            seq, c = uniques[k], counts[k]
-            st["N_TOT_READS"] += c
-            if v["best_match_score"] <= 0:
-                st["N_COMPUTED_NOTALN"] += 1
-                st["N_CACHED_NOTALN"] += c - 1
-                not_aligned[seq] = v
-            else:
-                variantCache[seq] = v
-                if "&" in v["class_name"] and weights[k] > 0:
-                    class_extra[v["class_name"]] = class_extra.get(v["class_name"], 0) + int(weights[k])
-                st["N_COMPUTED_ALN"] += 1
-                st["N_CACHED_ALN"] += c - 1
-                p = v["variant_" + v["best_match_name"]]
-                if st["READ_LENGTH"] == 0:
-                    st["READ_LENGTH"] = len(p["aln_seq"])
-                st["N_GLOBAL_SUBS"] += (p["substitution_n"] + p["substitutions_outside_window"]) * c
-                st["N_SUBS_OUTSIDE_WINDOW"] += p["substitutions_outside_window"] * c
-                st["N_MODS_IN_WINDOW"] += p["mods_in_window"] * c
-                st["N_MODS_OUTSIDE_WINDOW"] += p["mods_outside_window"] * c
-                if p["irregular_ends"]:
-                    st["N_READS_IRREGULAR_ENDS"] += c
-            k += 1
-    assert k == len(uniques)
-    for seq in not_aligned:
-        del variantCache[seq]
-    block = engine.counts(raw=merged)
-    for key, val in block.aln_stats_partial().items():
-        if val != st[key]:
-            raise EngineError("device aln_stats disagree with per-read records for %s: %d != %d" % (key, val, st[key]))
-    block.class_extra = class_extra
-    _blocks[id(variantCache)] = block
-    return st, not_aligned
+    if not variantCache:
+        buf, off, counts = dd.buf, dd.off, dd.counts
+        keys = lazy.make_keys(buf, off)
+    else:
+        for seq, c in zip(dd.uniques, dd.counts.tolist()):
+            variantCache[seq] = variantCache.get(seq, 0) + c
+        keys = list(variantCache.keys())
+        counts = np.asarray([variantCache[s] for s in keys], dtype=np.int32)
+        buf, off = pack_reads([s.encode("utf-8", errors="surrogateescape") for s in keys])
+    world_group = group if group is not None else dist.group.WORLD
+    return _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, refs, args, aln_matrix, on_out_of_contract,
+                            group=world_group)
 
 
 def quantify(variantCache):

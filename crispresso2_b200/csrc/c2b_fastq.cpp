@@ -27,6 +27,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <functional>
 #include <vector>
 
 namespace {
@@ -420,4 +421,64 @@ extern "C" int c2b_fastq_filter(const char *path_in, const char *path_out, int32
     if (n_in) *n_in = n_rec;
     if (n_out) *n_out = tot;
     return C2B_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------ reverse-complement merge
+// replaces: the count transfer at the head of the quantification loop (CRISPRessoCORE.py:3964-3975): walking the unique
+// reads in first-seen order, a read with a non-zero count absorbs the count of its reverse complement (CRISPRessoShared.py:
+// 399-403: upper-cased, A<->T, C<->G, N, '_', '-' kept), whose count drops to 0; a palindromic read absorbs itself (its
+// count doubles, as in the reference).  Reads holding any other symbol are left alone (the reference raises KeyError there).
+// `member` (optional, one byte per read): only reads with member != 0 are in the cache (the aligned ones, :1983-1985).
+// Hashing and the partner search run on host threads; the sweep that applies the rule is serial (it is order-dependent).
+extern "C" int c2b_rc_merge_weights(const uint8_t *seqs, const int64_t *offsets, int64_t n, const int32_t *counts,
+                                    const uint8_t *member, int32_t *weights, int32_t n_threads)
+{
+    if (!offsets || !counts || !weights || n < 0 || (n && !seqs)) return -2;
+    int T = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    T = (int)std::min<int64_t>(T, std::max<int64_t>(1, n / 4096));
+    size_t cap = 16;
+    while (cap < (size_t)n * 2 + 16) cap <<= 1;
+    std::vector<int64_t> table(cap, -1), partner((size_t)n, -1);
+    std::vector<uint64_t> hv((size_t)n);
+    auto run = [&](const std::function<void(int64_t, int64_t)> &fn) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(fn, n * t / T, n * (t + 1) / T);
+        fn(0, n / T);
+        for (auto &x : th) x.join();
+    };
+    run([&](int64_t lo, int64_t hi) { for (int64_t k = lo; k < hi; k++) hv[(size_t)k] = hash_bytes(seqs + offsets[k], (size_t)(offsets[k + 1] - offsets[k])); });
+    for (int64_t k = 0; k < n; k++) {                       // unique reads: every key is new
+        if (member && !member[k]) continue;
+        size_t h = (size_t)hv[(size_t)k] & (cap - 1);
+        while (table[h] >= 0) h = (h + 1) & (cap - 1);
+        table[h] = k;
+    }
+    static const struct Comp { uint8_t t[256]; Comp() { memset(t, 0, sizeof t); const char *a = "ACGTN_-acgtn", *b = "TGCAN_-TGCAN"; for (int i = 0; a[i]; i++) t[(uint8_t)a[i]] = (uint8_t)b[i]; } } comp;
+    run([&](int64_t lo, int64_t hi) {
+        std::vector<uint8_t> rc;
+        for (int64_t k = lo; k < hi; k++) {
+            if (member && !member[k]) continue;
+            const uint8_t *p = seqs + offsets[k];
+            const size_t L = (size_t)(offsets[k + 1] - offsets[k]);
+            rc.resize(L);
+            bool ok = true;
+            for (size_t i = 0; i < L; i++) { const uint8_t c = comp.t[p[L - 1 - i]]; if (!c) { ok = false; break; } rc[i] = c; }
+            if (!ok) continue;
+            const uint64_t hh = hash_bytes(rc.data(), L);
+            size_t h = (size_t)hh & (cap - 1);
+            while (table[h] >= 0) {
+                const int64_t j = table[h];
+                if (hv[(size_t)j] == hh && (size_t)(offsets[j + 1] - offsets[j]) == L && memcmp(seqs + offsets[j], rc.data(), L) == 0) { partner[(size_t)k] = j; break; }
+                h = (h + 1) & (cap - 1);
+            }
+        }
+    });
+    for (int64_t k = 0; k < n; k++) weights[k] = counts[k];
+    for (int64_t k = 0; k < n; k++) {
+        if (weights[k] == 0 || (member && !member[k])) continue;
+        const int64_t j = partner[(size_t)k];
+        if (j >= 0 && weights[j] > 0) { const int32_t tot = weights[k] + weights[j]; weights[j] = 0; weights[k] = tot; }
+    }
+    return 0;
 }

@@ -1,0 +1,82 @@
+/* c2b_pyext.c -- CPython helpers for the host side of process_fastq: bulk construction of the variantCache.
+ *
+ * replaces: the per-unique-read Python work at the end of CRISPRessoCORE.process_fastq (:1956-1985) -- one dict per unique
+ * read -- which at GPU alignment rates WAS the run time (r01: 35 us of Python per unique read around a 25 ns kernel).  The
+ * engine's results stay in compact arrays; this module only creates, per aligned unique read, the key string and one lazy
+ * dict object (crispresso2_b200/lazy.py: LazyVariant) that materialises the reference's dict / ResultsSlotsDict on first
+ * access.
+ *
+ * Build: gcc -O2 -shared -fPIC -I<python include> -o crispresso2_b200/_c2b_pyext<EXT_SUFFIX> crispresso2_b200/csrc/c2b_pyext.c
+ */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <stdint.h>
+
+/* make_keys(buf, off) -> list[str]: unique reads as the strings text-mode reading yields (UTF-8, surrogateescape) */
+static PyObject *make_keys(PyObject *self, PyObject *args)
+{
+    Py_buffer buf, off;
+    if (!PyArg_ParseTuple(args, "y*y*", &buf, &off)) return NULL;
+    const Py_ssize_t n = off.len / 8 - 1;
+    const int64_t *o = (const int64_t *)off.buf;
+    const char *b = (const char *)buf.buf;
+    PyObject *out = NULL;
+    if (n < 0 || (n >= 0 && o[n < 0 ? 0 : n] > buf.len)) { PyErr_SetString(PyExc_ValueError, "offsets exceed the buffer"); goto done; }
+    out = PyList_New(n);
+    if (!out) goto done;
+    for (Py_ssize_t k = 0; k < n; k++) {
+        PyObject *s = PyUnicode_DecodeUTF8(b + o[k], (Py_ssize_t)(o[k + 1] - o[k]), "surrogateescape");
+        if (!s) { Py_CLEAR(out); goto done; }
+        PyList_SET_ITEM(out, k, s);
+    }
+done:
+    PyBuffer_Release(&buf); PyBuffer_Release(&off);
+    return out;
+}
+
+/* fill_cache(cache, keys, sel, counts, cls, value) -> number inserted
+ * For every k with sel[k] == value: cache[keys[k]] = obj, obj = cls() with obj._k = k and obj['count'] = counts[k].
+ * Insertion order = k order (first-seen order of the unique reads). */
+static PyObject *fill_cache(PyObject *self, PyObject *args)
+{
+    PyObject *cache, *keys, *cls;
+    Py_buffer sel, counts;
+    int value;
+    if (!PyArg_ParseTuple(args, "O!O!y*y*Oi", &PyDict_Type, &cache, &PyList_Type, &keys, &sel, &counts, &cls, &value)) return NULL;
+    const Py_ssize_t n = PyList_GET_SIZE(keys);
+    PyObject *res = NULL, *s_k = NULL, *s_count = NULL;
+    Py_ssize_t done = 0;
+    if (sel.len < n || counts.len < 4 * n) { PyErr_SetString(PyExc_ValueError, "sel / counts shorter than keys"); goto out; }
+    s_k = PyUnicode_InternFromString("_k");
+    s_count = PyUnicode_InternFromString("count");
+    if (!s_k || !s_count) goto out;
+    {
+        const uint8_t *m = (const uint8_t *)sel.buf;
+        const int32_t *c = (const int32_t *)counts.buf;
+        for (Py_ssize_t k = 0; k < n; k++) {
+            if (m[k] != (uint8_t)value) continue;
+            PyObject *o = PyObject_CallNoArgs(cls);
+            if (!o) goto out;
+            PyObject *ik = PyLong_FromSsize_t(k), *cnt = PyLong_FromLong(c[k]);
+            int bad = !ik || !cnt || PyObject_SetAttr(o, s_k, ik) < 0 || PyDict_SetItem(o, s_count, cnt) < 0 ||
+                      PyDict_SetItem(cache, PyList_GET_ITEM(keys, k), o) < 0;
+            Py_XDECREF(ik); Py_XDECREF(cnt); Py_DECREF(o);
+            if (bad) goto out;
+            done++;
+        }
+    }
+    res = PyLong_FromSsize_t(done);
+out:
+    Py_XDECREF(s_k); Py_XDECREF(s_count);
+    PyBuffer_Release(&sel); PyBuffer_Release(&counts);
+    return res;
+}
+
+static PyMethodDef methods[] = {
+    {"make_keys", make_keys, METH_VARARGS, "make_keys(buf, off) -> list of str"},
+    {"fill_cache", fill_cache, METH_VARARGS, "fill_cache(cache, keys, sel, counts, cls, value) -> int"},
+    {NULL, NULL, 0, NULL}};
+
+static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_c2b_pyext", "bulk variantCache construction", -1, methods};
+
+PyMODINIT_FUNC PyInit__c2b_pyext(void) { return PyModule_Create(&moddef); }

@@ -24,15 +24,34 @@ class BatchResult:
     alns    : ALN_DTYPE  [n, R]            R = n_refs, or 1 when the batch carried a per-read ref_id (Pooled)
     strings : uint8      [n, R, 2, W]      (right-aligned; [.., 0, :] read, [.., 1, :] reference) or None
     edits   : EDIT_DTYPE [n, R, cap] or None
+    ops/meta: compact form (c2b_align_batch_compact): uint64 [n, R, W/32] op streams, uint32 [n, R] meta words; the strings
+              of any block of reads are rebuilt on demand by the library's host-side expansion (strings_block)
     """
 
-    def __init__(self, recs, alns, strings, edits, W):
+    def __init__(self, recs, alns, strings, edits, W, ops=None, meta=None, engine=None, buf=None, off=None, ref_id=None):
         self.recs, self.alns, self.strings, self.edits, self.W = recs, alns, strings, edits, W
+        self.ops, self.meta, self._engine, self._buf, self._off, self._ref_id = ops, meta, engine, buf, off, ref_id
+
+    def strings_block(self, lo, hi):
+        """uint8 [hi-lo, R, 2, W] aligned strings of reads lo..hi-1"""
+        if self.strings is not None:
+            return self.strings[lo:hi]
+        e = self._engine
+        off = np.ascontiguousarray(self._off[lo:hi + 1])
+        rid = None if self._ref_id is None else np.ascontiguousarray(self._ref_id[lo:hi], dtype=np.int32)
+        ops = np.ascontiguousarray(self.ops[lo:hi])
+        meta = np.ascontiguousarray(self.meta[lo:hi])
+        out = np.zeros((hi - lo, self.alns.shape[1], 2, self.W), dtype=np.uint8)
+        maxj = e._max_len_of(self.W)
+        e._check(e.L.c2b_expand_batch(e.h, self._buf.ctypes.data, off.ctypes.data, hi - lo,
+                                      rid.ctypes.data if rid is not None else None, ops.ctypes.data, meta.ctypes.data,
+                                      maxj, out.ctypes.data, 0), "c2b_expand_batch")
+        return out
 
     def pair(self, i, r=0):
         """(aligned_read, aligned_ref) of read i against reference r, as str."""
         n = int(self.alns[i, r]["aln_len"])
-        s = self.strings[i, r]
+        s = self.strings_block(i, i + 1)[0, r]
         return s[0, self.W - n:].tobytes().decode(), s[1, self.W - n:].tobytes().decode()
 
     def score(self, i, r=0):
@@ -147,26 +166,37 @@ class Engine:
             raise EngineError("engine not configured")
         return w
 
-    def align_packed(self, buf, off, count=None, qweight=None, ref_id=None, strings=True, edits=True):
+    def _max_len_of(self, W):
+        """a max_read_len that reproduces string width W (c2b_string_width rounds max_I + max_read_len up to 32)"""
+        return max(1, W - max(self.ref_lens))
+
+    def align_packed(self, buf, off, count=None, qweight=None, ref_id=None, strings=True, edits=True, compact=False):
+        """One batch through the host-buffer entry.  compact=True: op streams + meta words come back instead of the aligned
+        strings (c2b_align_batch_compact); BatchResult rebuilds strings for the reads somebody looks at."""
         n = len(off) - 1
         maxj = int(np.max(np.diff(off))) if n else 1
         W = self.string_width(max(maxj, 1))
         nr = 1 if ref_id is not None else self.n_refs      # Pooled (per-read ref_id): compact outputs, [read][0]
         recs = np.zeros(n, dtype=_lib.REC_DTYPE)
         alns = np.zeros((n, nr), dtype=_lib.ALN_DTYPE)
-        sarr = np.zeros((n, nr, 2, W), dtype=np.uint8) if strings else None
         earr = np.zeros((n, nr, self.edit_cap), dtype=_lib.EDIT_DTYPE) if (edits and self.edit_cap) else None
 
-        def ptr(a, dt=None):
-            if a is None:
-                return None
-            return a.ctypes.data
+        def ptr(a):
+            return None if a is None else a.ctypes.data
 
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.int64)
         cnt = None if count is None else np.ascontiguousarray(count, dtype=np.int32)
         qw = None if qweight is None else np.ascontiguousarray(qweight, dtype=np.int32)
         rid = None if ref_id is None else np.ascontiguousarray(ref_id, dtype=np.int32)
+        if compact:
+            ops = np.zeros((n, nr, W // 32), dtype=np.uint64)
+            meta = np.zeros((n, nr), dtype=np.uint32)
+            self._check(self.L.c2b_align_batch_compact(self.h, ptr(buf) if len(buf) else None, ptr(off), n, ptr(cnt), ptr(qw),
+                                                       ptr(rid), ptr(recs), ptr(alns), ptr(ops), ptr(meta), ptr(earr)),
+                        "c2b_align_batch_compact")
+            return BatchResult(recs, alns, None, earr, W, ops=ops, meta=meta, engine=self, buf=buf, off=off, ref_id=rid)
+        sarr = np.zeros((n, nr, 2, W), dtype=np.uint8) if strings else None
         self._check(self.L.c2b_align_batch(self.h, ptr(buf) if len(buf) else None, ptr(off), n, ptr(cnt), ptr(qw),
                                            ptr(rid), ptr(recs), ptr(alns), ptr(sarr), ptr(earr)), "c2b_align_batch")
         return BatchResult(recs, alns, sarr, earr, W)

@@ -300,6 +300,13 @@ const int64_t *c2b_fastq_first_index(const c2b_fastq *f); /* record index of eac
 void c2b_fastq_free(c2b_fastq *f);
 const char *c2b_fastq_last_error(void);
 
+/* replaces: the reverse-complement count transfer at the head of the quantification loop (CRISPRessoCORE.py:3964-3975) for
+ * packed unique reads in first-seen order: weights[k] = the count read k ends up with (0 for a read absorbed by an earlier
+ * reverse complement; doubled for a palindrome, as in the reference).  member (NULL = all): reads still in the cache
+ * (aligned ones).  Host threads (n_threads <= 0: all).                                                          */
+int  c2b_rc_merge_weights(const uint8_t *seqs, const int64_t *offsets, int64_t n, const int32_t *counts,
+                          const uint8_t *member, int32_t *weights, int32_t n_threads);
+
 /* replaces: filterFastqs.filterFastqs for single-end input (CRISPResso2/filterFastqs.py:29-229, called at
  * CRISPRessoCORE.py:3716-3717): keep a record iff min(q) >= min_bp_qual_in_read and mean(q) >= min_av_read_qual (each when
  * non-zero), mask bases with q < min_bp_qual_or_N as 'N'; q = byte - 33 (uint8).  Same record/line rules as the reference's
