@@ -423,13 +423,15 @@ def main():
         return np.frombuffer((C.c_uint8 * nbytes).from_address(p), dtype=np.uint8).view(dtype), p
 
     nb = int(w.off[-1])
+    NW = L.c2b_ops_words(eng.h, w.max_len)
     h_reads, p1 = pinned(nb)
     h_reads[:] = w.buf
     h_off, p2 = pinned((n + 1) * 8, np.int64)
     h_off[:] = w.off
     h_recs, p3 = pinned(n * 16)
     h_alns, p4 = pinned(n * R * 32)
-    h_str, p5 = pinned(n * R * 2 * W)
+    h_ops, p5 = pinned(n * R * NW * 8)
+    h_meta, p8 = pinned(n * R * 4)
     h_ed, p6 = pinned(n * R * args.edit_cap * 8)
     h_rid, p7 = (None, None)
     if w.ref_id is not None:
@@ -438,9 +440,10 @@ def main():
     h2d = nb + (n + 1) * 8 + (n * 4 if w.ref_id is not None else 0)
 
     def step_e2e():
-        rc = L.c2b_align_batch(eng.h, h_reads.ctypes.data, h_off.ctypes.data, n, None, None,
-                               h_rid.ctypes.data if h_rid is not None else None, h_recs.ctypes.data,
-                               h_alns.ctypes.data, h_str.ctypes.data, h_ed.ctypes.data)
+        # the compact form of the host-buffer call: op streams + meta words instead of the spelled-out strings
+        rc = L.c2b_align_batch_compact(eng.h, h_reads.ctypes.data, h_off.ctypes.data, n, None, None,
+                                       h_rid.ctypes.data if h_rid is not None else None, h_recs.ctypes.data,
+                                       h_alns.ctypes.data, h_ops.ctypes.data, h_meta.ctypes.data, h_ed.ctypes.data)
         if rc != 0:
             raise RuntimeError(L.c2b_last_error(eng.h).decode())
         if world > 1:
@@ -457,24 +460,56 @@ def main():
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
-    if sampler:                                  # sampled across both timed regions (device-resident and end-to-end)
-        sampler.stop_flag = True
-        sampler.join(timeout=3)
     h_al = np.frombuffer(h_alns.tobytes(), dtype=_lib.ALN_DTYPE).reshape(n, R)
     e2e_gate = bool((h_al["n_match"] == alns["n_match"]).all() and (h_al["aln_len"] == alns["aln_len"]).all()
                     and (h_al["n_sub_all"] == alns["n_sub_all"]).all())
-    # the library copies back only the right-hand Wt bytes of each W-byte string slot (Wt = widest alignment, rounded to 32)
+    # ... and the strings rebuilt on the host from the compact outputs equal the ones the device-resident leg left in HBM
+    if rank == 0:
+        G = min(GATE_READS, n)
+        exp = np.zeros((G, R, 2, W), dtype=np.uint8)
+        rc = L.c2b_expand_batch(eng.h, h_reads.ctypes.data, h_off.ctypes.data, G, h_rid.ctypes.data if h_rid is not None else None,
+                                h_ops.ctypes.data, h_meta.ctypes.data, w.max_len, exp.ctypes.data, 0)
+        t_str = d_str[: G * R * 2 * W].cpu().numpy().reshape(G, R, 2, W)
+        cols = np.arange(W)[None, None, None, :] >= (W - alns[:G]["aln_len"].astype(np.int64))[:, :, None, None]
+        has = (alns[:G]["aln_len"] > 0)[:, :, None, None]
+        e2e_gate = e2e_gate and rc == 0 and bool(((exp == t_str) | ~(cols & has)).all())
+    # only the first Wt/32 op words of every slot cross PCIe (Wt = the chunk's widest alignment, rounded to 32)
     Wt = min(W, (int(h_al["aln_len"].max()) + 31) & ~31)
-    d2h = n * 16 + n * R * 32 + n * R * 2 * Wt + n * R * args.edit_cap * 8
-    for p in (p1, p2, p3, p4, p5, p6, p7):
+    d2h = n * 16 + n * R * 32 + n * R * (Wt // 32) * 8 + n * R * 4 + n * R * args.edit_cap * 8
+    # secondary: the same batch with the spelled-out strings coming back (c2b_align_batch), fewer steps
+    h_str, p9 = pinned(n * R * 2 * W)
+
+    def step_e2e_strings():
+        rc = L.c2b_align_batch(eng.h, h_reads.ctypes.data, h_off.ctypes.data, n, None, None,
+                               h_rid.ctypes.data if h_rid is not None else None, h_recs.ctypes.data,
+                               h_alns.ctypes.data, h_str.ctypes.data, h_ed.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(L.c2b_last_error(eng.h).decode())
+        if world > 1:
+            cdist.allreduce_counts(eng)
+
+    step_e2e_strings()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for _ in range(3):
+        step_e2e_strings()
+    s1.record(stream)
+    barrier()
+    e2s_ms = s0.elapsed_time(s1)
+    d2h_strings = n * 16 + n * R * 32 + n * R * 2 * Wt + n * R * args.edit_cap * 8
+    if sampler:                                  # sampled across the timed regions (device-resident and end-to-end)
+        sampler.stop_flag = True
+        sampler.join(timeout=3)
+    for p in (p1, p2, p3, p4, p5, p6, p7, p8, p9):
         if p:
             L.c2b_host_free(p)
 
     # ---- reduce over ranks ----------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_ms, float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_ms, float(np.mean(kernel_ms)), e2s_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, k_ms = [float(x) for x in t.cpu()]
+    dev_ms, e2e_ms, k_ms, e2s_ms = [float(x) for x in t.cpu()]
     total_reads = n * world
     value = total_reads * args.steps / (dev_ms / 1000.0)
     e2e_val = total_reads * e2e_steps / (e2e_ms / 1000.0)
@@ -519,12 +554,15 @@ def main():
                        "parity_gate_detail": gate},
             "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "pipeline": ("launch per chunk" if os.environ.get("C2B_STREAMED") == "0" else
-                                 "one persistent launch per batch, read bytes streamed in behind it (c2b_align_batch)")},
+                    "api": "c2b_align_batch_compact: pinned host buffers in; records, op streams, meta words and edit lists out "
+                           "(aligned strings rebuilt on the host by c2b_expand_batch: checked equal to the device-resident leg's)",
+                    "pipeline": "chunks of 128 Ki reads through two staging sets: H2D | ALIGN, CLASSIFY, general kernel | D2H",
+                    "with_strings": {"value": total_reads * 3 / (e2s_ms / 1000.0), "ms_per_step": e2s_ms / 3, "steps": 3,
+                                     "d2h_bytes_per_step": d2h_strings, "api": "c2b_align_batch (two W-byte strings per slot)"}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
-                         "kernel": "c2b_align_classify_kernel", "kernel_ms": k_ms, "alg_bytes_per_launch": w.alg_bytes,
+                         "kernel": "c2b_align_kernel + c2b_classify_kernel + c2b_align_classify_kernel (left-overs), one batch", "kernel_ms": k_ms, "alg_bytes_per_launch": w.alg_bytes,
                          "secondary_int32": {"alg_ops_per_launch": alg_ops,
                                              "note": "alg_*: ops of the reference's full-matrix algorithm (10 per DP cell), a rate of USEFUL work, not a "
                                                      "utilisation: the banded DP evaluates a fraction of the cells.  executed_*: from the ncu capture "

@@ -86,6 +86,9 @@ static void rt_host_free(void *p) { free(p); }
 #endif
 constexpr int WARPS_PER_CTA = C2B_WARPS_PER_CTA;      // launch-bounds maximum; the launch may use fewer (env C2B_WARPS_PER_CTA)
 constexpr int B_WARPS_PER_CTA = 4;                    // CLASSIFY kernel
+#ifndef C2B_B_MIN_CTAS
+#define C2B_B_MIN_CTAS 6
+#endif
 
 // TMA-staged reference tile: the packed substitution profile of reference 0, once per CTA (cp.async.bulk + mbarrier);
 // every DP step then reads it with two 16-byte LDS.  -> shared-memory address of the tile, or nullptr
@@ -186,12 +189,24 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_A_MIN_CTAS) c2b_align_
 
 // CLASSIFY kernel (c2b_split.cuh: classify_read): one aligned read per warp, reads strided over the grid.
 template <bool ONE>
-__global__ void __launch_bounds__(B_WARPS_PER_CTA * 32) c2b_classify_kernel(const __grid_constant__ KParams P)
+__global__ void __launch_bounds__(B_WARPS_PER_CTA * 32, C2B_B_MIN_CTAS) c2b_classify_kernel(const __grid_constant__ KParams P)
 {
+    __shared__ BSmem smem[B_WARPS_PER_CTA];
+    BSmem &S = smem[threadIdx.x >> 5];
     const int64_t nw = (int64_t)gridDim.x * B_WARPS_PER_CTA;
-    for (int64_t rd = (int64_t)blockIdx.x * B_WARPS_PER_CTA + (threadIdx.x >> 5); rd < P.n_reads; rd += nw) {
-        classify_read<ONE>(P, rd);
+    const int64_t total_bytes = P.offsets[P.n_reads];
+    int64_t rd = (int64_t)blockIdx.x * B_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (rd >= P.n_reads) return;
+    BPre pre = classify_prefetch<ONE>(P, rd, total_bytes);
+    while (rd < P.n_reads) {
+        const BPre cur = pre;
+        if (cur.go) classify_stage<ONE>(cur, S);
         __syncwarp();
+        const int64_t nxt = rd + nw;
+        if (nxt < P.n_reads) pre = classify_prefetch<ONE>(P, nxt, total_bytes);     // in flight while this read is classified
+        if (cur.go) classify_read<ONE>(P, rd, cur, S);
+        __syncwarp();
+        rd = nxt;
     }
 }
 #endif
@@ -769,9 +784,11 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
             KParams A = P;
             A.left = d_left; A.left_n = wk + 3;
             for (int64_t w = 0; 8 * w < n_reads; w++) emu::run_warp([&]() { align_group(A, AS, nullptr, w, 0); });
+            static BSmem BS;
+            const int64_t total_bytes = d_offsets[n_reads];
             for (int64_t rd = 0; rd < n_reads; rd++) {
-                if (one) emu::run_warp([&]() { classify_read<true>(P, rd); });
-                else emu::run_warp([&]() { classify_read<false>(P, rd); });
+                if (one) emu::run_warp([&]() { const BPre b = classify_prefetch<true>(P, rd, total_bytes); if (b.go) { classify_stage<true>(b, BS); wp::sync(); classify_read<true>(P, rd, b, BS); } });
+                else emu::run_warp([&]() { const BPre b = classify_prefetch<false>(P, rd, total_bytes); if (b.go) { classify_stage<false>(b, BS); wp::sync(); classify_read<false>(P, rd, b, BS); } });
             }
             P.pair_order = d_left; P.n_dev = wk + 3; P.work_counter = wk + 2; P.tbq = nullptr; P.rgops = nullptr;
         }

@@ -58,6 +58,93 @@ C2B_DEV bool load_codes_a(const KParams &P, int64_t off, int J, uint8_t *fw, uin
     return wp::ballot(bad) != 0;
 }
 
+// Four tracebacks of one ring-banded DP at once.  walk_batch (c2b_core.cuh) is a chain of dependent L2 round trips -- one
+// slab gather per run of equal ops -- and four of them in sequence cost as much wall time as the DP itself (r02b: the ALIGN
+// kernel's issue slots were idle half the time).  Here every iteration issues the gathers of all four pairs before it
+// consumes any, so the four latencies overlap; the per-pair logic is walk_batch<true>'s for a ring slab, verbatim.
+C2B_DEV void walk_ring4(const KParams &P, const RefDev &R, const int *Jq, const uint2 *__restrict__ tb2, const int *s0, uint32_t mask,
+                        Walked *out)
+{
+    const int lane = wp::lane();
+    const int hl = lane & 15, hb = lane & 16;
+    const int TS = P.TS;
+    int i[4], j[4], s[4], n[4], err[4];
+    uint32_t acc[4], lo[4], hi[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const bool on = (mask >> q) & 1u;
+        i[q] = on ? R.I : 0; j[q] = on ? Jq[q] : 0; s[q] = s0[q]; n[q] = 0; err[q] = 0; acc[q] = 0; lo[q] = hi[q] = ~0u;
+    }
+    // append `cnt` (<= 32) copies of op to pair q's stream; acc holds the (n & 15) newest ops in its top bits
+#define C2B_PUSH4(q, op_, cnt_) do { int cnt = (cnt_); const uint32_t pat = (uint32_t)(op_) * 0x55555555u;                          \
+        while (cnt > 0) { const int room = 16 - (n[q] & 15); const int c = cnt < room ? cnt : room;                                  \
+            acc[q] = (uint32_t)((((uint64_t)pat << 32) | acc[q]) >> (2 * c)); n[q] += c; cnt -= c;                                   \
+            if ((n[q] & 15) == 0) { const int ix = (n[q] >> 4) - 1; if (hl == (ix >> 1)) { if (ix & 1) hi[q] = acc[q]; else lo[q] = acc[q]; } } } } while (0)
+    for (;;) {
+        uint2 w2[4]; bool valid[4], inband[4]; int sh[4];
+        bool anyact = false;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bool active = i[q] > 0 && j[q] > 0;
+            anyact |= active;
+            const int di = (s[q] != OP_I), dj = (s[q] != OP_J);
+            const int ci = i[q] - hl * di, cj = j[q] - hl * dj;
+            valid[q] = active && ci >= 1 && cj >= 1;
+            inband[q] = valid[q];
+            w2[q] = make_uint2(0u, 0u); sh[q] = 0;
+            if (valid[q]) {
+                const int r = ci - 1, l = (r >> 3) & 31;
+                const int slot = cj + l - 9 * l + RG_B;
+                inband[q] = (unsigned)slot < (unsigned)RG_NS;
+                sh[q] = 2 * (7 - (r & 7));
+                if (inband[q]) w2[q] = wp::ldcg2(tb2 + (int64_t)(8 * q + (l & 7)) * TS + cj + l);
+            }
+        }
+        if (!wp::ballot(anyact)) break;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bool active = i[q] > 0 && j[q] > 0;
+            const uint32_t w = hb ? ((w2[q].x & 0xffff0000u) | (w2[q].y >> 16)) : ((w2[q].x << 16) | (w2[q].y & 0xffffu));
+            const uint32_t v = (valid[q] && inband[q]) ? (w >> sh[q]) : 0u;
+            const int tag = (int)((v >> 16) & 3u);
+            const bool cont = valid[q] && (s[q] == OP_M ? tag == OP_M : (v & (uint32_t)s[q]) != 0u);
+            const uint32_t bc = (wp::ballot(cont) >> hb) & 0xffffu, bv = (wp::ballot(valid[q]) >> hb) & 0xffffu;
+            const uint32_t bo = (wp::ballot(valid[q] && !inband[q]) >> hb) & 0xffffu;
+            int nvalid = wp::popc(bv);
+            if (bo) { const int fo = wp::ffs(bo) - 1; if (fo < nvalid) nvalid = fo; }
+            const bool miss = active && nvalid == 0;
+            int f = wp::ffs(~bc) - 1;
+            if (f < 0 || f > nvalid) f = nvalid;
+            const bool brk = f < nvalid;
+            const int run = brk ? f + 1 : nvalid;
+            const int tagf = wp::shfl(tag, hb + (f < 16 ? f : 15));
+            if (miss) { err[q] |= 4; i[q] = 0; j[q] = 0; }
+            else if (active) {
+                const int di = (s[q] != OP_I), dj = (s[q] != OP_J);
+                const int news = brk ? (s[q] == OP_M ? tagf : OP_M) : s[q];
+                C2B_PUSH4(q, s[q], run);
+                i[q] -= run * di; j[q] -= run * dj;
+                err[q] |= (news == 3);
+                s[q] = news;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (j[q] > 0 && s[q] != OP_I) err[q] |= 1;              // row 0 / column 0 can only be left along their own border
+        if (i[q] > 0 && s[q] != OP_J) err[q] |= 1;
+        while (j[q] > 0) { const int c = j[q] < 32 ? j[q] : 32; C2B_PUSH4(q, OP_I, c); j[q] -= c; }
+        while (i[q] > 0) { const int c = i[q] < 32 ? i[q] : 32; C2B_PUSH4(q, OP_J, c); i[q] -= c; }
+        if (n[q] & 15) {
+            const int ix = n[q] >> 4, used = 2 * (n[q] & 15);
+            const uint32_t a = (acc[q] >> (32 - used)) | (~0u << used);
+            if (hl == (ix >> 1)) { if (ix & 1) hi[q] = a; else lo[q] = a; }
+        }
+        out[q].ops = (uint64_t)lo[q] | ((uint64_t)hi[q] << 32); out[q].n = n[q]; out[q].err = err[q];
+    }
+#undef C2B_PUSH4
+}
+
 // ---------------------------------------------------------------------------------------------------- ALIGN
 // Work group wq = reads 8wq..8wq+7 (four pairs).  Eligible groups (equal lengths per pair, every candidate reference admits
 // the band) run the ring-banded DP once per candidate reference and walk the four tracebacks; a pair whose two scores beat
@@ -145,21 +232,29 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
         const uint32_t b = wp::ballot(pass);
         uint32_t passmask = ((b & 1u) | ((b >> 7) & 2u) | ((b >> 14) & 4u) | ((b >> 21) & 8u)) & good;
         ntried += wp::popc(good);
-#pragma unroll 1
-        for (int q = 0; q < 4; q++) {
-            if (!((passmask >> q) & 1u)) continue;
-            const uint32_t sq = wp::shflu(s2, 8 * q);
-            const int Jq = wp::shfl(Jg, 8 * q);
-            const int s0 = (lane & 16) ? (int)(sq >> 16) : (int)(sq & 3u);
-            const Walked wk = walk_batch<true>(P, R, Jq, reinterpret_cast<const uint32_t *>(tbq), s0, SlabMode{9, RG_B, RG_NS, 1, 8 * q});
-            if (wp::ballot(wk.err != 0)) { passmask &= ~(1u << q); continue; }    // cannot happen when the bound holds; general kernel then
-            const int h = lane >> 4, hl = lane & 15;
-            const int64_t rd = read_at(P, 2 * (first + q) + h);
-            const int64_t slot = oslot(P, rd, k);
-            if (hl < P.NW) P.gops[slot * P.NW + hl] = wk.ops;
-            if (hl == 0) {
-                const int mode = (int)((modes >> (4 * q + 2 * h)) & 3u);
-                P.gmeta[slot] = gmeta_pack(wk.n, mode == 1, GM_NONE);        // state is set below, once every reference passed
+        {
+            int Jq[4], s0[4];
+            Walked wk4[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t sq = wp::shflu(s2, 8 * q);
+                Jq[q] = wp::shfl(Jg, 8 * q);
+                s0[q] = (lane & 16) ? (int)(sq >> 16) : (int)(sq & 3u);
+            }
+            walk_ring4(P, R, Jq, tbq, s0, passmask, wk4);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (!((passmask >> q) & 1u)) continue;
+                const Walked &wk = wk4[q];
+                if (wp::ballot(wk.err != 0)) { passmask &= ~(1u << q); continue; }    // cannot happen when the bound holds; general kernel then
+                const int h = lane >> 4, hl = lane & 15;
+                const int64_t rd = read_at(P, 2 * (first + q) + h);
+                const int64_t slot = oslot(P, rd, k);
+                if (hl < P.NW) P.gops[slot * P.NW + hl] = wk.ops;
+                if (hl == 0) {
+                    const int mode = (int)((modes >> (4 * q + 2 * h)) & 3u);
+                    P.gmeta[slot] = gmeta_pack(wk.n, mode == 1, GM_NONE);        // state is set below, once every reference passed
+                }
             }
         }
         npass += wp::popc(passmask);
@@ -195,9 +290,16 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
 // One alignment per warp, one column per lane, 32 columns per step, left to right.  Column c (from the left) is op number
 // n-1-c of the stream (the walk emits right to left).  With bI / bJ the ballots of the insertion / deletion columns of a
 // step, lane l's reference index is i0 + l - popc(bI below l) and its read index j0 + l - popc(bJ below l).
+// The read's bytes and its op streams are staged in shared memory by the kernel loop (one coalesced 16-byte load per lane,
+// issued one read ahead), so the scans below touch global memory only for the reference tables (L1-resident) and outputs.
+constexpr int B_RD_BYTES = 32 * 16;                    // staged window of read bytes (16-byte aligned start)
+struct BSmem {                                         // CLASSIFY kernel, per warp
+    uint64_t ops[RG_MAX_REFS][32];                     // op streams of the candidate references
+    uint8_t rd[B_RD_BYTES];                            // bytes [off & ~15, ...) of the read buffer
+};
 struct ColCtx {
-    const uint64_t *ops;           // P.gops + slot * NW
-    const uint8_t *rd;             // P.reads + offset of the read
+    const uint64_t *ops;           // op stream of this slot (shared memory)
+    const uint8_t *rd;             // the read's first byte (shared memory)
     int n, J, strand;
     uint32_t mmis, mI, mJ;         // lane m: ballots of step m (mismatching M columns, I columns, J columns) -- filled by colscan0
 };
@@ -212,7 +314,7 @@ C2B_DEV ColDec col_decode(const KParams &P, const RefDev &R, const ColCtx &c, in
     d.valid = col < c.n;
     const int q = c.n - 1 - col;
     d.op = OP_NONE;
-    if (d.valid) d.op = (int)((wp::ldcg64(c.ops + (q >> 5)) >> (2 * (q & 31))) & 3ull);
+    if (d.valid) d.op = (int)((c.ops[q >> 5] >> (2 * (q & 31))) & 3ull);
     d.bI = wp::ballot(d.op == OP_I); d.bJ = wp::ballot(d.op == OP_J);
     d.i = i0 + lane - wp::popc(d.bI & lt);
     d.j = j0 + lane - wp::popc(d.bJ & lt);
@@ -257,7 +359,7 @@ C2B_DEV ColOut colscan0(const KParams &P, const RefDev &R, ColCtx &c, uint8_t *o
 // Pass 1: find_indels_substitutions + the per-read quantification, same mode bits and outputs as rows_run (c2b_core.cuh),
 // evaluated over alignment columns.  Insertion / deletion runs are closed in the step that holds their first column to the
 // right (state carried across steps); flank positions shared by two insertions count once (numpy's fancy-index +=).
-C2B_DEV void colscan1(const KParams &P, const RefDev &R, const ColCtx &c, RowOut &o, c2b_edit *ed, long long w, int mode,
+C2B_DEVNOINL void colscan1(const KParams &P, const RefDev &R, const ColCtx &c, RowOut &o, c2b_edit *ed, long long w, int mode,
                       unsigned long long *Vt = nullptr)
 {
     const int lane = wp::lane();
@@ -425,18 +527,62 @@ C2B_DEV void colscan1(const KParams &P, const RefDev &R, const ColCtx &c, RowOut
 
 // Classification + counts of one read whose alignments to references r_begin..r_end-1 were produced by the ALIGN kernel:
 // the body of finish_read (c2b_core.cuh) over column scans instead of the shared-memory row view.
+// What the kernel loop loads for a read one iteration ahead (registers), and stages in shared memory before classify_read.
+struct BPre { uint64_t ops[RG_MAX_REFS]; uint4 bytes; uint32_t gm[RG_MAX_REFS]; int64_t off; int J, r_begin, nref; bool go; };
+
 template <bool ONE>
-C2B_DEV void classify_read(const KParams &P, int64_t rd)
+C2B_DEV BPre classify_prefetch(const KParams &P, int64_t rd, int64_t total_bytes)
 {
     const int lane = wp::lane();
-    const int r_begin = P.ref_id ? P.ref_id[rd] : 0;
-    const int r_end = (ONE || P.ref_id) ? r_begin + 1 : P.n_refs;
-    {   // handled by the ALIGN kernel?  (all candidate references or none)
-        const uint32_t m0 = wp::ldcg(P.gmeta + oslot(P, rd, r_begin));
-        if ((m0 >> 24) != GM_ALIGNED) return;
+    BPre b;
+    b.r_begin = P.ref_id ? P.ref_id[rd] : 0;
+    b.nref = (ONE || P.ref_id) ? 1 : P.n_refs;
+    const int64_t slot0 = oslot(P, rd, b.r_begin);
+    b.go = (wp::ldcg(P.gmeta + slot0) >> 24) == GM_ALIGNED;          // aligned by the ALIGN kernel (all candidates or none)
+    b.off = P.offsets[rd];
+    b.J = (int)(P.offsets[rd + 1] - b.off);
+    b.bytes = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < (ONE ? 1 : RG_MAX_REFS); k++) { b.ops[k] = ~0ull; b.gm[k] = 0; }
+    if (!b.go) return b;
+#pragma unroll
+    for (int k = 0; k < (ONE ? 1 : RG_MAX_REFS); k++) {
+        if (k < b.nref) {
+            b.gm[k] = wp::ldcg(P.gmeta + slot0 + k);
+            if (lane < P.NW) b.ops[k] = wp::ldcg64(P.gops + (slot0 + k) * P.NW + lane);
+        }
     }
-    const int64_t off = P.offsets[rd];
-    const int J = (int)(P.offsets[rd + 1] - off);
+    // 16-byte windows from the aligned address at or below the read's first byte (alignment of the ABSOLUTE address)
+    const uint8_t *p0 = P.reads + b.off;
+    const uint8_t *wa = p0 - ((uintptr_t)p0 & 15) + 16 * lane;
+    if (wa < p0 + b.J) {
+        if (wa >= P.reads && wa + 16 <= P.reads + total_bytes) b.bytes = wp::ldg4u(reinterpret_cast<const uint4 *>(wa));
+        else {                                               // first / last bytes of the buffer: no load outside it
+            uint32_t w[4] = {0, 0, 0, 0};
+            for (int x = 0; x < 16; x++) if (wa + x >= P.reads && wa + x < P.reads + total_bytes) w[x >> 2] |= (uint32_t)wa[x] << (8 * (x & 3));
+            b.bytes = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    return b;
+}
+
+template <bool ONE>
+C2B_DEV void classify_stage(const BPre &b, BSmem &S)
+{
+    const int lane = wp::lane();
+#pragma unroll
+    for (int k = 0; k < (ONE ? 1 : RG_MAX_REFS); k++) if (k < b.nref) S.ops[k][lane] = b.ops[k];
+    reinterpret_cast<uint4 *>(S.rd)[lane] = b.bytes;
+}
+
+template <bool ONE>
+C2B_DEV void classify_read(const KParams &P, int64_t rd, const BPre &pre, const BSmem &S)
+{
+    const int lane = wp::lane();
+    const int r_begin = pre.r_begin;
+    const int r_end = r_begin + pre.nref;
+    const int64_t off = pre.off;
+    const int J = pre.J;
     const bool multi = !ONE && (r_end - r_begin) > 1;
 
     c2b_read_rec rec; rec.winner_mask = 0; rec.best_score_milli = -1000; rec.best_ref = -1; rec.n_winners = 0;
@@ -449,8 +595,8 @@ C2B_DEV void classify_read(const KParams &P, int64_t rd)
         const RefDev &R = refdev(P, r);
         const int64_t slot = oslot(P, rd, r);
         ColCtx &c = cx[ONE ? 0 : r - r_begin];
-        const uint32_t gm = wp::ldcg(P.gmeta + slot);
-        c.ops = P.gops + slot * P.NW; c.rd = P.reads + off; c.n = (int)(gm & 0xffffu); c.J = J; c.strand = (int)((gm >> 16) & 1u);
+        const uint32_t gm = pre.gm[ONE ? 0 : r - r_begin];
+        c.ops = S.ops[ONE ? 0 : r - r_begin]; c.rd = S.rd + (int)((uintptr_t)(P.reads + off) & 15); c.n = (int)(gm & 0xffffu); c.J = J; c.strand = (int)((gm >> 16) & 1u);
         uint8_t *o_read = P.strings ? P.strings + (slot * 2) * (int64_t)P.W : nullptr;
         const ColOut co = colscan0(P, R, c, o_read, o_read ? o_read + P.W : nullptr);
         init_aln(a, 0);
