@@ -209,20 +209,20 @@ def merge_weights_packed(buf, off, counts, member=None, lib_path=None):
     return w
 
 
-_OK_SYMBOL = np.zeros(256, dtype=bool)
-_OK_SYMBOL[list(b"ACGTN")] = True
-
-
-def screen_reads(buf, off):
+def screen_reads(buf, off, lib_path=None):
     """-> bool mask of unique reads outside the engine's contract: empty, longer than MAX_READ_LEN, or holding a symbol
     other than A C G T N (lower case and IUPAC codes included: the reference indexes its score table with them -- lower case
-    out of bounds, Align.pyx:212 -- and its quantification loop raises KeyError on them at CRISPRessoCORE.py:4081)."""
-    lens = np.diff(off)
-    bad = (lens < 1) | (lens > _lib.MAX_READ_LEN)
-    odd = np.nonzero(~_OK_SYMBOL[buf])[0]
-    if len(odd):
-        bad[np.unique(np.searchsorted(off, odd, side="right") - 1)] = True
-    return bad
+    out of bounds, Align.pyx:212 -- and its quantification loop raises KeyError on them at CRISPRessoCORE.py:4081).
+    Native (c2b_screen_reads, host threads)."""
+    L = _lib.load(lib_path)
+    n = len(off) - 1
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    out = np.zeros(n, dtype=np.uint8)
+    rc = L.c2b_screen_reads(buf.ctypes.data if len(buf) else None, off.ctypes.data, n, _lib.MAX_READ_LEN, out.ctypes.data, 0)
+    if rc < 0:
+        raise EngineError("c2b_screen_reads failed (%d)" % rc)
+    return out.astype(bool)
 
 
 def align_uniques(engine, uniques, counts, ref_names, refs, flags, weights=None, packed=None, compact=False):
@@ -380,7 +380,7 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
     flags = _flags(args)
     configure_engine(engine, args, refs, ref_names, aln_matrix)
     engine.counts_reset()
-    bad = screen_reads(buf, off) if n else np.zeros(0, dtype=bool)
+    bad = screen_reads(buf, off, lib_path=engine.lib_path) if n else np.zeros(0, dtype=bool)
     n_bad = int(bad.sum())
     if n_bad:
         k = int(np.nonzero(bad)[0][0])
@@ -450,7 +450,7 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
         st["N_TOT_READS"] += cb
         st["N_COMPUTED_NOTALN"] += n_bad
         st["N_CACHED_NOTALN"] += cb - n_bad
-    src = lazy.BatchSource(None, keys_g, ref_names, refs, parts=parts)
+    src = lazy.BatchSource(None, keys_g, ref_names, refs, counts_g, parts=parts)
     cls = src.lazy_class()
     not_aligned = {}
     sel = aligned.astype(np.uint8)

@@ -955,7 +955,7 @@ C2B_DEV void finish_read(const KParams &P, int64_t rd, c2b_read_rec rec, int J, 
             // (derived on the host) instead
 #ifndef C2B_X_BISECT_R01J
             if (counted && lane == 0 && (two_scans || expand)) {
-                const bool discarded = two_scans && (o.del_n > 0 || o.ins_n > 0), joined = !ONE && expand && rec.n_winners > 1;
+                const bool discarded = two_scans && (o.del_n > 0 || o.ins_n > 0), joined = !ONE && expand && !first && rec.n_winners > 1;   // assign-first is tested first (:780-785)
                 if (discarded != joined) sc_add(SC, modified ? C2B_S_CLASS_MODIFIED : C2B_S_CLASS_UNMODIFIED, discarded ? w : -w);
             }
 #endif

@@ -132,6 +132,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_MIN_CTAS_PER_SM) c2b_a
     const int gs = P.phase_sync, g = gs > 0 ? gs : gs < 0 ? -gs : 1, wib = threadIdx.x >> 5, nsets = (int)(blockDim.x >> 5) / g;
     const int set = gs < 0 ? wib % nsets : wib / g, wis = gs < 0 ? wib / nsets : wib % g;
     const int64_t nrd = nreads(P);
+    if (P.n_dev) {
+        // over the ALIGN kernel's left-over list: one pair per hand-out (a warp that drew four hard pairs in a row was the
+        // critical path of the whole launch: 1.3 ms for 1 % of the reads)
+        const unsigned total = (unsigned)((nrd + 1) / 2);
+        for (;;) {
+            unsigned w = 0;
+            if ((threadIdx.x & 31) == 0) w = (unsigned)atomicAdd(P.work_counter, 1ull);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            if (w >= total) break;
+            process_item<ONE>(P, *S, staged_prof, (int64_t)w, warp_slot);
+            __syncwarp();
+        }
+        return;
+    }
     const unsigned long long total = ((unsigned long long)nrd + 7) / 8;
     auto hand_out = [&]() -> unsigned long long {
         if (wis == 0 && (threadIdx.x & 31) == 0) next_base[set] = atomicAdd(P.work_counter, (unsigned long long)g);
@@ -659,27 +673,32 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
     if (fresh_work) RTCHK(rt_zero(e->work.p, WORK_BYTES, e->stream));
     e->scratch_TS = TS;
 #ifndef C2B_EMU
-    {   // Keep the traceback slab (written once, read back by the same warp microseconds later) resident in L2:
-        // persisting window over the slab, everything else on this stream streams through the rest of L2.
+    {   // L2 policy for the traceback slabs (written once, read back by the same warp microseconds later).  C2B_L2_PERSIST:
+        //   unset / "none": no set-aside -- the whole L2 serves every access (r02 default: the ALIGN kernel's ring slabs are
+        //                   the hot set now, and a set-aside sized for the general kernel's banded slabs took 60 % of L2 away);
+        //   "ring"        : persisting window over the ring slabs (hit ratio = set-aside / slab bytes);
+        //   "band"        : the r01 setting, persisting window over the general kernel's banded slabs.
         cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
-            !getenv("C2B_NO_L2_PERSIST")) {
-            const size_t slab = 2 * e->set_tbb;                                   // the banded slabs (both sets): the hot set
-            const size_t carve = std::min((size_t)prop.persistingL2CacheMaxSize, slab);
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+        const char *mode = getenv("C2B_L2_PERSIST");
+        if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
             cudaStreamAttrValue av; memset(&av, 0, sizeof av);
-            av.accessPolicyWindow.base_ptr = e->tbb.p;
-            av.accessPolicyWindow.num_bytes = std::min(slab, (size_t)prop.accessPolicyMaxWindowSize);
-            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)std::max<size_t>(1, av.accessPolicyWindow.num_bytes));
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            size_t carve = 0;
+            if (mode && (!strcmp(mode, "ring") || !strcmp(mode, "band"))) {
+                const bool ring = !strcmp(mode, "ring");
+                const size_t slab = ring ? e->set_tbq : 2 * e->set_tbb;
+                carve = std::min((size_t)prop.persistingL2CacheMaxSize, slab);
+                av.accessPolicyWindow.base_ptr = ring ? e->tbq.p : e->tbb.p;
+                av.accessPolicyWindow.num_bytes = std::min(slab, (size_t)prop.accessPolicyMaxWindowSize);
+                av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)std::max<size_t>(1, av.accessPolicyWindow.num_bytes));
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            }
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
             cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
-            if (e->stream2) cudaStreamSetAttribute(e->stream2, cudaStreamAttributeAccessPolicyWindow, &av);
             cudaGetLastError();
             if (getenv("C2B_VERBOSE"))
-                fprintf(stderr, "[c2b] grid %d x %d warps, banded traceback slabs %.1f MB, persisting L2 max %.1f MB (L2 %.1f MB), window %.1f MB, hitRatio %.2f\n",
-                        e->grid, e->wpc, slab / 1e6, prop.persistingL2CacheMaxSize / 1e6, prop.l2CacheSize / 1e6,
-                        av.accessPolicyWindow.num_bytes / 1e6, av.accessPolicyWindow.hitRatio);
+                fprintf(stderr, "[c2b] scratch for %d warps: ring slabs %.1f MB, L2 %.1f MB, persisting set-aside %.1f MB (%s)\n",
+                        e->n_warps, e->set_tbq / 1e6, prop.l2CacheSize / 1e6, carve / 1e6, mode ? mode : "none");
         }
     }
 #endif
@@ -767,6 +786,7 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
         else c2b_classify_kernel<false><<<e->grid_b, B_WARPS_PER_CTA * 32, 0, cs>>>(P);
         // the general kernel over ALIGN's left-over pairs (free-running warps, no ring-banded attempt)
         P.pair_order = d_left; P.n_dev = wk + 3; P.work_counter = wk + 2; P.tbq = nullptr; P.rgops = nullptr;
+        P.tbb = nullptr;                                      // these pairs left the ring band: the banded slab would only cost a second DP
         e->launches += 2;
     }
     {
@@ -790,9 +810,15 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
                 if (one) emu::run_warp([&]() { const BPre b = classify_prefetch<true>(P, rd, total_bytes); if (b.go) { classify_stage<true>(b, BS); wp::sync(); classify_read<true>(P, rd, b, BS); } });
                 else emu::run_warp([&]() { const BPre b = classify_prefetch<false>(P, rd, total_bytes); if (b.go) { classify_stage<false>(b, BS); wp::sync(); classify_read<false>(P, rd, b, BS); } });
             }
-            P.pair_order = d_left; P.n_dev = wk + 3; P.work_counter = wk + 2; P.tbq = nullptr; P.rgops = nullptr;
+            P.pair_order = d_left; P.n_dev = wk + 3; P.work_counter = wk + 2; P.tbq = nullptr; P.rgops = nullptr; P.tbb = nullptr;
         }
         const int64_t nrd = P.n_dev ? (int64_t)*P.n_dev : n_reads;
+        if (P.n_dev) {                                      // left-over list: one pair per hand-out, like the kernel
+            for (int64_t w = 0; 2 * w < nrd; w++) {
+                if (one) emu::run_warp([&]() { process_item<true>(P, S, nullptr, w, 0); });
+                else emu::run_warp([&]() { process_item<false>(P, S, nullptr, w, 0); });
+            }
+        } else
         for (int64_t w = 0; 8 * w < nrd; w++) {
             wp::g_grp_syncs = 0;
             if (one) emu::run_warp([&]() { process_group<true>(P, S, Q, nullptr, w, 0); });

@@ -482,3 +482,35 @@ extern "C" int c2b_rc_merge_weights(const uint8_t *seqs, const int64_t *offsets,
     }
     return 0;
 }
+
+// Reads outside the engine's contract (crispresso2_b200/core.py: screen_reads): empty, longer than max_len, or holding a
+// symbol other than A C G T N.  out[k] = 1 for such reads.  Host threads.  -> number of flagged reads
+extern "C" int64_t c2b_screen_reads(const uint8_t *seqs, const int64_t *offsets, int64_t n, int32_t max_len, uint8_t *out, int32_t n_threads)
+{
+    if (!offsets || !out || n < 0 || (n && !seqs)) return -2;
+    int T = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    T = (int)std::min<int64_t>(T, std::max<int64_t>(1, n / 8192));
+    static const struct Ok { uint8_t t[256]; Ok() { memset(t, 0, sizeof t); for (const char *a = "ACGTN"; *a; a++) t[(uint8_t)*a] = 1; } } ok;
+    std::vector<int64_t> bad((size_t)T, 0);
+    auto work = [&](int t) {
+        const int64_t lo = n * t / T, hi = n * (t + 1) / T;
+        int64_t nb = 0;
+        for (int64_t k = lo; k < hi; k++) {
+            const int64_t L = offsets[k + 1] - offsets[k];
+            uint8_t b = (L < 1 || L > max_len) ? 1 : 0;
+            const uint8_t *p = seqs + offsets[k];
+            uint8_t all = 1;
+            for (int64_t i = 0; i < L; i++) all &= ok.t[p[i]];
+            b |= (uint8_t)(all ^ 1);
+            out[k] = b; nb += b;
+        }
+        bad[(size_t)t] = nb;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    int64_t tot = 0;
+    for (int64_t v : bad) tot += v;
+    return tot;
+}

@@ -35,8 +35,10 @@ done:
 }
 
 /* fill_cache(cache, keys, sel, counts, cls, value) -> number inserted
- * For every k with sel[k] == value: cache[keys[k]] = obj, obj = cls() with obj._k = k and obj['count'] = counts[k].
- * Insertion order = k order (first-seen order of the unique reads). */
+ * For every k with sel[k] == value: cache[keys[k]] = obj, obj = cls() with obj._k = k (the object answers ['count'] from
+ * the batch's count array on first use, lazy.py).  Insertion order = k order (first-seen order of the unique reads).
+ * The cyclic GC is paused meanwhile: half a million new containers would otherwise trigger full collections of a heap
+ * that holds nothing collectable. */
 static PyObject *fill_cache(PyObject *self, PyObject *args)
 {
     PyObject *cache, *keys, *cls;
@@ -44,30 +46,29 @@ static PyObject *fill_cache(PyObject *self, PyObject *args)
     int value;
     if (!PyArg_ParseTuple(args, "O!O!y*y*Oi", &PyDict_Type, &cache, &PyList_Type, &keys, &sel, &counts, &cls, &value)) return NULL;
     const Py_ssize_t n = PyList_GET_SIZE(keys);
-    PyObject *res = NULL, *s_k = NULL, *s_count = NULL;
+    PyObject *res = NULL, *s_k = NULL;
     Py_ssize_t done = 0;
+    const int gc_was = PyGC_Disable();
     if (sel.len < n || counts.len < 4 * n) { PyErr_SetString(PyExc_ValueError, "sel / counts shorter than keys"); goto out; }
     s_k = PyUnicode_InternFromString("_k");
-    s_count = PyUnicode_InternFromString("count");
-    if (!s_k || !s_count) goto out;
+    if (!s_k) goto out;
     {
         const uint8_t *m = (const uint8_t *)sel.buf;
-        const int32_t *c = (const int32_t *)counts.buf;
         for (Py_ssize_t k = 0; k < n; k++) {
             if (m[k] != (uint8_t)value) continue;
             PyObject *o = PyObject_CallNoArgs(cls);
             if (!o) goto out;
-            PyObject *ik = PyLong_FromSsize_t(k), *cnt = PyLong_FromLong(c[k]);
-            int bad = !ik || !cnt || PyObject_SetAttr(o, s_k, ik) < 0 || PyDict_SetItem(o, s_count, cnt) < 0 ||
-                      PyDict_SetItem(cache, PyList_GET_ITEM(keys, k), o) < 0;
-            Py_XDECREF(ik); Py_XDECREF(cnt); Py_DECREF(o);
+            PyObject *ik = PyLong_FromSsize_t(k);
+            int bad = !ik || PyObject_SetAttr(o, s_k, ik) < 0 || PyDict_SetItem(cache, PyList_GET_ITEM(keys, k), o) < 0;
+            Py_XDECREF(ik); Py_DECREF(o);
             if (bad) goto out;
             done++;
         }
     }
     res = PyLong_FromSsize_t(done);
 out:
-    Py_XDECREF(s_k); Py_XDECREF(s_count);
+    Py_XDECREF(s_k);
+    if (gc_was) PyGC_Enable();
     PyBuffer_Release(&sel); PyBuffer_Release(&counts);
     return res;
 }

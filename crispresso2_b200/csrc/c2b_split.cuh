@@ -659,7 +659,7 @@ C2B_DEV void classify_read(const KParams &P, int64_t rd, const BPre &pre, const 
             }
         } else if (ambiguous && nth == 0 && w > 0 && lane == 0) sc_add(SC, C2B_S_AMBIGUOUS_W, w);
         if (counted && lane == 0 && (two_scans || expand)) {
-            const bool discarded = two_scans && (o.del_n > 0 || o.ins_n > 0), joined = !ONE && expand && rec.n_winners > 1;
+            const bool discarded = two_scans && (o.del_n > 0 || o.ins_n > 0), joined = !ONE && expand && !first && rec.n_winners > 1;   // assign-first is tested first (:780-785)
             if (discarded != joined) sc_add(SC, modified ? C2B_S_CLASS_MODIFIED : C2B_S_CLASS_UNMODIFIED, discarded ? w : -w);
         }
         int irr = keep_irr;

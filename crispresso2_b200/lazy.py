@@ -25,23 +25,27 @@ class LazyVariant(dict):
     __slots__ = ("_k",)
     _src = None                                        # per-batch subclass attribute: the BatchSource
 
-    def __init__(self):
-        dict.__init__(self)
-        self._k = -1
+    # no Python-level __init__: instances are created half a million at a time (c2b_pyext.fill_cache); `_k` is the read's
+    # index in the batch until the entry is materialised, -1 (or unset) afterwards
 
     # -- materialisation ---------------------------------------------------------------------------------------
     def _fill(self):
-        k = self._k
+        k = getattr(self, "_k", -1)
         if k >= 0:
             self._k = -1
-            full = type(self)._src.variant(k)
-            if dict.__contains__(self, "count"):
-                full["count"] = dict.__getitem__(self, "count")
+            src = type(self)._src
+            full = src.variant(k)
+            full["count"] = dict.__getitem__(self, "count") if dict.__contains__(self, "count") else int(src.counts[k])
             dict.update(self, full)
 
     def __missing__(self, key):
-        if self._k < 0:
+        k = getattr(self, "_k", -1)
+        if k < 0:
             raise KeyError(key)
+        if key == "count":                             # the dedup multiplicity: answered from the batch's count array
+            c = int(type(self)._src.counts[k])
+            dict.__setitem__(self, "count", c)
+            return c
         self._fill()
         return dict.__getitem__(self, key)
 
@@ -145,8 +149,9 @@ class BatchSource:
     edit lists (reads whose list overflowed the batch's edit cap).  `parts` (multi-GPU): [(first read index, BatchResult,
     fix)] per rank, contiguous shards in read order."""
 
-    def __init__(self, res, keys, ref_names, refs, ref_id=None, fix=None, parts=None):
+    def __init__(self, res, keys, ref_names, refs, counts, ref_id=None, fix=None, parts=None):
         self.keys, self.ref_names, self.refs, self.ref_id = keys, list(ref_names), refs, ref_id
+        self.counts = counts                               # dedup multiplicity per read (variant['count'])
         self.parts = parts if parts is not None else [(0, res, fix or {})]
         self.starts = [p[0] for p in self.parts]
 
@@ -178,7 +183,7 @@ def make_keys(buf, off):
 
 
 def fill_cache(cache, keys, sel, counts, cls, value=1):
-    """cache[keys[k]] = cls() with ._k = k and ['count'] = counts[k], for every k with sel[k] == value, in k order"""
+    """cache[keys[k]] = cls() with ._k = k, for every k with sel[k] == value, in k order (counts: see LazyVariant.__missing__)"""
     sel = np.ascontiguousarray(sel, dtype=np.uint8)
     counts = np.ascontiguousarray(counts, dtype=np.int32)
     if _ext is not None:
@@ -187,7 +192,6 @@ def fill_cache(cache, keys, sel, counts, cls, value=1):
     for k in np.nonzero(sel == value)[0].tolist():
         o = cls()
         o._k = k
-        dict.__setitem__(o, "count", int(counts[k]))
         cache[keys[k]] = o
         n += 1
     return n

@@ -307,6 +307,11 @@ const char *c2b_fastq_last_error(void);
 int  c2b_rc_merge_weights(const uint8_t *seqs, const int64_t *offsets, int64_t n, const int32_t *counts,
                           const uint8_t *member, int32_t *weights, int32_t n_threads);
 
+/* Reads the engine cannot take (empty, longer than max_len, a symbol other than A C G T N): out[k] = 1.  Host threads.
+ * Returns their number.  (The reference indexes its score table with whatever byte arrives -- lower case out of bounds,
+ * Align.pyx:212 -- and its quantification loop raises KeyError on IUPAC codes, CRISPRessoCORE.py:4081.)             */
+int64_t c2b_screen_reads(const uint8_t *seqs, const int64_t *offsets, int64_t n, int32_t max_len, uint8_t *out, int32_t n_threads);
+
 /* replaces: filterFastqs.filterFastqs for single-end input (CRISPResso2/filterFastqs.py:29-229, called at
  * CRISPRessoCORE.py:3716-3717): keep a record iff min(q) >= min_bp_qual_in_read and mean(q) >= min_av_read_qual (each when
  * non-zero), mask bases with q < min_bp_qual_or_N as 'N'; q = byte - 33 (uint8).  Same record/line rules as the reference's

@@ -215,9 +215,18 @@ def check_band_fallback(engine, n=24, seed=31):
         else:
             s = amp
         reads.append(s[:250])
+    import os
+    os.environ["C2B_NO_SPLIT"] = "1"                       # the general kernel alone: its packed path keeps a banded slab
+    try:
+        check_against_oracle(engine, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
+        pairs, singles = engine.path_counts()
+        assert pairs > 0 and engine.band_reruns() > 0
+    finally:
+        del os.environ["C2B_NO_SPLIT"]
+    # the two-kernel form sends the same pairs to the general kernel with the full slab straight away
     check_against_oracle(engine, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
-    pairs, singles = engine.path_counts()
-    assert pairs > 0 and engine.band_reruns() > 0
+    engine.path_counts()
+    assert engine.band_reruns() == 0
 
 
 def check_ring_equals_full(engine, n=96, I=250, seed=41, oracle_subset=0):
