@@ -27,6 +27,7 @@ from .resources import payload_from_lists
 _COMP = str.maketrans("ACGTN_-", "TGCAN_-")
 _engines = {}
 _blocks = {}
+last_timings = {}                 # seconds of the last process_fastq call by stage (bench.py's api leg reports them)
 
 
 def reverse_complement(seq):
@@ -343,10 +344,17 @@ def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_
     engine = engine or get_engine()
     # FASTQ read + dedup of CRISPRessoCORE.py:1820-1849, done natively (c2b_fastq_dedup: threads, exact); the packed
     # unique sequences feed the batch call directly
+    import time
+    t0 = time.perf_counter()
     dd = fastq.dedup_file(fastq_filename, lib_path=engine.lib_path)
+    last_timings.clear()
+    last_timings["ingest_dedup"] = time.perf_counter() - t0
+    last_timings["n_reads"], last_timings["n_unique"] = int(dd.n_reads), int(len(dd.counts))
+    t0 = time.perf_counter()
     if not variantCache:
         buf, off, counts = dd.buf, dd.off, dd.counts
         keys = lazy.make_keys(buf, off)
+        last_timings["keys"] = time.perf_counter() - t0
     else:                                                   # caller pre-seeded the cache: same += semantics, same key order
         for seq, c in zip(dd.uniques, dd.counts.tolist()):
             variantCache[seq] = variantCache.get(seq, 0) + c
@@ -376,6 +384,8 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
     single-process call produces."""
     from . import lazy
     import logging
+    import time
+    t_start = time.perf_counter()
     n = len(keys)
     flags = _flags(args)
     configure_engine(engine, args, refs, ref_names, aln_matrix)
@@ -400,6 +410,8 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
         buf_g, off_g, counts_g, keys_g = buf, off, counts, keys
     ng = len(keys_g)
     weights = merge_weights_packed(buf_g, off_g, counts_g, lib_path=engine.lib_path)     # needs the global unique table: before sharding
+    last_timings["screen_rc_merge"] = time.perf_counter() - t_start
+    t_gpu = time.perf_counter()
     if group is None:
         res, _ = align_uniques(engine, None, counts_g, ref_names, refs, flags, weights=weights, packed=(buf_g, off_g), compact=True)
         parts = [(0, res, _complete_edit_lists(engine, res, buf_g, off_g, flags))]
@@ -430,6 +442,8 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
                     cache_r2[id(d)] = _result_from(engine, d, flags)
                 fx[k] = (cache_r2[id(d)], j)
             parts.append((g["lo"], _result_from(engine, g["res"], flags), fx))
+    last_timings["gpu_batch"] = time.perf_counter() - t_gpu
+    t_tab = time.perf_counter()
     # serial-branch statistics, part by part (rank order = unique order)
     st = dict.fromkeys(_STAT_KEYS, 0)
     aligned = np.zeros(ng, dtype=bool)
@@ -469,6 +483,7 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
             raise EngineError("device aln_stats disagree with per-read records for %s: %d != %d" % (key, val, st[key]))
     block.class_extra = extra
     _blocks[id(variantCache)] = block
+    last_timings["stats_cache"] = time.perf_counter() - t_tab
     return st, not_aligned
 
 

@@ -211,17 +211,26 @@ __global__ void __launch_bounds__(B_WARPS_PER_CTA * 32, C2B_B_MIN_CTAS) c2b_clas
     const int64_t total_bytes = P.offsets[P.n_reads];
     int64_t rd = (int64_t)blockIdx.x * B_WARPS_PER_CTA + (threadIdx.x >> 5);
     if (rd >= P.n_reads) return;
-    BPre pre = classify_prefetch<ONE>(P, rd, total_bytes);
+    ScAcc<ONE ? 1 : RG_MAX_REFS> acc;
+    sc_init(acc);
+    // two-deep input pipeline: stage A of read rd + 2 nw and stage B of read rd + nw are in flight while read rd is classified
+    BPreA a1 = classify_pre_a(P, rd);
+    BPre pre = classify_pre_b<ONE>(P, rd, a1, total_bytes);
+    if (rd + nw < P.n_reads) a1 = classify_pre_a(P, rd + nw);
     while (rd < P.n_reads) {
         const BPre cur = pre;
         if (cur.go) classify_stage<ONE>(cur, S);
         __syncwarp();
         const int64_t nxt = rd + nw;
-        if (nxt < P.n_reads) pre = classify_prefetch<ONE>(P, nxt, total_bytes);     // in flight while this read is classified
-        if (cur.go) classify_read<ONE>(P, rd, cur, S);
+        if (nxt < P.n_reads) {
+            pre = classify_pre_b<ONE>(P, nxt, a1, total_bytes);
+            if (nxt + nw < P.n_reads) a1 = classify_pre_a(P, nxt + nw);
+        }
+        if (cur.go) classify_read<ONE>(P, rd, cur, S, acc);
         __syncwarp();
         rd = nxt;
     }
+    sc_flush(acc, P);
 }
 #endif
 
@@ -807,8 +816,10 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
             static BSmem BS;
             const int64_t total_bytes = d_offsets[n_reads];
             for (int64_t rd = 0; rd < n_reads; rd++) {
-                if (one) emu::run_warp([&]() { const BPre b = classify_prefetch<true>(P, rd, total_bytes); if (b.go) { classify_stage<true>(b, BS); wp::sync(); classify_read<true>(P, rd, b, BS); } });
-                else emu::run_warp([&]() { const BPre b = classify_prefetch<false>(P, rd, total_bytes); if (b.go) { classify_stage<false>(b, BS); wp::sync(); classify_read<false>(P, rd, b, BS); } });
+                if (one) emu::run_warp([&]() { ScAcc<1> acc; sc_init(acc); const BPreA a = classify_pre_a(P, rd); const BPre b = classify_pre_b<true>(P, rd, a, total_bytes);
+                                               if (b.go) { classify_stage<true>(b, BS); wp::sync(); classify_read<true>(P, rd, b, BS, acc); } sc_flush(acc, P); });
+                else emu::run_warp([&]() { ScAcc<RG_MAX_REFS> acc; sc_init(acc); const BPreA a = classify_pre_a(P, rd); const BPre b = classify_pre_b<false>(P, rd, a, total_bytes);
+                                            if (b.go) { classify_stage<false>(b, BS); wp::sync(); classify_read<false>(P, rd, b, BS, acc); } sc_flush(acc, P); });
             }
             P.pair_order = d_left; P.n_dev = wk + 3; P.work_counter = wk + 2; P.tbq = nullptr; P.rgops = nullptr; P.tbb = nullptr;
         }

@@ -94,6 +94,25 @@ def write_fastq(path, reads):
             fh.write("@r%d\n%s\n+\n%s\n" % (k, s, "I" * len(s)))
 
 
+def write_fastq_fast(path, reads):
+    """FASTQ of a uint8 [n, L] read matrix in one vectorised pass (fixed-width names '@r%09d', quality 'I')."""
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    n, L = reads.shape
+    rec = np.empty((n, 11 + 1 + L + 1 + 2 + L + 1), dtype=np.uint8)
+    rec[:, 0], rec[:, 1] = ord("@"), ord("r")
+    idx = np.arange(n, dtype=np.int64)
+    for d in range(9):
+        rec[:, 10 - d] = ord("0") + (idx // 10 ** d) % 10
+    rec[:, 11] = 10
+    rec[:, 12:12 + L] = reads
+    rec[:, 12 + L] = 10
+    rec[:, 13 + L], rec[:, 14 + L] = ord("+"), 10
+    rec[:, 15 + L:15 + 2 * L] = ord("I")
+    rec[:, 15 + 2 * L] = 10
+    with open(path, "wb") as fh:
+        fh.write(rec.tobytes())
+
+
 # ------------------------------------------------------------------------------------------ BASELINE.json configs[2..4]
 def hdr_workload(arng, rng, n_reads):
     """configs[2]: WT + HDR (WT with a 3-bp substitution + 6-bp insertion near the cut) + a third allele with
