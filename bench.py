@@ -698,7 +698,7 @@ def parity_gate(eng, w, args, recs, alns, d_str, d_ed, W, R, dev):
     else:
         bad_counts = []
         for name, q in quant.items():
-            bad_counts += BG.compare_block(block, q, [name])
+            bad_counts += BG.compare_block(block, q, [name], per_amplicon=True)
     ok = same and summ["n_bad"] == 0 and not bad_counts and over == 0
     return {"reads": G, "ok": bool(ok), "timed_equals_gate_run": bool(same), "reads_differing_from_oracle": summ["n_bad"],
             "examples": [str(b) for b in summ["bad"][:3]], "oracle_undefined_skipped": summ["n_skipped"],

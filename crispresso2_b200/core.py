@@ -27,6 +27,7 @@ from .resources import payload_from_lists
 _COMP = str.maketrans("ACGTN_-", "TGCAN_-")
 _engines = {}
 _blocks = {}
+_sources = {}                     # id(variantCache) -> lazy.BatchSource of the process_fastq call that filled it (alleles.py)
 last_timings = {}                 # seconds of the last process_fastq call by stage (bench.py's api leg reports them)
 
 
@@ -465,6 +466,8 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
         st["N_COMPUTED_NOTALN"] += n_bad
         st["N_CACHED_NOTALN"] += cb - n_bad
     src = lazy.BatchSource(None, keys_g, ref_names, refs, counts_g, parts=parts)
+    src.weights, src.flags, src.lib_path = weights, flags, engine.lib_path
+    _sources[id(variantCache)] = src
     cls = src.lazy_class()
     not_aligned = {}
     sel = aligned.astype(np.uint8)
@@ -518,6 +521,14 @@ def process_fastq_sharded(fastq_filename, variantCache, ref_names, refs, args, f
     world_group = group if group is not None else dist.group.WORLD
     return _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, refs, args, aln_matrix, on_out_of_contract,
                             group=world_group)
+
+
+def source_of(variantCache):
+    """Compact results (lazy.BatchSource) of the process_fastq call that filled this variantCache."""
+    try:
+        return _sources[id(variantCache)]
+    except KeyError:
+        raise KeyError("this variantCache was not filled by crispresso2_b200.core.process_fastq") from None
 
 
 def quantify(variantCache):

@@ -480,6 +480,9 @@ C2B_DEV int score_milli(int m, int n)
 {
     // m <= n <= C2B_MAX_ALN_LEN = 1024: 100000*m < 2^27, so 32-bit unsigned arithmetic is exact (and the division is a
     // fraction of the 64-bit one's code)
+#ifdef C2B_DBG_DIV
+    if (n == 0) n = 1;
+#endif
     const uint32_t num = 100000u * (uint32_t)m, d = (uint32_t)n;
     uint32_t q = num / d; const uint32_t r = num - q * d;
     if (2u * r > d || (2u * r == d && (q & 1u))) q++;
@@ -1561,8 +1564,8 @@ C2B_DEV void process_quad(const KParams &P, WarpSmem &S, QuadSmem &Q, const uint
     wp::sync();
     if (lane == 0) {
         wp::addg(P.stats + 2, 4);
-        wp::addg(P.stats + 5, wp::popc(passmask));
-        wp::addg(P.stats + 6, 4 - wp::popc(passmask));
+        wp::addg(P.stats + 5, 2 * wp::popc(passmask));            // [5], [6]: in reads (the host reports pairs)
+        wp::addg(P.stats + 6, 2 * (4 - wp::popc(passmask)));
     }
 #pragma unroll 1
     for (int q = 0; q < 4; q++) {
@@ -1655,8 +1658,8 @@ C2B_DEVNOINL void process_quad_multi(const KParams &P, WarpSmem &S, QuadSmem &Q,
     if (P.phase_sync) wp::grp_sync(P.phase_sync);
     if (lane == 0) {
         wp::addg(P.stats + 2, 4);
-        wp::addg(P.stats + 5, npass);
-        wp::addg(P.stats + 6, 4 * P.n_refs - npass);
+        wp::addg(P.stats + 5, 2 * npass);
+        wp::addg(P.stats + 6, 2 * (4 * P.n_refs - npass));
     }
 #pragma unroll 1
     for (int q = 0; q < 4; q++) {

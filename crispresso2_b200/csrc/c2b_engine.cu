@@ -85,7 +85,10 @@ static void rt_host_free(void *p) { free(p); }
 #define C2B_MIN_CTAS_PER_SM 2
 #endif
 constexpr int WARPS_PER_CTA = C2B_WARPS_PER_CTA;      // launch-bounds maximum; the launch may use fewer (env C2B_WARPS_PER_CTA)
-constexpr int B_WARPS_PER_CTA = 4;                    // CLASSIFY kernel
+#ifndef C2B_B_WARPS
+#define C2B_B_WARPS 4
+#endif
+constexpr int B_WARPS_PER_CTA = C2B_B_WARPS;                    // CLASSIFY kernel
 #ifndef C2B_B_MIN_CTAS
 #define C2B_B_MIN_CTAS 6
 #endif
@@ -917,8 +920,9 @@ int c2b_path_counts(c2b_engine *e, int64_t *pair_items, int64_t *single_items)
     int64_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     RTCHK(rt_d2h(v, e->work.p, 64, e->stream));
     RTCHK(rt_sync(e->stream));
-    e->band_reruns = v[4]; e->ring_pairs = v[5]; e->ring_fallbacks = v[6];
-    if (pair_items) *pair_items = v[2];
+    // the ALIGN kernel counts reads ([5] kept by the ring, [6] sent on, [7] fully aligned); reported in pairs
+    e->band_reruns = v[4]; e->ring_pairs = (v[5] + 1) / 2; e->ring_fallbacks = (v[6] + 1) / 2;
+    if (pair_items) *pair_items = v[2] + (v[7] + 1) / 2;
     if (single_items) *single_items = v[3];
     return C2B_OK;
 }

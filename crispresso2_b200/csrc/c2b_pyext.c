@@ -73,7 +73,33 @@ out:
     return res;
 }
 
+/* slices(buf, starts, lens) -> list[str]: text of buf[starts[k] : starts[k] + lens[k]] (ASCII / latin-1) -- the aligned strings
+ * of the allele table as Python objects, one C call for the whole column */
+static PyObject *slices(PyObject *self, PyObject *args)
+{
+    Py_buffer buf, st, ln;
+    if (!PyArg_ParseTuple(args, "y*y*y*", &buf, &st, &ln)) return NULL;
+    const Py_ssize_t n = st.len / 8;
+    const int64_t *o = (const int64_t *)st.buf;
+    const int32_t *l = (const int32_t *)ln.buf;
+    const char *b = (const char *)buf.buf;
+    PyObject *out = NULL;
+    if (ln.len / 4 < n) { PyErr_SetString(PyExc_ValueError, "lens shorter than starts"); goto done; }
+    out = PyList_New(n);
+    if (!out) goto done;
+    for (Py_ssize_t k = 0; k < n; k++) {
+        if (o[k] < 0 || l[k] < 0 || o[k] + l[k] > buf.len) { PyErr_SetString(PyExc_ValueError, "slice outside the buffer"); Py_CLEAR(out); goto done; }
+        PyObject *s = PyUnicode_DecodeLatin1(b + o[k], (Py_ssize_t)l[k], NULL);
+        if (!s) { Py_CLEAR(out); goto done; }
+        PyList_SET_ITEM(out, k, s);
+    }
+done:
+    PyBuffer_Release(&buf); PyBuffer_Release(&st); PyBuffer_Release(&ln);
+    return out;
+}
+
 static PyMethodDef methods[] = {
+    {"slices", slices, METH_VARARGS, "slices(buf, starts, lens) -> list of str"},
     {"make_keys", make_keys, METH_VARARGS, "make_keys(buf, off) -> list of str"},
     {"fill_cache", fill_cache, METH_VARARGS, "fill_cache(cache, keys, sel, counts, cls, value) -> int"},
     {NULL, NULL, 0, NULL}};

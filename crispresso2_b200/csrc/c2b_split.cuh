@@ -38,6 +38,11 @@ C2B_DEV void leftover_pair(const KParams &P, int64_t rdA, int64_t rdB)
     }
 }
 
+C2B_DEV void leftover_one(const KParams &P, int64_t rd)
+{
+    if (wp::lane() == 0) { const unsigned long long pos = wp::fetch_add(P.left_n, 1ull); P.left[pos] = (int32_t)rd; }
+}
+
 // read -> alphabet codes for reads of at most RG_COMBO symbols; true if a symbol is outside the alphabet
 C2B_DEV bool load_codes_a(const KParams &P, int64_t off, int J, uint8_t *fw, uint8_t *rc)
 {
@@ -177,14 +182,16 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
         for (int q = 0; q < 4; q++) {
             if (2 * (first + q) >= P.n_reads) break;
             const int64_t rdA = read_at(P, 2 * (first + q));
-            const int64_t rdB = 2 * (first + q) + 1 < P.n_reads ? read_at(P, 2 * (first + q) + 1) : rdA;
-            leftover_pair(P, rdA, rdB);
+            // the list mixes pairs and single reads, and the general kernel takes its entries two at a time: the odd last read
+            // goes on it ONCE (an (rdA, rdA) entry could be split over two work items and be counted twice)
+            if (2 * (first + q) + 1 < P.n_reads) leftover_pair(P, rdA, read_at(P, 2 * (first + q) + 1));
+            else leftover_one(P, rdA);
         }
         return;
     }
     const int k0 = multi ? 0 : r0, k1 = multi ? P.n_refs : r0 + 1;
     uint2 *tbq = reinterpret_cast<uint2 *>(P.tbq + (int64_t)warp_slot * P.TS * 64);
-    uint32_t okmask = 0, modes = 0;
+    uint32_t okmask = 0, modes = 0, both2 = 0;              // both2: reads (bit 2q + h) to be aligned on both strands
     int Jg = 0, Jmax = 0;
 #pragma unroll 1
     for (int q = 0; q < 4; q++) {
@@ -203,20 +210,33 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
             if (k == k0) mAB = m; else agree = agree && (m == mAB);
         }
         const int mA = mAB & 3, mB = mAB >> 2;
-        if (!bad && agree && mA != 2 && mB != 2) {           // a read that needs both strands takes the general kernel
-            const uint8_t *cA = mA ? S.rc[0] : S.fw[0], *cB = mB ? S.rc[1] : S.fw[1];
+        if (!bad && agree) {
+            // a read whose seed test calls for both strands (mode 2) rides along on its forward strand -- its half of the ring
+            // result is ignored -- and is aligned on both strands over the full matrix below (r02d: such a read sent its whole
+            // pair to the general kernel: 0.8 % of the reads, 0.77 ms of a 15.7 ms batch)
+            const uint8_t *cA = mA == 1 ? S.rc[0] : S.fw[0], *cB = mB == 1 ? S.rc[1] : S.fw[1];
             for (int p = lane; p < J; p += 32) S.combo[q][p] = (uint8_t)(cA[p] * P.nq + cB[p]);
             okmask |= 1u << q; modes |= (uint32_t)mAB << (4 * q);
+            if (mA == 2) both2 |= 1u << (2 * q);
+            if (mB == 2) both2 |= 2u << (2 * q);
             if (g == q) Jg = J;
             if (J > Jmax) Jmax = J;
         }
         wp::sync();
     }
-    uint32_t good = okmask;                                  // pairs whose band held for every reference so far
-    int npass = 0, ntried = 0;
+    // reads (bit 2q + h: read h of pair q) whose band held for every reference so far.  The two halves of a packed value
+    // are independent DPs, so a pair may keep one read and send only the other to the general kernel (r02b: per pair,
+    // which doubled the left-over list).
+    uint32_t good2 = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) if ((okmask >> q) & 1u) good2 |= 3u << (2 * q);
+    if (!P.tb) { good2 &= ~both2; both2 = 0; }              // no full-matrix scratch: general kernel
+    int npass = 0, ntried = 0, nboth = 0;
 #pragma unroll 1
-    for (int k = k0; k < k1 && good; k++) {
+    for (int k = k0; k < k1 && good2; k++) {
         const RefDev &R = refdev(P, k);
+        const uint32_t ring2 = good2 & ~both2;              // reads whose ring result counts
+        nboth += wp::popc(both2 & good2);
         const bool staged = (k == 0 && staged_prof != nullptr);
         if (staged) dp_ring<true>(P, R, staged_prof, S.combo[g], Jg, Jmax + R.lstar, tbq, S.fin);
         else dp_ring<false>(P, R, R.prof2, S.combo[g], Jg, Jmax + R.lstar, tbq, S.fin);
@@ -226,28 +246,36 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
         wp::sync();
         const uint32_t z = wp::max3_2(cM, cY, cX);
         const uint32_t s2 = z & PK_TM;
-        // biased value = 4*(score + beta*(I+J) + 512) + tag: both reads must beat the out-of-band bound (ring_bound)
+        // biased value = 4*(score + beta*(I+J) + 512) + tag: a read must beat the out-of-band bound (ring_bound)
         const int thr = ring_bound(P, R, Jg) + 512 - P.ge * (R.I + Jg);
-        const bool pass = Jg > 0 && (int)((z & 0xffffu) >> 2) > thr && (int)(z >> 18) > thr;
-        const uint32_t b = wp::ballot(pass);
-        uint32_t passmask = ((b & 1u) | ((b >> 7) & 2u) | ((b >> 14) & 4u) | ((b >> 21) & 8u)) & good;
-        ntried += wp::popc(good);
+        const bool passA = Jg > 0 && (int)((z & 0xffffu) >> 2) > thr, passB = Jg > 0 && (int)(z >> 18) > thr;
+        const uint32_t bA = wp::ballot(passA), bB = wp::ballot(passB);
+        uint32_t pass2 = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) pass2 |= (((bA >> (8 * q)) & 1u) | (((bB >> (8 * q)) & 1u) << 1)) << (2 * q);
+        pass2 &= ring2;
+        ntried += wp::popc(ring2);
         {
             int Jq[4], s0[4];
             Walked wk4[4];
+            uint32_t walkmask = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const uint32_t sq = wp::shflu(s2, 8 * q);
                 Jq[q] = wp::shfl(Jg, 8 * q);
                 s0[q] = (lane & 16) ? (int)(sq >> 16) : (int)(sq & 3u);
+                if ((pass2 >> (2 * q)) & 3u) walkmask |= 1u << q;
             }
-            walk_ring4(P, R, Jq, tbq, s0, passmask, wk4);
+            walk_ring4(P, R, Jq, tbq, s0, walkmask, wk4);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                if (!((passmask >> q) & 1u)) continue;
+                if (!((walkmask >> q) & 1u)) continue;
                 const Walked &wk = wk4[q];
-                if (wp::ballot(wk.err != 0)) { passmask &= ~(1u << q); continue; }    // cannot happen when the bound holds; general kernel then
+                const uint32_t eb = wp::ballot(wk.err != 0);             // cannot happen when the bound holds; general kernel then
+                if (eb & 0xffffu) pass2 &= ~(1u << (2 * q));
+                if (eb >> 16) pass2 &= ~(2u << (2 * q));
                 const int h = lane >> 4, hl = lane & 15;
+                if (!((pass2 >> (2 * q + h)) & 1u)) continue;
                 const int64_t rd = read_at(P, 2 * (first + q) + h);
                 const int64_t slot = oslot(P, rd, k);
                 if (hl < P.NW) P.gops[slot * P.NW + hl] = wk.ops;
@@ -257,8 +285,67 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
                 }
             }
         }
-        npass += wp::popc(passmask);
-        good &= passmask;
+        npass += wp::popc(pass2);
+        // Full-matrix DPs (align_pair, the packed path of c2b_core.cuh), here and now, for what the ring did not settle for this
+        // reference: (job 0) pairs with a read the ring could not prove exact; (jobs 1, 2) a read that needs both strands,
+        // packed with ITSELF -- forward strand in the low halves, reverse complement in the high ones -- the better identity
+        // wins, the reverse complement only if strictly better (CRISPRessoCORE.py:678-687).  r02b sent all of these to the
+        // general kernel, whose launch then took 0.77 ms for 0.8 % of the reads: the latency of single pairs through its whole
+        // per-read path; inside this persistent kernel the same DPs hide among the other warps' work.
+        const uint32_t failed = ring2 & ~pass2;
+        if ((failed | (both2 & good2)) && P.tb) {
+            uint2 *tb2 = reinterpret_cast<uint2 *>(P.tb + (int64_t)warp_slot * P.tb_words_per_warp);
+            int32_t *bnd = P.bnd + (int64_t)warp_slot * P.bnd_words_per_warp;
+            const int h = lane >> 4, hl = lane & 15;
+#pragma unroll 1
+            for (int job = 0; job < 16; job++) {
+                const int q = job >> 2, kind = job & 3;              // kind 0: pair q; 1 / 2: read A / B of pair q on both strands
+                if (kind == 3) continue;
+                const uint32_t fq = (failed >> (2 * q)) & 3u;
+                const uint32_t bq = ((both2 & good2) >> (2 * q)) & 3u;
+                if (kind == 0 ? fq == 0 : !((bq >> (kind - 1)) & 1u)) continue;
+                const int Jp = wp::shfl(Jg, 8 * q);
+                const uint8_t *combo = S.combo[q];
+                wp::sync();
+                if (kind) {
+                    const int64_t rdx = read_at(P, 2 * (first + q) + (kind - 1));
+                    load_codes_a(P, P.offsets[rdx], Jp, S.fw[0], S.rc[0]);
+                    wp::sync();
+                    for (int p = lane; p < Jp; p += 32) S.fw[1][p] = (uint8_t)(S.fw[0][p] * P.nq + S.rc[0][p]);
+                    combo = S.fw[1];
+                    wp::sync();
+                }
+                const Walked wk = align_pair(P, R, staged ? staged_prof : R.prof2, staged, combo, Jp, tb2, nullptr, bnd);
+                const uint32_t eb = wp::ballot(wk.err != 0);             // the reference's undefined zone: general kernel
+                if (kind == 0) {
+                    const bool mine = ((fq >> h) & 1u) && !((h ? (eb >> 16) : (eb & 0xffffu)));
+                    if (mine) {
+                        const int64_t rd = read_at(P, 2 * (first + q) + h);
+                        const int64_t slot = oslot(P, rd, k);
+                        if (hl < P.NW) P.gops[slot * P.NW + hl] = wk.ops;
+                        if (hl == 0) P.gmeta[slot] = gmeta_pack(wk.n, (int)((modes >> (4 * q + 2 * h)) & 3u) == 1, GM_NONE);
+                    }
+                    const uint32_t mb = wp::ballot(mine);
+                    if (mb & 0xffffu) pass2 |= 1u << (2 * q);
+                    if (mb >> 16) pass2 |= 2u << (2 * q);
+                } else {
+                    const ColOut co = columns<true>(P, R, nullptr, nullptr, h ? S.rc[0] : S.fw[0], Jp, wk.ops, wk.n, 0, nullptr, nullptr);
+                    const int sc = score_milli(co.n_match, wk.n > 0 ? wk.n : 1);
+                    const int sc_fw = wp::shfl(sc, 0), sc_rc = wp::shfl(sc, 16);
+                    const int pick = sc_rc > sc_fw ? 1 : 0;
+                    const uint32_t bit = 1u << (2 * q + kind - 1);
+                    if (eb) good2 &= ~bit;                                   // either strand undefined: the general kernel decides
+                    else if (h == pick) {
+                        const int64_t rd = read_at(P, 2 * (first + q) + (kind - 1));
+                        const int64_t slot = oslot(P, rd, k);
+                        if (hl < P.NW) P.gops[slot * P.NW + hl] = wk.ops;
+                        if (hl == 0) P.gmeta[slot] = gmeta_pack(wk.n, pick, GM_NONE);
+                    }
+                }
+            }
+        }
+        pass2 |= both2 & good2;                                              // both-strand reads: settled above (or dropped from good2)
+        good2 &= pass2;
         wp::sync();
     }
 #ifndef C2B_EMU
@@ -270,19 +357,22 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
             asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + o) : "memory");
     }
 #endif
-    if (lane == 0) {
-        wp::addg(P.stats + 2, wp::popc(good));
+    if (lane == 0) {                                         // path statistics, in reads (the host reports pairs)
+        wp::addg(P.stats + 7, wp::popc(good2));
         wp::addg(P.stats + 5, npass);
-        wp::addg(P.stats + 6, ntried - npass + (k1 - k0) * (4 - wp::popc(okmask)));
+        wp::addg(P.stats + 6, ntried - npass + nboth + 2 * (k1 - k0) * (4 - wp::popc(okmask)));
     }
 #pragma unroll 1
     for (int q = 0; q < 4; q++) {
         const int64_t rdA = read_at(P, 2 * (first + q)), rdB = read_at(P, 2 * (first + q) + 1);
-        if ((good >> q) & 1u) {
+        const uint32_t gq = (good2 >> (2 * q)) & 3u;
+        if (gq) {
             const int64_t rd = (lane & 1) ? rdB : rdA;
             const int k = k0 + (lane >> 1);
-            if (k < k1) { const int64_t slot = oslot(P, rd, k); P.gmeta[slot] = (P.gmeta[slot] & 0x00ffffffu) | (GM_ALIGNED << 24); }
-        } else leftover_pair(P, rdA, rdB);
+            if (k < k1 && ((gq >> (lane & 1)) & 1u)) { const int64_t slot = oslot(P, rd, k); P.gmeta[slot] = (P.gmeta[slot] & 0x00ffffffu) | (GM_ALIGNED << 24); }
+        }
+        if (gq == 0) leftover_pair(P, rdA, rdB);
+        else if (gq != 3u) leftover_one(P, gq == 1u ? rdB : rdA);
     }
 }
 

@@ -320,6 +320,37 @@ int64_t c2b_screen_reads(const uint8_t *seqs, const int64_t *offsets, int64_t n,
 int  c2b_fastq_filter(const char *path_in, const char *path_out, int32_t min_bp_qual_in_read, int32_t min_av_read_qual,
                       int32_t min_bp_qual_or_N, int32_t n_threads, int64_t *n_in, int64_t *n_out);
 
+/* ---- allele-level consumers (host code, csrc/c2b_alleles.cpp): SURVEY.md section 8(f) rank 2 ----------------------------
+ * replaces: the allele table of CRISPRessoCORE.py:3909-3959 + :4298-4303 (rows, %Reads, sort), the text of
+ * Alleles_frequency_table.txt (:4498-4535) and CRISPRessoShared.get_dataframe_around_cut[_asymmetrical] (CRISPRessoShared.py:
+ * 1513-1531), for alignments held in the compact form of c2b_align_batch_compact.  Row i = one (unique read, reference)
+ * alignment: row_read[i] indexes reads/offsets, row_slot[i] indexes ops (NW words per slot) / meta, row_ref[i] the reference,
+ * row_count[i] = #Reads.  comp256: byte -> complement byte (reads aligned as their reverse complement).             */
+typedef struct c2b_alleles c2b_alleles;
+int  c2b_alleles_build(const uint8_t *reads, const int64_t *offsets, const uint64_t *ops, const uint32_t *meta, int32_t NW,
+                       int64_t n_rows, const int64_t *row_read, const int64_t *row_slot, const int32_t *row_ref,
+                       const int64_t *row_count, int32_t n_refs, const char *const *ref_seqs, const int32_t *ref_lens,
+                       const uint8_t *comp256, int32_t n_threads, c2b_alleles **out);
+void c2b_alleles_free(c2b_alleles *a);
+int64_t        c2b_alleles_n(const c2b_alleles *a);
+const int64_t *c2b_alleles_order(const c2b_alleles *a);    /* rows by (#Reads desc, Aligned_Sequence, Reference_Sequence), stable (:4303) */
+const uint8_t *c2b_alleles_arena(const c2b_alleles *a);    /* row i: aligned read at arena[offsets[i]], aligned reference right after it */
+const int64_t *c2b_alleles_offsets(const c2b_alleles *a);  /* n + 1 */
+const int32_t *c2b_alleles_lengths(const c2b_alleles *a);  /* alignment columns per row */
+/* header + one line per row of `rows`; name_id / status_id / pct_id index the caller's (small) string tables */
+int  c2b_alleles_write_tsv(const c2b_alleles *a, const char *path, int64_t n_sel, const int64_t *rows,
+                           const int32_t *name_id, const char *const *names, const int32_t *status_id, const char *const *statuses,
+                           const int32_t *n_deleted, const int32_t *n_inserted, const int32_t *n_mutated,
+                           const int32_t *pct_id, const char *const *pcts, int32_t n_threads);
+/* per-row arrays are indexed by row id; `rows` lists the rows of the (sorted, filtered) DataFrame in its order.
+ * -> number of groups, C2B_E_LIMIT when a row's alignment lacks reference position cut_point (ValueError in the reference) */
+int64_t c2b_alleles_around_cut(c2b_alleles *a, int64_t n_sel, const int64_t *rows, int32_t cut_point, int32_t plot_left,
+                               int32_t plot_right, const uint8_t *unedited, const int32_t *n_deleted, const int32_t *n_inserted,
+                               const int32_t *n_mutated, const double *pct);
+int32_t c2b_alleles_cut_width(const c2b_alleles *a);
+int  c2b_alleles_cut_fetch(const c2b_alleles *a, uint8_t *seq, uint8_t *ref, int32_t *wlen, uint8_t *unedited, int32_t *n_deleted,
+                           int32_t *n_inserted, int32_t *n_mutated, int64_t *reads, double *pct);
+
 /* pinned host memory (cudaHostAlloc) for callers that want full-speed host<->device copies */
 void *c2b_host_alloc(size_t n_bytes);
 void  c2b_host_free(void *p);

@@ -99,6 +99,23 @@ def run_case(name, argv, keep_files):
         keys = ["ref1_all_insertion_count_vectors", "ref1_all_insertion_left_count_vectors", "ref1_all_deletion_count_vectors",
                 "ref1_all_substitution_count_vectors", "ref1_all_indelsub_count_vectors", "ref1_all_base_count_vectors"]
         rec["ref1"] = {k: _plain(kw.get(k, {})) for k in keys}
+        # allele-level consumers: df_alleles as main() built it (CRISPRessoCORE.py:4298-4303) and what the
+        # reference's own get_dataframe_around_cut_asymmetrical (CRISPRessoShared.py:1518-1531) makes of it
+        from CRISPResso2 import CRISPRessoShared
+        df = kw["df_alleles"]
+        cols = ["#Reads", "Aligned_Sequence", "Reference_Sequence", "n_inserted", "n_deleted", "n_mutated", "Reference_Name",
+                "Read_Status", "Aligned_Reference_Names", "Aligned_Reference_Scores", "ref_positions", "%Reads"]
+        rec["alleles"] = {"tsv": df.loc[:, cols].to_csv(sep="\t", header=True, index=None), "index": [int(x) for x in df.index],
+                          "dtypes": {c: str(df[c].dtype) for c in cols}, "n_total": int(kw["N_TOTAL"]), "around_cut": {}}
+        for rn in kw["ref_names"]:
+            cuts = [int(c) for c in kw["refs"][rn]["sgRNA_cut_points"]] or [len(kw["refs"][rn]["sequence"]) // 2]
+            for cut in cuts:
+                for (pl, pr) in ((20, 20), (7, 31)):
+                    sub = df.loc[df["Reference_Name"] == rn]
+                    if sub.shape[0] == 0:
+                        continue
+                    out = CRISPRessoShared.get_dataframe_around_cut_asymmetrical(sub, cut, pl, pr)
+                    rec["alleles"]["around_cut"]["%s|%d|%d|%d" % (rn, cut, pl, pr)] = out.to_csv(sep="\t", header=True)
         return orig_ctx(*a, **kw)
 
     CRISPRessoCORE.CorePlotContext = ctx_spy

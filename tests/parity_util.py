@@ -36,6 +36,53 @@ def args_from(params):
     return a
 
 
+ALLELE_COLS = ["#Reads", "Aligned_Sequence", "Reference_Sequence", "n_inserted", "n_deleted", "n_mutated", "Reference_Name",
+               "Read_Status", "Aligned_Reference_Names", "Aligned_Reference_Scores", "ref_positions", "%Reads"]
+
+
+def check_alleles(engine, case, tmp_path):
+    """Allele-level consumers (crispresso2_b200/alleles.py) against what the UNMODIFIED reference produced for the same FASTQ
+    (tests/golden/gen_golden.py): df_alleles as main() handed it to CorePlotContext (every column, the row order and the index),
+    the text of Alleles_frequency_table.txt, and the reference's own get_dataframe_around_cut_asymmetrical for every reference,
+    guide and two window shapes -- compared as the text pandas writes, byte for byte."""
+    from crispresso2_b200 import alleles
+    rec = G.load(case)
+    refs = G.refs_from(rec)
+    fq = tmp_path / (case + ".fastq")
+    with open(fq, "w") as fh:
+        for k, s in enumerate(rec["reads"]):
+            fh.write("@r%d\n%s\n+\n%s\n" % (k, s, "I" * len(s)))
+    args = args_from(rec["params"])
+    if rec.get("ref1", {}).get("ref1_all_deletion_count_vectors"):
+        args.expected_hdr_amplicon_seq = refs[rec["ref_names"][1]]["sequence"]
+    cache = {}
+    core.process_fastq(str(fq), cache, rec["ref_names"], refs, args, [], str(tmp_path), engine=engine, aln_matrix=O.make_matrix())
+    t = alleles.AlleleTable(cache)
+    want = rec["alleles"]
+    assert t.n_total == want["n_total"]
+    df = t.to_dataframe()
+    assert [int(x) for x in df.index] == want["index"]
+    assert {c: str(df[c].dtype) for c in ALLELE_COLS} == want["dtypes"]
+    assert df.loc[:, ALLELE_COLS].to_csv(sep="\t", header=True, index=None) == want["tsv"]
+    # Alleles_frequency_table.txt (CRISPRessoCORE.py:4514: the nine crispresso2Cols columns of the same frame)
+    out = tmp_path / "Alleles_frequency_table.txt"
+    t.write_frequency_table(str(out))
+    text = out.read_text()
+    assert text == df.loc[:, alleles.CRISPRESSO2_COLS].to_csv(sep="\t", header=True, index=None)
+    z = tmp_path / "Alleles_frequency_table.zip"
+    t.write_frequency_zip(str(z))                           # zips the text file and removes it, as CRISPRessoCORE.py:4529-4531
+    import zipfile
+    with zipfile.ZipFile(z) as zf:
+        assert zf.namelist() == ["Alleles_frequency_table.txt"] and zf.read("Alleles_frequency_table.txt").decode() == text
+    assert not out.exists()
+    assert want["around_cut"]
+    for key, text in want["around_cut"].items():
+        rn, cut, pl, pr = key.split("|")
+        got = alleles.get_dataframe_around_cut_asymmetrical(df.loc[df["Reference_Name"] == rn], int(cut), int(pl), int(pr))
+        assert got.to_csv(sep="\t", header=True) == text, key
+    return len(df)
+
+
 REF1_KEYS = {"ref1_all_insertion_count_vectors": "ref1_all_insertion_count",
              "ref1_all_insertion_left_count_vectors": "ref1_all_insertion_left_count",
              "ref1_all_deletion_count_vectors": "ref1_all_deletion_count",
@@ -227,6 +274,31 @@ def check_band_fallback(engine, n=24, seed=31):
     check_against_oracle(engine, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
     engine.path_counts()
     assert engine.band_reruns() == 0
+
+
+def check_leftover_singles(engine, n=43, seed=77):
+    """Left-over list of the ALIGN kernel with single reads on it: pairs in which ONE read fails the ring bound (a random
+    read beside an amplicon-like one) put single entries on the list, and an odd read count puts the last read there alone;
+    the general kernel takes the list two entries at a time, so a read listed twice would be classified -- and counted --
+    twice (r02c: device aln_stats 3 above the per-read records on a 947 601-read batch)."""
+    from crispresso2_b200 import synth
+    rng = np.random.default_rng(seed)
+    amp = synth.random_amplicon(rng, 250)
+    ref = synth.amplicon_setup(amp)
+    base = [r.tobytes().decode() for r in synth.synth_reads(rng, amp, n, 250, sub_rate=0.01, cut=ref["cut_point"])]
+    acgt = list("ACGT")
+    reads = []
+    for k, s in enumerate(base):
+        if k % 7 in (1, 4):                                 # unrelated read: fails the bound, its pair partner passes
+            s = "".join(rng.choice(acgt, 250))
+        elif k % 11 == 5:                                   # 45-bp deletion: leaves the band
+            s = (amp[:80] + amp[125:] + "".join(rng.choice(acgt, 45)))[:250]
+        reads.append(s)
+    assert len(reads) % 2 == 1
+    check_against_oracle(engine, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
+    engine.path_counts()
+    kept, sent = engine.ring_counts()
+    assert kept > 0 and sent > 0, (kept, sent)
 
 
 def check_ring_equals_full(engine, n=96, I=250, seed=41, oracle_subset=0):

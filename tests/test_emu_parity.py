@@ -126,6 +126,11 @@ def test_ring_banded_path_equals_full_matrix(emu, I):
     PU.check_ring_equals_full(emu, n=96, I=I, seed=40 + I, oracle_subset=48)
 
 
+def test_leftover_list_with_single_reads_and_odd_tail(emu):
+    PU.check_leftover_singles(emu)
+    PU.check_leftover_singles(emu, n=9, seed=3)
+
+
 def test_pooled_ref_id(emu):
     PU.check_pooled(emu, n_amplicons=4, reads_per=24)
     PU.check_pooled(emu, n_amplicons=40, reads_per=3, seed=5)          # more references than C2B_MAX_REFS: Pooled only

@@ -223,6 +223,18 @@ def test_ring_banded_path_equals_full_matrix(eng, I):
     PU.check_ring_equals_full(eng, n=24000, I=I, seed=40 + I, oracle_subset=400)
 
 
+@pytest.mark.parametrize("case", G.CASES)
+def test_allele_tables_equal_the_reference(eng, case, tmp_path):
+    """df_alleles, Alleles_frequency_table text and the tables around the cut (crispresso2_b200/alleles.py) against what the
+    unmodified reference made of the same FASTQ (tests/golden)."""
+    assert PU.check_alleles(eng, case, tmp_path) > 100
+
+
+def test_leftover_list_with_single_reads_and_odd_tail(eng):
+    PU.check_leftover_singles(eng, n=4001, seed=5)
+    PU.check_leftover_singles(eng, n=43, seed=77)
+
+
 def test_pooled_ref_id(eng):
     """BASELINE configs[3] shape: many amplicons, each read aligned to its own one (ref_id), one launch."""
     PU.check_pooled(eng, n_amplicons=24, reads_per=120, amp_len=(180, 280))
