@@ -82,7 +82,7 @@ EXPORTS = ["c2b_create", "c2b_destroy", "c2b_last_error", "c2b_configure", "c2b_
            "c2b_classify_aligned", "c2b_host_alloc", "c2b_host_free",
            "c2b_fastq_dedup", "c2b_fastq_dedup_buffer", "c2b_fastq_n_reads", "c2b_fastq_n_unique", "c2b_fastq_max_len",
            "c2b_fastq_seqs", "c2b_fastq_offsets", "c2b_fastq_counts", "c2b_fastq_first_index", "c2b_fastq_free",
-           "c2b_fastq_last_error", "c2b_fastq_filter", "c2b_rc_merge_weights", "c2b_screen_reads",
+           "c2b_fastq_last_error", "c2b_fastq_filter", "c2b_rc_merge_weights", "c2b_screen_reads", "c2b_serial_stats",
            "c2b_alleles_build", "c2b_alleles_free", "c2b_alleles_n", "c2b_alleles_order", "c2b_alleles_arena", "c2b_alleles_offsets",
            "c2b_alleles_lengths", "c2b_alleles_write_tsv", "c2b_alleles_around_cut", "c2b_alleles_cut_width", "c2b_alleles_cut_fetch"]
 
@@ -184,6 +184,8 @@ def load(path=None):
     L.c2b_screen_reads.argtypes = [vp, vp, i64, i32, vp, i32]
     L.c2b_fastq_last_error.restype = C.c_char_p
     L.c2b_fastq_last_error.argtypes = []
+    L.c2b_serial_stats.restype = C.c_int
+    L.c2b_serial_stats.argtypes = [vp, vp, vp, i64, i32, vp, vp, i32]
     L.c2b_alleles_build.restype = C.c_int
     L.c2b_alleles_build.argtypes = [vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, i32, C.POINTER(C.c_char_p), vp, vp, i32, C.POINTER(vp)]
     L.c2b_alleles_free.restype = None

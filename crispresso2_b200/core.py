@@ -73,7 +73,7 @@ def get_engine(device=0, lib_path=None):
     return _engines[key]
 
 
-def configure_engine(engine, args, refs, ref_names, aln_matrix, edit_cap=24):
+def configure_engine(engine, args, refs, ref_names, aln_matrix, edit_cap=12):
     engine.configure(refs, ref_names, aln_matrix, args.needleman_wunsch_gap_open, args.needleman_wunsch_gap_extend,
                      args.aln_seed_count, args.aln_seed_min, _flags(args), "ACGTN", edit_cap)
     return engine
@@ -278,32 +278,24 @@ _STAT_KEYS = ["N_TOT_READS", "N_CACHED_ALN", "N_CACHED_NOTALN", "N_COMPUTED_ALN"
               "N_SUBS_OUTSIDE_WINDOW", "N_MODS_IN_WINDOW", "N_MODS_OUTSIDE_WINDOW", "N_READS_IRREGULAR_ENDS", "READ_LENGTH"]
 
 
-def _serial_stats(res, counts, n_extra_notaln=0, extra_count=0):
-    """aln_stats of the serial branch (CRISPRessoCORE.py:1956-1999) from the per-read records, vectorised: the statistics of
-    an aligned unique read are those of its best_match_name (the LAST winner)."""
-    c = np.asarray(counts, dtype=np.int64)
-    aligned = res.recs["best_score_milli"] > 0
-    st = dict.fromkeys(_STAT_KEYS, 0)
-    st["N_TOT_READS"] = int(c.sum()) + int(extra_count)
-    st["N_COMPUTED_ALN"] = int(aligned.sum())
-    st["N_CACHED_ALN"] = int((c[aligned] - 1).sum())
-    st["N_COMPUTED_NOTALN"] = int((~aligned).sum()) + int(n_extra_notaln)
-    st["N_CACHED_NOTALN"] = int((c[~aligned] - 1).sum()) + int(extra_count) - int(n_extra_notaln)
-    if aligned.any():
-        idx = np.nonzero(aligned)[0]
-        col = res.recs["best_ref"][idx].astype(np.int64) if res.alns.shape[1] > 1 else np.zeros(len(idx), dtype=np.int64)
-        a = res.alns[idx, col]
-        ca = c[idx]
-        n_sub_all, sub_n = a["n_sub_all"].astype(np.int64), a["substitution_n"].astype(np.int64)
-        in_win = sub_n + a["deletion_n"].astype(np.int64) + a["insertion_n"].astype(np.int64)
-        total = a["n_ins_all"].astype(np.int64) + a["n_del_pos_all"].astype(np.int64) + n_sub_all
-        st["N_GLOBAL_SUBS"] = int((n_sub_all * ca).sum())
-        st["N_SUBS_OUTSIDE_WINDOW"] = int(((n_sub_all - sub_n) * ca).sum())
-        st["N_MODS_IN_WINDOW"] = int((in_win * ca).sum())
-        st["N_MODS_OUTSIDE_WINDOW"] = int(((total - in_win) * ca).sum())
-        st["N_READS_IRREGULAR_ENDS"] = int((ca * (a["irregular_ends"] != 0)).sum())
-        st["READ_LENGTH"] = int(a["aln_len"][0])
-    return st, aligned
+def _serial_stats(res, counts, n_extra_notaln=0, extra_count=0, lib_path=None):
+    """aln_stats of the serial branch (CRISPRessoCORE.py:1956-1999) from the per-read records, natively (c2b_serial_stats: one
+    threaded pass): the statistics of an aligned unique read are those of its best_match_name (the LAST winner)."""
+    L = _lib.load(lib_path)
+    n, nr = res.alns.shape
+    recs = np.ascontiguousarray(res.recs)
+    alns = np.ascontiguousarray(res.alns)
+    c = np.ascontiguousarray(counts, dtype=np.int32)
+    out = np.zeros(11, dtype=np.int64)
+    aligned = np.zeros(n, dtype=np.uint8)
+    rc = L.c2b_serial_stats(recs.ctypes.data, alns.ctypes.data, c.ctypes.data, n, nr, out.ctypes.data, aligned.ctypes.data, 0)
+    if rc != 0:
+        raise EngineError("c2b_serial_stats failed (%d)" % rc)
+    st = dict(zip(_STAT_KEYS, (int(x) for x in out)))
+    st["N_TOT_READS"] += int(extra_count)
+    st["N_COMPUTED_NOTALN"] += int(n_extra_notaln)
+    st["N_CACHED_NOTALN"] += int(extra_count) - int(n_extra_notaln)
+    return st, aligned.view(bool)
 
 
 def _joined_classes(res, weights, ref_names, flags):
@@ -451,7 +443,7 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
     extra = {}
     for lo, res, _fx in parts:
         hi = lo + len(res.recs)
-        s1, al = _serial_stats(res, counts_g[lo:hi])
+        s1, al = _serial_stats(res, counts_g[lo:hi], lib_path=engine.lib_path)
         aligned[lo:hi] = al
         for key, val in s1.items():
             if key == "READ_LENGTH":

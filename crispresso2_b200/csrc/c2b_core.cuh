@@ -1232,6 +1232,9 @@ C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *pro
     const int lstar = R.lstar;
     const uint32_t combo_sa = wp::smem_addr(combo) - 1u;                 // combo[j-1] = [combo_sa + j]
     const uint32_t qstride = (uint32_t)R.Ipad * 4u;
+    // loop invariants read through R (global memory: the compiler re-loads them every step next to the slab stores)
+    const int Ipad = R.Ipad, Iref = R.I;
+    const uint32_t XB0 = R.pk_XB;
 
     uint32_t M[8], X[8], Y[8], cIe[8], g40, dI[8];                       // g4[k] = 4*gi[row] = cIe[k-1]; g40: the row above the lane's first
     int L = r8, slot = 1 - 9 * r8 + RG_B;                                // slot of step t = 1
@@ -1244,7 +1247,7 @@ C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *pro
         g40 = R.g42[row0];
         const uint32_t y0 = (8 * Lv - RG_B <= 0) ? R.pk_YB : (PK_SENT | PK_T1);   // window starts at column 0: the border column
         const uint32_t d4p = (uint32_t)((4 * (P.go - P.ge)) & 0xffff) * 0x00010001u;
-        const int klast = R.I - 8 * Lv - 1;                              // row I is this lane's row klast (if 0 <= klast < 8)
+        const int klast = Iref - 8 * Lv - 1;                              // row I is this lane's row klast (if 0 <= klast < 8)
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             M[k] = PK_SENT; X[k] = PK_SENT | PK_T2; Y[k] = y0;
@@ -1260,7 +1263,7 @@ C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *pro
 
     for (int t = 1; t <= nsteps; t++) {
         uint32_t uM = wp::shflu(M[7], src), uX = wp::shflu(X[7], src), uY = wp::shflu(Y[7], src);
-        if (L == 0) { uM = PK_SENT; uX = R.pk_XB; uY = PK_SENT | PK_T1; }     // row 0
+        if (L == 0) { uM = PK_SENT; uX = XB0; uY = PK_SENT | PK_T1; }     // row 0
         const int j = t - L;
         if (slot >= 0 && L <= lstar && j >= 1 && j <= J) {
             uint32_t s[8];
@@ -1269,7 +1272,7 @@ C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *pro
                 const uint4 sa = wp::lds_v4(a), sb = wp::lds_v4(a + 512u);
                 s[0] = sa.x; s[1] = sa.y; s[2] = sa.z; s[3] = sa.w; s[4] = sb.x; s[5] = sb.y; s[6] = sb.z; s[7] = sb.w;
             } else {
-                const uint4 *pp = reinterpret_cast<const uint4 *>(prof0 + combo[j - 1] * R.Ipad);
+                const uint4 *pp = reinterpret_cast<const uint4 *>(prof0 + combo[j - 1] * Ipad);
                 const uint4 sa = wp::ldg4u(pp), sb = wp::ldg4u(pp + 32);
                 s[0] = sa.x; s[1] = sa.y; s[2] = sa.z; s[3] = sa.w; s[4] = sb.x; s[5] = sb.y; s[6] = sb.z; s[7] = sb.w;
             }

@@ -268,6 +268,10 @@ struct c2b_engine {
     int scratch_TS = 0;
     // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
     struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed, maxlen, ord, gops, gmeta, left; int32_t *h_ord = nullptr; size_t h_ord_cap = 0; int64_t *h_off = nullptr; size_t h_off_cap = 0;
+                   // pinned bounce buffers for callers whose arrays are pageable (numpy): copies to / from them run on host
+                   // threads while the other set's kernels and DMA are in flight
+                   uint8_t *h_in = nullptr, *h_out = nullptr; size_t h_in_cap = 0, h_out_cap = 0;
+                   int64_t d_c0 = 0, d_n = 0; size_t d_Wt = 0; bool drain = false;     // chunk waiting in h_out
                    rt_event in_done, k_done, out_done; bool used = false; } stage[2];
     rt_stream s_in = 0, s_out = 0, stream2 = 0;     // stream2: second compute stream, kernels of odd chunks
     rt_event fork_ev = 0;                           // orders stream2 after what is already queued on `stream`
@@ -435,6 +439,8 @@ void c2b_destroy(c2b_engine *e)
         if (st.h_ord) rt_host_free(st.h_ord);
         for (DevBuf *b : sb) if (b->p) rt_free(b->p);
         if (st.h_off) rt_host_free(st.h_off);
+        if (st.h_in) rt_host_free(st.h_in);
+        if (st.h_out) rt_host_free(st.h_out);
         if (e->pipe_ready) { rt_event_destroy(st.in_done); rt_event_destroy(st.k_done); rt_event_destroy(st.out_done); }
     }
     if (e->pipe_ready) { rt_stream_destroy(e->s_in); rt_stream_destroy(e->s_out); }
@@ -637,7 +643,7 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
     {   // two-kernel form (c2b_split.cuh): the ring-banded DP must be admissible -- for one reference at least when every
         // read has one candidate, for all of them when every read is tried against every reference
         int n_ok = 0;
-        for (int r = 0; r < n_refs; r++) n_ok += (e->refdev[r].rg_ok && !e->refdev[r].coding) ? 1 : 0;
+        for (int r = 0; r < n_refs; r++) n_ok += (e->refdev[r].pk_maxJ > 0 && !e->refdev[r].coding) ? 1 : 0;     // the packed DP is admissible
         e->split_ok = !(p->flags & (C2B_F_NO_PAIRING | C2B_F_NO_RING)) && n_ok > 0;
         e->split_all = n_ok == n_refs;
     }
@@ -935,6 +941,46 @@ int c2b_ring_counts(c2b_engine *e, int64_t *ring_pairs, int64_t *ring_fallbacks)
     return C2B_OK;
 }
 
+// true when `p` is ordinary pageable host memory (cudaMemcpyAsync on it is staged by the driver and blocks the host thread)
+static bool is_pageable(const void *p)
+{
+#ifndef C2B_EMU
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+#else
+    (void)p; return false;
+#endif
+}
+
+// rows x width bytes between buffers of different pitch, split over a few host threads
+static void par_copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows)
+{
+    if (!rows || !width) return;
+    const size_t bytes = width * rows;
+    int T = bytes > (8u << 20) ? 4 : bytes > (1u << 20) ? 2 : 1;
+    auto work = [&](int t) {
+        const size_t lo = rows * t / T, hi = rows * (t + 1) / T;
+        if (dpitch == width && spitch == width) memcpy((char *)dst + lo * width, (const char *)src + lo * width, (hi - lo) * width);
+        else for (size_t r = lo; r < hi; r++) memcpy((char *)dst + r * dpitch, (const char *)src + r * spitch, width);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+}
+static void par_copy(void *dst, const void *src, size_t bytes) { par_copy2d(dst, bytes, src, bytes, bytes, 1 == 1 ? (bytes ? 1 : 0) : 0); }
+
+static int ensure_pinned(c2b_engine *e, uint8_t *&p, size_t &cap, size_t n)
+{
+    if (n <= cap) return C2B_OK;
+    if (p) rt_host_free(p);
+    const size_t want = n + n / 8 + 4096;
+    p = (uint8_t *)rt_host_alloc(want); cap = p ? want : 0;
+    return p ? C2B_OK : fail(e, C2B_E_CUDA, "c2b_align_batch: pinned allocation failed");
+}
+
 // Host buffers in, host buffers out: chunks pipeline through two staging sets and three streams -- H2D of chunk c+1 and
 // D2H of chunk c-1 overlap the kernels of chunk c.  strings (two W-byte slots per (read, reference)) and / or the compact
 // form (ops: W/32 words of 32 two-bit ops per slot, meta: one word per slot) are produced as requested; of either only the
@@ -971,25 +1017,65 @@ static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *
     int rc = C2B_OK;
     // D2H of a chunk is queued one iteration late: by then its kernels have finished and the widest alignment of the
     // chunk is known, so only the right-hand `Wt` bytes of every W-byte string slot (the first Wt/32 op words) cross PCIe.
+    // Pageable caller arrays (numpy): cudaMemcpyAsync on them is staged by the driver and blocks this thread -- measured 0.45 s
+    // per 0.95 M reads through process_fastq against 20 ms with pinned arrays (profiles/r02c_api_profile.txt).  Then every
+    // chunk goes through the set's pinned bounce buffers; the copies between them and the caller's arrays run on host threads
+    // while the other set's kernels and DMA are in flight.
+    const bool bounce = getenv("C2B_FORCE_BOUNCE") ? atoi(getenv("C2B_FORCE_BOUNCE")) != 0 : (is_pageable(reads) || is_pageable(recs));
+    auto al256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    struct OutLay { size_t recs, alns, ed, meta, str, ops, total; };
+    auto out_layout = [&](int64_t n) {
+        OutLay L; size_t o = 0;
+        L.recs = o; o = al256(o + (size_t)n * sizeof(c2b_read_rec));
+        L.alns = o; o = al256(o + (size_t)n * nr * sizeof(c2b_aln_rec));
+        L.ed = o; o = al256(o + (size_t)n * nr * cap * sizeof(c2b_edit));
+        L.meta = o; o = al256(o + (meta ? (size_t)n * nr * 4 : 0));
+        L.str = o; o = al256(o + (strings ? (size_t)n * nr * 2 * W : 0));
+        L.ops = o; o = al256(o + (ops ? (size_t)n * nr * NW * 8 : 0));
+        L.total = o;
+        return L;
+    };
     struct Pending { bool any = false; int64_t c0 = 0, n = 0; int set = 0; } pend;
     auto flush = [&](const Pending &q) -> int {
         c2b_engine::Stage &st = e->stage[q.set];
+        const OutLay L = out_layout(q.n);
+        int rc2;
+        if (bounce && (rc2 = ensure_pinned(e, st.h_out, st.h_out_cap, L.total))) return rc2;
+        uint8_t *ho = st.h_out;
         RTCHK(rt_wait(e->s_out, st.k_done));
-        RTCHK(rt_d2h(recs + q.c0, st.recs.p, (size_t)q.n * sizeof(c2b_read_rec), e->s_out));
-        RTCHK(rt_d2h(alns + q.c0 * nr, st.alns.p, (size_t)q.n * nr * sizeof(c2b_aln_rec), e->s_out));
-        if (cap) RTCHK(rt_d2h(edits + q.c0 * nr * cap, st.ed.p, (size_t)q.n * nr * cap * sizeof(c2b_edit), e->s_out));
-        if (meta) RTCHK(rt_d2h(meta + q.c0 * nr, st.gmeta.p, (size_t)q.n * nr * 4, e->s_out));
+        RTCHK(rt_d2h(bounce ? (void *)(ho + L.recs) : (void *)(recs + q.c0), st.recs.p, (size_t)q.n * sizeof(c2b_read_rec), e->s_out));
+        RTCHK(rt_d2h(bounce ? (void *)(ho + L.alns) : (void *)(alns + q.c0 * nr), st.alns.p, (size_t)q.n * nr * sizeof(c2b_aln_rec), e->s_out));
+        if (cap) RTCHK(rt_d2h(bounce ? (void *)(ho + L.ed) : (void *)(edits + q.c0 * nr * cap), st.ed.p, (size_t)q.n * nr * cap * sizeof(c2b_edit), e->s_out));
+        if (meta) RTCHK(rt_d2h(bounce ? (void *)(ho + L.meta) : (void *)(meta + q.c0 * nr), st.gmeta.p, (size_t)q.n * nr * 4, e->s_out));
+        size_t Wt = 0;
         if (strings || ops) {
             RTCHK(rt_event_sync(st.k_done));
             long long wmax = 0;
             RTCHK(rt_d2h(&wmax, (const char *)st.maxlen.p, 8, e->s_out));
             RTCHK(rt_sync(e->s_out));
-            size_t Wt = ((size_t)wmax + 31) & ~(size_t)31;
+            Wt = ((size_t)wmax + 31) & ~(size_t)31;
             if (Wt > (size_t)W) Wt = W;
-            if (strings) RTCHK(rt_d2h_2d(strings + q.c0 * nr * 2 * W + (W - Wt), (const uint8_t *)st.str.p + (W - Wt), W, Wt, (size_t)q.n * nr * 2, e->s_out));
-            if (ops) RTCHK(rt_d2h_2d(ops + q.c0 * nr * NW, st.gops.p, (size_t)NW * 8, Wt / 32 * 8, (size_t)q.n * nr, e->s_out));
+            if (strings) RTCHK(rt_d2h_2d((bounce ? ho + L.str : strings + q.c0 * nr * 2 * W) + (W - Wt), (const uint8_t *)st.str.p + (W - Wt), W, Wt, (size_t)q.n * nr * 2, e->s_out));
+            if (ops) RTCHK(rt_d2h_2d(bounce ? (void *)(ho + L.ops) : (void *)(ops + q.c0 * nr * NW), st.gops.p, (size_t)NW * 8, Wt / 32 * 8, (size_t)q.n * nr, e->s_out));
         }
         RTCHK(rt_record(st.out_done, e->s_out));
+        st.drain = bounce; st.d_c0 = q.c0; st.d_n = q.n; st.d_Wt = Wt;
+        return C2B_OK;
+    };
+    // bounce buffers -> the caller's arrays, once the set's D2H is done
+    auto drain = [&](c2b_engine::Stage &st) -> int {
+        if (!st.drain) return C2B_OK;
+        RTCHK(rt_event_sync(st.out_done));
+        const int64_t c0 = st.d_c0, n = st.d_n;
+        const OutLay L = out_layout(n);
+        const uint8_t *ho = st.h_out;
+        par_copy(recs + c0, ho + L.recs, (size_t)n * sizeof(c2b_read_rec));
+        par_copy(alns + c0 * nr, ho + L.alns, (size_t)n * nr * sizeof(c2b_aln_rec));
+        if (cap) par_copy(edits + c0 * nr * cap, ho + L.ed, (size_t)n * nr * cap * sizeof(c2b_edit));
+        if (meta) par_copy(meta + c0 * nr, ho + L.meta, (size_t)n * nr * 4);
+        if (strings) par_copy2d(strings + c0 * nr * 2 * W + (W - st.d_Wt), W, ho + L.str + (W - st.d_Wt), W, st.d_Wt, (size_t)n * nr * 2);
+        if (ops) par_copy2d(ops + c0 * nr * NW, (size_t)NW * 8, ho + L.ops, (size_t)NW * 8, st.d_Wt / 32 * 8, (size_t)n * nr);
+        st.drain = false;
         return C2B_OK;
     };
     // chunk boundaries: a small first chunk (its H2D is exposed) and a small last chunk (its D2H is exposed)
@@ -1009,6 +1095,7 @@ static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *
         const int64_t c0 = cuts[ci], n = cuts[ci + 1] - cuts[ci];
         const int64_t b0 = offsets[c0], b1 = offsets[c0 + n];
         if (st.used) RTCHK(rt_event_sync(st.out_done));        // set is being reused: the D2H of chunk ci-2 must be done
+        if ((rc = drain(st))) return rc;
         if ((rc = ensure(e, st.reads, (size_t)(b1 - b0) + 16))) return rc;
         if ((rc = ensure(e, st.off, (size_t)(n + 1) * 8))) return rc;
         if ((rc = ensure(e, st.recs, (size_t)n * sizeof(c2b_read_rec)))) return rc;
@@ -1026,11 +1113,21 @@ static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *
             if (!st.h_off) return fail(e, C2B_E_CUDA, "c2b_align_batch: pinned allocation failed");
         }
         for (int64_t k = 0; k <= n; k++) st.h_off[k] = offsets[c0 + k] - b0;      // chunk-relative offsets
-        RTCHK(rt_h2d(st.reads.p, reads + b0, (size_t)(b1 - b0), e->s_in));
+        const uint8_t *src_reads = reads + b0;
+        const int32_t *src_cnt = count ? count + c0 : nullptr, *src_qw = qweight ? qweight + c0 : nullptr, *src_rid = ref_id ? ref_id + c0 : nullptr;
+        if (bounce) {
+            const size_t rb = al256((size_t)(b1 - b0)), ib = al256((size_t)n * 4);
+            if ((rc = ensure_pinned(e, st.h_in, st.h_in_cap, rb + 3 * ib))) return rc;
+            par_copy(st.h_in, src_reads, (size_t)(b1 - b0)); src_reads = st.h_in;
+            if (count) { memcpy(st.h_in + rb, src_cnt, (size_t)n * 4); src_cnt = (const int32_t *)(st.h_in + rb); }
+            if (qweight) { memcpy(st.h_in + rb + ib, src_qw, (size_t)n * 4); src_qw = (const int32_t *)(st.h_in + rb + ib); }
+            if (ref_id) { memcpy(st.h_in + rb + 2 * ib, src_rid, (size_t)n * 4); src_rid = (const int32_t *)(st.h_in + rb + 2 * ib); }
+        }
+        RTCHK(rt_h2d(st.reads.p, src_reads, (size_t)(b1 - b0), e->s_in));
         RTCHK(rt_h2d(st.off.p, st.h_off, (size_t)(n + 1) * 8, e->s_in));
-        if (count) RTCHK(rt_h2d(st.cnt.p, count + c0, (size_t)n * 4, e->s_in));
-        if (qweight) RTCHK(rt_h2d(st.qw.p, qweight + c0, (size_t)n * 4, e->s_in));
-        if (ref_id) RTCHK(rt_h2d(st.rid.p, ref_id + c0, (size_t)n * 4, e->s_in));
+        if (count) RTCHK(rt_h2d(st.cnt.p, src_cnt, (size_t)n * 4, e->s_in));
+        if (qweight) RTCHK(rt_h2d(st.qw.p, src_qw, (size_t)n * 4, e->s_in));
+        if (ref_id) RTCHK(rt_h2d(st.rid.p, src_rid, (size_t)n * 4, e->s_in));
         // pairing order: counting sort of the chunk by (reference id, length) when reads differ, so equal ones are adjacent
         bool need_order = false;
         for (int64_t k = 1; k < n && !need_order; k++)
@@ -1076,6 +1173,7 @@ static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *
     if (pend.any && (rc = flush(pend))) return rc;
     RTCHK(rt_sync(e->s_out));
     RTCHK(rt_sync(e->stream));
+    for (auto &st : e->stage) if ((rc = drain(st))) return rc;
     return C2B_OK;
 }
 

@@ -160,8 +160,12 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
     const int lane = wp::lane(), g = lane >> 3;
     const int64_t first = 4 * wq;
     const bool multi = P.ref_id == nullptr && P.n_refs > 1;
-    bool quad = P.tbq != nullptr && 2 * first + 7 < P.n_reads && (!multi || P.n_refs <= RG_MAX_REFS);
+    // A group is taken here when its four pairs admit the packed 16-bit DP against every candidate reference (equal lengths
+    // within a pair, lengths inside the proven 16-bit range); per reference the ring-banded DP is tried when the band can hold
+    // the alignment (read length within RG_MAXD of the amplicon's, monotone bound), the full matrix otherwise.
+    bool quad = (P.tbq != nullptr || P.tb != nullptr) && 2 * first + 7 < P.n_reads && (!multi || P.n_refs <= RG_MAX_REFS);
     int r0 = 0;
+    uint32_t ringmask = 0;                                   // bit k - k0: the ring-banded DP is admissible for reference k
     if (quad) {
         const int x = lane & 7;
         const int64_t rd = read_at(P, 2 * first + x);
@@ -173,9 +177,12 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
         const int k0 = multi ? 0 : r0, k1 = multi ? P.n_refs : r0 + 1;
         for (int k = k0; k < k1; k++) {
             const RefDev &R = refdev(P, k);
-            ok = ok && R.rg_ok && !R.coding && Jx <= R.pk_maxJ && Jx - R.I <= RG_MAXD && R.I - Jx <= RG_MAXD;
+            ok = ok && !R.coding && Jx <= R.pk_maxJ;
+            const bool rk = P.tbq != nullptr && R.rg_ok && Jx - R.I <= RG_MAXD && R.I - Jx <= RG_MAXD;
+            if (wp::ballot(rk) == 0xffffffffu) ringmask |= 1u << (k - k0);
         }
         quad = wp::ballot(ok) == 0xffffffffu;
+        if (!P.tb && ringmask != (k1 - k0 >= 32 ? 0xffffffffu : (1u << (k1 - k0)) - 1u)) quad = false;    // no full-matrix scratch
     }
     if (!quad) {
 #pragma unroll 1
@@ -190,7 +197,7 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
         return;
     }
     const int k0 = multi ? 0 : r0, k1 = multi ? P.n_refs : r0 + 1;
-    uint2 *tbq = reinterpret_cast<uint2 *>(P.tbq + (int64_t)warp_slot * P.TS * 64);
+    uint2 *tbq = P.tbq ? reinterpret_cast<uint2 *>(P.tbq + (int64_t)warp_slot * P.TS * 64) : nullptr;
     uint32_t okmask = 0, modes = 0, both2 = 0;              // both2: reads (bit 2q + h) to be aligned on both strands
     int Jg = 0, Jmax = 0;
 #pragma unroll 1
@@ -238,6 +245,8 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
         const uint32_t ring2 = good2 & ~both2;              // reads whose ring result counts
         nboth += wp::popc(both2 & good2);
         const bool staged = (k == 0 && staged_prof != nullptr);
+        uint32_t pass2 = 0;
+        if (((ringmask >> (k - k0)) & 1u) && ring2) {
         if (staged) dp_ring<true>(P, R, staged_prof, S.combo[g], Jg, Jmax + R.lstar, tbq, S.fin);
         else dp_ring<false>(P, R, R.prof2, S.combo[g], Jg, Jmax + R.lstar, tbq, S.fin);
         wp::sync();
@@ -250,7 +259,6 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
         const int thr = ring_bound(P, R, Jg) + 512 - P.ge * (R.I + Jg);
         const bool passA = Jg > 0 && (int)((z & 0xffffu) >> 2) > thr, passB = Jg > 0 && (int)(z >> 18) > thr;
         const uint32_t bA = wp::ballot(passA), bB = wp::ballot(passB);
-        uint32_t pass2 = 0;
 #pragma unroll
         for (int q = 0; q < 4; q++) pass2 |= (((bA >> (8 * q)) & 1u) | (((bB >> (8 * q)) & 1u) << 1)) << (2 * q);
         pass2 &= ring2;
@@ -286,6 +294,7 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
             }
         }
         npass += wp::popc(pass2);
+        } else ntried += wp::popc(ring2);
         // Full-matrix DPs (align_pair, the packed path of c2b_core.cuh), here and now, for what the ring did not settle for this
         // reference: (job 0) pairs with a read the ring could not prove exact; (jobs 1, 2) a read that needs both strands,
         // packed with ITSELF -- forward strand in the low halves, reverse complement in the high ones -- the better identity
@@ -350,7 +359,7 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
     }
 #ifndef C2B_EMU
     // the slab is dead now: drop its lines from L2 instead of writing them back to HBM (10 KB per read otherwise)
-    if (P.discard_slab) {
+    if (P.discard_slab && tbq && ringmask) {
         const char *base = reinterpret_cast<const char *>(tbq);
         const int64_t bytes = (int64_t)P.TS * 64 * 4;
         for (int64_t o = (int64_t)lane * 128; o < bytes; o += 32 * 128)

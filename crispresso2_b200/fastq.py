@@ -34,21 +34,36 @@ class Dedup:
         return self._uniques
 
 
+class _Handle:
+    """Owns a c2b_fastq result: the arrays handed out are views of its memory (no copy of the packed reads) and keep it alive."""
+
+    def __init__(self, L, h):
+        self.L, self.h = L, h
+
+    def __del__(self):
+        h, self.h = self.h, None
+        if h:
+            self.L.c2b_fastq_free(h)
+
+    def view(self, addr, nbytes, dtype):
+        if not nbytes:
+            return np.zeros(0, dtype=dtype)
+        raw = (C.c_uint8 * nbytes).from_address(addr)
+        raw._owner = self                                  # ndarray -> ctypes array -> this handle
+        return np.frombuffer(raw, dtype=dtype)
+
+
 def _collect(L, h):
-    try:
-        nu, nr = int(L.c2b_fastq_n_unique(h)), int(L.c2b_fastq_n_reads(h))
-        off = np.ctypeslib.as_array(C.cast(L.c2b_fastq_offsets(h), C.POINTER(C.c_int64)), shape=(nu + 1,)).copy()
-        tot = int(off[-1])
-        buf = (np.ctypeslib.as_array(C.cast(L.c2b_fastq_seqs(h), C.POINTER(C.c_uint8)), shape=(max(tot, 1),))[:tot].copy()
-               if tot else np.zeros(0, dtype=np.uint8))
-        if nu:
-            counts = np.ctypeslib.as_array(C.cast(L.c2b_fastq_counts(h), C.POINTER(C.c_int32)), shape=(nu,)).copy()
-            first = np.ctypeslib.as_array(C.cast(L.c2b_fastq_first_index(h), C.POINTER(C.c_int64)), shape=(nu,)).copy()
-        else:
-            counts, first = np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int64)
-        return Dedup(buf, off, counts, first, nr)
-    finally:
-        L.c2b_fastq_free(h)
+    own = _Handle(L, h)
+    nu, nr = int(L.c2b_fastq_n_unique(h)), int(L.c2b_fastq_n_reads(h))
+    off = own.view(L.c2b_fastq_offsets(h), (nu + 1) * 8, np.int64)
+    if not len(off):
+        off = np.zeros(1, dtype=np.int64)
+    tot = int(off[-1])
+    buf = own.view(L.c2b_fastq_seqs(h), tot, np.uint8)
+    counts = own.view(L.c2b_fastq_counts(h), nu * 4, np.int32)
+    first = own.view(L.c2b_fastq_first_index(h), nu * 8, np.int64)
+    return Dedup(buf, off, counts, first, nr)
 
 
 def dedup_file(path, n_threads=0, lib_path=None):

@@ -312,6 +312,12 @@ int  c2b_rc_merge_weights(const uint8_t *seqs, const int64_t *offsets, int64_t n
  * Align.pyx:212 -- and its quantification loop raises KeyError on IUPAC codes, CRISPRessoCORE.py:4081.)             */
 int64_t c2b_screen_reads(const uint8_t *seqs, const int64_t *offsets, int64_t n, int32_t max_len, uint8_t *out, int32_t n_threads);
 
+/* replaces: the statistics loop of the serial process_fastq branch (CRISPRessoCORE.py:1956-1999) over a batch's records:
+ * out[11] = N_TOT_READS, N_CACHED_ALN, N_CACHED_NOTALN, N_COMPUTED_ALN, N_COMPUTED_NOTALN, N_GLOBAL_SUBS, N_SUBS_OUTSIDE_WINDOW,
+ * N_MODS_IN_WINDOW, N_MODS_OUTSIDE_WINDOW, N_READS_IRREGULAR_ENDS, READ_LENGTH; aligned[k] = best_match_score > 0.  Host threads. */
+int  c2b_serial_stats(const c2b_read_rec *recs, const c2b_aln_rec *alns, const int32_t *counts, int64_t n, int32_t nr,
+                      int64_t *out, uint8_t *aligned, int32_t n_threads);
+
 /* replaces: filterFastqs.filterFastqs for single-end input (CRISPResso2/filterFastqs.py:29-229, called at
  * CRISPRessoCORE.py:3716-3717): keep a record iff min(q) >= min_bp_qual_in_read and mean(q) >= min_av_read_qual (each when
  * non-zero), mask bases with q < min_bp_qual_or_N as 'N'; q = byte - 33 (uint8).  Same record/line rules as the reference's

@@ -9,7 +9,7 @@ import pytest
 import golden_util as G
 import parity_util as PU
 from crispresso2_b200 import _lib, synth
-from crispresso2_b200.engine import Engine
+from crispresso2_b200.engine import Engine, pack_reads
 from oracle import oracle as O
 
 
@@ -144,18 +144,27 @@ def test_chunked_pipeline_equals_one_chunk(emu, monkeypatch):
     reads = [r.tobytes().decode() for r in synth.synth_reads(rng, amp, 61, 100, sub_rate=0.02, cut=ref["cut_point"])]
     reads[5] = reads[5][:70]
     out = []
-    for chunk in (None, "7"):
+    # (chunk size, bounce): the pinned bounce buffers of callers with pageable arrays, forced on and off
+    for chunk, bounce, compact in ((None, "0", False), ("7", "0", False), ("7", "1", False), ("9", "1", True), (None, "1", True)):
         if chunk:
             monkeypatch.setenv("C2B_CHUNK", chunk)
+        else:
+            monkeypatch.delenv("C2B_CHUNK", raising=False)
+        monkeypatch.setenv("C2B_FORCE_BOUNCE", bounce)
         emu.configure({"Reference": ref}, ["Reference"], O.make_matrix(), -20, -2, 5, 2, 0, "ACGTN", 16)
         emu.counts_reset()
-        res = emu.align(reads)
+        buf, off = pack_reads(reads)
+        res = emu.align_packed(buf, off, compact=compact)
         out.append((res, emu.counts_raw()))
     monkeypatch.delenv("C2B_CHUNK", raising=False)
-    (a, ca), (b, cb) = out
-    assert (a.recs == b.recs).all() and (a.alns == b.alns).all() and (ca == cb).all()
-    for i in range(len(reads)):
-        assert a.pair(i) == b.pair(i)
+    monkeypatch.delenv("C2B_FORCE_BOUNCE", raising=False)
+    a, ca = out[0]
+    for b, cb in out[1:]:
+        assert (a.recs == b.recs).all() and (a.alns == b.alns).all() and (ca == cb).all()
+        (ea, fa), (eb, fb) = PU.edits_canonical(a), PU.edits_canonical(b)      # entries past n_edits are undefined
+        assert (fa == fb).all() and (ea[fa] == eb[fb]).all()
+        for i in range(len(reads)):
+            assert a.pair(i) == b.pair(i)
 
 
 def test_chunked_pipeline_with_per_read_amplicon(emu, monkeypatch):
