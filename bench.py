@@ -317,6 +317,47 @@ def api_leg(w, eng, reads, label):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def ingest_leg(reads):
+    """FASTQ front end alone: native parse + exact de-duplication (c2b_fastq_dedup: what feeds the kernels)
+    and the native quality filter (c2b_fastq_filter), on the timed batch written as plain text and -- a 256k-read slice -- as
+    gzip.  Wall clock, file in the page cache, best of 3."""
+    import gzip
+    import shutil
+    from crispresso2_b200 import fastq, filter_fastqs, synth
+    d = tempfile.mkdtemp(prefix="c2b_ing_")
+    out = {}
+    try:
+        plain = os.path.join(d, "r.fastq")
+        synth.write_fastq_fast(plain, reads)
+        sub = reads[:1 << 18]
+        small = os.path.join(d, "s.fastq")
+        synth.write_fastq_fast(small, sub)
+        gz = os.path.join(d, "s.fastq.gz")
+        with open(small, "rb") as fi, gzip.open(gz, "wb", compresslevel=1) as fo:
+            shutil.copyfileobj(fi, fo, 1 << 22)
+
+        def best(fn, reps=3):
+            t = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                r = fn()
+                t.append(time.perf_counter() - t0)
+            return min(t), r
+
+        for name, path, n in (("dedup_plain", plain, len(reads)), ("dedup_gzip", gz, len(sub))):
+            dt, dd = best(lambda: fastq.dedup_file(path))
+            assert dd.n_reads == n
+            out[name] = {"reads": n, "unique": int(len(dd.counts)), "seconds": dt, "reads_per_s": n / dt,
+                         "file_MB_per_s": os.path.getsize(path) / dt / 1e6}
+        for name, path, n in (("filter_plain", plain, len(reads)), ("filter_gzip_in_out", gz, len(sub))):
+            dst = os.path.join(d, "f_" + os.path.basename(path))
+            dt, r = best(lambda: filter_fastqs.filterFastqs(fastq_r1=path, fastq_r1_out=dst, min_av_read_qual=30, min_bp_qual_or_N=20), reps=2)
+            out[name] = {"reads": n, "kept": int(r[1]), "seconds": dt, "reads_per_s": n / dt, "file_MB_per_s": os.path.getsize(path) / dt / 1e6}
+        return out
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def reference_arm(args):
     """--impl reference: the reference's own Cython global_align + find_indels_substitutions (compiled from /root/reference,
     unmodified) on all host cores, on a bounded sample per step; falls back to the oracle port when neither baseline/_ref
@@ -633,6 +674,9 @@ def main():
             uniq = _synth.synth_reads_fast(np.random.default_rng(77), amp_seq, n, 250, sub_rate=0.02, cut=w.refs["Reference"]["cut_point"])
             line["api"] = {"process_fastq": api_leg(w, eng, rd, "the timed batch as a FASTQ file (%s reads)" % _fmt(n)),
                            "process_fastq_all_unique": api_leg(w, eng, uniq, "all-unique variant (substitution rate 0.02), %s reads" % _fmt(n))}
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):      # filterFastqs prints its completion line, like the reference
+                line["api"]["ingest"] = ingest_leg(rd)
         if not args.no_cpu_baseline and world == 1 and args.config == "single":
             line["cpu_baseline"] = cpu_baseline_block(w.refs["Reference"]["sequence"], w.refs["Reference"], w.buf.reshape(-1, 250))
         elif not args.no_cpu_baseline and world == 1:

@@ -82,7 +82,7 @@ EXPORTS = ["c2b_create", "c2b_destroy", "c2b_last_error", "c2b_configure", "c2b_
            "c2b_classify_aligned", "c2b_host_alloc", "c2b_host_free",
            "c2b_fastq_dedup", "c2b_fastq_dedup_buffer", "c2b_fastq_n_reads", "c2b_fastq_n_unique", "c2b_fastq_max_len",
            "c2b_fastq_seqs", "c2b_fastq_offsets", "c2b_fastq_counts", "c2b_fastq_first_index", "c2b_fastq_free",
-           "c2b_fastq_last_error", "c2b_fastq_filter", "c2b_rc_merge_weights", "c2b_screen_reads", "c2b_serial_stats",
+           "c2b_fastq_last_error", "c2b_fastq_filter", "c2b_fastq_filter_pair", "c2b_rc_merge_weights", "c2b_screen_reads", "c2b_serial_stats",
            "c2b_alleles_build", "c2b_alleles_free", "c2b_alleles_n", "c2b_alleles_order", "c2b_alleles_arena", "c2b_alleles_offsets",
            "c2b_alleles_lengths", "c2b_alleles_write_tsv", "c2b_alleles_around_cut", "c2b_alleles_cut_width", "c2b_alleles_cut_fetch"]
 
@@ -178,6 +178,8 @@ def load(path=None):
     L.c2b_fastq_free.argtypes = [vp]
     L.c2b_fastq_filter.restype = C.c_int
     L.c2b_fastq_filter.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.c2b_fastq_filter_pair.restype = C.c_int
+    L.c2b_fastq_filter_pair.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, i32, i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]
     L.c2b_rc_merge_weights.restype = C.c_int
     L.c2b_rc_merge_weights.argtypes = [vp, vp, i64, vp, vp, vp, i32]
     L.c2b_screen_reads.restype = i64

@@ -424,6 +424,132 @@ extern "C" int c2b_fastq_filter(const char *path_in, const char *path_out, int32
 }
 
 
+// Paired input of filterFastqs (reference: CRISPResso2/filterFastqs.py:230-407, the seven run_*_pair variants): the two files
+// are read in lockstep, four lines each per record, until read 1's id line is empty; a pair is kept iff BOTH mates pass.
+// Kept quirks: with only the min filter, or only the mean filter, mate 2 must be STRICTLY above the threshold (:262, :284:
+// `min2 > min_bp_qual_in_read`, `mean2 > min_av_read_qual`); with min + mean but no masking the mean is tested first (:300),
+// so an empty quality line drops the pair (mean of nothing is nan) instead of raising; every other order tests the min
+// first, where numpy.min of an empty array raises (-> C2B_E_LIMIT here).
+namespace {
+
+bool load_lines(const char *path, std::vector<uint8_t> &buf, std::vector<Line> &lines, std::string &err)
+{
+    const size_t Lp = strlen(path);
+    const bool gz = Lp > 3 && strcmp(path + Lp - 3, ".gz") == 0;
+    if (!(gz ? read_gz(path, buf, err) : read_plain(path, buf, err))) return false;
+    const uint8_t *data = buf.data();
+    const size_t n = buf.size();
+    lines.reserve(n / 60 + 16);
+    for (size_t p = 0; p < n;) {
+        const uint8_t *nl = (const uint8_t *)memchr(data + p, '\n', n - p);
+        size_t e = nl ? (size_t)(nl - data) : n;
+        size_t q = e;
+        while (q > p && is_bspace(data[q - 1])) q--;
+        lines.push_back({data + p, (uint32_t)(q - p)});
+        p = nl ? e + 1 : n;
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" int c2b_fastq_filter_pair(const char *path1_in, const char *path2_in, const char *path1_out, const char *path2_out,
+                                     int32_t min_bp_qual_in_read, int32_t min_av_read_qual, int32_t min_bp_qual_or_N,
+                                     int32_t n_threads, int64_t *n_in, int64_t *n_out)
+{
+    if (!path1_in || !path2_in || !path1_out || !path2_out) return C2B_E_ARG;
+    std::vector<uint8_t> buf1, buf2;
+    std::vector<Line> l1, l2;
+    std::string err;
+    if (!load_lines(path1_in, buf1, l1, err) || !load_lines(path2_in, buf2, l2, err)) { g_fastq_err = "c2b_fastq_filter_pair: " + err; return C2B_E_ARG; }
+    static const uint8_t nothing = 0;
+    auto at = [&](const std::vector<Line> &L, size_t k) -> Line { return k < L.size() ? L[k] : Line{&nothing, 0}; };
+    int64_t n_rec = 0;
+    while ((size_t)(4 * n_rec) < l1.size() && l1[(size_t)(4 * n_rec)].len > 0) n_rec++;
+    const bool bp = min_bp_qual_in_read != 0, rq = min_av_read_qual != 0, bpn = min_bp_qual_or_N != 0;
+    const bool strict2 = (bp != rq) && !bpn;                 // run_mBP_pair / run_mRQ_pair: mate 2 strictly above
+    const bool mean_first = bp && rq && !bpn;                // run_mBP_mRQ_pair
+    const size_t o1 = strlen(path1_out), o2 = strlen(path2_out);
+    const bool gz1 = o1 > 3 && strcmp(path1_out + o1 - 3, ".gz") == 0, gz2 = o2 > 3 && strcmp(path2_out + o2 - 3, ".gz") == 0;
+    int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    T = std::max(1, std::min(T, 64));
+    if (n_rec < 4096) T = 1;
+    std::vector<std::string> outs1(T), outs2(T);
+    std::vector<int64_t> kept(T, 0);
+    std::vector<int> fail_code(T, 0);
+    auto qmin = [](const Line &q) { uint8_t mn = 255; for (uint32_t k = 0; k < q.len; k++) mn = std::min<uint8_t>(mn, (uint8_t)(q.p[k] - 33)); return (int)mn; };
+    auto qsum = [](const Line &q) { uint64_t sm = 0; for (uint32_t k = 0; k < q.len; k++) sm += (uint8_t)(q.p[k] - 33); return (int64_t)sm; };
+    auto work = [&](int t) {
+        const int64_t a = n_rec * t / T, b = n_rec * (t + 1) / T;
+        std::string &w1 = outs1[t], &w2 = outs2[t];
+        w1.reserve((size_t)(b - a) * 560); w2.reserve((size_t)(b - a) * 560);
+        std::string masked;
+        auto emit = [&](std::string &o, const Line &id, const Line &sq, const Line &pl, const Line &ql) -> bool {
+            o.append((const char *)id.p, id.len); o.push_back('\n');
+            if (bpn) {
+                if (sq.len != ql.len) return false;          // boolean index of another length: IndexError in the reference
+                masked.assign((const char *)sq.p, sq.len);
+                for (uint32_t k = 0; k < ql.len; k++) if ((int)(uint8_t)(ql.p[k] - 33) < min_bp_qual_or_N) masked[k] = 'N';
+                o.append(masked);
+            } else o.append((const char *)sq.p, sq.len);
+            o.push_back('\n');
+            o.append((const char *)pl.p, pl.len); o.push_back('\n');
+            o.append((const char *)ql.p, ql.len); o.push_back('\n');
+            return true;
+        };
+        for (int64_t r = a; r < b; r++) {
+            const size_t k = (size_t)(4 * r);
+            const Line id1 = l1[k], sq1 = at(l1, k + 1), pl1 = at(l1, k + 2), ql1 = at(l1, k + 3);
+            const Line id2 = at(l2, k), sq2 = at(l2, k + 1), pl2 = at(l2, k + 2), ql2 = at(l2, k + 3);
+            auto mean_ok = [&]() {
+                if (ql1.len == 0 || ql2.len == 0) return false;                        // nan compares false
+                const int64_t t1 = (int64_t)min_av_read_qual * ql1.len, t2 = (int64_t)min_av_read_qual * ql2.len;
+                return qsum(ql1) >= t1 && (strict2 ? qsum(ql2) > t2 : qsum(ql2) >= t2);
+            };
+            auto min_ok = [&](bool &raised) {
+                if (ql1.len == 0 || ql2.len == 0) { raised = true; return false; }       // numpy.min of an empty array raises
+                return qmin(ql1) >= min_bp_qual_in_read && (strict2 ? qmin(ql2) > min_bp_qual_in_read : qmin(ql2) >= min_bp_qual_in_read);
+            };
+            bool raised = false, keep = true;
+            if (mean_first) keep = mean_ok() && min_ok(raised);
+            else {
+                if (bp) keep = min_ok(raised);
+                if (keep && rq) keep = mean_ok();
+            }
+            if (raised) { fail_code[t] = 1; return; }
+            if (!keep) continue;
+            if (!emit(w1, id1, sq1, pl1, ql1) || !emit(w2, id2, sq2, pl2, ql2)) { fail_code[t] = 2; return; }
+            kept[t]++;
+        }
+        if (gz1) { std::string z; if (!gz_member(w1, z)) { fail_code[t] = 3; return; } w1.swap(z); }
+        if (gz2) { std::string z; if (!gz_member(w2, z)) { fail_code[t] = 3; return; } w2.swap(z); }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+    }
+    for (int t = 0; t < T; t++) if (fail_code[t]) {
+        g_fastq_err = fail_code[t] == 1 ? "c2b_fastq_filter_pair: empty quality line" : fail_code[t] == 2 ? "c2b_fastq_filter_pair: sequence and quality lengths differ" : "c2b_fastq_filter_pair: deflate failed";
+        return fail_code[t] == 3 ? C2B_E_STATE : (fail_code[t] == 1 ? C2B_E_LIMIT : C2B_E_ARG);
+    }
+    int64_t tot = 0;
+    for (int f = 0; f < 2; f++) {
+        FILE *fh = fopen(f ? path2_out : path1_out, "wb");
+        if (!fh) { g_fastq_err = std::string("c2b_fastq_filter_pair: cannot write ") + (f ? path2_out : path1_out); return C2B_E_ARG; }
+        std::vector<std::string> &outs = f ? outs2 : outs1;
+        for (int t = 0; t < T; t++) if (!outs[t].empty()) fwrite(outs[t].data(), 1, outs[t].size(), fh);
+        if ((f ? gz2 : gz1) && n_rec == 0) { std::string z, e2; gz_member(e2, z); fwrite(z.data(), 1, z.size(), fh); }
+        fclose(fh);
+    }
+    for (int t = 0; t < T; t++) tot += kept[t];
+    if (n_in) *n_in = n_rec;
+    if (n_out) *n_out = tot;
+    return C2B_OK;
+}
+
+
 // ------------------------------------------------------------------------------------------ reverse-complement merge
 // replaces: the count transfer at the head of the quantification loop (CRISPRessoCORE.py:3964-3975): walking the unique
 // reads in first-seen order, a read with a non-zero count absorbs the count of its reverse complement (CRISPRessoShared.py:

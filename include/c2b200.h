@@ -357,6 +357,13 @@ int32_t c2b_alleles_cut_width(const c2b_alleles *a);
 int  c2b_alleles_cut_fetch(const c2b_alleles *a, uint8_t *seq, uint8_t *ref, int32_t *wlen, uint8_t *unedited, int32_t *n_deleted,
                            int32_t *n_inserted, int32_t *n_mutated, int64_t *reads, double *pct);
 
+/* replaces: filterFastqs.filterFastqs for paired input (CRISPResso2/filterFastqs.py:230-407, the seven run_*_pair variants): both
+ * files in lockstep, a pair kept iff both mates pass; mate 2 strictly above the threshold when only the min or only the mean
+ * filter is set (:262, :284); same error mapping as c2b_fastq_filter.                                              */
+int  c2b_fastq_filter_pair(const char *path1_in, const char *path2_in, const char *path1_out, const char *path2_out,
+                           int32_t min_bp_qual_in_read, int32_t min_av_read_qual, int32_t min_bp_qual_or_N,
+                           int32_t n_threads, int64_t *n_in, int64_t *n_out);
+
 /* pinned host memory (cudaHostAlloc) for callers that want full-speed host<->device copies */
 void *c2b_host_alloc(size_t n_bytes);
 void  c2b_host_free(void *p);

@@ -35,21 +35,19 @@ def main():
         eng = Engine(lib_path=None if lib == "default" else lib)
         state = {}
 
+        # the shipped launcher's re-binding (crispresso2_b200/launcher.py: process_fastq, filterFastqs, the table around the cut),
+        # with the count block of the call kept for the comparison below
+        from crispresso2_b200 import launcher
+        launcher.bind(CORE, engine=eng, lib_path=None if lib == "default" else lib)
+        bound = CORE.process_fastq
+
         def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory):
-            loc = os.path.join(CORE._ROOT, args.needleman_wunsch_aln_matrix_loc)      # CRISPRessoCORE.py:1811
-            m = core.read_matrix(loc)
-            out = core.process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_remove,
-                                     output_directory, engine=eng, aln_matrix=m)
+            out = bound(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory)
             state["block"] = core.quantify(variantCache)
             state["ref_names"] = list(ref_names)
             return out
 
         CORE.process_fastq = process_fastq
-        # quality filtering before the path (CRISPRessoCORE.py:3716-3717 imports the module and calls filterFastqs): native too
-        import functools
-        from CRISPResso2 import filterFastqs as FF
-        from crispresso2_b200 import filter_fastqs
-        FF.filterFastqs = functools.partial(filter_fastqs.filterFastqs, lib_path=None if lib == "default" else lib)
         orig_ctx = CORE.CorePlotContext
 
         def ctx_spy(*a, **kw):

@@ -91,6 +91,66 @@ def test_all_threshold_combinations(lib, tmp_path, thr, gz):
     assert n_in == 700 and n_out == content(got).count(b"\n") // 4
 
 
+def reference_filter_pair(r1, r2, o1, o2, mbp, mrq, mbpn):
+    """The reference's own paired filterFastqs (filterFastqs.py:230-407), imported from /root/reference."""
+    spec = importlib.util.spec_from_file_location("_ref_filterFastqs", REF_PY)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.filterFastqs(fastq_r1=r1, fastq_r2=r2, fastq_r1_out=o1, fastq_r2_out=o2, min_bp_qual_in_read=mbp, min_av_read_qual=mrq,
+                     min_bp_qual_or_N=mbpn)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PY), reason="needs the reference's filterFastqs.py")
+@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("thr", [t for t in itertools.product([None, 12], [None, 31], [None, 20]) if any(t)])
+def test_paired_all_threshold_combinations(lib, tmp_path, thr, gz):
+    """Paired input, every combination of the three thresholds (the seven run_*_pair variants, including the two whose mate-2
+    comparison is strict), thresholds chosen so that reads sit exactly ON them; byte-identical output for both mates."""
+    rng = np.random.default_rng(abs(hash(thr)) % 1000 + 7)
+    ext = ".fastq.gz" if gz else ".fastq"
+    paths = {}
+    for mate in (1, 2):
+        data = bytearray(make_fastq(rng, 900, L=50, low=0.03))
+        recs = bytes(data).split(b"\n")
+        for k in range(0, 900, 3):                            # every third record: constant quality ON a threshold
+            v = 12 if k % 2 else 31
+            recs[4 * k + 3] = bytes([33 + v]) * 50
+        paths[mate] = str(tmp_path / ("in_r%d%s" % (mate, ext)))
+        with (gzip.open(paths[mate], "wb") if gz else open(paths[mate], "wb")) as fh:
+            fh.write(b"\n".join(recs))
+    want = [str(tmp_path / ("want%d%s" % (m, ext))) for m in (1, 2)]
+    got = [str(tmp_path / ("got%d%s" % (m, ext))) for m in (1, 2)]
+    reference_filter_pair(paths[1], paths[2], want[0], want[1], *thr)
+    n_in, n_out = filter_fastqs.filterFastqs(fastq_r1=paths[1], fastq_r2=paths[2], fastq_r1_out=got[0], fastq_r2_out=got[1],
+                                             min_bp_qual_in_read=thr[0], min_av_read_qual=thr[1], min_bp_qual_or_N=thr[2], lib_path=lib)
+    assert content(got[0]) == content(want[0]) and content(got[1]) == content(want[1])
+    assert n_in == 900 and n_out == content(got[0]).count(b"\n") // 4 == content(got[1]).count(b"\n") // 4
+    assert 0 < n_out
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PY), reason="needs the reference's filterFastqs.py")
+def test_paired_shorter_mate_file_and_default_names(lib, tmp_path):
+    """Mate 2 runs out first: its lines read as empty -- with the mean filter the pair is dropped (mean of nothing is nan), with the
+    min filter numpy raises; default output names of filterFastqs.py:48-79."""
+    rng = np.random.default_rng(21)
+    r1, r2 = str(tmp_path / "a_R1.fastq"), str(tmp_path / "a_R2.fastq")
+    open(r1, "wb").write(make_fastq(rng, 40))
+    open(r2, "wb").write(make_fastq(rng, 25))
+    w1, w2 = str(tmp_path / "w1.fastq"), str(tmp_path / "w2.fastq")
+    reference_filter_pair(r1, r2, w1, w2, None, 25, None)
+    filter_fastqs.filterFastqs(fastq_r1=r1, fastq_r2=r2, min_av_read_qual=25, lib_path=lib)
+    assert content(str(tmp_path / "a_R1_filtered.fastq")) == content(w1) and content(str(tmp_path / "a_R2_filtered.fastq")) == content(w2)
+    with pytest.raises(ValueError):
+        reference_filter_pair(r1, r2, w1, w2, 5, None, None)
+    with pytest.raises(ValueError):
+        filter_fastqs.filterFastqs(fastq_r1=r1, fastq_r2=r2, min_bp_qual_in_read=5, lib_path=lib)
+    # min + mean without masking: the mean is tested first, so the short file drops pairs instead of raising (:300)
+    reference_filter_pair(r1, r2, w1, w2, 5, 25, None)
+    filter_fastqs.filterFastqs(fastq_r1=r1, fastq_r2=r2, fastq_r1_out=str(tmp_path / "g1.fastq"), fastq_r2_out=str(tmp_path / "g2.fastq"),
+                               min_bp_qual_in_read=5, min_av_read_qual=25, lib_path=lib)
+    assert content(str(tmp_path / "g1.fastq")) == content(w1) and content(str(tmp_path / "g2.fastq")) == content(w2)
+
+
 def test_crlf_truncated_and_blank_id(lib, tmp_path):
     rng = np.random.default_rng(3)
     cases = {
