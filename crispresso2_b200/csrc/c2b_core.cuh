@@ -177,11 +177,11 @@ struct WarpSmem {
     uint8_t rowinfo[MAXI];     // per reference position: read code of its column, or 8 = deleted (pair: halves of 512)
     uint32_t rowins[MAXI + 4]; // rowins[r]: bases inserted between reference positions r-1 and r (pair: halves of 514)
 };
-constexpr int PK_ROWINFO_STRIDE = 512, PK_ROWINS_STRIDE = 514, PK_MAX_ALN = 512;
+constexpr int PK_ROWINFO_STRIDE = 512, PK_ROWINS_STRIDE = 514, PK_MAX_ALN = 512, PK_MAX_ALN2 = 1024;
 // Ring-banded path: four pairs per warp, eight lanes each.  A group's lane r (0..7) plays the virtual lanes r, r+8, r+16, ...
 // (virtual lane L = rows 8L+1..8L+8) one after the other, each for the RG_NS wavefront steps around its diagonal
 // (step t -> slot t - 9L + RG_B); cells with column - row in [-(RG_B+1), RG_NS-RG_B-9] are always inside the band.
-constexpr int RG_NS = 72, RG_B = 32, RG_MAXD = 8, RG_COMBO = 272;
+constexpr int RG_NS = 72, RG_B = 32, RG_MAXD = 8, RG_COMBO = 320;
 constexpr int RG_MAX_REFS = 4, RG_OPS_STRIDE = 36;          // multi-reference ring path: references per read; u64 per (reference, pair): 32 op words + (n, err) of each half
 constexpr int RG_DLO = RG_B + 1, RG_DHI = RG_NS - RG_B - 9;
 struct QuadSmem {                                  // per warp; the op streams take the place of the base-pair codes once the DP is done
@@ -199,7 +199,9 @@ constexpr int PK_BAND_SLOTS = 64, PK_BAND_B = 28, PK_BAND_MAXD = 8;
 // i.e. a lane's steps are consecutive (a diagonal run of the walk touches two or three 32-byte sectors).
 struct SlabMode { int slope, off, ns, ring, gb; };
 
-struct Walked { uint64_t ops; int n; int err; };
+// ops: the lane's 32 columns of the op stream (lane L of the group: columns 32L..32L+31 from the right); ops2 (pair walks only):
+// columns 512 + 32L.. of alignments longer than 512 columns (r02g: the ALIGN kernel takes pairs with I + J up to PK_MAX_ALN2)
+struct Walked { uint64_t ops; int n; int err; uint64_t ops2; };
 
 // ------------------------------------------------------------------------------------------------ DP
 // Traceback word of (lane l, column j): bits [16+2k, 17+2k] = origin of M[i][j] (0 M, 1 J, 2 I) and bits
@@ -316,7 +318,15 @@ C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const 
     const int TS = P.TS;
     const uint2 *__restrict__ tb2 = reinterpret_cast<const uint2 *>(tb);
     int i = R.I, j = J, n = 0, err = 0;
-    uint32_t acc = 0, lo = ~0u, hi = ~0u;
+    uint32_t acc = 0, lo = ~0u, hi = ~0u, lo2 = ~0u, hi2 = ~0u;
+    // 16 ops fill one 32-bit half-word; half-word ix belongs to word ix >> 1 = lane (word & (G-1)), second word when word >= G
+    auto put = [&](int ix, uint32_t a) {
+        const int word = ix >> 1;
+        if (hl == (word & (G - 1))) {
+            if (PAIR && word >= G) { if (ix & 1) hi2 = a; else lo2 = a; }
+            else { if (ix & 1) hi = a; else lo = a; }
+        }
+    };
     // append `cnt` (<= 32) copies of op to the stream; acc holds the (n & 15) newest ops in its top bits
     auto push = [&](int op, int cnt) {
         const uint32_t pat = (uint32_t)op * 0x55555555u;
@@ -325,7 +335,7 @@ C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const 
             const int c = cnt < room ? cnt : room;
             acc = (uint32_t)((((uint64_t)pat << 32) | acc) >> (2 * c));
             n += c; cnt -= c;
-            if ((n & 15) == 0) { const int ix = (n >> 4) - 1; if (hl == (ix >> 1)) { if (ix & 1) hi = acc; else lo = acc; } }
+            if ((n & 15) == 0) put((n >> 4) - 1, acc);
         }
     };
     for (;;) {
@@ -389,11 +399,11 @@ C2B_DEV Walked walk_batch(const KParams &P, const RefDev &R, const int J, const 
     if (j > 0) { while (j > 0) { const int c = j < 32 ? j : 32; push(OP_I, c); j -= c; } }
     if (i > 0) { while (i > 0) { const int c = i < 32 ? i : 32; push(OP_J, c); i -= c; } }
     if (n & 15) {
-        const int ix = n >> 4, used = 2 * (n & 15);
-        const uint32_t a = (acc >> (32 - used)) | (~0u << used);
-        if (hl == (ix >> 1)) { if (ix & 1) hi = a; else lo = a; }
+        const int used = 2 * (n & 15);
+        put(n >> 4, (acc >> (32 - used)) | (~0u << used));
     }
-    Walked out; out.ops = (uint64_t)lo | ((uint64_t)hi << 32); out.n = n; out.err = err;
+    if (n > (PAIR ? PK_MAX_ALN2 : 1024)) err |= 8;          // more columns than the stream holds (excluded by the callers' length limits)
+    Walked out; out.ops = (uint64_t)lo | ((uint64_t)hi << 32); out.ops2 = (uint64_t)lo2 | ((uint64_t)hi2 << 32); out.n = n; out.err = err;
     return out;
 }
 
@@ -1483,7 +1493,7 @@ C2B_DEV void process_item(const KParams &P, WarpSmem &S, const uint32_t *staged_
         if (pair && P.ref_id && haveB && P.ref_id[rdA] != P.ref_id[rdB]) pair = false;
         if (pair) {
             const int r_begin = P.ref_id ? P.ref_id[rdA] : 0, r_end = P.ref_id ? r_begin + 1 : P.n_refs;
-            for (int r = r_begin; r < r_end; r++) if (Ja > refdev(P, r).pk_maxJ) pair = false;
+            for (int r = r_begin; r < r_end; r++) if (Ja > refdev(P, r).pk_maxJ || refdev(P, r).I + Ja > PK_MAX_ALN) pair = false;
         }
     }
     if (wp::lane() == 0) wp::addg(P.stats + (pair ? 2 : 3), 1);      // path statistics (c2b_path_counts)
@@ -1697,7 +1707,7 @@ C2B_DEV void process_group(const KParams &P, WarpSmem &S, QuadSmem &Q, const uin
         const int k0 = multi ? 0 : r0, k1 = multi ? P.n_refs : r0 + 1;
         for (int k = k0; k < k1; k++) {                     // every reference the reads are tried against must admit the band
             const RefDev &R = refdev(P, k);
-            ok = ok && R.rg_ok && Jx <= R.pk_maxJ && Jx - R.I <= RG_MAXD && R.I - Jx <= RG_MAXD;
+            ok = ok && R.rg_ok && Jx <= R.pk_maxJ && R.I + Jx <= PK_MAX_ALN && Jx - R.I <= RG_MAXD && R.I - Jx <= RG_MAXD;
         }
         quad = wp::ballot(ok) == 0xffffffffu;
     }

@@ -565,7 +565,7 @@ int c2b_configure(c2b_engine *e, const c2b_params *p, int32_t n_refs, const c2b_
                       (go - ge) > -1900 && 4 * (OFFu + (go - ge)) > 256 + 4 * gmax + 3 + 64 && !(p->flags & C2B_F_NO_PAIRING);
             d.pk_maxJ = 0;
             if (ok) {
-                for (int J = 1; J <= C2B_MAX_READ_LEN && I + J <= PK_MAX_ALN; J++) {
+                for (int J = 1; J <= C2B_MAX_READ_LEN && I + J <= PK_MAX_ALN2; J++) {      // device paths that hold 512 columns add I + J <= PK_MAX_ALN
                     const int64_t bound = 4 * ((smax + 2 * beta) * std::min(I, J) + gmax * (I + J + 2) + OFFu) + 3;
                     if (bound > 32000) break;
                     d.pk_maxJ = J;

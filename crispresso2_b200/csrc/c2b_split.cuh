@@ -145,9 +145,44 @@ C2B_DEV void walk_ring4(const KParams &P, const RefDev &R, const int *Jq, const 
             const uint32_t a = (acc[q] >> (32 - used)) | (~0u << used);
             if (hl == (ix >> 1)) { if (ix & 1) hi[q] = a; else lo[q] = a; }
         }
-        out[q].ops = (uint64_t)lo[q] | ((uint64_t)hi[q] << 32); out[q].n = n[q]; out[q].err = err[q];
+        out[q].ops = (uint64_t)lo[q] | ((uint64_t)hi[q] << 32); out[q].ops2 = ~0ull; out[q].n = n[q]; out[q].err = err[q];
     }
 #undef C2B_PUSH4
+}
+
+// matchCount (Align.pyx:338-421: columns where both strings hold the same character; N over N counts) of the alignment a pair
+// walk left in this half-warp's lanes: lane hl holds columns 32 hl .. of `ops` and 512 + 32 hl .. of `ops2`, counted from the
+// right end.  codes: the read as alphabet codes in the strand that was aligned.  All 32 lanes call; the result is per half.
+C2B_DEV int match_count_half(const KParams &P, const RefDev &R, const uint8_t *codes, int J, const Walked &wk)
+{
+    const int hl = wp::lane() & 15;
+    const uint64_t lo = 0x5555555555555555ull;
+    int base_i = R.I, base_j = J, match = 0;
+#pragma unroll 1
+    for (int word = 0; word < 2; word++) {
+        const uint64_t ops = word ? wk.ops2 : wk.ops;
+        const int ci = 32 - wp::popcll((ops >> 1) & lo);     // ops consuming a reference base (M, J); OP_NONE counts for neither
+        const int cj = 32 - wp::popcll(ops & lo);            // ops consuming a read base (M, I)
+        int pk = (ci << 16) | cj;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) { const int v = wp::shfl_up(pk, d); if (hl >= d) pk += v; }
+        const int tot = wp::shfl(pk, (wp::lane() & 16) | 15);
+        pk -= (ci << 16) | cj;                               // exclusive prefix inside the half-warp
+        int i = base_i - (pk >> 16), j = base_j - (pk & 0xffff);
+        uint64_t rest = ops;
+#pragma unroll 4
+        for (int e = 0; e < 32; e++) {
+            const int op = (int)rest & 3;
+            rest >>= 2;
+            if (op == OP_NONE) continue;
+            if (op == OP_M && (uint32_t)P.alpha[codes[j - 1]] == (uint32_t)R.asc[i - 1]) match++;
+            i -= (op != OP_I); j -= (op != OP_J);
+        }
+        base_i -= tot >> 16; base_j -= tot & 0xffff;
+    }
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) match += wp::shfl_xor(match, d);
+    return match;
 }
 
 // ---------------------------------------------------------------------------------------------------- ALIGN
@@ -178,7 +213,7 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
         for (int k = k0; k < k1; k++) {
             const RefDev &R = refdev(P, k);
             ok = ok && !R.coding && Jx <= R.pk_maxJ;
-            const bool rk = P.tbq != nullptr && R.rg_ok && Jx - R.I <= RG_MAXD && R.I - Jx <= RG_MAXD;
+            const bool rk = P.tbq != nullptr && R.rg_ok && R.I + Jx <= PK_MAX_ALN && Jx - R.I <= RG_MAXD && R.I - Jx <= RG_MAXD;
             if (wp::ballot(rk) == 0xffffffffu) ringmask |= 1u << (k - k0);
         }
         quad = wp::ballot(ok) == 0xffffffffu;
@@ -332,14 +367,15 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
                         const int64_t rd = read_at(P, 2 * (first + q) + h);
                         const int64_t slot = oslot(P, rd, k);
                         if (hl < P.NW) P.gops[slot * P.NW + hl] = wk.ops;
+                        if (hl + 16 < P.NW) P.gops[slot * P.NW + 16 + hl] = wk.ops2;
                         if (hl == 0) P.gmeta[slot] = gmeta_pack(wk.n, (int)((modes >> (4 * q + 2 * h)) & 3u) == 1, GM_NONE);
                     }
                     const uint32_t mb = wp::ballot(mine);
                     if (mb & 0xffffu) pass2 |= 1u << (2 * q);
                     if (mb >> 16) pass2 |= 2u << (2 * q);
                 } else {
-                    const ColOut co = columns<true>(P, R, nullptr, nullptr, h ? S.rc[0] : S.fw[0], Jp, wk.ops, wk.n, 0, nullptr, nullptr);
-                    const int sc = score_milli(co.n_match, wk.n > 0 ? wk.n : 1);
+                    const int nm = match_count_half(P, R, h ? S.rc[0] : S.fw[0], Jp, wk);
+                    const int sc = score_milli(nm, wk.n > 0 ? wk.n : 1);
                     const int sc_fw = wp::shfl(sc, 0), sc_rc = wp::shfl(sc, 16);
                     const int pick = sc_rc > sc_fw ? 1 : 0;
                     const uint32_t bit = 1u << (2 * q + kind - 1);
@@ -348,6 +384,7 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
                         const int64_t rd = read_at(P, 2 * (first + q) + (kind - 1));
                         const int64_t slot = oslot(P, rd, k);
                         if (hl < P.NW) P.gops[slot * P.NW + hl] = wk.ops;
+                        if (hl + 16 < P.NW) P.gops[slot * P.NW + 16 + hl] = wk.ops2;
                         if (hl == 0) P.gmeta[slot] = gmeta_pack(wk.n, pick, GM_NONE);
                     }
                 }

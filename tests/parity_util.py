@@ -301,6 +301,30 @@ def check_leftover_singles(engine, n=43, seed=77):
     assert kept > 0 and sent > 0, (kept, sent)
 
 
+def check_long_pairs(engine, n=40, seed=91):
+    """Pairs whose alignment can exceed 512 columns (I + J > 512): since r02g the ALIGN kernel takes them on the packed 16-bit
+    path with two op-stream words per lane and half (up to 1024 columns; amplicons of two row blocks included); before, they fell
+    to the one-read-per-warp 32-bit path of the general kernel."""
+    from crispresso2_b200 import synth
+    rng = np.random.default_rng(seed)
+    acgt = list("ACGT")
+    for I, J in ((300, 290), (450, 300), (280, 250), (500, 312)):
+        amp = synth.random_amplicon(rng, I)
+        ref = synth.amplicon_setup(amp, guide_start=I // 2 - 10)
+        reads = []
+        for k in range(n):
+            s = synth.synth_reads(rng, amp, 1, I, sub_rate=0.02, cut=ref["cut_point"])[0].tobytes().decode()
+            if k % 5 == 1:                                   # a long insertion: many gap columns, alignment well past 512 columns
+                p = int(rng.integers(40, I - 60))
+                s = s[:p] + "".join(rng.choice(acgt, 60)) + s[p:]
+            elif k % 5 == 2:                                 # a read that starts inside the amplicon: long leading gap
+                s = s[int(rng.integers(30, 90)):]
+            reads.append((s + "".join(rng.choice(acgt, J)))[:J])
+        check_against_oracle(engine, {"Reference": ref}, ["Reference"], O.Params(), reads, O.make_matrix())
+        pairs, singles = engine.path_counts()
+        assert singles <= 8 and pairs > 0, (I, J, pairs, singles)      # the last, incomplete group of eight goes to the general kernel
+
+
 def check_ring_equals_full(engine, n=96, I=250, seed=41, oracle_subset=0):
     """Ring-banded DP (four pairs per warp, only a diagonal band computed, result kept iff the score beats the
     out-of-band bound) against the full-matrix packed path: identical records, alignments, strings, edit lists and

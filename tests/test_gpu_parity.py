@@ -235,6 +235,10 @@ def test_leftover_list_with_single_reads_and_odd_tail(eng):
     PU.check_leftover_singles(eng, n=43, seed=77)
 
 
+def test_pairs_longer_than_512_columns(eng):
+    PU.check_long_pairs(eng, n=400)
+
+
 def test_pooled_ref_id(eng):
     """BASELINE configs[3] shape: many amplicons, each read aligned to its own one (ref_id), one launch."""
     PU.check_pooled(eng, n_amplicons=24, reads_per=120, amp_len=(180, 280))
