@@ -26,6 +26,7 @@ F_NO_STRAND_SEARCH = 64
 F_NO_PAIRING = 128
 F_HDR_REF1 = 256
 F_NO_RING = 512
+F_LEGACY_INS = 1024
 
 ST_BAD_CHAR = 1
 ST_UNDEFINED = 2
@@ -79,7 +80,7 @@ EXPORTS = ["c2b_create", "c2b_destroy", "c2b_last_error", "c2b_configure", "c2b_
            "c2b_align_batch_compact", "c2b_ops_words", "c2b_expand_alignment", "c2b_expand_batch", "c2b_ops_device",
            "c2b_align_batch_device", "c2b_set_pair_order", "c2b_sync", "c2b_stream", "c2b_last_kernel_ms", "c2b_launch_count", "c2b_path_counts", "c2b_band_reruns", "c2b_ring_counts",
            "c2b_counts_layout", "c2b_counts_hist_layout", "c2b_counts_reset", "c2b_counts_read", "c2b_counts_device", "c2b_global_align",
-           "c2b_classify_aligned", "c2b_host_alloc", "c2b_host_free",
+           "c2b_classify_aligned", "c2b_classify_aligned_flags", "c2b_host_alloc", "c2b_host_free",
            "c2b_fastq_dedup", "c2b_fastq_dedup_buffer", "c2b_fastq_n_reads", "c2b_fastq_n_unique", "c2b_fastq_max_len",
            "c2b_fastq_seqs", "c2b_fastq_offsets", "c2b_fastq_counts", "c2b_fastq_first_index", "c2b_fastq_free",
            "c2b_fastq_last_error", "c2b_fastq_filter", "c2b_fastq_filter_pair", "c2b_rc_merge_weights", "c2b_screen_reads", "c2b_serial_stats",
@@ -161,6 +162,8 @@ def load(path=None):
                                    C.c_char_p, C.c_char_p, C.POINTER(i32), C.POINTER(i32)]
     L.c2b_classify_aligned.restype = C.c_int
     L.c2b_classify_aligned.argtypes = [vp, C.c_char_p, C.c_char_p, i32, C.c_char_p, i32, vp, i32, vp, vp]
+    L.c2b_classify_aligned_flags.restype = C.c_int
+    L.c2b_classify_aligned_flags.argtypes = [vp, C.c_char_p, C.c_char_p, i32, C.c_char_p, i32, vp, i32, C.c_uint32, vp, vp]
     L.c2b_host_alloc.restype = vp
     L.c2b_host_alloc.argtypes = [C.c_size_t]
     L.c2b_host_free.restype = None

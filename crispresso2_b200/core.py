@@ -56,12 +56,14 @@ def _flags(args):
         f |= _lib.F_DISCARD_INDEL_READS
     if getattr(args, "expected_hdr_amplicon_seq", "") or getattr(args, "prime_editing_pegRNA_extension_seq", ""):
         f |= _lib.F_HDR_REF1
+    if getattr(args, "use_legacy_insertion_quantification", False):
+        f |= _lib.F_LEGACY_INS
     return f
 
 
-def _unsupported(args):
-    if getattr(args, "use_legacy_insertion_quantification", False):
-        raise NotImplementedError("use_legacy_insertion_quantification is not built on the GPU path")
+def _unsupported(args, refs=None):
+    if getattr(args, "use_legacy_insertion_quantification", False) and refs and any(r.get("contains_coding_seq") for r in refs.values()):
+        raise NotImplementedError("use_legacy_insertion_quantification together with a coding sequence is not built on the GPU path")
     if getattr(args, "prime_editing_pegRNA_scaffold_seq", ""):
         raise NotImplementedError("prime-editing scaffold search (CRISPRessoCORE.py:789-796) is not built on the GPU path")
 
@@ -164,7 +166,7 @@ def _variant_from(res, i, seq, ref_names, refs):
         n = a[_A_NEDITS]
         if a[_A_STATUS] & _lib.ST_EDIT_OVERFLOW or L.edits is None or n > len(L.edits[k][r]):
             raise OverflowError("edit list overflow")
-        p = payload_from_lists(a[_A_INS_N], a[_A_DEL_N], a[_A_SUB_N], L.edits[k][r][:n], s2)
+        p = payload_from_lists(a[_A_INS_N], a[_A_DEL_N], a[_A_SUB_N], L.edits[k][r][:n], s2, legacy=bool(res_flags(res) & _lib.F_LEGACY_INS))
         p.ref_name = name
         p.aln_scores = scores
         p.irregular_ends = bool(a[_A_IRR])
@@ -328,7 +330,7 @@ def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_
     "not_aligned" (default) files them under not_aligned_variants with best_match_score -1 and logs their number; "error"
     raises EngineError before anything is launched."""
     from . import lazy
-    _unsupported(args)
+    _unsupported(args, refs)
     if aln_matrix is None:
         loc = args.needleman_wunsch_aln_matrix_loc
         if not os.path.isabs(loc) and not os.path.exists(loc):
@@ -491,7 +493,7 @@ def process_fastq_sharded(fastq_filename, variantCache, ref_names, refs, args, f
         return process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory,
                              engine=engine, aln_matrix=aln_matrix, on_out_of_contract=on_out_of_contract)
     from . import lazy
-    _unsupported(args)
+    _unsupported(args, refs)
     if aln_matrix is None:
         aln_matrix = read_matrix(args.needleman_wunsch_aln_matrix_loc)
     if engine is None:
@@ -529,7 +531,7 @@ def quantify(variantCache):
 
 
 def get_new_variant_object(args, fastq_seq, refs, ref_names, aln_matrix, pe_scaffold_dna_info=None, engine=None):
-    _unsupported(args)
+    _unsupported(args, refs)
     engine = engine or get_engine()
     configure_engine(engine, args, refs, ref_names, aln_matrix, edit_cap=max(len(refs[r]["sequence"]) for r in ref_names)
                      + len(fastq_seq) + 1)

@@ -529,18 +529,28 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
     const int I = R.I;
     const int nchunks = (I + 32) >> 5;                    // covers position I itself (end of a trailing deletion)
 
-    auto run = [&](int a, int b) {                         // one deletion run [a,b)  (COREResources.pyx:143-160)
-        const int size = b - a;
-        const bool hit = (int)R.cum[b] - (int)R.cum[a] > 0;
+    // --use_legacy_insertion_quantification (COREResources.pyx:190-315): an insertion is in the window when EITHER flank is
+    // (:284); a deletion run is reported from reference position 0 when it starts in alignment column 0 or 1 (:252-254: a <= 1,
+    // an insertion column never precedes a deletion column) and up to the LAST reference index, not one past it, when it reaches
+    // the last column (:255-257: b == I); its size stays the column count.
+    const bool legacy = (P.flags & C2B_F_LEGACY_INS) != 0;
+    auto run = [&](int a0, int b0) {                       // one deletion run [a0,b0)  (COREResources.pyx:143-160)
+        const int size = b0 - a0;
+        const int a = (legacy && a0 <= 1) ? 0 : a0, b = (legacy && b0 == I) ? I - 1 : b0;
+        const int npos = b > a ? b - a : 0;
+        const bool hit = npos > 0 && (int)R.cum[b] - (int)R.cum[a] > 0;
         if (scal) {
-            o.n_del_all++; o.n_del_pos += size;
+            o.n_del_all++; o.n_del_pos += npos;
             if (hit) { o.n_del_win++; o.del_n += size; }
             if (lane == 0 && o.nent < P.edit_cap && ed) {
-                c2b_edit e; e.a = (uint16_t)a; e.b = (uint16_t)b; e.type = 3; e.in_window = hit; e.base = 0; e.pad = 0;
+                c2b_edit e; e.a = (uint16_t)a; e.b = (uint16_t)b; e.type = 3; e.in_window = hit; e.pad = 0;
+                e.base = legacy ? (uint8_t)(size - (b - a) + 2) : 0;            // legacy: size = b - a + base - 2
                 ed[o.nent] = e;
             }
             o.nent++;
         }
+        if (legacy && (vec || ref1))                       // all_deletion_positions = the reported range, not the deleted columns
+            for (int p = a + lane; p < b; p += 32) wp::addg(V + (int64_t)(ref1 ? C2B_V_R1_ALL_DEL : C2B_V_ALL_DEL) * vs + p, w);
         if (hit && ((vec && !ign_d) || lenv)) {
             for (int p = a + lane; p < b; p += 32) {
                 if (vec && !ign_d) wp::addg(V + (int64_t)C2B_V_DEL * vs + p, w);
@@ -563,8 +573,8 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
         if (!wp::ballot(isdel || differs || insr > 0 || insl > 0) && !prevD) continue;
         const bool issub = differs && readc != 'N';                         // COREResources.pyx:111
         const bool inc_p = valid && (R.incl[p] & 1u);
-        const bool win_r = insr > 0 && inc_p && (R.incl[p + 1] & 1u);             // both flanks in window (:120)
-        const bool win_l = insl > 0 && inc_p && (R.incl[p - 1] & 1u);
+        const bool win_r = insr > 0 && (legacy ? (inc_p || (R.incl[p + 1] & 1u)) : (inc_p && (R.incl[p + 1] & 1u)));   // both flanks in window (:120); legacy: either (:284)
+        const bool win_l = insl > 0 && (legacy ? (inc_p || (R.incl[p - 1] & 1u)) : (inc_p && (R.incl[p - 1] & 1u)));
         const uint32_t D = wp::ballot(isdel);
         if (scal) {
             const uint32_t Bs = wp::ballot(issub), Bsw = wp::ballot(issub && inc_p);
@@ -598,7 +608,7 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
             if (insr > 0) wp::addg(V + (int64_t)C2B_V_ALL_INS_LEFT * vs + p, w);
             if (insr > 0 || insl > 0) wp::addg(V + (int64_t)C2B_V_ALL_INS * vs + p, w);   // a shared flank counts once
             if (!ign_i && (win_r || win_l)) wp::addg(V + (int64_t)C2B_V_INS * vs + p, w);
-            if (isdel) wp::addg(V + (int64_t)C2B_V_ALL_DEL * vs + p, w);
+            if (isdel && !legacy) wp::addg(V + (int64_t)C2B_V_ALL_DEL * vs + p, w);
             if (issub) {
                 wp::addg(V + (int64_t)C2B_V_ALL_SUB * vs + p, w);
                 if (!ign_s) {
@@ -615,7 +625,7 @@ C2B_DEVNOINL void rows_run(const KParams &P, const RefDev &R, const uint8_t *row
         if (ref1) {
             if (insr > 0) wp::addg(V + (int64_t)C2B_V_R1_ALL_INS_LEFT * vs + p, w);
             if (insr > 0 || insl > 0) wp::addg(V + (int64_t)C2B_V_R1_ALL_INS * vs + p, w);
-            if (isdel) wp::addg(V + (int64_t)C2B_V_R1_ALL_DEL * vs + p, w);
+            if (isdel && !legacy) wp::addg(V + (int64_t)C2B_V_R1_ALL_DEL * vs + p, w);
             if (issub) wp::addg(V + (int64_t)C2B_V_R1_ALL_SUB * vs + p, w);
             if (isdel || differs) {
                 const int rc = R.rcode[p];

@@ -1333,6 +1333,13 @@ int c2b_classify_aligned(c2b_engine *e, const char *read_al, const char *ref_al,
                          const char *alphabet, int32_t nq, const int64_t *include_idx, int32_t n_include,
                          c2b_aln_rec *out, c2b_edit *edits)
 {
+    return c2b_classify_aligned_flags(e, read_al, ref_al, n_cols, alphabet, nq, include_idx, n_include, 0u, out, edits);
+}
+
+int c2b_classify_aligned_flags(c2b_engine *e, const char *read_al, const char *ref_al, int32_t n_cols,
+                               const char *alphabet, int32_t nq, const int64_t *include_idx, int32_t n_include,
+                               uint32_t flags, c2b_aln_rec *out, c2b_edit *edits)
+{
     if (!e || !read_al || !ref_al || !alphabet || !out || !edits || n_cols < 1) return fail(e, C2B_E_ARG, "c2b_classify_aligned: bad argument");
     if (n_cols > C2B_MAX_ALN_LEN) return fail(e, C2B_E_LIMIT, "c2b_classify_aligned: alignment longer than C2B_MAX_ALN_LEN");
     if (nq < 1 || nq > C2B_MAX_Q) return fail(e, C2B_E_LIMIT, "c2b_classify_aligned: alphabet larger than C2B_MAX_Q");
@@ -1353,7 +1360,7 @@ int c2b_classify_aligned(c2b_engine *e, const char *read_al, const char *ref_al,
     if (read.empty() || ref.empty()) return fail(e, C2B_E_ARG, "c2b_classify_aligned: empty sequence");
     if ((int)read.size() > C2B_MAX_READ_LEN || (int)ref.size() > C2B_MAX_REF_LEN) return fail(e, C2B_E_LIMIT, "c2b_classify_aligned: sequence too long");
     c2b_params p; memset(&p, 0, sizeof p);
-    p.gap_open = -1; p.gap_extend = -1; p.flags = C2B_F_NO_STRAND_SEARCH; p.nq = nq; p.edit_cap = n_cols + 1;
+    p.gap_open = -1; p.gap_extend = -1; p.flags = C2B_F_NO_STRAND_SEARCH | (flags & C2B_F_LEGACY_INS); p.nq = nq; p.edit_cap = n_cols + 1;
     memcpy(p.alphabet, alphabet, nq);
     for (int q = 0; q < nq; q++) p.complement[q] = (uint8_t)q;
     std::vector<int64_t> gi(ref.size() + 1, 0), rows((size_t)nq * ref.size(), 0);

@@ -584,18 +584,25 @@ C2B_DEVNOINL void colscan1(const KParams &P, const RefDev &R, const ColCtx &c, R
     int flank_all = -1, flank_win = -1;      // right flank of the last insertion counted in ALL_INS / INS
     const int nsteps = (c.n + 31) >> 5;
 
-    auto del_run = [&](int a, int b) {                     // one deletion run [a,b)  (COREResources.pyx:143-160)
-        const int size = b - a;
-        const bool hit = (int)R.cum[b] - (int)R.cum[a] > 0;
+    // --use_legacy_insertion_quantification: same rules as rows_run (c2b_core.cuh), COREResources.pyx:190-315
+    const bool legacy = (P.flags & C2B_F_LEGACY_INS) != 0;
+    auto del_run = [&](int a0, int b0) {                   // one deletion run [a0,b0)  (COREResources.pyx:143-160)
+        const int size = b0 - a0;
+        const int a = (legacy && a0 <= 1) ? 0 : a0, b = (legacy && b0 == I) ? I - 1 : b0;
+        const int npos = b > a ? b - a : 0;
+        const bool hit = npos > 0 && (int)R.cum[b] - (int)R.cum[a] > 0;
         if (scal) {
-            o.n_del_all++; o.n_del_pos += size;
+            o.n_del_all++; o.n_del_pos += npos;
             if (hit) { o.n_del_win++; o.del_n += size; }
             if (lane == 0 && o.nent < P.edit_cap && ed) {
-                c2b_edit e; e.a = (uint16_t)a; e.b = (uint16_t)b; e.type = 3; e.in_window = hit; e.base = 0; e.pad = 0;
+                c2b_edit e; e.a = (uint16_t)a; e.b = (uint16_t)b; e.type = 3; e.in_window = hit; e.pad = 0;
+                e.base = legacy ? (uint8_t)(size - (b - a) + 2) : 0;
                 ed[o.nent] = e;
             }
             o.nent++;
         }
+        if (legacy && (vec || ref1))
+            for (int p = a + lane; p < b; p += 32) wp::addg(V + (int64_t)(ref1 ? C2B_V_R1_ALL_DEL : C2B_V_ALL_DEL) * vs + p, w);
         if (hit && ((vec && !ign_d) || lenv)) {
             for (int p = a + lane; p < b; p += 32) {
                 if (vec && !ign_d) wp::addg(V + (int64_t)C2B_V_DEL * vs + p, w);
@@ -606,7 +613,7 @@ C2B_DEVNOINL void colscan1(const KParams &P, const RefDev &R, const ColCtx &c, R
     auto ins_run = [&](int p1, int size) {                 // insertion of `size` bases between reference positions p1-1 and p1
         if (p1 < 1 || p1 > I - 1) return;                  // before the first / after the last reference base: not an insertion (:117)
         const int p = p1 - 1;
-        const bool win = (R.incl[p] & 1u) && (R.incl[p1] & 1u);      // both flanks in the window (:120)
+        const bool win = legacy ? (((R.incl[p] | R.incl[p1]) & 1u) != 0) : ((R.incl[p] & 1u) && (R.incl[p1] & 1u));   // both flanks in the window (:120); legacy: either (:284)
         if (scal) {
             o.n_ins_all++;
             if (win) { o.n_ins_win++; o.ins_n += size; }
@@ -666,7 +673,7 @@ C2B_DEVNOINL void colscan1(const KParams &P, const RefDev &R, const ColCtx &c, R
             }
         }
         if (vec) {
-            if (isdel) wp::addg(V + (int64_t)C2B_V_ALL_DEL * vs + p, w);
+            if (isdel && !legacy) wp::addg(V + (int64_t)C2B_V_ALL_DEL * vs + p, w);
             if (issub) {
                 wp::addg(V + (int64_t)C2B_V_ALL_SUB * vs + p, w);
                 if (!ign_s) {
@@ -681,7 +688,7 @@ C2B_DEVNOINL void colscan1(const KParams &P, const RefDev &R, const ColCtx &c, R
             }
         }
         if (ref1) {
-            if (isdel) wp::addg(V + (int64_t)C2B_V_R1_ALL_DEL * vs + p, w);
+            if (isdel && !legacy) wp::addg(V + (int64_t)C2B_V_R1_ALL_DEL * vs + p, w);
             if (issub) wp::addg(V + (int64_t)C2B_V_R1_ALL_SUB * vs + p, w);
             if (isdel || differs) {
                 const int rc = R.rcode[p];

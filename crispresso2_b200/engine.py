@@ -205,8 +205,9 @@ class Engine:
         buf, off = pack_reads(reads)
         return self.align_packed(buf, off, **kw)
 
-    def classify_pair(self, read_al, ref_al, include_idx, alphabet=None):
-        """find_indels_substitutions on one aligned pair (GPU row-classification kernel).  Reconfigures."""
+    def classify_pair(self, read_al, ref_al, include_idx, alphabet=None, legacy=False):
+        """find_indels_substitutions (legacy=True: find_indels_substitutions_legacy) on one aligned pair (GPU row-classification
+        kernel).  Reconfigures."""
         n = len(ref_al)
         if alphabet is None:
             extra = sorted(set(read_al) - set("ACGTN-"))
@@ -214,8 +215,9 @@ class Engine:
         inc = np.ascontiguousarray(include_idx, dtype=np.int64)
         aln = np.zeros(1, dtype=_lib.ALN_DTYPE)
         edits = np.zeros(n + 1, dtype=_lib.EDIT_DTYPE)
-        rc = self.L.c2b_classify_aligned(self.h, read_al.encode(), ref_al.encode(), n, alphabet.encode(), len(alphabet),
-                                         inc.ctypes.data, len(inc), aln.ctypes.data, edits.ctypes.data)
+        rc = self.L.c2b_classify_aligned_flags(self.h, read_al.encode(), ref_al.encode(), n, alphabet.encode(), len(alphabet),
+                                               inc.ctypes.data, len(inc), _lib.F_LEGACY_INS if legacy else 0, aln.ctypes.data,
+                                               edits.ctypes.data)
         self.n_refs = 0
         if rc == -2:
             raise NotImplementedError("aligned pair outside the aligner's invariants: %s"

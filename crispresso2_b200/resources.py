@@ -72,7 +72,7 @@ def ref_positions_fast(aln_ref):
     return out
 
 
-def payload_from_lists(insertion_n, deletion_n, substitution_n, edits, aln_ref):
+def payload_from_lists(insertion_n, deletion_n, substitution_n, edits, aln_ref, legacy=False):
     """Batch fast path of payload_from_device: `edits` is a list of plain tuples (a, b, type, in_window, base, pad) --
     EDIT_DTYPE rows after one .tolist() per batch -- already cut to the alignment's n_edits.  Same lists, built with
     plain Python on the (usually 0-3) entries instead of numpy masks."""
@@ -101,7 +101,9 @@ def payload_from_lists(insertion_n, deletion_n, substitution_n, edits, aln_ref):
             if inw:
                 del_coords.append((a, b))
                 del_pos.extend(range(a, b))
-                del_sizes.append(b - a)
+                del_sizes.append(b - a + base - 2 if legacy else b - a)     # legacy: the column count (c2b_edit.base = size - (b - a) + 2)
+    if legacy:                                            # COREResources.pyx:311-312: numpy sums (0.0 for no window indel)
+        insertion_n, deletion_n = np.sum(ins_sizes), np.sum(del_sizes)
     p = ResultsSlotsDict.__new__(ResultsSlotsDict)
     p.all_insertion_positions = all_ins_pos
     p.all_insertion_left_positions = all_ins_left
@@ -124,7 +126,7 @@ def payload_from_lists(insertion_n, deletion_n, substitution_n, edits, aln_ref):
     return p
 
 
-def payload_from_device(aln, edits, aln_read, aln_ref):
+def payload_from_device(aln, edits, aln_read, aln_ref, legacy=False):
     """aln: one ALN_DTYPE record; edits: EDIT_DTYPE array (at least aln['n_edits'] valid entries)."""
     n = int(aln["n_edits"])
     if aln["status"] & _lib.ST_EDIT_OVERFLOW or n > len(edits):
@@ -148,13 +150,17 @@ def payload_from_device(aln, edits, aln_read, aln_ref):
     del_coords = [(int(a), int(b)) for a, b in zip(dw["a"], dw["b"])]
     del_pos = [p for a, b in del_coords for p in range(a, b)]
     del_sizes = [b - a for a, b in del_coords]
+    ins_n, del_n = int(aln["insertion_n"]), int(aln["deletion_n"])
+    if legacy:
+        del_sizes = [int(b) - int(a) + int(x) - 2 for a, b, x in zip(dw["a"], dw["b"], dw["base"])]
+        ins_n, del_n = np.sum(ins_sizes), np.sum(del_sizes)
     return ResultsSlotsDict(
         all_insertion_positions=all_ins_pos, all_insertion_left_positions=all_ins_left,
         insertion_positions=ins_pos, insertion_coordinates=ins_coords, insertion_sizes=ins_sizes,
-        insertion_n=int(aln["insertion_n"]),
+        insertion_n=ins_n,
         all_deletion_positions=all_del_pos, all_deletion_coordinates=all_del_coords,
         deletion_positions=del_pos, deletion_coordinates=del_coords, deletion_sizes=del_sizes,
-        deletion_n=int(aln["deletion_n"]),
+        deletion_n=del_n,
         all_substitution_positions=all_sub_pos, substitution_positions=sub_pos,
         all_substitution_values=np.array(all_sub_val), substitution_values=np.array(sub_val),
         substitution_n=int(aln["substitution_n"]),
@@ -165,7 +171,7 @@ def payload_from_device(aln, edits, aln_read, aln_ref):
 _pair_engine = None
 
 
-def find_indels_substitutions(read_seq_al, ref_seq_al, _include_indx):
+def find_indels_substitutions(read_seq_al, ref_seq_al, _include_indx, _legacy=False):
     """Drop-in for CRISPRessoCOREResources.find_indels_substitutions (COREResources.pyx:71) for aligned
     pairs that obey the aligner's invariants (no column with two gaps, no insertion column next to a
     deletion column -- true of every global_align output, Align.pyx:394-413).  Runs the engine's
@@ -177,5 +183,11 @@ def find_indels_substitutions(read_seq_al, ref_seq_al, _include_indx):
     if _pair_engine is None:
         _pair_engine = Engine()
     e = _pair_engine
-    aln, edits = e.classify_pair(read_seq_al, ref_seq_al, [int(v) for v in _include_indx])
-    return payload_from_device(aln, edits, read_seq_al, ref_seq_al)
+    aln, edits = e.classify_pair(read_seq_al, ref_seq_al, [int(v) for v in _include_indx], legacy=_legacy)
+    return payload_from_device(aln, edits, read_seq_al, ref_seq_al, legacy=_legacy)
+
+
+def find_indels_substitutions_legacy(read_seq_al, ref_seq_al, _include_indx):
+    """Drop-in for CRISPRessoCOREResources.find_indels_substitutions_legacy (COREResources.pyx:190-315,
+    `--use_legacy_insertion_quantification`), same restrictions as find_indels_substitutions."""
+    return find_indels_substitutions(read_seq_al, ref_seq_al, _include_indx, _legacy=True)

@@ -44,6 +44,7 @@ extern "C" {
 #define C2B_F_DISCARD_INDEL_READS  32u
 #define C2B_F_NO_STRAND_SEARCH     64u   /* global_align-only mode: forward strand, no seed test */
 #define C2B_F_NO_PAIRING          128u   /* debugging / A-B runs: never use the packed two-reads-per-warp path */
+#define C2B_F_LEGACY_INS         1024u   /* args.use_legacy_insertion_quantification: find_indels_substitutions_legacy (COREResources.pyx:190-315) */
 #define C2B_F_NO_RING             512u   /* debugging / A-B runs: never use the ring-banded four-pairs-per-warp path */
 #define C2B_F_HDR_REF1            256u   /* args.expected_hdr_amplicon_seq / prime-editing extension set: also build the
                                             "ref1" re-projection vectors of CRISPRessoCORE.py:4195-4272 */
@@ -281,6 +282,10 @@ int  c2b_global_align(c2b_engine *e, const char *read, int32_t read_len, const c
 int  c2b_classify_aligned(c2b_engine *e, const char *read_al, const char *ref_al, int32_t n_cols,
                           const char *alphabet, int32_t nq, const int64_t *include_idx, int32_t n_include,
                           c2b_aln_rec *out, c2b_edit *edits);
+/* the same with engine flags: C2B_F_LEGACY_INS selects find_indels_substitutions_legacy (COREResources.pyx:190-315) */
+int  c2b_classify_aligned_flags(c2b_engine *e, const char *read_al, const char *ref_al, int32_t n_cols,
+                                const char *alphabet, int32_t nq, const int64_t *include_idx, int32_t n_include,
+                                uint32_t flags, c2b_aln_rec *out, c2b_edit *edits);
 
 /* replaces: the FASTQ read + de-duplication loop of process_fastq (CRISPRessoCORE.py:1820-1849): four lines per
  * record (text-mode universal newlines), sequence = line 2 stripped of surrounding whitespace, identical sequences

@@ -213,8 +213,7 @@ def find_indels_substitutions(read_al, ref_al, include_idx):
 
 
 def find_indels_substitutions_legacy(read_al, ref_al, include_idx):
-    """Restatement of COREResources.pyx:190-315 (`--use_legacy_insertion_quantification`), kept for the next round: the device path
-    does not build it yet.  Differences from the current function: a window insertion needs only ONE flank in the window
+    """Restatement of COREResources.pyx:190-315 (`--use_legacy_insertion_quantification`).  Differences from the current function: a window insertion needs only ONE flank in the window
     (:284); deletion coordinates come from alignment columns with two end rules -- a run starting in column 0 or 1 is reported
     from reference position 0 (:252-254), a run reaching the last column ends at the last reference index, not one past it
     (:255-257); sizes are column counts; deletion_n / insertion_n are numpy sums (0.0 for an empty list)."""
@@ -283,6 +282,7 @@ class Params:
         self.expand_ambiguous_alignments = False
         self.discard_indel_reads = False
         self.expected_hdr_amplicon_seq = ""
+        self.use_legacy_insertion_quantification = False
         for k, v in kw.items():
             setattr(self, k, v)
 
@@ -336,7 +336,10 @@ def new_variant(params, seq, refs, ref_names, matrix):
     out["aln_ref_names"] = [w[0] for w in winners]
     labels = []
     for name, s1, s2, strand in winners:
-        p = find_indels_substitutions(s1, s2, refs[name]["include_idxs"])
+        if getattr(params, "use_legacy_insertion_quantification", False):          # CRISPRessoCORE.py:721-724
+            p = find_indels_substitutions_legacy(s1, s2, refs[name]["include_idxs"])
+        else:
+            p = find_indels_substitutions(s1, s2, refs[name]["include_idxs"])
         p["ref_name"] = name
         p["aln_scores"] = scores
         head_bad = s1[0] == "-" or s2[0] == "-" or s1[0] != s2[0]
@@ -582,7 +585,10 @@ def ref1_vectors(cache, refs, ref_names, params):
         if v["class_name"] == "AMBIGUOUS":
             continue
         _, s1, s2, _ = v["ref_aln_details"][0]
-        p = find_indels_substitutions(s1, s2, refs[r0]["include_idxs"])
+        if getattr(params, "use_legacy_insertion_quantification", False):          # CRISPRessoCORE.py:4244-4247
+            p = find_indels_substitutions_legacy(s1, s2, refs[r0]["include_idxs"])
+        else:
+            p = find_indels_substitutions(s1, s2, refs[r0]["include_idxs"])
         for r in v["aln_ref_names"]:
             if r == r0:
                 continue

@@ -26,7 +26,7 @@ def edits_canonical(res, r=0):
 
 def args_from(params):
     a = types.SimpleNamespace(**params)
-    a.use_legacy_insertion_quantification = False
+    a.use_legacy_insertion_quantification = bool(params.get("use_legacy_insertion_quantification", False))
     a.prime_editing_pegRNA_scaffold_seq = ""
     a.needleman_wunsch_aln_matrix_loc = "EDNAFULL"
     a.n_processes = "1"
@@ -299,6 +299,31 @@ def check_leftover_singles(engine, n=43, seed=77):
     engine.path_counts()
     kept, sent = engine.ring_counts()
     assert kept > 0 and sent > 0, (kept, sent)
+
+
+def check_legacy(engine, n=120, seed=17):
+    """--use_legacy_insertion_quantification (find_indels_substitutions_legacy, COREResources.pyx:190-315) through the whole path,
+    one amplicon and HDR mode (the ref1 re-projection uses the legacy function too, CRISPRessoCORE.py:4244-4247): insertions with
+    ONE flank in the window, deletions that start at reference position 0 / 1 or reach the last position."""
+    from crispresso2_b200 import synth
+    rng = np.random.default_rng(seed)
+    acgt = list("ACGT")
+    amp = synth.random_amplicon(rng, 200)
+    ref = synth.amplicon_setup(amp, guide_start=90, window_size=3)
+    cut = ref["cut_point"]
+    lo, hi = int(min(ref["include_idxs"])), int(max(ref["include_idxs"]))
+    reads = [r.tobytes().decode() for r in synth.synth_reads(rng, amp, n, 200, sub_rate=0.01, cut=cut)]
+    extra = [amp[1:], amp[2:] + "AC", amp[:-1], amp[:-3] + "GGT", amp[:1] + amp[3:],                       # end rules of the deletion coordinates
+             amp[:lo] + "TTTT" + amp[lo:], amp[:hi + 1] + "GG" + amp[hi + 1:], amp[:lo - 1] + "CA" + amp[lo - 1:],   # one flank / both / none in the window
+             amp[:hi + 2] + "ACG" + amp[hi + 2:], amp[:cut - 20] + amp[cut + 15:]]
+    reads += [(e + "".join(rng.choice(acgt, 200)))[:200] for e in extra]
+    check_against_oracle(engine, {"Reference": ref}, ["Reference"], O.Params(use_legacy_insertion_quantification=True), reads,
+                         O.make_matrix())
+    hdr = amp[:cut - 2] + "TGA" + amp[cut + 1:cut + 4] + "ACGTAC" + amp[cut + 4:]
+    ref2 = synth.amplicon_setup(hdr, guide_start=90, window_size=3)
+    r2 = [r.tobytes().decode() for r in synth.synth_reads(rng, hdr, 60, 200, del_frac=0.1, ins_frac=0.05, cut=ref2["cut_point"])]
+    P = O.Params(use_legacy_insertion_quantification=True, expected_hdr_amplicon_seq=hdr)
+    check_against_oracle(engine, {"Reference": ref, "HDR": ref2}, ["Reference", "HDR"], P, reads[:60] + r2 + reads[-10:], O.make_matrix())
 
 
 def check_long_pairs(engine, n=40, seed=91):

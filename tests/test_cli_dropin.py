@@ -88,10 +88,11 @@ def _cases():
         # process_fastq_write_out (CRISPRessoCORE.py:2283-2348) wraps the module-global process_fastq and
         # annotates every FASTQ record from variantCache / not_aligned -- with the engine's lazy entries behind it
         "fanc_fastq_output": ["-r1", fq, "-a", ns["FANC"], "-g", g, "-e", ns["FANC_HDR"], "--fastq_output"],
+        "fanc_legacy": ["-r1", fq, "-a", ns["FANC"], "-g", g, "-e", ns["FANC_HDR"], "--use_legacy_insertion_quantification", "-w", "4"],
     }
 
 
-@pytest.mark.parametrize("case", ["fanc_default", "fanc_params", "fanc_flags", "fanc_fastq_output"])
+@pytest.mark.parametrize("case", ["fanc_default", "fanc_params", "fanc_flags", "fanc_fastq_output", "fanc_legacy"])
 def test_reference_cli_with_engine_process_fastq_is_byte_identical(case, tmp_path):
     import build_emu
     lib = build_emu.build()

@@ -135,6 +135,10 @@ def test_pairs_longer_than_512_columns(emu):
     PU.check_long_pairs(emu, n=16)
 
 
+def test_legacy_insertion_quantification(emu):
+    PU.check_legacy(emu)
+
+
 def test_pooled_ref_id(emu):
     PU.check_pooled(emu, n_amplicons=4, reads_per=24)
     PU.check_pooled(emu, n_amplicons=40, reads_per=3, seed=5)          # more references than C2B_MAX_REFS: Pooled only

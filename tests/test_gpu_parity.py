@@ -239,6 +239,10 @@ def test_pairs_longer_than_512_columns(eng):
     PU.check_long_pairs(eng, n=400)
 
 
+def test_legacy_insertion_quantification(eng):
+    PU.check_legacy(eng, n=3000)
+
+
 def test_pooled_ref_id(eng):
     """BASELINE configs[3] shape: many amplicons, each read aligned to its own one (ref_id), one launch."""
     PU.check_pooled(eng, n_amplicons=24, reads_per=120, amp_len=(180, 280))

@@ -1,8 +1,8 @@
 """The reference's OWN unit tests for its two native modules (tests/unit_tests/test_CRISPResso2Align.py,
 test_CRISPRessoCOREResources.py), executed from /root/reference against the replacement modules: `CRISPResso2Align` and
 `CRISPRessoCOREResources` are stand-ins exposing crispresso2_b200.align / .resources on the warp-emulator build of the engine.
-CPU only; skipped where /root/reference is absent.  Not built and therefore expected to fail: the legacy insertion
-quantification (`find_indels_substitutions_legacy`)."""
+CPU only; skipped where /root/reference is absent.  All of them must pass (r02: the legacy insertion quantification,
+`find_indels_substitutions_legacy`, included)."""
 import importlib.util
 import os
 import sys
@@ -15,7 +15,7 @@ REF = "/root/reference"
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "tests", "unit_tests")), reason="needs /root/reference")
 sys.path.insert(0, os.path.join(HERE, "emu"))
 
-NOT_BUILT = {"test_find_indels_substitutions_legacy"}
+NOT_BUILT = set()
 
 
 def _load(test_file):
@@ -33,7 +33,12 @@ def _load(test_file):
         a, ed = eng.classify_pair(read_al, ref_al, [int(v) for v in inc])
         return resources.payload_from_device(a, ed, read_al, ref_al)
 
+    def find_legacy(read_al, ref_al, inc):
+        a, ed = eng.classify_pair(read_al, ref_al, [int(v) for v in inc], legacy=True)
+        return resources.payload_from_device(a, ed, read_al, ref_al, legacy=True)
+
     R.find_indels_substitutions = find
+    R.find_indels_substitutions_legacy = find_legacy
     R.ResultsSlotsDict = resources.ResultsSlotsDict
     pkg = types.ModuleType("CRISPResso2")
     pkg.CRISPResso2Align, pkg.CRISPRessoCOREResources = A, R
