@@ -348,8 +348,7 @@ def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_
     t0 = time.perf_counter()
     if not variantCache:
         buf, off, counts = dd.buf, dd.off, dd.counts
-        keys = lazy.make_keys(buf, off)
-        last_timings["keys"] = time.perf_counter() - t0
+        keys = None                                         # made while the GPU batch runs (_process_uniques)
     else:                                                   # caller pre-seeded the cache: same += semantics, same key order
         for seq, c in zip(dd.uniques, dd.counts.tolist()):
             variantCache[seq] = variantCache.get(seq, 0) + c
@@ -381,7 +380,7 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
     import logging
     import time
     t_start = time.perf_counter()
-    n = len(keys)
+    n = len(off) - 1
     flags = _flags(args)
     configure_engine(engine, args, refs, ref_names, aln_matrix)
     engine.counts_reset()
@@ -389,8 +388,9 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
     n_bad = int(bad.sum())
     if n_bad:
         k = int(np.nonzero(bad)[0][0])
+        first = bytes(buf[off[k]:off[k + 1]][:40]).decode("utf-8", errors="replace")
         msg = ("%d unique read(s) (%d reads) are outside the engine's contract (empty, longer than %d bp, or symbols other than "
-               "ACGTN), first: %r" % (n_bad, int(counts[bad].sum()), _lib.MAX_READ_LEN, keys[k][:40]))
+               "ACGTN), first: %r" % (n_bad, int(counts[bad].sum()), _lib.MAX_READ_LEN, first))
         if on_out_of_contract == "error":
             raise EngineError(msg)
         logging.getLogger("CRISPResso2").warning("crispresso2_b200: %s -- filed under not-aligned reads", msg)
@@ -400,18 +400,42 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
         np.cumsum(lens, out=o2[1:])
         keep = np.repeat(~bad, np.diff(off))
         buf_g, off_g, counts_g = buf[keep], o2, np.ascontiguousarray(counts[good])
-        keys_g = [keys[k] for k in good.tolist()]
     else:
-        buf_g, off_g, counts_g, keys_g = buf, off, counts, keys
-    ng = len(keys_g)
+        buf_g, off_g, counts_g = buf, off, counts
+    ng = len(off_g) - 1
+
+    def key_lists():
+        """the unique reads as Python strings (variantCache keys): all of them, and the ones the engine takes"""
+        t0 = time.perf_counter()
+        ks = keys if keys is not None else lazy.make_keys(buf, off)
+        last_timings["keys"] = time.perf_counter() - t0
+        return ks, ([ks[k] for k in good.tolist()] if n_bad else ks)
+
     weights = merge_weights_packed(buf_g, off_g, counts_g, lib_path=engine.lib_path)     # needs the global unique table: before sharding
     last_timings["screen_rc_merge"] = time.perf_counter() - t_start
     t_gpu = time.perf_counter()
     if group is None:
-        res, _ = align_uniques(engine, None, counts_g, ref_names, refs, flags, weights=weights, packed=(buf_g, off_g), compact=True)
+        # the batch call spends its time inside the library (GIL released): the key strings are made meanwhile
+        import threading
+        box = {}
+
+        def batch():
+            try:
+                box["res"] = align_uniques(engine, None, counts_g, ref_names, refs, flags, weights=weights, packed=(buf_g, off_g), compact=True)[0]
+            except BaseException as ex:                     # noqa: BLE001 -- re-raised on the calling thread
+                box["err"] = ex
+
+        th = threading.Thread(target=batch)
+        th.start()
+        keys, keys_g = key_lists()
+        th.join()
+        if "err" in box:
+            raise box["err"]
+        res = box["res"]
         parts = [(0, res, _complete_edit_lists(engine, res, buf_g, off_g, flags))]
         raw = None
     else:
+        keys, keys_g = key_lists()
         import torch.distributed as dist
         from . import dist as cdist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -505,7 +529,7 @@ def process_fastq_sharded(fastq_filename, variantCache, ref_names, refs, args, f
     dd = fastq.dedup_file(fastq_filename, lib_path=engine.lib_path)
     if not variantCache:
         buf, off, counts = dd.buf, dd.off, dd.counts
-        keys = lazy.make_keys(buf, off)
+        keys = None
     else:
         for seq, c in zip(dd.uniques, dd.counts.tolist()):
             variantCache[seq] = variantCache.get(seq, 0) + c

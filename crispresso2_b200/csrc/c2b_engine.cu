@@ -871,6 +871,9 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
                            uint8_t *d_strings, c2b_edit *d_edits)
 {
     if (!e || !e->configured) return fail(e, C2B_E_STATE, "c2b_align_batch_device: engine not configured");
+#ifndef C2B_EMU
+    cudaSetDevice(e->device);
+#endif
     if (max_read_len < 1) max_read_len = 1;
     const int W = (e->max_I + max_read_len + 31) & ~31, nr = d_ref_id ? 1 : e->n_refs;
     int rc = ensure_ops(e, e->gops, e->gmeta, e->left, n_reads, nr, W);
@@ -992,6 +995,9 @@ static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *
     if (!e || !e->configured) return fail(e, C2B_E_STATE, "c2b_align_batch: engine not configured");
     if (n_reads < 0 || !recs || !alns || (n_reads && (!reads || !offsets))) return fail(e, C2B_E_ARG, "c2b_align_batch: bad argument");
     if ((ops == nullptr) != (meta == nullptr)) return fail(e, C2B_E_ARG, "c2b_align_batch: ops and meta go together");
+#ifndef C2B_EMU
+    cudaSetDevice(e->device);                              // the current device is per host thread: callers may use a worker thread
+#endif
     if (n_reads == 0) return C2B_OK;
     int64_t maxJ = 1;
     for (int64_t r = 0; r < n_reads; r++) {

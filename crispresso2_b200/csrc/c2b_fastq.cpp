@@ -21,6 +21,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <memory>
 #include <chrono>
 #include <cstdlib>
 #include <cstdio>
@@ -89,7 +90,7 @@ bool read_gz(const char *path, std::vector<uint8_t> &buf, std::string &err)
 }  // namespace
 
 struct c2b_fastq {
-    std::vector<uint8_t> seqs;
+    std::unique_ptr<uint8_t[]> seqs;                        // packed unique sequences (uninitialised storage: every byte is written by emit)
     std::vector<int64_t> offsets;
     std::vector<int32_t> counts;
     std::vector<int64_t> first_index;
@@ -225,37 +226,54 @@ int c2b_fastq_dedup_buffer(const uint8_t *data, size_t n, int32_t n_threads, c2b
     }
 
     lap("dedup");
-    // (4) merge by first index (every shard list is already ascending)
-    size_t nu = 0;
-    for (auto &E : found) nu += E.size();
-    std::vector<Ent> all;
-    all.reserve(nu);
-    for (auto &E : found) all.insert(all.end(), E.begin(), E.end());
-    if (T > 1) std::sort(all.begin(), all.end(), [](const Ent &a, const Ent &b) { return a.first < b.first; });
+    // (4) unique reads in first-seen order: the shards' entries are scattered to their first record (disjoint records, so
+    // in parallel), a prefix count over the records numbers them -- no sort, no serial pass over the unique reads
+    std::vector<int32_t> cnt_at((size_t)n_rec, 0);
+    {
+        auto scatter = [&](int t) { for (const Ent &e : found[(size_t)t]) cnt_at[(size_t)e.first] = e.count; };
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(scatter, t);
+        scatter(0);
+        for (auto &x : th) x.join();
+    }
+    std::vector<size_t> u0((size_t)T + 1, 0);              // unique reads / bytes before thread t's record range
+    std::vector<int64_t> b0((size_t)T + 1, 0);
+    std::vector<int32_t> mx((size_t)T, 0);
+    auto rec_lo = [&](int t) { return n_rec * t / T; };
+    {
+        auto count = [&](int t) {
+            size_t u = 0; int64_t by = 0; int32_t m = 0;
+            for (int64_t r = rec_lo(t); r < rec_lo(t + 1); r++) if (cnt_at[(size_t)r]) { u++; by += seq[(size_t)r].len; m = std::max<int32_t>(m, (int32_t)seq[(size_t)r].len); }
+            u0[(size_t)t + 1] = u; b0[(size_t)t + 1] = by; mx[(size_t)t] = m;
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(count, t);
+        count(0);
+        for (auto &x : th) x.join();
+    }
+    for (int t = 0; t < T; t++) { u0[(size_t)t + 1] += u0[(size_t)t]; b0[(size_t)t + 1] += b0[(size_t)t]; F->max_len = std::max(F->max_len, mx[(size_t)t]); }
+    const size_t nu = u0[(size_t)T];
+    const int64_t tot = b0[(size_t)T];
     F->offsets.resize(nu + 1);
     F->counts.resize(nu);
     F->first_index.resize(nu);
-    int64_t tot = 0;
-    for (size_t u = 0; u < nu; u++) {
-        F->offsets[u] = tot;
-        tot += seq[(size_t)all[u].first].len;
-        F->counts[u] = all[u].count;
-        F->first_index[u] = all[u].first;
-        F->max_len = std::max<int32_t>(F->max_len, (int32_t)seq[(size_t)all[u].first].len);
-    }
     F->offsets[nu] = tot;
-    F->seqs.resize((size_t)tot + 16);
-    auto copy_range = [&](int t) {
-        const size_t a = nu * t / T, b = nu * (t + 1) / T;
-        for (size_t u = a; u < b; u++) {
-            const Seq &s = seq[(size_t)all[u].first];
-            memcpy(F->seqs.data() + F->offsets[u], s.p, s.len);
-        }
-    };
+    F->seqs.reset(new uint8_t[(size_t)tot + 16]);
     {
+        auto emit = [&](int t) {
+            size_t u = u0[(size_t)t]; int64_t by = b0[(size_t)t];
+            for (int64_t r = rec_lo(t); r < rec_lo(t + 1); r++) {
+                const int32_t c = cnt_at[(size_t)r];
+                if (!c) continue;
+                const Seq &q = seq[(size_t)r];
+                F->offsets[u] = by; F->counts[u] = c; F->first_index[u] = r;
+                memcpy(F->seqs.get() + by, q.p, q.len);
+                by += q.len; u++;
+            }
+        };
         std::vector<std::thread> th;
-        for (int t = 1; t < T; t++) th.emplace_back(copy_range, t);
-        copy_range(0);
+        for (int t = 1; t < T; t++) th.emplace_back(emit, t);
+        emit(0);
         for (auto &x : th) x.join();
     }
     lap("emit");
@@ -296,7 +314,7 @@ int c2b_fastq_dedup(const char *path, int32_t n_threads, c2b_fastq **out)
 int64_t c2b_fastq_n_reads(const c2b_fastq *f) { return f ? f->n_reads : 0; }
 int64_t c2b_fastq_n_unique(const c2b_fastq *f) { return f ? (int64_t)f->counts.size() : 0; }
 int32_t c2b_fastq_max_len(const c2b_fastq *f) { return f ? f->max_len : 0; }
-const uint8_t *c2b_fastq_seqs(const c2b_fastq *f) { return f ? f->seqs.data() : nullptr; }
+const uint8_t *c2b_fastq_seqs(const c2b_fastq *f) { return f ? f->seqs.get() : nullptr; }
 const int64_t *c2b_fastq_offsets(const c2b_fastq *f) { return f ? f->offsets.data() : nullptr; }
 const int32_t *c2b_fastq_counts(const c2b_fastq *f) { return f ? f->counts.data() : nullptr; }
 const int64_t *c2b_fastq_first_index(const c2b_fastq *f) { return f ? f->first_index.data() : nullptr; }

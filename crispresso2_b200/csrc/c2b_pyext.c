@@ -25,7 +25,15 @@ static PyObject *make_keys(PyObject *self, PyObject *args)
     out = PyList_New(n);
     if (!out) goto done;
     for (Py_ssize_t k = 0; k < n; k++) {
-        PyObject *s = PyUnicode_DecodeUTF8(b + o[k], (Py_ssize_t)(o[k + 1] - o[k]), "surrogateescape");
+        const Py_ssize_t len = (Py_ssize_t)(o[k + 1] - o[k]);
+        const unsigned char *p = (const unsigned char *)b + o[k];
+        unsigned char hi = 0;
+        for (Py_ssize_t x = 0; x < len; x++) hi |= p[x];
+        PyObject *s;
+        if (hi < 128) {                                    /* ASCII (every read that reaches the engine): no decoder */
+            s = PyUnicode_New(len, 127);
+            if (s) memcpy(PyUnicode_1BYTE_DATA(s), p, (size_t)len);
+        } else s = PyUnicode_DecodeUTF8((const char *)p, len, "surrogateescape");
         if (!s) { Py_CLEAR(out); goto done; }
         PyList_SET_ITEM(out, k, s);
     }
@@ -53,17 +61,29 @@ static PyObject *fill_cache(PyObject *self, PyObject *args)
     s_k = PyUnicode_InternFromString("_k");
     if (!s_k) goto out;
     {
+        /* `cls` is a dict subclass with a `_k` slot (lazy.LazyVariant): instances are made with dict's tp_new directly (no
+         * __init__ dispatch), `_k` is set through the slot's descriptor looked up once, and the new object is taken off the
+         * cyclic GC's lists -- it holds an int until somebody materialises it (dict re-tracks itself when a container value
+         * arrives), so a million of them must not turn every later collection into a 60 ms walk. */
+        PyTypeObject *tp = (PyTypeObject *)cls;
+        PyObject *descr = PyType_Check(cls) ? _PyType_Lookup(tp, s_k) : NULL;      /* borrowed */
+        descrsetfunc setk = descr ? Py_TYPE(descr)->tp_descr_set : NULL;
+        PyObject *empty = PyTuple_New(0);
+        const int fast = PyType_Check(cls) && PyType_IsSubtype(tp, &PyDict_Type) && setk != NULL && empty != NULL;
         const uint8_t *m = (const uint8_t *)sel.buf;
         for (Py_ssize_t k = 0; k < n; k++) {
             if (m[k] != (uint8_t)value) continue;
-            PyObject *o = PyObject_CallNoArgs(cls);
-            if (!o) goto out;
+            PyObject *o = fast ? PyDict_Type.tp_new(tp, empty, NULL) : PyObject_CallNoArgs(cls);
+            if (!o) { Py_XDECREF(empty); goto out; }
             PyObject *ik = PyLong_FromSsize_t(k);
-            int bad = !ik || PyObject_SetAttr(o, s_k, ik) < 0 || PyDict_SetItem(cache, PyList_GET_ITEM(keys, k), o) < 0;
+            int bad = !ik || (fast ? setk(descr, o, ik) < 0 : PyObject_SetAttr(o, s_k, ik) < 0);
+            if (!bad && fast && PyObject_GC_IsTracked(o)) PyObject_GC_UnTrack(o);
+            bad = bad || PyDict_SetItem(cache, PyList_GET_ITEM(keys, k), o) < 0;
             Py_XDECREF(ik); Py_DECREF(o);
-            if (bad) goto out;
+            if (bad) { Py_XDECREF(empty); goto out; }
             done++;
         }
+        Py_XDECREF(empty);
     }
     res = PyLong_FromSsize_t(done);
 out:
