@@ -149,6 +149,7 @@ struct KParams {
     // (and by the general kernel for the pairs it aligns), read by the CLASSIFY kernel and copied out as the compact output
     uint64_t *gops; uint32_t *gmeta; int32_t NW;            // NW = W / 32 words of 32 ops per slot
     int32_t *left; unsigned long long *left_n;              // ALIGN kernel: pairs left over for the general kernel, and their count
+    int32_t *left2; unsigned long long *left2_n;            // ALIGN kernel, narrow first tier: reads for the second-tier launch (nullptr: no narrow tier)
     const unsigned long long *n_dev;                        // general kernel over the left-over list: *n_dev reads (entries of pair_order)
     int32_t discard_slab;                                   // ALIGN kernel: drop the dead slab lines from L2 instead of writing them back
     unsigned long long *stats;             // cumulative path statistics (c2b_path_counts), indices 2..6
@@ -1243,12 +1244,15 @@ C2B_DEV Walked align_pair(const KParams &P, const RefDev &R, const uint32_t *pro
 // of every alignment that leaves the band -- the full-matrix traceback lies inside the band and the banded traceback
 // reproduces it cell for cell (ties included).  Otherwise the pair takes align_pair() over the full matrix.
 // Slab: entry (t, physical lane), one coalesced 256-byte row per step.
-template <bool STAGED>
+// RL = lanes per ring: 8 (four pairs per warp, band RG_NS = 72 slots) or 4 (eight pairs per warp, band 36 slots: the narrow
+// first tier of r02i -- twice the reads per pass for reads whose alignment stays within about [-17, +11] of the diagonal).
+template <bool STAGED, int RL = 8>
 C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *prof, const uint8_t *combo, const int J, const int nsteps,
                           uint2 *__restrict__ tbq, uint32_t *fin)
 {
-    const int lane = wp::lane(), r8 = lane & 7;
-    const int src = (lane & 24) | ((lane + 7) & 7);                      // ring predecessor
+    constexpr int NS = 9 * RL, B = 4 * RL;                               // slots per window, slots left of the diagonal
+    const int lane = wp::lane(), r8 = lane & (RL - 1);
+    const int src = (lane & ~(RL - 1)) | ((lane + RL - 1) & (RL - 1));   // ring predecessor
     const int lstar = R.lstar;
     const uint32_t combo_sa = wp::smem_addr(combo) - 1u;                 // combo[j-1] = [combo_sa + j]
     const uint32_t qstride = (uint32_t)R.Ipad * 4u;
@@ -1257,7 +1261,7 @@ C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *pro
     const uint32_t XB0 = R.pk_XB;
 
     uint32_t M[8], X[8], Y[8], cIe[8], g40, dI[8];                       // g4[k] = 4*gi[row] = cIe[k-1]; g40: the row above the lane's first
-    int L = r8, slot = 1 - 9 * r8 + RG_B;                                // slot of step t = 1
+    int L = r8, slot = 1 - 9 * r8 + B;                                // slot of step t = 1
     uint32_t prof_sa = 0; const uint32_t *prof0 = prof;
     auto enter = [&](int Lv) {                                           // constants and left-of-band state of virtual lane Lv
         const int row0 = 8 * (Lv <= lstar ? Lv : lstar);                 // past the last row block: inert, any valid rows
@@ -1265,7 +1269,7 @@ C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *pro
         const uint4 a = wp::ldg4u(pc), b = wp::ldg4u(pc + 1);
         cIe[0] = a.x; cIe[1] = a.y; cIe[2] = a.z; cIe[3] = a.w; cIe[4] = b.x; cIe[5] = b.y; cIe[6] = b.z; cIe[7] = b.w;
         g40 = R.g42[row0];
-        const uint32_t y0 = (8 * Lv - RG_B <= 0) ? R.pk_YB : (PK_SENT | PK_T1);   // window starts at column 0: the border column
+        const uint32_t y0 = (8 * Lv - B <= 0) ? R.pk_YB : (PK_SENT | PK_T1);   // window starts at column 0: the border column
         const uint32_t d4p = (uint32_t)((4 * (P.go - P.ge)) & 0xffff) * 0x00010001u;
         const int klast = Iref - 8 * Lv - 1;                              // row I is this lane's row klast (if 0 <= klast < 8)
 #pragma unroll
@@ -1297,8 +1301,8 @@ C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *pro
                 s[0] = sa.x; s[1] = sa.y; s[2] = sa.z; s[3] = sa.w; s[4] = sb.x; s[5] = sb.y; s[6] = sb.z; s[7] = sb.w;
             }
             const uint32_t cm = (j == J) ? 0u : 0xffffffffu;             // free opening in the last column
-            // the row above leaves the band RG_NS-8 slots into the window (its diagonal neighbour one slot later)
-            const bool lateU = slot >= RG_NS - 8, lateP = slot > RG_NS - 8;
+            // the row above leaves the band NS-8 slots into the window (its diagonal neighbour one slot later)
+            const bool lateU = slot >= NS - 8, lateP = slot > NS - 8;
             uint32_t dM = lateP ? PK_SENT : pM, dX = lateP ? (PK_SENT | PK_T2) : pX, dY = lateP ? (PK_SENT | PK_T1) : pY;
             uint32_t upM = lateU ? PK_SENT : uM, upY = lateU ? (PK_SENT | PK_T1) : uY, wT = 0, wIJ = 0;
 #pragma unroll
@@ -1325,7 +1329,7 @@ C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *pro
         }
         else if (pend) { tbp[t - 1] = make_uint2(hT, hIJ); pend = false; }     // the active stretch ended on an even step
         pM = uM; pX = uX; pY = uY;                                       // raw: a lane entering its next window needs the uncapped edge
-        if (++slot == RG_NS) { L += 8; slot = 0; enter(L); }
+        if (++slot == NS) { L += RL; slot = 0; enter(L); }
     }
     if (pend) tbp[nsteps] = make_uint2(hT, hIJ);
 }
@@ -1335,17 +1339,17 @@ C2B_DEVNOINL void dp_ring(const KParams &P, const RefDev &R, const uint32_t *pro
 // ones) or nv >= RG_DLO+1 reference-only columns (and nh = nv + (J-I)); a gap column scores at most gap_extend (+ the
 // largest incentive for read-only columns; reference-only runs collect each row's incentive at most once, gsum in
 // total), a diagonal column at most smax.  The host proves the bound decreasing in the free count (RefDev::rg_ok).
-C2B_DEV int ring_bound(const KParams &P, const RefDev &R, int J)
+C2B_DEV int ring_bound(const KParams &P, const RefDev &R, int J, const int DLO = RG_DLO, const int DHI = RG_DHI)
 {
     const int I = R.I, D = J - I, ge = P.ge, smax = R.rg_smax, gmax = R.rg_gmax;
     int U = -(1 << 28);
     {
-        int nh = RG_DHI + 1; if (nh < D) nh = D;
+        int nh = DHI + 1; if (nh < D) nh = D;
         const int nv = nh - D;
         if (nh <= J && nv <= I) { const int u = smax * (J - nh) + nh * (ge + gmax) + nv * ge + R.rg_gsum; if (u > U) U = u; }
     }
     {
-        int nv = RG_DLO + 1; if (nv < -D) nv = -D;
+        int nv = DLO + 1; if (nv < -D) nv = -D;
         const int nh = nv + D;
         if (nv <= I && nh <= J && nh >= 0) { const int u = smax * (I - nv) + nh * (ge + gmax) + nv * ge + R.rg_gsum; if (u > U) U = u; }
     }

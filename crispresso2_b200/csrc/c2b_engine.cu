@@ -186,8 +186,32 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_A_MIN_CTAS) c2b_align_
     const int nw = blockDim.x >> 5;
     const int warp_slot = blockIdx.x * nw + (threadIdx.x >> 5);
     const uint32_t *staged_prof = stage_profile(P, smem_raw + (((size_t)nw * sizeof(ASmem) + 127) & ~(size_t)127));
-    const unsigned total = (unsigned)((P.n_reads + 7) / 8);
+    const int64_t nrd = nreads(P);
     const unsigned ahead = gridDim.x * nw;
+    if (P.left2) {
+        // narrow first tier: work in units of sixteen reads; units it does not take run as two ordinary groups of eight
+        const unsigned total = (unsigned)((nrd + 15) / 16);
+        for (;;) {
+            unsigned w = 0;
+            if ((threadIdx.x & 31) == 0) w = (unsigned)atomicAdd(P.work_counter, 1ull);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            if (w >= total) break;
+            if (w + ahead < total) {                            // the unit this warp is likely to get next: bytes towards L2
+                const int64_t g = (int64_t)w + ahead;
+                const int64_t last = 16 * g + 16 < nrd ? 16 * g + 16 : nrd;
+                const int64_t a = P.offsets[16 * g] + (int64_t)(threadIdx.x & 31) * 128;
+                if (a < P.offsets[last]) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.reads + a));
+            }
+            if (!align_narrow16(P, *S, staged_prof, (int64_t)w, warp_slot)) {
+                align_group(P, *S, staged_prof, 2 * (int64_t)w, warp_slot);
+                __syncwarp();
+                if (8 * (2 * (int64_t)w + 1) < nrd) align_group(P, *S, staged_prof, 2 * (int64_t)w + 1, warp_slot);
+            }
+            __syncwarp();
+        }
+        return;
+    }
+    const unsigned total = (unsigned)((nrd + 7) / 8);
     for (;;) {
         unsigned w = 0;
         if ((threadIdx.x & 31) == 0) w = (unsigned)atomicAdd(P.work_counter, 1ull);
@@ -195,7 +219,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_A_MIN_CTAS) c2b_align_
         if (w >= total) break;
         if (w + ahead < total && !P.pair_order) {           // the group this warp is likely to get next: bytes towards L2
             const int64_t g = (int64_t)w + ahead;
-            const int64_t last = 8 * g + 8 < P.n_reads ? 8 * g + 8 : P.n_reads;
+            const int64_t last = 8 * g + 8 < nrd ? 8 * g + 8 : nrd;
             const int64_t a = P.offsets[8 * g] + (int64_t)(threadIdx.x & 31) * 128;
             if (a < P.offsets[last]) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.reads + a));
         }
@@ -260,14 +284,14 @@ struct c2b_engine {
     unsigned long long *d_counts = nullptr; size_t counts_n = 0;
     // scratch
     DevBuf tb, tbb, tbq, bnd, ops, rgo, work, lut;
-    DevBuf gops, gmeta, left;          // device-pointer API: op streams / meta words / left-over list of the last launch
+    DevBuf gops, gmeta, left, left2;   // device-pointer API: op streams / meta words / left-over list of the last launch
     int n_warps = 0, grid = 0, wpc = 8, stage_cap = 0;
     int grid_a = 0, grid_b = 0, stage_cap_a = 0;       // ALIGN / CLASSIFY kernels
     int split_ok = 0, split_all = 0;                   // configuration admits the two-kernel form (some / all references)
     int numa_node = -1;                                // NUMA node of the device (-1: unknown / single node)
     int scratch_TS = 0;
     // staging for the host-pointer API: two buffer sets, copy-in / compute / copy-out streams
-    struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed, maxlen, ord, gops, gmeta, left; int32_t *h_ord = nullptr; size_t h_ord_cap = 0; int64_t *h_off = nullptr; size_t h_off_cap = 0;
+    struct Stage { DevBuf reads, off, cnt, qw, rid, recs, alns, str, ed, maxlen, ord, gops, gmeta, left, left2; int32_t *h_ord = nullptr; size_t h_ord_cap = 0; int64_t *h_off = nullptr; size_t h_off_cap = 0;
                    // pinned bounce buffers for callers whose arrays are pageable (numpy): copies to / from them run on host
                    // threads while the other set's kernels and DMA are in flight
                    uint8_t *h_in = nullptr, *h_out = nullptr; size_t h_in_cap = 0, h_out_cap = 0;
@@ -432,10 +456,10 @@ int c2b_create(int device, c2b_engine **out)
 void c2b_destroy(c2b_engine *e)
 {
     if (!e) return;
-    DevBuf *bufs[] = {&e->tb, &e->tbb, &e->tbq, &e->bnd, &e->ops, &e->rgo, &e->work, &e->lut, &e->gops, &e->gmeta, &e->left};
+    DevBuf *bufs[] = {&e->tb, &e->tbb, &e->tbq, &e->bnd, &e->ops, &e->rgo, &e->work, &e->lut, &e->gops, &e->gmeta, &e->left, &e->left2};
     for (DevBuf *b : bufs) if (b->p) rt_free(b->p);
     for (auto &st : e->stage) {
-        DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed, &st.maxlen, &st.ord, &st.gops, &st.gmeta, &st.left};
+        DevBuf *sb[] = {&st.reads, &st.off, &st.cnt, &st.qw, &st.rid, &st.recs, &st.alns, &st.str, &st.ed, &st.maxlen, &st.ord, &st.gops, &st.gmeta, &st.left, &st.left2};
         if (st.h_ord) rt_host_free(st.h_ord);
         for (DevBuf *b : sb) if (b->p) rt_free(b->p);
         if (st.h_off) rt_host_free(st.h_off);
@@ -730,7 +754,7 @@ static int ensure_scratch(c2b_engine *e, int maxJ)
 static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_reads, const int64_t *d_offsets, int64_t n_reads,
                      int32_t max_read_len, const int32_t *d_count, const int32_t *d_qweight,
                      const int32_t *d_ref_id, c2b_read_rec *d_recs, c2b_aln_rec *d_alns,
-                     uint8_t *d_strings, c2b_edit *d_edits, uint64_t *d_gops, uint32_t *d_gmeta, int32_t *d_left)
+                     uint8_t *d_strings, c2b_edit *d_edits, uint64_t *d_gops, uint32_t *d_gmeta, int32_t *d_left, int32_t *d_left2 = nullptr)
 {
     if (!e || !e->configured) return fail(e, C2B_E_STATE, "c2b_align_batch: engine not configured");
     if (n_reads < 0 || !d_recs || !d_alns || (n_reads && (!d_reads || !d_offsets))) return fail(e, C2B_E_ARG, "c2b_align_batch: bad argument");
@@ -786,7 +810,7 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
         if (e->n_refs > 1 && !d_ref_id && getenv("C2B_NO_MULTI_PHASE")) P.phase_sync = 0;
     }
     const bool one = (e->n_refs == 1 || d_ref_id != nullptr) && !getenv("C2B_GENERIC_KERNEL");      // one candidate reference per read
-    RTCHK(rt_zero(wk, 32, cs));                           // this set's counters and widest alignment
+    RTCHK(rt_zero(wk, 64, cs));                           // this set's counters and widest alignment ([4], [5]: second-tier ALIGN launch)
     if (d_gmeta) RTCHK(rt_zero(d_gmeta, (size_t)n_reads * P.out_refs * 4, cs));
 #ifndef C2B_EMU
     const RefDev &r0 = e->refdev[0];
@@ -799,7 +823,18 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
         A.discard_slab = getenv("C2B_NO_DISCARD") ? 0 : 1;
         if (can_stage && tile <= (size_t)e->stage_cap_a) { A.stage_bytes = (int32_t)tile; A.stage_src = r0.prof2; }
         const size_t smem_a = sizeof(ASmem) * e->wpc + 128 + (size_t)A.stage_bytes;
+        // narrow first tier (align_narrow16): reads in their given order (no pairing order = the caller's reads are of one
+        // length, or unsorted -- then hardly any unit of sixteen qualifies), one candidate reference per read
+        const bool narrow = d_left2 && !P.pair_order && (e->n_refs == 1 || d_ref_id != nullptr) && !getenv("C2B_NO_NARROW");
+        if (narrow) { A.left2 = d_left2; A.left2_n = wk + 5; }
         c2b_align_kernel<<<e->grid_a, e->wpc * 32, smem_a, cs>>>(A);
+        if (narrow) {                                         // second tier: what the narrow band did not settle, eight reads per group
+            KParams A2 = A;
+            A2.left2 = nullptr; A2.left2_n = nullptr;
+            A2.pair_order = d_left2; A2.n_dev = wk + 5; A2.work_counter = wk + 4;
+            c2b_align_kernel<<<e->grid_a, e->wpc * 32, smem_a, cs>>>(A2);
+            e->launches++;
+        }
         if (one) c2b_classify_kernel<true><<<e->grid_b, B_WARPS_PER_CTA * 32, 0, cs>>>(P);
         else c2b_classify_kernel<false><<<e->grid_b, B_WARPS_PER_CTA * 32, 0, cs>>>(P);
         // the general kernel over ALIGN's left-over pairs (free-running warps, no ring-banded attempt)
@@ -821,6 +856,22 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
         if (split) {
             KParams A = P;
             A.left = d_left; A.left_n = wk + 3;
+            const bool narrow = d_left2 && !P.pair_order && (e->n_refs == 1 || d_ref_id != nullptr) && !getenv("C2B_NO_NARROW");
+            if (narrow) {
+                A.left2 = d_left2; A.left2_n = wk + 5;
+                for (int64_t w = 0; 16 * w < n_reads; w++)
+                    emu::run_warp([&]() {
+                        if (!align_narrow16(A, AS, nullptr, w, 0)) {
+                            align_group(A, AS, nullptr, 2 * w, 0);
+                            wp::sync();
+                            if (8 * (2 * w + 1) < n_reads) align_group(A, AS, nullptr, 2 * w + 1, 0);
+                        }
+                    });
+                KParams A2 = A;
+                A2.left2 = nullptr; A2.left2_n = nullptr; A2.pair_order = d_left2; A2.n_dev = wk + 5; A2.work_counter = wk + 4;
+                const int64_t n2 = (int64_t)*A2.n_dev;
+                for (int64_t w = 0; 8 * w < n2; w++) emu::run_warp([&]() { align_group(A2, AS, nullptr, w, 0); });
+            } else
             for (int64_t w = 0; 8 * w < n_reads; w++) emu::run_warp([&]() { align_group(A, AS, nullptr, w, 0); });
             static BSmem BS;
             const int64_t total_bytes = d_offsets[n_reads];
@@ -856,12 +907,13 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
 }
 
 // op-stream buffers of the device-pointer API (engine-owned, sized for the batch)
-static int ensure_ops(c2b_engine *e, DevBuf &gops, DevBuf &gmeta, DevBuf &left, int64_t n_reads, int nr, int W)
+static int ensure_ops(c2b_engine *e, DevBuf &gops, DevBuf &gmeta, DevBuf &left, DevBuf &left2, int64_t n_reads, int nr, int W)
 {
     int rc;
     if ((rc = ensure(e, gops, (size_t)n_reads * nr * (W / 32) * 8))) return rc;
     if ((rc = ensure(e, gmeta, (size_t)n_reads * nr * 4))) return rc;
     if ((rc = ensure(e, left, (size_t)(n_reads + 8) * 4))) return rc;
+    if ((rc = ensure(e, left2, (size_t)(n_reads + 16) * 4))) return rc;
     return C2B_OK;
 }
 
@@ -876,10 +928,10 @@ int c2b_align_batch_device(c2b_engine *e, const uint8_t *d_reads, const int64_t 
 #endif
     if (max_read_len < 1) max_read_len = 1;
     const int W = (e->max_I + max_read_len + 31) & ~31, nr = d_ref_id ? 1 : e->n_refs;
-    int rc = ensure_ops(e, e->gops, e->gmeta, e->left, n_reads, nr, W);
+    int rc = ensure_ops(e, e->gops, e->gmeta, e->left, e->left2, n_reads, nr, W);
     if (rc) return rc;
     return launch_on(e, e->stream, 0, d_reads, d_offsets, n_reads, max_read_len, d_count, d_qweight, d_ref_id, d_recs,
-                     d_alns, d_strings, d_edits, (uint64_t *)e->gops.p, (uint32_t *)e->gmeta.p, (int32_t *)e->left.p);
+                     d_alns, d_strings, d_edits, (uint64_t *)e->gops.p, (uint32_t *)e->gmeta.p, (int32_t *)e->left.p, (int32_t *)e->left2.p);
 }
 
 int c2b_ops_device(c2b_engine *e, void **d_ops, void **d_meta)
@@ -1112,7 +1164,7 @@ static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *
         if (count && (rc = ensure(e, st.cnt, (size_t)n * 4))) return rc;
         if (qweight && (rc = ensure(e, st.qw, (size_t)n * 4))) return rc;
         if (ref_id && (rc = ensure(e, st.rid, (size_t)n * 4))) return rc;
-        if ((rc = ensure_ops(e, st.gops, st.gmeta, st.left, n, nr, W))) return rc;
+        if ((rc = ensure_ops(e, st.gops, st.gmeta, st.left, st.left2, n, nr, W))) return rc;
         if (st.h_off_cap < (size_t)(n + 1)) {
             if (st.h_off) rt_host_free(st.h_off);
             st.h_off = (int64_t *)rt_host_alloc((size_t)(n + 1) * 8); st.h_off_cap = st.h_off ? (size_t)(n + 1) : 0;
@@ -1166,7 +1218,7 @@ static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *
                        count ? (const int32_t *)st.cnt.p : nullptr, qweight ? (const int32_t *)st.qw.p : nullptr,
                        ref_id ? (const int32_t *)st.rid.p : nullptr, (c2b_read_rec *)st.recs.p,
                        (c2b_aln_rec *)st.alns.p, strings ? (uint8_t *)st.str.p : nullptr,
-                       cap ? (c2b_edit *)st.ed.p : nullptr, (uint64_t *)st.gops.p, (uint32_t *)st.gmeta.p, (int32_t *)st.left.p);
+                       cap ? (c2b_edit *)st.ed.p : nullptr, (uint64_t *)st.gops.p, (uint32_t *)st.gmeta.p, (int32_t *)st.left.p, (int32_t *)st.left2.p);
         e->pair_order = nullptr;
         if (rc) return rc;
         // keep this batch's "widest alignment" before the next launch sequence resets it

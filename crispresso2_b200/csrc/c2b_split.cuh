@@ -24,7 +24,7 @@ C2B_DEV uint32_t gmeta_pack(int n, int strand, uint32_t state) { return (uint32_
 
 struct ASmem {                                         // ALIGN kernel, per warp
     uint8_t fw[2][RG_COMBO], rc[2][RG_COMBO];          // the two reads of the pair being prepared, as alphabet codes
-    uint8_t combo[4][RG_COMBO];                        // base-pair codes of the four pairs
+    uint8_t combo[8][RG_COMBO];                        // base-pair codes of the pairs (four; eight in the narrow first tier)
     uint32_t fin[96];                                  // M, X, Y of cell (I, J) per lane
 };
 
@@ -67,9 +67,12 @@ C2B_DEV bool load_codes_a(const KParams &P, int64_t off, int J, uint8_t *fw, uin
 // slab gather per run of equal ops -- and four of them in sequence cost as much wall time as the DP itself (r02b: the ALIGN
 // kernel's issue slots were idle half the time).  Here every iteration issues the gathers of all four pairs before it
 // consumes any, so the four latencies overlap; the per-pair logic is walk_batch<true>'s for a ring slab, verbatim.
+// RL / q0: ring size of the DP that filled the slab (8 or 4 lanes) and the first of the four pairs walked by this call.
+template <int RL = 8>
 C2B_DEV void walk_ring4(const KParams &P, const RefDev &R, const int *Jq, const uint2 *__restrict__ tb2, const int *s0, uint32_t mask,
-                        Walked *out)
+                        Walked *out, const int q0 = 0)
 {
+    constexpr int NS = 9 * RL, B = 4 * RL;
     const int lane = wp::lane();
     const int hl = lane & 15, hb = lane & 16;
     const int TS = P.TS;
@@ -99,10 +102,10 @@ C2B_DEV void walk_ring4(const KParams &P, const RefDev &R, const int *Jq, const 
             w2[q] = make_uint2(0u, 0u); sh[q] = 0;
             if (valid[q]) {
                 const int r = ci - 1, l = (r >> 3) & 31;
-                const int slot = cj + l - 9 * l + RG_B;
-                inband[q] = (unsigned)slot < (unsigned)RG_NS;
+                const int slot = cj + l - 9 * l + B;
+                inband[q] = (unsigned)slot < (unsigned)NS;
                 sh[q] = 2 * (7 - (r & 7));
-                if (inband[q]) w2[q] = wp::ldcg2(tb2 + (int64_t)(8 * q + (l & 7)) * TS + cj + l);
+                if (inband[q]) w2[q] = wp::ldcg2(tb2 + (int64_t)(RL * (q0 + q) + (l & (RL - 1))) * TS + cj + l);
             }
         }
         if (!wp::ballot(anyact)) break;
@@ -198,7 +201,7 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
     // A group is taken here when its four pairs admit the packed 16-bit DP against every candidate reference (equal lengths
     // within a pair, lengths inside the proven 16-bit range); per reference the ring-banded DP is tried when the band can hold
     // the alignment (read length within RG_MAXD of the amplicon's, monotone bound), the full matrix otherwise.
-    bool quad = (P.tbq != nullptr || P.tb != nullptr) && 2 * first + 7 < P.n_reads && (!multi || P.n_refs <= RG_MAX_REFS);
+    bool quad = (P.tbq != nullptr || P.tb != nullptr) && 2 * first + 7 < nreads(P) && (!multi || P.n_refs <= RG_MAX_REFS);
     int r0 = 0;
     uint32_t ringmask = 0;                                   // bit k - k0: the ring-banded DP is admissible for reference k
     if (quad) {
@@ -222,11 +225,11 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
     if (!quad) {
 #pragma unroll 1
         for (int q = 0; q < 4; q++) {
-            if (2 * (first + q) >= P.n_reads) break;
+            if (2 * (first + q) >= nreads(P)) break;
             const int64_t rdA = read_at(P, 2 * (first + q));
             // the list mixes pairs and single reads, and the general kernel takes its entries two at a time: the odd last read
             // goes on it ONCE (an (rdA, rdA) entry could be split over two work items and be counted twice)
-            if (2 * (first + q) + 1 < P.n_reads) leftover_pair(P, rdA, read_at(P, 2 * (first + q) + 1));
+            if (2 * (first + q) + 1 < nreads(P)) leftover_pair(P, rdA, read_at(P, 2 * (first + q) + 1));
             else leftover_one(P, rdA);
         }
         return;
@@ -420,6 +423,121 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
         if (gq == 0) leftover_pair(P, rdA, rdB);
         else if (gq != 3u) leftover_one(P, gq == 1u ? rdB : rdA);
     }
+}
+
+// ---------------------------------------------------------------------------------------- ALIGN, narrow first tier (r02i)
+// Sixteen reads (eight pairs) per warp in ONE ring-banded pass: rings of four lanes, band of 36 slots (cells with column - row
+// in about [-17, +11]).  Same DP, same exactness argument with the narrower band's bound (ring_bound(.., 17, 11)): a read
+// whose banded score beats it -- every read within ~10 substitutions of the amplicon, deletions up to ~8 bp, insertions up to
+// ~9 bp: 84 % of the bench reads -- has its exact full-matrix traceback at half the cost per read.  Every other read goes,
+// alone, on the tier-2 list (P.left2), which a second launch of this kernel works through in groups of eight with the
+// 72-slot band, the full matrix and the both-strand alignment of align_group.
+// Taken only for sixteen consecutive reads of one length and one single candidate reference that admits the ring; returns
+// false otherwise (the caller runs align_group on the two groups of eight).
+C2B_DEV bool align_narrow16(const KParams &P, ASmem &S, const uint32_t *staged_prof, int64_t w16, int warp_slot)
+{
+    constexpr int RL = 4, DLO = 4 * RL + 1, DHI = 9 * RL - 4 * RL - 9;
+    const int lane = wp::lane(), g = lane >> 2;
+    const int64_t first = 16 * w16;                         // first read
+    if (!P.left2 || P.tbq == nullptr || first + 15 >= nreads(P) || (P.ref_id == nullptr && P.n_refs > 1)) return false;
+    int r0, J0;
+    {
+        const int64_t rd = read_at(P, first + (lane & 15));
+        const int Jx = (int)(P.offsets[rd + 1] - P.offsets[rd]);
+        const int rx = P.ref_id ? P.ref_id[rd] : 0;
+        r0 = wp::shfl(rx, 0); J0 = wp::shfl(Jx, 0);
+        const RefDev &R = refdev(P, r0);
+        const bool ok = rx == r0 && Jx == J0 && Jx >= 1 && Jx <= RG_COMBO && Jx + 32 <= P.TS && R.rg_ok && !R.coding && Jx <= R.pk_maxJ &&
+                        R.I + Jx <= PK_MAX_ALN && Jx - R.I <= RG_MAXD && R.I - Jx <= RG_MAXD;
+        if (wp::ballot(ok) != 0xffffffffu) return false;
+    }
+    const RefDev &R = refdev(P, r0);
+    const int J = J0;
+    uint2 *tbq = reinterpret_cast<uint2 *>(P.tbq + (int64_t)warp_slot * P.TS * 64);
+    uint32_t modes = 0, use2 = 0;                            // use2: reads (bit 2q + h) whose ring result counts
+#pragma unroll 1
+    for (int q = 0; q < 8; q++) {
+        const int64_t rdA = read_at(P, first + 2 * q), rdB = read_at(P, first + 2 * q + 1);
+        bool badA = load_codes_a(P, P.offsets[rdA], J, S.fw[0], S.rc[0]);
+        bool badB = load_codes_a(P, P.offsets[rdB], J, S.fw[1], S.rc[1]);
+        wp::sync();
+        int m = 0;
+#pragma unroll 1
+        for (int x = 0; x < 2; x++) m |= strand_mode(P, R, S.fw[x], J) << (2 * x);
+        const int mA = m & 3, mB = m >> 2;
+        // a read with a symbol outside the alphabet or in need of both strands rides along on its forward strand; tier 2 settles it
+        const uint8_t *cA = mA == 1 ? S.rc[0] : S.fw[0], *cB = mB == 1 ? S.rc[1] : S.fw[1];
+        for (int p = lane; p < J; p += 32) S.combo[q][p] = (uint8_t)(cA[p] * P.nq + cB[p]);
+        modes |= (uint32_t)m << (4 * q);
+        if (!badA && mA != 2) use2 |= 1u << (2 * q);
+        if (!badB && mB != 2) use2 |= 2u << (2 * q);
+        wp::sync();
+    }
+    const bool staged = (r0 == 0 && staged_prof != nullptr);
+    if (staged) dp_ring<true, RL>(P, R, staged_prof, S.combo[g], J, J + R.lstar, tbq, S.fin);
+    else dp_ring<false, RL>(P, R, R.prof2, S.combo[g], J, J + R.lstar, tbq, S.fin);
+    wp::sync();
+    const int fl = 3 * ((lane & ~(RL - 1)) | (R.lstar & (RL - 1)));
+    const uint32_t cM = S.fin[fl], cX = S.fin[fl + 1], cY = S.fin[fl + 2];
+    wp::sync();
+    const uint32_t z = wp::max3_2(cM, cY, cX);
+    const uint32_t s2 = z & PK_TM;
+    const int thr = ring_bound(P, R, J, DLO, DHI) + 512 - P.ge * (R.I + J);
+    const uint32_t bA = wp::ballot((int)((z & 0xffffu) >> 2) > thr), bB = wp::ballot((int)(z >> 18) > thr);
+    uint32_t pass2 = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) pass2 |= (((bA >> (RL * q)) & 1u) | (((bB >> (RL * q)) & 1u) << 1)) << (2 * q);
+    pass2 &= use2;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {                   // tracebacks: pairs 0-3, then 4-7, four interleaved at a time
+        const int q0 = 4 * half;
+        int Jq[4], s0[4];
+        Walked wk4[4];
+        uint32_t walkmask = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t sq = wp::shflu(s2, RL * (q0 + q));
+            Jq[q] = J;
+            s0[q] = (lane & 16) ? (int)(sq >> 16) : (int)(sq & 3u);
+            if ((pass2 >> (2 * (q0 + q))) & 3u) walkmask |= 1u << q;
+        }
+        if (!walkmask) continue;
+        walk_ring4<RL>(P, R, Jq, tbq, s0, walkmask, wk4, q0);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (!((walkmask >> q) & 1u)) continue;
+            const int qq = q0 + q;
+            const Walked &wk = wk4[q];
+            const uint32_t eb = wp::ballot(wk.err != 0);
+            if (eb & 0xffffu) pass2 &= ~(1u << (2 * qq));
+            if (eb >> 16) pass2 &= ~(2u << (2 * qq));
+            const int h = lane >> 4, hl = lane & 15;
+            if (!((pass2 >> (2 * qq + h)) & 1u)) continue;
+            const int64_t rd = read_at(P, first + 2 * qq + h);
+            const int64_t slot = oslot(P, rd, r0);
+            if (hl < P.NW) P.gops[slot * P.NW + hl] = wk.ops;
+            if (hl == 0) P.gmeta[slot] = gmeta_pack(wk.n, (int)((modes >> (4 * qq + 2 * h)) & 3u) == 1, GM_ALIGNED);
+        }
+    }
+#ifndef C2B_EMU
+    if (P.discard_slab) {                                    // the slab is dead now: drop its lines from L2
+        const char *base = reinterpret_cast<const char *>(tbq);
+        const int64_t bytes = (int64_t)P.TS * 64 * 4;
+        for (int64_t o = (int64_t)lane * 128; o < bytes; o += 32 * 128)
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + o) : "memory");
+    }
+#endif
+    // everything the narrow band did not settle: one entry each on the tier-2 list
+    const uint32_t rest = 0xffffu & ~pass2;
+    if (lane < 16 && ((rest >> lane) & 1u)) {
+        const unsigned long long pos = wp::fetch_add(P.left2_n, 1ull);
+        P.left2[pos] = (int32_t)read_at(P, first + lane);
+    }
+    if (lane == 0) {
+        wp::addg(P.stats + 7, wp::popc(pass2));
+        wp::addg(P.stats + 5, wp::popc(pass2));
+    }
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------- CLASSIFY

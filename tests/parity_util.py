@@ -326,6 +326,69 @@ def check_legacy(engine, n=120, seed=17):
     check_against_oracle(engine, {"Reference": ref, "HDR": ref2}, ["Reference", "HDR"], P, reads[:60] + r2 + reads[-10:], O.make_matrix())
 
 
+def check_narrow_equals_wide(engine, n=640, I=250, seed=59, oracle_subset=0):
+    """Narrow first tier of the ALIGN kernel (sixteen reads per warp, band of 36 slots, result kept iff the score beats that
+    band's bound; everything else re-queued for the 72-slot ring / the full matrix) against the same batch with the tier
+    switched off (C2B_NO_NARROW): identical records, op streams, strings, edit lists and count block.  Reads straddle the narrow
+    bound: deletions of 1..24 bp, insertions of 1..16 bp, 0..40 substitutions, reverse-complemented and both-strand reads."""
+    import os
+    from crispresso2_b200 import synth
+    from crispresso2_b200.engine import pack_reads
+    rng = np.random.default_rng(seed)
+    amp = synth.random_amplicon(rng, I)
+    ref = synth.amplicon_setup(amp, guide_start=max(1, I // 2 - 10))
+    acgt = list("ACGT")
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    reads = []
+    for k in range(n):
+        kind = k % 8
+        if kind == 0:
+            d = int(rng.integers(1, 25)); a = int(rng.integers(20, I - d - 20))
+            s = amp[:a] + amp[a + d:] + "".join(rng.choice(acgt, d))
+        elif kind == 1:
+            d = int(rng.integers(1, 17)); a = int(rng.integers(20, I - 20))
+            s = amp[:a] + "".join(rng.choice(acgt, d)) + amp[a:]
+        elif kind == 2:
+            s = list(amp)
+            for p in rng.choice(I, int(rng.integers(0, 41)), replace=False):
+                s[p] = acgt[int(rng.integers(0, 4))]
+            s = "".join(s)
+        elif kind == 3:
+            s = "".join(comp[c] for c in reversed(amp))                     # reverse complement
+        elif kind == 4:
+            s = amp[:40] + "".join(rng.choice(acgt, I - 80)) + amp[-40:]         # few seeds left: both strands tried
+        else:
+            s = synth.synth_reads(rng, amp, 1, I, sub_rate=0.01, cut=ref["cut_point"])[0].tobytes().decode()
+        reads.append(s[:I].ljust(I, "A"))
+    buf, off = pack_reads(reads)
+    out = []
+    for off_switch in (None, "1"):
+        if off_switch:
+            os.environ["C2B_NO_NARROW"] = off_switch
+        try:
+            engine.configure({"Reference": ref}, ["Reference"], O.make_matrix(), -20, -2, 5, 2, 0, "ACGTN", 48)
+            engine.counts_reset()
+            res = engine.align_packed(buf, off)
+            cres = engine.align_packed(buf, off, compact=True, count=np.zeros(n, dtype=np.int32), qweight=np.zeros(n, dtype=np.int32))
+            out.append((res, engine.counts_raw(), cres))
+        finally:
+            os.environ.pop("C2B_NO_NARROW", None)
+    (a, ca, xa), (b, cb, xb) = out
+    assert (a.recs == b.recs).all() and (a.alns == b.alns).all() and (ca == cb).all()
+    assert ((xa.meta & 0xffffff) == (xb.meta & 0xffffff)).all() and (((xa.meta >> 24) != 0) == ((xb.meta >> 24) != 0)).all()   # columns, strand; the state byte names the kernel that aligned
+    W = a.W
+    cols = np.arange(W)[None, :] >= (W - a.alns[:, 0]["aln_len"].astype(np.int64))[:, None]
+    assert ((a.strings[:, 0] == b.strings[:, 0]) | ~cols[:, None, :]).all()
+    (ea, fa), (eb, fb) = edits_canonical(a), edits_canonical(b)
+    assert (fa == fb).all() and (ea[fa] == eb[fb]).all()
+    nw = (xa.meta.reshape(-1) & 0xffff).astype(np.int64)                      # op words in use per alignment
+    for k in range(n):
+        used = (int(nw[k]) + 31) // 32
+        assert (xa.ops.reshape(n, -1)[k, :used] == xb.ops.reshape(n, -1)[k, :used]).all(), k
+    if oracle_subset:
+        check_against_oracle(engine, {"Reference": ref}, ["Reference"], O.Params(), reads[:oracle_subset], O.make_matrix())
+
+
 def check_long_pairs(engine, n=40, seed=91):
     """Pairs whose alignment can exceed 512 columns (I + J > 512): since r02g the ALIGN kernel takes them on the packed 16-bit
     path with two op-stream words per lane and half (up to 1024 columns; amplicons of two row blocks included); before, they fell

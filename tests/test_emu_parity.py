@@ -139,6 +139,11 @@ def test_legacy_insertion_quantification(emu):
     PU.check_legacy(emu)
 
 
+def test_narrow_first_tier_equals_the_wide_ring(emu):
+    PU.check_narrow_equals_wide(emu, n=160, oracle_subset=64)
+    PU.check_narrow_equals_wide(emu, n=96, I=131, seed=7)
+
+
 def test_pooled_ref_id(emu):
     PU.check_pooled(emu, n_amplicons=4, reads_per=24)
     PU.check_pooled(emu, n_amplicons=40, reads_per=3, seed=5)          # more references than C2B_MAX_REFS: Pooled only

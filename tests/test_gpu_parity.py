@@ -243,6 +243,11 @@ def test_legacy_insertion_quantification(eng):
     PU.check_legacy(eng, n=3000)
 
 
+@pytest.mark.parametrize("I", [250, 256, 131])
+def test_narrow_first_tier_equals_the_wide_ring(eng, I):
+    PU.check_narrow_equals_wide(eng, n=32000, I=I, seed=50 + I, oracle_subset=480)
+
+
 def test_pooled_ref_id(eng):
     """BASELINE configs[3] shape: many amplicons, each read aligned to its own one (ref_id), one launch."""
     PU.check_pooled(eng, n_amplicons=24, reads_per=120, amp_len=(180, 280))
