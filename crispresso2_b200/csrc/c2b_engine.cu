@@ -1068,7 +1068,10 @@ static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *
     const int cap = edits ? e->prm.edit_cap : 0;
     const int nr = ref_id ? 1 : e->n_refs;                 // output slots per read (compact when ref_id is given)
     const int64_t per_read = (int64_t)nr * (2 * (int64_t)W * (strings ? 1 : 0) + NW * 8 + (int64_t)cap * 8 + 36) + 16 + maxJ + 28;
-    int64_t chunk = std::max<int64_t>(4096, std::min<int64_t>((int64_t)(768ll << 20) / per_read, 1 << 17));
+    // 256 Ki reads per chunk: every chunk's launches end in a tail of partly idle SMs (persistent kernels, a second-tier launch of
+    // one or two waves), so fewer, larger chunks win until the exposed first copy-in / last copy-out take over (measured r02i:
+    // 128 Ki 52.0, 256 Ki 56.8, 512 Ki 52.4 M reads/s end to end)
+    int64_t chunk = std::max<int64_t>(4096, std::min<int64_t>((int64_t)(1536ll << 20) / per_read, 1 << 18));
     if (n_reads < 4 * chunk) chunk = std::max<int64_t>(4096, (n_reads + 3) / 4);
     if (const char *v = getenv("C2B_CHUNK")) chunk = std::max<int64_t>(2, atoll(v));     // test hook: force many small chunks
     for (auto &st : e->stage) st.used = false;
@@ -1212,9 +1215,13 @@ static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *
             e->pair_order = (const int32_t *)st.ord.p;
         }
         RTCHK(rt_record(st.in_done, e->s_in));
-        rt_stream cs = e->stream;
+        // C2B_TWO_STREAMS=1: consecutive chunks alternate between two compute streams (and the two scratch sets) so that the
+        // head of chunk c+1's ALIGN launch could fill the SMs the tails of chunk c's launches leave idle.  Measured r02j: 49.6
+        // against 56.5 M reads/s end to end on one stream (two sets of ring slabs in flight, 350 MB, against a 126 MB L2) -- off.
+        const int set = (e->stream2 && getenv("C2B_TWO_STREAMS")) ? (ci & 1) : 0;
+        rt_stream cs = set ? e->stream2 : e->stream;
         RTCHK(rt_wait(cs, st.in_done));
-        rc = launch_on(e, cs, 0, (const uint8_t *)st.reads.p, (const int64_t *)st.off.p, n, (int32_t)maxJ,
+        rc = launch_on(e, cs, set, (const uint8_t *)st.reads.p, (const int64_t *)st.off.p, n, (int32_t)maxJ,
                        count ? (const int32_t *)st.cnt.p : nullptr, qweight ? (const int32_t *)st.qw.p : nullptr,
                        ref_id ? (const int32_t *)st.rid.p : nullptr, (c2b_read_rec *)st.recs.p,
                        (c2b_aln_rec *)st.alns.p, strings ? (uint8_t *)st.str.p : nullptr,
@@ -1222,7 +1229,7 @@ static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *
         e->pair_order = nullptr;
         if (rc) return rc;
         // keep this batch's "widest alignment" before the next launch sequence resets it
-        RTCHK(cudaMemcpyAsyncOrCopy(st.maxlen.p, (const char *)e->work.p + 9 * 8, 8, cs));
+        RTCHK(cudaMemcpyAsyncOrCopy(st.maxlen.p, (const char *)e->work.p + (9 + 8 * set) * 8, 8, cs));
         RTCHK(rt_record(st.k_done, cs));
         st.used = true;
         if (pend.any && (rc = flush(pend))) return rc;           // chunk ci-1: overlaps this chunk's kernels
@@ -1231,6 +1238,7 @@ static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *
     if (pend.any && (rc = flush(pend))) return rc;
     RTCHK(rt_sync(e->s_out));
     RTCHK(rt_sync(e->stream));
+    if (e->stream2) RTCHK(rt_sync(e->stream2));
     for (auto &st : e->stage) if ((rc = drain(st))) return rc;
     return C2B_OK;
 }

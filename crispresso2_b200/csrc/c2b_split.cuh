@@ -686,8 +686,11 @@ C2B_DEV ColOut colscan0(const KParams &P, const RefDev &R, ColCtx &c, uint8_t *o
 // Pass 1: find_indels_substitutions + the per-read quantification, same mode bits and outputs as rows_run (c2b_core.cuh),
 // evaluated over alignment columns.  Insertion / deletion runs are closed in the step that holds their first column to the
 // right (state carried across steps); flank positions shared by two insertions count once (numpy's fancy-index +=).
-C2B_DEVNOINL void colscan1(const KParams &P, const RefDev &R, const ColCtx &c, RowOut &o, c2b_edit *ed, long long w, int mode,
-                      unsigned long long *Vt = nullptr)
+// LEGACY = --use_legacy_insertion_quantification as a template parameter: one more flag test inside the scan cost the default
+// instantiation registers it does not have (80 at six CTAs per SM: 304 -> 468 bytes of spills, 3.65 -> 3.98 ms per 1 Mi reads).
+template <bool LEGACY>
+C2B_DEVNOINL void colscan1_t(const KParams &P, const RefDev &R, const ColCtx &c, RowOut &o, c2b_edit *ed, long long w, int mode,
+                             unsigned long long *Vt = nullptr)
 {
     const int lane = wp::lane();
     const uint32_t lt = (1u << lane) - 1u;
@@ -703,7 +706,7 @@ C2B_DEVNOINL void colscan1(const KParams &P, const RefDev &R, const ColCtx &c, R
     const int nsteps = (c.n + 31) >> 5;
 
     // --use_legacy_insertion_quantification: same rules as rows_run (c2b_core.cuh), COREResources.pyx:190-315
-    const bool legacy = (P.flags & C2B_F_LEGACY_INS) != 0;
+    constexpr bool legacy = LEGACY;
     auto del_run = [&](int a0, int b0) {                   // one deletion run [a0,b0)  (COREResources.pyx:143-160)
         const int size = b0 - a0;
         const int a = (legacy && a0 <= 1) ? 0 : a0, b = (legacy && b0 == I) ? I - 1 : b0;
@@ -857,6 +860,13 @@ C2B_DEVNOINL void colscan1(const KParams &P, const RefDev &R, const ColCtx &c, R
     }
     if (del_a >= 0) del_run(del_a, I);                     // a deletion that reaches the end of the alignment
     // an insertion run that reaches the end of the alignment lies after the last reference base: not counted
+}
+
+C2B_DEV void colscan1(const KParams &P, const RefDev &R, const ColCtx &c, RowOut &o, c2b_edit *ed, long long w, int mode,
+                      unsigned long long *Vt = nullptr)
+{
+    if (P.flags & C2B_F_LEGACY_INS) colscan1_t<true>(P, R, c, o, ed, w, mode, Vt);
+    else colscan1_t<false>(P, R, c, o, ed, w, mode, Vt);
 }
 
 // Classification + counts of one read whose alignments to references r_begin..r_end-1 were produced by the ALIGN kernel:
