@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, C2B_A_MIN_CTAS) c2b_align_
     const int nw = blockDim.x >> 5;
     const int warp_slot = blockIdx.x * nw + (threadIdx.x >> 5);
     const uint32_t *staged_prof = stage_profile(P, smem_raw + (((size_t)nw * sizeof(ASmem) + 127) & ~(size_t)127));
+    asmem_init(P, *S);
     const int64_t nrd = nreads(P);
     const unsigned ahead = gridDim.x * nw;
     if (P.left2) {
@@ -856,6 +857,7 @@ static int launch_on(c2b_engine *e, rt_stream cs, int set, const uint8_t *d_read
         if (split) {
             KParams A = P;
             A.left = d_left; A.left_n = wk + 3;
+            emu::run_warp([&]() { asmem_init(A, AS); });
             const bool narrow = d_left2 && !P.pair_order && (e->n_refs == 1 || d_ref_id != nullptr) && !getenv("C2B_NO_NARROW");
             if (narrow) {
                 A.left2 = d_left2; A.left2_n = wk + 5;

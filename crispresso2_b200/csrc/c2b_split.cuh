@@ -26,7 +26,16 @@ struct ASmem {                                         // ALIGN kernel, per warp
     uint8_t fw[2][RG_COMBO], rc[2][RG_COMBO];          // the two reads of the pair being prepared, as alphabet codes
     uint8_t combo[8][RG_COMBO];                        // base-pair codes of the pairs (four; eight in the narrow first tier)
     uint32_t fin[96];                                  // M, X, Y of cell (I, J) per lane
+    uint8_t lut[256];                                  // ASCII -> alphabet code (copy of P.lut: the per-base lookups of load_codes_a
+                                                       // waited on global memory, 2.9 % of the tier-1 stall samples at r02k)
 };
+
+C2B_DEV void asmem_init(const KParams &P, ASmem &S)
+{
+    const int lane = wp::lane();
+    for (int k = lane; k < 256; k += 32) S.lut[k] = P.lut[k];
+    wp::sync();
+}
 
 C2B_DEV int64_t read_at(const KParams &P, int64_t idx) { return P.pair_order ? (int64_t)P.pair_order[idx] : idx; }
 
@@ -44,7 +53,7 @@ C2B_DEV void leftover_one(const KParams &P, int64_t rd)
 }
 
 // read -> alphabet codes for reads of at most RG_COMBO symbols; true if a symbol is outside the alphabet
-C2B_DEV bool load_codes_a(const KParams &P, int64_t off, int J, uint8_t *fw, uint8_t *rc)
+C2B_DEV bool load_codes_a(const KParams &P, const uint8_t *lut, int64_t off, int J, uint8_t *fw, uint8_t *rc)
 {
     const int lane = wp::lane();
     bool bad = false;
@@ -55,7 +64,7 @@ C2B_DEV bool load_codes_a(const KParams &P, int64_t off, int J, uint8_t *fw, uin
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const int p = base + lane + 32 * e;
-            int code = P.lut[ch[e]];
+            int code = lut[ch[e]];
             if (code == 255) { bad = true; code = 0; }
             if (p < J) { fw[p] = (uint8_t)code; rc[J - 1 - p] = P.comp[code]; }
         }
@@ -244,7 +253,7 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
         const int J = (int)(P.offsets[rdA + 1] - P.offsets[rdA]);
         bool bad = false;
 #pragma unroll 1
-        for (int x = 0; x < 2; x++) bad |= load_codes_a(P, P.offsets[x ? rdB : rdA], J, S.fw[x], S.rc[x]);
+        for (int x = 0; x < 2; x++) bad |= load_codes_a(P, S.lut, P.offsets[x ? rdB : rdA], J, S.fw[x], S.rc[x]);
         wp::sync();
         int mAB = 0; bool agree = true;
 #pragma unroll 1
@@ -356,7 +365,7 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
                 wp::sync();
                 if (kind) {
                     const int64_t rdx = read_at(P, 2 * (first + q) + (kind - 1));
-                    load_codes_a(P, P.offsets[rdx], Jp, S.fw[0], S.rc[0]);
+                    load_codes_a(P, S.lut, P.offsets[rdx], Jp, S.fw[0], S.rc[0]);
                     wp::sync();
                     for (int p = lane; p < Jp; p += 32) S.fw[1][p] = (uint8_t)(S.fw[0][p] * P.nq + S.rc[0][p]);
                     combo = S.fw[1];
@@ -458,8 +467,8 @@ C2B_DEV bool align_narrow16(const KParams &P, ASmem &S, const uint32_t *staged_p
 #pragma unroll 1
     for (int q = 0; q < 8; q++) {
         const int64_t rdA = read_at(P, first + 2 * q), rdB = read_at(P, first + 2 * q + 1);
-        bool badA = load_codes_a(P, P.offsets[rdA], J, S.fw[0], S.rc[0]);
-        bool badB = load_codes_a(P, P.offsets[rdB], J, S.fw[1], S.rc[1]);
+        bool badA = load_codes_a(P, S.lut, P.offsets[rdA], J, S.fw[0], S.rc[0]);
+        bool badB = load_codes_a(P, S.lut, P.offsets[rdB], J, S.fw[1], S.rc[1]);
         wp::sync();
         int m = 0;
 #pragma unroll 1
