@@ -1053,12 +1053,13 @@ static int align_batch_host(c2b_engine *e, const uint8_t *reads, const int64_t *
     cudaSetDevice(e->device);                              // the current device is per host thread: callers may use a worker thread
 #endif
     if (n_reads == 0) return C2B_OK;
-    int64_t maxJ = 1;
+    int64_t maxJ = 1, minJ = 0;                            // branch-free reductions (vectorised): this scan runs before anything is queued
     for (int64_t r = 0; r < n_reads; r++) {
         const int64_t L = offsets[r + 1] - offsets[r];
-        if (L < 0) return fail(e, C2B_E_ARG, "c2b_align_batch: offsets not monotone");
-        maxJ = std::max(maxJ, L);
+        maxJ = L > maxJ ? L : maxJ;
+        minJ = L < minJ ? L : minJ;
     }
+    if (minJ < 0) return fail(e, C2B_E_ARG, "c2b_align_batch: offsets not monotone");
     if (maxJ > C2B_MAX_READ_LEN) return fail(e, C2B_E_LIMIT, "c2b_align_batch: read longer than C2B_MAX_READ_LEN");
     if (!e->pipe_ready) {
         RTCHK(rt_stream_create(&e->s_in));

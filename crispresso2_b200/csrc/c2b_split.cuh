@@ -76,8 +76,8 @@ C2B_DEV bool load_codes_a(const KParams &P, const uint8_t *lut, int64_t off, int
 // slab gather per run of equal ops -- and four of them in sequence cost as much wall time as the DP itself (r02b: the ALIGN
 // kernel's issue slots were idle half the time).  Here every iteration issues the gathers of all four pairs before it
 // consumes any, so the four latencies overlap; the per-pair logic is walk_batch<true>'s for a ring slab, verbatim.
-// RL / q0: ring size of the DP that filled the slab (8 or 4 lanes) and the first of the four pairs walked by this call.
-template <int RL = 8>
+// RL / q0 / NP: ring size of the DP that filled the slab (8 or 4 lanes), first pair and number of pairs walked (interleaved) by this call.
+template <int RL = 8, int NP = 4>
 C2B_DEV void walk_ring4(const KParams &P, const RefDev &R, const int *Jq, const uint2 *__restrict__ tb2, const int *s0, uint32_t mask,
                         Walked *out, const int q0 = 0)
 {
@@ -85,10 +85,10 @@ C2B_DEV void walk_ring4(const KParams &P, const RefDev &R, const int *Jq, const 
     const int lane = wp::lane();
     const int hl = lane & 15, hb = lane & 16;
     const int TS = P.TS;
-    int i[4], j[4], s[4], n[4], err[4];
-    uint32_t acc[4], lo[4], hi[4];
+    int i[NP], j[NP], s[NP], n[NP], err[NP];
+    uint32_t acc[NP], lo[NP], hi[NP];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < NP; q++) {
         const bool on = (mask >> q) & 1u;
         i[q] = on ? R.I : 0; j[q] = on ? Jq[q] : 0; s[q] = s0[q]; n[q] = 0; err[q] = 0; acc[q] = 0; lo[q] = hi[q] = ~0u;
     }
@@ -98,10 +98,10 @@ C2B_DEV void walk_ring4(const KParams &P, const RefDev &R, const int *Jq, const 
             acc[q] = (uint32_t)((((uint64_t)pat << 32) | acc[q]) >> (2 * c)); n[q] += c; cnt -= c;                                   \
             if ((n[q] & 15) == 0) { const int ix = (n[q] >> 4) - 1; if (hl == (ix >> 1)) { if (ix & 1) hi[q] = acc[q]; else lo[q] = acc[q]; } } } } while (0)
     for (;;) {
-        uint2 w2[4]; bool valid[4], inband[4]; int sh[4];
+        uint2 w2[NP]; bool valid[NP], inband[NP]; int sh[NP];
         bool anyact = false;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < NP; q++) {
             const bool active = i[q] > 0 && j[q] > 0;
             anyact |= active;
             const int di = (s[q] != OP_I), dj = (s[q] != OP_J);
@@ -119,7 +119,7 @@ C2B_DEV void walk_ring4(const KParams &P, const RefDev &R, const int *Jq, const 
         }
         if (!wp::ballot(anyact)) break;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < NP; q++) {
             const bool active = i[q] > 0 && j[q] > 0;
             const uint32_t w = hb ? ((w2[q].x & 0xffff0000u) | (w2[q].y >> 16)) : ((w2[q].x << 16) | (w2[q].y & 0xffffu));
             const uint32_t v = (valid[q] && inband[q]) ? (w >> sh[q]) : 0u;
@@ -147,7 +147,7 @@ C2B_DEV void walk_ring4(const KParams &P, const RefDev &R, const int *Jq, const 
         }
     }
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < NP; q++) {
         if (j[q] > 0 && s[q] != OP_I) err[q] |= 1;              // row 0 / column 0 can only be left along their own border
         if (i[q] > 0 && s[q] != OP_J) err[q] |= 1;
         while (j[q] > 0) { const int c = j[q] < 32 ? j[q] : 32; C2B_PUSH4(q, OP_I, c); j[q] -= c; }
@@ -497,8 +497,10 @@ C2B_DEV bool align_narrow16(const KParams &P, ASmem &S, const uint32_t *staged_p
 #pragma unroll
     for (int q = 0; q < 8; q++) pass2 |= (((bA >> (RL * q)) & 1u) | (((bB >> (RL * q)) & 1u) << 1)) << (2 * q);
     pass2 &= use2;
+    // tracebacks: pairs 0-3, then 4-7, four interleaved at a time (all eight at once was measured slower: tier 1 8.14 ms against
+    // 7.46 ms per 1 Mi reads, r02n)
 #pragma unroll 1
-    for (int half = 0; half < 2; half++) {                   // tracebacks: pairs 0-3, then 4-7, four interleaved at a time
+    for (int half = 0; half < 2; half++) {
         const int q0 = 4 * half;
         int Jq[4], s0[4];
         Walked wk4[4];
@@ -511,7 +513,7 @@ C2B_DEV bool align_narrow16(const KParams &P, ASmem &S, const uint32_t *staged_p
             if ((pass2 >> (2 * (q0 + q))) & 3u) walkmask |= 1u << q;
         }
         if (!walkmask) continue;
-        walk_ring4<RL>(P, R, Jq, tbq, s0, walkmask, wk4, q0);
+        walk_ring4<RL, 4>(P, R, Jq, tbq, s0, walkmask, wk4, q0);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (!((walkmask >> q) & 1u)) continue;

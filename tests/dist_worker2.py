@@ -1,5 +1,7 @@
-"""Worker for tests/test_dist_gloo.py: world_size ranks (gloo, CPU, emulator build of the engine) run
-core.process_fastq_sharded on the same FASTQ; rank 0 writes what it returned."""
+"""Worker for tests/test_dist_gloo.py (gloo, CPU, emulator build of the engine) and tests/test_gpu_dist.py (nccl, one GPU per
+rank, sm_100a library, NO explicit engine: every rank must pick the GPU named by LOCAL_RANK): world_size ranks run
+core.process_fastq_sharded on the same FASTQ; rank 0 writes what it returned.
+usage: dist_worker2.py <fastq> <out.json> [gloo|nccl]"""
 import json
 import os
 import sys
@@ -21,13 +23,19 @@ def main():
     from crispresso2_b200.engine import Engine
     from oracle import oracle as O
     fq, out_path = sys.argv[1:3]
-    dist.init_process_group("gloo")
+    backend = sys.argv[3] if len(sys.argv) > 3 else "gloo"
+    if backend == "nccl":
+        import torch
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+    else:
+        dist.init_process_group("gloo")
     rank = dist.get_rank()
     rec = G.load("synth_hdr")
     refs = G.refs_from(rec)
     args = PU.args_from(rec["params"])
     args.expected_hdr_amplicon_seq = refs[rec["ref_names"][1]]["sequence"]
-    eng = Engine(lib_path=build_emu.build())
+    eng = Engine(lib_path=build_emu.build()) if backend == "gloo" else None       # nccl: the default engine of the rank's own GPU
     cache = {}
     stats, lost = core.process_fastq_sharded(fq, cache, rec["ref_names"], refs, args, [], os.path.dirname(out_path),
                                              engine=eng, aln_matrix=O.make_matrix())

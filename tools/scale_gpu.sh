@@ -14,3 +14,4 @@ import json
 d=json.load(open('gpurun_out/scale_${tag}_n$n.json'))
 print('N=$n value %.1f M/s (%.2f ms/step)  e2e %.1f M/s (%.2f ms/step)  gate %s clocks %s' % (d['value']/1e6, d['ms_per_step'], d['e2e']['value']/1e6, d['e2e']['ms_per_step'], d['config']['parity_gate'], d.get('clocks')))" || tail -5 gpurun_out/scale_${tag}_n$n.err
 done
+python -m pytest tests/test_gpu_dist.py -m gpu -q 2>&1 | tail -3
