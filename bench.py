@@ -317,6 +317,10 @@ def api_leg(w, eng, reads, label):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def _ingest_device():
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
 def ingest_leg(reads):
     """FASTQ front end alone: native parse + exact de-duplication (c2b_fastq_dedup: what feeds the kernels)
     and the native quality filter (c2b_fastq_filter), on the timed batch written as plain text and -- a 256k-read slice -- as
@@ -349,6 +353,13 @@ def ingest_leg(reads):
             assert dd.n_reads == n
             out[name] = {"reads": n, "unique": int(len(dd.counts)), "seconds": dt, "reads_per_s": n / dt,
                          "file_MB_per_s": os.path.getsize(path) / dt / 1e6}
+        for name, path, n in (("dedup_gpu_plain", plain, len(reads)), ("dedup_gpu_gzip", gz, len(sub))):
+            # the same front end on the GPU (c2b_fastq_dedup_gpu): file bytes over PCIe once, parse + exact dedup on the device
+            dt, dg = best(lambda: fastq.dedup_file(path, device=_ingest_device()))
+            hd = fastq.dedup_file(path)
+            assert dg.n_reads == n and np.array_equal(dg.off, hd.off) and np.array_equal(dg.buf, hd.buf) and np.array_equal(dg.counts, hd.counts)
+            out[name] = {"reads": n, "unique": int(len(dg.counts)), "seconds": dt, "reads_per_s": n / dt,
+                         "file_MB_per_s": os.path.getsize(path) / dt / 1e6, "equals_host_front_end": True}
         for name, path, n in (("filter_plain", plain, len(reads)), ("filter_gzip_in_out", gz, len(sub))):
             dst = os.path.join(d, "f_" + os.path.basename(path))
             dt, r = best(lambda: filter_fastqs.filterFastqs(fastq_r1=path, fastq_r1_out=dst, min_av_read_qual=30, min_bp_qual_or_N=20), reps=2)
@@ -358,7 +369,7 @@ def ingest_leg(reads):
         shutil.rmtree(d, ignore_errors=True)
 
 
-def reference_arm(args):
+def reference_arm(args, emit):
     """--impl reference: the reference's own Cython global_align + find_indels_substitutions (compiled from /root/reference,
     unmodified) on all host cores, on a bounded sample per step; falls back to the oracle port when neither baseline/_ref
     nor oracle/_ref travelled."""
@@ -392,7 +403,7 @@ def reference_arm(args):
             "config": {"workload": "synthetic 1M x 250 bp reads, 1 amplicon (bounded sample per step)"},
             "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- main
@@ -415,9 +426,19 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # stdout carries the ONE JSON line and nothing else: libraries that write to fd 1 (NCCL's version banner, the reference's
+    # logger) go to stderr for the whole run; the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(line):
+        real_out.write(json.dumps(line) + "\n")
+        real_out.flush()
+
     if args.impl == "reference":
         if rank == 0:
-            reference_arm(args)
+            reference_arm(args, emit)
         return 0
 
     import torch
@@ -681,7 +702,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline_block(w.refs["Reference"]["sequence"], w.refs["Reference"], w.buf.reshape(-1, 250))
         elif not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_generic(w)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -81,7 +81,7 @@ EXPORTS = ["c2b_create", "c2b_destroy", "c2b_last_error", "c2b_configure", "c2b_
            "c2b_align_batch_device", "c2b_set_pair_order", "c2b_sync", "c2b_stream", "c2b_last_kernel_ms", "c2b_launch_count", "c2b_path_counts", "c2b_band_reruns", "c2b_ring_counts",
            "c2b_counts_layout", "c2b_counts_hist_layout", "c2b_counts_reset", "c2b_counts_read", "c2b_counts_device", "c2b_global_align",
            "c2b_classify_aligned", "c2b_classify_aligned_flags", "c2b_host_alloc", "c2b_host_free",
-           "c2b_fastq_dedup", "c2b_fastq_dedup_buffer", "c2b_fastq_n_reads", "c2b_fastq_n_unique", "c2b_fastq_max_len",
+           "c2b_fastq_dedup", "c2b_fastq_dedup_buffer", "c2b_fastq_gpu_available", "c2b_fastq_dedup_gpu", "c2b_fastq_dedup_gpu_buffer", "c2b_fastq_n_reads", "c2b_fastq_n_unique", "c2b_fastq_max_len",
            "c2b_fastq_seqs", "c2b_fastq_offsets", "c2b_fastq_counts", "c2b_fastq_first_index", "c2b_fastq_free",
            "c2b_fastq_last_error", "c2b_fastq_filter", "c2b_fastq_filter_pair", "c2b_rc_merge_weights", "c2b_screen_reads", "c2b_serial_stats",
            "c2b_alleles_build", "c2b_alleles_free", "c2b_alleles_n", "c2b_alleles_order", "c2b_alleles_arena", "c2b_alleles_offsets",
@@ -179,6 +179,12 @@ def load(path=None):
         getattr(L, name).argtypes = [vp]
     L.c2b_fastq_free.restype = None
     L.c2b_fastq_free.argtypes = [vp]
+    L.c2b_fastq_gpu_available.restype = C.c_int
+    L.c2b_fastq_gpu_available.argtypes = []
+    L.c2b_fastq_dedup_gpu.restype = C.c_int
+    L.c2b_fastq_dedup_gpu.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+    L.c2b_fastq_dedup_gpu_buffer.restype = C.c_int
+    L.c2b_fastq_dedup_gpu_buffer.argtypes = [vp, C.c_size_t, i32, C.POINTER(vp)]
     L.c2b_fastq_filter.restype = C.c_int
     L.c2b_fastq_filter.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]
     L.c2b_fastq_filter_pair.restype = C.c_int

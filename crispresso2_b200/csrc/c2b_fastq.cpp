@@ -13,6 +13,7 @@
 // walks them in file order through an open-addressing table (full byte compare on hash match -- exact, no
 // probabilistic step); (4) merge the shards' (first index, count) lists by first index.
 #include "c2b200.h"
+#include "c2b_fastq_int.h"
 
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -89,17 +90,10 @@ bool read_gz(const char *path, std::vector<uint8_t> &buf, std::string &err)
 
 }  // namespace
 
-struct c2b_fastq {
-    std::unique_ptr<uint8_t[]> seqs;                        // packed unique sequences (uninitialised storage: every byte is written by emit)
-    std::vector<int64_t> offsets;
-    std::vector<int32_t> counts;
-    std::vector<int64_t> first_index;
-    int64_t n_reads = 0;
-    int32_t max_len = 0;
-    std::string err;
-};
-
 static std::string g_fastq_err;
+
+bool c2b_fastq_read_gz(const char *path, std::vector<uint8_t> &buf, std::string &err) { return read_gz(path, buf, err); }
+void c2b_fastq_set_error(const std::string &m) { g_fastq_err = m; }
 
 extern "C" {
 
@@ -310,6 +304,13 @@ int c2b_fastq_dedup(const char *path, int32_t n_threads, c2b_fastq **out)
         fprintf(stderr, "[c2b_fastq] read       %.3f s (%zu bytes)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), buf.size());
     return c2b_fastq_dedup_buffer(buf.data(), buf.size(), n_threads, out);
 }
+
+#ifdef C2B_EMU
+// the CPU warp-emulator build (test infrastructure) has no device front end
+int c2b_fastq_gpu_available(void) { return 0; }
+int c2b_fastq_dedup_gpu(const char *, int32_t, c2b_fastq **out) { if (out) *out = nullptr; g_fastq_err = "c2b_fastq_dedup_gpu: not built (emulator)"; return C2B_E_STATE; }
+int c2b_fastq_dedup_gpu_buffer(const uint8_t *, size_t, int32_t, c2b_fastq **out) { if (out) *out = nullptr; g_fastq_err = "c2b_fastq_dedup_gpu: not built (emulator)"; return C2B_E_STATE; }
+#endif
 
 int64_t c2b_fastq_n_reads(const c2b_fastq *f) { return f ? f->n_reads : 0; }
 int64_t c2b_fastq_n_unique(const c2b_fastq *f) { return f ? (int64_t)f->counts.size() : 0; }

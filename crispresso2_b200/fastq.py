@@ -66,20 +66,55 @@ def _collect(L, h):
     return Dedup(buf, off, counts, first, nr)
 
 
-def dedup_file(path, n_threads=0, lib_path=None):
+GPU_INGEST_MAX_PLAIN = 8 << 30        # the text and its tables (about 3x the file) stay far below one GPU's HBM
+GPU_INGEST_MAX_GZ = 1 << 30
+
+
+def gpu_ingest_device(path, engine_device=None, lib_path=None):
+    """Which front end process_fastq uses for `path`: a device index (c2b_fastq_dedup_gpu) or None (c2b_fastq_dedup on the
+    host threads).  C2B_GPU_INGEST=1 forces the GPU, =0 the host; unset: the GPU when the library has the device front end
+    (not the emulator test build) and the file is small enough to sit in HBM whole."""
+    import os
+    dev = 0 if engine_device is None else int(engine_device)
+    env = os.environ.get("C2B_GPU_INGEST", "")
+    if env == "0":
+        return None
+    if env not in ("", "0"):
+        return dev
+    if not _lib.load(lib_path).c2b_fastq_gpu_available():
+        return None
+    try:
+        size = os.path.getsize(path)
+    except OSError:
+        return None
+    return dev if size <= (GPU_INGEST_MAX_GZ if str(path).endswith(".gz") else GPU_INGEST_MAX_PLAIN) else None
+
+
+def dedup_file(path, n_threads=0, lib_path=None, device=None):
+    """device=None: the host front end (c2b_fastq_dedup, n_threads workers); device=k: parse + de-duplicate on GPU k
+    (c2b_fastq_dedup_gpu) -- same result object either way."""
     L = _lib.load(lib_path)
     h = C.c_void_p()
-    rc = L.c2b_fastq_dedup(str(path).encode(), int(n_threads), C.byref(h))
+    if device is not None:
+        rc = L.c2b_fastq_dedup_gpu(str(path).encode(), int(device), C.byref(h))
+        name = "c2b_fastq_dedup_gpu"
+    else:
+        rc = L.c2b_fastq_dedup(str(path).encode(), int(n_threads), C.byref(h))
+        name = "c2b_fastq_dedup"
     if rc != 0:
-        raise FastqError("c2b_fastq_dedup failed (%d): %s" % (rc, L.c2b_fastq_last_error().decode()))
+        raise FastqError("%s failed (%d): %s" % (name, rc, L.c2b_fastq_last_error().decode()))
     return _collect(L, h)
 
 
-def dedup_bytes(data, n_threads=0, lib_path=None):
+def dedup_bytes(data, n_threads=0, lib_path=None, device=None):
     L = _lib.load(lib_path)
     h = C.c_void_p()
     arr = np.frombuffer(data, dtype=np.uint8)
-    rc = L.c2b_fastq_dedup_buffer(arr.ctypes.data if len(arr) else None, len(arr), int(n_threads), C.byref(h))
+    ptr = arr.ctypes.data if len(arr) else None
+    if device is not None:
+        rc = L.c2b_fastq_dedup_gpu_buffer(ptr, len(arr), int(device), C.byref(h))
+    else:
+        rc = L.c2b_fastq_dedup_buffer(ptr, len(arr), int(n_threads), C.byref(h))
     if rc != 0:
-        raise FastqError("c2b_fastq_dedup_buffer failed (%d)" % rc)
+        raise FastqError("c2b_fastq_dedup%s_buffer failed (%d): %s" % ("_gpu" if device is not None else "", rc, L.c2b_fastq_last_error().decode()))
     return _collect(L, h)

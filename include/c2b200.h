@@ -304,6 +304,12 @@ const int32_t *c2b_fastq_counts(const c2b_fastq *f);
 const int64_t *c2b_fastq_first_index(const c2b_fastq *f); /* record index of each unique sequence's first occurrence */
 void c2b_fastq_free(c2b_fastq *f);
 const char *c2b_fastq_last_error(void);
+/* the same front end ON the GPU (csrc/c2b_fastq_gpu.cu): the file's bytes cross PCIe once; line index, per-record strip + hash,
+ * exact de-duplication in a device hash table (byte compare on a hash match), first-seen order by a radix sort of the groups'
+ * first records.  Same c2b_fastq result, same semantics (CRISPRessoCORE.py:1820-1849), gzip inflated on the host first. */
+int  c2b_fastq_gpu_available(void);              /* 1 in the CUDA build; 0 in the CPU emulator test build (no device front end) */
+int  c2b_fastq_dedup_gpu(const char *path, int32_t device, c2b_fastq **out);
+int  c2b_fastq_dedup_gpu_buffer(const uint8_t *data, size_t n_bytes, int32_t device, c2b_fastq **out);
 
 /* replaces: the reverse-complement count transfer at the head of the quantification loop (CRISPRessoCORE.py:3964-3975) for
  * packed unique reads in first-seen order: weights[k] = the count read k ends up with (0 for a read absorbed by an earlier

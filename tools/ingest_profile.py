@@ -13,8 +13,9 @@ for name, reads in (("bench batch", w.buf.reshape(-1, 250)),
                     ("all unique", synth.synth_reads_fast(np.random.default_rng(77), amp, 1 << 20, 250, sub_rate=0.02, cut=w.refs["Reference"]["cut_point"]))):
     fq = os.path.join(d, "r.fastq")
     synth.write_fastq_fast(fq, reads)
-    for rep in range(3):
+    for rep in range(6):
+        dev = 0 if (rep >= 3 and os.environ.get("C2B_INGEST_GPU", "1") != "0") else None
         t0 = time.perf_counter()
-        dd = fastq.dedup_file(fq)
+        dd = fastq.dedup_file(fq, device=dev)
         dt = time.perf_counter() - t0
-        print("%s rep %d: %.3f s, %d unique of %d, %.2f M reads/s, %.2f GB/s" % (name, rep, dt, len(dd.counts), dd.n_reads, dd.n_reads / dt / 1e6, os.path.getsize(fq) / dt / 1e9), file=sys.stderr)
+        print(("gpu  " if dev is not None else "host ") + "%s rep %d: %.3f s, %d unique of %d, %.2f M reads/s, %.2f GB/s" % (name, rep, dt, len(dd.counts), dd.n_reads, dd.n_reads / dt / 1e6, os.path.getsize(fq) / dt / 1e9), file=sys.stderr)
