@@ -96,6 +96,7 @@ class AlleleTable:
     def __init__(self, variantCache, lib_path=None):
         from . import core
         src = core.source_of(variantCache)
+        scaffold = getattr(src, "scaffold", None)            # prime editing: reads re-labelled 'Scaffold-incorporated' (:789-796)
         self.L = _lib.load(lib_path or src.lib_path)
         self.ref_names = list(src.ref_names)
         self.ref_seqs = [src.refs[r]["sequence"] for r in self.ref_names]
@@ -128,6 +129,15 @@ class AlleleTable:
             first = np.where(low > 0, np.log2(np.maximum(low, 1)).astype(np.int64), 0)
         amb = (recs["ambiguous"] != 0) if nr > 1 else np.zeros(n, dtype=bool)
         assign_first = bool(flags & _lib.F_ASSIGN_FIRST)
+        hit, pe_idx = np.zeros(n, dtype=bool), -1
+        if scaffold is not None:                              # one row per re-labelled read: its prime-edited alignment
+            pe_idx = self.ref_names.index(core.PE_REF)
+            hs = []
+            for _lo, res, _fx in parts:
+                h = getattr(res, "_scaffold_hits", None)
+                hs.append(h if h is not None else core.scaffold_hits(res, pe_idx, scaffold[0], scaffold[1]))
+            hit = np.concatenate(hs) if len(hs) > 1 else hs[0]
+            amb = amb & ~hit
         rows_read, rows_r = [], []
         if nr == 1:
             idx = np.nonzero(sel)[0]
@@ -137,8 +147,9 @@ class AlleleTable:
             for r in range(nr):
                 won = sel & (((mask >> r) & 1) != 0)
                 if assign_first:
-                    won &= (first == r)
+                    won &= (first == r) | hit
                 won &= ~amb | (first == r)                          # AMBIGUOUS: one row, the first winner's payload (:3989-3993)
+                won &= ~hit | (r == pe_idx)
                 idx = np.nonzero(won)[0]
                 rows_read.append(idx)
                 rows_r.append(np.full(len(idx), r, dtype=np.int64))
@@ -154,23 +165,26 @@ class AlleleTable:
         self.count = np.ascontiguousarray(w[self.row_read])
         ref_of_row = (np.asarray(ref_id)[self.row_read].astype(np.int64) if ref_id is not None else self.row_r)
         # Reference_Name: the reference, or AMBIGUOUS_<first winner> (:3991), or DISCARDED_<first winner> (:3999)
-        nn = len(self.ref_names)
+        label_names = self.ref_names + ([core.SCAFFOLD_REF] if scaffold is not None else [])
+        nn = len(label_names)
+        hit_row = hit[self.row_read]
         kind = np.zeros(m, dtype=np.int64)
         discard = (a["deletion_n"] > 0) | (a["insertion_n"] > 0) if (flags & _lib.F_DISCARD_INDEL_READS) else np.zeros(m, dtype=bool)
         fw_row = first[self.row_read] if nr > 1 else ref_of_row
         kind[discard] = 2
         kind[amb[self.row_read]] = 1
-        name_ref = np.where(kind == 0, ref_of_row, fw_row)
+        name_ref = np.where(hit_row, nn - 1, np.where(kind == 0, ref_of_row, fw_row))
         self.name_id = np.ascontiguousarray((kind * nn + name_ref).astype(np.int32))
-        self.names = self.ref_names + ["AMBIGUOUS_" + x for x in self.ref_names] + ["DISCARDED_" + x for x in self.ref_names]
+        self.names = label_names + ["AMBIGUOUS_" + x for x in label_names] + ["DISCARDED_" + x for x in label_names]
         # Aligned_Reference_Names / _Scores: per unique read, spelled once per distinct value
         if ref_id is not None:
             self._names_id = ref_of_row.astype(np.int64)
             self._names_tab = list(self.ref_names)
         else:
             mk = np.where(assign_first & (mask > 0), mask & -mask, mask)[self.row_read]
+            mk = np.where(hit_row, 0, mk)                           # aln_ref_names of a re-labelled read: the scaffold reference alone
             uq, inv = np.unique(mk, return_inverse=True)
-            self._names_tab = ["&".join(self.ref_names[r] for r in range(nr) if (int(v) >> r) & 1) for v in uq]
+            self._names_tab = ["&".join(self.ref_names[r] for r in range(nr) if (int(v) >> r) & 1) if v else core.SCAFFOLD_REF for v in uq]
             self._names_id = inv
         sc = alns["score_milli"][self.row_read]                                        # [m, nr]
         uq, inv = np.unique(sc, axis=0, return_inverse=True)

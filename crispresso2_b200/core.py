@@ -64,8 +64,61 @@ def _flags(args):
 def _unsupported(args, refs=None):
     if getattr(args, "use_legacy_insertion_quantification", False) and refs and any(r.get("contains_coding_seq") for r in refs.values()):
         raise NotImplementedError("use_legacy_insertion_quantification together with a coding sequence is not built on the GPU path")
-    if getattr(args, "prime_editing_pegRNA_scaffold_seq", ""):
-        raise NotImplementedError("prime-editing scaffold search (CRISPRessoCORE.py:789-796) is not built on the GPU path")
+
+
+SCAFFOLD_REF, PE_REF = "Scaffold-incorporated", "Prime-edited"
+
+
+def scaffold_search(args, refs):
+    """pe_scaffold_dna_info of process_fastq (CRISPRessoCORE.py:1814-1816; plots/data_prep.py:3827-3860): (position in the
+    prime-edited amplicon right after the pegRNA extension, the shortest scaffold prefix whose presence there cannot come from
+    the amplicon itself), or None when no scaffold sequence was given."""
+    scaf = getattr(args, "prime_editing_pegRNA_scaffold_seq", "") or ""
+    if not scaf:
+        return None
+    ext = getattr(args, "prime_editing_pegRNA_extension_seq", "") or ""
+    if not ext:
+        raise ValueError("prime_editing_pegRNA_scaffold_seq needs prime_editing_pegRNA_extension_seq")
+    amplicon = refs[PE_REF]["sequence"]
+    scaffold_dna = reverse_complement(scaf.upper().replace("U", "T"))
+    ext_dna = reverse_complement(ext.upper().replace("U", "T"))
+    loc = amplicon.index(ext_dna) + len(ext_dna)
+    k = int(getattr(args, "prime_editing_pegRNA_scaffold_min_match_length", 1))
+    while ext_dna + scaffold_dna[:k] in amplicon:
+        if k > len(scaffold_dna):
+            raise ValueError("The DNA scaffold provided is found in the unedited reference sequence. "
+                             "Please provide a longer scaffold sequence.")
+        k += 1
+    return loc, scaffold_dna[:k]
+
+
+def scaffold_hits(res, pe_idx, loc, seq, block=32768):
+    """Reads of a batch that the scaffold step of get_new_variant_object re-labels (CRISPRessoCORE.py:789-796): 'Prime-edited'
+    among the best references, and the read's aligned string carrying `seq` right after the column of prime-edited position
+    loc - 1.  Vectorised over the aligned strings (rebuilt from the op streams block by block).  -> bool [n]"""
+    n = len(res.recs)
+    out = np.zeros(n, dtype=bool)
+    cand = ((res.recs["winner_mask"].astype(np.int64) >> pe_idx) & 1).astype(bool) & (res.recs["best_score_milli"] > 0)
+    if not cand.any():
+        return out
+    W, k = res.W, len(seq)
+    want = np.frombuffer(seq.encode(), dtype=np.uint8)
+    cols = np.arange(W, dtype=np.int32)
+    for lo in range(0, n, block):
+        hi = min(n, lo + block)
+        idx = np.nonzero(cand[lo:hi])[0]
+        if not len(idx):
+            continue
+        S = res.strings_block(lo, hi)[idx, pe_idx]                       # [m, 2, W], right-aligned
+        alen = res.alns["aln_len"][lo:hi][idx, pe_idx].astype(np.int32)
+        base = (S[:, 1, :] != ord("-")) & (cols[None, :] >= (W - alen)[:, None])
+        here = base & (np.cumsum(base, axis=1, dtype=np.int32) == loc)
+        at = np.argmax(here, axis=1) + 1                                  # ref_positions.index(loc - 1) + 1
+        ok = here.any(axis=1) & (at + k <= W)
+        take = np.minimum(at[:, None] + np.arange(k, dtype=np.int64)[None, :], W - 1)
+        got = np.take_along_axis(S[:, 0, :], take, axis=1)
+        out[lo + idx] = ok & (got == want[None, :]).all(axis=1)
+    return out
 
 
 def get_engine(device=0, lib_path=None):
@@ -190,6 +243,18 @@ def _variant_from(res, i, seq, ref_names, refs):
             v["aln_ref_names"] = [ref_names[winners[0]]]
         elif not (res_flags(res) & _lib.F_EXPAND_AMBIGUOUS):
             v["class_name"] = "AMBIGUOUS"
+    sc = getattr(res, "scaffold", None)
+    if sc is not None and any(ref_names[r] == PE_REF for r in winners):     # CRISPRessoCORE.py:789-796
+        from copy import deepcopy
+        loc, seq = sc
+        pe = v["variant_" + PE_REF]
+        at = pe.ref_positions.index(loc - 1) + 1
+        if pe.aln_seq[at:at + len(seq)] == seq:
+            v["aln_ref_names"] = [SCAFFOLD_REF]
+            v["class_name"] = SCAFFOLD_REF
+            old = deepcopy(pe)
+            old.ref_name = SCAFFOLD_REF
+            v["variant_" + SCAFFOLD_REF] = old
     return v
 
 
@@ -244,6 +309,59 @@ def align_uniques(engine, uniques, counts, ref_names, refs, flags, weights=None,
         k = int(np.nonzero(hard)[0][0])
         raise EngineError("read %d outside the engine's contract: status %d" % (k, int(st[k])))
     return res, weights
+
+
+def _subset(buf, off, idx):
+    lens = (off[idx + 1] - off[idx]).astype(np.int64)
+    o2 = np.zeros(len(idx) + 1, dtype=np.int64)
+    np.cumsum(lens, out=o2[1:])
+    b2 = np.concatenate([buf[off[k]:off[k + 1]] for k in idx.tolist()]) if len(idx) else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(b2), o2
+
+
+def _batch(engine, buf, off, counts, weights, ref_names, refs, flags, args, aln_matrix, scaffold):
+    """The batch over (a slice of) the unique reads.  -> (BatchResult, scaffold extra or None).
+    Prime editing with a scaffold sequence (CRISPRessoCORE.py:789-796): reads the scaffold step re-labels count under the
+    extra reference 'Scaffold-incorporated' with their alignment to the prime-edited amplicon, whatever else they tied with.
+    All of it stays on the device, as further passes of the same kernels:
+      1. the batch as usual; scaffold_hits() picks the re-labelled reads H out of the aligned strings;
+      A. H alone, every read bound to the prime-edited amplicon (the per-read reference id of Pooled batches): that
+         amplicon's segment of the count block is the new reference's segment;
+      B. H alone, bound to reference 0 with no score threshold and no --discard_indel_reads: reference 0's all_* rows are what
+         the HDR / prime-editing re-projection (:4226-4272) adds for the new reference;
+      2. the batch again with H's weights at zero: the block of the ordinary references."""
+    res, _ = align_uniques(engine, None, counts, ref_names, refs, flags, weights=weights, packed=(buf, off), compact=True)
+    if scaffold is None:
+        return res, None
+    loc, seq = scaffold
+    pe_idx = list(ref_names).index(PE_REF)
+    res.scaffold = scaffold
+    hits = res._scaffold_hits = scaffold_hits(res, pe_idx, loc, seq)
+    extra = {"rawA": None, "rawB": None, "weight": 0, "pe_idx": pe_idx}
+    if not hits.any():
+        return res, extra
+    idx = np.nonzero(hits)[0]
+    bS, oS = _subset(buf, off, idx)
+    wS = np.ascontiguousarray(np.asarray(weights, dtype=np.int32)[idx])
+    zero = np.zeros(len(idx), dtype=np.int32)
+    engine.counts_reset()
+    engine.align_packed(bS, oS, count=zero, qweight=wS, ref_id=np.full(len(idx), pe_idx, dtype=np.int32), compact=True)
+    extra["rawA"] = engine.counts_raw()
+    refs_b = dict(refs)
+    refs_b[ref_names[0]] = dict(refs[ref_names[0]], min_aln_score=-1.0)
+    engine.configure(refs_b, ref_names, aln_matrix, args.needleman_wunsch_gap_open, args.needleman_wunsch_gap_extend,
+                     args.aln_seed_count, args.aln_seed_min, flags & ~_lib.F_DISCARD_INDEL_READS, "ACGTN", engine.edit_cap)
+    engine.counts_reset()
+    engine.align_packed(bS, oS, count=zero, qweight=wS, ref_id=np.zeros(len(idx), dtype=np.int32), compact=True)
+    extra["rawB"] = engine.counts_raw()
+    extra["weight"] = int(wS.astype(np.int64).sum())
+    configure_engine(engine, args, refs, ref_names, aln_matrix)
+    engine.counts_reset()
+    w2 = np.array(weights, dtype=np.int32)
+    w2[hits] = 0
+    res, _ = align_uniques(engine, None, counts, ref_names, refs, flags, weights=w2, packed=(buf, off), compact=True)
+    res.scaffold, res._scaffold_hits = scaffold, hits
+    return res, extra
 
 
 def _complete_edit_lists(engine, res, buf, off, flags, ref_id=None):
@@ -382,6 +500,7 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
     t_start = time.perf_counter()
     n = len(off) - 1
     flags = _flags(args)
+    scaffold = scaffold_search(args, refs)
     configure_engine(engine, args, refs, ref_names, aln_matrix)
     engine.counts_reset()
     bad = screen_reads(buf, off, lib_path=engine.lib_path) if n else np.zeros(0, dtype=bool)
@@ -421,7 +540,7 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
 
         def batch():
             try:
-                box["res"] = align_uniques(engine, None, counts_g, ref_names, refs, flags, weights=weights, packed=(buf_g, off_g), compact=True)[0]
+                box["res"], box["extra"] = _batch(engine, buf_g, off_g, counts_g, weights, ref_names, refs, flags, args, aln_matrix, scaffold)
             except BaseException as ex:                     # noqa: BLE001 -- re-raised on the calling thread
                 box["err"] = ex
 
@@ -431,7 +550,7 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
         th.join()
         if "err" in box:
             raise box["err"]
-        res = box["res"]
+        res, sc_extra = box["res"], box["extra"]
         parts = [(0, res, _complete_edit_lists(engine, res, buf_g, off_g, flags))]
         raw = None
     else:
@@ -441,13 +560,22 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         lo, hi = cdist.shard_bounds(ng, rank, world)
         mine = None
+        sc_extra = None
         if hi > lo:
             b0, b1 = int(off_g[lo]), int(off_g[hi])
             sb, so = np.ascontiguousarray(buf_g[b0:b1]), np.ascontiguousarray(off_g[lo:hi + 1] - b0)
-            res, _ = align_uniques(engine, None, counts_g[lo:hi], ref_names, refs, flags, weights=weights[lo:hi], packed=(sb, so), compact=True)
+            res, sc_extra = _batch(engine, sb, so, counts_g[lo:hi], weights[lo:hi], ref_names, refs, flags, args, aln_matrix, scaffold)
             fix = _complete_edit_lists(engine, res, sb, so, flags)
             mine = {"lo": lo, "res": _result_arrays(res), "fix": {k: (_result_arrays(r2), j) for k, (r2, j) in fix.items()}}
         raw = cdist.allreduce_counts(engine, group)          # the path's one collective on device data
+        if scaffold is not None:                             # the scaffold reference's segments: summed over ranks like the block
+            size = len(raw)
+            sc_extra = sc_extra or {"rawA": None, "rawB": None, "weight": 0, "pe_idx": list(ref_names).index(PE_REF)}
+            both = np.zeros(2 * size + 1, dtype=np.int64)
+            if sc_extra["rawA"] is not None:
+                both[:size], both[size:2 * size], both[-1] = sc_extra["rawA"], sc_extra["rawB"], sc_extra["weight"]
+            both = cdist.allreduce_array(both, engine, group)
+            sc_extra = dict(sc_extra, rawA=both[:size], rawB=both[size:2 * size], weight=int(both[-1]))
         gathered = [None] * world
         dist.all_gather_object(gathered, mine, group=group)
         parts = []
@@ -469,6 +597,15 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
     extra = {}
     for lo, res, _fx in parts:
         hi = lo + len(res.recs)
+        w_part = weights[lo:hi]
+        if scaffold is not None:                            # re-labelled reads carry the scaffold class, nothing else
+            res.scaffold = scaffold
+            for r2, _j in _fx.values():
+                r2.scaffold = scaffold
+            h = getattr(res, "_scaffold_hits", None)
+            if h is None:
+                h = scaffold_hits(res, list(ref_names).index(PE_REF), scaffold[0], scaffold[1])
+            w_part = np.where(h, 0, w_part)
         s1, al = _serial_stats(res, counts_g[lo:hi], lib_path=engine.lib_path)
         aligned[lo:hi] = al
         for key, val in s1.items():
@@ -476,7 +613,7 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
                 st[key] = st[key] or val
             else:
                 st[key] += val
-        for lab, val in _joined_classes(res, weights[lo:hi], ref_names, flags).items():
+        for lab, val in _joined_classes(res, w_part, ref_names, flags).items():
             extra[lab] = extra.get(lab, 0) + val
     if n_bad:
         cb = int(counts[bad].sum())
@@ -484,7 +621,7 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
         st["N_COMPUTED_NOTALN"] += n_bad
         st["N_CACHED_NOTALN"] += cb - n_bad
     src = lazy.BatchSource(None, keys_g, ref_names, refs, counts_g, parts=parts)
-    src.weights, src.flags, src.lib_path = weights, flags, engine.lib_path
+    src.weights, src.flags, src.lib_path, src.scaffold = weights, flags, engine.lib_path, scaffold
     _sources[id(variantCache)] = src
     cls = src.lazy_class()
     not_aligned = {}
@@ -498,11 +635,15 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
             not_aligned[keys[k]] = {"count": int(counts[k]), "aln_scores": [], "ref_aln_details": [], "best_match_score": -1}
             variantCache.pop(keys[k], None)
     block = engine.counts(raw=raw)
+    if scaffold is not None:
+        block.add_scaffold_reference(SCAFFOLD_REF, refs[PE_REF]["sequence"], sc_extra["pe_idx"], sc_extra["rawA"], sc_extra["rawB"],
+                                     sc_extra["weight"])
     dev = block.aln_stats_partial()                         # the kernel's own sums must agree with the records
     for key, val in dev.items():
         if val != st[key]:
             raise EngineError("device aln_stats disagree with per-read records for %s: %d != %d" % (key, val, st[key]))
-    block.class_extra = extra
+    for lab, val in extra.items():
+        block.class_extra[lab] = block.class_extra.get(lab, 0) + val
     _blocks[id(variantCache)] = block
     last_timings["stats_cache"] = time.perf_counter() - t_tab
     return st, not_aligned
@@ -560,4 +701,6 @@ def get_new_variant_object(args, fastq_seq, refs, ref_names, aln_matrix, pe_scaf
     configure_engine(engine, args, refs, ref_names, aln_matrix, edit_cap=max(len(refs[r]["sequence"]) for r in ref_names)
                      + len(fastq_seq) + 1)
     res, _ = align_uniques(engine, [fastq_seq], [1], ref_names, refs, _flags(args), weights=[0])
+    if getattr(args, "prime_editing_pegRNA_scaffold_seq", ""):
+        res.scaffold = tuple(pe_scaffold_dna_info)
     return _variant_from(res, 0, fastq_seq, ref_names, refs)

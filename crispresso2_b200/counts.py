@@ -15,6 +15,7 @@ class CountBlock:
         self.n_vec, self.stride, self.n_scal = n_vec, stride, n_scal
         self.n_hist, self.hstride, self.hist_zero, self.flags = n_hist, hstride, hist_zero, flags
         self.class_extra = {}         # joined class labels of --expand_ambiguous_alignments reads (core.process_fastq)
+        self.class_whole = set()      # references whose reads carry the bare reference name as class ('Scaffold-incorporated')
         nv, nh = n_vec * stride, n_hist * hstride
         per = nv + nh + n_scal
         self._vec, self._scal, self._hist = {}, {}, {}
@@ -23,6 +24,36 @@ class CountBlock:
             self._vec[name] = blk[:nv].reshape(n_vec, stride)
             self._hist[name] = blk[nv:nv + nh].reshape(n_hist, hstride)
             self._scal[name] = blk[nv + nh:]
+
+    def add_scaffold_reference(self, name, seq, pe_idx, raw_a, raw_b, weight):
+        """Prime editing with a scaffold sequence: appends the reference the scaffold step of get_new_variant_object assigns
+        reads to (CRISPRessoCORE.py:789-796, :3759-3764).  raw_a: block of the re-labelled reads bound to the prime-edited
+        amplicon (segment pe_idx becomes the new segment); raw_b: block of the same reads bound to reference 0 (its all_* rows
+        are the new segment's re-projection onto reference 0, :4226-4272); None, None = no such read."""
+        nv, nh = self.n_vec * self.stride, self.n_hist * self.hstride
+        per = nv + nh + self.n_scal
+        seg = np.zeros(per, dtype=np.int64)
+        if raw_a is not None:
+            seg[:] = np.asarray(raw_a, dtype=np.int64)[pe_idx * per:(pe_idx + 1) * per]
+            b = np.asarray(raw_b, dtype=np.int64)[:per]
+            va, vb = seg[:nv].reshape(self.n_vec, self.stride), b[:nv].reshape(self.n_vec, self.stride)
+            for dst, src in ((_lib.V_R1_ALL_INS, _lib.V_ALL_INS), (_lib.V_R1_ALL_INS_LEFT, _lib.V_ALL_INS_LEFT),
+                             (_lib.V_R1_ALL_DEL, _lib.V_ALL_DEL), (_lib.V_R1_ALL_SUB, _lib.V_ALL_SUB)):
+                va[dst] = vb[src]
+            for q in range(len(self.alphabet) + 1):
+                va[_lib.V_R1_BASEDEV0 + q] = vb[_lib.V_BASEDEV0 + q]
+            seg[nv + nh + _lib.S["REF1_W"]] = b[nv + nh + _lib.S["TOTAL"]]
+        self.raw = np.concatenate([np.asarray(self.raw, dtype=np.int64), seg])
+        k = len(self.ref_names)
+        self.ref_names.append(name)
+        self.ref_seqs.append(seq)
+        blk = self.raw[k * per:(k + 1) * per]
+        self._vec[name] = blk[:nv].reshape(self.n_vec, self.stride)
+        self._hist[name] = blk[nv:nv + nh].reshape(self.n_hist, self.hstride)
+        self._scal[name] = blk[nv + nh:]
+        self.class_whole.add(name)
+        if weight:
+            self.class_extra[name] = self.class_extra.get(name, 0) + int(weight)
 
     def scalar(self, ref, name):
         return int(self._scal[ref][_lib.S[name]])
@@ -46,6 +77,8 @@ class CountBlock:
         out = {}
         amb = 0
         for r in self.ref_names:
+            if r in self.class_whole:
+                continue
             for lab, key, base in (("_MODIFIED", "CLASS_MODIFIED", "MODIFIED"), ("_UNMODIFIED", "CLASS_UNMODIFIED", "UNMODIFIED")):
                 v = self.scalar(r, base) + self.scalar(r, key)          # counts_* plus the signed deviation (c2b200.h)
                 if v:

@@ -43,3 +43,18 @@ def allreduce_counts(engine, group=None):
     t = torch.from_numpy(engine.counts_raw())
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.numpy()
+
+
+def allreduce_array(arr, engine, group=None):
+    """Sum of an int64 host array over the ranks (NCCL through a tensor on the engine's GPU, gloo on the host)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return arr
+    if dist.get_backend(group) == "nccl":
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to("cuda:%d" % engine.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.cpu().numpy()
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64).copy())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.numpy()

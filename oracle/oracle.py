@@ -11,8 +11,9 @@ What is restated here (reference file:line, all under /root/reference):
   global_align                   CRISPResso2/CRISPResso2Align.pyx:101-434   (C: c2o_global_align)
   find_indels_substitutions      CRISPResso2/CRISPRessoCOREResources.pyx:68-187 (C: c2o_find_indels)
   reverse_complement             CRISPResso2/CRISPRessoShared.py:399-403
-  new_variant                    CRISPResso2/CRISPRessoCORE.py:627-798  (get_new_variant_object, minus the
+  new_variant                    CRISPResso2/CRISPRessoCORE.py:627-798  (get_new_variant_object, incl. the
                                  prime-editing scaffold branch :789-796 and the legacy insertion switch)
+  pe_scaffold_search             CRISPResso2/plots/data_prep.py:3827-3860 (get_pe_scaffold_search)
   process_reads                  CRISPResso2/CRISPRessoCORE.py:1956-2000 (serial branch of process_fastq)
   count_vectors                  CRISPResso2/CRISPRessoCORE.py:3964-4181 (vectors, counters, the size Counters and the
                                  --coding_seq frameshift / splicing block), pinned against the reference's own
@@ -302,7 +303,28 @@ def _strand_choice(params, seq, ref):
     return "both"
 
 
-def new_variant(params, seq, refs, ref_names, matrix):
+def pe_scaffold_search(params, refs):
+    """(scaffold start in the prime-edited amplicon, shortest telling scaffold prefix) -- plots/data_prep.py:3827-3860, called
+    by process_fastq at CRISPRessoCORE.py:1814-1816; (0, None) without a scaffold sequence."""
+    scaf = getattr(params, "prime_editing_pegRNA_scaffold_seq", "") or ""
+    ext = getattr(params, "prime_editing_pegRNA_extension_seq", "") or ""
+    if not scaf or not ext:
+        return (0, None)
+    pe = refs["Prime-edited"]["sequence"]
+    sdna = reverse_complement(scaf.upper().replace("U", "T"))
+    edna = reverse_complement(ext.upper().replace("U", "T"))
+    start = pe.index(edna) + len(edna)
+    n = getattr(params, "prime_editing_pegRNA_scaffold_min_match_length", 1)
+    probe = edna + sdna[0:n]
+    while probe in pe:
+        if n > len(sdna):
+            raise ValueError("scaffold found in the unedited reference sequence")
+        n += 1
+        probe = edna + sdna[0:n]
+    return (start, sdna[0:n])
+
+
+def new_variant(params, seq, refs, ref_names, matrix, pe_scaffold_dna_info=(0, None)):
     """Payload for one unique read (CRISPRessoCORE.py:627-798)."""
     go, ge = params.needleman_wunsch_gap_open, params.needleman_wunsch_gap_extend
     scores, details = [], []
@@ -371,6 +393,17 @@ def new_variant(params, seq, refs, ref_names, matrix):
             out["aln_ref_names"] = [winners[0][0]]
         elif not params.expand_ambiguous_alignments:
             out["class_name"] = "AMBIGUOUS"
+    if getattr(params, "prime_editing_pegRNA_scaffold_seq", "") and "Prime-edited" in [w[0] for w in winners]:     # :789-796
+        import copy
+        loc, probe = pe_scaffold_dna_info
+        pe = out["variant_Prime-edited"]
+        at = pe["ref_positions"].index(loc - 1) + 1
+        if pe["aln_seq"][at:at + len(probe)] == probe:
+            out["aln_ref_names"] = ["Scaffold-incorporated"]
+            out["class_name"] = "Scaffold-incorporated"
+            moved = copy.deepcopy(pe)
+            moved["ref_name"] = "Scaffold-incorporated"
+            out["variant_Scaffold-incorporated"] = moved
     return out
 
 
@@ -386,10 +419,11 @@ def process_reads(read_iter, refs, ref_names, params, matrix):
                         "N_GLOBAL_SUBS", "N_SUBS_OUTSIDE_WINDOW", "N_MODS_IN_WINDOW", "N_MODS_OUTSIDE_WINDOW",
                         "N_READS_IRREGULAR_ENDS", "READ_LENGTH"], 0)
     lost = {}
+    info = pe_scaffold_search(params, refs)
     for s in list(cache.keys()):
         c = cache[s]
         st["N_TOT_READS"] += c
-        v = new_variant(params, s, refs, ref_names, matrix)
+        v = new_variant(params, s, refs, ref_names, matrix, info)
         v["count"] = c
         if v["best_match_score"] <= 0:
             st["N_COMPUTED_NOTALN"] += 1

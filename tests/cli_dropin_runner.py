@@ -44,7 +44,7 @@ def main():
         def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory):
             out = bound(fastq_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory)
             state["block"] = core.quantify(variantCache)
-            state["ref_names"] = list(ref_names)
+            state["ref_names"] = list(state["block"].ref_names)      # prime editing with a scaffold: + 'Scaffold-incorporated'
             return out
 
         CORE.process_fastq = process_fastq

@@ -51,7 +51,8 @@ FANC_HDR = ("CGGCCGGATGTTCCAATCAGTACGCAGAGAGTCGCCGTCTCCAAGGTGAAAGCTGAAGTAGGGCCTT
 
 PARAM_KEYS = ["aln_seed_count", "aln_seed_min", "needleman_wunsch_gap_open", "needleman_wunsch_gap_extend",
               "ignore_substitutions", "ignore_insertions", "ignore_deletions",
-              "assign_ambiguous_alignments_to_first_reference", "expand_ambiguous_alignments", "discard_indel_reads"]
+              "assign_ambiguous_alignments_to_first_reference", "expand_ambiguous_alignments", "discard_indel_reads",
+              "prime_editing_pegRNA_extension_seq", "prime_editing_pegRNA_scaffold_seq", "prime_editing_pegRNA_scaffold_min_match_length"]
 
 
 def _plain(o):
@@ -218,8 +219,24 @@ def alignment_vectors():
     print("align_vectors", len(cases))
 
 
+def pe_scaffold_case():
+    """prime editing with a scaffold sequence: 'Scaffold-incorporated' re-labelling (CRISPRessoCORE.py:789-796, :3759-3764)"""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import pe_case
+    fq = os.path.join(tempfile.gettempdir(), "c2gold_pe.fastq")
+    ext, scaffold = pe_case.write_fastq(fq, FANC)
+    rec, rd, work = run_case("fanc_pe_scaffold", ["-r1", fq, "-a", FANC, "--prime_editing_pegRNA_spacer_seq", pe_case.SPACER,
+                                                  "--prime_editing_pegRNA_extension_seq", ext, "--prime_editing_pegRNA_scaffold_seq", scaffold],
+                             KEEP)
+    assert any(v.get("class_name") == "Scaffold-incorporated" for v in rec["variants"].values())
+    shutil.rmtree(work)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["fanc_pe_scaffold"]:
+        pe_scaffold_case()
+        return
     alignment_vectors()
 
     fanc_fq = "/root/reference/tests/FANC.Cas9.fastq"
@@ -260,6 +277,7 @@ def main():
     synth.write_fastq(fq2, allr)
     rec, rd, work = run_case("synth_hdr", ["-r1", fq2, "-a", amp, "-g", amp[110:130], "-e", hdr], KEEP)
     shutil.rmtree(work)
+    pe_scaffold_case()
 
 
 if __name__ == "__main__":

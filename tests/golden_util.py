@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["fanc_cas9", "fanc_params", "synth_single", "synth_hdr"]
+CASES = ["fanc_cas9", "fanc_params", "synth_single", "synth_hdr", "fanc_pe_scaffold"]
 
 
 def load(name):

@@ -27,12 +27,13 @@ def edits_canonical(res, r=0):
 def args_from(params):
     a = types.SimpleNamespace(**params)
     a.use_legacy_insertion_quantification = bool(params.get("use_legacy_insertion_quantification", False))
-    a.prime_editing_pegRNA_scaffold_seq = ""
+    a.prime_editing_pegRNA_scaffold_seq = params.get("prime_editing_pegRNA_scaffold_seq", "") or ""
     a.needleman_wunsch_aln_matrix_loc = "EDNAFULL"
     a.n_processes = "1"
     if not hasattr(a, "expected_hdr_amplicon_seq"):
         a.expected_hdr_amplicon_seq = ""
-    a.prime_editing_pegRNA_extension_seq = ""
+    a.prime_editing_pegRNA_extension_seq = params.get("prime_editing_pegRNA_extension_seq", "") or ""
+    a.prime_editing_pegRNA_scaffold_min_match_length = params.get("prime_editing_pegRNA_scaffold_min_match_length", 1)
     return a
 
 
@@ -53,7 +54,7 @@ def check_alleles(engine, case, tmp_path):
         for k, s in enumerate(rec["reads"]):
             fh.write("@r%d\n%s\n+\n%s\n" % (k, s, "I" * len(s)))
     args = args_from(rec["params"])
-    if rec.get("ref1", {}).get("ref1_all_deletion_count_vectors"):
+    if rec.get("ref1", {}).get("ref1_all_deletion_count_vectors") and not args.prime_editing_pegRNA_extension_seq:
         args.expected_hdr_amplicon_seq = refs[rec["ref_names"][1]]["sequence"]
     cache = {}
     core.process_fastq(str(fq), cache, rec["ref_names"], refs, args, [], str(tmp_path), engine=engine, aln_matrix=O.make_matrix())
@@ -101,7 +102,7 @@ def check_golden_case(engine, case, tmp_path, max_reads=None):
             fh.write("@r%d\n%s\n+\n%s\n" % (k, s, "I" * len(s)))
     args = args_from(rec["params"])
     hdr = bool(rec.get("ref1", {}).get("ref1_all_deletion_count_vectors"))
-    if hdr:
+    if hdr and not args.prime_editing_pegRNA_extension_seq:
         args.expected_hdr_amplicon_seq = refs[rec["ref_names"][1]]["sequence"]
     cache = {}
     stats, lost = core.process_fastq(str(fq), cache, rec["ref_names"], refs, args, [], str(tmp_path), engine=engine,
@@ -125,8 +126,14 @@ def check_golden_case(engine, case, tmp_path, max_reads=None):
     if max_reads is not None:
         return
     block = core.quantify(cache)
-    for r in rec["ref_names"]:
-        seq = refs[r]["sequence"]
+    if args.prime_editing_pegRNA_scaffold_seq:              # the reference appended by main() after process_fastq (:3759-3764)
+        assert block.ref_names == rec["ref_names"] + ["Scaffold-incorporated"]
+        assert any(v["class_name"] == "Scaffold-incorporated" for v in cache.values())
+    want_classes = {}
+    for s, v in rec["variants"].items():                    # counts as process_fastq left them; the rc merge moves none across classes here
+        want_classes[v["class_name"]] = want_classes.get(v["class_name"], 0) + v["count"]
+    assert block.class_counts() == want_classes
+    for r, seq in zip(block.ref_names, block.ref_seqs):
         V = block.vectors(r)
         tot = block.scalar(r, "TOTAL")
         assert G.mod_count_text(seq, V, tot) == G.file_for(rec, r, "Modification_count_vectors.txt")

@@ -66,7 +66,7 @@ def _info_stats(outdir):
     return info["results"]["alignment_stats"]
 
 
-def _cases():
+def _cases(tmp=None):
     with open(os.path.join(HERE, "golden", "gen_golden.py")) as fh:
         src = fh.read()
     ns = {}
@@ -76,7 +76,17 @@ def _cases():
         exec(src[start:end], ns)
     fq = "/root/reference/tests/FANC.Cas9.fastq"
     g = "GGAATCCCTTCTGCAGCACC"
+    pe = []
+    if tmp is not None:
+        pe_fq = os.path.join(str(tmp), "pe_scaffold.fastq")
+        import pe_case
+        ext, scaffold = pe_case.write_fastq(pe_fq, ns["FANC"])
+        pe = ["-r1", pe_fq, "-a", ns["FANC"], "--prime_editing_pegRNA_spacer_seq", g, "--prime_editing_pegRNA_extension_seq", ext,
+              "--prime_editing_pegRNA_scaffold_seq", scaffold, "--write_detailed_allele_table"]
     return {
+        # CRISPRessoCORE.py:789-796: reads with the pegRNA scaffold after the extension move to 'Scaffold-incorporated'
+        "fanc_pe_scaffold": pe,
+        "fanc_pe_scaffold_discard": pe + ["--discard_indel_reads", "--expand_ambiguous_alignments"],
         "fanc_default": ["-r1", fq, "-a", ns["FANC"], "-g", g, "--write_detailed_allele_table"],
         "fanc_params": ["-r1", fq, "-a", ns["FANC"], "-g", g, "-e", ns["FANC_HDR"],
                         "-c", "GGGCCTTCGCGCACCTCATGGAATCCCTTCTGCAGCACCTGGATCGCTTTT", "--dump", "-qwc", "20-30_45-50",
@@ -92,11 +102,12 @@ def _cases():
     }
 
 
-@pytest.mark.parametrize("case", ["fanc_default", "fanc_params", "fanc_flags", "fanc_fastq_output", "fanc_legacy"])
+@pytest.mark.parametrize("case", ["fanc_default", "fanc_params", "fanc_flags", "fanc_fastq_output", "fanc_legacy", "fanc_pe_scaffold",
+                                  "fanc_pe_scaffold_discard"])
 def test_reference_cli_with_engine_process_fastq_is_byte_identical(case, tmp_path):
     import build_emu
     lib = build_emu.build()
-    argv = _cases()[case]
+    argv = _cases(tmp_path)[case]
     ref_dir, b200_dir = str(tmp_path / "ref"), str(tmp_path / "b200")
     _run("reference", "default", ref_dir, argv)
     rep = _run("b200", lib, b200_dir, argv)

@@ -21,7 +21,7 @@ def emu():
     return Engine(lib_path=build_emu.build())
 
 
-@pytest.mark.parametrize("case", ["fanc_cas9", "fanc_params", "synth_hdr"])
+@pytest.mark.parametrize("case", ["fanc_cas9", "fanc_params", "synth_hdr", "fanc_pe_scaffold"])
 def test_golden_whole_path(emu, case, tmp_path):
     PU.check_golden_case(emu, case, tmp_path)
 

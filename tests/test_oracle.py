@@ -88,8 +88,13 @@ def test_whole_path_golden(case, ednafull):
         for r in want["aln_ref_names"]:
             bad = G.payload_equal(want["variant_" + r], got["variant_" + r])
             assert not bad, (s, r, bad)
-    vec, sca, classes, total = O.count_vectors(cache, refs, rec["ref_names"], params)
-    for r in rec["ref_names"]:
+    names = list(rec["ref_names"])
+    if rec["params"].get("prime_editing_pegRNA_scaffold_seq"):          # the reference main() appends after process_fastq (:3759-3764)
+        names.append("Scaffold-incorporated")
+        refs["Scaffold-incorporated"] = dict(refs["Prime-edited"])
+        assert any(v["class_name"] == "Scaffold-incorporated" for v in cache.values())
+    vec, sca, classes, total = O.count_vectors(cache, refs, names, params)
+    for r in names:
         seq = refs[r]["sequence"]
         assert G.mod_count_text(seq, vec[r], sca[r]["counts_total"]) == G.file_for(rec, r, "Modification_count_vectors.txt")
         assert G.qw_count_text(seq, vec[r], sca[r]["counts_total"]) == G.file_for(
