@@ -1,7 +1,7 @@
 """Worker for tests/test_dist_gloo.py (gloo, CPU, emulator build of the engine) and tests/test_gpu_dist.py (nccl, one GPU per
 rank, sm_100a library, NO explicit engine: every rank must pick the GPU named by LOCAL_RANK): world_size ranks run
 core.process_fastq_sharded on the same FASTQ; rank 0 writes what it returned.
-usage: dist_worker2.py <fastq> <out.json> [gloo|nccl]"""
+usage: dist_worker2.py <fastq> <out.json> [gloo|nccl] [golden case]"""
 import json
 import os
 import sys
@@ -31,10 +31,12 @@ def main():
     else:
         dist.init_process_group("gloo")
     rank = dist.get_rank()
-    rec = G.load("synth_hdr")
+    case = sys.argv[4] if len(sys.argv) > 4 else "synth_hdr"
+    rec = G.load(case)
     refs = G.refs_from(rec)
     args = PU.args_from(rec["params"])
-    args.expected_hdr_amplicon_seq = refs[rec["ref_names"][1]]["sequence"]
+    if not args.prime_editing_pegRNA_extension_seq:
+        args.expected_hdr_amplicon_seq = refs[rec["ref_names"][1]]["sequence"]
     eng = Engine(lib_path=build_emu.build()) if backend == "gloo" else None       # nccl: the default engine of the rank's own GPU
     cache = {}
     stats, lost = core.process_fastq_sharded(fq, cache, rec["ref_names"], refs, args, [], os.path.dirname(out_path),
@@ -45,7 +47,7 @@ def main():
                    "classes": {s: v["class_name"] for s, v in cache.items()},
                    "payload_ok": all(not G.payload_equal(rec["variants"][s]["variant_" + r], cache[s]["variant_" + r])
                                      for s in cache for r in rec["variants"][s]["aln_ref_names"]),
-                   "vec": {r: {k: v.tolist() for k, v in blk.vectors(r).items()} for r in rec["ref_names"]},
+                   "vec": {r: {k: v.tolist() for k, v in blk.vectors(r).items()} for r in blk.ref_names},
                    "class_counts": blk.class_counts()}
         with open(out_path, "w") as fh:
             json.dump(summary, fh)

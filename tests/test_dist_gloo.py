@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
 
@@ -51,12 +52,14 @@ def test_two_ranks_gloo_merge_matches_oracle(tmp_path):
         assert got["scalars"][name] == sca["Reference"][name], name
 
 
-def test_process_fastq_sharded_over_two_ranks_equals_single_process(tmp_path):
+@pytest.mark.parametrize("case", ["synth_hdr", "fanc_pe_scaffold"])
+def test_process_fastq_sharded_over_two_ranks_equals_single_process(tmp_path, case):
     """The drop-in process_fastq with unique reads sharded over 2 ranks (gloo; count block all-reduced, variants gathered):
-    every rank must hold what the reference's serial loop produces -- checked on the HDR golden fixture."""
+    every rank must hold what the reference's serial loop produces -- checked on the HDR golden fixture and on the prime-editing
+    one (the 'Scaffold-incorporated' segments are summed over ranks next to the block)."""
     import golden_util as G
     import parity_util as PU
-    rec = G.load("synth_hdr")
+    rec = G.load(case)
     fq = tmp_path / "hdr.fastq"
     with open(fq, "w") as fh:
         for k, s in enumerate(rec["reads"]):
@@ -64,7 +67,7 @@ def test_process_fastq_sharded_over_two_ranks_equals_single_process(tmp_path):
     out = tmp_path / "sharded.json"
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29534", os.path.join(ROOT, "tests", "dist_worker2.py"), str(fq), str(out)]
+           "--master-port", "29534", os.path.join(ROOT, "tests", "dist_worker2.py"), str(fq), str(out), "gloo", case]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     got = json.load(open(out))
@@ -74,7 +77,12 @@ def test_process_fastq_sharded_over_two_ranks_equals_single_process(tmp_path):
     assert got["classes"] == {s: v["class_name"] for s, v in rec["variants"].items()}
     assert got["payload_ok"]
     refs = G.refs_from(rec)
-    for rname in rec["ref_names"]:
+    names = list(rec["ref_names"])
+    if case == "fanc_pe_scaffold":
+        names.append("Scaffold-incorporated")
+        refs["Scaffold-incorporated"] = refs["Prime-edited"]
+        assert "Scaffold-incorporated" in got["class_counts"]
+    for rname in names:
         seq = refs[rname]["sequence"]
         V = {k: np.asarray(v) for k, v in got["vec"][rname].items()}
         tot = int(V["all_base_count_A"][0] + V["all_base_count_C"][0] + V["all_base_count_G"][0] + V["all_base_count_T"][0]
