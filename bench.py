@@ -340,6 +340,10 @@ def ingest_leg(reads):
         with open(small, "rb") as fi, gzip.open(gz, "wb", compresslevel=1) as fo:
             shutil.copyfileobj(fi, fo, 1 << 22)
 
+        bgz = os.path.join(d, "s_blocked.fastq.gz")
+        with open(small, "rb") as fi, open(bgz, "wb") as fo:
+            fo.write(synth.bgzf_bytes(fi.read()))
+
         def best(fn, reps=3):
             t = []
             for _ in range(reps):
@@ -348,12 +352,12 @@ def ingest_leg(reads):
                 t.append(time.perf_counter() - t0)
             return min(t), r
 
-        for name, path, n in (("dedup_plain", plain, len(reads)), ("dedup_gzip", gz, len(sub))):
+        for name, path, n in (("dedup_plain", plain, len(reads)), ("dedup_gzip", gz, len(sub)), ("dedup_blocked_gzip", bgz, len(sub))):
             dt, dd = best(lambda: fastq.dedup_file(path))
             assert dd.n_reads == n
             out[name] = {"reads": n, "unique": int(len(dd.counts)), "seconds": dt, "reads_per_s": n / dt,
                          "file_MB_per_s": os.path.getsize(path) / dt / 1e6}
-        for name, path, n in (("dedup_gpu_plain", plain, len(reads)), ("dedup_gpu_gzip", gz, len(sub))):
+        for name, path, n in (("dedup_gpu_plain", plain, len(reads)), ("dedup_gpu_gzip", gz, len(sub)), ("dedup_gpu_blocked_gzip", bgz, len(sub))):
             # the same front end on the GPU (c2b_fastq_dedup_gpu): file bytes over PCIe once, parse + exact dedup on the device
             dt, dg = best(lambda: fastq.dedup_file(path, device=_ingest_device()))
             hd = fastq.dedup_file(path)

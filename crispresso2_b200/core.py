@@ -294,14 +294,14 @@ def screen_reads(buf, off, lib_path=None):
     return out.astype(bool)
 
 
-def align_uniques(engine, uniques, counts, ref_names, refs, flags, weights=None, packed=None, compact=False):
+def align_uniques(engine, uniques, counts, ref_names, refs, flags, weights=None, packed=None, compact=False, on_launch=None):
     """One GPU batch over unique reads -> (BatchResult, merge weights).  `packed` = (bytes, offsets) of `uniques`
     when the caller already holds them in the engine's layout."""
     buf, off = packed if packed is not None else pack_reads(uniques)
     if weights is None:
         weights = merge_weights_packed(buf, off, counts, lib_path=engine.lib_path)
     res = engine.align_packed(buf, off, count=np.asarray(counts, dtype=np.int32), qweight=np.asarray(weights, dtype=np.int32),
-                              compact=compact)
+                              compact=compact, on_launch=on_launch)
     res.flags = flags
     st = res.recs["status"]
     hard = st & ~np.uint32(_lib.ST_EDIT_OVERFLOW)
@@ -319,7 +319,7 @@ def _subset(buf, off, idx):
     return np.ascontiguousarray(b2), o2
 
 
-def _batch(engine, buf, off, counts, weights, ref_names, refs, flags, args, aln_matrix, scaffold):
+def _batch(engine, buf, off, counts, weights, ref_names, refs, flags, args, aln_matrix, scaffold, on_launch=None):
     """The batch over (a slice of) the unique reads.  -> (BatchResult, scaffold extra or None).
     Prime editing with a scaffold sequence (CRISPRessoCORE.py:789-796): reads the scaffold step re-labels count under the
     extra reference 'Scaffold-incorporated' with their alignment to the prime-edited amplicon, whatever else they tied with.
@@ -330,7 +330,8 @@ def _batch(engine, buf, off, counts, weights, ref_names, refs, flags, args, aln_
       B. H alone, bound to reference 0 with no score threshold and no --discard_indel_reads: reference 0's all_* rows are what
          the HDR / prime-editing re-projection (:4226-4272) adds for the new reference;
       2. the batch again with H's weights at zero: the block of the ordinary references."""
-    res, _ = align_uniques(engine, None, counts, ref_names, refs, flags, weights=weights, packed=(buf, off), compact=True)
+    res, _ = align_uniques(engine, None, counts, ref_names, refs, flags, weights=weights, packed=(buf, off), compact=True,
+                           on_launch=on_launch)
     if scaffold is None:
         return res, None
     loc, seq = scaffold
@@ -537,15 +538,21 @@ def _process_uniques(engine, buf, off, counts, keys, variantCache, ref_names, re
         # the batch call spends its time inside the library (GIL released): the key strings are made meanwhile
         import threading
         box = {}
+        launched = threading.Event()                        # set when the batch thread is about to enter the library: key creation
+                                                            # holds the GIL in one long native call and would otherwise run FIRST
 
         def batch():
             try:
-                box["res"], box["extra"] = _batch(engine, buf_g, off_g, counts_g, weights, ref_names, refs, flags, args, aln_matrix, scaffold)
+                box["res"], box["extra"] = _batch(engine, buf_g, off_g, counts_g, weights, ref_names, refs, flags, args, aln_matrix,
+                                                  scaffold, on_launch=launched.set)
             except BaseException as ex:                     # noqa: BLE001 -- re-raised on the calling thread
                 box["err"] = ex
+            finally:
+                launched.set()
 
         th = threading.Thread(target=batch)
         th.start()
+        launched.wait()
         keys, keys_g = key_lists()
         th.join()
         if "err" in box:

@@ -22,6 +22,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <memory>
 #include <chrono>
 #include <cstdlib>
@@ -54,7 +55,7 @@ inline uint64_t hash_bytes(const uint8_t *p, size_t n)
     return h;
 }
 
-bool read_plain(const char *path, std::vector<uint8_t> &buf, std::string &err)
+bool read_plain(const char *path, c2b_bytes &buf, std::string &err)
 {
     FILE *f = fopen(path, "rb");
     if (!f) { err = std::string("cannot open ") + path; return false; }
@@ -69,8 +70,87 @@ bool read_plain(const char *path, std::vector<uint8_t> &buf, std::string &err)
     return true;
 }
 
-bool read_gz(const char *path, std::vector<uint8_t> &buf, std::string &err)
+// Blocked gzip (BGZF: what bgzip and Illumina's converters write): every member's header carries its compressed size in a 'BC'
+// extra subfield, so the members can be listed without inflating anything and inflated independently -- here by all host threads,
+// each member straight to its place in the output (the ISIZE trailers give the offsets).  Returns false without touching `buf`
+// when the file is not of that form (plain gzip: one stream, read_gz's serial path) or anything about it is inconsistent.
+bool read_bgzf(const char *path, c2b_bytes &buf)
 {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 28) { close(fd); return false; }
+    const size_t n = (size_t)st.st_size;
+    void *mp = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (mp == MAP_FAILED) return false;
+    const uint8_t *d = (const uint8_t *)mp;
+    struct Member { size_t data, clen, out; uint32_t isize, crc; };
+    std::vector<Member> mem;
+    size_t p = 0, total = 0;
+    bool ok = true;
+    while (p < n) {
+        if (n - p < 18 || d[p] != 0x1f || d[p + 1] != 0x8b || d[p + 2] != 8 || d[p + 3] != 4) { ok = false; break; }    // FLG = FEXTRA only
+        const size_t xlen = d[p + 10] | ((size_t)d[p + 11] << 8);
+        if (p + 12 + xlen > n) { ok = false; break; }
+        size_t bsize = 0, q = p + 12;
+        const size_t xe = q + xlen;
+        while (q + 4 <= xe) {
+            const size_t slen = d[q + 2] | ((size_t)d[q + 3] << 8);
+            if (d[q] == 'B' && d[q + 1] == 'C' && slen == 2 && q + 6 <= xe) bsize = (d[q + 4] | ((size_t)d[q + 5] << 8)) + 1;
+            q += 4 + slen;
+        }
+        if (bsize < 12 + xlen + 8 || p + bsize > n) { ok = false; break; }
+        Member m;
+        m.data = p + 12 + xlen;
+        m.clen = bsize - (12 + xlen) - 8;
+        const uint8_t *tr = d + p + bsize - 8;
+        m.crc = tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+        m.isize = tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
+        m.out = total;
+        total += m.isize;
+        mem.push_back(m);
+        p += bsize;
+    }
+    if (!ok || mem.empty()) { munmap(mp, n); return false; }
+    c2b_bytes out(total);
+    int T = (int)std::thread::hardware_concurrency();
+    T = std::max(1, std::min(T, 64));
+    if (mem.size() < 64) T = 1;
+    std::atomic<size_t> next(0);
+    std::atomic<bool> bad(false);
+    auto work = [&]() {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { bad.store(true); return; }
+        for (;;) {
+            const size_t k0 = next.fetch_add(16);
+            if (k0 >= mem.size() || bad.load()) break;
+            for (size_t k = k0; k < std::min(mem.size(), k0 + 16); k++) {
+                const Member &m = mem[k];
+                if (m.isize == 0 && m.clen <= 2) continue;                  // the empty end-of-file block
+                inflateReset(&zs);
+                zs.next_in = (Bytef *)(d + m.data); zs.avail_in = (uInt)m.clen;
+                zs.next_out = out.data() + m.out; zs.avail_out = m.isize;
+                const int rc = inflate(&zs, Z_FINISH);
+                if (rc != Z_STREAM_END || zs.avail_out != 0 || crc32(0L, out.data() + m.out, m.isize) != m.crc) { bad.store(true); break; }
+            }
+        }
+        inflateEnd(&zs);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work);
+    work();
+    for (auto &x : th) x.join();
+    munmap(mp, n);
+    if (bad.load()) return false;
+    buf.swap(out);
+    return true;
+}
+
+bool read_gz(const char *path, c2b_bytes &buf, std::string &err)
+{
+    if (read_bgzf(path, buf)) return true;
     gzFile g = gzopen(path, "rb");
     if (!g) { err = std::string("cannot open ") + path; return false; }
     gzbuffer(g, 1 << 20);
@@ -92,7 +172,7 @@ bool read_gz(const char *path, std::vector<uint8_t> &buf, std::string &err)
 
 static std::string g_fastq_err;
 
-bool c2b_fastq_read_gz(const char *path, std::vector<uint8_t> &buf, std::string &err) { return read_gz(path, buf, err); }
+bool c2b_fastq_read_gz(const char *path, c2b_bytes &buf, std::string &err) { return read_gz(path, buf, err); }
 void c2b_fastq_set_error(const std::string &m) { g_fastq_err = m; }
 
 extern "C" {
@@ -278,7 +358,7 @@ int c2b_fastq_dedup_buffer(const uint8_t *data, size_t n, int32_t n_threads, c2b
 int c2b_fastq_dedup(const char *path, int32_t n_threads, c2b_fastq **out)
 {
     if (!path || !out) return C2B_E_ARG;
-    std::vector<uint8_t> buf;
+    c2b_bytes buf;
     std::string err;
     const size_t L = strlen(path);
     const bool gz = L > 3 && strcmp(path + L - 3, ".gz") == 0;            // CRISPRessoCORE.py:1820
@@ -359,7 +439,7 @@ extern "C" int c2b_fastq_filter(const char *path_in, const char *path_out, int32
                                 int32_t min_bp_qual_or_N, int32_t n_threads, int64_t *n_in, int64_t *n_out)
 {
     if (!path_in || !path_out) return C2B_E_ARG;
-    std::vector<uint8_t> buf;
+    c2b_bytes buf;
     std::string err;
     const size_t Li = strlen(path_in), Lo = strlen(path_out);
     const bool gz_in = Li > 3 && strcmp(path_in + Li - 3, ".gz") == 0, gz_out = Lo > 3 && strcmp(path_out + Lo - 3, ".gz") == 0;
@@ -451,7 +531,7 @@ extern "C" int c2b_fastq_filter(const char *path_in, const char *path_out, int32
 // first, where numpy.min of an empty array raises (-> C2B_E_LIMIT here).
 namespace {
 
-bool load_lines(const char *path, std::vector<uint8_t> &buf, std::vector<Line> &lines, std::string &err)
+bool load_lines(const char *path, c2b_bytes &buf, std::vector<Line> &lines, std::string &err)
 {
     const size_t Lp = strlen(path);
     const bool gz = Lp > 3 && strcmp(path + Lp - 3, ".gz") == 0;
@@ -477,7 +557,7 @@ extern "C" int c2b_fastq_filter_pair(const char *path1_in, const char *path2_in,
                                      int32_t n_threads, int64_t *n_in, int64_t *n_out)
 {
     if (!path1_in || !path2_in || !path1_out || !path2_out) return C2B_E_ARG;
-    std::vector<uint8_t> buf1, buf2;
+    c2b_bytes buf1, buf2;
     std::vector<Line> l1, l2;
     std::string err;
     if (!load_lines(path1_in, buf1, l1, err) || !load_lines(path2_in, buf2, l2, err)) { g_fastq_err = "c2b_fastq_filter_pair: " + err; return C2B_E_ARG; }

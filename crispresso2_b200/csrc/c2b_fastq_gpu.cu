@@ -458,7 +458,7 @@ extern "C" int c2b_fastq_dedup_gpu(const char *path, int32_t device, c2b_fastq *
     *out = nullptr;
     const size_t L = strlen(path);
     if (L > 3 && strcmp(path + L - 3, ".gz") == 0) {          // gzip: one inflate stream on the host, then the same device passes
-        std::vector<uint8_t> buf;
+        c2b_bytes buf;
         std::string err;
         if (!c2b_fastq_read_gz(path, buf, err)) { c2b_fastq_set_error("c2b_fastq_dedup_gpu: " + err); return C2B_E_ARG; }
         Source src;

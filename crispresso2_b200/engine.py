@@ -170,7 +170,7 @@ class Engine:
         """a max_read_len that reproduces string width W (c2b_string_width rounds max_I + max_read_len up to 32)"""
         return max(1, W - max(self.ref_lens))
 
-    def align_packed(self, buf, off, count=None, qweight=None, ref_id=None, strings=True, edits=True, compact=False):
+    def align_packed(self, buf, off, count=None, qweight=None, ref_id=None, strings=True, edits=True, compact=False, on_launch=None):
         """One batch through the host-buffer entry.  compact=True: op streams + meta words come back instead of the aligned
         strings (c2b_align_batch_compact); BatchResult rebuilds strings for the reads somebody looks at."""
         n = len(off) - 1
@@ -192,6 +192,8 @@ class Engine:
         if compact:
             ops = np.zeros((n, nr, W // 32), dtype=np.uint64)
             meta = np.zeros((n, nr), dtype=np.uint32)
+            if on_launch is not None:                       # the call below releases the GIL: a waiting thread may take it now
+                on_launch()
             self._check(self.L.c2b_align_batch_compact(self.h, ptr(buf) if len(buf) else None, ptr(off), n, ptr(cnt), ptr(qw),
                                                        ptr(rid), ptr(recs), ptr(alns), ptr(ops), ptr(meta), ptr(earr)),
                         "c2b_align_batch_compact")

@@ -158,3 +158,19 @@ def mixed_length_reads(rng, amplicon, n_reads, lo=50, hi=300, cut=None):
     off = np.zeros(n_reads + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
     return base[np.arange(hi)[None, :] < lens[:, None]], off
+
+
+def bgzf_bytes(data, block=60000, level=1):
+    """`data` as blocked gzip (BGZF, what bgzip / Illumina's converters write): members of at most `block` input bytes whose
+    header carries the member's size in a 'BC' extra subfield, then the empty end-of-file member."""
+    import struct
+    import zlib
+    out = bytearray()
+    chunks = [data[k:k + block] for k in range(0, len(data), block)] + [b""]
+    for ch in chunks:
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        raw = c.compress(ch) + c.flush()
+        bsize = 12 + 6 + len(raw) + 8
+        out += b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+        out += raw + struct.pack("<II", zlib.crc32(ch) & 0xffffffff, len(ch))
+    return bytes(out)
