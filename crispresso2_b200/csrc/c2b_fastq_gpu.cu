@@ -15,6 +15,7 @@
 //   select + radix sort           representatives, ordered by their group's first record = first-seen order
 //   k_emit                        packed sequences, offsets, counts, first indices
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <cuda_runtime.h>
 
 #include <fcntl.h>
@@ -392,7 +393,7 @@ int dedup_device(const Source &src, size_t n, int device, c2b_fastq **out)
     lap("dedup");
     // representatives, then their order by first record
     GCHK(d_reps.get((size_t)n_rec * 4)); GCHK(d_nsel.get(8));
-    cub::CountingInputIterator<int32_t> iota(0);
+    thrust::counting_iterator<int32_t> iota(0);
     size_t b1 = 0, b2 = 0;
     GCHK(cub::DeviceSelect::Flagged(nullptr, b1, iota, d_isrep.as<uint8_t>(), d_reps.as<int32_t>(), d_nsel.as<int32_t>(), (int)n_rec, s));
     if (b1 + 256 > tmp_cap) { d_tmp.drop(); tmp_cap = b1 + 256; GCHK(d_tmp.get(tmp_cap)); }
