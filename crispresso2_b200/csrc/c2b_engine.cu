@@ -5,6 +5,8 @@
 //        -Iinclude -o crispresso2_b200/libc2b200.so crispresso2_b200/csrc/c2b_engine.cu
 // The same file compiles with g++ -DC2B_EMU against tests/emu/warp_emu.h (CPU-only logic tests).
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #ifndef C2B_EMU
 #include <sched.h>
 #include <sys/syscall.h>
@@ -37,14 +39,58 @@ static rt_err rt_d2h(void *h, const void *d, size_t n, rt_stream s) { return n ?
 static rt_err rt_zero(void *d, size_t n, rt_stream s) { return cudaMemsetAsync(d, 0, n, s); }
 static rt_err rt_d2h_2d(void *h, const void *d, size_t pitch, size_t width, size_t rows, rt_stream s)
 { return (width && rows) ? cudaMemcpy2DAsync(h, pitch, d, pitch, width, rows, cudaMemcpyDeviceToHost, s) : cudaSuccess; }
-static rt_err rt_sync(rt_stream s) { return cudaStreamSynchronize(s); }
+// A persistent kernel that never finishes (a lost barrier, a spin on a flag nobody sets) would block its host thread for ever and
+// nothing can cancel it.  Every blocking wait registers itself; a watchdog thread ends the process with a message when one has lasted
+// longer than C2B_WATCHDOG_S seconds (default 1800; 0 = no watchdog) -- a loud failure instead of a silent hang.
+static std::atomic<int64_t> g_wait_since[32];
+static int64_t wd_now_ms() { return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static int64_t wd_limit_ms()
+{
+    static const int64_t lim = [] { const char *v = getenv("C2B_WATCHDOG_S"); const double s = v ? atof(v) : 1800.0; return (int64_t)(s * 1000.0); }();
+    return lim;
+}
+static void wd_start()
+{
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (wd_limit_ms() <= 0) return;
+        std::thread([] {
+            const int64_t lim = wd_limit_ms();
+            const auto nap = std::chrono::milliseconds(std::max<int64_t>(20, std::min<int64_t>(1000, lim / 4)));
+            for (;;) {
+                std::this_thread::sleep_for(nap);
+                const int64_t now = wd_now_ms();
+                for (auto &w : g_wait_since) {
+                    const int64_t t = w.load(std::memory_order_relaxed);
+                    if (t && now - t > lim) {
+                        fprintf(stderr, "c2b200: a wait for the GPU has lasted more than %.0f s (a kernel that does not finish?) -- ending the "
+                                        "process; C2B_WATCHDOG_S sets the limit, 0 disables\n", lim / 1000.0);
+                        fflush(stderr);
+                        _exit(70);
+                    }
+                }
+            }
+        }).detach();
+    });
+}
+struct WaitGuard {
+    int k = -1;
+    WaitGuard()
+    {
+        wd_start();
+        const int64_t now = wd_now_ms();
+        for (int i = 0; i < 32; i++) { int64_t z = 0; if (g_wait_since[i].compare_exchange_strong(z, now, std::memory_order_relaxed)) { k = i; break; } }
+    }
+    ~WaitGuard() { if (k >= 0) g_wait_since[k].store(0, std::memory_order_relaxed); }
+};
+static rt_err rt_sync(rt_stream s) { WaitGuard g; return cudaStreamSynchronize(s); }
 static rt_err cudaMemcpyAsyncOrCopy(void *d, const void *s_, size_t n, rt_stream st) { return cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, st); }
 typedef cudaEvent_t rt_event;
 static rt_err rt_event_create(rt_event *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); }
 static rt_err rt_event_destroy(rt_event e) { return cudaEventDestroy(e); }
 static rt_err rt_record(rt_event e, rt_stream s) { return cudaEventRecord(e, s); }
 static rt_err rt_wait(rt_stream s, rt_event e) { return cudaStreamWaitEvent(s, e, 0); }
-static rt_err rt_event_sync(rt_event e) { return cudaEventSynchronize(e); }
+static rt_err rt_event_sync(rt_event e) { WaitGuard g; return cudaEventSynchronize(e); }
 static rt_err rt_stream_create(rt_stream *s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
 static rt_err rt_stream_destroy(rt_stream s) { return cudaStreamDestroy(s); }
 static void *rt_host_alloc(size_t n) { void *p = nullptr; return cudaHostAlloc(&p, n ? n : 16, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }

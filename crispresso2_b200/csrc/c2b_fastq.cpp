@@ -55,19 +55,69 @@ inline uint64_t hash_bytes(const uint8_t *p, size_t n)
     return h;
 }
 
+int host_threads(size_t bytes, int asked = 0)
+{
+    int T = asked > 0 ? asked : (int)std::thread::hardware_concurrency();
+    T = std::max(1, std::min(T, 64));
+    return bytes < (4u << 20) ? 1 : T;
+}
+
+template <class F> void run_threads(int T, F fn)            // fn(t) on T threads (this one is thread 0)
+{
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(fn, t);
+    fn(0);
+    for (auto &x : th) x.join();
+}
+
+// whole file into an uninitialised buffer, pread by all host threads (page-cache copies run at memory speed in parallel)
 bool read_plain(const char *path, c2b_bytes &buf, std::string &err)
 {
-    FILE *f = fopen(path, "rb");
-    if (!f) { err = std::string("cannot open ") + path; return false; }
-    fseek(f, 0, SEEK_END);
-    long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    if (n < 0) { fclose(f); err = "cannot size file"; return false; }
-    buf.resize((size_t)n);
-    size_t got = n ? fread(buf.data(), 1, (size_t)n, f) : 0;
-    fclose(f);
-    if (got != (size_t)n) { err = "short read"; return false; }
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { err = std::string("cannot open ") + path; return false; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 0) { close(fd); err = "cannot size file"; return false; }
+    const size_t n = (size_t)st.st_size;
+    buf.resize(n);
+    const int T = host_threads(n);
+    std::atomic<bool> bad(false);
+    run_threads(T, [&](int t) {
+        size_t a = n * (size_t)t / T;
+        const size_t b = n * (size_t)(t + 1) / T;
+        while (a < b) {
+            const ssize_t r = pread(fd, buf.data() + a, b - a, (off_t)a);
+            if (r <= 0) { bad.store(true); return; }
+            a += (size_t)r;
+        }
+    });
+    close(fd);
+    if (bad.load()) { err = "short read"; return false; }
     return true;
+}
+
+// output parts written at their offsets by all host threads
+bool write_parts(const char *path, const std::vector<std::string> &parts, const std::string &tail)
+{
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) return false;
+    std::vector<size_t> off(parts.size() + 1, 0);
+    for (size_t k = 0; k < parts.size(); k++) off[k + 1] = off[k] + parts[k].size();
+    const size_t total = off[parts.size()] + tail.size();
+    if (total && ftruncate(fd, (off_t)total) != 0) { close(fd); return false; }
+    std::atomic<bool> bad(false);
+    auto put = [&](const char *p, size_t n, size_t at) {
+        while (n) {
+            const ssize_t r = pwrite(fd, p, n, (off_t)at);
+            if (r <= 0) { bad.store(true); return; }
+            p += r; n -= (size_t)r; at += (size_t)r;
+        }
+    };
+    const int T = total < (4u << 20) ? 1 : (int)parts.size();
+    if (T <= 1) { for (size_t k = 0; k < parts.size(); k++) put(parts[k].data(), parts[k].size(), off[k]); }
+    else run_threads(T, [&](int t) { put(parts[(size_t)t].data(), parts[(size_t)t].size(), off[(size_t)t]); });
+    if (!tail.empty()) put(tail.data(), tail.size(), off[parts.size()]);
+    close(fd);
+    return !bad.load();
 }
 
 // Blocked gzip (BGZF: what bgzip and Illumina's converters write): every member's header carries its compressed size in a 'BC'
@@ -416,6 +466,40 @@ namespace {
 inline bool is_bspace(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }     // bytes.rstrip()
 
 struct Line { const uint8_t *p; uint32_t len; };
+typedef std::vector<Line, c2b_noinit_alloc<Line>> Lines;
+
+// lines of a buffer (split at '\n' only, right-stripped like bytes.rstrip()), indexed by all host threads: thread t takes the
+// lines that START in its byte range (ranges are cut right after a '\n'), then the pieces are laid end to end
+void split_lines(const uint8_t *data, size_t n, Lines &lines)
+{
+    const int T = host_threads(n);
+    std::vector<size_t> cut((size_t)T + 1, 0);
+    cut[(size_t)T] = n;
+    for (int t = 1; t < T; t++) {
+        size_t p = std::max(cut[(size_t)t - 1], n / (size_t)T * (size_t)t);
+        const uint8_t *nl = p < n ? (const uint8_t *)memchr(data + p, '\n', n - p) : nullptr;
+        cut[(size_t)t] = nl ? (size_t)(nl - data) + 1 : n;
+    }
+    std::vector<Lines> part((size_t)T);
+    run_threads(T, [&](int t) {
+        Lines &L = part[(size_t)t];
+        const size_t e0 = cut[(size_t)t + 1];
+        L.reserve((e0 - cut[(size_t)t]) / 60 + 16);
+        for (size_t p = cut[(size_t)t]; p < e0;) {
+            const uint8_t *nl = (const uint8_t *)memchr(data + p, '\n', e0 - p);
+            const size_t e = nl ? (size_t)(nl - data) : e0;
+            size_t q = e;
+            while (q > p && is_bspace(data[q - 1])) q--;
+            L.push_back({data + p, (uint32_t)(q - p)});
+            p = nl ? e + 1 : e0;
+        }
+    });
+    if (T == 1) { lines.swap(part[0]); return; }
+    std::vector<size_t> at((size_t)T + 1, 0);
+    for (int t = 0; t < T; t++) at[(size_t)t + 1] = at[(size_t)t] + part[(size_t)t].size();
+    lines.resize(at[(size_t)T]);
+    run_threads(T, [&](int t) { if (!part[(size_t)t].empty()) memcpy(lines.data() + at[(size_t)t], part[(size_t)t].data(), part[(size_t)t].size() * sizeof(Line)); });
+}
 
 bool gz_member(const std::string &in, std::string &out)
 {
@@ -446,17 +530,8 @@ extern "C" int c2b_fastq_filter(const char *path_in, const char *path_out, int32
     if (!(gz_in ? read_gz(path_in, buf, err) : read_plain(path_in, buf, err))) { g_fastq_err = "c2b_fastq_filter: " + err; return C2B_E_ARG; }
     const uint8_t *data = buf.data();
     const size_t n = buf.size();
-    // lines (split at '\n' only), right-stripped
-    std::vector<Line> lines;
-    lines.reserve(n / 60 + 16);
-    for (size_t p = 0; p < n;) {
-        const uint8_t *nl = (const uint8_t *)memchr(data + p, '\n', n - p);
-        size_t e = nl ? (size_t)(nl - data) : n;
-        size_t q = e;
-        while (q > p && is_bspace(data[q - 1])) q--;
-        lines.push_back({data + p, (uint32_t)(q - p)});
-        p = nl ? e + 1 : n;
-    }
+    Lines lines;
+    split_lines(data, n, lines);
     // records up to the first empty id line
     int64_t n_rec = 0;
     while ((size_t)(4 * n_rec) < lines.size() && lines[(size_t)(4 * n_rec)].len > 0) n_rec++;
@@ -511,12 +586,11 @@ extern "C" int c2b_fastq_filter(const char *path_in, const char *path_out, int32
         g_fastq_err = fail_code[t] == 1 ? "c2b_fastq_filter: empty quality line" : fail_code[t] == 2 ? "c2b_fastq_filter: sequence and quality lengths differ" : "c2b_fastq_filter: deflate failed";
         return fail_code[t] == 3 ? C2B_E_STATE : (fail_code[t] == 1 ? C2B_E_LIMIT : C2B_E_ARG);
     }
-    FILE *f = fopen(path_out, "wb");
-    if (!f) { g_fastq_err = std::string("c2b_fastq_filter: cannot write ") + path_out; return C2B_E_ARG; }
     int64_t tot = 0;
-    for (int t = 0; t < T; t++) { if (!outs[t].empty()) fwrite(outs[t].data(), 1, outs[t].size(), f); tot += kept[t]; }
-    if (gz_out && n_rec == 0) { std::string z, e2; gz_member(e2, z); fwrite(z.data(), 1, z.size(), f); }   // an empty but valid gzip file
-    fclose(f);
+    for (int t = 0; t < T; t++) tot += kept[t];
+    std::string tail;
+    if (gz_out && n_rec == 0) { std::string e2; gz_member(e2, tail); }                  // an empty but valid gzip file
+    if (!write_parts(path_out, outs, tail)) { g_fastq_err = std::string("c2b_fastq_filter: cannot write ") + path_out; return C2B_E_ARG; }
     if (n_in) *n_in = n_rec;
     if (n_out) *n_out = tot;
     return C2B_OK;
@@ -531,22 +605,12 @@ extern "C" int c2b_fastq_filter(const char *path_in, const char *path_out, int32
 // first, where numpy.min of an empty array raises (-> C2B_E_LIMIT here).
 namespace {
 
-bool load_lines(const char *path, c2b_bytes &buf, std::vector<Line> &lines, std::string &err)
+bool load_lines(const char *path, c2b_bytes &buf, Lines &lines, std::string &err)
 {
     const size_t Lp = strlen(path);
     const bool gz = Lp > 3 && strcmp(path + Lp - 3, ".gz") == 0;
     if (!(gz ? read_gz(path, buf, err) : read_plain(path, buf, err))) return false;
-    const uint8_t *data = buf.data();
-    const size_t n = buf.size();
-    lines.reserve(n / 60 + 16);
-    for (size_t p = 0; p < n;) {
-        const uint8_t *nl = (const uint8_t *)memchr(data + p, '\n', n - p);
-        size_t e = nl ? (size_t)(nl - data) : n;
-        size_t q = e;
-        while (q > p && is_bspace(data[q - 1])) q--;
-        lines.push_back({data + p, (uint32_t)(q - p)});
-        p = nl ? e + 1 : n;
-    }
+    split_lines(buf.data(), buf.size(), lines);
     return true;
 }
 
@@ -558,11 +622,11 @@ extern "C" int c2b_fastq_filter_pair(const char *path1_in, const char *path2_in,
 {
     if (!path1_in || !path2_in || !path1_out || !path2_out) return C2B_E_ARG;
     c2b_bytes buf1, buf2;
-    std::vector<Line> l1, l2;
+    Lines l1, l2;
     std::string err;
     if (!load_lines(path1_in, buf1, l1, err) || !load_lines(path2_in, buf2, l2, err)) { g_fastq_err = "c2b_fastq_filter_pair: " + err; return C2B_E_ARG; }
     static const uint8_t nothing = 0;
-    auto at = [&](const std::vector<Line> &L, size_t k) -> Line { return k < L.size() ? L[k] : Line{&nothing, 0}; };
+    auto at = [&](const Lines &L, size_t k) -> Line { return k < L.size() ? L[k] : Line{&nothing, 0}; };
     int64_t n_rec = 0;
     while ((size_t)(4 * n_rec) < l1.size() && l1[(size_t)(4 * n_rec)].len > 0) n_rec++;
     const bool bp = min_bp_qual_in_read != 0, rq = min_av_read_qual != 0, bpn = min_bp_qual_or_N != 0;
@@ -635,12 +699,12 @@ extern "C" int c2b_fastq_filter_pair(const char *path1_in, const char *path2_in,
     }
     int64_t tot = 0;
     for (int f = 0; f < 2; f++) {
-        FILE *fh = fopen(f ? path2_out : path1_out, "wb");
-        if (!fh) { g_fastq_err = std::string("c2b_fastq_filter_pair: cannot write ") + (f ? path2_out : path1_out); return C2B_E_ARG; }
-        std::vector<std::string> &outs = f ? outs2 : outs1;
-        for (int t = 0; t < T; t++) if (!outs[t].empty()) fwrite(outs[t].data(), 1, outs[t].size(), fh);
-        if ((f ? gz2 : gz1) && n_rec == 0) { std::string z, e2; gz_member(e2, z); fwrite(z.data(), 1, z.size(), fh); }
-        fclose(fh);
+        std::string tail;
+        if ((f ? gz2 : gz1) && n_rec == 0) { std::string e2; gz_member(e2, tail); }
+        if (!write_parts(f ? path2_out : path1_out, f ? outs2 : outs1, tail)) {
+            g_fastq_err = std::string("c2b_fastq_filter_pair: cannot write ") + (f ? path2_out : path1_out);
+            return C2B_E_ARG;
+        }
     }
     for (int t = 0; t < T; t++) tot += kept[t];
     if (n_in) *n_in = n_rec;

@@ -44,3 +44,20 @@ eng.configure({'Reference': ref}, ['Reference'], m, -20, -2, 5, 2, 0, 'ACGTN', 8
 eng.counts_reset()
 res = eng.align_packed(big.reshape(-1), np.arange(70001, dtype=np.int64) * 250)
 print('streamed', eng.path_counts(), int((res.recs['best_score_milli'] > 0).sum()))
+# compact outputs with the narrow first tier + legacy insertion quantification
+eng.configure({'Reference': ref}, ['Reference'], m, -20, -2, 5, 2, _lib.F_LEGACY_INS, 'ACGTN', 8)
+eng.counts_reset()
+buf, off = pack_reads(reads[:1200])
+res = eng.align_packed(buf, off, compact=True)
+print('compact+legacy', eng.path_counts(), eng.ring_counts(), res.strings_block(0, 4).shape)
+# FASTQ front end on the GPU: mixed line ends, blank tail, duplicates
+from crispresso2_b200 import fastq
+recs = []
+for k, s in enumerate(reads[:3000] + reads[:500]):
+    e = [b"\n", b"\r\n", b"\r"][k % 3]
+    recs.append(b"@r%d" % k + e + s.encode() + e + b"+" + e + b"I" * len(s) + e)
+data = b"".join(recs) + b"\n\n"
+dd = fastq.dedup_bytes(data, device=0)
+hh = fastq.dedup_bytes(data)
+assert dd.n_reads == hh.n_reads and np.array_equal(dd.buf, hh.buf) and np.array_equal(dd.counts, hh.counts)
+print('gpu ingest', dd.n_reads, len(dd.counts))
