@@ -63,7 +63,7 @@ static void wd_start()
                 for (auto &w : g_wait_since) {
                     const int64_t t = w.load(std::memory_order_relaxed);
                     if (t && now - t > lim) {
-                        fprintf(stderr, "c2b200: a wait for the GPU has lasted more than %.0f s (a kernel that does not finish?) -- ending the "
+                        fprintf(stderr, "c2b200: a wait for the GPU has lasted more than %.3g s (a kernel that does not finish?) -- ending the "
                                         "process; C2B_WATCHDOG_S sets the limit, 0 disables\n", lim / 1000.0);
                         fflush(stderr);
                         _exit(70);
