@@ -91,3 +91,16 @@ def test_process_fastq_with_gpu_ingest_equals_host_ingest(tmp_path, monkeypatch)
         out.append((st, list(cache.keys()), sorted(lost), {r: {k: v.tolist() for k, v in blk.vectors(r).items()} for r in rec["ref_names"]},
                     blk.class_counts()))
     assert out[0] == out[1]
+
+
+def test_blocked_gzip_through_the_gpu_front_end(tmp_path):
+    rng = np.random.default_rng(13)
+    amp = synth.random_amplicon(rng, 250)
+    reads = synth.synth_reads_fast(rng, amp, 40000, 250, sub_rate=0.002, cut=126, n_templates=512)
+    plain = tmp_path / "b.fastq"
+    synth.write_fastq_fast(str(plain), reads)
+    bg = tmp_path / "b.fastq.gz"
+    bg.write_bytes(synth.bgzf_bytes(plain.read_bytes()))
+    got = check_gpu(str(bg))
+    want = fastq.dedup_file(str(plain))
+    assert np.array_equal(got.buf, want.buf) and np.array_equal(got.counts, want.counts)
