@@ -1031,6 +1031,10 @@ int c2b_path_counts(c2b_engine *e, int64_t *pair_items, int64_t *single_items)
     RTCHK(rt_sync(e->stream));
     // the ALIGN kernel counts reads ([5] kept by the ring, [6] sent on, [7] fully aligned); reported in pairs
     e->band_reruns = v[4]; e->ring_pairs = (v[5] + 1) / 2; e->ring_fallbacks = (v[6] + 1) / 2;
+    if (getenv("C2B_VERBOSE"))
+        fprintf(stderr, "[c2b] counters: general kernel %lld pair items + %lld single items; ALIGN: %lld read x reference combinations kept "
+                        "by the ring, %lld sent to the full matrix, %lld reads settled\n", (long long)v[2], (long long)v[3], (long long)v[5],
+                (long long)v[6], (long long)v[7]);
     if (pair_items) *pair_items = v[2] + (v[7] + 1) / 2;
     if (single_items) *single_items = v[3];
     return C2B_OK;

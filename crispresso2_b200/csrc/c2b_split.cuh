@@ -245,7 +245,13 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
     }
     const int k0 = multi ? 0 : r0, k1 = multi ? P.n_refs : r0 + 1;
     uint2 *tbq = P.tbq ? reinterpret_cast<uint2 *>(P.tbq + (int64_t)warp_slot * P.TS * 64) : nullptr;
-    uint32_t okmask = 0, modes = 0, both2 = 0;              // both2: reads (bit 2q + h) to be aligned on both strands
+    uint32_t okmask = 0, modes = 0;
+    // both2[k - k0]: reads (bit 2q + h) that reference k's seed test wants aligned on both strands.  The seed tests of the
+    // candidate references may disagree (r02y: 8 % of the HDR bench reads miss the seeds of ONE amplicon; their pairs used to go
+    // to the general kernel, which then cost 44 % of the HDR step): the strand a read rides the packed DP on is the first
+    // reference's choice, a reference that wants both strands gets its own both-strand alignment below, and only a forward /
+    // reverse-complement conflict between references still sends the pair on.
+    uint32_t both2[RG_MAX_REFS] = {0, 0, 0, 0};
     int Jg = 0, Jmax = 0;
 #pragma unroll 1
     for (int q = 0; q < 4; q++) {
@@ -256,23 +262,30 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
         for (int x = 0; x < 2; x++) bad |= load_codes_a(P, S.lut, P.offsets[x ? rdB : rdA], J, S.fw[x], S.rc[x]);
         wp::sync();
         int mAB = 0; bool agree = true;
+        uint32_t bothq[RG_MAX_REFS] = {0, 0, 0, 0};
 #pragma unroll 1
-        for (int k = k0; k < k1; k++) {                     // every candidate reference's seed test must pick the same single strand
+        for (int k = k0; k < k1; k++) {
             int m = 0;
 #pragma unroll 1
             for (int x = 0; x < 2; x++) m |= strand_mode(P, refdev(P, k), S.fw[x], J) << (2 * x);
-            if (k == k0) mAB = m; else agree = agree && (m == mAB);
+            if (k == k0) mAB = m;
+#pragma unroll
+            for (int x = 0; x < 2; x++) {
+                const int mk = (m >> (2 * x)) & 3, m0 = (mAB >> (2 * x)) & 3;
+                if (mk == 2) bothq[(k - k0) & (RG_MAX_REFS - 1)] |= 1u << x;        // this reference: both strands, whatever the ride
+                else if (mk != (m0 == 2 ? 0 : m0)) agree = false;                    // forward here, reverse complement there
+            }
         }
         const int mA = mAB & 3, mB = mAB >> 2;
         if (!bad && agree) {
             // a read whose seed test calls for both strands (mode 2) rides along on its forward strand -- its half of the ring
-            // result is ignored -- and is aligned on both strands over the full matrix below (r02d: such a read sent its whole
-            // pair to the general kernel: 0.8 % of the reads, 0.77 ms of a 15.7 ms batch)
+            // result is ignored for that reference -- and is aligned on both strands over the full matrix below (r02d: such a read
+            // sent its whole pair to the general kernel: 0.8 % of the reads, 0.77 ms of a 15.7 ms batch)
             const uint8_t *cA = mA == 1 ? S.rc[0] : S.fw[0], *cB = mB == 1 ? S.rc[1] : S.fw[1];
             for (int p = lane; p < J; p += 32) S.combo[q][p] = (uint8_t)(cA[p] * P.nq + cB[p]);
             okmask |= 1u << q; modes |= (uint32_t)mAB << (4 * q);
-            if (mA == 2) both2 |= 1u << (2 * q);
-            if (mB == 2) both2 |= 2u << (2 * q);
+#pragma unroll
+            for (int kk = 0; kk < RG_MAX_REFS; kk++) both2[kk] |= bothq[kk] << (2 * q);
             if (g == q) Jg = J;
             if (J > Jmax) Jmax = J;
         }
@@ -284,13 +297,17 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
     uint32_t good2 = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) if ((okmask >> q) & 1u) good2 |= 3u << (2 * q);
-    if (!P.tb) { good2 &= ~both2; both2 = 0; }              // no full-matrix scratch: general kernel
+    if (!P.tb) {                                            // no full-matrix scratch: general kernel
+#pragma unroll
+        for (int kk = 0; kk < RG_MAX_REFS; kk++) { good2 &= ~both2[kk]; both2[kk] = 0; }
+    }
     int npass = 0, ntried = 0, nboth = 0;
 #pragma unroll 1
     for (int k = k0; k < k1 && good2; k++) {
         const RefDev &R = refdev(P, k);
-        const uint32_t ring2 = good2 & ~both2;              // reads whose ring result counts
-        nboth += wp::popc(both2 & good2);
+        const uint32_t bothk = both2[(k - k0) & (RG_MAX_REFS - 1)];
+        const uint32_t ring2 = good2 & ~bothk;              // reads whose ring result counts for this reference
+        nboth += wp::popc(bothk & good2);
         const bool staged = (k == 0 && staged_prof != nullptr);
         uint32_t pass2 = 0;
         if (((ringmask >> (k - k0)) & 1u) && ring2) {
@@ -349,7 +366,7 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
         // general kernel, whose launch then took 0.77 ms for 0.8 % of the reads: the latency of single pairs through its whole
         // per-read path; inside this persistent kernel the same DPs hide among the other warps' work.
         const uint32_t failed = ring2 & ~pass2;
-        if ((failed | (both2 & good2)) && P.tb) {
+        if ((failed | (bothk & good2)) && P.tb) {
             uint2 *tb2 = reinterpret_cast<uint2 *>(P.tb + (int64_t)warp_slot * P.tb_words_per_warp);
             int32_t *bnd = P.bnd + (int64_t)warp_slot * P.bnd_words_per_warp;
             const int h = lane >> 4, hl = lane & 15;
@@ -358,7 +375,7 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
                 const int q = job >> 2, kind = job & 3;              // kind 0: pair q; 1 / 2: read A / B of pair q on both strands
                 if (kind == 3) continue;
                 const uint32_t fq = (failed >> (2 * q)) & 3u;
-                const uint32_t bq = ((both2 & good2) >> (2 * q)) & 3u;
+                const uint32_t bq = ((bothk & good2) >> (2 * q)) & 3u;
                 if (kind == 0 ? fq == 0 : !((bq >> (kind - 1)) & 1u)) continue;
                 const int Jp = wp::shfl(Jg, 8 * q);
                 const uint8_t *combo = S.combo[q];
@@ -402,7 +419,7 @@ C2B_DEV void align_group(const KParams &P, ASmem &S, const uint32_t *staged_prof
                 }
             }
         }
-        pass2 |= both2 & good2;                                              // both-strand reads: settled above (or dropped from good2)
+        pass2 |= bothk & good2;                                              // both-strand reads: settled above (or dropped from good2)
         good2 &= pass2;
         wp::sync();
     }

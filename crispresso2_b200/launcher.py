@@ -7,6 +7,8 @@ also usable as CRISPRessoPooled / CRISPRessoBatch's `--crispresso_command "pytho
 What is re-bound, nothing else of the reference changes:
   * CRISPRessoCORE.process_fastq (module global, resolved by name at CRISPRessoCORE.py:3750; also reached through
     process_fastq_write_out :2285 and process_single_fastq_write_bam_out :2373)   -> crispresso2_b200.core.process_fastq
+  * CRISPRessoCORE.process_paired_fastq (--crispresso_merge, :3744-3748)   -> crispresso2_b200.paired: the reference's loop with its
+    global_align calls answered from one GPU batch over every distinct mate sequence
   * filterFastqs.filterFastqs (imported and called at CRISPRessoCORE.py:3716-3717)          -> crispresso2_b200.filter_fastqs.filterFastqs
   * CRISPRessoShared.get_dataframe_around_cut_asymmetrical (plots/data_prep.py:1537)        -> the native grouping of
     crispresso2_b200.alleles when the frame was built by AlleleTable.to_dataframe(), the reference's own function otherwise.
@@ -65,6 +67,20 @@ def bind(CORE=None, engine=None, lib_path=None):
                   engine=get_engine(), aln_matrix=matrix)
 
     CORE.process_fastq = process_fastq
+    # paired-end merge mode (--crispresso_merge): the reference's own loop over one batch of GPU alignments (paired.py)
+    from . import paired
+    reference_paired = CORE.process_paired_fastq
+
+    def process_paired_fastq(fastq1_filename, fastq2_filename, variantCache, ref_names, refs, args, files_to_remove, output_directory,
+                             fastq_write_out_file=None):
+        loc = args.needleman_wunsch_aln_matrix_loc
+        if not os.path.isabs(loc):
+            loc = os.path.join(CORE._ROOT, loc)
+        return paired.process_paired_fastq(reference_paired, CORE.CRISPResso2Align, get_engine(), fastq1_filename, fastq2_filename,
+                                           variantCache, ref_names, refs, args, files_to_remove, output_directory,
+                                           fastq_write_out_file, aln_matrix=core.read_matrix(loc))
+
+    CORE.process_paired_fastq = process_paired_fastq
     from CRISPResso2 import filterFastqs as FF
     FF.filterFastqs = functools.partial(filter_fastqs.filterFastqs, lib_path=lib_path)
     from CRISPResso2 import CRISPRessoShared as SH

@@ -29,6 +29,8 @@ def main():
     import gen_golden as GG                                  # installs the stubs, imports the reference CORE
     CORE = GG.CRISPRessoCORE
     report = {"mode": mode, "mismatch": [], "checked": 0}
+    if "--crispresso_merge" in argv:                          # fastp is a third-party binary this image does not have: tests/fake_fastp.py
+        CORE.check_fastp = lambda: None
     if mode == "b200":
         from crispresso2_b200 import core
         from crispresso2_b200.engine import Engine
@@ -51,6 +53,11 @@ def main():
         orig_ctx = CORE.CorePlotContext
 
         def ctx_spy(*a, **kw):
+            if "block" not in state:                          # paired-end merge mode: the reference's loop built the counts itself
+                from crispresso2_b200 import paired
+                memo = paired.process_paired_fastq.last_memo
+                report["memo"] = {"hits": memo.hits, "misses": memo.misses, "sequences": len(memo.index)}
+                return orig_ctx(*a, **kw)
             blk = state["block"]
             bad = report["mismatch"]
 

@@ -197,6 +197,22 @@ def check_against_oracle(engine, refs, ref_names, params, reads, matrix):
                 assert (R1[name] == v).all(), (r, name)
 
 
+def check_seed_disagreement(engine, n=1536):
+    """Reads whose seed tests disagree across the candidate amplicons (forward for two, both strands for the third -- 8 % of the
+    HDR bench workload; plus constructed forward / reverse-complement conflicts): ALIGN gives such a reference its own both-strand
+    alignment instead of sending the pair to the general kernel (r02y).  Every field and the count block against the oracle."""
+    import bench
+    w = bench.Workload("hdr", n, 0)
+    reads = [r.tobytes().decode() for r in w.buf.reshape(-1, 250)]
+    # conflicts: the front of a forward read joined to the reverse complement of its back half hits forward AND reverse seeds
+    reads += [reads[k][:125] + O.reverse_complement(reads[k])[:125] for k in range(0, 64, 2)]
+    reads += [O.reverse_complement(reads[k]) for k in range(1, 64, 2)]
+    modes = [tuple(O._strand_choice(w.params, s, w.refs[r]) for r in w.ref_names) for s in reads]
+    assert sum(1 for m in modes if len(set(m)) > 1) > n // 40
+    check_against_oracle(engine, w.refs, w.ref_names, w.params, reads, O.make_matrix())
+    return sum(1 for m in modes if len(set(m)) > 1)
+
+
 def check_pooled(engine, n_amplicons=6, reads_per=40, seed=21, amp_len=(120, 200)):
     """Config-4 shape (post-demultiplex Pooled): every read carries the index of its single amplicon (ref_id).
     Each (amplicon, read) must equal what the oracle computes with that amplicon alone; the count block of

@@ -36,3 +36,37 @@ def write_fastq(path, amp):
         for k, s in enumerate(reads):
             fh.write("@r%d\n%s\n+\n%s\n" % (k, s, "I" * len(s)))
     return extension(amp), SCAFFOLD
+
+
+def write_pairs(path1, path2, amp, n=260, seed=5):
+    """Paired-end reads over `amp` for --crispresso_merge: 150 bp mates overlapping in the middle, edits at the cut, sequencing
+    errors inside the overlap with unequal qualities (the consensus then picks by quality and the pair may not be cached),
+    pairs sequenced from the other strand, duplicates."""
+    rnd = random.Random(seed)
+    L = 150
+    pairs = []
+    for k in range(n):
+        t = amp
+        u = rnd.random()
+        if u < 0.25:
+            d = rnd.randint(1, 12)
+            t = t[:92 - d // 2] + t[92 - d // 2 + d:]
+        elif u < 0.35:
+            t = t[:92] + "".join(rnd.choice("ACGT") for _ in range(rnd.randint(1, 5))) + t[92:]
+        elif u < 0.45:
+            t = t[:90] + rnd.choice("ACGT") + t[91:]
+        if rnd.random() < 0.15:
+            t = rc(t)
+        m1, m2 = t[:L], rc(t[-L:])
+        q1 = "".join(rnd.choice("II5#") for _ in m1)
+        q2 = "".join(rnd.choice("II5#") for _ in m2)
+        if rnd.random() < 0.3:                                # an error in one mate, inside the overlap
+            p = rnd.randint(len(t) - L + 2, L - 3) if len(t) - L + 2 < L - 3 else L // 2
+            m1 = m1[:p] + rnd.choice("ACGT") + m1[p + 1:]
+        pairs.append((m1, q1, m2, q2))
+    pairs += pairs[10:60]
+    for path, a, b in ((path1, 0, 1), (path2, 2, 3)):
+        with open(path, "w") as fh:
+            for k, pr in enumerate(pairs):
+                fh.write("@p%d\n%s\n+\n%s\n" % (k, pr[a], pr[b]))
+    return len(pairs)

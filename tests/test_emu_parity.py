@@ -260,3 +260,7 @@ def test_batch_gate_matches_and_catches_corruption(emu):
     summ3, _ = BG.run(reads.reshape(-1), off, refs, names, O.Params(), O.make_matrix(), res.recs, a2, res.strings, res.edits,
                       res.W, n_workers=2)
     assert summ3["n_bad"] == 1
+
+
+def test_seed_tests_disagreeing_across_references(emu):
+    assert PU.check_seed_disagreement(emu, n=768) > 20

@@ -319,3 +319,7 @@ def test_split_kernels_equal_general_kernel_and_chunking(eng, monkeypatch, mixed
 def test_random_configurations_against_oracle(eng):
     for seed in range(100, 160):
         PU.check_random_config(eng, seed)
+
+
+def test_seed_tests_disagreeing_across_references(eng):
+    assert PU.check_seed_disagreement(eng, n=8192) > 200
