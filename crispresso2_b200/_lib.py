@@ -31,6 +31,7 @@ F_LEGACY_INS = 1024
 ST_BAD_CHAR = 1
 ST_UNDEFINED = 2
 ST_EDIT_OVERFLOW = 4
+E_ARG, E_LIMIT, E_STATE = -2, -3, -4                    # C2B_E_* of include/c2b200.h
 ST_TOO_LONG = 8
 
 # count-block layout (enum order of c2b200.h)
@@ -84,7 +85,7 @@ EXPORTS = ["c2b_create", "c2b_destroy", "c2b_last_error", "c2b_configure", "c2b_
            "c2b_fastq_dedup", "c2b_fastq_dedup_buffer", "c2b_fastq_gpu_available", "c2b_fastq_dedup_gpu", "c2b_fastq_dedup_gpu_buffer", "c2b_fastq_n_reads", "c2b_fastq_n_unique", "c2b_fastq_max_len",
            "c2b_fastq_seqs", "c2b_fastq_offsets", "c2b_fastq_counts", "c2b_fastq_first_index", "c2b_fastq_free",
            "c2b_fastq_last_error", "c2b_fastq_filter", "c2b_fastq_filter_pair", "c2b_rc_merge_weights", "c2b_screen_reads", "c2b_serial_stats",
-           "c2b_alleles_build", "c2b_alleles_free", "c2b_alleles_n", "c2b_alleles_order", "c2b_alleles_arena", "c2b_alleles_offsets",
+           "c2b_consensus_from_pairs", "c2b_alleles_build", "c2b_alleles_free", "c2b_alleles_n", "c2b_alleles_order", "c2b_alleles_arena", "c2b_alleles_offsets",
            "c2b_alleles_lengths", "c2b_alleles_write_tsv", "c2b_alleles_around_cut", "c2b_alleles_cut_width", "c2b_alleles_cut_fetch"]
 
 _cache = {}
@@ -179,6 +180,11 @@ def load(path=None):
         getattr(L, name).argtypes = [vp]
     L.c2b_fastq_free.restype = None
     L.c2b_fastq_free.argtypes = [vp]
+    L.c2b_consensus_from_pairs.restype = C.c_int
+    L.c2b_consensus_from_pairs.argtypes = [C.c_char_p, i32, C.c_char_p, i32, C.c_double, C.c_char_p, i32,
+                                           C.c_char_p, i32, C.c_char_p, i32, C.c_double, C.c_char_p, i32,
+                                           C.c_char_p, C.c_char_p, C.c_char_p, i32,
+                                           C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.c2b_fastq_gpu_available.restype = C.c_int
     L.c2b_fastq_gpu_available.argtypes = []
     L.c2b_fastq_dedup_gpu.restype = C.c_int

@@ -11,7 +11,9 @@ programming is what costs; everything after it is the reference's own bookkeepin
      (C2B_F_NO_STRAND_SEARCH: the strand logic stays with the caller, exactly as global_align has none);
   3. `CRISPResso2Align.global_align` is re-bound, for the duration of the call, to a lookup into that batch (a sequence the
      batch does not hold -- there should be none -- is aligned by a single GPU call, never on the CPU);
-  4. the reference's own process_paired_fastq runs unchanged on top.
+  4. get_consensus_alignment_from_pairs (:829-985), the per-column merge of the two mates' alignments, is re-bound to its native
+     restatement (c2b_consensus_from_pairs; the reference's own unit test for it and a differential fuzz pin it);
+  5. the reference's own process_paired_fastq runs unchanged on top.
 
 Same arguments, same return value, same variantCache as the reference; parity is by construction as long as global_align's
 results are the reference's (tests/test_reference_unit_tests.py, tests/test_gpu_parity.py).
@@ -22,6 +24,30 @@ from . import _lib, align, fastq
 from .engine import pack_reads
 
 _COMP = bytes.maketrans(b"ACGTNacgtn", b"TGCANTGCAN")
+
+
+def get_consensus_alignment_from_pairs(aln_seq_r1, aln_ref_r1, score_r1, qual_r1, aln_seq_r2, aln_ref_r2, score_r2, qual_r2, lib_path=None):
+    """CRISPRessoCORE.get_consensus_alignment_from_pairs (:829-985), natively (c2b_consensus_from_pairs).
+    -> (final_aln, final_qual, final_ref, homology score, caching_is_ok)"""
+    import ctypes as C
+    L = _lib.load(lib_path)
+    parts = (aln_seq_r1, aln_ref_r1, qual_r1, aln_seq_r2, aln_ref_r2, qual_r2)
+    if not all(p.isascii() for p in parts):
+        raise ValueError("get_consensus_alignment_from_pairs: non-ASCII sequence or quality string")
+    b = [p.encode("ascii") for p in parts]
+    cap = len(b[1]) + len(b[4]) + 1
+    out = [C.create_string_buffer(cap) for _ in range(3)]
+    n, nq, m, ok = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    rc = L.c2b_consensus_from_pairs(b[0], len(b[0]), b[1], len(b[1]), float(score_r1), b[2], len(b[2]),
+                                    b[3], len(b[3]), b[4], len(b[4]), float(score_r2), b[5], len(b[5]),
+                                    out[0], out[1], out[2], cap, C.byref(n), C.byref(nq), C.byref(m), C.byref(ok))
+    if rc in (_lib.E_LIMIT, _lib.E_STATE):
+        raise IndexError("string index out of range")
+    if rc != 0:
+        raise RuntimeError("c2b_consensus_from_pairs failed (%d)" % rc)
+    cols = n.value
+    return (out[0].raw[:cols].decode("ascii"), out[1].raw[:nq.value].decode("ascii"), out[2].raw[:cols].decode("ascii"),
+            round(float(100 * m.value / float(cols)), 3), bool(ok.value))
 
 
 class AlignmentMemo:
@@ -91,6 +117,12 @@ def process_paired_fastq(original, CRISPResso2Align, engine, fastq1_filename, fa
     saved_ga, saved_rm = CRISPResso2Align.global_align, CRISPResso2Align.read_matrix
     CRISPResso2Align.global_align = memo.global_align
     CRISPResso2Align.read_matrix = lambda path: aln_matrix          # the matrix object the memo was built with (:1277)
+    import functools
+    import sys
+    host = sys.modules[original.__module__]                         # the module whose globals the reference's loop resolves
+    saved_cons = getattr(host, "get_consensus_alignment_from_pairs", None)
+    if saved_cons is not None:
+        host.get_consensus_alignment_from_pairs = functools.partial(get_consensus_alignment_from_pairs, lib_path=engine.lib_path)
     try:
         n_proc, args.n_processes = args.n_processes, "1"            # the serial branch: the lookups live in this process
         try:
@@ -103,5 +135,7 @@ def process_paired_fastq(original, CRISPResso2Align, engine, fastq1_filename, fa
             args.n_processes = n_proc
     finally:
         CRISPResso2Align.global_align, CRISPResso2Align.read_matrix = saved_ga, saved_rm
+        if saved_cons is not None:
+            host.get_consensus_alignment_from_pairs = saved_cons
     process_paired_fastq.last_memo = memo
     return out

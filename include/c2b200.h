@@ -375,6 +375,19 @@ int  c2b_fastq_filter_pair(const char *path1_in, const char *path2_in, const cha
                            int32_t min_bp_qual_in_read, int32_t min_av_read_qual, int32_t min_bp_qual_or_N,
                            int32_t n_threads, int64_t *n_in, int64_t *n_out);
 
+/* ---- paired-end merge mode (csrc/c2b_paired.cpp) ----
+ * get_consensus_alignment_from_pairs (CRISPRessoCORE.py:829-985, get_greater_qual_nuc :801-826): the two mates' alignments to one
+ * amplicon (aligned read, aligned amplicon, score, quality string of the read's bases) merged column by column into one aligned
+ * read / amplicon / quality triple.  out_* hold at least `cap` >= n1 + n2 bytes.  n_match / n_cols give the homology
+ * (round(100 * n_match / n_cols, 3) on the caller's side); caching_is_ok = 0 when a base was chosen by quality.
+ * C2B_E_LIMIT: a quality string (or an aligned read) shorter than what the walk over the amplicon strings consumes (IndexError in
+ * the reference); C2B_E_STATE: nothing but
+ * amplicon gaps (IndexError there too). */
+int  c2b_consensus_from_pairs(const char *aln_seq_r1, int32_t ns1, const char *aln_ref_r1, int32_t n1, double score_r1, const char *qual_r1, int32_t nq1,
+                              const char *aln_seq_r2, int32_t ns2, const char *aln_ref_r2, int32_t n2, double score_r2, const char *qual_r2, int32_t nq2,
+                              char *out_aln, char *out_qual, char *out_ref, int32_t cap,
+                              int32_t *n_cols, int32_t *n_qual, int32_t *n_match, int32_t *caching_is_ok);
+
 /* pinned host memory (cudaHostAlloc) for callers that want full-speed host<->device copies */
 void *c2b_host_alloc(size_t n_bytes);
 void  c2b_host_free(void *p);
