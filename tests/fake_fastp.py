@@ -10,6 +10,9 @@ import sys
 
 def main():
     a = sys.argv[1:]
+    if "--version" in a:                                     # CRISPRessoCORE.check_program parses `fastp X.Y.Z`
+        print("fastp 0.23.4")
+        return 0
     val = lambda flag: a[a.index(flag) + 1]
     for src, dst in ((val("-i"), val("--out1")), (val("-I"), val("--out2"))):
         opener = gzip.open if src.endswith(".gz") else open

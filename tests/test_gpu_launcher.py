@@ -60,3 +60,57 @@ def test_launcher_output_folder_equals_the_reference(case, extra, tmp_path):
     assert not diff, diff
     assert len(a) >= 10
     assert _info_stats(outs["ref"]) == _info_stats(outs["b200"])
+
+
+def _run_both(argv, tmp_path, env):
+    outs = {}
+    for mode, cmd in (("ref", [sys.executable, "-c", REF_MAIN]), ("b200", [sys.executable, "-m", "crispresso2_b200.launcher"])):
+        out = str(tmp_path / mode)
+        os.makedirs(out)
+        p = subprocess.run(cmd + argv + ["--suppress_plots", "--suppress_report", "-o", out], capture_output=True, text=True, timeout=900,
+                           env=env, cwd=out)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+        outs[mode] = out
+    a, b = _snapshot(outs["ref"]), _snapshot(outs["b200"])
+    assert sorted(a) == sorted(b)
+    diff = [k for k in a if a[k] != b[k]]
+    assert not diff, diff
+    assert _info_stats(outs["ref"]) == _info_stats(outs["b200"])
+    return a
+
+
+def test_launcher_prime_editing_scaffold(tmp_path):
+    """'Scaffold-incorporated' re-labelling (CRISPRessoCORE.py:789-796) through the sm_100a library: the reads and pegRNA of the
+    reference-generated fixture tests/golden/fanc_pe_scaffold.json.gz."""
+    from baseline import ref_shim
+    if not ref_shim.available():
+        pytest.skip("baseline/_ref (the pip-installed reference) did not travel")
+    rec, fq = _fastq(tmp_path, "fanc_pe_scaffold")
+    P = rec["params"]
+    argv = ["-r1", fq, "-a", rec["refs"]["Reference"]["sequence"], "--prime_editing_pegRNA_spacer_seq", "GGAATCCCTTCTGCAGCACC",
+            "--prime_editing_pegRNA_extension_seq", P["prime_editing_pegRNA_extension_seq"],
+            "--prime_editing_pegRNA_scaffold_seq", P["prime_editing_pegRNA_scaffold_seq"]]
+    snap = _run_both(argv, tmp_path, dict(os.environ, PYTHONPATH=ROOT))
+    assert any(k.startswith("Scaffold-incorporated.") for k in snap) and "Scaffold_insertion_sizes.txt" in snap
+
+
+def test_launcher_paired_end_merge_mode(tmp_path):
+    """--crispresso_merge (process_paired_fastq, :1245-1733) through crispresso2_b200.paired on the GPU; `fastp`, which the
+    reference runs first even in this mode, is the pass-through stand-in tests/fake_fastp.py put on PATH."""
+    from baseline import ref_shim
+    if not ref_shim.available():
+        pytest.skip("baseline/_ref (the pip-installed reference) did not travel")
+    import stat
+    import pe_case
+    amp = G.load("fanc_cas9")["refs"]["Reference"]["sequence"]
+    r1, r2 = str(tmp_path / "R1.fastq"), str(tmp_path / "R2.fastq")
+    pe_case.write_pairs(r1, r2, amp, n=600)
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    exe = bindir / "fastp"
+    exe.write_text("#!/bin/sh\nexec %s %s \"$@\"\n" % (sys.executable, os.path.join(HERE, "fake_fastp.py")))
+    exe.chmod(exe.stat().st_mode | stat.S_IXUSR | stat.S_IXGRP | stat.S_IXOTH)
+    env = dict(os.environ, PYTHONPATH=ROOT, PATH=str(bindir) + os.pathsep + os.environ.get("PATH", ""))
+    argv = ["-r1", r1, "-r2", r2, "-a", amp, "-g", "GGAATCCCTTCTGCAGCACC", "--crispresso_merge", "--fastq_output"]
+    snap = _run_both(argv, tmp_path, env)
+    assert len(snap) >= 10
