@@ -702,6 +702,10 @@ def main():
             import contextlib
             with contextlib.redirect_stdout(sys.stderr):      # filterFastqs prints its completion line, like the reference
                 line["api"]["ingest"] = ingest_leg(rd)
+            # paired-end merge mode: the reference's process_paired_fastq against paired.process_paired_fastq
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import paired_bench
+            line["api"]["paired_merge"] = paired_bench.run(5000, local)
         if not args.no_cpu_baseline and world == 1 and args.config == "single":
             line["cpu_baseline"] = cpu_baseline_block(w.refs["Reference"]["sequence"], w.refs["Reference"], w.buf.reshape(-1, 250))
         elif not args.no_cpu_baseline and world == 1:

@@ -9,6 +9,7 @@ d=json.load(open('gpurun_out/bench_$tag.json'))
 print('value %.1f M  e2e %.1f M  gate %s' % (d['value']/1e6, d['e2e']['value']/1e6, d['config']['parity_gate']))
 for k,v in d.get('api',{}).items():
     if 'stages_s' in v: print(' ',k, round(v['reads_per_s']), round(v['unique_per_s']), round(v['seconds'],3), v['stages_s'])
-    else:
+    elif v and all(isinstance(x, dict) for x in v.values()):
         for kk,vv in v.items(): print('   ',kk, {a:(round(b,3) if isinstance(b,float) else b) for a,b in vv.items()})
+    else: print(' ',k, {a:(round(b,3) if isinstance(b,float) else b) for a,b in (v or {}).items() if a != 'call'})
 PY

@@ -45,8 +45,10 @@ def write_pairs(p1, p2, amp, n, seed=5):
             f2.write("@p%d\n%s\n+\n%s\n" % (k, m2, q2))
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+def run(n, device=0):
+    """-> dict of the comparison (None when baseline/_ref is absent)"""
+    if not ref_shim.available():
+        return None
     CORE = ref_shim.load_core()
     from CRISPResso2 import CRISPRessoShared, CRISPResso2Align
     import logging
@@ -69,7 +71,7 @@ def main():
         t0 = time.perf_counter()
         st_ref, lost_ref = CORE.process_paired_fastq(r1, r2, c_ref, names, refs, args, [], d)
         t_ref = time.perf_counter() - t0
-        eng = core.get_engine(int(os.environ.get("LOCAL_RANK", "0")))
+        eng = core.get_engine(device)
         loc = os.path.join(CORE._ROOT, args.needleman_wunsch_aln_matrix_loc)
         m = core.read_matrix(loc)
         best = None
@@ -88,11 +90,16 @@ def main():
     same = (st_ref == st_gpu and list(c_ref) == list(c_gpu) and sorted(lost_ref) == sorted(lost_gpu)
             and all(c_ref[k]["count"] == c_gpu[k]["count"] and c_ref[k]["class_name"] == c_gpu[k]["class_name"]
                     and c_ref[k]["ref_aln_details"] == c_gpu[k]["ref_aln_details"] for k in c_ref))
-    print(json.dumps({"pairs": n, "identical_to_reference": bool(same), "reference_pairs_per_s": n / t_ref, "reference_seconds": t_ref,
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
+    return ({"pairs": n, "identical_to_reference": bool(same), "reference_pairs_per_s": n / t_ref, "reference_seconds": t_ref,
                       "b200_pairs_per_s": n / best, "b200_seconds": best, "speedup": t_ref / best,
                       "global_align_calls_served_from_the_batch": memo.hits, "single_gpu_calls": memo.misses,
-                      "distinct_sequences_in_the_batch": len(memo.index), "aligned_unique": st_gpu["N_COMPUTED_ALN"]}))
+                      "distinct_sequences_in_the_batch": len(memo.index), "aligned_unique": st_gpu["N_COMPUTED_ALN"],
+             "call": "CRISPRessoCORE.process_paired_fastq (unmodified reference, serial branch) vs crispresso2_b200.paired.process_paired_fastq "
+                     "on the same two FASTQ files of 150 bp mates; best of 2 for the GPU path"})
 
 
 if __name__ == "__main__":
-    main()
+    out = run(int(sys.argv[1]) if len(sys.argv) > 1 else 20000, int(os.environ.get("LOCAL_RANK", "0")))
+    print(json.dumps(out))
