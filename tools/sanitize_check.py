@@ -61,3 +61,10 @@ dd = fastq.dedup_bytes(data, device=0)
 hh = fastq.dedup_bytes(data)
 assert dd.n_reads == hh.n_reads and np.array_equal(dd.buf, hh.buf) and np.array_equal(dd.counts, hh.counts)
 print('gpu ingest', dd.n_reads, len(dd.counts))
+# three amplicons whose seed tests disagree for 8 % of the reads (per-reference both-strand alignment inside ALIGN, r02y)
+import bench
+w3 = bench.Workload("hdr", 2048, 0)
+eng.configure(w3.refs, w3.ref_names, m, -20, -2, 5, 2, w3.flags, 'ACGTN', 8)
+eng.counts_reset()
+res = eng.align_packed(w3.buf, w3.off, compact=True)
+print('hdr3', eng.path_counts(), eng.ring_counts(), int((res.recs['best_score_milli'] > 0).sum()))
