@@ -460,7 +460,7 @@ def process_fastq(fastq_filename, variantCache, ref_names, refs, args, files_to_
     # unique sequences feed the batch call directly
     import time
     t0 = time.perf_counter()
-    dd = fastq.dedup_file(fastq_filename, lib_path=engine.lib_path, device=fastq.gpu_ingest_device(fastq_filename, engine.device, engine.lib_path))
+    dd = fastq.dedup_for_process_fastq(fastq_filename, engine.device, engine.lib_path)
     last_timings.clear()
     last_timings["ingest_dedup"] = time.perf_counter() - t0
     last_timings["n_reads"], last_timings["n_unique"] = int(dd.n_reads), int(len(dd.counts))
@@ -674,7 +674,7 @@ def process_fastq_sharded(fastq_filename, variantCache, ref_names, refs, args, f
             import torch
             torch.cuda.set_device(dev)
         engine = get_engine(dev)
-    dd = fastq.dedup_file(fastq_filename, lib_path=engine.lib_path, device=fastq.gpu_ingest_device(fastq_filename, engine.device, engine.lib_path))
+    dd = fastq.dedup_for_process_fastq(fastq_filename, engine.device, engine.lib_path)
     if not variantCache:
         buf, off, counts = dd.buf, dd.off, dd.counts
         keys = None

@@ -90,6 +90,18 @@ def gpu_ingest_device(path, engine_device=None, lib_path=None):
     return dev if size <= (GPU_INGEST_MAX_GZ if str(path).endswith(".gz") else GPU_INGEST_MAX_PLAIN) else None
 
 
+def dedup_for_process_fastq(path, engine_device, lib_path=None):
+    """The front end process_fastq uses: the GPU one when gpu_ingest_device() picks it (by build and file size), else the host
+    threads.  A failure of the chosen one raises -- nothing is retried on the other; C2B_GPU_INGEST=0 / 1 forces either."""
+    dev = gpu_ingest_device(path, engine_device, lib_path)
+    try:
+        return dedup_file(path, lib_path=lib_path, device=dev)
+    except FastqError as ex:
+        if dev is not None:
+            raise FastqError("%s (GPU FASTQ front end; C2B_GPU_INGEST=0 selects the host threads)" % ex) from None
+        raise
+
+
 def dedup_file(path, n_threads=0, lib_path=None, device=None):
     """device=None: the host front end (c2b_fastq_dedup, n_threads workers); device=k: parse + de-duplicate on GPU k
     (c2b_fastq_dedup_gpu) -- same result object either way."""
