@@ -150,3 +150,21 @@ def test_blocked_gzip_large_parallel_inflate_and_fallbacks(lib, tmp_path):
 def test_buffer_entry(lib):
     got = fastq.dedup_bytes(CASES["clean"], lib_path=lib)
     assert got.uniques == ["ACGT", "TTTT"] and got.counts.tolist() == [2, 1] and got.n_reads == 3
+
+
+def test_front_end_selection(lib, tmp_path, monkeypatch):
+    """process_fastq's choice of FASTQ front end: the emulator build has no device front end (host threads); C2B_GPU_INGEST
+    forces either way; unreadable paths fall to the host front end, which reports them."""
+    p = tmp_path / "x.fastq"
+    p.write_bytes(CASES["clean"])
+    monkeypatch.delenv("C2B_GPU_INGEST", raising=False)
+    assert fastq.gpu_ingest_device(str(p), 3, lib) is None
+    monkeypatch.setenv("C2B_GPU_INGEST", "1")
+    assert fastq.gpu_ingest_device(str(p), 3, lib) == 3
+    monkeypatch.setenv("C2B_GPU_INGEST", "0")
+    assert fastq.gpu_ingest_device(str(p), 3, lib) is None
+    got = fastq.dedup_for_process_fastq(str(p), 0, lib)
+    assert got.uniques == ["ACGT", "TTTT"]
+    monkeypatch.setenv("C2B_GPU_INGEST", "1")                # forced onto a build without it: a loud failure naming the switch
+    with pytest.raises(fastq.FastqError, match="C2B_GPU_INGEST=0"):
+        fastq.dedup_for_process_fastq(str(p), 0, lib)
