@@ -10,7 +10,43 @@
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
+#include <pthread.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <unistd.h>
+
+/* str hashes of the keys, computed ahead by plain threads.  A dict insertion hashes its key; for a million 250-character keys
+ * that is ~0.25 GB through SipHash on the thread that holds the GIL (measured: about half of the variantCache fill).  CPython's
+ * str hash is _Py_HashBytes over the character data -- a pure function of the bytes and the process's hash secret -- so it is
+ * computed here from the packed reads without the GIL and stored in the new str objects' hash field (where unicode_hash itself
+ * caches it). */
+typedef struct { const char *b; const int64_t *o; Py_hash_t *h; Py_ssize_t lo, hi; } hash_job;
+static void *hash_worker(void *arg)
+{
+    hash_job *j = (hash_job *)arg;
+    for (Py_ssize_t k = j->lo; k < j->hi; k++) j->h[k] = _Py_HashBytes(j->b + j->o[k], (Py_ssize_t)(j->o[k + 1] - j->o[k]));
+    return NULL;
+}
+static Py_hash_t *hash_ahead(const char *b, const int64_t *o, Py_ssize_t n)
+{
+    if (n < 4096) return NULL;
+    Py_hash_t *h = (Py_hash_t *)malloc((size_t)n * sizeof(Py_hash_t));
+    if (!h) return NULL;
+    long nc = sysconf(_SC_NPROCESSORS_ONLN);
+    int T = nc > 32 ? 16 : nc > 3 ? (int)(nc / 2) : 1;
+    pthread_t th[16];
+    hash_job job[16];
+    int started = 0;
+    Py_BEGIN_ALLOW_THREADS
+    for (int t = 0; t < T; t++) {
+        job[t].b = b; job[t].o = o; job[t].h = h; job[t].lo = n * t / T; job[t].hi = n * (t + 1) / T;
+        if (t == T - 1 || pthread_create(&th[t], NULL, hash_worker, &job[t]) != 0) { hash_worker(&job[t]); th[t] = 0; }
+        else started |= 1 << t;
+    }
+    for (int t = 0; t < T; t++) if (started & (1 << t)) pthread_join(th[t], NULL);
+    Py_END_ALLOW_THREADS
+    return h;
+}
 
 /* make_keys(buf, off) -> list[str]: unique reads as the strings text-mode reading yields (UTF-8, surrogateescape) */
 static PyObject *make_keys(PyObject *self, PyObject *args)
@@ -21,9 +57,11 @@ static PyObject *make_keys(PyObject *self, PyObject *args)
     const int64_t *o = (const int64_t *)off.buf;
     const char *b = (const char *)buf.buf;
     PyObject *out = NULL;
+    Py_hash_t *hashes = NULL;
     if (n < 0 || (n >= 0 && o[n < 0 ? 0 : n] > buf.len)) { PyErr_SetString(PyExc_ValueError, "offsets exceed the buffer"); goto done; }
     out = PyList_New(n);
     if (!out) goto done;
+    hashes = hash_ahead(b, o, n);
     for (Py_ssize_t k = 0; k < n; k++) {
         const Py_ssize_t len = (Py_ssize_t)(o[k + 1] - o[k]);
         const unsigned char *p = (const unsigned char *)b + o[k];
@@ -32,12 +70,16 @@ static PyObject *make_keys(PyObject *self, PyObject *args)
         PyObject *s;
         if (hi < 128) {                                    /* ASCII (every read that reaches the engine): no decoder */
             s = PyUnicode_New(len, 127);
-            if (s) memcpy(PyUnicode_1BYTE_DATA(s), p, (size_t)len);
+            if (s) {
+                memcpy(PyUnicode_1BYTE_DATA(s), p, (size_t)len);
+                if (hashes) ((PyASCIIObject *)s)->hash = hashes[k];          /* the bytes ARE the character data */
+            }
         } else s = PyUnicode_DecodeUTF8((const char *)p, len, "surrogateescape");
         if (!s) { Py_CLEAR(out); goto done; }
         PyList_SET_ITEM(out, k, s);
     }
 done:
+    free(hashes);
     PyBuffer_Release(&buf); PyBuffer_Release(&off);
     return out;
 }
@@ -54,7 +96,7 @@ static PyObject *fill_cache(PyObject *self, PyObject *args)
     int value;
     if (!PyArg_ParseTuple(args, "O!O!y*y*Oi", &PyDict_Type, &cache, &PyList_Type, &keys, &sel, &counts, &cls, &value)) return NULL;
     const Py_ssize_t n = PyList_GET_SIZE(keys);
-    PyObject *res = NULL, *s_k = NULL;
+    PyObject *res = NULL, *s_k = NULL, *staged = NULL, *target = cache;
     Py_ssize_t done = 0;
     const int gc_was = PyGC_Disable();
     if (sel.len < n || counts.len < 4 * n) { PyErr_SetString(PyExc_ValueError, "sel / counts shorter than keys"); goto out; }
@@ -71,6 +113,15 @@ static PyObject *fill_cache(PyObject *self, PyObject *args)
         PyObject *empty = PyTuple_New(0);
         const int fast = PyType_Check(cls) && PyType_IsSubtype(tp, &PyDict_Type) && setk != NULL && empty != NULL;
         const uint8_t *m = (const uint8_t *)sel.buf;
+        /* an empty plain dict is filled through a right-sized temporary: no rehash of half a million entries every time the table
+         * grows, and dict.update() of an empty dict from such a table clones it wholesale (dict_merge's fast path) */
+        Py_ssize_t want = 0;
+        for (Py_ssize_t k = 0; k < n; k++) want += (m[k] == (uint8_t)value);
+        if (PyDict_CheckExact(cache) && PyDict_GET_SIZE(cache) == 0 && want >= 4096) {
+            staged = _PyDict_NewPresized(want);
+            if (!staged) { Py_XDECREF(empty); goto out; }
+            target = staged;
+        }
         for (Py_ssize_t k = 0; k < n; k++) {
             if (m[k] != (uint8_t)value) continue;
             PyObject *o = fast ? PyDict_Type.tp_new(tp, empty, NULL) : PyObject_CallNoArgs(cls);
@@ -78,16 +129,18 @@ static PyObject *fill_cache(PyObject *self, PyObject *args)
             PyObject *ik = PyLong_FromSsize_t(k);
             int bad = !ik || (fast ? setk(descr, o, ik) < 0 : PyObject_SetAttr(o, s_k, ik) < 0);
             if (!bad && fast && PyObject_GC_IsTracked(o)) PyObject_GC_UnTrack(o);
-            bad = bad || PyDict_SetItem(cache, PyList_GET_ITEM(keys, k), o) < 0;
+            bad = bad || PyDict_SetItem(target, PyList_GET_ITEM(keys, k), o) < 0;
             Py_XDECREF(ik); Py_DECREF(o);
             if (bad) { Py_XDECREF(empty); goto out; }
             done++;
         }
         Py_XDECREF(empty);
+        if (staged && PyDict_Update(cache, staged) < 0) goto out;
     }
     res = PyLong_FromSsize_t(done);
 out:
     Py_XDECREF(s_k);
+    Py_XDECREF(staged);
     if (gc_was) PyGC_Enable();
     PyBuffer_Release(&sel); PyBuffer_Release(&counts);
     return res;
