@@ -204,3 +204,39 @@ def test_assign_first_wins_over_expand_when_both_flags_are_set(emu, tmp_path):
         assert cache[s]["class_name"] == want["class_name"] and cache[s]["aln_ref_names"] == want["aln_ref_names"] == ["A"]
     vec, sca, classes, total = O.count_vectors(cache_o, refs, ["A", "B"], p, {})
     assert core.quantify(cache).class_counts() == classes
+
+
+def test_bulk_keys_carry_the_hashes_python_would_compute():
+    """lazy.make_keys pre-computes the str hashes of the variantCache keys on plain threads (csrc/c2b_pyext.c: hash_ahead) and
+    fill_cache stages an empty dict through a right-sized temporary: equal strings built any other way must hash alike, find the
+    entries, and the cache must keep first-seen order; a pre-seeded cache takes the plain path."""
+    from crispresso2_b200 import lazy
+    rng = np.random.default_rng(3)
+    n = 20000                                                # above hash_ahead's and the staging dict's thresholds
+    lens = rng.integers(0, 60, size=n)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    buf = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=int(off[-1])).astype(np.uint8)
+    keys = lazy.make_keys(buf, off)
+    raw = buf.tobytes()
+    for k in range(0, n, 37):
+        fresh = raw[off[k]:off[k + 1]].decode("ascii")
+        assert keys[k] == fresh and hash(keys[k]) == hash(fresh)
+
+    class LV(dict):
+        __slots__ = ("_k",)
+
+    uniq = {}
+    for k, s in enumerate(keys):
+        uniq.setdefault(s, k)
+    sel = np.zeros(n, dtype=np.uint8)
+    sel[list(uniq.values())] = 1
+    sel[::11] = 0
+    counts = np.ones(n, dtype=np.int32)
+    cache = {}
+    made = lazy.fill_cache(cache, keys, sel, counts, LV, 1)
+    want = [k for k in range(n) if sel[k]]
+    assert made == len(want) == len(cache) and [v._k for v in cache.values()] == want and list(cache) == [keys[k] for k in want]
+    assert all(raw[off[k]:off[k + 1]].decode("ascii") in cache for k in want[::53])
+    seeded = {"seed": 1}
+    assert lazy.fill_cache(seeded, keys, sel, counts, LV, 1) == len(want) and list(seeded)[0] == "seed" and len(seeded) == len(want) + 1
