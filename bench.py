@@ -675,7 +675,7 @@ def main():
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "c2b_align_batch_compact: pinned host buffers in; records, op streams, meta words and edit lists out "
                            "(aligned strings rebuilt on the host by c2b_expand_batch: checked equal to the device-resident leg's)",
-                    "pipeline": "chunks of 128 Ki reads through two staging sets: H2D | ALIGN, CLASSIFY, general kernel | D2H",
+                    "pipeline": "chunks of up to 256 Ki reads (a small first and last one) through two staging sets: H2D | ALIGN tier 1, tier 2, CLASSIFY, general kernel | D2H",
                     "with_strings": {"value": total_reads * 3 / (e2s_ms / 1000.0), "ms_per_step": e2s_ms / 3, "steps": 3,
                                      "d2h_bytes_per_step": d2h_strings, "api": "c2b_align_batch (two W-byte strings per slot)"}},
             "gpu_launches": int(launches),
