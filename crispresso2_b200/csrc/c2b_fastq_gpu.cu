@@ -50,11 +50,33 @@ __device__ __forceinline__ bool line_end_at(const uint8_t *t, int64_t n, int64_t
     return c == '\n' || (c == '\r' && !(p + 1 < n && t[p + 1] == '\n'));
 }
 
+// line ends among the 16 bytes at `base` (a multiple of 16; the text buffer is 256-byte aligned): one 16-byte load and the byte
+// after it instead of 17 byte loads -- bit k set = byte base + k ends a line
+__device__ __forceinline__ uint32_t ends16(const uint8_t *__restrict__ t, int64_t n, int64_t base)
+{
+    if (base >= n) return 0u;
+    uint32_t m = 0;
+    if (base + 16 <= n) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(t + base));
+        const uint32_t nxt = (base + 16 < n) ? (uint32_t)t[base + 16] : 0u;        // past the last byte: a final '\r' ends its line
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t c = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+            const uint32_t d = (k < 15) ? ((w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu) : nxt;
+            if (c == '\n' || (c == '\r' && d != '\n')) m |= 1u << k;
+        }
+        return m;
+    }
+    for (int k = 0; k < 16; k++) { const int64_t p = base + k; if (p < n && line_end_at(t, n, p)) m |= 1u << k; }
+    return m;
+}
+
 __global__ void __launch_bounds__(TILE_T) k_count_ends(const uint8_t *__restrict__ t, int64_t n, int32_t *__restrict__ tile_count)
 {
+    static_assert(TILE_B == 16, "ends16 handles 16 bytes per thread");
     const int64_t base = (int64_t)blockIdx.x * TILE + (int64_t)threadIdx.x * TILE_B;
-    int c = 0;
-    for (int k = 0; k < TILE_B; k++) { const int64_t p = base + k; if (p < n && line_end_at(t, n, p)) c++; }
+    const int c = __popc(ends16(t, n, base));
     typedef cub::BlockReduce<int, TILE_T> BR;
     __shared__ typename BR::TempStorage tmp;
     const int tot = BR(tmp).Sum(c);
@@ -65,14 +87,13 @@ __global__ void __launch_bounds__(TILE_T) k_write_ends(const uint8_t *__restrict
                                                       int64_t *__restrict__ ends)
 {
     const int64_t base = (int64_t)blockIdx.x * TILE + (int64_t)threadIdx.x * TILE_B;
-    int c = 0;
-    for (int k = 0; k < TILE_B; k++) { const int64_t p = base + k; if (p < n && line_end_at(t, n, p)) c++; }
+    uint32_t m = ends16(t, n, base);
     typedef cub::BlockScan<int, TILE_T> BS;
     __shared__ typename BS::TempStorage tmp;
     int pre;
-    BS(tmp).ExclusiveSum(c, pre);
+    BS(tmp).ExclusiveSum(__popc(m), pre);
     int64_t o = tile_off[blockIdx.x] + pre;
-    for (int k = 0; k < TILE_B; k++) { const int64_t p = base + k; if (p < n && line_end_at(t, n, p)) ends[o++] = p; }
+    while (m) { ends[o++] = base + (__ffs(m) - 1); m &= m - 1; }              // ascending positions
 }
 
 // record r = lines 4r .. 4r+3; its sequence is line 4r+1 (absent: empty), stripped
